@@ -1,0 +1,119 @@
+/* kaiju_b200.h -- C ABI of the B200-native Kaiju classification path (libkaijub200.so).
+ *
+ * Drop-in boundary: the reference has no FFI; its seam is the C++ class ConsumerThread
+ * (src/ConsumerThread.hpp:64-121): N threads each pop ReadItem* from a queue, classify it against the
+ * shared read-only Config (FMI + suffix array + nodes map) and append "C\tname\ttaxid\n" lines.  This
+ * library replaces everything between "ReadItems popped" and "taxon id known" for a whole batch:
+ *
+ *   reference call / type                                    replaced by
+ *   -------------------------------------------------------  -------------------------------------
+ *   readFMI + Config::init        (util.cpp:265-276, Config.cpp:19-28)   kj_index_view (views into the loader's
+ *                                                                         buffers) or kj_fmi_load() (our loader)
+ *   parseNodesDmp                 (util.cpp:79-99)                        kj_taxonomy_view or kj_nodes_load()
+ *   new ConsumerThread(queue,config) x N (kaiju.cpp:250-257)              kj_create()
+ *   ConsumerThread::doWork        (ConsumerThread.cpp:630-749)            kj_classify() / kj_classify_device()
+ *   delete ConsumerThread / Config                                         kj_destroy()
+ *
+ * All entry points return 0 on success or a negative kj_status; the library never calls exit().
+ * Plain pointers and sizes only; the caller owns every buffer it passes in.
+ */
+#ifndef KAIJU_B200_H
+#define KAIJU_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    KJ_OK = 0,
+    KJ_ERR_ARG = -1,            /* null/invalid argument */
+    KJ_ERR_IO = -2,             /* file could not be read / is not a .fmi */
+    KJ_ERR_CUDA = -3,           /* CUDA runtime failure (kj_last_error() has the text) */
+    KJ_ERR_NO_DEVICE = -4,      /* no usable GPU: there is NO CPU fallback */
+    KJ_ERR_UNSUPPORTED = -5,    /* alphabet > 24 letters, read longer than KJ_MAX_READ_LEN, -e > 8 ... */
+    KJ_ERR_OVERFLOW = -6,       /* an internal per-read work queue overflowed (results of the batch are invalid) */
+    KJ_ERR_NOMEM = -7
+} kj_status;
+
+#define KJ_MAX_READ_LEN 381     /* bases per mate (SEG trim bookkeeping is sized for fragments <= 127 aa) */
+
+/* Mode / Config fields consumed by the path (src/Config.hpp:31-66, set by kaiju.cpp:74-202) */
+typedef struct {
+    int32_t mode;                 /* 0 = MEM (-a mem), 1 = GREEDY (-a greedy)            */
+    uint32_t min_fragment_length; /* -m, default 11                                      */
+    uint32_t mismatches;          /* -e, default 3  (Greedy)                             */
+    uint32_t min_score;           /* -s, default 65 (Greedy)                             */
+    uint32_t seed_length;         /* -l, default 7  (Greedy)                             */
+    int32_t use_evalue;           /* Greedy: 1 unless disabled; MEM: must be 0           */
+    double min_evalue;            /* -E, default 0.01                                    */
+    int32_t seg;                  /* -x (1, default) / -X (0)                            */
+    int32_t input_is_protein;     /* -p: not supported yet (KJ_ERR_UNSUPPORTED)          */
+} kj_params;
+
+/* Host views straight out of a .fmi loader (the reference's BWT/FMI/suffixArray structs:
+ * bwt/bwt.h:13-23, bwt/compactfmi.h:10-19, bwt/suffixArray.h:10-33).  Nothing is retained after kj_create(). */
+typedef struct {
+    int32_t alen;                 /* FMI.alen (alphabet incl. terminator, 21 for proteins)          */
+    const char *alphabet;         /* BWT.alphabet ("*ACDEFGHIKLMNPQRSTVWY")                         */
+    int64_t bwtlen;               /* FMI.bwtlen                                                      */
+    const uint8_t *bwt;           /* FMI.bwt : byte codes (letter + distance), length bwtlen         */
+    const int32_t *startLcode;    /* FMI.startLcode[alen+1] : code range of each letter              */
+    int64_t db_len;               /* BWT.len  (E-value uses len - nseq, Config.cpp:20)               */
+    int32_t nseq;                 /* BWT.nseq                                                        */
+    int64_t ncheck;               /* suffixArray.ncheck                                              */
+    int32_t chpt_exp, nbytes, pbits; /* suffixArray.chpt_exp / nbytes / pbits                        */
+    const uint8_t *sa;            /* suffixArray.sa : ncheck * nbytes big-endian packed (seq,pos)     */
+    const uint64_t *seq_taxon;    /* [nseq] taxon id parsed from suffixArray.ids[i] with the rule of
+                                     ConsumerThread.cpp:812-832 (UINT64_MAX = "bad number", skipped) */
+} kj_index_view;
+
+typedef struct {
+    uint64_t n;                   /* number of (node,parent) pairs, i.e. nodes.dmp lines             */
+    const uint64_t *node;         /* child taxon id                                                   */
+    const uint64_t *parent;       /* parent taxon id (root: parent == node)                           */
+} kj_taxonomy_view;
+
+typedef struct kj_fmi kj_fmi;           /* an owned, parsed .fmi file                */
+typedef struct kj_nodes kj_nodes;       /* an owned, parsed nodes.dmp                */
+typedef struct kj_ctx kj_ctx;           /* one GPU context: index + taxonomy in HBM  */
+
+/* --- loaders (our own re-implementation of the on-disk formats) --- */
+int kj_fmi_load(const char *path, kj_fmi **out);
+void kj_fmi_view(const kj_fmi *f, kj_index_view *view);
+void kj_fmi_free(kj_fmi *f);
+int kj_nodes_load(const char *path, kj_nodes **out);
+void kj_nodes_view(const kj_nodes *t, kj_taxonomy_view *view);
+void kj_nodes_free(kj_nodes *t);
+
+/* --- context --- */
+/* Transcodes the index into the device layout, uploads it and the taxonomy to HBM of `device`. */
+int kj_create(kj_ctx **out, int device, const kj_params *params, const kj_index_view *index, const kj_taxonomy_view *taxonomy);
+/* Change the run parameters of an existing context (index stays resident). */
+int kj_set_params(kj_ctx *ctx, const kj_params *params);
+void kj_destroy(kj_ctx *ctx);
+
+/* --- classification --- */
+/* Host buffers.  seq1 = concatenated bases of mate 1, off1[n_reads+1] byte offsets; seq2/off2 = mate 2 or NULL
+ * for single-end input.  taxon_out[n_reads]: NCBI taxon id, 0 = unclassified (the "U" line).  best_out (optional):
+ * match length (MEM) or score (Greedy) -- column 4 of the reference's -v output.  Blocking; H2D/D2H inside. */
+int kj_classify(kj_ctx *ctx, const char *seq1, const uint64_t *off1, const char *seq2, const uint64_t *off2,
+                uint64_t n_reads, uint64_t *taxon_out, uint32_t *best_out);
+/* Device buffers (same layout, all pointers in the context's device memory), enqueued on `cuda_stream`
+ * (a cudaStream_t, NULL = default stream); returns after the launch, results are ready when the stream is.
+ * max_len1/max_len2: upper bounds of the mate lengths in the batch (0 = let the library compute them on the device). */
+int kj_classify_device(kj_ctx *ctx, const char *d_seq1, const uint64_t *d_off1, const char *d_seq2, const uint64_t *d_off2,
+                       uint64_t n_reads, uint32_t max_len1, uint32_t max_len2, uint64_t *d_taxon_out, uint32_t *d_best_out,
+                       void *cuda_stream);
+
+/* --- introspection --- */
+const char *kj_last_error(void);                  /* thread-local text of the last failure          */
+uint64_t kj_kernel_launches(const kj_ctx *ctx);   /* number of kernels this context has launched    */
+uint64_t kj_index_bytes(const kj_ctx *ctx);       /* bytes of HBM held by the index                 */
+double kj_last_kernel_ms(const kj_ctx *ctx);      /* device time of the last classify kernel (CUDA events) */
+int kj_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,165 @@
+"""kaiju_b200 -- B200-native Kaiju classification path (host-side Python mirror of include/kaiju_b200.h).
+
+The product is the C-ABI shared library ``kaiju_b200/libkaijub200.so`` (CUDA, sm_100a).  This module only
+binds it with ctypes; there is no Python or CPU implementation of the path, and importing the binding on a
+machine without the built library raises immediately.
+
+Reference seam mirrored here: ``ConsumerThread`` + ``Config`` (src/ConsumerThread.hpp:64-121,
+src/Config.hpp:31-66) -- construct once with the index/taxonomy/parameters, then classify batches of reads.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkaijub200.so")
+
+MEM, GREEDY = 0, 1
+
+
+class KjParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("min_fragment_length", C.c_uint32), ("mismatches", C.c_uint32),
+                ("min_score", C.c_uint32), ("seed_length", C.c_uint32), ("use_evalue", C.c_int32),
+                ("min_evalue", C.c_double), ("seg", C.c_int32), ("input_is_protein", C.c_int32)]
+
+
+class KjIndexView(C.Structure):
+    _fields_ = [("alen", C.c_int32), ("alphabet", C.c_char_p), ("bwtlen", C.c_int64), ("bwt", C.c_void_p),
+                ("startLcode", C.c_void_p), ("db_len", C.c_int64), ("nseq", C.c_int32), ("ncheck", C.c_int64),
+                ("chpt_exp", C.c_int32), ("nbytes", C.c_int32), ("pbits", C.c_int32), ("sa", C.c_void_p),
+                ("seq_taxon", C.c_void_p)]
+
+
+class KjTaxonomyView(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("node", C.c_void_p), ("parent", C.c_void_p)]
+
+
+class KaijuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libkaijub200.so; fails loudly if the CUDA library has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KaijuError("kaiju_b200: %s is missing -- build it with `make -C kaiju_b200/csrc` "
+                             "(or python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.kj_last_error.restype = C.c_char_p
+        L.kj_fmi_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.kj_fmi_view.argtypes = [C.c_void_p, C.POINTER(KjIndexView)]
+        L.kj_fmi_free.argtypes = [C.c_void_p]
+        L.kj_nodes_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.kj_nodes_view.argtypes = [C.c_void_p, C.POINTER(KjTaxonomyView)]
+        L.kj_nodes_free.argtypes = [C.c_void_p]
+        L.kj_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(KjParams), C.POINTER(KjIndexView), C.POINTER(KjTaxonomyView)]
+        L.kj_set_params.argtypes = [C.c_void_p, C.POINTER(KjParams)]
+        L.kj_destroy.argtypes = [C.c_void_p]
+        L.kj_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.kj_classify_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kj_kernel_launches.restype = C.c_uint64; L.kj_kernel_launches.argtypes = [C.c_void_p]
+        L.kj_index_bytes.restype = C.c_uint64; L.kj_index_bytes.argtypes = [C.c_void_p]
+        L.kj_last_kernel_ms.restype = C.c_double; L.kj_last_kernel_ms.argtypes = [C.c_void_p]
+        L.kj_check_errors.argtypes = [C.c_void_p]
+        L.kj_launch_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.kj_version.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise KaijuError("kaiju_b200 error %d: %s" % (rc, lib().kj_last_error().decode()))
+
+
+def make_params(mode="mem", m=11, e=3, s=65, seed=7, E=0.01, seg=True, use_evalue=None):
+    """Config fields as the kaiju CLI sets them (kaiju.cpp:74-202): -a -m -e -s -l -E -x/-X."""
+    greedy = mode in ("greedy", GREEDY, 1)
+    if use_evalue is None:
+        use_evalue = greedy
+    return KjParams(mode=1 if greedy else 0, min_fragment_length=m, mismatches=e, min_score=s, seed_length=seed,
+                    use_evalue=1 if (use_evalue and greedy) else 0, min_evalue=E, seg=1 if seg else 0, input_is_protein=0)
+
+
+class Classifier:
+    """One GPU context: the .fmi index and nodes.dmp taxonomy resident in HBM + run parameters."""
+
+    def __init__(self, fmi_path, nodes_path, device=0, params=None, **kw):
+        L = lib()
+        self._ctx = C.c_void_p()
+        fmi = C.c_void_p(); nodes = C.c_void_p()
+        _check(L.kj_fmi_load(fmi_path.encode(), C.byref(fmi)))
+        try:
+            _check(L.kj_nodes_load(nodes_path.encode(), C.byref(nodes)))
+            try:
+                iv = KjIndexView(); tv = KjTaxonomyView()
+                L.kj_fmi_view(fmi, C.byref(iv)); L.kj_nodes_view(nodes, C.byref(tv))
+                self.params = params if params is not None else make_params(**kw)
+                self.bwtlen = int(iv.bwtlen); self.nseq = int(iv.nseq)
+                _check(L.kj_create(C.byref(self._ctx), device, C.byref(self.params), C.byref(iv), C.byref(tv)))
+            finally:
+                L.kj_nodes_free(nodes)
+        finally:
+            L.kj_fmi_free(fmi)
+        self.device = device
+
+    def set_params(self, params=None, **kw):
+        self.params = params if params is not None else make_params(**kw)
+        _check(lib().kj_set_params(self._ctx, C.byref(self.params)))
+
+    def close(self):
+        if self._ctx:
+            lib().kj_destroy(self._ctx); self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host buffers (numpy): H2D + kernel + D2H inside, like handing ReadItems to the consumer threads
+    def classify(self, seq1, off1, seq2=None, off2=None, want_best=True):
+        n = len(off1) - 1
+        seq1 = np.ascontiguousarray(seq1, dtype=np.uint8); off1 = np.ascontiguousarray(off1, dtype=np.uint64)
+        p2 = o2 = None
+        if seq2 is not None:
+            seq2 = np.ascontiguousarray(seq2, dtype=np.uint8); off2 = np.ascontiguousarray(off2, dtype=np.uint64)
+            p2, o2 = seq2.ctypes.data, off2.ctypes.data
+        tax = np.zeros(n, dtype=np.uint64); best = np.zeros(n, dtype=np.uint32) if want_best else None
+        _check(lib().kj_classify(self._ctx, seq1.ctypes.data, off1.ctypes.data, p2, o2, n, tax.ctypes.data,
+                                 best.ctypes.data if want_best else None))
+        return (tax, best) if want_best else tax
+
+    def classify_ptrs(self, seq1_ptr, off1_ptr, seq2_ptr, off2_ptr, n, tax_ptr, best_ptr):
+        """Host pointers (e.g. pinned torch tensors' data_ptr())."""
+        _check(lib().kj_classify(self._ctx, seq1_ptr, off1_ptr, seq2_ptr, off2_ptr, n, tax_ptr, best_ptr))
+
+    # ---- device buffers (raw device pointers, e.g. torch tensors' data_ptr()); asynchronous on `stream`
+    def classify_device(self, d_seq1, d_off1, d_seq2, d_off2, n, d_tax, d_best=None, max_len1=0, max_len2=0, stream=None):
+        _check(lib().kj_classify_device(self._ctx, d_seq1, d_off1, d_seq2, d_off2, n, max_len1, max_len2, d_tax, d_best, stream))
+
+    def check_errors(self):
+        _check(lib().kj_check_errors(self._ctx))
+
+    @property
+    def kernel_launches(self):
+        return int(lib().kj_kernel_launches(self._ctx))
+
+    @property
+    def index_bytes(self):
+        return int(lib().kj_index_bytes(self._ctx))
+
+    @property
+    def last_kernel_ms(self):
+        return float(lib().kj_last_kernel_ms(self._ctx))
+
+    @property
+    def launch_geometry(self):
+        g = C.c_int(); b = C.c_int(); s = C.c_int()
+        lib().kj_launch_geometry(self._ctx, C.byref(g), C.byref(b), C.byref(s))
+        return g.value, b.value, s.value

@@ -1,0 +1,520 @@
+// kj_core.h -- the per-read classification path as warp-cooperative device code (one warp = one read item).
+//
+// Replaces, behind the C ABI of include/kaiju_b200.h, the reference's
+//   ConsumerThread::doWork / getAllFragmentsBits / getNextFragment / classify_length / classify_greedyblosum /
+//   addAllMismatchVariantsAtPosSI / eval_match_scores / ids_from_SI   (src/ConsumerThread.cpp:190-845)
+//   greedyExact / maxMatches / maxMatches_withStart / UpdateSI / InitialSI / get_suffix (src/bwt/bwt.c:105-380)
+//   FMindex / FMindexCurrent (src/bwt/compactfmi.c:267-336), SeqBufferSeg (blast_seg.c:2278-2332),
+//   lca_from_ids (src/util.cpp:194-263).
+// It is not a translation: lanes run independent backward-search chains (one per match end position j),
+// the fragment priority queue is a shared-memory key array popped by warp arg-max, SEG's window entropies
+// are integer class look-ups and its trim search is lane-parallel, ids are resolved 32 SA rows at a time.
+// The sequential semantics that decide ties (SURVEY.md 8a "exactness notes") are replayed exactly.
+//
+// Conventions: every warp collective is called from warp-uniform control flow with the full mask;
+// variables commented "uniform" hold the same value in all 32 lanes.
+#pragma once
+#include "kj_warp.h"
+#include "kj_layout.h"
+
+// ---------------------------------------------------------------------------------------------
+// per-warp shared-memory carve-up
+// ---------------------------------------------------------------------------------------------
+#define KJ_SEG_CAP(max_frag) ((max_frag) / 4u + 8u)
+struct KjKept { uint64_t lo; uint32_t len; uint32_t aux; };     // one suffix interval (an SI of bwt.h:25-34)
+
+struct KjSmemLayout {
+    uint32_t qkey_off, qpay_off, kept_off, res_off, ids_off, aa_off, aa_stride, frag_off, hflag_off,
+             segcnt_off, seghist_off, segs_off, total;
+};
+static KJ_HD uint32_t kj_align(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
+    KjSmemLayout L; uint32_t o = 0;
+    L.qkey_off = o; o += 8u * p.item_cap;
+    L.kept_off = o; o += 16u * p.kept_cap_smem;
+    L.res_off = o; o += 16u * kj_align(p.max_frag + 1, 2);           // per-j chain results (greedy)
+    L.qpay_off = o; o += 4u * kj_align(p.item_cap, 2);
+    L.ids_off = o; o += 4u * 24u;
+    L.segs_off = o; o += 8u * KJ_SEG_CAP(p.max_frag);                     // {int begin,end}
+    L.aa_stride = kj_align(p.max_len + 4, 8);
+    L.aa_off = o; o += 4u * L.aa_stride;
+    L.frag_off = o; o += kj_align(p.max_frag + 8, 8);
+    L.hflag_off = o; o += kj_align(p.max_frag + 8, 8);
+    L.segcnt_off = o; o += 20u * 32u;
+    L.seghist_off = o; o += kj_align((p.max_frag + 2) * 32u, 8);
+    L.total = kj_align(o, 16);
+    return L;
+}
+
+struct KjWarpCtx {
+    Warp w;
+    const KjDevIndex* ix;
+    const KjRunParams* rp;
+    const KjTables* tb;
+    uint8_t* smem;                      // this warp's carve-up
+    KjSmemLayout L;
+    KjKept* spill;                      // global scratch of this warp: rp->scratch_entries entries
+    void* gscratch;                     // global scratch of this warp for the greedy variant queue
+    uint32_t* err;                      // global error flags: 1 item-queue overflow, 2 spill overflow, 4 greedy queue overflow
+};
+static KJ_DEV void kj_flag_error(KjWarpCtx& cx, uint32_t bit) {
+#if defined(KJ_EMU)
+    *cx.err |= bit;
+#else
+    atomicOr(cx.err, bit);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// FM index primitives
+// ---------------------------------------------------------------------------------------------
+static KJ_DEV KjRankBlock kj_ld_block(const KjRankBlock* p) {
+#if defined(KJ_EMU)
+    return *p;
+#else
+    KjRankBlock b;   // one 256-bit read-only load = exactly one 32-byte sector
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.cnt), "=l"(b.w0), "=l"(b.w1), "=l"(b.w2) : "l"(p));
+    return b;
+#endif
+}
+// FMindex(f, c, k) = C[c] + rank_c(BWT[0..k))        (compactfmi.c:267-307)
+static KJ_DEV uint64_t kj_rank_in_block(const KjRankBlock& b, uint32_t r) {
+    uint32_t wi = r >> 6, bit = r & 63u;
+    uint64_t ww = wi == 0 ? b.w0 : (wi == 1 ? b.w1 : b.w2);
+    uint64_t n = b.cnt + (uint64_t)kj_popcll(ww & ((1ull << bit) - 1ull));
+    if (wi > 0) n += (uint64_t)kj_popcll(b.w0);
+    if (wi > 1) n += (uint64_t)kj_popcll(b.w1);
+    return n;
+}
+static KJ_DEV uint64_t kj_rank(const KjDevIndex& ix, uint32_t c, uint64_t k) {
+    uint64_t b = k / KJ_RANK_BLOCK; uint32_t r = (uint32_t)(k - b * KJ_RANK_BLOCK);
+    return kj_rank_in_block(kj_ld_block(ix.rank + (uint64_t)c * ix.nb + b), r);
+}
+// UpdateSI (bwt.c:160-173); the record is shared when both interval ends fall in one block
+static KJ_DEV bool kj_update_si(const KjDevIndex& ix, uint32_t c, uint64_t& lo, uint64_t& hi) {
+    uint64_t b0 = lo / KJ_RANK_BLOCK, b1 = hi / KJ_RANK_BLOCK;
+    const KjRankBlock* base = ix.rank + (uint64_t)c * ix.nb;
+    KjRankBlock B0 = kj_ld_block(base + b0);
+    uint64_t nlo = kj_rank_in_block(B0, (uint32_t)(lo - b0 * KJ_RANK_BLOCK)), nhi;
+    if (b1 == b0) nhi = kj_rank_in_block(B0, (uint32_t)(hi - b1 * KJ_RANK_BLOCK));
+    else { KjRankBlock B1 = kj_ld_block(base + b1); nhi = kj_rank_in_block(B1, (uint32_t)(hi - b1 * KJ_RANK_BLOCK)); }
+    if (nlo >= nhi) return false;
+    lo = nlo; hi = nhi; return true;
+}
+static KJ_DEV int kj_hibit64(uint64_t x) { uint32_t h = (uint32_t)(x >> 32); return h ? 63 - kj_clz(h) : 31 - kj_clz((uint32_t)x); }
+static KJ_DEV uint32_t kj_letter(const KjDevIndex& ix, uint64_t k) {
+    uint64_t wd = k / KJ_LETTERS_PER_WORD; uint32_t s = (uint32_t)(k - wd * KJ_LETTERS_PER_WORD) * 5u;
+    return (uint32_t)(ix.letters[wd] >> s) & 31u;
+}
+// get_suffix (bwt.c:105-121) reduced to the taxon of the sequence the suffix lies in
+static KJ_DEV uint32_t kj_sa_taxon(const KjDevIndex& ix, uint64_t k) {
+    uint32_t c = 1;
+    while (c != 0 && (k & ix.sa_check)) { c = kj_letter(ix, k); k = kj_rank(ix, c, k); }
+    if (c != 0) return ix.sa_tax[(uint64_t)((int64_t)(k >> ix.sa_exp) - ix.sa_bias)];
+    return ix.seq_tax[k];
+}
+// one backward-search chain ending at j (inner loop of bwt.c:267-275 / 355-363): returns the match start
+static KJ_DEV int kj_chain(const KjDevIndex& ix, const uint8_t* frag, int j, uint64_t& lo, uint64_t& hi) {
+    uint32_t c = frag[j]; lo = ix.C[c]; hi = ix.C[c + 1];          // InitialSI (bwt.c:146-152)
+    int i = j;
+    while (i > 0) { if (!kj_update_si(ix, frag[i - 1], lo, hi)) break; i--; }
+    return i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fragment queue (std::multimap<unsigned,Fragment*,greater>, ConsumerThread.hpp:83): highest key first,
+// FIFO among equal keys.  key64 = val<<32 | (0xffffff-order)<<8 | 1  (0 = free slot); payload =
+// arr(2) segchecked(1) start(15) len(14).  Originals get order = arr<<16 | scan position (their
+// insertion order, ConsumerThread.cpp:196-268); SEG pieces and greedy variants take a running counter.
+// ---------------------------------------------------------------------------------------------
+#define KJ_ORDER_LATE (1u << 20)
+struct KjQueue { uint64_t* key; uint32_t* pay; uint32_t cap, n, late; };    // n, late: uniform
+static KJ_DEV uint64_t kj_qkey(uint32_t val, uint32_t order) { return ((uint64_t)val << 32) | ((uint64_t)(0xffffffu - order) << 8) | 1ull; }
+static KJ_DEV uint32_t kj_qpay(uint32_t arr, bool segchecked, uint32_t start, uint32_t len) { return (arr << 30) | ((segchecked ? 1u : 0u) << 29) | (start << 14) | len; }
+
+// emit from several lanes at once (emit predicate per lane)
+static KJ_DEV void kj_queue_emit(KjWarpCtx& cx, KjQueue& q, bool emit, uint32_t val, uint32_t order, uint32_t pay) {
+    uint32_t mask = cx.w.ballot(emit);
+    if (!mask) return;
+    uint32_t cnt = (uint32_t)kj_popc(mask);
+    if (q.n + cnt > q.cap) { if (cx.w.lane == 0) kj_flag_error(cx, 1u); return; }
+    if (emit) { uint32_t s = q.n + (uint32_t)kj_popc(mask & lanemask_lt(cx.w.lane)); q.key[s] = kj_qkey(val, order); q.pay[s] = pay; }
+    q.n += cnt;
+}
+// pop the top entry if its sort value is >= min_val (getNextFragment's gate, ConsumerThread.cpp:276-283)
+static KJ_DEV bool kj_queue_pop(KjWarpCtx& cx, KjQueue& q, uint32_t min_val, uint32_t& val, uint32_t& pay) {
+    cx.w.sync();
+    uint64_t best = 0; uint32_t slot = 0;
+    for (uint32_t s = (uint32_t)cx.w.lane; s < q.n; s += 32) { uint64_t k = q.key[s]; if (k > best) { best = k; slot = s; } }
+    uint64_t g = warp_max_u64(cx.w, best);
+    if (g == 0) return false;
+    val = (uint32_t)(g >> 32);
+    if (val < min_val) return false;
+    uint32_t own = cx.w.ballot(best == g);
+    int src = kj_ffs(own) - 1;
+    uint32_t p = 0;
+    if (cx.w.lane == src) { p = q.pay[slot]; q.key[slot] = 0; }
+    pay = cx.w.shfl(p, src);
+    cx.w.sync();
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// six-frame translation + stop splitting of one mate  (getAllFragmentsBits, ConsumerThread.cpp:190-270)
+// arrays: aa[2*mate+0][count] forward codon starting at base `count`; aa[2*mate+1][r] reverse-strand codon
+// in the reference's scan order (r = n-3-count), so every frame is a stride-3 walk in array order.
+// ---------------------------------------------------------------------------------------------
+static KJ_DEV uint32_t kj_nuc(uint8_t ch) {          // nuc2int (ConsumerThread.cpp:32-37): A0 C1 G2 T/U3, else invalid
+    uint32_t u = ch & 0xDFu;
+    return u == 'A' ? 0u : u == 'C' ? 1u : u == 'G' ? 2u : (u == 'T' || u == 'U') ? 3u : 4u;
+}
+static KJ_DEV void kj_translate_mate(KjWarpCtx& cx, KjQueue& q, int mate, const uint8_t* seq, int n, bool greedy) {
+    const Warp& w = cx.w; const KjTables& tb = *cx.tb;
+    uint8_t* aaF = cx.smem + cx.L.aa_off + (uint32_t)(2 * mate) * cx.L.aa_stride;
+    uint8_t* aaR = aaF + cx.L.aa_stride;
+    const int na = n - 2;
+    for (int count = w.lane; count < na; count += 32) {
+        uint32_t c0 = kj_nuc(seq[count]), c1 = kj_nuc(seq[count + 1]), c2 = kj_nuc(seq[count + 2]);
+        bool ok = (c0 | c1 | c2) < 4u;
+        aaF[count] = ok ? tb.codon_aa[c0 << 4 | c1 << 2 | c2] : (uint8_t)0;
+        aaR[na - 1 - count] = ok ? tb.codon_aa[(3u - c2) << 4 | (3u - c1) << 2 | (3u - c0)] : (uint8_t)0;
+    }
+    w.sync();
+    // lanes 0..5 = (strand, residue class of the array index); all lanes walk the same trip count
+    const uint32_t m = cx.rp->m;
+    const int strand = w.lane / 3, r = w.lane % 3;
+    const bool mine = w.lane < 6;
+    const uint32_t arr = (uint32_t)(2 * mate + strand);
+    const uint8_t* A = strand ? aaR : aaF;
+    uint32_t run_start = 0, run_len = 0, run_score = 0;
+    for (int idx0 = 0; idx0 < na; idx0 += 3) {
+        int idx = idx0 + r; bool valid = mine && idx < na;
+        uint32_t a = valid ? A[idx] : 1u;
+        bool stop = valid && a == 0;
+        bool emit = stop && run_len >= m && (!greedy || run_score >= cx.rp->min_score);
+        kj_queue_emit(cx, q, emit, greedy ? run_score : run_len, (arr << 16) | (uint32_t)idx, kj_qpay(arr, false, run_start, run_len));
+        if (valid) {
+            if (stop) { run_len = 0; run_score = 0; }
+            else { if (run_len == 0) run_start = (uint32_t)idx; run_len++; run_score += (uint32_t)tb.b62[a][a]; }
+        }
+    }
+    // leftovers in frame order 0,1,2 where frame = count % 3 in FORWARD coordinates (ConsumerThread.cpp:219-232, 256-268)
+    int frame = strand ? (((n - 3 - r) % 3) + 3) % 3 : r;
+    bool emit = mine && run_len >= m && (!greedy || run_score >= cx.rp->min_score);
+    kj_queue_emit(cx, q, emit, greedy ? run_score : run_len, (arr << 16) | (40000u + (uint32_t)frame), kj_qpay(arr, false, run_start, run_len));
+}
+
+// copy the characters of item (arr,start,len) into the contiguous fragment buffer
+static KJ_DEV void kj_load_frag(KjWarpCtx& cx, uint32_t arr, uint32_t start, uint32_t len) {
+    const uint8_t* A = cx.smem + cx.L.aa_off + arr * cx.L.aa_stride;
+    uint8_t* frag = cx.smem + cx.L.frag_off;
+    for (uint32_t t = (uint32_t)cx.w.lane; t < len; t += 32) frag[t] = A[start + 3u * t];
+    cx.w.sync();
+}
+
+// ---------------------------------------------------------------------------------------------
+// SEG low-complexity filter (SeqBufferSeg with SegParametersNewAa + overlaps, blast_seg.c:2027-2332)
+// on frag[0..n).  Output: ascending [begin,end] regions in the segs array; returns their number.
+// ---------------------------------------------------------------------------------------------
+struct KjSeg { int begin, end; };
+#define KJ_SEG_DOWNSET 5      // (window+1)/2 - 1
+#define KJ_SEG_UPSET 7        // window - downset
+#define KJ_SEG_MAXTRIM 50
+
+// entropy class of every 12-window: bit0 = H <= locut, bit1 = H <= hicut   (s_SeqEntropy/s_Entropy, 1596-1798)
+static KJ_DEV void kj_seg_flags(KjWarpCtx& cx, int n) {
+    const uint8_t* frag = cx.smem + cx.L.frag_off; uint8_t* hf = cx.smem + cx.L.hflag_off; const KjTables& tb = *cx.tb;
+    for (int p = cx.w.lane; p + KJ_SEG_WINDOW <= n; p += 32) {
+        uint64_t c_lo = 0, c_hi = 0;                         // 4-bit counters for letters 1..16 / 17..20 (max count 12)
+        for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; if (a < 16u) c_lo += 1ull << (4u * a); else c_hi += 1ull << (4u * (a - 16u)); }
+        int32_t x = 0;
+        for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; uint32_t c = a < 16u ? (uint32_t)(c_lo >> (4u * a)) & 15u : (uint32_t)(c_hi >> (4u * (a - 16u))) & 15u; x += tb.seg_logfix[c]; }
+        hf[p] = (uint8_t)((x <= tb.seg_locut_fix ? 1 : 0) | (x <= tb.seg_hicut_fix ? 2 : 0));
+    }
+    cx.w.sync();
+}
+
+// s_Trim (blast_seg.c:1971-2015): the sub-window of s[0..n2) with minimal s_GetProb; first in
+// (len descending, start ascending) order wins ties.  One lane per window length, sliding start.
+static KJ_DEV void kj_seg_trim(KjWarpCtx& cx, const uint8_t* s, int n2, int& leftend, int& rightend) {
+    const Warp& w = cx.w;
+    uint8_t* cnt = cx.smem + cx.L.segcnt_off;       // [20][32]
+    uint8_t* hist = cx.smem + cx.L.seghist_off;     // [n2+1][32] number of letters having count v
+    const double* lnf = cx.ix->lnfact;
+    int minlen = 1; if (n2 - KJ_SEG_MAXTRIM > minlen) minlen = n2 - KJ_SEG_MAXTRIM;
+    const int nlens = n2 - minlen;
+    double g_prob = 1.0; int g_lend = 0, g_rend = n2 - 1;            // uniform
+    for (int pass = 0; pass * 32 < nlens; pass++) {
+        const int len = n2 - (pass * 32 + w.lane);
+        const bool act = (pass * 32 + w.lane) < nlens;
+        for (int a = 0; a < 20; a++) cnt[a * 32 + w.lane] = 0;
+        for (int v = 0; v <= n2; v++) hist[v * 32 + w.lane] = 0;
+        uint64_t m0 = 0, m1 = 0; int nz = 0;                          // bit v set <=> hist[v] > 0 (v < 128)
+        double my_prob = 1.0; int my_i = 0;
+        if (act) {
+            #define KJ_SEG_ADD(letter) { uint32_t a_ = (letter) - 1u; uint32_t c_ = cnt[a_ * 32 + w.lane]; \
+                if (c_ > 0) { uint8_t h_ = --hist[c_ * 32 + w.lane]; if (h_ == 0) { if (c_ < 64) m0 &= ~(1ull << c_); else m1 &= ~(1ull << (c_ - 64)); } } else nz++; \
+                cnt[a_ * 32 + w.lane] = (uint8_t)(c_ + 1); hist[(c_ + 1) * 32 + w.lane]++; if (c_ + 1 < 64) m0 |= 1ull << (c_ + 1); else m1 |= 1ull << (c_ + 1 - 64); }
+            #define KJ_SEG_DEL(letter) { uint32_t a_ = (letter) - 1u; uint32_t c_ = cnt[a_ * 32 + w.lane]; \
+                { uint8_t h_ = --hist[c_ * 32 + w.lane]; if (h_ == 0) { if (c_ < 64) m0 &= ~(1ull << c_); else m1 &= ~(1ull << (c_ - 64)); } } \
+                cnt[a_ * 32 + w.lane] = (uint8_t)(c_ - 1); if (c_ > 1) { hist[(c_ - 1) * 32 + w.lane]++; if (c_ - 1 < 64) m0 |= 1ull << (c_ - 1); else m1 |= 1ull << (c_ - 1 - 64); } else nz--; }
+            for (int t = 0; t < len; t++) KJ_SEG_ADD(s[t]);
+            for (int i = 0; i + len <= n2; i++) {
+                // s_GetProb (1941-1962) = s_LnAss (1890-1930) + s_LnPerm (1865-1879) - len*ln20, same operation order
+                double ans1 = lnf[20], ans2 = lnf[len];
+                uint64_t a0 = m0, a1 = m1;
+                while (a0 | a1) {
+                    int v;                                           // highest set bit of the 128-bit mask = next larger count
+                    if (a1) { v = 64 + kj_hibit64(a1); a1 &= ~(1ull << (v - 64)); }
+                    else { v = kj_hibit64(a0); a0 &= ~(1ull << v); }
+                    int cls = hist[v * 32 + w.lane];
+                    ans1 = kj_dsub(ans1, lnf[cls]);
+                    for (int rep = 0; rep < cls; rep++) ans2 = kj_dsub(ans2, lnf[v]);
+                }
+                if (nz < 20) ans1 = kj_dsub(ans1, lnf[20 - nz]);
+                double prob = kj_dsub(kj_dadd(ans1, ans2), kj_dmul((double)len, 2.9957322735539909));
+                if (prob < my_prob) { my_prob = prob; my_i = i; }
+                if (i + len < n2) { KJ_SEG_DEL(s[i]); KJ_SEG_ADD(s[i + len]); }
+            }
+            #undef KJ_SEG_ADD
+            #undef KJ_SEG_DEL
+        }
+        w.sync();
+        // arg-min over lanes, lowest lane (longest window) wins ties
+        double mn = my_prob;
+        for (int mm = 16; mm > 0; mm >>= 1) { double o = w.shfl_d(mn, w.lane ^ mm); mn = o < mn ? o : mn; }
+        if (mn < g_prob) {
+            int src = kj_ffs(w.ballot(my_prob == mn)) - 1;
+            int wi = w.shfl(my_i, src); int wlen = n2 - (pass * 32 + src);
+            g_prob = mn; g_lend = wi; g_rend = wlen + wi - 1;
+        }
+    }
+    leftend += g_lend; rightend -= (n2 - g_rend - 1);
+}
+
+// s_SegSeq (blast_seg.c:2027-2113) on frag[s0 .. s0+n).  LEVEL 0 collects regions; LEVEL 1 is the
+// "trigger window fell into the left trim" recursion, of which the caller keeps only the last region
+// created (the list head, 2093-2097), so deeper recursion levels can never influence the result.
+template <int LEVEL>
+static KJ_DEV int kj_seg_level(KjWarpCtx& cx, int s0, int n, KjSeg* segs, int nsegs) {
+    const uint8_t* frag = cx.smem + cx.L.frag_off; const uint8_t* hf = cx.smem + cx.L.hflag_off;
+    if (KJ_SEG_WINDOW > n) return nsegs;
+    const int first = KJ_SEG_DOWNSET, last = n - KJ_SEG_UPSET; int lowlim = first;
+    for (int i = first; i <= last; i++) {
+        if (hf[s0 + i - KJ_SEG_DOWNSET] & 1) {
+            int j = i; while (j >= lowlim && (hf[s0 + j - KJ_SEG_DOWNSET] & 2)) j--; const int loi = j + 1;         // s_FindLow
+            j = i; while (j <= last && (hf[s0 + j - KJ_SEG_DOWNSET] & 2)) j++; const int hii = j - 1;               // s_FindHigh
+            int leftend = loi - KJ_SEG_DOWNSET, rightend = hii + KJ_SEG_UPSET - 1;
+            kj_seg_trim(cx, frag + s0 + leftend, rightend - leftend + 1, leftend, rightend);
+            if (LEVEL == 0 && i + KJ_SEG_UPSET - 1 < leftend) {
+                const int lend = loi - KJ_SEG_DOWNSET, rend = leftend - 1;
+                KjSeg tmp; tmp.begin = -1; tmp.end = -1;
+                int got = kj_seg_level<1>(cx, s0 + lend, rend - lend + 1, &tmp, 0);
+                if (got > 0 && nsegs + 2 < (int)KJ_SEG_CAP(cx.rp->max_frag)) { if (cx.w.lane == 0) segs[nsegs] = tmp; nsegs++; }
+            }
+            if (LEVEL == 0) {
+                if (nsegs + 2 < (int)KJ_SEG_CAP(cx.rp->max_frag)) { if (cx.w.lane == 0) { segs[nsegs].begin = leftend + s0; segs[nsegs].end = rightend + s0; } nsegs++; }
+                else if (cx.w.lane == 0) kj_flag_error(cx, 8u);
+            }
+            else { segs[0].begin = leftend + s0; segs[0].end = rightend + s0; nsegs = 1; }      // LEVEL 1: register struct, keep the last
+            i = hii < rightend + KJ_SEG_DOWNSET ? hii : rightend + KJ_SEG_DOWNSET;
+            lowlim = i + 1;
+        }
+    }
+    return nsegs;
+}
+// full SEG on frag[0..n): flags, regions, s_MergeSegs (2122-2152); returns number of regions (ascending)
+static KJ_DEV int kj_seg(KjWarpCtx& cx, int n) {
+    KjSeg* segs = (KjSeg*)(cx.smem + cx.L.segs_off);
+    if (n < KJ_SEG_WINDOW) return 0;
+    kj_seg_flags(cx, n);
+    int ns = kj_seg_level<0>(cx, 0, n, segs, 0);
+    cx.w.sync();
+    if (ns > 1) {
+        // creation order == ascending; the reference walks the reversed list from its head
+        if (cx.w.lane == 0) {
+            int cur = ns - 1, cnt = ns;
+            // emulate on an index-linked view: nxt[i] = i-1
+            // merged entries are marked begin = -1
+            int nx = cur - 1;
+            while (nx >= 0) {
+                if (segs[cur].begin - segs[nx].end - 1 < 0) {
+                    if (segs[cur].end < segs[nx].end) segs[cur].end = segs[nx].end;
+                    if (segs[cur].begin > segs[nx].begin) segs[cur].begin = segs[nx].begin;
+                    segs[nx].begin = -1; cnt--;
+                } else cur = nx;
+                nx--;
+            }
+            // compact
+            int o = 0; for (int t = 0; t < ns; t++) if (segs[t].begin >= 0) segs[o++] = segs[t];
+            segs[ns].begin = o;                                  // pass the count through shared memory
+        }
+        cx.w.sync();
+        ns = segs[ns].begin;
+        cx.w.sync();
+    }
+    return ns;
+}
+
+// ---------------------------------------------------------------------------------------------
+// winners ("kept" suffix intervals): first kept_cap_smem in shared memory, the rest in global scratch
+// ---------------------------------------------------------------------------------------------
+static KJ_DEV KjKept* kj_kept_ptr(KjWarpCtx& cx, uint32_t idx) {
+    if (idx < cx.rp->kept_cap_smem) return (KjKept*)(cx.smem + cx.L.kept_off) + idx;
+    uint32_t s = idx - cx.rp->kept_cap_smem;
+    if (s >= cx.rp->scratch_entries) { kj_flag_error(cx, 2u); s = cx.rp->scratch_entries - 1; }
+    return cx.spill + s;
+}
+
+// taxon ids of the kept intervals in order, k ascending, stop once the set exceeds 20 entries
+// (ids_from_SI, ConsumerThread.cpp:799-835); then LCA (util.cpp:194-263).  Returns compact taxon or KJ_TAX_BAD for "none".
+static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
+    const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix;
+    uint32_t* ids = (uint32_t*)(cx.smem + cx.L.ids_off);
+    uint32_t nids = 0;                                                    // uniform
+    for (uint32_t e = 0; e < nkept && nids <= 20; e++) {
+        KjKept kk = *kj_kept_ptr(cx, e);
+        for (uint32_t base = 0; base < kk.len && nids <= 20; base += 32) {
+            uint32_t t = base + (uint32_t)w.lane; bool act = t < kk.len;
+            uint32_t tax = act ? kj_sa_taxon(ix, kk.lo + t) : KJ_TAX_BAD;
+            uint32_t nact = kk.len - base < 32u ? kk.len - base : 32u;
+            for (uint32_t s = 0; s < nact && nids <= 20; s++) {
+                uint32_t id = w.shfl(tax, (int)s);
+                if (id == KJ_TAX_BAD) continue;
+                bool dup = (uint32_t)w.lane < nids && ids[w.lane] == id;
+                if (!w.any(dup)) { if (w.lane == 0) ids[nids] = id; nids++; w.sync(); }
+            }
+        }
+    }
+    if (nids == 0) return KJ_TAX_BAD;
+    w.sync();
+    if (nids == 1) return ids[0];                                         // returned without a nodes.dmp check (ConsumerThread.cpp:625)
+    // lca_from_ids: drop ids absent from nodes.dmp (depth 0), lift to the shallowest depth, climb in lockstep
+    uint32_t id = (uint32_t)w.lane < nids ? ids[w.lane] : KJ_TAX_BAD;
+    uint32_t depth = id != KJ_TAX_BAD ? ix.tax_depth[id] : 0u;
+    bool present = depth > 0;
+    uint32_t pm = w.ballot(present);
+    if (!pm) return KJ_TAX_BAD;
+    uint32_t shallow = warp_min_u32(w, present ? depth : 0xffffffffu);
+    if (present) for (uint32_t d = depth; d > shallow; d--) id = ix.tax_parent[id];
+    int first = kj_ffs(pm) - 1;
+    for (uint32_t guard = 0; guard <= shallow + 1; guard++) {
+        uint32_t f = w.shfl(id, first);
+        bool diff = present && id != f;
+        if (!w.any(diff)) return f;
+        if (present) id = ix.tax_parent[id];
+    }
+    return KJ_TAX_BAD;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MEM mode  (classify_length, ConsumerThread.cpp:543-628, with greedyExact, bwt.c:347-380)
+// ---------------------------------------------------------------------------------------------
+#define KJ_ROUND_SMALL 4        // chains launched first per fragment (a full-length hit ends the fragment at once)
+#define KJ_LONG_MATCH 14        // a round that saw a match this long keeps the rounds small
+
+// SEG gate of getNextFragment (ConsumerThread.cpp:285-339): returns true if the item was split (pieces pushed)
+static KJ_DEV bool kj_seg_gate(KjWarpCtx& cx, KjQueue& q, uint32_t arr, uint32_t start, uint32_t len, bool greedy) {
+    int ns = kj_seg(cx, (int)len);
+    if (ns == 0) return false;
+    const KjSeg* segs = (const KjSeg*)(cx.smem + cx.L.segs_off);
+    const uint8_t* frag = cx.smem + cx.L.frag_off; const KjTables& tb = *cx.tb;
+    uint32_t st = 0;
+    for (int s = 0; s <= ns; s++) {
+        int plen = (s < ns ? segs[s].begin : (int)len) - (int)st;         // non-masked piece [st, st+plen)
+        if (plen > (int)cx.rp->m) {                                        // strict '>' for pieces (298, 312)
+            uint32_t val = (uint32_t)plen; bool ok = true;
+            if (greedy) { uint32_t sc = 0; for (int t = 0; t < plen; t++) { uint32_t a = frag[st + t]; sc += (uint32_t)tb.b62[a][a]; } val = sc; ok = sc >= cx.rp->min_score; }
+            kj_queue_emit(cx, q, cx.w.lane == 0 && ok, val, KJ_ORDER_LATE + q.late, kj_qpay(arr, true, start + 3u * st, (uint32_t)plen));
+            if (ok) q.late++;
+        }
+        if (s < ns) st = (uint32_t)segs[s].end + 1u;
+    }
+    return true;
+}
+
+static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best_out) {
+    const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix; const KjRunParams& rp = *cx.rp;
+    const uint8_t* frag = cx.smem + cx.L.frag_off;
+    uint32_t longest = 0, nkept = 0;                                      // uniform
+    uint32_t val, pay;
+    while (kj_queue_pop(cx, q, longest, val, pay)) {
+        const uint32_t arr = pay >> 30, start = (pay >> 14) & 0x7fffu, len = pay & 0x3fffu; const bool segchecked = (pay >> 29) & 1u;
+        kj_load_frag(cx, arr, start, len);
+        if (rp.seg && !segchecked && kj_seg_gate(cx, q, arr, start, len, false)) continue;
+        // greedyExact(f, seq, len, max(m,longest), -1): chains for j = len-1 .. L-1, L growing
+        uint32_t L = rp.m > longest ? rp.m : longest;
+        uint32_t item_best = 0, item_cnt = 0;                             // uniform
+        int jhi = (int)len - 1; bool small_round = true;
+        while (jhi >= (int)L - 1) {
+            int nj = jhi - ((int)L - 1) + 1; const int G = small_round ? KJ_ROUND_SMALL : 32; if (nj > G) nj = G;
+            const int j = jhi - w.lane; const bool act = w.lane < nj;
+            uint64_t lo = 0, hi = 0; int i = 0;
+            if (act) i = kj_chain(ix, frag, j, lo, hi);
+            w.sync();
+            uint32_t l = act ? (uint32_t)(j - i + 1) : 0u;
+            // `if (i<=1) break` (bwt.c:376): lanes below the first lane that reached i<=1 were never run by the reference
+            uint32_t brk = w.ballot(act && i <= 1);
+            const int cut = brk ? kj_ffs(brk) - 1 : 31;
+            const bool valid = act && w.lane <= cut;
+            uint32_t lmax = warp_max_u32(w, valid ? l : 0u);
+            if (lmax >= L) {
+                if (lmax > item_best) { item_best = lmax; item_cnt = 0; L = lmax; }
+                uint32_t wm = w.ballot(valid && l == item_best);
+                if (valid && l == item_best) { KjKept* k = kj_kept_ptr(cx, nkept + item_cnt + (uint32_t)kj_popc(wm & lanemask_lt(w.lane))); k->lo = lo; k->len = (uint32_t)(hi - lo); k->aux = 0; }
+                item_cnt += (uint32_t)kj_popc(wm);
+            }
+            small_round = lmax >= KJ_LONG_MATCH;
+            if (brk) break;
+            jhi -= nj;
+        }
+        w.sync();
+        if (item_cnt > 0) {
+            // winners were appended j-descending; the reference's chain is newest (smallest j) first
+            for (uint32_t t = (uint32_t)w.lane; t < item_cnt / 2; t += 32) {
+                KjKept* a = kj_kept_ptr(cx, nkept + t); KjKept* b = kj_kept_ptr(cx, nkept + item_cnt - 1 - t);
+                KjKept x = *a; *a = *b; *b = x;
+            }
+            w.sync();
+            if (item_best > longest) {                                    // replace (ConsumerThread.cpp:574-585)
+                if (nkept > 0) {
+                    for (uint32_t t0 = 0; t0 < item_cnt; t0 += 32) {      // move down, chunk by chunk (src index > dst index)
+                        uint32_t t = t0 + (uint32_t)w.lane; KjKept x; x.lo = 0; x.len = 0; x.aux = 0;
+                        if (t < item_cnt) x = *kj_kept_ptr(cx, nkept + t);
+                        w.sync();
+                        if (t < item_cnt) *kj_kept_ptr(cx, t) = x;
+                        w.sync();
+                    }
+                }
+                nkept = item_cnt; longest = item_best;
+            } else if (item_best == longest) nkept += item_cnt;           // append (586-591)
+        }
+    }
+    best_out = 0;
+    if (nkept == 0) return KJ_TAX_BAD;
+    w.sync();
+    uint32_t t = kj_ids_and_lca(cx, nkept);
+    if (t != KJ_TAX_BAD) best_out = longest;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ConsumerThread::doWork for one item (ConsumerThread.cpp:630-749): gates, translation, mode dispatch.
+// Returns the compact taxon (KJ_TAX_BAD = unclassified).
+// ---------------------------------------------------------------------------------------------
+static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int n2, uint32_t& best_out);
+
+static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1, const uint8_t* s2, int n2, bool paired, uint32_t& best_out) {
+    const KjRunParams& rp = *cx.rp;
+    best_out = 0;
+    const int m3 = (int)rp.m * 3;
+    // short-read gate (648-653): SE len1 < 3m; PE only if BOTH mates are short
+    if ((!paired && n1 < m3) || (paired && n1 < m3 && n2 < m3)) return KJ_TAX_BAD;
+    KjQueue q; q.key = (uint64_t*)(cx.smem + cx.L.qkey_off); q.pay = (uint32_t*)(cx.smem + cx.L.qpay_off);
+    q.cap = rp.item_cap; q.n = 0; q.late = 0;
+    const bool greedy = rp.mode == 1;
+    if (n1 >= m3) kj_translate_mate(cx, q, 0, s1, n1, greedy);            // a short mate is skipped individually (699, 705)
+    if (paired && n2 >= m3) kj_translate_mate(cx, q, 1, s2, n2, greedy);
+    if (!greedy) return kj_classify_mem(cx, q, best_out);
+    return kj_classify_greedy(cx, q, n1, paired ? n2 : 0, best_out);
+}

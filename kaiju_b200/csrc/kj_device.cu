@@ -1,0 +1,311 @@
+// kj_device.cu -- CUDA side of libkaijub200.so: index upload, the persistent classification kernel and the
+// C ABI entry points kj_create / kj_classify / kj_classify_device / kj_destroy (include/kaiju_b200.h).
+//
+// Execution model: one warp classifies one read item at a time (kj_core.h); a persistent grid of
+// (#SM x resident CTAs) pulls read indices from a global counter, so fast ("U" after the length gate)
+// and slow (long matches, SEG trims) reads balance without a host-side scheduler -- the GPU replacement of
+// the reference's ProducerConsumerQueue + N ConsumerThreads (kaiju.cpp:250-257, 288-396).
+// There is no CPU fallback: without a GPU kj_create() fails with KJ_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include "kj_core.h"
+#include "kj_core_greedy.h"
+#include "kj_host.h"
+
+#define KJ_WARPS_PER_CTA 8
+#define KJ_CHUNK_READS (1u << 20)
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { kj_err() = std::string(#call) + ": " + cudaGetErrorString(e_); return KJ_ERR_CUDA; } } while (0)
+
+struct KjCtaShared { KjDevIndex ix; KjTables tb; };
+
+__global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32)
+kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ KjRunParams rp,
+                   const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
+                   const uint8_t* __restrict__ seq2, const uint64_t* __restrict__ off2,
+                   uint64_t base1, uint64_t base2, uint64_t n_reads,
+                   uint64_t* __restrict__ taxon_out, uint32_t* __restrict__ best_out,
+                   unsigned long long* __restrict__ counter, KjKept* __restrict__ spill, uint8_t* __restrict__ gscratch,
+                   uint32_t gscratch_bytes, uint32_t* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    KjCtaShared* sh = (KjCtaShared*)smem_raw;
+    {   // stage the index descriptor (C[] etc.) and the small tables once per CTA
+        const uint32_t* src = (const uint32_t*)g_ix; uint32_t* dst = (uint32_t*)&sh->ix;
+        for (uint32_t i = threadIdx.x; i < sizeof(KjDevIndex) / 4; i += blockDim.x) dst[i] = src[i];
+        const uint32_t* ts = (const uint32_t*)g_ix->tables; uint32_t* td = (uint32_t*)&sh->tb;
+        for (uint32_t i = threadIdx.x; i < sizeof(KjTables) / 4; i += blockDim.x) td[i] = ts[i];
+    }
+    __syncthreads();
+    const int warp_in_cta = threadIdx.x >> 5;
+    KjWarpCtx cx;
+    cx.w.lane = threadIdx.x & 31;
+    cx.ix = &sh->ix; cx.rp = &rp; cx.tb = &sh->tb;
+    cx.L = kj_smem_layout(rp);
+    cx.smem = smem_raw + kj_align((uint32_t)sizeof(KjCtaShared), 16) + (uint32_t)warp_in_cta * cx.L.total;
+    const uint64_t gwarp = (uint64_t)blockIdx.x * KJ_WARPS_PER_CTA + (uint64_t)warp_in_cta;
+    cx.spill = spill + gwarp * rp.scratch_entries;
+    cx.gscratch = gscratch + gwarp * gscratch_bytes;
+    cx.err = err;
+    const bool paired = seq2 != nullptr;
+    for (;;) {
+        unsigned long long r = 0;
+        if (cx.w.lane == 0) r = atomicAdd(counter, 1ull);
+        r = cx.w.shfl64(r, 0);
+        if (r >= n_reads) break;
+        const uint64_t a0 = off1[r] - base1, a1 = off1[r + 1] - base1;
+        uint64_t b0 = 0, b1 = 0; if (paired) { b0 = off2[r] - base2; b1 = off2[r + 1] - base2; }
+        uint32_t best = 0;
+        uint32_t t = kj_classify_item(cx, seq1 + a0, (int)(a1 - a0), paired ? seq2 + b0 : nullptr, (int)(b1 - b0), paired, best);
+        if (cx.w.lane == 0) {
+            uint64_t id = t == KJ_TAX_BAD ? 0ull : sh->ix.tax_id[t];
+            taxon_out[r] = id;
+            if (best_out) best_out[r] = id ? best : 0u;
+        }
+        cx.w.sync();
+    }
+}
+
+__global__ void kj_maxlen_kernel(const uint64_t* __restrict__ off, uint64_t n, unsigned int* __restrict__ out) {
+    unsigned int m = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) { uint64_t l = off[i + 1] - off[i]; m = max(m, (unsigned int)min(l, (uint64_t)0xffffffffu)); }
+    for (int s = 16; s > 0; s >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct kj_ctx {
+    int device = 0; kj_params params{}; int sm_count = 0;
+    KjHostIndex H;                 // big arrays are released after upload; small ones stay
+    KjDevIndex dix{};              // host copy of the descriptor (device pointers inside)
+    KjDevIndex* d_ix = nullptr; KjTables* d_tables = nullptr;
+    void* d_rank = nullptr; void* d_letters = nullptr; void* d_sa_tax = nullptr; void* d_seq_tax = nullptr;
+    void* d_tax_parent = nullptr; void* d_tax_depth = nullptr; void* d_tax_id = nullptr; void* d_lnfact = nullptr;
+    uint64_t index_bytes = 0;
+    // run state
+    unsigned long long* d_counter = nullptr; uint32_t* d_err = nullptr; unsigned int* d_maxlen = nullptr;
+    KjKept* d_spill = nullptr; size_t spill_bytes = 0; uint8_t* d_gscratch = nullptr; size_t gscratch_bytes_total = 0;
+    uint16_t* d_evtab = nullptr; uint32_t ev1 = 0, ev2 = 0; std::vector<uint16_t> evtab;
+    cudaStream_t stream[2] = {nullptr, nullptr}; cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // staging for kj_classify (host buffers)
+    uint8_t* d_seq[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; size_t d_seq_cap[2][2] = {{0, 0}, {0, 0}};
+    uint64_t* d_off[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; uint64_t* d_tax[2] = {nullptr, nullptr}; uint32_t* d_best[2] = {nullptr, nullptr};
+    size_t d_reads_cap = 0;
+    uint64_t launches = 0; double last_kernel_ms = 0.0;
+    int grid = 0; size_t smem_bytes = 0;
+};
+
+template <class T> static int upload(const std::vector<T>& v, void** d, uint64_t& total) {
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    CK(cudaMalloc(d, bytes));
+    if (!v.empty()) CK(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    total += bytes; return KJ_OK;
+}
+
+static int configure_launch(kj_ctx* c, const KjRunParams& rp, size_t& smem, int& grid) {
+    KjSmemLayout L = kj_smem_layout(rp);
+    smem = kj_align((uint32_t)sizeof(KjCtaShared), 16) + (size_t)KJ_WARPS_PER_CTA * L.total;
+    if (smem > 227 * 1024) { kj_err() = "per-CTA shared memory exceeds 227 KB (reads too long / -m too small)"; return KJ_ERR_UNSUPPORTED; }
+    if (smem == c->smem_bytes && c->grid > 0) { grid = c->grid; return KJ_OK; }
+    CK(cudaFuncSetAttribute(kj_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel, KJ_WARPS_PER_CTA * 32, smem));
+    if (per_sm < 1) { kj_err() = "kernel does not fit on an SM"; return KJ_ERR_UNSUPPORTED; }
+    grid = c->sm_count * per_sm;             // persistent grid: a whole number of CTAs per SM
+    return KJ_OK;
+}
+
+static int ensure_scratch(kj_ctx* c, const KjRunParams& rp, int grid) {
+    size_t warps = (size_t)grid * KJ_WARPS_PER_CTA * 2;   // two pipeline slots may be in flight
+    size_t need = warps * rp.scratch_entries * sizeof(KjKept);
+    if (need > c->spill_bytes) { if (c->d_spill) cudaFree(c->d_spill); c->d_spill = nullptr; CK(cudaMalloc((void**)&c->d_spill, need)); c->spill_bytes = need; }
+    size_t gneed = warps * (size_t)kj_greedy_scratch_bytes(rp);
+    if (gneed > c->gscratch_bytes_total) { if (c->d_gscratch) cudaFree(c->d_gscratch); c->d_gscratch = nullptr; CK(cudaMalloc((void**)&c->d_gscratch, gneed)); c->gscratch_bytes_total = gneed; }
+    return KJ_OK;
+}
+
+static int ensure_evalue_table(kj_ctx* c, KjRunParams& rp, uint32_t max1, uint32_t max2, cudaStream_t st) {
+    if (!(c->params.mode == 1 && c->params.use_evalue)) { rp.evalue_min_score = nullptr; rp.ev_stride = 0; return KJ_OK; }
+    if (!c->d_evtab || max1 > c->ev1 || max2 > c->ev2) {
+        uint32_t n1 = std::max(max1, c->ev1), n2 = std::max(max2, c->ev2);
+        kj_build_evalue_table(c->params, c->H.db_length, n1, n2, c->evtab);
+        if (c->d_evtab) cudaFree(c->d_evtab); c->d_evtab = nullptr;
+        CK(cudaMalloc((void**)&c->d_evtab, c->evtab.size() * sizeof(uint16_t)));
+        CK(cudaMemcpyAsync(c->d_evtab, c->evtab.data(), c->evtab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        c->ev1 = n1; c->ev2 = n2;
+    }
+    rp.evalue_min_score = c->d_evtab; rp.ev_stride = c->ev2 + 1;
+    return KJ_OK;
+}
+
+extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, const kj_index_view* index, const kj_taxonomy_view* taxonomy) {
+    if (!out || !params || !index || !taxonomy) { kj_err() = "kj_create: null argument"; return KJ_ERR_ARG; }
+    int rc = kj_check_params(*params); if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { kj_err() = "no CUDA device available (this library has no CPU fallback)"; return KJ_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) { kj_err() = "device ordinal out of range"; return KJ_ERR_ARG; }
+    CK(cudaSetDevice(device));
+    kj_ctx* c = new kj_ctx(); c->device = device; c->params = *params;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); c->sm_count = prop.multiProcessorCount;
+    rc = kj_build_host_index(*index, *taxonomy, c->H); if (rc) { delete c; return rc; }
+    KjHostIndex& H = c->H; uint64_t tot = 0;
+    if ((rc = upload(H.rank, &c->d_rank, tot)) || (rc = upload(H.letters, &c->d_letters, tot)) || (rc = upload(H.sa_tax, &c->d_sa_tax, tot)) ||
+        (rc = upload(H.seq_tax, &c->d_seq_tax, tot)) || (rc = upload(H.tax_parent, &c->d_tax_parent, tot)) || (rc = upload(H.tax_depth, &c->d_tax_depth, tot)) ||
+        (rc = upload(H.tax_id, &c->d_tax_id, tot)) || (rc = upload(H.lnfact, &c->d_lnfact, tot))) { kj_destroy(c); return rc; }
+    CK(cudaMalloc((void**)&c->d_tables, sizeof(KjTables))); CK(cudaMemcpy(c->d_tables, &H.tables, sizeof(KjTables), cudaMemcpyHostToDevice));
+    KjDevIndex& D = c->dix; memset(&D, 0, sizeof D);
+    D.rank = (const KjRankBlock*)c->d_rank; D.nb = H.nb; D.letters = (const uint64_t*)c->d_letters; D.bwtlen = H.bwtlen; D.alen = H.alen;
+    for (int a = 0; a <= H.alen; a++) D.C[a] = H.C[a];
+    D.sa_tax = (const uint32_t*)c->d_sa_tax; D.seq_tax = (const uint32_t*)c->d_seq_tax; D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
+    D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
+    D.tax_parent = (const uint32_t*)c->d_tax_parent; D.tax_depth = (const uint32_t*)c->d_tax_depth; D.tax_id = (const uint64_t*)c->d_tax_id; D.n_tax = (uint32_t)H.tax_id.size();
+    D.lnfact = (const double*)c->d_lnfact; D.n_lnfact = (int)H.lnfact.size(); D.kmer = nullptr; D.kmer_k = 0; D.tables = c->d_tables;
+    CK(cudaMalloc((void**)&c->d_ix, sizeof(KjDevIndex))); CK(cudaMemcpy(c->d_ix, &D, sizeof(KjDevIndex), cudaMemcpyHostToDevice));
+    c->index_bytes = tot;
+    // host copies of the big arrays are no longer needed
+    std::vector<KjRankBlock>().swap(H.rank); std::vector<uint64_t>().swap(H.letters); std::vector<uint32_t>().swap(H.sa_tax);
+    CK(cudaMalloc((void**)&c->d_counter, 2 * sizeof(unsigned long long))); CK(cudaMalloc((void**)&c->d_err, sizeof(uint32_t))); CK(cudaMalloc((void**)&c->d_maxlen, 2 * sizeof(unsigned int)));
+    CK(cudaMemset(c->d_err, 0, sizeof(uint32_t)));
+    for (int s = 0; s < 2; s++) CK(cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev_a)); CK(cudaEventCreate(&c->ev_b));
+    *out = c; return KJ_OK;
+}
+
+extern "C" int kj_set_params(kj_ctx* c, const kj_params* p) {
+    if (!c || !p) { kj_err() = "kj_set_params: null argument"; return KJ_ERR_ARG; }
+    int rc = kj_check_params(*p); if (rc) return rc;
+    c->params = *p; c->ev1 = c->ev2 = 0; if (c->d_evtab) { cudaFree(c->d_evtab); c->d_evtab = nullptr; }
+    return KJ_OK;
+}
+
+extern "C" void kj_destroy(kj_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    void* ptrs[] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_tax_parent, c->d_tax_depth, c->d_tax_id, c->d_lnfact, c->d_tables, c->d_ix,
+                    c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evtab, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
+                    c->d_seq[0][0], c->d_seq[0][1], c->d_seq[1][0], c->d_seq[1][1], c->d_off[0][0], c->d_off[0][1], c->d_off[1][0], c->d_off[1][1]};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int s = 0; s < 2; s++) if (c->stream[s]) cudaStreamDestroy(c->stream[s]);
+    if (c->ev_a) cudaEventDestroy(c->ev_a); if (c->ev_b) cudaEventDestroy(c->ev_b);
+    delete c;
+}
+
+// one launch over reads [0,n) whose sequences/offsets are resident on the device
+static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_off1, const uint8_t* d_seq2, const uint64_t* d_off2, uint64_t base1, uint64_t base2,
+                  uint64_t n, uint32_t max1, uint32_t max2, uint64_t* d_tax, uint32_t* d_best, cudaStream_t st, bool time_it) {
+    if (max1 > KJ_MAX_READ_LEN || max2 > KJ_MAX_READ_LEN) { kj_err() = "read longer than KJ_MAX_READ_LEN (381 bases) is not supported yet"; return KJ_ERR_UNSUPPORTED; }
+    KjRunParams rp; kj_fill_run_params(c->params, std::max(max1, max2), rp);
+    int rc = ensure_evalue_table(c, rp, max1, max2, st); if (rc) return rc;
+    size_t smem; int grid; rc = configure_launch(c, rp, smem, grid); if (rc) return rc;
+    rc = ensure_scratch(c, rp, grid); if (rc) return rc;
+    c->grid = grid; c->smem_bytes = smem;
+    CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
+    if (time_it) CK(cudaEventRecord(c->ev_a, st));
+    const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
+    kj_classify_kernel<<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best,
+                                                                 c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries,
+                                                                 c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), c->d_err);
+    CK(cudaGetLastError());
+    if (time_it) CK(cudaEventRecord(c->ev_b, st));
+    c->launches++;
+    return KJ_OK;
+}
+
+static int check_err_flag(kj_ctx* c) {
+    uint32_t e = 0; CK(cudaMemcpy(&e, c->d_err, sizeof e, cudaMemcpyDeviceToHost));
+    if (e) { CK(cudaMemset(c->d_err, 0, sizeof e)); char b[96]; snprintf(b, sizeof b, "per-read work queue overflow on the device (flags 0x%x)", e); kj_err() = b; return KJ_ERR_OVERFLOW; }
+    return KJ_OK;
+}
+
+extern "C" int kj_classify_device(kj_ctx* c, const char* d_seq1, const uint64_t* d_off1, const char* d_seq2, const uint64_t* d_off2, uint64_t n,
+                                  uint32_t max_len1, uint32_t max_len2, uint64_t* d_tax, uint32_t* d_best, void* cuda_stream) {
+    if (!c || !d_seq1 || !d_off1 || !d_tax || (d_seq2 && !d_off2)) { kj_err() = "kj_classify_device: null argument"; return KJ_ERR_ARG; }
+    if (n == 0) return KJ_OK;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (max_len1 == 0 || (d_seq2 && max_len2 == 0)) {
+        CK(cudaMemsetAsync(c->d_maxlen, 0, 2 * sizeof(unsigned int), st));
+        kj_maxlen_kernel<<<256, 256, 0, st>>>(d_off1, n, c->d_maxlen); c->launches++;
+        if (d_seq2) { kj_maxlen_kernel<<<256, 256, 0, st>>>(d_off2, n, c->d_maxlen + 1); c->launches++; }
+        unsigned int h[2] = {0, 0}; CK(cudaMemcpyAsync(h, c->d_maxlen, sizeof h, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        max_len1 = h[0]; max_len2 = h[1];
+    }
+    return launch(c, 0, (const uint8_t*)d_seq1, d_off1, (const uint8_t*)d_seq2, d_off2, 0, 0, n, max_len1, max_len2, d_tax, d_best, st, true);
+}
+
+static int ensure_staging(kj_ctx* c, int slot, size_t bytes1, size_t bytes2, size_t reads) {
+    size_t need[2] = {bytes1, bytes2};
+    for (int m = 0; m < 2; m++) if (need[m] > c->d_seq_cap[slot][m]) {
+        if (c->d_seq[slot][m]) cudaFree(c->d_seq[slot][m]); c->d_seq[slot][m] = nullptr;
+        size_t cap = need[m] + need[m] / 8 + 4096; CK(cudaMalloc((void**)&c->d_seq[slot][m], cap)); c->d_seq_cap[slot][m] = cap;
+    }
+    if (reads > c->d_reads_cap) {
+        for (int s = 0; s < 2; s++) {
+            for (int m = 0; m < 2; m++) { if (c->d_off[s][m]) cudaFree(c->d_off[s][m]); c->d_off[s][m] = nullptr; CK(cudaMalloc((void**)&c->d_off[s][m], (reads + 1) * sizeof(uint64_t))); }
+            if (c->d_tax[s]) cudaFree(c->d_tax[s]); if (c->d_best[s]) cudaFree(c->d_best[s]); c->d_tax[s] = nullptr; c->d_best[s] = nullptr;
+            CK(cudaMalloc((void**)&c->d_tax[s], reads * sizeof(uint64_t))); CK(cudaMalloc((void**)&c->d_best[s], reads * sizeof(uint32_t)));
+        }
+        c->d_reads_cap = reads;
+    }
+    return KJ_OK;
+}
+
+extern "C" int kj_classify(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
+                           uint64_t* taxon_out, uint32_t* best_out) {
+    if (!c || !seq1 || !off1 || !taxon_out || (seq2 && !off2)) { kj_err() = "kj_classify: null argument"; return KJ_ERR_ARG; }
+    if (n == 0) return KJ_OK;
+    CK(cudaSetDevice(c->device));
+    const bool paired = seq2 != nullptr;
+    // batch-wide length bounds (fixes the shared-memory carve-up for all chunks)
+    uint32_t max1 = 0, max2 = 0;
+    {
+        unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency())); std::vector<uint32_t> m1(nthr, 0), m2(nthr, 0); std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthr; t++) th.emplace_back([&, t] { uint64_t a = n * t / nthr, b = n * (t + 1) / nthr; uint32_t x = 0, y = 0;
+            for (uint64_t i = a; i < b; i++) { uint64_t l = off1[i + 1] - off1[i]; if (l > 0xffffffffull) l = 0xffffffffull; x = std::max(x, (uint32_t)l);
+                                               if (paired) { uint64_t k = off2[i + 1] - off2[i]; if (k > 0xffffffffull) k = 0xffffffffull; y = std::max(y, (uint32_t)k); } }
+            m1[t] = x; m2[t] = y; });
+        for (auto& x : th) x.join();
+        for (unsigned t = 0; t < nthr; t++) { max1 = std::max(max1, m1[t]); max2 = std::max(max2, m2[t]); }
+    }
+    int rc = ensure_staging(c, 0, 0, 0, std::min<uint64_t>(n, KJ_CHUNK_READS)); if (rc) return rc;
+    // software pipeline over chunks: H2D + kernel + D2H of chunk k on stream k&1 overlap with chunk k+1
+    double kernel_ms = 0.0;
+    for (uint64_t start = 0, k = 0; start < n; start += KJ_CHUNK_READS, k++) {
+        const int s = (int)(k & 1); cudaStream_t st = c->stream[s];
+        const uint64_t cnt = std::min<uint64_t>(KJ_CHUNK_READS, n - start);
+        CK(cudaStreamSynchronize(st));                      // slot s free again (its previous D2H has landed)
+        const uint64_t b1 = off1[start], e1 = off1[start + cnt], b2 = paired ? off2[start] : 0, e2 = paired ? off2[start + cnt] : 0;
+        rc = ensure_staging(c, s, (size_t)(e1 - b1), (size_t)(e2 - b2), c->d_reads_cap); if (rc) return rc;
+        CK(cudaMemcpyAsync(c->d_seq[s][0], seq1 + b1, (size_t)(e1 - b1), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->d_off[s][0], off1 + start, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        if (paired) {
+            CK(cudaMemcpyAsync(c->d_seq[s][1], seq2 + b2, (size_t)(e2 - b2), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->d_off[s][1], off2 + start, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        }
+        rc = launch(c, s, c->d_seq[s][0], c->d_off[s][0], paired ? c->d_seq[s][1] : nullptr, paired ? c->d_off[s][1] : nullptr, b1, b2, cnt, max1, max2,
+                    c->d_tax[s], best_out ? c->d_best[s] : nullptr, st, false);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(taxon_out + start, c->d_tax[s], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (best_out) CK(cudaMemcpyAsync(best_out + start, c->d_best[s], cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(c->stream[0])); CK(cudaStreamSynchronize(c->stream[1]));
+    (void)kernel_ms;
+    return check_err_flag(c);
+}
+
+extern "C" uint64_t kj_kernel_launches(const kj_ctx* c) { return c ? c->launches : 0; }
+extern "C" uint64_t kj_index_bytes(const kj_ctx* c) { return c ? c->index_bytes : 0; }
+extern "C" double kj_last_kernel_ms(const kj_ctx* c) {
+    if (!c) return 0.0;
+    float ms = 0.f; if (cudaEventSynchronize(c->ev_b) != cudaSuccess) return 0.0;
+    if (cudaEventElapsedTime(&ms, c->ev_a, c->ev_b) != cudaSuccess) return 0.0;
+    return (double)ms;
+}
+extern "C" int kj_check_errors(kj_ctx* c) { if (!c) return KJ_ERR_ARG; cudaSetDevice(c->device); return check_err_flag(c); }
+extern "C" int kj_launch_geometry(const kj_ctx* c, int* grid, int* block, int* smem) { if (!c) return KJ_ERR_ARG; if (grid) *grid = c->grid; if (block) *block = KJ_WARPS_PER_CTA * 32; if (smem) *smem = (int)c->smem_bytes; return KJ_OK; }

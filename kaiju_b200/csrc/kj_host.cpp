@@ -1,0 +1,311 @@
+// kj_host.cpp -- loaders for the reference's on-disk formats and the host-side transcoder to the device layout.
+#include "kj_host.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <climits>
+#include <thread>
+#include <unordered_map>
+
+std::string& kj_err() { static thread_local std::string e; return e; }
+extern "C" const char* kj_last_error(void) { return kj_err().c_str(); }
+extern "C" int kj_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------
+// .fmi  (written by kaiju-mkfmi, mkfmi.c:68-77): BWT header (bwt.c:40-45), suffix-array header + body
+// (suffixArray.c:261-277, 325-328), FM index (fmicommon.h:175-184, compactfmi.c:176-179).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Reader {
+    FILE* fp; bool ok = true;
+    explicit Reader(FILE* f) : fp(f) {}
+    template <class T> T get() { T v{}; if (fread(&v, sizeof(T), 1, fp) != 1) ok = false; return v; }
+    void bytes(void* p, size_t n) { if (n && fread(p, 1, n, fp) != n) ok = false; }
+    void skip(int64_t n) { if (fseeko(fp, (off_t)n, SEEK_CUR) != 0) ok = false; }
+};
+uint64_t taxon_of_name(const std::string& name) {
+    // ConsumerThread.cpp:812-832: digits after the LAST '_', or the whole name when there is none
+    const char* s = name.c_str(); const char* u = strrchr(s, '_');
+    unsigned long v = strtoul(u ? u + 1 : s, nullptr, 10);
+    return v == ULONG_MAX ? UINT64_MAX : (uint64_t)v;
+}
+}  // namespace
+
+extern "C" int kj_fmi_load(const char* path, kj_fmi** out) {
+    if (!path || !out) { kj_err() = "kj_fmi_load: null argument"; return KJ_ERR_ARG; }
+    FILE* fp = fopen(path, "rb");
+    if (!fp) { kj_err() = std::string("could not open ") + path; return KJ_ERR_IO; }
+    kj_fmi* f = new kj_fmi(); Reader r(fp);
+    f->len = r.get<int64_t>(); f->nseq = r.get<int32_t>(); f->alen = r.get<int32_t>();
+    if (!r.ok || f->alen <= 1 || f->alen > 64 || f->nseq < 0 || f->len <= 0) { fclose(fp); delete f; kj_err() = "not a .fmi file (BWT header)"; return KJ_ERR_IO; }
+    f->alphabet.resize((size_t)f->alen); r.bytes(&f->alphabet[0], (size_t)f->alen);
+    f->sa_len = r.get<int64_t>(); f->ncheck = r.get<int64_t>(); f->chpt_exp = r.get<int32_t>(); f->nbytes = r.get<int32_t>();
+    f->sbits = r.get<int32_t>(); f->pbits = r.get<int32_t>(); f->mask = r.get<int64_t>(); f->check = r.get<int64_t>();
+    int32_t nseq2 = r.get<int32_t>();
+    if (!r.ok || nseq2 != f->nseq || f->nbytes <= 0 || f->nbytes > 8 || f->ncheck < 0 || f->chpt_exp < 0 || f->chpt_exp > 30) { fclose(fp); delete f; kj_err() = "not a .fmi file (suffix-array header)"; return KJ_ERR_IO; }
+    f->ids.resize((size_t)f->nseq); f->seq_taxon.resize((size_t)f->nseq);
+    for (int32_t i = 0; i < f->nseq && r.ok; i++) {
+        uint8_t l = r.get<uint8_t>(); std::string& s = f->ids[(size_t)i]; s.resize(l); r.bytes(l ? &s[0] : nullptr, l);
+        f->seq_taxon[(size_t)i] = taxon_of_name(s);
+    }
+    r.skip((int64_t)f->nseq * 4); r.skip((int64_t)f->nseq * 8);          // seqTermOrder, seqlengths: not needed for classification
+    f->sa.resize((size_t)(f->ncheck * f->nbytes)); r.bytes(f->sa.data(), f->sa.size());
+    int32_t alen2 = r.get<int32_t>(); f->bwtlen = r.get<int64_t>(); f->N1 = r.get<int32_t>(); f->N2 = r.get<int32_t>();
+    if (!r.ok || alen2 != f->alen || f->bwtlen <= 0) { fclose(fp); delete f; kj_err() = "not a .fmi file (FMI header)"; return KJ_ERR_IO; }
+    f->bwt.resize((size_t)f->bwtlen); r.bytes(f->bwt.data(), f->bwt.size());
+    r.skip((int64_t)f->N1 * f->alen * 8); r.skip((int64_t)f->N2 * f->alen * 2);   // index1/index2: rank tables are rebuilt in the device layout
+    f->startLcode.resize((size_t)f->alen + 1); r.bytes(f->startLcode.data(), sizeof(int32_t) * ((size_t)f->alen + 1));
+    bool ok = r.ok; fclose(fp);
+    if (!ok) { delete f; kj_err() = "truncated .fmi file"; return KJ_ERR_IO; }
+    *out = f; return KJ_OK;
+}
+extern "C" void kj_fmi_view(const kj_fmi* f, kj_index_view* v) {
+    v->alen = f->alen; v->alphabet = f->alphabet.c_str(); v->bwtlen = f->bwtlen; v->bwt = f->bwt.data(); v->startLcode = f->startLcode.data();
+    v->db_len = f->len; v->nseq = f->nseq; v->ncheck = f->ncheck; v->chpt_exp = f->chpt_exp; v->nbytes = f->nbytes; v->pbits = f->pbits;
+    v->sa = f->sa.data(); v->seq_taxon = f->seq_taxon.data();
+}
+extern "C" void kj_fmi_free(kj_fmi* f) { delete f; }
+
+// nodes.dmp (parseNodesDmp, util.cpp:79-99): first integer = node, next integer = parent; bad lines skipped
+extern "C" int kj_nodes_load(const char* path, kj_nodes** out) {
+    if (!path || !out) { kj_err() = "kj_nodes_load: null argument"; return KJ_ERR_ARG; }
+    FILE* fp = fopen(path, "r");
+    if (!fp) { kj_err() = std::string("could not open ") + path; return KJ_ERR_IO; }
+    kj_nodes* t = new kj_nodes(); char* line = nullptr; size_t cap = 0; ssize_t n;
+    while ((n = getline(&line, &cap, fp)) > 0) {
+        const char* p = line; if (*p < '0' || *p > '9') continue;
+        char* e; uint64_t node = strtoull(p, &e, 10); p = e;
+        while (*p && (*p < '0' || *p > '9')) p++;
+        if (!*p) continue;
+        t->node.push_back(node); t->parent.push_back(strtoull(p, nullptr, 10));
+    }
+    free(line); fclose(fp); *out = t; return KJ_OK;
+}
+extern "C" void kj_nodes_view(const kj_nodes* t, kj_taxonomy_view* v) { v->n = t->node.size(); v->node = t->node.data(); v->parent = t->parent.data(); }
+extern "C" void kj_nodes_free(kj_nodes* t) { delete t; }
+
+// ------------------------------------------------------------------------------------------------
+// tables
+// ------------------------------------------------------------------------------------------------
+namespace {
+const char* kAaOrder = "ARNDCQEGHILKMFPSTWYV";                     // aa2int (ConsumerThread.cpp:45-65)
+const int8_t kB62[20][20] = {                                       // BLOSUM62 in kAaOrder (ConsumerThread.cpp:66-107)
+ { 4,-1,-2,-2, 0,-1,-1, 0,-2,-1,-1,-1,-1,-2,-1, 1, 0,-3,-2, 0}, {-1, 5, 0,-2,-3, 1, 0,-2, 0,-3,-2, 2,-1,-3,-2,-1,-1,-3,-2,-3},
+ {-2, 0, 6, 1,-3, 0, 0, 0, 1,-3,-3, 0,-2,-3,-2, 1, 0,-4,-2,-3}, {-2,-2, 1, 6,-3, 0, 2,-1,-1,-3,-4,-1,-3,-3,-1, 0,-1,-4,-3,-3},
+ { 0,-3,-3,-3, 9,-3,-4,-3,-3,-1,-1,-3,-1,-2,-3,-1,-1,-2,-2,-1}, {-1, 1, 0, 0,-3, 5, 2,-2, 0,-3,-2, 1, 0,-3,-1, 0,-1,-2,-1,-2},
+ {-1, 0, 0, 2,-4, 2, 5,-2, 0,-3,-3, 1,-2,-3,-1, 0,-1,-3,-2,-2}, { 0,-2, 0,-1,-3,-2,-2, 6,-2,-4,-4,-2,-3,-3,-2, 0,-2,-2,-3,-3},
+ {-2, 0, 1,-1,-3, 0, 0,-2, 8,-3,-3,-1,-2,-1,-2,-1,-2,-2, 2,-3}, {-1,-3,-3,-3,-1,-3,-3,-4,-3, 4, 2,-3, 1, 0,-3,-2,-1,-3,-1, 3},
+ {-1,-2,-3,-4,-1,-2,-3,-4,-3, 2, 4,-2, 2, 0,-3,-2,-1,-2,-1, 1}, {-1, 2, 0,-1,-3, 1, 1,-2,-1,-3,-2, 5,-1,-3,-1, 0,-1,-3,-2,-2},
+ {-1,-1,-2,-3,-1, 0,-2,-3,-2, 1, 2,-1, 5, 0,-2,-1,-1,-1,-1, 1}, {-2,-3,-3,-3,-2,-3,-3,-3,-1, 0, 0,-3, 0, 6,-4,-2,-2, 1, 3,-1},
+ {-1,-2,-2,-1,-3,-1,-1,-2,-2,-3,-3,-1,-2,-4, 7,-1,-1,-4,-3,-2}, { 1,-1, 1, 0,-1, 0, 0, 0,-1,-2,-2, 0,-1,-2,-1, 4, 1,-3,-2,-2},
+ { 0,-1, 0,-1,-1,-1,-1,-2,-2,-1,-1,-1,-1,-2,-1, 1, 5,-2,-2, 0}, {-3,-3,-4,-4,-2,-2,-3,-2,-2,-3,-2,-3,-1, 1,-4,-3,-2,11, 2,-3},
+ {-2,-2,-2,-3,-2,-1,-2,-3, 2,-1,-1,-2,-1, 3,-3,-2,-2, 2, 7,-1}, { 0,-3,-3,-3,-1,-2,-2,-3,-3, 3, 1,-2, 1,-1,-2,-2, 0,-3,-1, 4} };
+// substitution try-order per residue (the reference's blosum_subst map, ConsumerThread.cpp:10-30)
+const char* kSubst[20] = {
+ "A:SVTGCPMKLIEQRYFHDNW", "R:KQHENTSMAYPLGDVWFIC", "N:SHDTKGEQRYPMAVFLICW", "D:ENSQTPKHGRAVYFMICWL", "C:AVTSMLIYWFPKHGQDNRE",
+ "Q:EKRSMHDNYTPAVWLGFIC", "E:QDKSHNRTPAVYMGWFLIC", "G:SNADWTPKHEQRVYFMCLI", "H:YNEQRSFKDWTPMGAVLIC", "I:VLMFYTCASWPKHEQDNRG",
+ "L:MIVFYTCAWSKQRPHENGD", "K:REQSNTPMHDAVYLGWFIC", "M:LVIFQYWTSKCRAPHENGD", "F:YWMLIVHTSCAKGEQDNRP", "P:TSKEQDAVMHGNRYLICWF",
+ "S:TNAKGEQDPMHCRVYFLIW", "T:SVNAPMKLIEQCDRYWFHG", "W:YFMTLHGQCVSKIERAPDN", "Y:FWHVMLIQTSKECNRAPGD", "V:IMLTAYFCSPKEQWHGDNR" };
+// standard genetic code, index n0<<4|n1<<2|n2 with A0 C1 G2 T3 (the reference's codon2aa, ConsumerThread.cpp:117-181)
+const char* kCode = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF";
+
+int build_tables(const std::string& alphabet, KjTables& tb) {
+    memset(&tb, 0, sizeof(tb));
+    const int alen = (int)alphabet.size();
+    // translation_table (sequence.c:68-97): letters not in the alphabet map to the last index
+    uint8_t trans[256]; memset(trans, (uint8_t)(alen - 1), sizeof trans);
+    for (int a = 0; a < alen; a++) trans[(uint8_t)alphabet[(size_t)a]] = (uint8_t)a;
+    for (int c = 0; c < 64; c++) tb.codon_aa[c] = kCode[c] == '*' ? 0 : trans[(uint8_t)kCode[c]];
+    int ai_of[256]; for (int i = 0; i < 256; i++) ai_of[i] = -1;
+    for (int i = 0; i < 20; i++) ai_of[(uint8_t)kAaOrder[i]] = i;
+    for (int a = 0; a < alen; a++) for (int b = 0; b < alen; b++) {
+        int ia = ai_of[(uint8_t)alphabet[(size_t)a]], ib = ai_of[(uint8_t)alphabet[(size_t)b]];
+        tb.b62[a][b] = (ia >= 0 && ib >= 0) ? kB62[ia][ib] : 0;
+    }
+    for (int i = 0; i < 20; i++) {
+        int a = trans[(uint8_t)kSubst[i][0]];
+        for (int k = 0; k < 19; k++) tb.subst[a][k] = trans[(uint8_t)kSubst[i][2 + k]];
+    }
+    // SEG window entropy in fixed point; verify on all partitions of 12 that the integer decisions equal
+    // the reference's FP64 decisions (s_Entropy, blast_seg.c:1596-1626; kSegLocut 2.2, kSegHicut 2.5)
+    for (int c = 1; c <= KJ_SEG_WINDOW; c++) tb.seg_logfix[c] = (int32_t)llround(log2(12.0 / c) * 16777216.0);
+    tb.seg_locut_fix = (int32_t)llround(2.2 * 12.0 * 16777216.0);
+    tb.seg_hicut_fix = (int32_t)llround(2.5 * 12.0 * 16777216.0);
+    int part[13]; bool okp = true;
+    // enumerate partitions of 12 (descending parts)
+    struct Rec { static void go(int left, int maxp, int* part, int n, const KjTables& tb, bool& ok) {
+        if (left == 0) {
+            double ent = 0.0; int64_t x = 0;
+            for (int i = 0; i < n; i++) { ent += ((double)part[i]) * log(((double)part[i]) / 12.0) / 0.69314718055994530941723212145818; x += (int64_t)part[i] * tb.seg_logfix[part[i]]; }
+            ent = fabs(ent / 12.0);
+            if ((ent <= 2.2) != (x <= tb.seg_locut_fix) || (ent > 2.5) != (x > tb.seg_hicut_fix)) ok = false;
+            return;
+        }
+        for (int p = std::min(left, maxp); p >= 1; p--) { part[n] = p; go(left - p, p, part, n + 1, tb, ok); }
+    } };
+    Rec::go(12, 12, part, 0, tb, okp);
+    if (!okp) { kj_err() = "SEG fixed-point entropy classes disagree with FP64"; return KJ_ERR_UNSUPPORTED; }
+    return KJ_OK;
+}
+}  // namespace
+
+extern "C" int kj_check_params_c(const kj_params* p) { return p ? kj_check_params(*p) : KJ_ERR_ARG; }
+int kj_check_params(const kj_params& p) {
+    if (p.mode != 0 && p.mode != 1) { kj_err() = "mode must be 0 (MEM) or 1 (GREEDY)"; return KJ_ERR_ARG; }
+    if (p.min_fragment_length == 0 || p.min_fragment_length > 1000) { kj_err() = "min_fragment_length out of range"; return KJ_ERR_ARG; }
+    if (p.mode == 0 && p.use_evalue) { kj_err() = "E-value calculation is only possible in Greedy mode"; return KJ_ERR_ARG; }   // kaiju.cpp:202
+    if (p.mode == 1 && p.mismatches > KJ_MAX_MM) { kj_err() = "more than 8 mismatches (-e) are not supported"; return KJ_ERR_UNSUPPORTED; }
+    if (p.mode == 1 && (p.min_score == 0 || p.seed_length == 0)) { kj_err() = "min_score and seed_length must be > 0"; return KJ_ERR_ARG; }
+    if (p.input_is_protein) { kj_err() = "protein input (-p) is not supported yet"; return KJ_ERR_UNSUPPORTED; }
+    if (p.use_evalue && !(p.min_evalue > 0.0)) { kj_err() = "E-value threshold must be greater than 0"; return KJ_ERR_ARG; }
+    return KJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// transcoder: reference in-memory index -> device layout
+// ------------------------------------------------------------------------------------------------
+int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHostIndex& H) {
+    if (!v.bwt || !v.startLcode || !v.alphabet || !v.sa || !v.seq_taxon || v.bwtlen <= 0) { kj_err() = "kj_create: incomplete index view"; return KJ_ERR_ARG; }
+    if (v.alen < 2 || v.alen > KJ_MAX_ALEN) { kj_err() = "alphabet size not supported"; return KJ_ERR_UNSUPPORTED; }
+    const int alen = v.alen; const uint64_t n = (uint64_t)v.bwtlen;
+    H.alen = alen; H.bwtlen = n; H.nseq = (uint32_t)v.nseq; H.db_length = (double)(v.db_len - v.nseq);
+    int rc = build_tables(std::string(v.alphabet, (size_t)alen), H.tables); if (rc) return rc;
+    // byte code -> letter (fmi_fill_codes, compactfmi.c:75-89)
+    uint8_t lcode[256]; memset(lcode, 0, sizeof lcode);
+    for (int a = 0; a < alen; a++) {
+        int s = v.startLcode[a], e = v.startLcode[a + 1];
+        if (s < 0 || e > 256 || s > e) { kj_err() = "corrupt startLcode"; return KJ_ERR_IO; }
+        for (int k = s; k < e; k++) lcode[k] = (uint8_t)a;
+    }
+    // rank records + packed letters, chunked over threads
+    const uint64_t nb = n / KJ_RANK_BLOCK + 1; H.nb = nb;
+    const uint64_t CH = (uint64_t)KJ_RANK_BLOCK * 2048;                 // positions per chunk (multiple of 192 and 12)
+    const uint64_t nch = (n + CH - 1) / CH;
+    std::vector<uint64_t> ccount((size_t)(nch + 1) * alen, 0);
+    unsigned nthr = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    auto par = [&](auto fn) {
+        std::vector<std::thread> th; for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] { for (uint64_t c = tI; c < nch; c += nthr) fn(c); });
+        for (auto& x : th) x.join();
+    };
+    par([&](uint64_t c) { uint64_t* cc = &ccount[(size_t)(c + 1) * alen]; uint64_t e = std::min(n, (c + 1) * CH); for (uint64_t k = c * CH; k < e; k++) cc[lcode[v.bwt[k]]]++; });
+    for (uint64_t c = 1; c <= nch; c++) for (int a = 0; a < alen; a++) ccount[(size_t)c * alen + a] += ccount[(size_t)(c - 1) * alen + a];
+    const uint64_t* total = &ccount[(size_t)nch * alen];
+    H.C[0] = 0; for (int a = 0; a < alen; a++) H.C[a + 1] = H.C[a] + total[a];
+    if (H.C[alen] != n) { kj_err() = "letter counts do not add up"; return KJ_ERR_IO; }
+    try { H.rank.assign((size_t)alen * nb, KjRankBlock{0, 0, 0, 0}); H.letters.assign((size_t)(n / KJ_LETTERS_PER_WORD + 2), 0); }
+    catch (...) { kj_err() = "out of host memory building the rank table"; return KJ_ERR_NOMEM; }
+    par([&](uint64_t c) {
+        uint64_t run[KJ_MAX_ALEN]; for (int a = 0; a < alen; a++) run[a] = H.C[a] + ccount[(size_t)c * alen + a];
+        uint64_t e = std::min(n, (c + 1) * CH);
+        for (uint64_t b0 = c * CH; b0 < e; b0 += KJ_RANK_BLOCK) {
+            uint64_t b = b0 / KJ_RANK_BLOCK, be = std::min(n, b0 + KJ_RANK_BLOCK);
+            for (int a = 0; a < alen; a++) H.rank[(size_t)a * nb + b].cnt = run[a];
+            for (uint64_t k = b0; k < be; k++) {
+                uint32_t a = lcode[v.bwt[k]], r = (uint32_t)(k - b0); KjRankBlock& B = H.rank[(size_t)a * nb + b];
+                (r < 64 ? B.w0 : r < 128 ? B.w1 : B.w2) |= 1ull << (r & 63);
+                run[a]++;
+            }
+        }
+        for (uint64_t k = c * CH; k < e; k++) H.letters[k / KJ_LETTERS_PER_WORD] |= (uint64_t)lcode[v.bwt[k]] << (5 * (k % KJ_LETTERS_PER_WORD));
+    });
+    // the record after the last letter (k == bwtlen lands there when bwtlen % 192 == 0; otherwise the last partial block already exists)
+    if (n % KJ_RANK_BLOCK == 0) for (int a = 0; a < alen; a++) H.rank[(size_t)a * nb + (nb - 1)].cnt = H.C[a] + total[a];
+
+    // ---- taxonomy re-indexing
+    std::unordered_map<uint64_t, uint64_t> par_of; par_of.reserve((size_t)t.n * 2 + 16);
+    for (uint64_t i = 0; i < t.n; i++) par_of.emplace(t.node[i], t.parent[i]);          // emplace keeps the first (util.cpp:91)
+    std::vector<uint64_t> present; present.reserve(par_of.size());
+    for (auto& kv : par_of) present.push_back(kv.first);
+    std::sort(present.begin(), present.end());
+    std::vector<uint64_t> extra;
+    for (auto& kv : par_of) if (!par_of.count(kv.second)) extra.push_back(kv.second);
+    for (int32_t i = 0; i < v.nseq; i++) { uint64_t x = v.seq_taxon[i]; if (x != UINT64_MAX && !par_of.count(x)) extra.push_back(x); }
+    std::sort(extra.begin(), extra.end()); extra.erase(std::unique(extra.begin(), extra.end()), extra.end());
+    const size_t np = present.size(), nt = np + extra.size();
+    if (nt >= 0xfffffff0ull) { kj_err() = "too many taxa"; return KJ_ERR_UNSUPPORTED; }
+    H.tax_id = present; H.tax_id.insert(H.tax_id.end(), extra.begin(), extra.end());
+    auto index_of = [&](uint64_t id) -> uint32_t {
+        auto it = std::lower_bound(present.begin(), present.end(), id);
+        if (it != present.end() && *it == id) return (uint32_t)(it - present.begin());
+        auto jt = std::lower_bound(extra.begin(), extra.end(), id);
+        return (uint32_t)(np + (size_t)(jt - extra.begin()));
+    };
+    H.tax_parent.resize(nt); H.tax_depth.assign(nt, 0);
+    for (size_t i = 0; i < np; i++) H.tax_parent[i] = index_of(par_of[present[i]]);
+    for (size_t i = np; i < nt; i++) H.tax_parent[i] = (uint32_t)i;
+    // depth = 1 + hops to the self-parent root or to a node missing from nodes.dmp (util.cpp:217-222)
+    {
+        std::vector<uint32_t> stack;
+        for (size_t i = 0; i < np; i++) {
+            if (H.tax_depth[i]) continue;
+            uint32_t cur = (uint32_t)i; stack.clear();
+            while (true) {
+                if (cur >= np) { break; }                                   // absent node: contributes depth "0" below it -> child depth 1+... handled on unwind
+                if (H.tax_depth[cur]) break;
+                if (H.tax_parent[cur] == cur) { H.tax_depth[cur] = 1; break; }
+                if (stack.size() > nt) { kj_err() = "cycle in nodes.dmp"; return KJ_ERR_IO; }
+                stack.push_back(cur); cur = H.tax_parent[cur];
+            }
+            // depth of `cur`: present -> tax_depth[cur]; absent -> the hop onto it still counted (depth++ then loop ends)
+            uint32_t d = cur >= np ? 1u : H.tax_depth[cur];
+            while (!stack.empty()) { uint32_t x = stack.back(); stack.pop_back(); d += 1; H.tax_depth[x] = d; }
+        }
+    }
+    // ---- sequence -> compact taxon; sampled SA -> compact taxon
+    H.seq_tax.resize((size_t)v.nseq);
+    for (int32_t i = 0; i < v.nseq; i++) H.seq_tax[(size_t)i] = v.seq_taxon[i] == UINT64_MAX ? KJ_TAX_BAD : index_of(v.seq_taxon[i]);
+    H.sa_exp = v.chpt_exp; H.sa_check = (1ull << v.chpt_exp) - 1ull;                         // suffixArray_set_masks (suffixArray.c:34-37)
+    H.sa_bias = ((int64_t)(v.nseq - 1) >> v.chpt_exp) + 1;                                   // bwt.c:115-116
+    H.sa_tax.resize((size_t)v.ncheck);
+    {
+        std::vector<std::thread> th; const uint64_t nc = (uint64_t)v.ncheck; bool bad = false;
+        for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] {
+            for (uint64_t e = tI; e < nc; e += nthr) {
+                const uint8_t* p = v.sa + e * (uint64_t)v.nbytes; uint64_t val = 0;
+                for (int b = 0; b < v.nbytes; b++) val = (val << 8) + p[b];                  // uchar2long (suffixArray.h:37-41)
+                uint64_t seq = val >> v.pbits;
+                if (seq >= (uint64_t)v.nseq) { bad = true; continue; }
+                H.sa_tax[e] = H.seq_tax[seq];
+            }
+        });
+        for (auto& x : th) x.join();
+        if (bad) { kj_err() = "corrupt suffix array (sequence number out of range)"; return KJ_ERR_IO; }
+    }
+    // ---- ln(n!) exactly as the reference's literals (blast_seg.c:53-1306 are "%.6f" prints of lgamma)
+    H.lnfact.resize(256);
+    for (int i = 0; i < 256; i++) { char b[64]; snprintf(b, sizeof b, "%.6f", lgamma((double)i + 1.0)); H.lnfact[(size_t)i] = strtod(b, nullptr); }
+    H.lnfact[0] = H.lnfact[1] = 0.0;
+    return KJ_OK;
+}
+
+void kj_build_evalue_table(const kj_params& p, double db_length, uint32_t max1, uint32_t max2, std::vector<uint16_t>& tab) {
+    tab.assign((size_t)(max1 + 1) * (max2 + 1), 0);
+    auto passes = [&](double query_len, unsigned best) {
+        double bitscore = (0.3176 * best - (-2.009915479)) / 0.6931471805;                  // LAMBDA, LN_K, LN_2 (ConsumerThread.hpp:41-44)
+        double Evalue = db_length * query_len * pow(2, -1 * bitscore);
+        return !(Evalue > p.min_evalue);
+    };
+    for (uint32_t a = 0; a <= max1; a++) for (uint32_t b = 0; b <= max2; b++) {
+        double q = static_cast<double>(a) / 3.0; q += static_cast<double>(b) / 3.0;         // ConsumerThread.cpp:698, 704
+        unsigned lo = 0, hi = 65535;
+        if (!passes(q, hi)) { tab[(size_t)a * (max2 + 1) + b] = 65535; continue; }
+        while (lo < hi) { unsigned mid = (lo + hi) / 2; if (passes(q, mid)) hi = mid; else lo = mid + 1; }
+        while (lo > 0 && passes(q, lo - 1)) lo--;
+        tab[(size_t)a * (max2 + 1) + b] = (uint16_t)lo;
+    }
+}
+
+void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp) {
+    memset(&rp, 0, sizeof rp);
+    rp.mode = p.mode; rp.m = p.min_fragment_length; rp.e = p.mismatches; rp.min_score = p.min_score; rp.seed_length = p.seed_length;
+    rp.use_evalue = p.use_evalue; rp.seg = p.seg; rp.protein = p.input_is_protein;
+    if (max_len < 24) max_len = 24;
+    rp.max_len = (max_len + 7) / 8 * 8;
+    rp.max_frag = rp.max_len / 3 + 1;
+    uint32_t per_class = (rp.max_frag + 1 + rp.m) / (rp.m + 1);
+    rp.item_cap = 2 * 12 * per_class + 8; rp.item_cap = (rp.item_cap + 1) & ~1u;
+    rp.kept_cap_smem = 16;
+    rp.scratch_entries = 4 * rp.max_len + 64;
+}

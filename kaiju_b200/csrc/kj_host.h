@@ -1,0 +1,38 @@
+// kj_host.h -- host side of the boundary: .fmi / nodes.dmp loaders (the on-disk formats are the input
+// contract) and the transcoder from the reference's in-memory index to the device
+// layout of kj_layout.h.  Pure C++ (no CUDA) so the test emulator can share it.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/kaiju_b200.h"
+#include "kj_layout.h"
+
+struct kj_fmi {
+    int64_t len = 0; int32_t nseq = 0, alen = 0; std::string alphabet;
+    int64_t sa_len = 0, ncheck = 0; int32_t chpt_exp = 0, nbytes = 0, sbits = 0, pbits = 0; int64_t mask = 0, check = 0;
+    std::vector<std::string> ids; std::vector<uint64_t> seq_taxon; std::vector<uint8_t> sa;
+    int64_t bwtlen = 0; int32_t N1 = 0, N2 = 0; std::vector<uint8_t> bwt; std::vector<int32_t> startLcode;
+};
+struct kj_nodes { std::vector<uint64_t> node, parent; };
+
+// device-layout arrays, built on the host
+struct KjHostIndex {
+    std::vector<KjRankBlock> rank; uint64_t nb = 0;
+    std::vector<uint64_t> letters;
+    uint64_t bwtlen = 0; int alen = 0; uint64_t C[KJ_MAX_ALEN + 1] = {0};
+    std::vector<uint32_t> sa_tax, seq_tax;
+    uint64_t sa_check = 0; int sa_exp = 0; int64_t sa_bias = 0; uint32_t nseq = 0;
+    std::vector<uint32_t> tax_parent, tax_depth; std::vector<uint64_t> tax_id;
+    std::vector<double> lnfact;
+    KjTables tables;
+    double db_length = 0;          // bwt.len - bwt.nseq (Config.cpp:20)
+};
+
+std::string& kj_err();             // thread-local last error text
+int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHostIndex& out);
+int kj_check_params(const kj_params& p);
+// E-value gate (ConsumerThread.cpp:500-513) as the minimal passing integer score per (len1,len2)
+void kj_build_evalue_table(const kj_params& p, double db_length, uint32_t max1, uint32_t max2, std::vector<uint16_t>& tab);
+// per-warp scratch geometry for a batch whose longest mate has max_len bases
+void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp);

@@ -1,0 +1,67 @@
+// kj_layout.h -- HBM data layout of the index, taxonomy and tables (shared by host builder and kernels).
+//
+// The reference keeps the BWT as one byte per letter that also encodes a distance to the nearest 256-
+// checkpoint (bwt/compactfmi.c:44-65) plus two checkpoint tables behind row pointers
+// (bwt/fmicommon.h:60-73).  A rank query there costs two dependent pointer derefs plus a byte scan of
+// ~18-30 bytes.  Rank values are a pure function of the decoded letters (SURVEY.md 8a exactness note a),
+// so the device uses its own layout, built at load time from the decoded letters:
+//
+//   rank[c][b] : one 32-byte record per (letter c, block b of 192 BWT positions)
+//                { cnt = C[c] + #{p < 192 b : L[p] == c},  w0,w1,w2 = one-hot bitmap of L[p]==c }
+//                -> FMindex(c,k) touches exactly ONE 32-byte DRAM sector:  cnt + popc(bits below k).
+//   letters    : the decoded BWT packed 12 letters (5 bit) per 64-bit word, read only by the SA walk.
+//   sa_tax     : the sampled suffix array reduced to what classification needs -- the (compact) taxon of
+//                the sequence each sampled suffix belongs to (bwt/suffixArray.h:47-51 + ConsumerThread.cpp:812-832).
+//   seq_tax    : compact taxon per sequence number (used when the LF walk runs into a terminator, bwt.c:119).
+//   tax_*      : taxonomy re-indexed densely: ids present in nodes.dmp get indices [0,n_present), DB taxa
+//                absent from nodes.dmp get the indices after that (depth 0 marks "absent", util.cpp:206).
+#pragma once
+#include <stdint.h>
+
+#define KJ_RANK_BLOCK 192          // positions per rank record (3 x 64-bit words)
+#define KJ_LETTERS_PER_WORD 12
+#define KJ_MAX_ALEN 24
+#define KJ_MAX_IDS 21              // max_match_ids = 20 -> the set holds at most 21 (ConsumerThread.cpp:805)
+#define KJ_MAX_BEST_SI 20          // max_matches_SI (Config.hpp:35)
+#define KJ_TAX_BAD 0xffffffffu     // "bad number" database name (ConsumerThread.cpp:817-820): skipped
+#define KJ_MAX_MM 8                // max supported -e
+#define KJ_SEG_WINDOW 12
+
+struct alignas(32) KjRankBlock { uint64_t cnt, w0, w1, w2; };
+
+struct KjKmer { uint64_t lo, hi; };  // SA interval of a k-mer (empty if lo >= hi)
+
+struct KjTables {
+    uint8_t codon_aa[64];            // (n0<<4|n1<<2|n2) -> alphabet index, 0 = stop  (ConsumerThread.cpp:117-181 + sequence.c:68-97)
+    int8_t b62[KJ_MAX_ALEN][KJ_MAX_ALEN];   // BLOSUM62 indexed by ALPHABET index        (ConsumerThread.cpp:88-107)
+    uint8_t subst[KJ_MAX_ALEN][20];  // substitution try-order per residue, alphabet indices (ConsumerThread.cpp:10-30)
+    int32_t seg_logfix[KJ_SEG_WINDOW + 1];  // round(2^24 log2(12/c)) : entropy of a 12-window in fixed point
+    int32_t seg_locut_fix, seg_hicut_fix;   // 12*2.2*2^24, 12*2.5*2^24 (margins checked on host against FP64)
+};
+
+struct KjDevIndex {
+    const KjRankBlock* rank; uint64_t nb;       // [alen][nb]
+    const uint64_t* letters;
+    uint64_t bwtlen; int alen;
+    uint64_t C[KJ_MAX_ALEN + 1];                // C[c] = first SA row of letter c; C[alen] = bwtlen
+    const uint32_t* sa_tax; const uint32_t* seq_tax;
+    uint64_t sa_check; int sa_exp; int64_t sa_bias; uint64_t n_sa; uint32_t nseq;
+    const uint32_t* tax_parent; const uint32_t* tax_depth; const uint64_t* tax_id; uint32_t n_tax;
+    const double* lnfact; int n_lnfact;
+    const KjKmer* kmer; int kmer_k;             // optional direct-address table of k-mer intervals (0 = off)
+    const KjTables* tables;
+};
+
+struct KjRunParams {
+    int mode;                       // 0 MEM, 1 GREEDY
+    uint32_t m, e, min_score, seed_length;
+    int use_evalue, seg, protein;
+    // E-value gate as an integer threshold table: min passing best score for (len1,len2)
+    const uint16_t* evalue_min_score; uint32_t ev_stride;   // [len1*(ev_stride)+len2]
+    // per-warp scratch geometry
+    uint32_t max_len;               // longest read (bases) in the batch, rounded up
+    uint32_t max_frag;              // longest fragment (residues)
+    uint32_t item_cap;              // fragment-queue capacity per warp
+    uint32_t kept_cap_smem;         // winners kept in shared memory before spilling
+    uint32_t scratch_entries;       // global spill entries per warp
+};

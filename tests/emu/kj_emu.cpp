@@ -1,0 +1,182 @@
+// kj_emu.cpp -- TEST INFRASTRUCTURE ONLY: runs the product's kernel source (kaiju_b200/csrc/kj_core.h,
+// compiled with -DKJ_EMU) on a CPU by emulating one warp with 32 cooperatively scheduled fibers, so the
+// exact device logic can be checked against the oracle on a machine without a GPU.  The product library
+// (libkaijub200.so) never contains this file and has no CPU execution path.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <thread>
+#include <vector>
+#include <atomic>
+#define KJ_EMU 1
+#include "../../kaiju_b200/csrc/kj_warp.h"
+
+namespace kjemu {
+extern "C" void kjemu_ctx_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl kjemu_ctx_switch
+.type kjemu_ctx_switch,@function
+kjemu_ctx_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+)");
+
+struct Sched {
+    static const int NL = 32;
+    void* sp[NL]; char* stack[NL]; bool done[NL]; void* main_sp;
+    int cur; uint64_t slots[2][NL]; int arrived[2]; long gen[NL]; long complete; long progress; int ndone;
+    void (*body)(Sched*, int, void*); void* arg;
+    size_t stack_size;
+    Sched() : stack_size(256 * 1024) { for (int i = 0; i < NL; i++) stack[i] = (char*)aligned_alloc(64, stack_size); }
+    ~Sched() { for (int i = 0; i < NL; i++) free(stack[i]); }
+    void yield_from(int lane) {
+        long p0 = progress; int spins = 0;
+        for (;;) {
+            int nx = lane;
+            for (int t = 1; t <= NL; t++) { int c = (lane + t) % NL; if (!done[c]) { nx = c; break; } }
+            if (nx == lane) {   // nobody else runnable
+                fprintf(stderr, "kjemu: deadlock -- lane %d waits in a collective while all other lanes have exited\n", lane); abort();
+            }
+            int me = lane; cur = nx; kjemu_ctx_switch(&sp[me], sp[nx]);
+            // resumed
+            if (progress != p0) return;
+            if (++spins > 4 * NL) { fprintf(stderr, "kjemu: deadlock -- lanes diverged around a warp collective (lane %d)\n", lane); abort(); }
+            return;   // let the caller re-check its condition
+        }
+    }
+};
+static thread_local Sched* tls_sched = nullptr;
+
+static void fiber_entry() {
+    Sched* s = tls_sched; int lane = s->cur;
+    s->body(s, lane, s->arg);
+    s->done[lane] = true; s->ndone++; s->progress++;
+    if (s->ndone == Sched::NL) { void* dummy; kjemu_ctx_switch(&dummy, s->main_sp); }
+    for (;;) {
+        int nx = -1; for (int t = 1; t <= Sched::NL; t++) { int c = (lane + t) % Sched::NL; if (!s->done[c]) { nx = c; break; } }
+        if (nx < 0) { void* dummy; kjemu_ctx_switch(&dummy, s->main_sp); }
+        s->cur = nx; void* dummy; kjemu_ctx_switch(&dummy, s->sp[nx]);
+    }
+}
+
+static void run_warp(Sched* s, void (*body)(Sched*, int, void*), void* arg) {
+    tls_sched = s; s->body = body; s->arg = arg; s->arrived[0] = s->arrived[1] = 0; s->complete = -1; s->progress = 0; s->ndone = 0;
+    for (int i = 0; i < Sched::NL; i++) {
+        s->done[i] = false; s->gen[i] = 0;
+        uintptr_t top = ((uintptr_t)(s->stack[i] + s->stack_size)) & ~(uintptr_t)63;
+        void** p = (void**)(top - 64);
+        // layout popped by kjemu_ctx_switch: r15 r14 r13 r12 rbx rbp, then ret -> fiber_entry (rsp must be 8 mod 16 at entry)
+        p[-1] = nullptr;                 // fake return address of fiber_entry (never used)
+        p[-2] = (void*)&fiber_entry;     // address at 16-aligned slot -> after ret rsp = &p[-1] which is 8 mod 16
+        for (int k = 3; k <= 8; k++) p[-k] = nullptr;
+        s->sp[i] = (void*)&p[-8];
+    }
+    s->cur = 0; kjemu_ctx_switch(&s->main_sp, s->sp[0]);
+}
+
+uint64_t rendezvous(Sched* s, int lane, uint64_t v, int kind, int arg) {
+    long g = s->gen[lane]++; int par = (int)(g & 1);
+    s->slots[par][lane] = v;
+    if (++s->arrived[par] == Sched::NL) { s->arrived[par] = 0; s->complete = g; s->progress++; }
+    int spins = 0;
+    while (s->complete < g) { s->yield_from(lane); if (++spins > 100000) { fprintf(stderr, "kjemu: stuck collective\n"); abort(); } }
+    int src = kind == 0 ? (arg & 31) : ((lane ^ arg) & 31);
+    return s->slots[par][src];
+}
+uint32_t rendezvous_ballot(Sched* s, int lane, bool p) {
+    long g = s->gen[lane]++; int par = (int)(g & 1);
+    s->slots[par][lane] = p ? 1 : 0;
+    if (++s->arrived[par] == Sched::NL) { s->arrived[par] = 0; s->complete = g; s->progress++; }
+    int spins = 0;
+    while (s->complete < g) { s->yield_from(lane); if (++spins > 100000) { fprintf(stderr, "kjemu: stuck collective\n"); abort(); } }
+    uint32_t m = 0; for (int i = 0; i < Sched::NL; i++) if (s->slots[par][i]) m |= 1u << i;
+    return m;
+}
+}  // namespace kjemu
+
+#include "../../kaiju_b200/csrc/kj_core.h"
+#include "../../kaiju_b200/csrc/kj_core_greedy.h"
+#include "../../kaiju_b200/csrc/kj_host.h"
+
+struct EmuCtx {
+    KjHostIndex H; KjDevIndex D; kj_params P; std::vector<uint16_t> evtab; uint32_t ev1 = 0, ev2 = 0;
+};
+struct ItemArg { EmuCtx* c; KjRunParams* rp; uint8_t* smem; KjKept* spill; void* gscratch; uint32_t* err; const uint8_t* s1; int n1; const uint8_t* s2; int n2; bool paired; uint32_t tax[32]; uint32_t best[32]; };
+
+static void item_body(kjemu::Sched* s, int lane, void* a) {
+    ItemArg* A = (ItemArg*)a;
+    KjWarpCtx cx; cx.w.lane = lane; cx.w.s = s; cx.ix = &A->c->D; cx.rp = A->rp; cx.tb = &A->c->H.tables; cx.smem = A->smem;
+    cx.L = kj_smem_layout(*A->rp); cx.spill = A->spill; cx.gscratch = A->gscratch; cx.err = A->err;
+    uint32_t best = 0;
+    uint32_t t = kj_classify_item(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best);
+    A->tax[lane] = t; A->best[lane] = best;
+}
+
+extern "C" {
+void* kjemu_create(const char* fmi_path, const char* nodes_path, const kj_params* p) {
+    kj_fmi* f = nullptr; kj_nodes* t = nullptr;
+    if (kj_fmi_load(fmi_path, &f) != KJ_OK) { fprintf(stderr, "kjemu: %s\n", kj_last_error()); return nullptr; }
+    if (kj_nodes_load(nodes_path, &t) != KJ_OK) { fprintf(stderr, "kjemu: %s\n", kj_last_error()); return nullptr; }
+    kj_index_view iv; kj_taxonomy_view tv; kj_fmi_view(f, &iv); kj_nodes_view(t, &tv);
+    EmuCtx* c = new EmuCtx(); c->P = *p;
+    if (kj_check_params(*p) != KJ_OK || kj_build_host_index(iv, tv, c->H) != KJ_OK) { fprintf(stderr, "kjemu: %s\n", kj_last_error()); delete c; return nullptr; }
+    kj_fmi_free(f); kj_nodes_free(t);
+    KjDevIndex& D = c->D; KjHostIndex& H = c->H; memset(&D, 0, sizeof D);
+    D.rank = H.rank.data(); D.nb = H.nb; D.letters = H.letters.data(); D.bwtlen = H.bwtlen; D.alen = H.alen;
+    for (int a = 0; a <= H.alen; a++) D.C[a] = H.C[a];
+    D.sa_tax = H.sa_tax.data(); D.seq_tax = H.seq_tax.data(); D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
+    D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
+    D.tax_parent = H.tax_parent.data(); D.tax_depth = H.tax_depth.data(); D.tax_id = H.tax_id.data(); D.n_tax = (uint32_t)H.tax_id.size();
+    D.lnfact = H.lnfact.data(); D.n_lnfact = (int)H.lnfact.size(); D.kmer = nullptr; D.kmer_k = 0; D.tables = &H.tables;
+    return c;
+}
+void kjemu_destroy(void* h) { delete (EmuCtx*)h; }
+
+int kjemu_classify(void* h, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
+                   uint64_t* taxon_out, uint32_t* best_out, int nthreads) {
+    EmuCtx* c = (EmuCtx*)h; bool paired = seq2 != nullptr;
+    uint32_t max1 = 0, max2 = 0;
+    for (uint64_t i = 0; i < n; i++) { max1 = std::max<uint32_t>(max1, (uint32_t)(off1[i + 1] - off1[i])); if (paired) max2 = std::max<uint32_t>(max2, (uint32_t)(off2[i + 1] - off2[i])); }
+    if (max1 > KJ_MAX_READ_LEN || max2 > KJ_MAX_READ_LEN) return KJ_ERR_UNSUPPORTED;
+    KjRunParams rp; kj_fill_run_params(c->P, std::max(max1, max2), rp);
+    if (c->P.mode == 1 && c->P.use_evalue) { kj_build_evalue_table(c->P, c->H.db_length, max1, max2, c->evtab); rp.evalue_min_score = c->evtab.data(); rp.ev_stride = max2 + 1; }
+    KjSmemLayout L = kj_smem_layout(rp);
+    std::atomic<uint64_t> next(0); std::atomic<uint32_t> errs(0);
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back([&] {
+        kjemu::Sched* s = new kjemu::Sched();
+        std::vector<uint8_t> smem(L.total + 64); std::vector<KjKept> spill(rp.scratch_entries);
+        std::vector<uint8_t> gscratch(kj_greedy_scratch_bytes(rp)); uint32_t err = 0;
+        for (;;) {
+            uint64_t i = next.fetch_add(1); if (i >= n) break;
+            ItemArg A; A.c = c; A.rp = &rp; A.smem = smem.data(); A.spill = spill.data(); A.gscratch = gscratch.data(); A.err = &err;
+            A.s1 = (const uint8_t*)seq1 + off1[i]; A.n1 = (int)(off1[i + 1] - off1[i]);
+            A.s2 = paired ? (const uint8_t*)seq2 + off2[i] : nullptr; A.n2 = paired ? (int)(off2[i + 1] - off2[i]) : 0; A.paired = paired;
+            memset(smem.data(), 0xA5, smem.size());      // poison: the kernel must not rely on zeroed shared memory
+            kjemu::run_warp(s, item_body, &A);
+            for (int l = 1; l < 32; l++) if (A.tax[l] != A.tax[0] || A.best[l] != A.best[0]) { fprintf(stderr, "kjemu: non-uniform result at read %llu\n", (unsigned long long)i); abort(); }
+            taxon_out[i] = A.tax[0] == KJ_TAX_BAD ? 0 : c->H.tax_id[A.tax[0]];
+            if (best_out) best_out[i] = taxon_out[i] ? A.best[0] : 0;
+        }
+        errs |= err; delete s;
+    });
+    for (auto& x : th) x.join();
+    return errs.load() ? KJ_ERR_OVERFLOW - 100 * (int)errs.load() : KJ_OK;
+}
+}
