@@ -24,7 +24,7 @@
 struct KjKept { uint64_t lo; uint32_t len; uint32_t aux; };     // one suffix interval (an SI of bwt.h:25-34)
 
 struct KjSmemLayout {
-    uint32_t qkey_off, qpay_off, kept_off, res_off, ids_off, aa_off, aa_stride, frag_off, hflag_off,
+    uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, aa_off, aa_stride, frag_off, hflag_off,
              segcnt_off, seghist_off, segs_off, total;
 };
 static KJ_HD uint32_t kj_align(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -33,8 +33,10 @@ static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
     L.qkey_off = o; o += 8u * p.item_cap;
     L.kept_off = o; o += 16u * p.kept_cap_smem;
     L.res_off = o; o += 16u * kj_align(p.max_frag + 1, 2);           // per-j chain results (greedy)
+    L.res2_off = o; o += 16u * kj_align(p.max_frag + 1, 2);          // recorded matches in class order (greedy)
     L.qpay_off = o; o += 4u * kj_align(p.item_cap, 2);
     L.ids_off = o; o += 4u * 24u;
+    L.pre_off = o; o += 2u * kj_align(p.max_frag + 2, 4);            // prefix sums of the BLOSUM62 diagonal (greedy)
     L.segs_off = o; o += 8u * KJ_SEG_CAP(p.max_frag);                     // {int begin,end}
     L.aa_stride = kj_align(p.max_len + 4, 8);
     L.aa_off = o; o += 4u * L.aa_stride;

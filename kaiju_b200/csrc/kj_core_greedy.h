@@ -1,5 +1,261 @@
-// kj_core_greedy.h -- Greedy mode (stub while MEM is brought up)
+// kj_core_greedy.h -- Greedy mode: classify_greedyblosum (ConsumerThread.cpp:424-541) with maxMatches /
+// maxMatches_withStart (bwt.c:261-336), addAllMismatchVariantsAtPosSI (346-395) and eval_match_scores (751-797).
+//
+// The reference's priority queue decides which equal-score matches survive the 20-SI and 21-id caps, so the
+// queue is emulated per read (one warp), not relaxed: un-substituted fragments live in the shared-memory
+// key queue of kj_core.h, substituted variants (sequence = source run + <= 8 point substitutions + truncation)
+// in a per-warp global scratch ring that stays L2-resident.  Inside one pop the lanes parallelise what the
+// reference does serially: all seed end positions j of maxMatches, the 19 substitution probes of one
+// position, and the scoring of the recorded matches.
 #pragma once
 #include "kj_core.h"
-static KJ_HD uint32_t kj_greedy_scratch_bytes(const KjRunParams& rp) { return 64; }
-static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int n2, uint32_t& best_out) { best_out = 0; return KJ_TAX_BAD; }
+
+struct alignas(16) KjVariant {
+    uint64_t key;              // kj_qkey(score, order); 0 = free
+    uint64_t lo, hi;           // resume interval (Fragment::si0/si1, ConsumerThread.hpp:52)
+    uint32_t pay;              // source run: arr(2) start(15) len(14) -- len already truncated
+    int32_t diff;              // accumulated substitution score delta (Fragment::diff)
+    uint16_t matchlen; uint8_t num_mm; uint8_t pad;
+    uint16_t subs[KJ_MAX_MM];  // pos << 5 | letter
+    uint32_t pad2;
+};
+#define KJ_VARIANT_CAP 256u
+static KJ_HD uint32_t kj_greedy_scratch_bytes(const KjRunParams& rp) { return rp.mode == 1 ? KJ_VARIANT_CAP * (uint32_t)sizeof(KjVariant) : 64u; }
+
+struct KjMatch { uint64_t lo; uint32_t len; uint16_t qi, ql; };    // one SI: interval + query position/length
+
+struct KjVQueue { KjVariant* v; uint32_t n; };                     // n: high-water mark (uniform)
+
+// compact live variants to the front (called when the ring is full)
+static KJ_DEV void kj_vq_compact(KjWarpCtx& cx, KjVQueue& vq) {
+    const Warp& w = cx.w; uint32_t out = 0;
+    for (uint32_t b = 0; b < vq.n; b += 32) {
+        uint32_t s = b + (uint32_t)w.lane; bool live = s < vq.n && vq.v[s].key != 0;
+        KjVariant tmp; if (live) tmp = vq.v[s];
+        uint32_t mask = w.ballot(live);
+        w.sync();
+        if (live) vq.v[out + (uint32_t)kj_popc(mask & lanemask_lt(w.lane))] = tmp;
+        out += (uint32_t)kj_popc(mask);
+        w.sync();
+    }
+    vq.n = out;
+}
+
+// inclusive warp scan helper (uint32)
+static KJ_DEV uint32_t kj_scan_incl(const Warp& w, uint32_t v) {
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = w.shfl(v, w.lane - d); if (w.lane >= d) v += o; }
+    return v;
+}
+
+static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int n2, uint32_t& best_out) {
+    const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix; const KjRunParams& rp = *cx.rp; const KjTables& tb = *cx.tb;
+    uint8_t* frag = cx.smem + cx.L.frag_off;
+    uint16_t* pre = (uint16_t*)(cx.smem + cx.L.pre_off);               // pre[t] = sum diag(frag[0..t))
+    KjMatch* res = (KjMatch*)(cx.smem + cx.L.res_off);                  // per-j chain results, then recorded matches
+    KjMatch* cls = (KjMatch*)(cx.smem + cx.L.res2_off);                 // recorded matches sorted into classes
+    KjVQueue vq; vq.v = (KjVariant*)cx.gscratch; vq.n = 0;
+    uint32_t best = 0, nbest = 0;                                        // best_match_score, best_matches_SI.size()  (uniform)
+    best_out = 0;
+
+    for (;;) {
+        // ---------------- getNextFragment(best): top of both queues (ConsumerThread.cpp:272-283)
+        w.sync();
+        uint64_t kb = 0; uint32_t slot_b = 0;
+        for (uint32_t s = (uint32_t)w.lane; s < vq.n; s += 32) { uint64_t k = vq.v[s].key; if (k > kb) { kb = k; slot_b = s; } }
+        uint64_t gb = warp_max_u64(w, kb);
+        uint64_t ka = 0; uint32_t slot_a = 0;
+        for (uint32_t s = (uint32_t)w.lane; s < q.n; s += 32) { uint64_t k = q.key[s]; if (k > ka) { ka = k; slot_a = s; } }
+        uint64_t ga = warp_max_u64(w, ka);
+        const uint64_t g = ga > gb ? ga : gb;
+        if (g == 0) break;
+        if ((uint32_t)(g >> 32) < best) break;
+        uint32_t arr, start, len, num_mm = 0, matchlen = 0; int diff = 0; uint64_t si0 = 0, si1 = 0; bool segchecked; uint32_t nsub = 0; uint16_t mysub = 0;
+        if (ga >= gb) {
+            int src = kj_ffs(w.ballot(ka == g)) - 1; uint32_t p = 0;
+            if (w.lane == src) { p = q.pay[slot_a]; q.key[slot_a] = 0; }
+            p = w.shfl(p, src);
+            arr = p >> 30; segchecked = (p >> 29) & 1u; start = (p >> 14) & 0x7fffu; len = p & 0x3fffu;
+        } else {
+            int src = kj_ffs(w.ballot(kb == g)) - 1; uint32_t sl = w.shfl(slot_b, src);
+            const KjVariant& V = vq.v[sl];
+            uint32_t p = V.pay; arr = p >> 30; start = (p >> 14) & 0x7fffu; len = p & 0x3fffu; segchecked = true;
+            num_mm = V.num_mm; matchlen = V.matchlen; diff = V.diff; si0 = V.lo; si1 = V.hi; nsub = num_mm;
+            if ((uint32_t)w.lane < nsub) mysub = V.subs[w.lane];
+            w.sync();
+            if (w.lane == 0) vq.v[sl].key = 0;
+        }
+        kj_load_frag(cx, arr, start, len);
+        if ((uint32_t)w.lane < nsub) frag[mysub >> 5] = (uint8_t)(mysub & 31u);
+        w.sync();
+        if (rp.seg && !segchecked && kj_seg_gate(cx, q, arr, start, len, true)) continue;
+
+        // prefix sums of the BLOSUM62 diagonal (calcScore, ConsumerThread.cpp:397-421)
+        {
+            uint32_t carry = 0;
+            for (uint32_t b = 0; b < len; b += 32) {
+                uint32_t t = b + (uint32_t)w.lane; uint32_t a = t < len ? frag[t] : 0u;
+                uint32_t d = t < len ? (uint32_t)tb.b62[a][a] : 0u;
+                uint32_t sc = kj_scan_incl(w, d) + carry;
+                if (t < len) pre[t + 1] = (uint16_t)sc;
+                carry = w.shfl(sc, 31);
+            }
+            if (w.lane == 0) pre[0] = 0;
+            w.sync();
+        }
+
+        // ---------------- search
+        uint32_t nrec = 0;                                                // recorded matches (uniform)
+        if (num_mm > 0) {
+            // maxMatches_withStart (bwt.c:298-336): extend the stored interval leftwards from len - matchlen; all lanes
+            // run the same chain (identical addresses coalesce into one sector per step)
+            uint64_t lo = si0, hi = si1; int i = (int)len - (int)matchlen;
+            while (i > 0) { if (!kj_update_si(ix, frag[i - 1], lo, hi)) break; i--; }
+            uint32_t l = len - (uint32_t)i;
+            uint32_t Lreq = (num_mm == rp.e) ? rp.m : matchlen;           // ConsumerThread.cpp:445-450
+            if (l >= Lreq) { if (w.lane == 0) { cls[0].lo = lo; cls[0].len = (uint32_t)(hi - lo); cls[0].qi = (uint16_t)i; cls[0].ql = (uint16_t)l; } nrec = 1; }
+            w.sync();
+        } else {
+            // maxMatches(f, seq, len, seed_length, 0) (bwt.c:261-296): one chain per end position j
+            const int L = (int)rp.seed_length;
+            int jhi = (int)len - 1, jlow = (int)len;                       // processed range [jlow, len-1]
+            bool small_round = true;
+            while (jhi >= L - 1) {
+                int nj = jhi - (L - 1) + 1; const int G = small_round ? KJ_ROUND_SMALL : 32; if (nj > G) nj = G;
+                const int j = jhi - w.lane; const bool act = w.lane < nj;
+                uint64_t lo = 0, hi = 0; int i = 0;
+                if (act) i = kj_chain(ix, frag, j, lo, hi);
+                w.sync();
+                uint32_t brk = w.ballot(act && i <= 1);                    // `if (i<=1) break` (bwt.c:292)
+                const int cut = brk ? kj_ffs(brk) - 1 : 31;
+                const bool valid = act && w.lane <= cut;
+                if (valid) { res[j].lo = lo; res[j].len = (uint32_t)(hi - lo); res[j].qi = (uint16_t)i; res[j].ql = (uint16_t)(j - i + 1); }
+                int nvalid = brk ? cut + 1 : nj;
+                jlow = jhi - nvalid + 1;
+                small_round = false;
+                if (brk) break;
+                jhi -= nj;
+            }
+            w.sync();
+            // recorded matches: l >= L and start strictly left of the previously recorded one (bwt.c:276-281);
+            // starts are monotone in j, so "same start as j+1" is the only way to be skipped
+            // pass 1: flags + found order (j descending); pass 2: class position = (#longer) + (#same length found earlier)
+            const int nproc = (int)len - jlow;                             // processed j = len-1-t, t in [0,nproc)
+            for (int b = 0; b < nproc; b += 32) {
+                int t = b + w.lane; int j = (int)len - 1 - t; bool rec = false;
+                if (t < nproc) { KjMatch r = res[j]; rec = r.ql >= (uint32_t)L && !(t > 0 && res[j + 1].qi == r.qi); }
+                uint32_t mk = w.ballot(rec);
+                if (rec) { KjMatch r = res[j]; cls[nrec + (uint32_t)kj_popc(mk & lanemask_lt(w.lane))] = r; }   // found order, temporarily in cls
+                nrec += (uint32_t)kj_popc(mk);
+            }
+            w.sync();
+            // stable sort by ql descending into res (insert_SI_sorted, bwt.c:225-252)
+            for (uint32_t b = 0; b < nrec; b += 32) {
+                uint32_t t = b + (uint32_t)w.lane;
+                if (t < nrec) {
+                    KjMatch r = cls[t]; uint32_t pos = 0;
+                    for (uint32_t u = 0; u < nrec; u++) { uint32_t q2 = cls[u].ql; pos += (q2 > r.ql || (q2 == r.ql && u < t)) ? 1u : 0u; }
+                    res[pos] = r;
+                }
+            }
+            w.sync();
+            for (uint32_t t = (uint32_t)w.lane; t < nrec; t += 32) cls[t] = res[t];
+            w.sync();
+        }
+        if (nrec == 0) continue;                                           // "No match for this fragment" (457-462)
+
+        // ---------------- substitution variants (465-479 + addAllMismatchVariantsAtPosSI 346-395)
+        if (rp.e > 0 && num_mm < rp.e) {
+            // walk: class head, then its samelen chain fn..f2 if the class has >1 member (and stop), else the next class head
+            uint32_t c0 = 0;
+            while (c0 < nrec) {
+                uint32_t c1 = c0 + 1; const uint32_t qlc = cls[c0].ql; while (c1 < nrec && cls[c1].ql == qlc) c1++;
+                const uint32_t nmem = c1 - c0;
+                for (uint32_t wi = 0; wi < nmem; wi++) {
+                    const KjMatch sm = cls[wi == 0 ? c0 : c1 - wi];
+                    const uint32_t mre1 = (uint32_t)sm.qi + sm.ql;         // match_right_end + 1
+                    if (sm.qi > 0 && mre1 >= rp.m) {
+                        const uint32_t new_len = mre1 < len ? mre1 : len;   // erase_pos (474)
+                        const uint32_t pos = (uint32_t)sm.qi - 1u; const uint32_t o = frag[pos];
+                        int sc0 = (int)pre[new_len] + diff; if (sc0 < 0) sc0 = 0;
+                        const int score = sc0 - (int)tb.b62[o][o];          // (363)
+                        const bool lane_sub = w.lane < 19;
+                        const uint32_t sub = lane_sub ? tb.subst[o][w.lane] : 0u;
+                        const int after = lane_sub ? score + (int)tb.b62[o][sub] : 0;
+                        const bool pass = lane_sub && after >= (int)best && after >= (int)rp.min_score;
+                        const uint32_t failmask = ~w.ballot(pass) & 0x7ffffu;
+                        const int n_ok = failmask ? kj_ffs(failmask) - 1 : 19;      // first failing substitute ends the loop (391)
+                        uint64_t lo = sm.lo, hi = sm.lo + sm.len; bool ok = false;
+                        if (w.lane < n_ok) ok = kj_update_si(ix, sub, lo, hi);
+                        w.sync();
+                        const uint32_t okmask = w.ballot(ok); const uint32_t cnt = (uint32_t)kj_popc(okmask);
+                        if (cnt) {
+                            if (vq.n + cnt > KJ_VARIANT_CAP) { kj_vq_compact(cx, vq); }
+                            if (vq.n + cnt > KJ_VARIANT_CAP) { if (w.lane == 0) kj_flag_error(cx, 4u); }
+                            else {
+                                const uint32_t rk = (uint32_t)kj_popc(okmask & lanemask_lt(w.lane));
+                                KjVariant* V = vq.v + (vq.n + rk);                 // dereferenced by `ok` lanes only
+                                // the parent's substitutions that survive the truncation, then the new one
+                                uint32_t ns = 0;
+                                for (uint32_t u = 0; u < nsub; u++) {
+                                    uint32_t sv = w.shfl((uint32_t)mysub, (int)u);
+                                    if ((sv >> 5) < new_len) { if (ok) V->subs[ns] = (uint16_t)sv; ns++; }
+                                }
+                                if (ok) {
+                                    V->subs[ns] = (uint16_t)((pos << 5) | sub);
+                                    V->lo = lo; V->hi = hi; V->pay = kj_qpay(arr, true, start, new_len);
+                                    V->diff = diff + (int)tb.b62[o][sub] - (int)tb.b62[sub][sub];
+                                    V->matchlen = (uint16_t)(sm.ql + 1u); V->num_mm = (uint8_t)(ns + 1u); V->pad = 0; V->pad2 = 0;
+                                    V->key = kj_qkey((uint32_t)after, KJ_ORDER_LATE + q.late + rk);
+                                }
+                                vq.n += cnt; q.late += cnt;
+                            }
+                        }
+                        w.sync();
+                    }
+                }
+                if (nmem > 1) break;
+                c0 = c1;
+            }
+        }
+
+        if (cls[0].ql < rp.m) continue;                                    // "Match ... is too short" (482-488)
+
+        // ---------------- eval_match_scores (751-797): [class0: f2..fn][class1: f2..fn]...[heads, last class first]
+        {
+            uint32_t K = 0, ncand = 0;                                     // classes with ql >= m, members in them
+            { uint32_t c0 = 0; while (c0 < nrec && cls[c0].ql >= rp.m) { uint32_t c1 = c0 + 1; while (c1 < nrec && cls[c1].ql == cls[c0].ql) c1++; K++; ncand = c1; c0 = c1; } }
+            // evaluation position of candidate t (index into cls): non-heads keep their relative order, heads go last in reverse class order
+            for (uint32_t b = 0; b < ncand; b += 32) {
+                uint32_t t = b + (uint32_t)w.lane;
+                if (t < ncand) {
+                    KjMatch r = cls[t]; bool head = (t == 0) || cls[t - 1].ql != r.ql;
+                    uint32_t cidx = 0, heads_before = 0;                   // class index of t, number of heads at indices < t
+                    for (uint32_t u = 1; u <= t; u++) if (cls[u].ql != cls[u - 1].ql) cidx++;
+                    heads_before = cidx + (head ? 0u : 1u);
+                    uint32_t pos = head ? (ncand - K) + (K - 1u - cidx) : t - heads_before;
+                    int sc = (int)pre[r.qi + r.ql] - (int)pre[r.qi] + diff; if (sc < 0) sc = 0;
+                    res[pos].lo = r.lo; res[pos].len = r.len; res[pos].qi = (uint16_t)(sc > 65535 ? 65535 : sc); res[pos].ql = r.ql;
+                }
+            }
+            w.sync();
+            KjKept* bl = (KjKept*)(cx.smem + cx.L.kept_off);               // best_matches_SI (<= 20)
+            for (uint32_t t = 0; t < ncand; t++) {
+                const KjMatch r = res[t]; const uint32_t sc = r.qi;
+                if (sc < rp.min_score) continue;
+                if (sc > best) { best = sc; nbest = 0; if (w.lane == 0) { bl[0].lo = r.lo; bl[0].len = r.len; bl[0].aux = 0; } nbest = 1; }
+                else if (sc == best && nbest < KJ_MAX_BEST_SI) { if (w.lane == 0) { bl[nbest].lo = r.lo; bl[nbest].len = r.len; bl[nbest].aux = 0; } nbest++; }
+            }
+            w.sync();
+        }
+    }
+
+    if (nbest == 0) return KJ_TAX_BAD;
+    if (rp.use_evalue) {                                                   // E-value gate (500-513) as an integer threshold
+        uint32_t thr = rp.evalue_min_score[(uint32_t)n1 * rp.ev_stride + (uint32_t)n2];
+        if (best < thr) return KJ_TAX_BAD;
+    }
+    w.sync();
+    uint32_t t = kj_ids_and_lca(cx, nbest);
+    if (t != KJ_TAX_BAD) best_out = best;
+    return t;
+}

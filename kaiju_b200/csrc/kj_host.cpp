@@ -306,6 +306,6 @@ void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp) {
     rp.max_frag = rp.max_len / 3 + 1;
     uint32_t per_class = (rp.max_frag + 1 + rp.m) / (rp.m + 1);
     rp.item_cap = 2 * 12 * per_class + 8; rp.item_cap = (rp.item_cap + 1) & ~1u;
-    rp.kept_cap_smem = 16;
+    rp.kept_cap_smem = 24;                 // >= max_matches_SI (20): greedy keeps its best list here
     rp.scratch_entries = 4 * rp.max_len + 64;
 }
