@@ -506,6 +506,7 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
 // ---------------------------------------------------------------------------------------------
 static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int n2, uint32_t& best_out);
 
+template <int MODE>
 static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1, const uint8_t* s2, int n2, bool paired, uint32_t& best_out) {
     const KjRunParams& rp = *cx.rp;
     best_out = 0;
@@ -514,9 +515,9 @@ static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1
     if ((!paired && n1 < m3) || (paired && n1 < m3 && n2 < m3)) return KJ_TAX_BAD;
     KjQueue q; q.key = (uint64_t*)(cx.smem + cx.L.qkey_off); q.pay = (uint32_t*)(cx.smem + cx.L.qpay_off);
     q.cap = rp.item_cap; q.n = 0; q.late = 0;
-    const bool greedy = rp.mode == 1;
+    const bool greedy = MODE == 1;
     if (n1 >= m3) kj_translate_mate(cx, q, 0, s1, n1, greedy);            // a short mate is skipped individually (699, 705)
     if (paired && n2 >= m3) kj_translate_mate(cx, q, 1, s2, n2, greedy);
-    if (!greedy) return kj_classify_mem(cx, q, best_out);
-    return kj_classify_greedy(cx, q, n1, paired ? n2 : 0, best_out);
+    if (MODE == 0) return kj_classify_mem(cx, q, best_out);
+    else return kj_classify_greedy(cx, q, n1, paired ? n2 : 0, best_out);
 }

@@ -25,6 +25,7 @@
 
 struct KjCtaShared { KjDevIndex ix; KjTables tb; };
 
+template <int MODE>
 __global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32)
 kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ KjRunParams rp,
                    const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
@@ -61,7 +62,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
         const uint64_t a0 = off1[r] - base1, a1 = off1[r + 1] - base1;
         uint64_t b0 = 0, b1 = 0; if (paired) { b0 = off2[r] - base2; b1 = off2[r + 1] - base2; }
         uint32_t best = 0;
-        uint32_t t = kj_classify_item(cx, seq1 + a0, (int)(a1 - a0), paired ? seq2 + b0 : nullptr, (int)(b1 - b0), paired, best);
+        uint32_t t = kj_classify_item<MODE>(cx, seq1 + a0, (int)(a1 - a0), paired ? seq2 + b0 : nullptr, (int)(b1 - b0), paired, best);
         if (cx.w.lane == 0) {
             uint64_t id = t == KJ_TAX_BAD ? 0ull : sh->ix.tax_id[t];
             taxon_out[r] = id;
@@ -97,7 +98,7 @@ struct kj_ctx {
     uint64_t* d_off[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; uint64_t* d_tax[2] = {nullptr, nullptr}; uint32_t* d_best[2] = {nullptr, nullptr};
     size_t d_reads_cap = 0;
     uint64_t launches = 0; double last_kernel_ms = 0.0;
-    int grid = 0; size_t smem_bytes = 0;
+    int grid = 0; size_t smem_bytes = 0; int cfg_mode = -1;
 };
 
 template <class T> static int upload(const std::vector<T>& v, void** d, uint64_t& total) {
@@ -111,10 +112,16 @@ static int configure_launch(kj_ctx* c, const KjRunParams& rp, size_t& smem, int&
     KjSmemLayout L = kj_smem_layout(rp);
     smem = kj_align((uint32_t)sizeof(KjCtaShared), 16) + (size_t)KJ_WARPS_PER_CTA * L.total;
     if (smem > 227 * 1024) { kj_err() = "per-CTA shared memory exceeds 227 KB (reads too long / -m too small)"; return KJ_ERR_UNSUPPORTED; }
-    if (smem == c->smem_bytes && c->grid > 0) { grid = c->grid; return KJ_OK; }
-    CK(cudaFuncSetAttribute(kj_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem == c->smem_bytes && c->grid > 0 && c->cfg_mode == rp.mode) { grid = c->grid; return KJ_OK; }
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel, KJ_WARPS_PER_CTA * 32, smem));
+    if (rp.mode == 0) {
+        CK(cudaFuncSetAttribute(kj_classify_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<0>, KJ_WARPS_PER_CTA * 32, smem));
+    } else {
+        CK(cudaFuncSetAttribute(kj_classify_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<1>, KJ_WARPS_PER_CTA * 32, smem));
+    }
+    c->cfg_mode = rp.mode;
     if (per_sm < 1) { kj_err() = "kernel does not fit on an SM"; return KJ_ERR_UNSUPPORTED; }
     grid = c->sm_count * per_sm;             // persistent grid: a whole number of CTAs per SM
     return KJ_OK;
@@ -208,9 +215,14 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
     if (time_it) CK(cudaEventRecord(c->ev_a, st));
     const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
-    kj_classify_kernel<<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best,
-                                                                 c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries,
-                                                                 c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), c->d_err);
+    if (rp.mode == 0)
+        kj_classify_kernel<0><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best,
+            c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries,
+            c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), c->d_err);
+    else
+        kj_classify_kernel<1><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best,
+            c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries,
+            c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), c->d_err);
     CK(cudaGetLastError());
     if (time_it) CK(cudaEventRecord(c->ev_b, st));
     c->launches++;

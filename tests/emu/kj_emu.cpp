@@ -123,7 +123,7 @@ static void item_body(kjemu::Sched* s, int lane, void* a) {
     KjWarpCtx cx; cx.w.lane = lane; cx.w.s = s; cx.ix = &A->c->D; cx.rp = A->rp; cx.tb = &A->c->H.tables; cx.smem = A->smem;
     cx.L = kj_smem_layout(*A->rp); cx.spill = A->spill; cx.gscratch = A->gscratch; cx.err = A->err;
     uint32_t best = 0;
-    uint32_t t = kj_classify_item(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best);
+    uint32_t t = A->rp->mode == 0 ? kj_classify_item<0>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best) : kj_classify_item<1>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best);
     A->tax[lane] = t; A->best[lane] = best;
 }
 

@@ -1,0 +1,41 @@
+"""The product's kernel source (kaiju_b200/csrc/kj_core*.h) executed on the CPU warp emulator (tests/emu) against the
+golden reference outputs and the oracle.  This checks the device LOGIC without a GPU; the `gpu` tests check the real thing."""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+from conftest import GOLDEN_CONFIGS, ROOT
+from helpers import Oracle, make_params, SynthDB
+
+
+class KjParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("min_fragment_length", C.c_uint32), ("mismatches", C.c_uint32), ("min_score", C.c_uint32),
+                ("seed_length", C.c_uint32), ("use_evalue", C.c_int32), ("min_evalue", C.c_double), ("seg", C.c_int32), ("input_is_protein", C.c_int32)]
+
+
+@pytest.fixture(scope="module")
+def emu(built):
+    E = C.CDLL(os.path.join(ROOT, "tests", "emu", "libkjemu.so"))
+    E.kjemu_create.restype = C.c_void_p; E.kjemu_create.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(KjParams)]
+    E.kjemu_destroy.argtypes = [C.c_void_p]
+    E.kjemu_classify.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
+    return E
+
+
+def emu_classify(E, fmi, nodes, P, s1, o1, s2, o2):
+    kp = KjParams(**P); h = E.kjemu_create(fmi.encode(), nodes.encode(), C.byref(kp)); assert h
+    n = len(o1) - 1; tax = np.zeros(n, dtype=np.uint64); best = np.zeros(n, dtype=np.uint32)
+    rc = E.kjemu_classify(h, s1.ctypes.data, o1.ctypes.data, s2.ctypes.data if s2 is not None else None, o2.ctypes.data if s2 is not None else None,
+                          n, tax.ctypes.data, best.ctypes.data, 4)
+    E.kjemu_destroy(h); assert rc == 0
+    return tax, best
+
+
+@pytest.mark.parametrize("cfg", sorted(GOLDEN_CONFIGS))
+@pytest.mark.parametrize("tag", ["pe150", "se100"])
+def test_emulated_kernel_matches_reference_golden(emu, golden, cfg, tag):
+    names, s1, o1, s2, o2 = golden.reads(tag)
+    tax, best = emu_classify(emu, golden.fmi, golden.nodes, make_params(**GOLDEN_CONFIGS[cfg]), s1, o1, s2, o2)
+    etax, ebest, _ = golden.expected(cfg, tag)
+    bad = np.nonzero((tax != etax) | (best != ebest))[0]
+    assert len(bad) == 0, [(names[i], int(tax[i]), int(etax[i]), int(best[i]), int(ebest[i])) for i in bad[:5]]
