@@ -120,7 +120,7 @@ def main():
         if rank != 0:
             return
         db, fmi, nodes = build_workload(args, 0)
-        n_sample = args.cpu_sample or max(20000, min(400000, 4000 * cores))
+        n_sample = args.cpu_sample or max(20000, min(3000000, 20000 * cores))
         vals = []
         for s in range(args.warmup + args.steps):
             v, dt = ref_cpu_run(db, fmi, nodes, args, n_sample, 1000 + s, 0, cores)
@@ -243,7 +243,7 @@ def main():
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                                 "algorithmic_bytes_per_item": alg, "peak_source": peak_src,
                                 "note": "numerator = reference algorithm's bytes (instrumented oracle, %d-pair sample) x items per launch; kernel time from CUDA events on the launch stream" % n_or}
-            n_cpu = args.cpu_sample or max(20000, min(400000, 4000 * cores))
+            n_cpu = args.cpu_sample or max(20000, min(3000000, 20000 * cores))
             v, dt = ref_cpu_run(db, fmi, nodes, args, n_cpu, 7, 0, cores)
             line["cpu_baseline"] = {"value": v, "unit": "read pairs/s", "cores": cores, "kind": "reference",
                                     "sample": "first %d pairs of the same workload, oracle/_ref/kaiju -z %d, %.1f s, index load excluded by differential" % (n_cpu, cores, dt),
