@@ -32,11 +32,12 @@ static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
     KjSmemLayout L; uint32_t o = 0;
     L.qkey_off = o; o += 8u * p.item_cap;
     L.kept_off = o; o += 16u * p.kept_cap_smem;
-    L.res_off = o; o += 16u * kj_align(p.max_frag + 1, 2);           // per-j chain results (greedy)
-    L.res2_off = o; o += 16u * kj_align(p.max_frag + 1, 2);          // recorded matches in class order (greedy)
+    const uint32_t g = p.mode == 1 ? 1u : 0u;                                 // greedy-only areas cost nothing in MEM mode
+    L.res_off = o; o += g * 16u * kj_align(p.max_frag + 1, 2);        // per-j chain results (greedy)
+    L.res2_off = o; o += g * 16u * kj_align(p.max_frag + 1, 2);       // recorded matches in class order (greedy)
     L.qpay_off = o; o += 4u * kj_align(p.item_cap, 2);
     L.ids_off = o; o += 4u * 24u;
-    L.pre_off = o; o += 2u * kj_align(p.max_frag + 2, 4);            // prefix sums of the BLOSUM62 diagonal (greedy)
+    L.pre_off = o; o += g * 2u * kj_align(p.max_frag + 2, 4);        // prefix sums of the BLOSUM62 diagonal (greedy)
     L.segs_off = o; o += 8u * KJ_SEG_CAP(p.max_frag);                     // {int begin,end}
     L.aa_stride = kj_align(p.max_len + 4, 8);
     L.aa_off = o; o += 4u * L.aa_stride;
@@ -68,38 +69,46 @@ static KJ_DEV void kj_flag_error(KjWarpCtx& cx, uint32_t bit) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// FM index primitives
+// FM index primitives.  IdxT = uint32_t for indexes with bwtlen < 2^32 (all interval arithmetic in 32 bit), uint64_t otherwise.
 // ---------------------------------------------------------------------------------------------
 static KJ_DEV KjRankBlock kj_ld_block(const KjRankBlock* p) {
 #if defined(KJ_EMU)
     return *p;
 #else
     KjRankBlock b;   // one 256-bit read-only load = exactly one 32-byte sector
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.cnt), "=l"(b.w0), "=l"(b.w1), "=l"(b.w2) : "l"(p));
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.hdr), "=l"(b.w0), "=l"(b.w1), "=l"(b.w2) : "l"(p));
     return b;
 #endif
 }
-// FMindex(f, c, k) = C[c] + rank_c(BWT[0..k))        (compactfmi.c:267-307)
-static KJ_DEV uint64_t kj_rank_in_block(const KjRankBlock& b, uint32_t r) {
-    uint32_t wi = r >> 6, bit = r & 63u;
-    uint64_t ww = wi == 0 ? b.w0 : (wi == 1 ? b.w1 : b.w2);
-    uint64_t n = b.cnt + (uint64_t)kj_popcll(ww & ((1ull << bit) - 1ull));
-    if (wi > 0) n += (uint64_t)kj_popcll(b.w0);
-    if (wi > 1) n += (uint64_t)kj_popcll(b.w1);
-    return n;
+// FMindex(f, c, k) = C[c] + rank_c(BWT[0..k))        (compactfmi.c:267-307): header count + prefix popcount byte + ONE popcount
+template <class IdxT>
+static KJ_DEV IdxT kj_rank_in_block(const KjRankBlock& b, uint32_t wi, uint32_t bit) {
+    const uint64_t ww = wi == 0 ? b.w0 : (wi == 1 ? b.w1 : b.w2);
+    const uint32_t h = (uint32_t)(b.hdr >> 32);
+    const uint32_t add = wi == 0 ? 0u : ((h >> (8u + 8u * wi)) & 0xffu);
+    const uint32_t pc = (uint32_t)kj_popcll(ww & ((1ull << bit) - 1ull));
+    if (sizeof(IdxT) == 4) return (IdxT)((uint32_t)b.hdr + add + pc);
+    return (IdxT)((b.hdr & KJ_CNT_MASK) + (uint64_t)(add + pc));
 }
-static KJ_DEV uint64_t kj_rank(const KjDevIndex& ix, uint32_t c, uint64_t k) {
-    uint64_t b = k / KJ_RANK_BLOCK; uint32_t r = (uint32_t)(k - b * KJ_RANK_BLOCK);
-    return kj_rank_in_block(kj_ld_block(ix.rank + (uint64_t)c * ix.nb + b), r);
+// position k -> (block, word in block, bit in word); k < 2^38 so k >> 6 fits 32 bits
+template <class IdxT>
+static KJ_DEV void kj_split(IdxT k, uint32_t& blk, uint32_t& wi, uint32_t& bit) {
+    const uint32_t q = (uint32_t)(k >> 6); blk = q / 3u; wi = q - 3u * blk; bit = (uint32_t)k & 63u;
+}
+template <class IdxT>
+static KJ_DEV IdxT kj_rank(const KjDevIndex& ix, uint32_t c, IdxT k) {
+    uint32_t blk, wi, bit; kj_split<IdxT>(k, blk, wi, bit);
+    return kj_rank_in_block<IdxT>(kj_ld_block(ix.rank + ((uint64_t)c * ix.nb + blk)), wi, bit);
 }
 // UpdateSI (bwt.c:160-173); the record is shared when both interval ends fall in one block
-static KJ_DEV bool kj_update_si(const KjDevIndex& ix, uint32_t c, uint64_t& lo, uint64_t& hi) {
-    uint64_t b0 = lo / KJ_RANK_BLOCK, b1 = hi / KJ_RANK_BLOCK;
+template <class IdxT>
+static KJ_DEV bool kj_update_si(const KjDevIndex& ix, uint32_t c, IdxT& lo, IdxT& hi) {
+    uint32_t b0, w0, t0, b1, w1, t1; kj_split<IdxT>(lo, b0, w0, t0); kj_split<IdxT>(hi, b1, w1, t1);
     const KjRankBlock* base = ix.rank + (uint64_t)c * ix.nb;
-    KjRankBlock B0 = kj_ld_block(base + b0);
-    uint64_t nlo = kj_rank_in_block(B0, (uint32_t)(lo - b0 * KJ_RANK_BLOCK)), nhi;
-    if (b1 == b0) nhi = kj_rank_in_block(B0, (uint32_t)(hi - b1 * KJ_RANK_BLOCK));
-    else { KjRankBlock B1 = kj_ld_block(base + b1); nhi = kj_rank_in_block(B1, (uint32_t)(hi - b1 * KJ_RANK_BLOCK)); }
+    const KjRankBlock B0 = kj_ld_block(base + b0);
+    const IdxT nlo = kj_rank_in_block<IdxT>(B0, w0, t0); IdxT nhi;
+    if (b1 == b0) nhi = kj_rank_in_block<IdxT>(B0, w1, t1);
+    else { const KjRankBlock B1 = kj_ld_block(base + b1); nhi = kj_rank_in_block<IdxT>(B1, w1, t1); }
     if (nlo >= nhi) return false;
     lo = nlo; hi = nhi; return true;
 }
@@ -111,16 +120,49 @@ static KJ_DEV uint32_t kj_letter(const KjDevIndex& ix, uint64_t k) {
 // get_suffix (bwt.c:105-121) reduced to the taxon of the sequence the suffix lies in
 static KJ_DEV uint32_t kj_sa_taxon(const KjDevIndex& ix, uint64_t k) {
     uint32_t c = 1;
-    while (c != 0 && (k & ix.sa_check)) { c = kj_letter(ix, k); k = kj_rank(ix, c, k); }
+    while (c != 0 && (k & ix.sa_check)) { c = kj_letter(ix, k); k = kj_rank<uint64_t>(ix, c, k); }
     if (c != 0) return ix.sa_tax[(uint64_t)((int64_t)(k >> ix.sa_exp) - ix.sa_bias)];
     return ix.seq_tax[k];
 }
-// one backward-search chain ending at j (inner loop of bwt.c:267-275 / 355-363): returns the match start
-static KJ_DEV int kj_chain(const KjDevIndex& ix, const uint8_t* frag, int j, uint64_t& lo, uint64_t& hi) {
-    uint32_t c = frag[j]; lo = ix.C[c]; hi = ix.C[c + 1];          // InitialSI (bwt.c:146-152)
-    int i = j;
-    while (i > 0) { if (!kj_update_si(ix, frag[i - 1], lo, hi)) break; i--; }
-    return i;
+
+// ---------------------------------------------------------------------------------------------
+// Backward-search chains (the inner loops of greedyExact / maxMatches, bwt.c:267-275, 355-363).
+// One lane owns the chain of one end position j.  A chain is run in two phases so that the many chains that die
+// after ~log20(N) letters are handled at full warp width and only real matches are followed to their end:
+//   phase A: k-mer table look-up (first k letters in one access; exactness-preserving because callers only use
+//            chains with l >= Lmin >= k, and for j >= k an empty k-mer interval implies a match start >= 2, so the
+//            `i<=1` break cannot be affected) followed by a few single steps, all lanes together;
+//   phase B: the surviving chains are completed a few at a time in descending j, replaying the reference's
+//            sequential rules (growing L, `if (i<=1) break`) between groups.
+// ---------------------------------------------------------------------------------------------
+#define KJ_PHASE_A_LETTERS 9      // letters matched in phase A (k-mer + single steps)
+#define KJ_GROUP_MEM 4            // chains completed together in phase B (MEM)
+template <class IdxT> struct KjChain { IdxT lo, hi; int i; bool done; };
+
+template <class IdxT>
+static KJ_DEV void kj_chain_start(const KjDevIndex& ix, const uint8_t* frag, int j, uint32_t Lmin, KjChain<IdxT>& ch) {
+    const int k = ix.kmer_k; int i = j; int budget = KJ_PHASE_A_LETTERS - 1;
+    ch.done = false;
+    if (k > 0 && j >= k && Lmin >= (uint32_t)k) {
+        uint32_t idx = 0;
+        for (int t = 0; t < k; t++) idx = idx * 20u + (uint32_t)(frag[j - t] - 1u);
+        IdxT lo, hi;
+        if (sizeof(IdxT) == 4) { const KjKmer32 e = ((const KjKmer32*)ix.kmer)[idx]; lo = (IdxT)e.lo; hi = (IdxT)e.hi; }
+        else { const KjKmer e = ((const KjKmer*)ix.kmer)[idx]; lo = (IdxT)e.lo; hi = (IdxT)e.hi; }
+        if (lo >= hi) { ch.lo = 0; ch.hi = 0; ch.i = j + 1; ch.done = true; return; }       // failed inside the k-mer: length 0
+        ch.lo = lo; ch.hi = hi; i = j - k + 1; budget = KJ_PHASE_A_LETTERS - k;
+    } else {
+        const uint32_t c = frag[j]; ch.lo = (IdxT)ix.C[c]; ch.hi = (IdxT)ix.C[c + 1];      // InitialSI (bwt.c:146-152)
+    }
+    while (i > 0 && budget > 0) { if (!kj_update_si<IdxT>(ix, frag[i - 1], ch.lo, ch.hi)) { ch.done = true; break; } i--; budget--; }
+    if (i == 0) ch.done = true;
+    ch.i = i;
+}
+template <class IdxT>
+static KJ_DEV void kj_chain_finish(const KjDevIndex& ix, const uint8_t* frag, KjChain<IdxT>& ch) {
+    int i = ch.i;
+    while (i > 0) { if (!kj_update_si<IdxT>(ix, frag[i - 1], ch.lo, ch.hi)) break; i--; }
+    ch.i = i; ch.done = true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -223,17 +265,30 @@ struct KjSeg { int begin, end; };
 #define KJ_SEG_UPSET 7        // window - downset
 #define KJ_SEG_MAXTRIM 50
 
-// entropy class of every 12-window: bit0 = H <= locut, bit1 = H <= hicut   (s_SeqEntropy/s_Entropy, 1596-1798)
-static KJ_DEV void kj_seg_flags(KjWarpCtx& cx, int n) {
+// entropy class of every 12-window: bit0 = H <= locut, bit1 = H <= hicut   (s_SeqEntropy/s_Entropy, 1596-1798).
+// A window with >= 8 distinct residues has H >= 2.617 > hicut (checked on the host over all partitions), so only the
+// rare low-diversity windows need the composition count.  Returns whether any window can trigger SEG at all.
+static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
     const uint8_t* frag = cx.smem + cx.L.frag_off; uint8_t* hf = cx.smem + cx.L.hflag_off; const KjTables& tb = *cx.tb;
-    for (int p = cx.w.lane; p + KJ_SEG_WINDOW <= n; p += 32) {
-        uint64_t c_lo = 0, c_hi = 0;                         // 4-bit counters for letters 1..16 / 17..20 (max count 12)
-        for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; if (a < 16u) c_lo += 1ull << (4u * a); else c_hi += 1ull << (4u * (a - 16u)); }
-        int32_t x = 0;
-        for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; uint32_t c = a < 16u ? (uint32_t)(c_lo >> (4u * a)) & 15u : (uint32_t)(c_hi >> (4u * (a - 16u))) & 15u; x += tb.seg_logfix[c]; }
-        hf[p] = (uint8_t)((x <= tb.seg_locut_fix ? 1 : 0) | (x <= tb.seg_hicut_fix ? 2 : 0));
+    bool any_low = false;
+    for (int p0 = 0; p0 + KJ_SEG_WINDOW <= n; p0 += 32) {
+        const int p = p0 + cx.w.lane; uint32_t flags = 0;
+        if (p + KJ_SEG_WINDOW <= n) {
+            uint32_t seen = 0;
+            for (int t = 0; t < KJ_SEG_WINDOW; t++) seen |= 1u << frag[p + t];
+            if (kj_popc(seen) < 8) {
+                uint64_t c_lo = 0, c_hi = 0;                     // 4-bit counters for letters 1..16 / 17..20 (max count 12)
+                for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; if (a < 16u) c_lo += 1ull << (4u * a); else c_hi += 1ull << (4u * (a - 16u)); }
+                int32_t x = 0;
+                for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; uint32_t c = a < 16u ? (uint32_t)(c_lo >> (4u * a)) & 15u : (uint32_t)(c_hi >> (4u * (a - 16u))) & 15u; x += tb.seg_logfix[c]; }
+                flags = (x <= tb.seg_locut_fix ? 1u : 0u) | (x <= tb.seg_hicut_fix ? 2u : 0u);
+            }
+            hf[p] = (uint8_t)flags;
+        }
+        any_low = cx.w.any((flags & 1u) != 0) || any_low;
     }
     cx.w.sync();
+    return any_low;
 }
 
 // s_Trim (blast_seg.c:1971-2015): the sub-window of s[0..n2) with minimal s_GetProb; first in
@@ -329,7 +384,7 @@ static KJ_DEV int kj_seg_level(KjWarpCtx& cx, int s0, int n, KjSeg* segs, int ns
 static KJ_DEV int kj_seg(KjWarpCtx& cx, int n) {
     KjSeg* segs = (KjSeg*)(cx.smem + cx.L.segs_off);
     if (n < KJ_SEG_WINDOW) return 0;
-    kj_seg_flags(cx, n);
+    if (!kj_seg_flags(cx, n)) return 0;                      // no window at or below locut: s_SegSeq cannot trigger
     int ns = kj_seg_level<0>(cx, 0, n, segs, 0);
     cx.w.sync();
     if (ns > 1) {
@@ -412,8 +467,6 @@ static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
 // ---------------------------------------------------------------------------------------------
 // MEM mode  (classify_length, ConsumerThread.cpp:543-628, with greedyExact, bwt.c:347-380)
 // ---------------------------------------------------------------------------------------------
-#define KJ_ROUND_SMALL 4        // chains launched first per fragment (a full-length hit ends the fragment at once)
-#define KJ_LONG_MATCH 14        // a round that saw a match this long keeps the rounds small
 
 // SEG gate of getNextFragment (ConsumerThread.cpp:285-339): returns true if the item was split (pieces pushed)
 static KJ_DEV bool kj_seg_gate(KjWarpCtx& cx, KjQueue& q, uint32_t arr, uint32_t start, uint32_t len, bool greedy) {
@@ -435,6 +488,7 @@ static KJ_DEV bool kj_seg_gate(KjWarpCtx& cx, KjQueue& q, uint32_t arr, uint32_t
     return true;
 }
 
+template <class IdxT>
 static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best_out) {
     const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix; const KjRunParams& rp = *cx.rp;
     const uint8_t* frag = cx.smem + cx.L.frag_off;
@@ -444,31 +498,39 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
         const uint32_t arr = pay >> 30, start = (pay >> 14) & 0x7fffu, len = pay & 0x3fffu; const bool segchecked = (pay >> 29) & 1u;
         kj_load_frag(cx, arr, start, len);
         if (rp.seg && !segchecked && kj_seg_gate(cx, q, arr, start, len, false)) continue;
-        // greedyExact(f, seq, len, max(m,longest), -1): chains for j = len-1 .. L-1, L growing
+        // greedyExact(f, seq, len, max(m,longest), -1) (bwt.c:347-380): chains for j = len-1 .. L-1, L growing
         uint32_t L = rp.m > longest ? rp.m : longest;
         uint32_t item_best = 0, item_cnt = 0;                             // uniform
-        int jhi = (int)len - 1; bool small_round = true;
-        while (jhi >= (int)L - 1) {
-            int nj = jhi - ((int)L - 1) + 1; const int G = small_round ? KJ_ROUND_SMALL : 32; if (nj > G) nj = G;
-            const int j = jhi - w.lane; const bool act = w.lane < nj;
-            uint64_t lo = 0, hi = 0; int i = 0;
-            if (act) i = kj_chain(ix, frag, j, lo, hi);
+        bool broke = false;
+        for (int jhi = (int)len - 1; !broke && jhi >= (int)L - 1; jhi -= 32) {
+            const int j = jhi - w.lane; const bool act = j >= (int)L - 1;
+            KjChain<IdxT> ch; ch.lo = 0; ch.hi = 0; ch.i = 0; ch.done = true;
+            if (act) kj_chain_start<IdxT>(ix, frag, j, rp.m, ch);                         // phase A
             w.sync();
-            uint32_t l = act ? (uint32_t)(j - i + 1) : 0u;
-            // `if (i<=1) break` (bwt.c:376): lanes below the first lane that reached i<=1 were never run by the reference
-            uint32_t brk = w.ballot(act && i <= 1);
-            const int cut = brk ? kj_ffs(brk) - 1 : 31;
-            const bool valid = act && w.lane <= cut;
-            uint32_t lmax = warp_max_u32(w, valid ? l : 0u);
-            if (lmax >= L) {
-                if (lmax > item_best) { item_best = lmax; item_cnt = 0; L = lmax; }
-                uint32_t wm = w.ballot(valid && l == item_best);
-                if (valid && l == item_best) { KjKept* k = kj_kept_ptr(cx, nkept + item_cnt + (uint32_t)kj_popc(wm & lanemask_lt(w.lane))); k->lo = lo; k->len = (uint32_t)(hi - lo); k->aux = 0; }
+            uint32_t Lc = L; bool valid = false;
+            for (;;) {                                                                      // phase B
+                // `if (i<=1) break` (bwt.c:376): lanes below the first finished lane with i<=1 were never run by the reference
+                const uint32_t brk = w.ballot(act && ch.done && ch.i <= 1);
+                const int cut = brk ? kj_ffs(brk) - 1 : 31; broke = brk != 0;
+                valid = act && w.lane <= cut;
+                const uint32_t ldone = (valid && ch.done) ? (uint32_t)(j - ch.i + 1) : 0u;
+                const uint32_t lmax = warp_max_u32(w, ldone);
+                Lc = lmax > L ? lmax : L;                                                   // L after the finished chains
+                const bool elig = valid && !ch.done && j >= (int)Lc - 1;                    // the j-loop bound with the grown L
+                const uint32_t em = w.ballot(elig);
+                if (!em) break;
+                if (elig && kj_popc(em & lanemask_lt(w.lane)) < KJ_GROUP_MEM) kj_chain_finish<IdxT>(ix, frag, ch);
+                w.sync();
+            }
+            const uint32_t l = (valid && ch.done) ? (uint32_t)(j - ch.i + 1) : 0u;
+            if (Lc >= L && warp_max_u32(w, l) >= L) {
+                const uint32_t lmax = Lc;
+                if (lmax > item_best) { item_best = lmax; item_cnt = 0; }
+                L = lmax;
+                const uint32_t wm = w.ballot(l == item_best && l > 0);
+                if (l == item_best && l > 0) { KjKept* k = kj_kept_ptr(cx, nkept + item_cnt + (uint32_t)kj_popc(wm & lanemask_lt(w.lane))); k->lo = (uint64_t)ch.lo; k->len = (uint32_t)(ch.hi - ch.lo); k->aux = 0; }
                 item_cnt += (uint32_t)kj_popc(wm);
             }
-            small_round = lmax >= KJ_LONG_MATCH;
-            if (brk) break;
-            jhi -= nj;
         }
         w.sync();
         if (item_cnt > 0) {
@@ -504,9 +566,9 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
 // ConsumerThread::doWork for one item (ConsumerThread.cpp:630-749): gates, translation, mode dispatch.
 // Returns the compact taxon (KJ_TAX_BAD = unclassified).
 // ---------------------------------------------------------------------------------------------
-static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int n2, uint32_t& best_out);
+template <class IdxT> static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int n2, uint32_t& best_out);
 
-template <int MODE>
+template <int MODE, class IdxT>
 static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1, const uint8_t* s2, int n2, bool paired, uint32_t& best_out) {
     const KjRunParams& rp = *cx.rp;
     best_out = 0;
@@ -518,6 +580,6 @@ static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1
     const bool greedy = MODE == 1;
     if (n1 >= m3) kj_translate_mate(cx, q, 0, s1, n1, greedy);            // a short mate is skipped individually (699, 705)
     if (paired && n2 >= m3) kj_translate_mate(cx, q, 1, s2, n2, greedy);
-    if (MODE == 0) return kj_classify_mem(cx, q, best_out);
-    else return kj_classify_greedy(cx, q, n1, paired ? n2 : 0, best_out);
+    if (MODE == 0) return kj_classify_mem<IdxT>(cx, q, best_out);
+    else return kj_classify_greedy<IdxT>(cx, q, n1, paired ? n2 : 0, best_out);
 }

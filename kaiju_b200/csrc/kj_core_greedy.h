@@ -47,6 +47,7 @@ static KJ_DEV uint32_t kj_scan_incl(const Warp& w, uint32_t v) {
     return v;
 }
 
+template <class IdxT>
 static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int n2, uint32_t& best_out) {
     const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix; const KjRunParams& rp = *cx.rp; const KjTables& tb = *cx.tb;
     uint8_t* frag = cx.smem + cx.L.frag_off;
@@ -108,32 +109,36 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
         if (num_mm > 0) {
             // maxMatches_withStart (bwt.c:298-336): extend the stored interval leftwards from len - matchlen; all lanes
             // run the same chain (identical addresses coalesce into one sector per step)
-            uint64_t lo = si0, hi = si1; int i = (int)len - (int)matchlen;
-            while (i > 0) { if (!kj_update_si(ix, frag[i - 1], lo, hi)) break; i--; }
+            IdxT lo = (IdxT)si0, hi = (IdxT)si1; int i = (int)len - (int)matchlen;
+            while (i > 0) { if (!kj_update_si<IdxT>(ix, frag[i - 1], lo, hi)) break; i--; }
             uint32_t l = len - (uint32_t)i;
             uint32_t Lreq = (num_mm == rp.e) ? rp.m : matchlen;           // ConsumerThread.cpp:445-450
-            if (l >= Lreq) { if (w.lane == 0) { cls[0].lo = lo; cls[0].len = (uint32_t)(hi - lo); cls[0].qi = (uint16_t)i; cls[0].ql = (uint16_t)l; } nrec = 1; }
+            if (l >= Lreq) { if (w.lane == 0) { cls[0].lo = (uint64_t)lo; cls[0].len = (uint32_t)(hi - lo); cls[0].qi = (uint16_t)i; cls[0].ql = (uint16_t)l; } nrec = 1; }
             w.sync();
         } else {
             // maxMatches(f, seq, len, seed_length, 0) (bwt.c:261-296): one chain per end position j
             const int L = (int)rp.seed_length;
-            int jhi = (int)len - 1, jlow = (int)len;                       // processed range [jlow, len-1]
-            bool small_round = true;
-            while (jhi >= L - 1) {
-                int nj = jhi - (L - 1) + 1; const int G = small_round ? KJ_ROUND_SMALL : 32; if (nj > G) nj = G;
-                const int j = jhi - w.lane; const bool act = w.lane < nj;
-                uint64_t lo = 0, hi = 0; int i = 0;
-                if (act) i = kj_chain(ix, frag, j, lo, hi);
+            int jlow = (int)len; bool broke = false, first_group = true;          // processed range [jlow, len-1]
+            for (int jhi = (int)len - 1; !broke && jhi >= L - 1; jhi -= 32) {
+                const int j = jhi - w.lane; const bool act = j >= L - 1;
+                KjChain<IdxT> ch; ch.lo = 0; ch.hi = 0; ch.i = 0; ch.done = true;
+                if (act) kj_chain_start<IdxT>(ix, frag, j, rp.seed_length, ch);
                 w.sync();
-                uint32_t brk = w.ballot(act && i <= 1);                    // `if (i<=1) break` (bwt.c:292)
-                const int cut = brk ? kj_ffs(brk) - 1 : 31;
-                const bool valid = act && w.lane <= cut;
-                if (valid) { res[j].lo = lo; res[j].len = (uint32_t)(hi - lo); res[j].qi = (uint16_t)i; res[j].ql = (uint16_t)(j - i + 1); }
-                int nvalid = brk ? cut + 1 : nj;
-                jlow = jhi - nvalid + 1;
-                small_round = false;
-                if (brk) break;
-                jhi -= nj;
+                bool valid = false; int cut = 31;
+                for (;;) {
+                    const uint32_t brk = w.ballot(act && ch.done && ch.i <= 1);    // `if (i<=1) break` (bwt.c:292)
+                    cut = brk ? kj_ffs(brk) - 1 : 31; broke = brk != 0;
+                    valid = act && w.lane <= cut;
+                    const bool elig = valid && !ch.done;                            // every chain above the break is needed
+                    const uint32_t em = w.ballot(elig);
+                    if (!em) break;
+                    const int G = first_group ? 4 : 32; first_group = false;        // a full-length hit ends the fragment after 4 chains
+                    if (elig && kj_popc(em & lanemask_lt(w.lane)) < G) kj_chain_finish<IdxT>(ix, frag, ch);
+                    w.sync();
+                }
+                if (valid) { res[j].lo = (uint64_t)ch.lo; res[j].len = (uint32_t)(ch.hi - ch.lo); res[j].qi = (uint16_t)ch.i; res[j].ql = (uint16_t)(j - ch.i + 1); }
+                const int nact = (jhi - (L - 1) + 1) < 32 ? (jhi - (L - 1) + 1) : 32;
+                jlow = jhi - (broke ? cut + 1 : nact) + 1;
             }
             w.sync();
             // recorded matches: l >= L and start strictly left of the previously recorded one (bwt.c:276-281);
@@ -184,8 +189,8 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
                         const bool pass = lane_sub && after >= (int)best && after >= (int)rp.min_score;
                         const uint32_t failmask = ~w.ballot(pass) & 0x7ffffu;
                         const int n_ok = failmask ? kj_ffs(failmask) - 1 : 19;      // first failing substitute ends the loop (391)
-                        uint64_t lo = sm.lo, hi = sm.lo + sm.len; bool ok = false;
-                        if (w.lane < n_ok) ok = kj_update_si(ix, sub, lo, hi);
+                        IdxT lo = (IdxT)sm.lo, hi = (IdxT)(sm.lo + sm.len); bool ok = false;
+                        if (w.lane < n_ok) ok = kj_update_si<IdxT>(ix, sub, lo, hi);
                         w.sync();
                         const uint32_t okmask = w.ballot(ok); const uint32_t cnt = (uint32_t)kj_popc(okmask);
                         if (cnt) {
@@ -202,7 +207,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
                                 }
                                 if (ok) {
                                     V->subs[ns] = (uint16_t)((pos << 5) | sub);
-                                    V->lo = lo; V->hi = hi; V->pay = kj_qpay(arr, true, start, new_len);
+                                    V->lo = (uint64_t)lo; V->hi = (uint64_t)hi; V->pay = kj_qpay(arr, true, start, new_len);
                                     V->diff = diff + (int)tb.b62[o][sub] - (int)tb.b62[sub][sub];
                                     V->matchlen = (uint16_t)(sm.ql + 1u); V->num_mm = (uint8_t)(ns + 1u); V->pad = 0; V->pad2 = 0;
                                     V->key = kj_qkey((uint32_t)after, KJ_ORDER_LATE + q.late + rk);

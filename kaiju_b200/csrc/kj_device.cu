@@ -25,7 +25,7 @@
 
 struct KjCtaShared { KjDevIndex ix; KjTables tb; };
 
-template <int MODE>
+template <int MODE, class IdxT>
 __global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32)
 kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ KjRunParams rp,
                    const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
@@ -62,7 +62,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
         const uint64_t a0 = off1[r] - base1, a1 = off1[r + 1] - base1;
         uint64_t b0 = 0, b1 = 0; if (paired) { b0 = off2[r] - base2; b1 = off2[r + 1] - base2; }
         uint32_t best = 0;
-        uint32_t t = kj_classify_item<MODE>(cx, seq1 + a0, (int)(a1 - a0), paired ? seq2 + b0 : nullptr, (int)(b1 - b0), paired, best);
+        uint32_t t = kj_classify_item<MODE, IdxT>(cx, seq1 + a0, (int)(a1 - a0), paired ? seq2 + b0 : nullptr, (int)(b1 - b0), paired, best);
         if (cx.w.lane == 0) {
             uint64_t id = t == KJ_TAX_BAD ? 0ull : sh->ix.tax_id[t];
             taxon_out[r] = id;
@@ -86,7 +86,7 @@ struct kj_ctx {
     KjDevIndex dix{};              // host copy of the descriptor (device pointers inside)
     KjDevIndex* d_ix = nullptr; KjTables* d_tables = nullptr;
     void* d_rank = nullptr; void* d_letters = nullptr; void* d_sa_tax = nullptr; void* d_seq_tax = nullptr;
-    void* d_tax_parent = nullptr; void* d_tax_depth = nullptr; void* d_tax_id = nullptr; void* d_lnfact = nullptr;
+    void* d_tax_parent = nullptr; void* d_tax_depth = nullptr; void* d_tax_id = nullptr; void* d_lnfact = nullptr; void* d_kmer = nullptr;
     uint64_t index_bytes = 0;
     // run state
     unsigned long long* d_counter = nullptr; uint32_t* d_err = nullptr; unsigned int* d_maxlen = nullptr;
@@ -114,13 +114,11 @@ static int configure_launch(kj_ctx* c, const KjRunParams& rp, size_t& smem, int&
     if (smem > 227 * 1024) { kj_err() = "per-CTA shared memory exceeds 227 KB (reads too long / -m too small)"; return KJ_ERR_UNSUPPORTED; }
     if (smem == c->smem_bytes && c->grid > 0 && c->cfg_mode == rp.mode) { grid = c->grid; return KJ_OK; }
     int per_sm = 0;
-    if (rp.mode == 0) {
-        CK(cudaFuncSetAttribute(kj_classify_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<0>, KJ_WARPS_PER_CTA * 32, smem));
-    } else {
-        CK(cudaFuncSetAttribute(kj_classify_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<1>, KJ_WARPS_PER_CTA * 32, smem));
-    }
+#define KJ_CFG(M, T) { CK(cudaFuncSetAttribute(kj_classify_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<M, T>, KJ_WARPS_PER_CTA * 32, smem)); }
+    if (rp.mode == 0) { if (c->H.wide) KJ_CFG(0, uint64_t) else KJ_CFG(0, uint32_t) }
+    else { if (c->H.wide) KJ_CFG(1, uint64_t) else KJ_CFG(1, uint32_t) }
+#undef KJ_CFG
     c->cfg_mode = rp.mode;
     if (per_sm < 1) { kj_err() = "kernel does not fit on an SM"; return KJ_ERR_UNSUPPORTED; }
     grid = c->sm_count * per_sm;             // persistent grid: a whole number of CTAs per SM
@@ -164,7 +162,7 @@ extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, cons
     KjHostIndex& H = c->H; uint64_t tot = 0;
     if ((rc = upload(H.rank, &c->d_rank, tot)) || (rc = upload(H.letters, &c->d_letters, tot)) || (rc = upload(H.sa_tax, &c->d_sa_tax, tot)) ||
         (rc = upload(H.seq_tax, &c->d_seq_tax, tot)) || (rc = upload(H.tax_parent, &c->d_tax_parent, tot)) || (rc = upload(H.tax_depth, &c->d_tax_depth, tot)) ||
-        (rc = upload(H.tax_id, &c->d_tax_id, tot)) || (rc = upload(H.lnfact, &c->d_lnfact, tot))) { kj_destroy(c); return rc; }
+        (rc = upload(H.tax_id, &c->d_tax_id, tot)) || (rc = upload(H.lnfact, &c->d_lnfact, tot)) || (rc = (H.wide ? upload(H.kmer, &c->d_kmer, tot) : upload(H.kmer32, &c->d_kmer, tot)))) { kj_destroy(c); return rc; }
     CK(cudaMalloc((void**)&c->d_tables, sizeof(KjTables))); CK(cudaMemcpy(c->d_tables, &H.tables, sizeof(KjTables), cudaMemcpyHostToDevice));
     KjDevIndex& D = c->dix; memset(&D, 0, sizeof D);
     D.rank = (const KjRankBlock*)c->d_rank; D.nb = H.nb; D.letters = (const uint64_t*)c->d_letters; D.bwtlen = H.bwtlen; D.alen = H.alen;
@@ -172,11 +170,11 @@ extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, cons
     D.sa_tax = (const uint32_t*)c->d_sa_tax; D.seq_tax = (const uint32_t*)c->d_seq_tax; D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
     D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
     D.tax_parent = (const uint32_t*)c->d_tax_parent; D.tax_depth = (const uint32_t*)c->d_tax_depth; D.tax_id = (const uint64_t*)c->d_tax_id; D.n_tax = (uint32_t)H.tax_id.size();
-    D.lnfact = (const double*)c->d_lnfact; D.n_lnfact = (int)H.lnfact.size(); D.kmer = nullptr; D.kmer_k = 0; D.tables = c->d_tables;
+    D.lnfact = (const double*)c->d_lnfact; D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? c->d_kmer : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = c->d_tables;
     CK(cudaMalloc((void**)&c->d_ix, sizeof(KjDevIndex))); CK(cudaMemcpy(c->d_ix, &D, sizeof(KjDevIndex), cudaMemcpyHostToDevice));
     c->index_bytes = tot;
     // host copies of the big arrays are no longer needed
-    std::vector<KjRankBlock>().swap(H.rank); std::vector<uint64_t>().swap(H.letters); std::vector<uint32_t>().swap(H.sa_tax);
+    std::vector<KjRankBlock>().swap(H.rank); std::vector<uint64_t>().swap(H.letters); std::vector<uint32_t>().swap(H.sa_tax); std::vector<KjKmer>().swap(H.kmer); std::vector<KjKmer32>().swap(H.kmer32);
     CK(cudaMalloc((void**)&c->d_counter, 2 * sizeof(unsigned long long))); CK(cudaMalloc((void**)&c->d_err, sizeof(uint32_t))); CK(cudaMalloc((void**)&c->d_maxlen, 2 * sizeof(unsigned int)));
     CK(cudaMemset(c->d_err, 0, sizeof(uint32_t)));
     for (int s = 0; s < 2; s++) CK(cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking));
@@ -194,7 +192,7 @@ extern "C" int kj_set_params(kj_ctx* c, const kj_params* p) {
 extern "C" void kj_destroy(kj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    void* ptrs[] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_tax_parent, c->d_tax_depth, c->d_tax_id, c->d_lnfact, c->d_tables, c->d_ix,
+    void* ptrs[] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_tax_parent, c->d_tax_depth, c->d_tax_id, c->d_lnfact, c->d_kmer, c->d_tables, c->d_ix,
                     c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evtab, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
                     c->d_seq[0][0], c->d_seq[0][1], c->d_seq[1][0], c->d_seq[1][1], c->d_off[0][0], c->d_off[0][1], c->d_off[1][0], c->d_off[1][1]};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -215,14 +213,12 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
     if (time_it) CK(cudaEventRecord(c->ev_a, st));
     const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
-    if (rp.mode == 0)
-        kj_classify_kernel<0><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best,
-            c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries,
-            c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), c->d_err);
-    else
-        kj_classify_kernel<1><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best,
-            c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries,
-            c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), c->d_err);
+#define KJ_LAUNCH(M, T) kj_classify_kernel<M, T><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, \
+            c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
+            c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), c->d_err)
+    if (rp.mode == 0) { if (c->H.wide) KJ_LAUNCH(0, uint64_t); else KJ_LAUNCH(0, uint32_t); }
+    else { if (c->H.wide) KJ_LAUNCH(1, uint64_t); else KJ_LAUNCH(1, uint32_t); }
+#undef KJ_LAUNCH
     CK(cudaGetLastError());
     if (time_it) CK(cudaEventRecord(c->ev_b, st));
     c->launches++;

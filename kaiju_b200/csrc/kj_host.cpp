@@ -141,6 +141,7 @@ int build_tables(const std::string& alphabet, KjTables& tb) {
             for (int i = 0; i < n; i++) { ent += ((double)part[i]) * log(((double)part[i]) / 12.0) / 0.69314718055994530941723212145818; x += (int64_t)part[i] * tb.seg_logfix[part[i]]; }
             ent = fabs(ent / 12.0);
             if ((ent <= 2.2) != (x <= tb.seg_locut_fix) || (ent > 2.5) != (x > tb.seg_hicut_fix)) ok = false;
+            if (n >= 8 && !(ent > 2.5)) ok = false;          // the kernel's >= 8 distinct residues shortcut
             return;
         }
         for (int p = std::min(left, maxp); p >= 1; p--) { part[n] = p; go(left - p, p, part, n + 1, tb, ok); }
@@ -201,7 +202,7 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
         uint64_t e = std::min(n, (c + 1) * CH);
         for (uint64_t b0 = c * CH; b0 < e; b0 += KJ_RANK_BLOCK) {
             uint64_t b = b0 / KJ_RANK_BLOCK, be = std::min(n, b0 + KJ_RANK_BLOCK);
-            for (int a = 0; a < alen; a++) H.rank[(size_t)a * nb + b].cnt = run[a];
+            for (int a = 0; a < alen; a++) H.rank[(size_t)a * nb + b].hdr = run[a];
             for (uint64_t k = b0; k < be; k++) {
                 uint32_t a = lcode[v.bwt[k]], r = (uint32_t)(k - b0); KjRankBlock& B = H.rank[(size_t)a * nb + b];
                 (r < 64 ? B.w0 : r < 128 ? B.w1 : B.w2) |= 1ull << (r & 63);
@@ -211,7 +212,15 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
         for (uint64_t k = c * CH; k < e; k++) H.letters[k / KJ_LETTERS_PER_WORD] |= (uint64_t)lcode[v.bwt[k]] << (5 * (k % KJ_LETTERS_PER_WORD));
     });
     // the record after the last letter (k == bwtlen lands there when bwtlen % 192 == 0; otherwise the last partial block already exists)
-    if (n % KJ_RANK_BLOCK == 0) for (int a = 0; a < alen; a++) H.rank[(size_t)a * nb + (nb - 1)].cnt = H.C[a] + total[a];
+    if (n % KJ_RANK_BLOCK == 0) for (int a = 0; a < alen; a++) H.rank[(size_t)a * nb + (nb - 1)].hdr = H.C[a] + total[a];
+    if (n >= (1ull << 47)) { kj_err() = "index too large"; return KJ_ERR_UNSUPPORTED; }
+    H.wide = (n >= 0xffffff00ull || getenv("KJ_FORCE_WIDE")) ? 1 : 0;     // KJ_FORCE_WIDE: exercise the 64-bit kernels on small test indexes
+    {   // fold the in-block prefix popcounts into the header
+        std::vector<std::thread> th; const size_t tot = (size_t)alen * nb;
+        for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] { for (size_t i = tI; i < tot; i += nthr) { KjRankBlock& B = H.rank[i];
+            uint64_t p1 = (uint64_t)__builtin_popcountll(B.w0), p2 = p1 + (uint64_t)__builtin_popcountll(B.w1); B.hdr = (B.hdr & KJ_CNT_MASK) | (p1 << 48) | (p2 << 56); } });
+        for (auto& x : th) x.join();
+    }
 
     // ---- taxonomy re-indexing
     std::unordered_map<uint64_t, uint64_t> par_of; par_of.reserve((size_t)t.n * 2 + 16);
@@ -273,11 +282,46 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
         for (auto& x : th) x.join();
         if (bad) { kj_err() = "corrupt suffix array (sequence number out of range)"; return KJ_ERR_IO; }
     }
+    { const char* ek = getenv("KJ_KMER_K"); kj_build_kmer_table(H, ek ? atoi(ek) : 5); }
     // ---- ln(n!) exactly as the reference's literals (blast_seg.c:53-1306 are "%.6f" prints of lgamma)
     H.lnfact.resize(256);
     for (int i = 0; i < 256; i++) { char b[64]; snprintf(b, sizeof b, "%.6f", lgamma((double)i + 1.0)); H.lnfact[(size_t)i] = strtod(b, nullptr); }
     H.lnfact[0] = H.lnfact[1] = 0.0;
     return KJ_OK;
+}
+
+// host-side rank on the device layout (used only to fill the k-mer table)
+static inline uint64_t host_rank(const KjHostIndex& H, uint32_t c, uint64_t k) {
+    uint64_t b = k / KJ_RANK_BLOCK; uint32_t r = (uint32_t)(k - b * KJ_RANK_BLOCK); const KjRankBlock& B = H.rank[(size_t)c * H.nb + b];
+    uint32_t wi = r >> 6, bit = r & 63u; uint64_t ww = wi == 0 ? B.w0 : (wi == 1 ? B.w1 : B.w2);
+    uint64_t add = wi == 0 ? 0 : ((B.hdr >> (40 + 8 * wi)) & 0xff);
+    return (B.hdr & KJ_CNT_MASK) + add + (uint64_t)__builtin_popcountll(ww & ((1ull << bit) - 1ull));
+}
+// index = a0*20^(k-1) + a1*20^(k-2) + ... + a(k-1), a_t = letter consumed t-th by the backward search (end of the k-mer first), letters 1..20 -> 0..19
+void kj_build_kmer_table(KjHostIndex& H, int k) {
+    H.kmer.clear(); H.kmer32.clear(); H.kmer_k = 0;
+    if (k < 2 || k > 6 || H.alen != 21) return;
+    std::vector<KjKmer> cur(20), nxt;
+    for (uint32_t a = 0; a < 20; a++) { cur[a].lo = H.C[a + 1]; cur[a].hi = H.C[a + 2]; }
+    unsigned nthr = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    for (int d = 1; d < k; d++) {
+        nxt.assign(cur.size() * 20, KjKmer{0, 0});
+        std::vector<std::thread> th; const size_t n = cur.size();
+        for (unsigned t = 0; t < nthr; t++) th.emplace_back([&, t] {
+            for (size_t i = t; i < n; i += nthr) {
+                const KjKmer iv = cur[i];
+                for (uint32_t a = 0; a < 20; a++) {
+                    KjKmer o{0, 0};
+                    if (iv.lo < iv.hi) { o.lo = host_rank(H, a + 1, iv.lo); o.hi = host_rank(H, a + 1, iv.hi); if (o.lo >= o.hi) { o.lo = 0; o.hi = 0; } }
+                    nxt[i * 20 + a] = o;
+                }
+            }
+        });
+        for (auto& x : th) x.join();
+        cur.swap(nxt);
+    }
+    if (H.wide) H.kmer.swap(cur); else { H.kmer32.resize(cur.size()); for (size_t i = 0; i < cur.size(); i++) { H.kmer32[i].lo = (uint32_t)cur[i].lo; H.kmer32[i].hi = (uint32_t)cur[i].hi; } }
+    H.kmer_k = k;
 }
 
 void kj_build_evalue_table(const kj_params& p, double db_length, uint32_t max1, uint32_t max2, std::vector<uint16_t>& tab) {

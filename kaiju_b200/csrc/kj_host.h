@@ -25,12 +25,15 @@ struct KjHostIndex {
     uint64_t sa_check = 0; int sa_exp = 0; int64_t sa_bias = 0; uint32_t nseq = 0;
     std::vector<uint32_t> tax_parent, tax_depth; std::vector<uint64_t> tax_id;
     std::vector<double> lnfact;
+    std::vector<KjKmer> kmer; std::vector<KjKmer32> kmer32; int kmer_k = 0; int wide = 0;   // k-mer suffix intervals (letters 1..20)
     KjTables tables;
     double db_length = 0;          // bwt.len - bwt.nseq (Config.cpp:20)
 };
 
 std::string& kj_err();             // thread-local last error text
 int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHostIndex& out);
+// SA intervals of all 20^k k-mers over the 20 residue letters (exactness-preserving shortcut for the first k LF steps)
+void kj_build_kmer_table(KjHostIndex& H, int k);
 int kj_check_params(const kj_params& p);
 // E-value gate (ConsumerThread.cpp:500-513) as the minimal passing integer score per (len1,len2)
 void kj_build_evalue_table(const kj_params& p, double db_length, uint32_t max1, uint32_t max2, std::vector<uint16_t>& tab);

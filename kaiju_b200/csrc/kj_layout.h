@@ -7,8 +7,9 @@
 // so the device uses its own layout, built at load time from the decoded letters:
 //
 //   rank[c][b] : one 32-byte record per (letter c, block b of 192 BWT positions)
-//                { cnt = C[c] + #{p < 192 b : L[p] == c},  w0,w1,w2 = one-hot bitmap of L[p]==c }
-//                -> FMindex(c,k) touches exactly ONE 32-byte DRAM sector:  cnt + popc(bits below k).
+//                { hdr = C[c] + #{p < 192 b : L[p] == c} (48 bit) + the popcounts of w0 and w0|w1 (2 x 8 bit),
+//                  w0,w1,w2 = one-hot bitmap of L[p]==c }
+//                -> FMindex(c,k) touches exactly ONE 32-byte DRAM sector and needs ONE 64-bit popcount.
 //   letters    : the decoded BWT packed 12 letters (5 bit) per 64-bit word, read only by the SA walk.
 //   sa_tax     : the sampled suffix array reduced to what classification needs -- the (compact) taxon of
 //                the sequence each sampled suffix belongs to (bwt/suffixArray.h:47-51 + ConsumerThread.cpp:812-832).
@@ -27,9 +28,12 @@
 #define KJ_MAX_MM 8                // max supported -e
 #define KJ_SEG_WINDOW 12
 
-struct alignas(32) KjRankBlock { uint64_t cnt, w0, w1, w2; };
+// hdr = cnt (48 bit: C[c] + #c before the block) | popc(w0) << 48 | (popc(w0)+popc(w1)) << 56 ; w0..w2 = one-hot bitmap
+struct alignas(32) KjRankBlock { uint64_t hdr, w0, w1, w2; };
+#define KJ_CNT_MASK 0xffffffffffffull
 
-struct KjKmer { uint64_t lo, hi; };  // SA interval of a k-mer (empty if lo >= hi)
+struct KjKmer { uint64_t lo, hi; };    // SA interval of a k-mer (empty if lo >= hi), indexes >= 2^32
+struct KjKmer32 { uint32_t lo, hi; };  // same, for indexes with bwtlen < 2^32
 
 struct KjTables {
     uint8_t codon_aa[64];            // (n0<<4|n1<<2|n2) -> alphabet index, 0 = stop  (ConsumerThread.cpp:117-181 + sequence.c:68-97)
@@ -48,7 +52,8 @@ struct KjDevIndex {
     uint64_t sa_check; int sa_exp; int64_t sa_bias; uint64_t n_sa; uint32_t nseq;
     const uint32_t* tax_parent; const uint32_t* tax_depth; const uint64_t* tax_id; uint32_t n_tax;
     const double* lnfact; int n_lnfact;
-    const KjKmer* kmer; int kmer_k;             // optional direct-address table of k-mer intervals (0 = off)
+    const void* kmer; int kmer_k;               // direct-address table of k-mer intervals (KjKmer32 if !wide else KjKmer; 0 = off)
+    int wide;                                   // 1 if bwtlen >= 2^32 (64-bit interval arithmetic in the kernels)
     const KjTables* tables;
 };
 

@@ -123,7 +123,9 @@ static void item_body(kjemu::Sched* s, int lane, void* a) {
     KjWarpCtx cx; cx.w.lane = lane; cx.w.s = s; cx.ix = &A->c->D; cx.rp = A->rp; cx.tb = &A->c->H.tables; cx.smem = A->smem;
     cx.L = kj_smem_layout(*A->rp); cx.spill = A->spill; cx.gscratch = A->gscratch; cx.err = A->err;
     uint32_t best = 0;
-    uint32_t t = A->rp->mode == 0 ? kj_classify_item<0>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best) : kj_classify_item<1>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best);
+    const bool wide = A->c->D.wide != 0;
+    uint32_t t = A->rp->mode == 0 ? (wide ? kj_classify_item<0, uint64_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best) : kj_classify_item<0, uint32_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best))
+        : wide ? kj_classify_item<1, uint64_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best) : kj_classify_item<1, uint32_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best);
     A->tax[lane] = t; A->best[lane] = best;
 }
 
@@ -142,7 +144,7 @@ void* kjemu_create(const char* fmi_path, const char* nodes_path, const kj_params
     D.sa_tax = H.sa_tax.data(); D.seq_tax = H.seq_tax.data(); D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
     D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
     D.tax_parent = H.tax_parent.data(); D.tax_depth = H.tax_depth.data(); D.tax_id = H.tax_id.data(); D.n_tax = (uint32_t)H.tax_id.size();
-    D.lnfact = H.lnfact.data(); D.n_lnfact = (int)H.lnfact.size(); D.kmer = nullptr; D.kmer_k = 0; D.tables = &H.tables;
+    D.lnfact = H.lnfact.data(); D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? (H.wide ? (const void*)H.kmer.data() : (const void*)H.kmer32.data()) : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = &H.tables;
     return c;
 }
 void kjemu_destroy(void* h) { delete (EmuCtx*)h; }

@@ -116,3 +116,19 @@ def test_properties_at_scale(kb, fresh):
     assert np.array_equal(otax, tax[sub]) and np.array_equal(obest, best[sub])
     assert 0.55 < (tax != 0).mean() < 0.85          # ~70 % of the synthetic reads come from the DB
     clf.close()
+
+
+def test_wide_index_kernels_and_no_kmer_table(kb, golden, monkeypatch):
+    """The 64-bit-interval kernels (indexes >= 2^32 rows) and the table-free chain start, forced on the small golden index."""
+    names, s1, o1, s2, o2 = golden.reads("pe150")
+    for env in ({"KJ_FORCE_WIDE": "1"}, {"KJ_KMER_K": "0"}, {"KJ_KMER_K": "3"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for cfg in ("mem_default", "greedy_default"):
+            clf = kb.Classifier(golden.fmi, golden.nodes, device=0, params=kb_params(kb, GOLDEN_CONFIGS[cfg]))
+            tax, best = clf.classify(s1, o1, s2, o2)
+            etax, ebest, _ = golden.expected(cfg, "pe150")
+            assert np.array_equal(tax, etax) and np.array_equal(best, ebest), (env, cfg)
+            clf.close()
+        for k in env:
+            monkeypatch.delenv(k)
