@@ -71,44 +71,39 @@ static KJ_DEV void kj_flag_error(KjWarpCtx& cx, uint32_t bit) {
 // ---------------------------------------------------------------------------------------------
 // FM index primitives.  IdxT = uint32_t for indexes with bwtlen < 2^32 (all interval arithmetic in 32 bit), uint64_t otherwise.
 // ---------------------------------------------------------------------------------------------
-static KJ_DEV KjRankBlock kj_ld_block(const KjRankBlock* p) {
+static KJ_DEV uint64_t kj_ld64(const void* p) {
 #if defined(KJ_EMU)
-    return *p;
+    return *(const uint64_t*)p;
 #else
-    KjRankBlock b;   // one 256-bit read-only load = exactly one 32-byte sector
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.hdr), "=l"(b.w0), "=l"(b.w1), "=l"(b.w2) : "l"(p));
-    return b;
+    uint64_t v; asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v;
 #endif
-}
-// FMindex(f, c, k) = C[c] + rank_c(BWT[0..k))        (compactfmi.c:267-307): header count + prefix popcount byte + ONE popcount
-template <class IdxT>
-static KJ_DEV IdxT kj_rank_in_block(const KjRankBlock& b, uint32_t wi, uint32_t bit) {
-    const uint64_t ww = wi == 0 ? b.w0 : (wi == 1 ? b.w1 : b.w2);
-    const uint32_t h = (uint32_t)(b.hdr >> 32);
-    const uint32_t add = wi == 0 ? 0u : ((h >> (8u + 8u * wi)) & 0xffu);
-    const uint32_t pc = (uint32_t)kj_popcll(ww & ((1ull << bit) - 1ull));
-    if (sizeof(IdxT) == 4) return (IdxT)((uint32_t)b.hdr + add + pc);
-    return (IdxT)((b.hdr & KJ_CNT_MASK) + (uint64_t)(add + pc));
 }
 // position k -> (block, word in block, bit in word); k < 2^38 so k >> 6 fits 32 bits
 template <class IdxT>
 static KJ_DEV void kj_split(IdxT k, uint32_t& blk, uint32_t& wi, uint32_t& bit) {
     const uint32_t q = (uint32_t)(k >> 6); blk = q / 3u; wi = q - 3u * blk; bit = (uint32_t)k & 63u;
 }
+// FMindex(f, c, k) = C[c] + rank_c(BWT[0..k))        (compactfmi.c:267-307) for one end of an interval:
+// header (count + in-block prefix bytes) and the ONE bitmap word holding row k -- two 8-byte loads from the same
+// 32-byte sector, one 64-bit popcount, no data-dependent branches.  `base` = records of letter c.
 template <class IdxT>
-static KJ_DEV IdxT kj_rank(const KjDevIndex& ix, uint32_t c, IdxT k) {
+static KJ_DEV IdxT kj_rank_at(const KjRankBlock* base, IdxT k) {
     uint32_t blk, wi, bit; kj_split<IdxT>(k, blk, wi, bit);
-    return kj_rank_in_block<IdxT>(kj_ld_block(ix.rank + ((uint64_t)c * ix.nb + blk)), wi, bit);
+    const uint8_t* rec = (const uint8_t*)(base + blk);
+    const uint64_t hdr = kj_ld64(rec);
+    const uint64_t ww = kj_ld64(rec + 8u + 8u * wi);
+    const uint32_t pc = (uint32_t)kj_popcll(ww & ((1ull << bit) - 1ull));
+    if (sizeof(IdxT) == 4) return (IdxT)((uint32_t)hdr + (((uint32_t)(hdr >> 32) >> (8u * wi)) & 0xffu) + pc);   // byte 4 of hdr is 0 below 2^32 rows
+    const uint32_t add = wi == 0 ? 0u : ((uint32_t)(hdr >> (32u + 8u * wi)) & 0xffu);
+    return (IdxT)((hdr & KJ_CNT_MASK) + (uint64_t)(add + pc));
 }
-// UpdateSI (bwt.c:160-173); the record is shared when both interval ends fall in one block
+template <class IdxT>
+static KJ_DEV IdxT kj_rank(const KjDevIndex& ix, uint32_t c, IdxT k) { return kj_rank_at<IdxT>(ix.rank + (uint64_t)c * ix.nb, k); }
+// UpdateSI (bwt.c:160-173)
 template <class IdxT>
 static KJ_DEV bool kj_update_si(const KjDevIndex& ix, uint32_t c, IdxT& lo, IdxT& hi) {
-    uint32_t b0, w0, t0, b1, w1, t1; kj_split<IdxT>(lo, b0, w0, t0); kj_split<IdxT>(hi, b1, w1, t1);
     const KjRankBlock* base = ix.rank + (uint64_t)c * ix.nb;
-    const KjRankBlock B0 = kj_ld_block(base + b0);
-    const IdxT nlo = kj_rank_in_block<IdxT>(B0, w0, t0); IdxT nhi;
-    if (b1 == b0) nhi = kj_rank_in_block<IdxT>(B0, w1, t1);
-    else { const KjRankBlock B1 = kj_ld_block(base + b1); nhi = kj_rank_in_block<IdxT>(B1, w1, t1); }
+    const IdxT nlo = kj_rank_at<IdxT>(base, lo), nhi = kj_rank_at<IdxT>(base, hi);
     if (nlo >= nhi) return false;
     lo = nlo; hi = nhi; return true;
 }
@@ -136,7 +131,8 @@ static KJ_DEV uint32_t kj_sa_taxon(const KjDevIndex& ix, uint64_t k) {
 //            sequential rules (growing L, `if (i<=1) break`) between groups.
 // ---------------------------------------------------------------------------------------------
 #define KJ_PHASE_A_LETTERS 9      // letters matched in phase A (k-mer + single steps)
-#define KJ_GROUP_MEM 4            // chains completed together in phase B (MEM)
+#define KJ_GROUP_FIRST 2          // chains completed first in phase B: a full-length hit (i<=1) or a long match usually ends the fragment
+#define KJ_GROUP_NEXT 8           // then this many at a time (issue slots, not DRAM, are the scarce resource: see profiles/)
 template <class IdxT> struct KjChain { IdxT lo, hi; int i; bool done; };
 
 template <class IdxT>
@@ -217,35 +213,52 @@ static KJ_DEV void kj_translate_mate(KjWarpCtx& cx, KjQueue& q, int mate, const 
     uint8_t* aaF = cx.smem + cx.L.aa_off + (uint32_t)(2 * mate) * cx.L.aa_stride;
     uint8_t* aaR = aaF + cx.L.aa_stride;
     const int na = n - 2;
-    for (int count = w.lane; count < na; count += 32) {
-        uint32_t c0 = kj_nuc(seq[count]), c1 = kj_nuc(seq[count + 1]), c2 = kj_nuc(seq[count + 2]);
-        bool ok = (c0 | c1 | c2) < 4u;
-        aaF[count] = ok ? tb.codon_aa[c0 << 4 | c1 << 2 | c2] : (uint8_t)0;
-        aaR[na - 1 - count] = ok ? tb.codon_aa[(3u - c2) << 4 | (3u - c1) << 2 | (3u - c0)] : (uint8_t)0;
-    }
-    w.sync();
-    // lanes 0..5 = (strand, residue class of the array index); all lanes walk the same trip count
-    const uint32_t m = cx.rp->m;
-    const int strand = w.lane / 3, r = w.lane % 3;
-    const bool mine = w.lane < 6;
-    const uint32_t arr = (uint32_t)(2 * mate + strand);
-    const uint8_t* A = strand ? aaR : aaF;
-    uint32_t run_start = 0, run_len = 0, run_score = 0;
-    for (int idx0 = 0; idx0 < na; idx0 += 3) {
-        int idx = idx0 + r; bool valid = mine && idx < na;
-        uint32_t a = valid ? A[idx] : 1u;
-        bool stop = valid && a == 0;
-        bool emit = stop && run_len >= m && (!greedy || run_score >= cx.rp->min_score);
-        kj_queue_emit(cx, q, emit, greedy ? run_score : run_len, (arr << 16) | (uint32_t)idx, kj_qpay(arr, false, run_start, run_len));
-        if (valid) {
-            if (stop) { run_len = 0; run_score = 0; }
-            else { if (run_len == 0) run_start = (uint32_t)idx; run_len++; run_score += (uint32_t)tb.b62[a][a]; }
+    // 30 codon positions per pass: every lane decodes ONE base, its two successors come from the next lanes
+    for (int b = 0; b < na; b += 30) {
+        const int pos = b + w.lane;
+        const uint32_t c0 = pos < n ? kj_nuc(seq[pos]) : 4u;
+        const uint32_t c1 = w.shfl(c0, w.lane + 1), c2 = w.shfl(c0, w.lane + 2);
+        if (w.lane < 30 && pos < na) {
+            const bool ok = (c0 | c1 | c2) < 4u;
+            aaF[pos] = ok ? tb.codon_aa[c0 << 4 | c1 << 2 | c2] : (uint8_t)0;
+            aaR[na - 1 - pos] = ok ? tb.codon_aa[(3u - c2) << 4 | (3u - c1) << 2 | (3u - c0)] : (uint8_t)0;
         }
     }
-    // leftovers in frame order 0,1,2 where frame = count % 3 in FORWARD coordinates (ConsumerThread.cpp:219-232, 256-268)
-    int frame = strand ? (((n - 3 - r) % 3) + 3) % 3 : r;
-    bool emit = mine && run_len >= m && (!greedy || run_score >= cx.rp->min_score);
-    kj_queue_emit(cx, q, emit, greedy ? run_score : run_len, (arr << 16) | (40000u + (uint32_t)frame), kj_qpay(arr, false, run_start, run_len));
+    w.sync();
+    // fragments = maximal stop-free runs of every frame (a stride-3 walk of an array).  Per frame the stop positions
+    // become a bit mask (ballot), so each lane finds "am I the last residue of a run, and where does it start" with bit
+    // operations instead of a serial scan.  Insertion order (ConsumerThread.cpp:196-268): runs closed by a stop in scan
+    // order of that stop; leftovers afterwards in frame order 0,1,2 where frame = count % 3 in FORWARD coordinates.
+    const uint32_t m = cx.rp->m;
+    for (int strand = 0; strand < 2; strand++) {
+        const uint8_t* A = strand ? aaR : aaF; const uint32_t arr = (uint32_t)(2 * mate + strand);
+        for (int r = 0; r < 3; r++) {
+            const int nelem = (na - r + 2) / 3;                          // elements e: array index r + 3e
+            for (int e0 = 0; e0 < nelem; e0 += 32) {
+                const int e = e0 + w.lane; const bool in = e < nelem;
+                const bool stop = in && A[r + 3 * e] == 0;
+                const uint32_t sm = w.ballot(stop);                       // stops of this 32-element chunk
+                // a run ends at e if e is a residue and e+1 is a stop or the end; runs crossing chunk borders are
+                // resolved by looking at the neighbouring elements directly
+                const bool is_res = in && !stop;
+                const bool next_stop = (e + 1 >= nelem) || (w.lane < 31 ? ((sm >> (w.lane + 1)) & 1u) != 0 : A[r + 3 * (e + 1)] == 0);
+                const bool is_end = is_res && next_stop;
+                uint32_t run_start = 0, run_len = 0, run_score = 0;
+                if (is_end) {
+                    const uint32_t below = sm & lanemask_lt(w.lane);
+                    int s = below ? e0 + (32 - kj_clz(below)) : e0;       // first element after the previous stop in this chunk
+                    if (!below) { while (s > 0 && A[r + 3 * (s - 1)] != 0) s--; }   // run started in an earlier chunk
+                    run_start = (uint32_t)(r + 3 * s); run_len = (uint32_t)(e - s + 1);
+                    if (greedy && run_len >= m) for (int t = s; t <= e; t++) { const uint32_t a = A[r + 3 * t]; run_score += (uint32_t)tb.b62[a][a]; }
+                }
+                const bool leftover = e + 1 >= nelem;
+                const int frame = strand ? (((n - 3 - r) % 3) + 3) % 3 : r;
+                const uint32_t order = (arr << 16) | (leftover ? 40000u + (uint32_t)frame : (uint32_t)(r + 3 * (e + 1)));
+                const bool emit = is_end && run_len >= m && (!greedy || run_score >= cx.rp->min_score);
+                kj_queue_emit(cx, q, emit, greedy ? run_score : run_len, order, kj_qpay(arr, false, run_start, run_len));
+            }
+        }
+    }
 }
 
 // copy the characters of item (arr,start,len) into the contiguous fragment buffer
@@ -507,7 +520,7 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
             KjChain<IdxT> ch; ch.lo = 0; ch.hi = 0; ch.i = 0; ch.done = true;
             if (act) kj_chain_start<IdxT>(ix, frag, j, rp.m, ch);                         // phase A
             w.sync();
-            uint32_t Lc = L; bool valid = false;
+            uint32_t Lc = L; bool valid = false; int group = KJ_GROUP_FIRST;
             for (;;) {                                                                      // phase B
                 // `if (i<=1) break` (bwt.c:376): lanes below the first finished lane with i<=1 were never run by the reference
                 const uint32_t brk = w.ballot(act && ch.done && ch.i <= 1);
@@ -519,7 +532,8 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
                 const bool elig = valid && !ch.done && j >= (int)Lc - 1;                    // the j-loop bound with the grown L
                 const uint32_t em = w.ballot(elig);
                 if (!em) break;
-                if (elig && kj_popc(em & lanemask_lt(w.lane)) < KJ_GROUP_MEM) kj_chain_finish<IdxT>(ix, frag, ch);
+                if (elig && kj_popc(em & lanemask_lt(w.lane)) < group) kj_chain_finish<IdxT>(ix, frag, ch);
+                group = KJ_GROUP_NEXT;
                 w.sync();
             }
             const uint32_t l = (valid && ch.done) ? (uint32_t)(j - ch.i + 1) : 0u;

@@ -132,7 +132,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
                     const bool elig = valid && !ch.done;                            // every chain above the break is needed
                     const uint32_t em = w.ballot(elig);
                     if (!em) break;
-                    const int G = first_group ? 4 : 32; first_group = false;        // a full-length hit ends the fragment after 4 chains
+                    const int G = first_group ? KJ_GROUP_FIRST : 32; first_group = false;   // a full-length hit ends the fragment after the first group
                     if (elig && kj_popc(em & lanemask_lt(w.lane)) < G) kj_chain_finish<IdxT>(ix, frag, ch);
                     w.sync();
                 }

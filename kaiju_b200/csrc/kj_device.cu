@@ -19,6 +19,12 @@
 #include "kj_host.h"
 
 #define KJ_WARPS_PER_CTA 8
+#ifndef KJ_MIN_BLOCKS
+#define KJ_MIN_BLOCKS 4          // resident CTAs per SM the register allocation is tuned for (ncu: latency-bound, see profiles/)
+#endif
+#ifndef KJ_MIN_BLOCKS_GREEDY
+#define KJ_MIN_BLOCKS_GREEDY 3
+#endif
 #define KJ_CHUNK_READS (1u << 20)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { kj_err() = std::string(#call) + ": " + cudaGetErrorString(e_); return KJ_ERR_CUDA; } } while (0)
@@ -26,7 +32,7 @@
 struct KjCtaShared { KjDevIndex ix; KjTables tb; };
 
 template <int MODE, class IdxT>
-__global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32, MODE == 0 ? KJ_MIN_BLOCKS : KJ_MIN_BLOCKS_GREEDY)
 kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ KjRunParams rp,
                    const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
                    const uint8_t* __restrict__ seq2, const uint64_t* __restrict__ off2,

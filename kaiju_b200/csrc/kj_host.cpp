@@ -213,12 +213,12 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
     });
     // the record after the last letter (k == bwtlen lands there when bwtlen % 192 == 0; otherwise the last partial block already exists)
     if (n % KJ_RANK_BLOCK == 0) for (int a = 0; a < alen; a++) H.rank[(size_t)a * nb + (nb - 1)].hdr = H.C[a] + total[a];
-    if (n >= (1ull << 47)) { kj_err() = "index too large"; return KJ_ERR_UNSUPPORTED; }
+    if (n >= (1ull << 38)) { kj_err() = "index too large (>= 2^38 rows)"; return KJ_ERR_UNSUPPORTED; }
     H.wide = (n >= 0xffffff00ull || getenv("KJ_FORCE_WIDE")) ? 1 : 0;     // KJ_FORCE_WIDE: exercise the 64-bit kernels on small test indexes
     {   // fold the in-block prefix popcounts into the header
         std::vector<std::thread> th; const size_t tot = (size_t)alen * nb;
         for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] { for (size_t i = tI; i < tot; i += nthr) { KjRankBlock& B = H.rank[i];
-            uint64_t p1 = (uint64_t)__builtin_popcountll(B.w0), p2 = p1 + (uint64_t)__builtin_popcountll(B.w1); B.hdr = (B.hdr & KJ_CNT_MASK) | (p1 << 48) | (p2 << 56); } });
+            uint64_t p1 = (uint64_t)__builtin_popcountll(B.w0), p2 = p1 + (uint64_t)__builtin_popcountll(B.w1); B.hdr = (B.hdr & KJ_CNT_MASK) | (p1 << KJ_P1_SHIFT) | (p2 << KJ_P2_SHIFT); } });
         for (auto& x : th) x.join();
     }
 
@@ -294,7 +294,7 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
 static inline uint64_t host_rank(const KjHostIndex& H, uint32_t c, uint64_t k) {
     uint64_t b = k / KJ_RANK_BLOCK; uint32_t r = (uint32_t)(k - b * KJ_RANK_BLOCK); const KjRankBlock& B = H.rank[(size_t)c * H.nb + b];
     uint32_t wi = r >> 6, bit = r & 63u; uint64_t ww = wi == 0 ? B.w0 : (wi == 1 ? B.w1 : B.w2);
-    uint64_t add = wi == 0 ? 0 : ((B.hdr >> (40 + 8 * wi)) & 0xff);
+    uint64_t add = wi == 0 ? 0 : ((B.hdr >> (32 + 8 * wi)) & 0xff);
     return (B.hdr & KJ_CNT_MASK) + add + (uint64_t)__builtin_popcountll(ww & ((1ull << bit) - 1ull));
 }
 // index = a0*20^(k-1) + a1*20^(k-2) + ... + a(k-1), a_t = letter consumed t-th by the backward search (end of the k-mer first), letters 1..20 -> 0..19

@@ -7,7 +7,7 @@
 // so the device uses its own layout, built at load time from the decoded letters:
 //
 //   rank[c][b] : one 32-byte record per (letter c, block b of 192 BWT positions)
-//                { hdr = C[c] + #{p < 192 b : L[p] == c} (48 bit) + the popcounts of w0 and w0|w1 (2 x 8 bit),
+//                { hdr = C[c] + #{p < 192 b : L[p] == c} (40 bit) + the popcounts of w0 and w0|w1 (2 x 8 bit),
 //                  w0,w1,w2 = one-hot bitmap of L[p]==c }
 //                -> FMindex(c,k) touches exactly ONE 32-byte DRAM sector and needs ONE 64-bit popcount.
 //   letters    : the decoded BWT packed 12 letters (5 bit) per 64-bit word, read only by the SA walk.
@@ -28,9 +28,12 @@
 #define KJ_MAX_MM 8                // max supported -e
 #define KJ_SEG_WINDOW 12
 
-// hdr = cnt (48 bit: C[c] + #c before the block) | popc(w0) << 48 | (popc(w0)+popc(w1)) << 56 ; w0..w2 = one-hot bitmap
+// hdr = cnt (40 bit: C[c] + #c before the block) | popc(w0) << 40 | (popc(w0)+popc(w1)) << 48 ; w0..w2 = one-hot bitmap.
+// For indexes below 2^32 rows byte 4 is zero, so (hdr >> 32 >> 8*word) & 0xff is the in-block prefix for word 0,1,2 without a select.
 struct alignas(32) KjRankBlock { uint64_t hdr, w0, w1, w2; };
-#define KJ_CNT_MASK 0xffffffffffffull
+#define KJ_CNT_MASK 0xffffffffffull
+#define KJ_P1_SHIFT 40
+#define KJ_P2_SHIFT 48
 
 struct KjKmer { uint64_t lo, hi; };    // SA interval of a k-mer (empty if lo >= hi), indexes >= 2^32
 struct KjKmer32 { uint32_t lo, hi; };  // same, for indexes with bwtlen < 2^32

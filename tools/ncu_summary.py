@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (one profiled launch) into a small markdown file for profiles/: headline metrics from the raw
+page and the hottest source lines (instructions executed, stall samples) from the cuda,sass source page."""
+import csv, io, subprocess, sys
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
+
+
+def main():
+    rep, out, note = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    with open(out, "w") as f:
+        f.write("# ncu summary: %s\n\n%s\n\n" % (rep.split("/")[-1], note))
+        for vals in rows[2:]:
+            f.write("## launch: %s\n\n| metric | value | unit |\n|---|---|---|\n" % vals[hdr.index("Kernel Name")][:80])
+            for m in WANT:
+                if m in hdr:
+                    i = hdr.index(m); f.write("| %s | %s | %s |\n" % (m, vals[i], units[i]))
+            f.write("\n")
+        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
+        cur = "?"; h = None; lines = []
+        for r in csv.reader(io.StringIO(src)):
+            if len(r) >= 2 and "File" in r[0]:
+                cur = r[1]; continue
+            if len(r) > 5 and r[0] == "Line No":
+                h = r; continue
+            if h is None or len(r) < len(h) or not r[0].isdigit():
+                continue
+            ie = r[h.index("Instructions Executed")]; sm = r[h.index("# Samples")]; te = r[h.index("Thread Instructions Executed")]; ls = r[h.index("stall_long_sb")]
+            if ie.isdigit():
+                lines.append((int(ie), int(sm) if sm.isdigit() else 0, int(te) if te.isdigit() else 0, int(ls) if ls.isdigit() else 0, cur.split("/")[-1], int(r[0]), r[1].strip()[:100]))
+        tot = sum(x[0] for x in lines) or 1; ts = sum(x[1] for x in lines) or 1
+        f.write("## hottest source lines (share of warp instructions executed / of stall samples; active threads per instruction; long-scoreboard samples)\n\n")
+        f.write("| inst %% | samples %% | thr/inst | long_sb | location | source |\n|---|---|---|---|---|---|\n")
+        for x in sorted(lines, reverse=True)[:40]:
+            f.write("| %.1f | %.1f | %.1f | %d | %s:%d | `%s` |\n" % (100.0 * x[0] / tot, 100.0 * x[1] / ts, x[2] / max(x[0], 1), x[3], x[4], x[5], x[6].replace("|", "\\|")))
+
+
+if __name__ == "__main__":
+    main()
