@@ -98,11 +98,11 @@ static KJ_DEV IdxT kj_rank_at(const KjRankBlock* base, IdxT k) {
     return (IdxT)((hdr & KJ_CNT_MASK) + (uint64_t)(add + pc));
 }
 template <class IdxT>
-static KJ_DEV IdxT kj_rank(const KjDevIndex& ix, uint32_t c, IdxT k) { return kj_rank_at<IdxT>(ix.rank + (uint64_t)c * ix.nb, k); }
+static KJ_DEV IdxT kj_rank(const KjDevIndex& ix, uint32_t c, IdxT k) { return kj_rank_at<IdxT>(ix.rank_base[c], k); }
 // UpdateSI (bwt.c:160-173)
 template <class IdxT>
 static KJ_DEV bool kj_update_si(const KjDevIndex& ix, uint32_t c, IdxT& lo, IdxT& hi) {
-    const KjRankBlock* base = ix.rank + (uint64_t)c * ix.nb;
+    const KjRankBlock* base = ix.rank_base[c];
     const IdxT nlo = kj_rank_at<IdxT>(base, lo), nhi = kj_rank_at<IdxT>(base, hi);
     if (nlo >= nhi) return false;
     lo = nlo; hi = nhi; return true;
@@ -234,6 +234,7 @@ static KJ_DEV void kj_translate_mate(KjWarpCtx& cx, KjQueue& q, int mate, const 
         const uint8_t* A = strand ? aaR : aaF; const uint32_t arr = (uint32_t)(2 * mate + strand);
         for (int r = 0; r < 3; r++) {
             const int nelem = (na - r + 2) / 3;                          // elements e: array index r + 3e
+            int run_open = 0;                                            // first element after the last stop of the earlier chunks (uniform)
             for (int e0 = 0; e0 < nelem; e0 += 32) {
                 const int e = e0 + w.lane; const bool in = e < nelem;
                 const bool stop = in && A[r + 3 * e] == 0;
@@ -246,8 +247,7 @@ static KJ_DEV void kj_translate_mate(KjWarpCtx& cx, KjQueue& q, int mate, const 
                 uint32_t run_start = 0, run_len = 0, run_score = 0;
                 if (is_end) {
                     const uint32_t below = sm & lanemask_lt(w.lane);
-                    int s = below ? e0 + (32 - kj_clz(below)) : e0;       // first element after the previous stop in this chunk
-                    if (!below) { while (s > 0 && A[r + 3 * (s - 1)] != 0) s--; }   // run started in an earlier chunk
+                    const int s = below ? e0 + (32 - kj_clz(below)) : run_open;   // first element after the previous stop
                     run_start = (uint32_t)(r + 3 * s); run_len = (uint32_t)(e - s + 1);
                     if (greedy && run_len >= m) for (int t = s; t <= e; t++) { const uint32_t a = A[r + 3 * t]; run_score += (uint32_t)tb.b62[a][a]; }
                 }
@@ -256,6 +256,7 @@ static KJ_DEV void kj_translate_mate(KjWarpCtx& cx, KjQueue& q, int mate, const 
                 const uint32_t order = (arr << 16) | (leftover ? 40000u + (uint32_t)frame : (uint32_t)(r + 3 * (e + 1)));
                 const bool emit = is_end && run_len >= m && (!greedy || run_score >= cx.rp->min_score);
                 kj_queue_emit(cx, q, emit, greedy ? run_score : run_len, order, kj_qpay(arr, false, run_start, run_len));
+                if (sm) run_open = e0 + (32 - kj_clz(sm));
             }
         }
     }
@@ -283,19 +284,32 @@ struct KjSeg { int begin, end; };
 // rare low-diversity windows need the composition count.  Returns whether any window can trigger SEG at all.
 static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
     const uint8_t* frag = cx.smem + cx.L.frag_off; uint8_t* hf = cx.smem + cx.L.hflag_off; const KjTables& tb = *cx.tb;
-    bool any_low = false;
+    uint8_t* list = cx.smem + cx.L.segcnt_off;                  // low-diversity windows of the whole fragment (trim scratch is idle here)
+    uint32_t nlist = 0;                                          // uniform
     for (int p0 = 0; p0 + KJ_SEG_WINDOW <= n; p0 += 32) {
-        const int p = p0 + cx.w.lane; uint32_t flags = 0;
+        const int p = p0 + cx.w.lane; bool low_div = false;
         if (p + KJ_SEG_WINDOW <= n) {
             uint32_t seen = 0;
             for (int t = 0; t < KJ_SEG_WINDOW; t++) seen |= 1u << frag[p + t];
-            if (kj_popc(seen) < 8) {
-                uint64_t c_lo = 0, c_hi = 0;                     // 4-bit counters for letters 1..16 / 17..20 (max count 12)
-                for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; if (a < 16u) c_lo += 1ull << (4u * a); else c_hi += 1ull << (4u * (a - 16u)); }
-                int32_t x = 0;
-                for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; uint32_t c = a < 16u ? (uint32_t)(c_lo >> (4u * a)) & 15u : (uint32_t)(c_hi >> (4u * (a - 16u))) & 15u; x += tb.seg_logfix[c]; }
-                flags = (x <= tb.seg_locut_fix ? 1u : 0u) | (x <= tb.seg_hicut_fix ? 2u : 0u);
-            }
+            low_div = kj_popc(seen) < 8;
+            hf[p] = 0;
+        }
+        const uint32_t mk = cx.w.ballot(low_div);
+        if (low_div) list[nlist + (uint32_t)kj_popc(mk & lanemask_lt(cx.w.lane))] = (uint8_t)p;
+        nlist += (uint32_t)kj_popc(mk);
+    }
+    if (nlist == 0) return false;
+    cx.w.sync();
+    bool any_low = false;
+    for (uint32_t t0 = 0; t0 < nlist; t0 += 32) {                // the composition count runs once per fragment, lanes = flagged windows
+        const uint32_t t = t0 + (uint32_t)cx.w.lane; uint32_t flags = 0;
+        if (t < nlist) {
+            const int p = list[t];
+            uint64_t c_lo = 0, c_hi = 0;                         // 4-bit counters for letters 1..16 / 17..20 (max count 12)
+            for (int u = 0; u < KJ_SEG_WINDOW; u++) { uint32_t a = frag[p + u] - 1u; if (a < 16u) c_lo += 1ull << (4u * a); else c_hi += 1ull << (4u * (a - 16u)); }
+            int32_t x = 0;
+            for (int u = 0; u < KJ_SEG_WINDOW; u++) { uint32_t a = frag[p + u] - 1u; uint32_t c = a < 16u ? (uint32_t)(c_lo >> (4u * a)) & 15u : (uint32_t)(c_hi >> (4u * (a - 16u))) & 15u; x += tb.seg_logfix[c]; }
+            flags = (x <= tb.seg_locut_fix ? 1u : 0u) | (x <= tb.seg_hicut_fix ? 2u : 0u);
             hf[p] = (uint8_t)flags;
         }
         any_low = cx.w.any((flags & 1u) != 0) || any_low;

@@ -48,6 +48,7 @@ struct KjTables {
 
 struct KjDevIndex {
     const KjRankBlock* rank; uint64_t nb;       // [alen][nb]
+    const KjRankBlock* rank_base[KJ_MAX_ALEN];  // rank + c*nb per letter (saves the multiply in the inner loop)
     const uint64_t* letters;
     uint64_t bwtlen; int alen;
     uint64_t C[KJ_MAX_ALEN + 1];                // C[c] = first SA row of letter c; C[alen] = bwtlen
