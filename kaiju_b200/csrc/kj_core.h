@@ -68,6 +68,17 @@ static KJ_DEV void kj_flag_error(KjWarpCtx& cx, uint32_t bit) {
 #endif
 }
 
+// tunables (A/B-tested on the B200, see profiles/): the kernel is bound by the dependent-instruction latency of one warp,
+// not by issue slots or DRAM, so shorter dependence chains beat fewer instructions.
+#ifndef KJ_OPT_RANKBASE
+#define KJ_OPT_RANKBASE 1         // 1: per-letter record base from shared memory, 0: multiply            (A/B: 29.5 vs 28.7 M pairs/s)
+#endif
+#ifndef KJ_OPT_PAIRED
+#define KJ_OPT_PAIRED 0           // 1: two lanes per chain in phase B (half the instructions, +1 shuffle per step) (A/B: 26.6 vs 28.7)
+#endif
+#ifndef KJ_OPT_SEGCOMPACT
+#define KJ_OPT_SEGCOMPACT 0       // 1: low-diversity windows are compacted before the composition count  (A/B: 25.7 vs 28.7)
+#endif
 // ---------------------------------------------------------------------------------------------
 // FM index primitives.  IdxT = uint32_t for indexes with bwtlen < 2^32 (all interval arithmetic in 32 bit), uint64_t otherwise.
 // ---------------------------------------------------------------------------------------------
@@ -97,12 +108,19 @@ static KJ_DEV IdxT kj_rank_at(const KjRankBlock* base, IdxT k) {
     const uint32_t add = wi == 0 ? 0u : ((uint32_t)(hdr >> (32u + 8u * wi)) & 0xffu);
     return (IdxT)((hdr & KJ_CNT_MASK) + (uint64_t)(add + pc));
 }
+static KJ_DEV const KjRankBlock* kj_letter_base(const KjDevIndex& ix, uint32_t c) {
+#if KJ_OPT_RANKBASE
+    return ix.rank_base[c];
+#else
+    return ix.rank + (uint64_t)c * ix.nb;
+#endif
+}
 template <class IdxT>
-static KJ_DEV IdxT kj_rank(const KjDevIndex& ix, uint32_t c, IdxT k) { return kj_rank_at<IdxT>(ix.rank_base[c], k); }
+static KJ_DEV IdxT kj_rank(const KjDevIndex& ix, uint32_t c, IdxT k) { return kj_rank_at<IdxT>(kj_letter_base(ix, c), k); }
 // UpdateSI (bwt.c:160-173)
 template <class IdxT>
 static KJ_DEV bool kj_update_si(const KjDevIndex& ix, uint32_t c, IdxT& lo, IdxT& hi) {
-    const KjRankBlock* base = ix.rank_base[c];
+    const KjRankBlock* base = kj_letter_base(ix, c);
     const IdxT nlo = kj_rank_at<IdxT>(base, lo), nhi = kj_rank_at<IdxT>(base, hi);
     if (nlo >= nhi) return false;
     lo = nlo; hi = nhi; return true;
@@ -131,8 +149,14 @@ static KJ_DEV uint32_t kj_sa_taxon(const KjDevIndex& ix, uint64_t k) {
 //            sequential rules (growing L, `if (i<=1) break`) between groups.
 // ---------------------------------------------------------------------------------------------
 #define KJ_PHASE_A_LETTERS 9      // letters matched in phase A (k-mer + single steps)
-#define KJ_GROUP_FIRST 2          // chains completed first in phase B: a full-length hit (i<=1) or a long match usually ends the fragment
-#define KJ_GROUP_NEXT 8           // then this many at a time (issue slots, not DRAM, are the scarce resource: see profiles/)
+#ifndef KJ_GROUP_FIRST
+#define KJ_GROUP_FIRST 8            // (A/B: 29.0 with 8 vs 28.7 with 2; DRAM is at ~3 % of peak, speculation is cheap)
+#endif
+#ifndef KJ_GROUP_NEXT
+#define KJ_GROUP_NEXT 8
+#endif
+//      KJ_GROUP_FIRST            // chains completed first in phase B: a full-length hit (i<=1) or a long match usually ends the fragment
+//      KJ_GROUP_NEXT             // then this many at a time
 template <class IdxT> struct KjChain { IdxT lo, hi; int i; bool done; };
 
 template <class IdxT>
@@ -154,11 +178,48 @@ static KJ_DEV void kj_chain_start(const KjDevIndex& ix, const uint8_t* frag, int
     if (i == 0) ch.done = true;
     ch.i = i;
 }
+// Phase B with TWO lanes per chain: lane 2r computes the new lower end, lane 2r+1 the new upper end of chain r's interval
+// (one rank each instead of two), then they swap results.  `sel` = chains chosen for completion (<= 16); their state is
+// fetched from the owning lanes, completed by the pairs and handed back.  Halves the instructions issued per LF step.
+template <class IdxT>
+static KJ_DEV void kj_finish_paired(const Warp& w, const KjDevIndex& ix, const uint8_t* frag, uint32_t selmask, KjChain<IdxT>& ch) {
+    const int nsel = kj_popc(selmask);
+    const int r = w.lane >> 1; const bool mine = r < nsel;
+    const int owner = mine ? kj_fns(selmask, r) : 0;
+    IdxT lo = (IdxT)w.shfl64((uint64_t)ch.lo, owner), hi = (IdxT)w.shfl64((uint64_t)ch.hi, owner);
+    int i = w.shfl(ch.i, owner);
+    if (mine) {
+        const bool upper = (w.lane & 1) != 0;
+        while (i > 0) {
+            const IdxT mineval = kj_rank_at<IdxT>(kj_letter_base(ix, frag[i - 1]), upper ? hi : lo);
+            const IdxT other = (IdxT)w.pair_xchg64((uint64_t)mineval);
+            const IdxT nlo = upper ? other : mineval, nhi = upper ? mineval : other;
+            if (nlo >= nhi) break;
+            lo = nlo; hi = nhi; i--;
+        }
+    }
+    w.sync();
+    // hand the results back: owner lane = the (rank of owner in selmask)-th pair's even lane
+    const bool is_owner = (selmask >> w.lane) & 1u;
+    const int src = 2 * kj_popc(selmask & lanemask_lt(w.lane));
+    const IdxT rlo = (IdxT)w.shfl64((uint64_t)lo, src), rhi = (IdxT)w.shfl64((uint64_t)hi, src); const int ri = w.shfl(i, src);
+    if (is_owner) { ch.lo = rlo; ch.hi = rhi; ch.i = ri; ch.done = true; }
+}
 template <class IdxT>
 static KJ_DEV void kj_chain_finish(const KjDevIndex& ix, const uint8_t* frag, KjChain<IdxT>& ch) {
     int i = ch.i;
     while (i > 0) { if (!kj_update_si<IdxT>(ix, frag[i - 1], ch.lo, ch.hi)) break; i--; }
     ch.i = i; ch.done = true;
+}
+// complete the selected chains (one lane each, or a lane pair each)
+template <class IdxT>
+static KJ_DEV void kj_finish_selected(const Warp& w, const KjDevIndex& ix, const uint8_t* frag, bool sel, KjChain<IdxT>& ch) {
+#if KJ_OPT_PAIRED
+    kj_finish_paired<IdxT>(w, ix, frag, w.ballot(sel), ch);
+#else
+    if (sel) kj_chain_finish<IdxT>(ix, frag, ch);
+    w.sync();
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -282,6 +343,7 @@ struct KjSeg { int begin, end; };
 // entropy class of every 12-window: bit0 = H <= locut, bit1 = H <= hicut   (s_SeqEntropy/s_Entropy, 1596-1798).
 // A window with >= 8 distinct residues has H >= 2.617 > hicut (checked on the host over all partitions), so only the
 // rare low-diversity windows need the composition count.  Returns whether any window can trigger SEG at all.
+#if KJ_OPT_SEGCOMPACT
 static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
     const uint8_t* frag = cx.smem + cx.L.frag_off; uint8_t* hf = cx.smem + cx.L.hflag_off; const KjTables& tb = *cx.tb;
     uint8_t* list = cx.smem + cx.L.segcnt_off;                  // low-diversity windows of the whole fragment (trim scratch is idle here)
@@ -317,6 +379,30 @@ static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
     cx.w.sync();
     return any_low;
 }
+#else
+static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
+    const uint8_t* frag = cx.smem + cx.L.frag_off; uint8_t* hf = cx.smem + cx.L.hflag_off; const KjTables& tb = *cx.tb;
+    bool any_low = false;
+    for (int p0 = 0; p0 + KJ_SEG_WINDOW <= n; p0 += 32) {
+        const int p = p0 + cx.w.lane; uint32_t flags = 0;
+        if (p + KJ_SEG_WINDOW <= n) {
+            uint32_t seen = 0;
+            for (int t = 0; t < KJ_SEG_WINDOW; t++) seen |= 1u << frag[p + t];
+            if (kj_popc(seen) < 8) {
+                uint64_t c_lo = 0, c_hi = 0;                     // 4-bit counters for letters 1..16 / 17..20 (max count 12)
+                for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; if (a < 16u) c_lo += 1ull << (4u * a); else c_hi += 1ull << (4u * (a - 16u)); }
+                int32_t x = 0;
+                for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; uint32_t c = a < 16u ? (uint32_t)(c_lo >> (4u * a)) & 15u : (uint32_t)(c_hi >> (4u * (a - 16u))) & 15u; x += tb.seg_logfix[c]; }
+                flags = (x <= tb.seg_locut_fix ? 1u : 0u) | (x <= tb.seg_hicut_fix ? 2u : 0u);
+            }
+            hf[p] = (uint8_t)flags;
+        }
+        any_low = cx.w.any((flags & 1u) != 0) || any_low;
+    }
+    cx.w.sync();
+    return any_low;
+}
+#endif
 
 // s_Trim (blast_seg.c:1971-2015): the sub-window of s[0..n2) with minimal s_GetProb; first in
 // (len descending, start ascending) order wins ties.  One lane per window length, sliding start.
@@ -546,9 +632,9 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
                 const bool elig = valid && !ch.done && j >= (int)Lc - 1;                    // the j-loop bound with the grown L
                 const uint32_t em = w.ballot(elig);
                 if (!em) break;
-                if (elig && kj_popc(em & lanemask_lt(w.lane)) < group) kj_chain_finish<IdxT>(ix, frag, ch);
+                const bool sel = elig && kj_popc(em & lanemask_lt(w.lane)) < group;
+                kj_finish_selected<IdxT>(w, ix, frag, sel, ch);
                 group = KJ_GROUP_NEXT;
-                w.sync();
             }
             const uint32_t l = (valid && ch.done) ? (uint32_t)(j - ch.i + 1) : 0u;
             if (Lc >= L && warp_max_u32(w, l) >= L) {

@@ -107,10 +107,16 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
         // ---------------- search
         uint32_t nrec = 0;                                                // recorded matches (uniform)
         if (num_mm > 0) {
-            // maxMatches_withStart (bwt.c:298-336): extend the stored interval leftwards from len - matchlen; all lanes
-            // run the same chain (identical addresses coalesce into one sector per step)
-            IdxT lo = (IdxT)si0, hi = (IdxT)si1; int i = (int)len - (int)matchlen;
-            while (i > 0) { if (!kj_update_si<IdxT>(ix, frag[i - 1], lo, hi)) break; i--; }
+            // maxMatches_withStart (bwt.c:298-336): extend the stored interval leftwards from len - matchlen
+            // one chain: lanes 0/1 compute the lower/upper interval end (kj_finish_paired on a one-chain selection)
+            KjChain<IdxT> one; one.lo = (IdxT)si0; one.hi = (IdxT)si1; one.i = (int)len - (int)matchlen; one.done = false;
+#if KJ_OPT_PAIRED
+            kj_finish_paired<IdxT>(w, ix, frag, 1u, one);
+            const IdxT lo = (IdxT)w.shfl64((uint64_t)one.lo, 0), hi = (IdxT)w.shfl64((uint64_t)one.hi, 0); const int i = w.shfl(one.i, 0);
+#else
+            kj_chain_finish<IdxT>(ix, frag, one);                          // every lane runs the same chain: identical addresses, one sector per step
+            const IdxT lo = one.lo, hi = one.hi; const int i = one.i;
+#endif
             uint32_t l = len - (uint32_t)i;
             uint32_t Lreq = (num_mm == rp.e) ? rp.m : matchlen;           // ConsumerThread.cpp:445-450
             if (l >= Lreq) { if (w.lane == 0) { cls[0].lo = (uint64_t)lo; cls[0].len = (uint32_t)(hi - lo); cls[0].qi = (uint16_t)i; cls[0].ql = (uint16_t)l; } nrec = 1; }
@@ -132,9 +138,9 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
                     const bool elig = valid && !ch.done;                            // every chain above the break is needed
                     const uint32_t em = w.ballot(elig);
                     if (!em) break;
-                    const int G = first_group ? KJ_GROUP_FIRST : 32; first_group = false;   // a full-length hit ends the fragment after the first group
-                    if (elig && kj_popc(em & lanemask_lt(w.lane)) < G) kj_chain_finish<IdxT>(ix, frag, ch);
-                    w.sync();
+                    const int G = first_group ? KJ_GROUP_FIRST : 16; first_group = false;   // a full-length hit ends the fragment after the first group
+                    const bool sel = elig && kj_popc(em & lanemask_lt(w.lane)) < G;
+                    kj_finish_selected<IdxT>(w, ix, frag, sel, ch);
                 }
                 if (valid) { res[j].lo = (uint64_t)ch.lo; res[j].len = (uint32_t)(ch.hi - ch.lo); res[j].qi = (uint16_t)ch.i; res[j].ql = (uint16_t)(j - ch.i + 1); }
                 const int nact = (jhi - (L - 1) + 1) < 32 ? (jhi - (L - 1) + 1) : 32;
