@@ -76,6 +76,9 @@ static KJ_DEV void kj_flag_error(KjWarpCtx& cx, uint32_t bit) {
 #ifndef KJ_OPT_PAIRED
 #define KJ_OPT_PAIRED 0           // 1: two lanes per chain in phase B (half the instructions, +1 shuffle per step) (A/B: 26.6 vs 28.7)
 #endif
+#ifndef KJ_OPT_SEGPACKED
+#define KJ_OPT_SEGPACKED 1         // 1: window residues packed in 3 words, byte-compare counting on the low-diversity path
+#endif
 #ifndef KJ_OPT_SEGCOMPACT
 #define KJ_OPT_SEGCOMPACT 0       // 1: low-diversity windows are compacted before the composition count  (A/B: 25.7 vs 28.7)
 #endif
@@ -343,7 +346,38 @@ struct KjSeg { int begin, end; };
 // entropy class of every 12-window: bit0 = H <= locut, bit1 = H <= hicut   (s_SeqEntropy/s_Entropy, 1596-1798).
 // A window with >= 8 distinct residues has H >= 2.617 > hicut (checked on the host over all partitions), so only the
 // rare low-diversity windows need the composition count.  Returns whether any window can trigger SEG at all.
-#if KJ_OPT_SEGCOMPACT
+#if KJ_OPT_SEGPACKED
+// packed variant: the 12 residues of a window live in three 32-bit words; per distinct residue (<= 7 on the slow path)
+// the count is three byte-wise compares + popcounts instead of a 12-step nibble-counter loop
+static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
+    const uint8_t* frag = cx.smem + cx.L.frag_off; uint8_t* hf = cx.smem + cx.L.hflag_off; const KjTables& tb = *cx.tb;
+    bool any_low = false;
+    for (int p0 = 0; p0 + KJ_SEG_WINDOW <= n; p0 += 32) {
+        const int p = p0 + cx.w.lane; uint32_t flags = 0;
+        if (p + KJ_SEG_WINDOW <= n) {
+            const uint32_t* aw = (const uint32_t*)(frag + (p & ~3)); const uint32_t sh = (uint32_t)(p & 3) * 8u;
+            const uint32_t a0 = aw[0], a1 = aw[1], a2 = aw[2], a3 = aw[3];
+            const uint32_t w0 = kj_funnel_r(a0, a1, sh), w1 = kj_funnel_r(a1, a2, sh), w2 = kj_funnel_r(a2, a3, sh);
+            uint32_t seen = 0;
+            for (int t = 0; t < 4; t++) { seen |= 1u << ((w0 >> (8 * t)) & 0xffu); seen |= 1u << ((w1 >> (8 * t)) & 0xffu); seen |= 1u << ((w2 >> (8 * t)) & 0xffu); }
+            if (kj_popc(seen) < 8) {
+                int32_t x = 0;
+                while (seen) {
+                    const uint32_t a = (uint32_t)kj_ffs(seen) - 1u; seen &= seen - 1u;
+                    const uint32_t a4 = a * 0x01010101u;
+                    const uint32_t c = (uint32_t)(kj_popc(kj_vcmpeq4(w0, a4)) + kj_popc(kj_vcmpeq4(w1, a4)) + kj_popc(kj_vcmpeq4(w2, a4))) >> 3;
+                    x += (int32_t)c * tb.seg_logfix[c];
+                }
+                flags = (x <= tb.seg_locut_fix ? 1u : 0u) | (x <= tb.seg_hicut_fix ? 2u : 0u);
+            }
+            hf[p] = (uint8_t)flags;
+        }
+        any_low = cx.w.any((flags & 1u) != 0) || any_low;
+    }
+    cx.w.sync();
+    return any_low;
+}
+#elif KJ_OPT_SEGCOMPACT
 static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
     const uint8_t* frag = cx.smem + cx.L.frag_off; uint8_t* hf = cx.smem + cx.L.hflag_off; const KjTables& tb = *cx.tb;
     uint8_t* list = cx.smem + cx.L.segcnt_off;                  // low-diversity windows of the whole fragment (trim scratch is idle here)

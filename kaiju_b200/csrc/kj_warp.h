@@ -22,6 +22,8 @@ static inline int kj_popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int kj_popcll(uint64_t x) { return __builtin_popcountll(x); }
 static inline int kj_ffs(uint32_t x) { return __builtin_ffs((int)x); }
 static inline int kj_clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+static inline uint32_t kj_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31u)); }
+static inline uint32_t kj_vcmpeq4(uint32_t a, uint32_t b) { uint32_t r = 0; for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xffu) == ((b >> (8 * i)) & 0xffu)) r |= 0xffu << (8 * i); return r; }
 static inline double kj_dadd(double a, double b) { volatile double r = a + b; return r; }
 static inline double kj_dsub(double a, double b) { volatile double r = a - b; return r; }
 static inline double kj_dmul(double a, double b) { volatile double r = a * b; return r; }
@@ -52,6 +54,8 @@ static KJ_DEV int kj_popc(uint32_t x) { return __popc(x); }
 static KJ_DEV int kj_popcll(uint64_t x) { return __popcll(x); }
 static KJ_DEV int kj_ffs(uint32_t x) { return __ffs((int)x); }
 static KJ_DEV int kj_clz(uint32_t x) { return __clz((int)x); }
+static KJ_DEV uint32_t kj_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+static KJ_DEV uint32_t kj_vcmpeq4(uint32_t a, uint32_t b) { return __vcmpeq4(a, b); }
 // SEG's FP64 must round exactly like the reference's scalar x86 code: no FMA contraction.
 static KJ_DEV double kj_dadd(double a, double b) { return __dadd_rn(a, b); }
 static KJ_DEV double kj_dsub(double a, double b) { return __dsub_rn(a, b); }
