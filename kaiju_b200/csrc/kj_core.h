@@ -32,19 +32,25 @@ static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
     KjSmemLayout L; uint32_t o = 0;
     L.qkey_off = o; o += 8u * p.item_cap;
     L.kept_off = o; o += 16u * p.kept_cap_smem;
-    const uint32_t g = p.mode == 1 ? 1u : 0u;                                 // greedy-only areas cost nothing in MEM mode
-    L.res_off = o; o += g * 16u * kj_align(p.max_frag + 1, 2);        // per-j chain results (greedy)
-    L.res2_off = o; o += g * 16u * kj_align(p.max_frag + 1, 2);       // recorded matches in class order (greedy)
+    L.segs_off = o; o += 8u * KJ_SEG_CAP(p.max_frag);                     // {int begin,end}
     L.qpay_off = o; o += 4u * kj_align(p.item_cap, 2);
     L.ids_off = o; o += 4u * 24u;
-    L.pre_off = o; o += g * 2u * kj_align(p.max_frag + 2, 4);        // prefix sums of the BLOSUM62 diagonal (greedy)
-    L.segs_off = o; o += 8u * KJ_SEG_CAP(p.max_frag);                     // {int begin,end}
     L.aa_stride = kj_align(p.max_len + 4, 8);
     L.aa_off = o; o += 4u * L.aa_stride;
     L.frag_off = o; o += kj_align(p.max_frag + 8, 8);
     L.hflag_off = o; o += kj_align(p.max_frag + 8, 8);
-    L.segcnt_off = o; o += 20u * 32u;
-    L.seghist_off = o; o += kj_align((p.max_frag + 2) * 32u, 8);
+    // union: SEG trim scratch (alive inside getNextFragment's SEG gate) | greedy search arrays (alive after the gate)
+    const uint32_t u = o;
+    L.segcnt_off = u; L.seghist_off = u + 20u * 32u;
+    const uint32_t seg_bytes = 20u * 32u + kj_align((p.max_frag + 2) * 32u, 8);
+    uint32_t g_bytes = 0;
+    L.res_off = u; L.res2_off = u; L.pre_off = u;
+    if (p.mode == 1) {
+        L.res_off = u; g_bytes += 16u * kj_align(p.max_frag + 1, 2);           // per-j chain results
+        L.res2_off = u + g_bytes; g_bytes += 16u * kj_align(p.max_frag + 1, 2);  // recorded matches in class order
+        L.pre_off = u + g_bytes; g_bytes += 2u * kj_align(p.max_frag + 2, 4);    // prefix sums of the BLOSUM62 diagonal
+    }
+    o = u + (seg_bytes > g_bytes ? seg_bytes : g_bytes);
     L.total = kj_align(o, 16);
     return L;
 }

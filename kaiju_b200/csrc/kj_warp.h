@@ -43,6 +43,8 @@ struct Warp {
     KJ_DEV double shfl_d(double v, int src) const { uint64_t u; memcpy(&u, &v, 8); u = shfl64(u, src); memcpy(&v, &u, 8); return v; }
     // exchange with lane^1; only the two lanes of a pair take part (they may be in a divergent region together)
     KJ_DEV uint64_t pair_xchg64(uint64_t v) const { return kjemu::pair_exchange(s, lane, v); }
+    KJ_DEV uint32_t redux_max(uint32_t v) const { for (int m = 16; m > 0; m >>= 1) { uint32_t o = shfl_xor(v, m); v = o > v ? o : v; } return v; }
+    KJ_DEV uint32_t redux_min(uint32_t v) const { for (int m = 16; m > 0; m >>= 1) { uint32_t o = shfl_xor(v, m); v = o < v ? o : v; } return v; }
 };
 static inline int kj_fns(uint32_t mask, int n) { for (int b = 0; b < 32; b++) if ((mask >> b) & 1u) { if (n-- == 0) return b; } return -1; }
 #else
@@ -75,25 +77,21 @@ struct Warp {
     KJ_DEV double shfl_d(double v, int src) const { return __shfl_sync(KJ_FULL, v, src); }
     // exchange with lane^1; only the two lanes of a pair take part (they may be in a divergent region together)
     KJ_DEV uint64_t pair_xchg64(uint64_t v) const { return __shfl_xor_sync(3u << (lane & 30), (unsigned long long)v, 1); }
+    // redux.sync: one instruction per 32-bit warp reduction (sm_80+)
+    KJ_DEV uint32_t redux_max(uint32_t v) const { return __reduce_max_sync(KJ_FULL, v); }
+    KJ_DEV uint32_t redux_min(uint32_t v) const { return __reduce_min_sync(KJ_FULL, v); }
 };
 static KJ_DEV int kj_fns(uint32_t mask, int n) { return (int)__fns(mask, 0, n + 1); }     // index of the n-th (0-based) set bit
 #endif
 
 // collectives built on the primitives (identical in both builds)
-static KJ_DEV uint32_t warp_max_u32(const Warp& w, uint32_t v) {
-    for (int m = 16; m > 0; m >>= 1) { uint32_t o = w.shfl_xor(v, m); v = o > v ? o : v; }
-    return v;
-}
-static KJ_DEV int warp_max_i32(const Warp& w, int v) {
-    for (int m = 16; m > 0; m >>= 1) { int o = w.shfl_xor(v, m); v = o > v ? o : v; }
-    return v;
-}
-static KJ_DEV uint32_t warp_min_u32(const Warp& w, uint32_t v) {
-    for (int m = 16; m > 0; m >>= 1) { uint32_t o = w.shfl_xor(v, m); v = o < v ? o : v; }
-    return v;
-}
+static KJ_DEV uint32_t warp_max_u32(const Warp& w, uint32_t v) { return w.redux_max(v); }
+static KJ_DEV int warp_max_i32(const Warp& w, int v) { return (int)(w.redux_max((uint32_t)v ^ 0x80000000u) ^ 0x80000000u); }
+static KJ_DEV uint32_t warp_min_u32(const Warp& w, uint32_t v) { return w.redux_min(v); }
+// 64-bit max as two 32-bit reductions: high words first, then the low words of the lanes that tie on the high word
 static KJ_DEV uint64_t warp_max_u64(const Warp& w, uint64_t v) {
-    for (int m = 16; m > 0; m >>= 1) { uint64_t o = w.shfl_xor64(v, m); v = o > v ? o : v; }
-    return v;
+    const uint32_t hi = (uint32_t)(v >> 32), mh = w.redux_max(hi);
+    const uint32_t ml = w.redux_max(hi == mh ? (uint32_t)v : 0u);
+    return ((uint64_t)mh << 32) | ml;
 }
 static KJ_DEV uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
