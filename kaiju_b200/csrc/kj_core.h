@@ -650,7 +650,10 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
     while (kj_queue_pop(cx, q, longest, val, pay)) {
         const uint32_t arr = pay >> 30, start = (pay >> 14) & 0x7fffu, len = pay & 0x3fffu; const bool segchecked = (pay >> 29) & 1u;
         kj_load_frag(cx, arr, start, len);
-        if (rp.seg && !segchecked && kj_seg_gate(cx, q, arr, start, len, false)) continue;
+        // SEG is deferred until the fragment is known to matter: every match inside a SEG piece is also a match inside the
+        // whole fragment (for each end position the piece's match is a suffix of the fragment's), so a fragment whose
+        // search finds nothing >= L cannot contribute through its pieces either, and un-pushed useless pieces are not
+        // observable (they never change `longest`, the kept list or the relative order of other queue entries).
         // greedyExact(f, seq, len, max(m,longest), -1) (bwt.c:347-380): chains for j = len-1 .. L-1, L growing
         uint32_t L = rp.m > longest ? rp.m : longest;
         uint32_t item_best = 0, item_cnt = 0;                             // uniform
@@ -687,6 +690,9 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
             }
         }
         w.sync();
+        // the SEG gate of getNextFragment (ConsumerThread.cpp:285-339), now that the fragment has a match >= L: if SEG masks
+        // something the fragment is replaced by its pieces exactly as in the reference and this search result is dropped
+        if (item_cnt > 0 && rp.seg && !segchecked && kj_seg_gate(cx, q, arr, start, len, false)) continue;
         if (item_cnt > 0) {
             // winners were appended j-descending; the reference's chain is newest (smallest j) first
             for (uint32_t t = (uint32_t)w.lane; t < item_cnt / 2; t += 32) {

@@ -23,7 +23,7 @@
 #define KJ_MIN_BLOCKS 4          // resident CTAs per SM the register allocation is tuned for (ncu: latency-bound, see profiles/)
 #endif
 #ifndef KJ_MIN_BLOCKS_GREEDY
-#define KJ_MIN_BLOCKS_GREEDY 3
+#define KJ_MIN_BLOCKS_GREEDY 4   // A/B: 8.30 vs 7.94 M pairs/s
 #endif
 #define KJ_CHUNK_READS (1u << 20)
 
