@@ -24,7 +24,7 @@
 struct KjKept { uint64_t lo; uint32_t len; uint32_t aux; };     // one suffix interval (an SI of bwt.h:25-34)
 
 struct KjSmemLayout {
-    uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, aa_off, aa_stride, frag_off, hflag_off,
+    uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, batch_off, aa_off, aa_stride, frag_off, hflag_off,
              segcnt_off, seghist_off, segs_off, total;
 };
 static KJ_HD uint32_t kj_align(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -35,6 +35,8 @@ static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
     L.segs_off = o; o += 8u * KJ_SEG_CAP(p.max_frag);                     // {int begin,end}
     L.qpay_off = o; o += 4u * kj_align(p.item_cap, 2);
     L.ids_off = o; o += 4u * 24u;
+    L.batch_off = o; o += 8u * 9u + 4u * 9u * 3u + 4u;               // screening batch: keys, payloads, slots, chain prefix sums (+pending)
+    o = kj_align(o, 8);
     L.aa_stride = kj_align(p.max_len + 4, 8);
     L.aa_off = o; o += 4u * L.aa_stride;
     L.frag_off = o; o += kj_align(p.max_frag + 8, 8);
@@ -214,6 +216,48 @@ static KJ_DEV void kj_finish_paired(const Warp& w, const KjDevIndex& ix, const u
     const IdxT rlo = (IdxT)w.shfl64((uint64_t)lo, src), rhi = (IdxT)w.shfl64((uint64_t)hi, src); const int ri = w.shfl(i, src);
     if (is_owner) { ch.lo = rlo; ch.hi = rhi; ch.i = ri; ch.done = true; }
 }
+// Phase A for TWO chains per lane straight from the translation arrays (residue t of a fragment = f[3 t]); the two chains'
+// loads are issued together so their latencies overlap.  Used to screen several queued fragments at once.
+template <class IdxT>
+static KJ_DEV void kj_chain_start2(const KjDevIndex& ix, const uint8_t* f0, int j0, bool a0, const uint8_t* f1, int j1, bool a1,
+                                   uint32_t Lmin, KjChain<IdxT>& c0, KjChain<IdxT>& c1) {
+    const int k = ix.kmer_k; int b0 = KJ_PHASE_A_LETTERS - 1, b1 = KJ_PHASE_A_LETTERS - 1;
+    c0.lo = 0; c0.hi = 0; c0.i = j0; c0.done = !a0; c1.lo = 0; c1.hi = 0; c1.i = j1; c1.done = !a1;
+    const bool k0 = a0 && k > 0 && j0 >= k && Lmin >= (uint32_t)k, k1 = a1 && k > 0 && j1 >= k && Lmin >= (uint32_t)k;
+    uint32_t x0 = 0, x1 = 0;
+    if (k0) for (int t = 0; t < k; t++) x0 = x0 * 20u + (uint32_t)(f0[3 * (j0 - t)] - 1u);
+    if (k1) for (int t = 0; t < k; t++) x1 = x1 * 20u + (uint32_t)(f1[3 * (j1 - t)] - 1u);
+    if (sizeof(IdxT) == 4) {
+        KjKmer32 e0 = {0, 0}, e1 = {0, 0};
+        if (k0) e0 = ((const KjKmer32*)ix.kmer)[x0];
+        if (k1) e1 = ((const KjKmer32*)ix.kmer)[x1];
+        if (k0) { c0.lo = (IdxT)e0.lo; c0.hi = (IdxT)e0.hi; }
+        if (k1) { c1.lo = (IdxT)e1.lo; c1.hi = (IdxT)e1.hi; }
+    } else {
+        KjKmer e0 = {0, 0}, e1 = {0, 0};
+        if (k0) e0 = ((const KjKmer*)ix.kmer)[x0];
+        if (k1) e1 = ((const KjKmer*)ix.kmer)[x1];
+        if (k0) { c0.lo = (IdxT)e0.lo; c0.hi = (IdxT)e0.hi; }
+        if (k1) { c1.lo = (IdxT)e1.lo; c1.hi = (IdxT)e1.hi; }
+    }
+    if (k0) { if (c0.lo >= c0.hi) { c0.lo = 0; c0.hi = 0; c0.i = j0 + 1; c0.done = true; } else { c0.i = j0 - k + 1; b0 = KJ_PHASE_A_LETTERS - k; } }
+    else if (a0) { const uint32_t c = f0[3 * j0]; c0.lo = (IdxT)ix.C[c]; c0.hi = (IdxT)ix.C[c + 1]; }
+    if (k1) { if (c1.lo >= c1.hi) { c1.lo = 0; c1.hi = 0; c1.i = j1 + 1; c1.done = true; } else { c1.i = j1 - k + 1; b1 = KJ_PHASE_A_LETTERS - k; } }
+    else if (a1) { const uint32_t c = f1[3 * j1]; c1.lo = (IdxT)ix.C[c]; c1.hi = (IdxT)ix.C[c + 1]; }
+    for (;;) {
+        const bool s0 = !c0.done && c0.i > 0 && b0 > 0, s1 = !c1.done && c1.i > 0 && b1 > 0;
+        if (!(s0 || s1)) break;
+        // both steps are computed unconditionally (idle chains re-rank their frozen interval: valid addresses, result ignored)
+        const uint32_t l0 = s0 ? f0[3 * (c0.i - 1)] : 1u, l1 = s1 ? f1[3 * (c1.i - 1)] : 1u;
+        const KjRankBlock* r0 = kj_letter_base(ix, l0); const KjRankBlock* r1 = kj_letter_base(ix, l1);
+        const IdxT nlo0 = kj_rank_at<IdxT>(r0, c0.lo), nhi0 = kj_rank_at<IdxT>(r0, c0.hi);
+        const IdxT nlo1 = kj_rank_at<IdxT>(r1, c1.lo), nhi1 = kj_rank_at<IdxT>(r1, c1.hi);
+        if (s0) { if (nlo0 >= nhi0) c0.done = true; else { c0.lo = nlo0; c0.hi = nhi0; c0.i--; b0--; } }
+        if (s1) { if (nlo1 >= nhi1) c1.done = true; else { c1.lo = nlo1; c1.hi = nhi1; c1.i--; b1--; } }
+    }
+    if (c0.i == 0) c0.done = true;
+    if (c1.i == 0) c1.done = true;
+}
 template <class IdxT>
 static KJ_DEV void kj_chain_finish(const KjDevIndex& ix, const uint8_t* frag, KjChain<IdxT>& ch) {
     int i = ch.i;
@@ -252,7 +296,7 @@ static KJ_DEV void kj_queue_emit(KjWarpCtx& cx, KjQueue& q, bool emit, uint32_t 
     q.n += cnt;
 }
 // pop the top entry if its sort value is >= min_val (getNextFragment's gate, ConsumerThread.cpp:276-283)
-static KJ_DEV bool kj_queue_pop(KjWarpCtx& cx, KjQueue& q, uint32_t min_val, uint32_t& val, uint32_t& pay) {
+static KJ_DEV bool kj_queue_pop(KjWarpCtx& cx, KjQueue& q, uint32_t min_val, uint32_t& val, uint32_t& pay, uint32_t* slot_out = nullptr, uint64_t* key_out = nullptr) {
     cx.w.sync();
     uint64_t best = 0; uint32_t slot = 0;
     for (uint32_t s = (uint32_t)cx.w.lane; s < q.n; s += 32) { uint64_t k = q.key[s]; if (k > best) { best = k; slot = s; } }
@@ -265,9 +309,13 @@ static KJ_DEV bool kj_queue_pop(KjWarpCtx& cx, KjQueue& q, uint32_t min_val, uin
     uint32_t p = 0;
     if (cx.w.lane == src) { p = q.pay[slot]; q.key[slot] = 0; }
     pay = cx.w.shfl(p, src);
+    if (slot_out) *slot_out = cx.w.shfl(slot, src);
+    if (key_out) *key_out = g;
     cx.w.sync();
     return true;
 }
+// undo a pop (the payload word of the slot is still in place)
+static KJ_DEV void kj_queue_unpop(KjWarpCtx& cx, KjQueue& q, uint32_t slot, uint64_t key) { if (cx.w.lane == 0) q.key[slot] = key; }
 
 // ---------------------------------------------------------------------------------------------
 // six-frame translation + stop splitting of one mate  (getAllFragmentsBits, ConsumerThread.cpp:190-270)
@@ -641,14 +689,18 @@ static KJ_DEV bool kj_seg_gate(KjWarpCtx& cx, KjQueue& q, uint32_t arr, uint32_t
     return true;
 }
 
+#ifndef KJ_OPT_SCREEN
+#define KJ_OPT_SCREEN 1           // 1: after a fragment without candidate, the following fragments are screened several at a time
+#endif
+#define KJ_SCREEN_ITEMS 8
+#define KJ_SCREEN_CHAINS 64       // two chains per lane
+
+// One popped fragment: search, deferred SEG gate, merge into the kept list.  Returns true if it had a match >= L.
 template <class IdxT>
-static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best_out) {
+static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t& longest, uint32_t& nkept) {
     const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix; const KjRunParams& rp = *cx.rp;
     const uint8_t* frag = cx.smem + cx.L.frag_off;
-    uint32_t longest = 0, nkept = 0;                                      // uniform
-    uint32_t val, pay;
-    while (kj_queue_pop(cx, q, longest, val, pay)) {
-        const uint32_t arr = pay >> 30, start = (pay >> 14) & 0x7fffu, len = pay & 0x3fffu; const bool segchecked = (pay >> 29) & 1u;
+    const uint32_t arr = pay >> 30, start = (pay >> 14) & 0x7fffu, len = pay & 0x3fffu; const bool segchecked = (pay >> 29) & 1u;
         kj_load_frag(cx, arr, start, len);
         // SEG is deferred until the fragment is known to matter: every match inside a SEG piece is also a match inside the
         // whole fragment (for each end position the piece's match is a suffix of the fragment's), so a fragment whose
@@ -692,7 +744,7 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
         w.sync();
         // the SEG gate of getNextFragment (ConsumerThread.cpp:285-339), now that the fragment has a match >= L: if SEG masks
         // something the fragment is replaced by its pieces exactly as in the reference and this search result is dropped
-        if (item_cnt > 0 && rp.seg && !segchecked && kj_seg_gate(cx, q, arr, start, len, false)) continue;
+        if (item_cnt > 0 && rp.seg && !segchecked && kj_seg_gate(cx, q, arr, start, len, false)) return true;
         if (item_cnt > 0) {
             // winners were appended j-descending; the reference's chain is newest (smallest j) first
             for (uint32_t t = (uint32_t)w.lane; t < item_cnt / 2; t += 32) {
@@ -713,6 +765,69 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
                 nkept = item_cnt; longest = item_best;
             } else if (item_best == longest) nkept += item_cnt;           // append (586-591)
         }
+    return item_cnt > 0;
+}
+
+// Screening (phase A only) of the chains of several queued fragments at once, two chains per lane.  Returns true if some
+// chain is still alive or already reached L -- then the fragments are processed one by one in order; false PROVES that
+// none of them has a match >= L (L can only grow while they are processed), i.e. none of them can change anything.
+template <class IdxT>
+static KJ_DEV bool kj_mem_screen(KjWarpCtx& cx, const uint32_t* bpay, const uint32_t* bcum, int nb, uint32_t L) {
+    const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix;
+    const uint32_t total = bcum[nb];
+    const uint8_t* f[2] = {cx.smem, cx.smem}; int j[2] = {0, 0}; bool act[2] = {false, false};
+    for (int s2 = 0; s2 < 2; s2++) {
+        const uint32_t c = (uint32_t)w.lane + 32u * (uint32_t)s2;
+        if (c < total) {
+            int k = 0; while (c >= bcum[k + 1]) k++;
+            const uint32_t pay = bpay[k]; const uint32_t arr = pay >> 30, start = (pay >> 14) & 0x7fffu, len = pay & 0x3fffu;
+            f[s2] = cx.smem + cx.L.aa_off + arr * cx.L.aa_stride + start; j[s2] = (int)len - 1 - (int)(c - bcum[k]); act[s2] = true;
+        }
+    }
+    KjChain<IdxT> c0, c1;
+    kj_chain_start2<IdxT>(ix, f[0], j[0], act[0], f[1], j[1], act[1], cx.rp->m, c0, c1);
+    const bool cand = (act[0] && (!c0.done || (uint32_t)(j[0] - c0.i + 1) >= L)) || (act[1] && (!c1.done || (uint32_t)(j[1] - c1.i + 1) >= L));
+    return w.any(cand);
+}
+
+template <class IdxT>
+static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best_out) {
+    const Warp& w = cx.w; const KjRunParams& rp = *cx.rp;
+    uint32_t longest = 0, nkept = 0;                                      // uniform
+    uint32_t val, pay;
+    // screening batch (slot 8 = the fragment popped last that did not fit): keys and slots allow an exact un-pop
+    uint64_t* bkey = (uint64_t*)(cx.smem + cx.L.batch_off); uint32_t* bpay = (uint32_t*)(bkey + 9); uint32_t* bslot = bpay + 9; uint32_t* bcum = bslot + 9;
+    bool screen = false; int normal_left = 0;                             // uniform
+    for (;;) {
+        if (!(KJ_OPT_SCREEN && screen && normal_left == 0)) {
+            if (!kj_queue_pop(cx, q, longest, val, pay)) break;
+            const bool cand = kj_mem_item<IdxT>(cx, q, pay, longest, nkept);
+            if (normal_left > 0) normal_left--;
+            screen = !cand;
+            continue;
+        }
+        // collect the next fragments in pop order while their chains fit two per lane
+        const uint32_t L = rp.m > longest ? rp.m : longest;
+        int nb = 0; uint32_t tot = 0; bool overflow = false;
+        while (nb < KJ_SCREEN_ITEMS) {
+            uint32_t slot; uint64_t key;
+            if (!kj_queue_pop(cx, q, longest, val, pay, &slot, &key)) break;
+            const uint32_t chains = (pay & 0x3fffu) - L + 1u;
+            if (tot + chains > KJ_SCREEN_CHAINS) { kj_queue_unpop(cx, q, slot, key); overflow = true; break; }
+            if (w.lane == 0) { bkey[nb] = key; bpay[nb] = pay; bslot[nb] = slot; bcum[nb] = tot; }
+            tot += chains; nb++;
+        }
+        if (nb == 0) {
+            if (!overflow) break;                                         // queue exhausted (or everything left is shorter than `longest`)
+            normal_left = 1; continue;                                    // one fragment with more than 64 chains: normal path
+        }
+        if (w.lane == 0) bcum[nb] = tot;
+        w.sync();
+        if (!kj_mem_screen<IdxT>(cx, bpay, bcum, nb, L)) continue;        // proven: none of them can matter
+        // some chain survived: put the fragments back and let the normal path take them one by one, in exact pop order
+        // (a SEG split may push pieces that belong between them)
+        for (int k = 0; k < nb; k++) kj_queue_unpop(cx, q, bslot[k], bkey[k]);
+        normal_left = nb;
     }
     best_out = 0;
     if (nkept == 0) return KJ_TAX_BAD;

@@ -40,6 +40,29 @@ def main():
             if ie.isdigit():
                 lines.append((int(ie), int(sm) if sm.isdigit() else 0, int(te) if te.isdigit() else 0, int(ls) if ls.isdigit() else 0, cur.split("/")[-1], int(r[0]), r[1].strip()[:100]))
         tot = sum(x[0] for x in lines) or 1; ts = sum(x[1] for x in lines) or 1
+        # time by function: map kj_core*.h lines to the enclosing `static KJ_DEV ... kj_xxx(` definition
+        import os, re
+        fmap = {}
+        for fn in ("kj_core.h", "kj_core_greedy.h"):
+            path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "kaiju_b200", "csrc", fn)
+            cur = "(top)"; m = {}
+            try:
+                for i, l in enumerate(open(path).read().split("\n"), 1):
+                    mm = re.match(r"^static KJ_DEV .*?\b(kj_\w+)\s*\(", l)
+                    if mm:
+                        cur = mm.group(1)
+                    m[i] = cur
+            except OSError:
+                pass
+            fmap[fn] = m
+        agg = {}
+        for x in lines:
+            key = fmap.get(x[4], {}).get(x[5], x[4]) if x[4] in fmap else x[4]
+            a = agg.setdefault(key, [0, 0]); a[0] += x[0]; a[1] += x[1]
+        f.write("## time by function (stall-sample share = share of warp time; valid when the report was taken from the committed source)\n\n| function / file | warp instructions % | warp time % |\n|---|---|---|\n")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:18]:
+            f.write("| %s | %.1f | %.1f |\n" % (k, 100.0 * a[0] / tot, 100.0 * a[1] / ts))
+        f.write("\n")
         f.write("## hottest source lines (share of warp instructions executed / of stall samples; active threads per instruction; long-scoreboard samples)\n\n")
         f.write("| inst %% | samples %% | thr/inst | long_sb | location | source |\n|---|---|---|---|---|---|\n")
         for x in sorted(lines, reverse=True)[:40]:
