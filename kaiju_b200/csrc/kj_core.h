@@ -24,7 +24,7 @@
 struct KjKept { uint64_t lo; uint32_t len; uint32_t aux; };     // one suffix interval (an SI of bwt.h:25-34)
 
 struct KjSmemLayout {
-    uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, batch_off, aa_off, aa_stride, frag_off, hflag_off,
+    uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, aa_off, aa_stride, frag_off, hflag_off,
              segcnt_off, seghist_off, segs_off, total;
 };
 static KJ_HD uint32_t kj_align(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -35,8 +35,6 @@ static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
     L.segs_off = o; o += 8u * KJ_SEG_CAP(p.max_frag);                     // {int begin,end}
     L.qpay_off = o; o += 4u * kj_align(p.item_cap, 2);
     L.ids_off = o; o += 4u * 24u;
-    L.batch_off = o; o += 8u * 9u + 4u * 9u * 3u + 4u;               // screening batch: keys, payloads, slots, chain prefix sums (+pending)
-    o = kj_align(o, 8);
     L.aa_stride = kj_align(p.max_len + 4, 8);
     L.aa_off = o; o += 4u * L.aa_stride;
     L.frag_off = o; o += kj_align(p.max_frag + 8, 8);
@@ -76,19 +74,11 @@ static KJ_DEV void kj_flag_error(KjWarpCtx& cx, uint32_t bit) {
 #endif
 }
 
-// tunables (A/B-tested on the B200, see profiles/): the kernel is bound by the dependent-instruction latency of one warp,
-// not by issue slots or DRAM, so shorter dependence chains beat fewer instructions.
+// A/B-tested on the B200 (profiles/README.md): one warp's time is dominated by chains of dependent short-latency instructions,
+// so shorter dependence chains beat fewer instructions.  Tried and rejected: two lanes per chain in phase B (-7 %),
+// compaction of low-diversity SEG windows (-10 %), screening several queued fragments at once with two chains per lane (-29 %).
 #ifndef KJ_OPT_RANKBASE
-#define KJ_OPT_RANKBASE 1         // 1: per-letter record base from shared memory, 0: multiply            (A/B: 29.5 vs 28.7 M pairs/s)
-#endif
-#ifndef KJ_OPT_PAIRED
-#define KJ_OPT_PAIRED 0           // 1: two lanes per chain in phase B (half the instructions, +1 shuffle per step) (A/B: 26.6 vs 28.7)
-#endif
-#ifndef KJ_OPT_SEGPACKED
-#define KJ_OPT_SEGPACKED 1         // 1: window residues packed in 3 words, byte-compare counting on the low-diversity path
-#endif
-#ifndef KJ_OPT_SEGCOMPACT
-#define KJ_OPT_SEGCOMPACT 0       // 1: low-diversity windows are compacted before the composition count  (A/B: 25.7 vs 28.7)
+#define KJ_OPT_RANKBASE 1         // 1: per-letter record base from shared memory, 0: multiply (A/B: +3 %)
 #endif
 // ---------------------------------------------------------------------------------------------
 // FM index primitives.  IdxT = uint32_t for indexes with bwtlen < 2^32 (all interval arithmetic in 32 bit), uint64_t otherwise.
@@ -189,90 +179,17 @@ static KJ_DEV void kj_chain_start(const KjDevIndex& ix, const uint8_t* frag, int
     if (i == 0) ch.done = true;
     ch.i = i;
 }
-// Phase B with TWO lanes per chain: lane 2r computes the new lower end, lane 2r+1 the new upper end of chain r's interval
-// (one rank each instead of two), then they swap results.  `sel` = chains chosen for completion (<= 16); their state is
-// fetched from the owning lanes, completed by the pairs and handed back.  Halves the instructions issued per LF step.
-template <class IdxT>
-static KJ_DEV void kj_finish_paired(const Warp& w, const KjDevIndex& ix, const uint8_t* frag, uint32_t selmask, KjChain<IdxT>& ch) {
-    const int nsel = kj_popc(selmask);
-    const int r = w.lane >> 1; const bool mine = r < nsel;
-    const int owner = mine ? kj_fns(selmask, r) : 0;
-    IdxT lo = (IdxT)w.shfl64((uint64_t)ch.lo, owner), hi = (IdxT)w.shfl64((uint64_t)ch.hi, owner);
-    int i = w.shfl(ch.i, owner);
-    if (mine) {
-        const bool upper = (w.lane & 1) != 0;
-        while (i > 0) {
-            const IdxT mineval = kj_rank_at<IdxT>(kj_letter_base(ix, frag[i - 1]), upper ? hi : lo);
-            const IdxT other = (IdxT)w.pair_xchg64((uint64_t)mineval);
-            const IdxT nlo = upper ? other : mineval, nhi = upper ? mineval : other;
-            if (nlo >= nhi) break;
-            lo = nlo; hi = nhi; i--;
-        }
-    }
-    w.sync();
-    // hand the results back: owner lane = the (rank of owner in selmask)-th pair's even lane
-    const bool is_owner = (selmask >> w.lane) & 1u;
-    const int src = 2 * kj_popc(selmask & lanemask_lt(w.lane));
-    const IdxT rlo = (IdxT)w.shfl64((uint64_t)lo, src), rhi = (IdxT)w.shfl64((uint64_t)hi, src); const int ri = w.shfl(i, src);
-    if (is_owner) { ch.lo = rlo; ch.hi = rhi; ch.i = ri; ch.done = true; }
-}
-// Phase A for TWO chains per lane straight from the translation arrays (residue t of a fragment = f[3 t]); the two chains'
-// loads are issued together so their latencies overlap.  Used to screen several queued fragments at once.
-template <class IdxT>
-static KJ_DEV void kj_chain_start2(const KjDevIndex& ix, const uint8_t* f0, int j0, bool a0, const uint8_t* f1, int j1, bool a1,
-                                   uint32_t Lmin, KjChain<IdxT>& c0, KjChain<IdxT>& c1) {
-    const int k = ix.kmer_k; int b0 = KJ_PHASE_A_LETTERS - 1, b1 = KJ_PHASE_A_LETTERS - 1;
-    c0.lo = 0; c0.hi = 0; c0.i = j0; c0.done = !a0; c1.lo = 0; c1.hi = 0; c1.i = j1; c1.done = !a1;
-    const bool k0 = a0 && k > 0 && j0 >= k && Lmin >= (uint32_t)k, k1 = a1 && k > 0 && j1 >= k && Lmin >= (uint32_t)k;
-    uint32_t x0 = 0, x1 = 0;
-    if (k0) for (int t = 0; t < k; t++) x0 = x0 * 20u + (uint32_t)(f0[3 * (j0 - t)] - 1u);
-    if (k1) for (int t = 0; t < k; t++) x1 = x1 * 20u + (uint32_t)(f1[3 * (j1 - t)] - 1u);
-    if (sizeof(IdxT) == 4) {
-        KjKmer32 e0 = {0, 0}, e1 = {0, 0};
-        if (k0) e0 = ((const KjKmer32*)ix.kmer)[x0];
-        if (k1) e1 = ((const KjKmer32*)ix.kmer)[x1];
-        if (k0) { c0.lo = (IdxT)e0.lo; c0.hi = (IdxT)e0.hi; }
-        if (k1) { c1.lo = (IdxT)e1.lo; c1.hi = (IdxT)e1.hi; }
-    } else {
-        KjKmer e0 = {0, 0}, e1 = {0, 0};
-        if (k0) e0 = ((const KjKmer*)ix.kmer)[x0];
-        if (k1) e1 = ((const KjKmer*)ix.kmer)[x1];
-        if (k0) { c0.lo = (IdxT)e0.lo; c0.hi = (IdxT)e0.hi; }
-        if (k1) { c1.lo = (IdxT)e1.lo; c1.hi = (IdxT)e1.hi; }
-    }
-    if (k0) { if (c0.lo >= c0.hi) { c0.lo = 0; c0.hi = 0; c0.i = j0 + 1; c0.done = true; } else { c0.i = j0 - k + 1; b0 = KJ_PHASE_A_LETTERS - k; } }
-    else if (a0) { const uint32_t c = f0[3 * j0]; c0.lo = (IdxT)ix.C[c]; c0.hi = (IdxT)ix.C[c + 1]; }
-    if (k1) { if (c1.lo >= c1.hi) { c1.lo = 0; c1.hi = 0; c1.i = j1 + 1; c1.done = true; } else { c1.i = j1 - k + 1; b1 = KJ_PHASE_A_LETTERS - k; } }
-    else if (a1) { const uint32_t c = f1[3 * j1]; c1.lo = (IdxT)ix.C[c]; c1.hi = (IdxT)ix.C[c + 1]; }
-    for (;;) {
-        const bool s0 = !c0.done && c0.i > 0 && b0 > 0, s1 = !c1.done && c1.i > 0 && b1 > 0;
-        if (!(s0 || s1)) break;
-        // both steps are computed unconditionally (idle chains re-rank their frozen interval: valid addresses, result ignored)
-        const uint32_t l0 = s0 ? f0[3 * (c0.i - 1)] : 1u, l1 = s1 ? f1[3 * (c1.i - 1)] : 1u;
-        const KjRankBlock* r0 = kj_letter_base(ix, l0); const KjRankBlock* r1 = kj_letter_base(ix, l1);
-        const IdxT nlo0 = kj_rank_at<IdxT>(r0, c0.lo), nhi0 = kj_rank_at<IdxT>(r0, c0.hi);
-        const IdxT nlo1 = kj_rank_at<IdxT>(r1, c1.lo), nhi1 = kj_rank_at<IdxT>(r1, c1.hi);
-        if (s0) { if (nlo0 >= nhi0) c0.done = true; else { c0.lo = nlo0; c0.hi = nhi0; c0.i--; b0--; } }
-        if (s1) { if (nlo1 >= nhi1) c1.done = true; else { c1.lo = nlo1; c1.hi = nhi1; c1.i--; b1--; } }
-    }
-    if (c0.i == 0) c0.done = true;
-    if (c1.i == 0) c1.done = true;
-}
 template <class IdxT>
 static KJ_DEV void kj_chain_finish(const KjDevIndex& ix, const uint8_t* frag, KjChain<IdxT>& ch) {
     int i = ch.i;
     while (i > 0) { if (!kj_update_si<IdxT>(ix, frag[i - 1], ch.lo, ch.hi)) break; i--; }
     ch.i = i; ch.done = true;
 }
-// complete the selected chains (one lane each, or a lane pair each)
+// complete the selected chains (one lane each)
 template <class IdxT>
 static KJ_DEV void kj_finish_selected(const Warp& w, const KjDevIndex& ix, const uint8_t* frag, bool sel, KjChain<IdxT>& ch) {
-#if KJ_OPT_PAIRED
-    kj_finish_paired<IdxT>(w, ix, frag, w.ballot(sel), ch);
-#else
     if (sel) kj_chain_finish<IdxT>(ix, frag, ch);
     w.sync();
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -296,7 +213,7 @@ static KJ_DEV void kj_queue_emit(KjWarpCtx& cx, KjQueue& q, bool emit, uint32_t 
     q.n += cnt;
 }
 // pop the top entry if its sort value is >= min_val (getNextFragment's gate, ConsumerThread.cpp:276-283)
-static KJ_DEV bool kj_queue_pop(KjWarpCtx& cx, KjQueue& q, uint32_t min_val, uint32_t& val, uint32_t& pay, uint32_t* slot_out = nullptr, uint64_t* key_out = nullptr) {
+static KJ_DEV bool kj_queue_pop(KjWarpCtx& cx, KjQueue& q, uint32_t min_val, uint32_t& val, uint32_t& pay) {
     cx.w.sync();
     uint64_t best = 0; uint32_t slot = 0;
     for (uint32_t s = (uint32_t)cx.w.lane; s < q.n; s += 32) { uint64_t k = q.key[s]; if (k > best) { best = k; slot = s; } }
@@ -309,14 +226,9 @@ static KJ_DEV bool kj_queue_pop(KjWarpCtx& cx, KjQueue& q, uint32_t min_val, uin
     uint32_t p = 0;
     if (cx.w.lane == src) { p = q.pay[slot]; q.key[slot] = 0; }
     pay = cx.w.shfl(p, src);
-    if (slot_out) *slot_out = cx.w.shfl(slot, src);
-    if (key_out) *key_out = g;
     cx.w.sync();
     return true;
 }
-// undo a pop (the payload word of the slot is still in place)
-static KJ_DEV void kj_queue_unpop(KjWarpCtx& cx, KjQueue& q, uint32_t slot, uint64_t key) { if (cx.w.lane == 0) q.key[slot] = key; }
-
 // ---------------------------------------------------------------------------------------------
 // six-frame translation + stop splitting of one mate  (getAllFragmentsBits, ConsumerThread.cpp:190-270)
 // arrays: aa[2*mate+0][count] forward codon starting at base `count`; aa[2*mate+1][r] reverse-strand codon
@@ -400,7 +312,6 @@ struct KjSeg { int begin, end; };
 // entropy class of every 12-window: bit0 = H <= locut, bit1 = H <= hicut   (s_SeqEntropy/s_Entropy, 1596-1798).
 // A window with >= 8 distinct residues has H >= 2.617 > hicut (checked on the host over all partitions), so only the
 // rare low-diversity windows need the composition count.  Returns whether any window can trigger SEG at all.
-#if KJ_OPT_SEGPACKED
 // packed variant: the 12 residues of a window live in three 32-bit words; per distinct residue (<= 7 on the slow path)
 // the count is three byte-wise compares + popcounts instead of a 12-step nibble-counter loop
 static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
@@ -431,66 +342,6 @@ static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
     cx.w.sync();
     return any_low;
 }
-#elif KJ_OPT_SEGCOMPACT
-static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
-    const uint8_t* frag = cx.smem + cx.L.frag_off; uint8_t* hf = cx.smem + cx.L.hflag_off; const KjTables& tb = *cx.tb;
-    uint8_t* list = cx.smem + cx.L.segcnt_off;                  // low-diversity windows of the whole fragment (trim scratch is idle here)
-    uint32_t nlist = 0;                                          // uniform
-    for (int p0 = 0; p0 + KJ_SEG_WINDOW <= n; p0 += 32) {
-        const int p = p0 + cx.w.lane; bool low_div = false;
-        if (p + KJ_SEG_WINDOW <= n) {
-            uint32_t seen = 0;
-            for (int t = 0; t < KJ_SEG_WINDOW; t++) seen |= 1u << frag[p + t];
-            low_div = kj_popc(seen) < 8;
-            hf[p] = 0;
-        }
-        const uint32_t mk = cx.w.ballot(low_div);
-        if (low_div) list[nlist + (uint32_t)kj_popc(mk & lanemask_lt(cx.w.lane))] = (uint8_t)p;
-        nlist += (uint32_t)kj_popc(mk);
-    }
-    if (nlist == 0) return false;
-    cx.w.sync();
-    bool any_low = false;
-    for (uint32_t t0 = 0; t0 < nlist; t0 += 32) {                // the composition count runs once per fragment, lanes = flagged windows
-        const uint32_t t = t0 + (uint32_t)cx.w.lane; uint32_t flags = 0;
-        if (t < nlist) {
-            const int p = list[t];
-            uint64_t c_lo = 0, c_hi = 0;                         // 4-bit counters for letters 1..16 / 17..20 (max count 12)
-            for (int u = 0; u < KJ_SEG_WINDOW; u++) { uint32_t a = frag[p + u] - 1u; if (a < 16u) c_lo += 1ull << (4u * a); else c_hi += 1ull << (4u * (a - 16u)); }
-            int32_t x = 0;
-            for (int u = 0; u < KJ_SEG_WINDOW; u++) { uint32_t a = frag[p + u] - 1u; uint32_t c = a < 16u ? (uint32_t)(c_lo >> (4u * a)) & 15u : (uint32_t)(c_hi >> (4u * (a - 16u))) & 15u; x += tb.seg_logfix[c]; }
-            flags = (x <= tb.seg_locut_fix ? 1u : 0u) | (x <= tb.seg_hicut_fix ? 2u : 0u);
-            hf[p] = (uint8_t)flags;
-        }
-        any_low = cx.w.any((flags & 1u) != 0) || any_low;
-    }
-    cx.w.sync();
-    return any_low;
-}
-#else
-static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
-    const uint8_t* frag = cx.smem + cx.L.frag_off; uint8_t* hf = cx.smem + cx.L.hflag_off; const KjTables& tb = *cx.tb;
-    bool any_low = false;
-    for (int p0 = 0; p0 + KJ_SEG_WINDOW <= n; p0 += 32) {
-        const int p = p0 + cx.w.lane; uint32_t flags = 0;
-        if (p + KJ_SEG_WINDOW <= n) {
-            uint32_t seen = 0;
-            for (int t = 0; t < KJ_SEG_WINDOW; t++) seen |= 1u << frag[p + t];
-            if (kj_popc(seen) < 8) {
-                uint64_t c_lo = 0, c_hi = 0;                     // 4-bit counters for letters 1..16 / 17..20 (max count 12)
-                for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; if (a < 16u) c_lo += 1ull << (4u * a); else c_hi += 1ull << (4u * (a - 16u)); }
-                int32_t x = 0;
-                for (int t = 0; t < KJ_SEG_WINDOW; t++) { uint32_t a = frag[p + t] - 1u; uint32_t c = a < 16u ? (uint32_t)(c_lo >> (4u * a)) & 15u : (uint32_t)(c_hi >> (4u * (a - 16u))) & 15u; x += tb.seg_logfix[c]; }
-                flags = (x <= tb.seg_locut_fix ? 1u : 0u) | (x <= tb.seg_hicut_fix ? 2u : 0u);
-            }
-            hf[p] = (uint8_t)flags;
-        }
-        any_low = cx.w.any((flags & 1u) != 0) || any_low;
-    }
-    cx.w.sync();
-    return any_low;
-}
-#endif
 
 // s_Trim (blast_seg.c:1971-2015): the sub-window of s[0..n2) with minimal s_GetProb; first in
 // (len descending, start ascending) order wins ties.  One lane per window length, sliding start.
@@ -689,12 +540,6 @@ static KJ_DEV bool kj_seg_gate(KjWarpCtx& cx, KjQueue& q, uint32_t arr, uint32_t
     return true;
 }
 
-#ifndef KJ_OPT_SCREEN
-#define KJ_OPT_SCREEN 1           // 1: after a fragment without candidate, the following fragments are screened several at a time
-#endif
-#define KJ_SCREEN_ITEMS 8
-#define KJ_SCREEN_CHAINS 64       // two chains per lane
-
 // One popped fragment: search, deferred SEG gate, merge into the kept list.  Returns true if it had a match >= L.
 template <class IdxT>
 static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t& longest, uint32_t& nkept) {
@@ -768,70 +613,14 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
     return item_cnt > 0;
 }
 
-// Screening (phase A only) of the chains of several queued fragments at once, two chains per lane.  Returns true if some
-// chain is still alive or already reached L -- then the fragments are processed one by one in order; false PROVES that
-// none of them has a match >= L (L can only grow while they are processed), i.e. none of them can change anything.
-template <class IdxT>
-static KJ_DEV bool kj_mem_screen(KjWarpCtx& cx, const uint32_t* bpay, const uint32_t* bcum, int nb, uint32_t L) {
-    const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix;
-    const uint32_t total = bcum[nb];
-    const uint8_t* f[2] = {cx.smem, cx.smem}; int j[2] = {0, 0}; bool act[2] = {false, false};
-    for (int s2 = 0; s2 < 2; s2++) {
-        const uint32_t c = (uint32_t)w.lane + 32u * (uint32_t)s2;
-        if (c < total) {
-            int k = 0; while (c >= bcum[k + 1]) k++;
-            const uint32_t pay = bpay[k]; const uint32_t arr = pay >> 30, start = (pay >> 14) & 0x7fffu, len = pay & 0x3fffu;
-            f[s2] = cx.smem + cx.L.aa_off + arr * cx.L.aa_stride + start; j[s2] = (int)len - 1 - (int)(c - bcum[k]); act[s2] = true;
-        }
-    }
-    KjChain<IdxT> c0, c1;
-    kj_chain_start2<IdxT>(ix, f[0], j[0], act[0], f[1], j[1], act[1], cx.rp->m, c0, c1);
-    const bool cand = (act[0] && (!c0.done || (uint32_t)(j[0] - c0.i + 1) >= L)) || (act[1] && (!c1.done || (uint32_t)(j[1] - c1.i + 1) >= L));
-    return w.any(cand);
-}
-
 template <class IdxT>
 static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best_out) {
-    const Warp& w = cx.w; const KjRunParams& rp = *cx.rp;
     uint32_t longest = 0, nkept = 0;                                      // uniform
     uint32_t val, pay;
-    // screening batch (slot 8 = the fragment popped last that did not fit): keys and slots allow an exact un-pop
-    uint64_t* bkey = (uint64_t*)(cx.smem + cx.L.batch_off); uint32_t* bpay = (uint32_t*)(bkey + 9); uint32_t* bslot = bpay + 9; uint32_t* bcum = bslot + 9;
-    bool screen = false; int normal_left = 0;                             // uniform
-    for (;;) {
-        if (!(KJ_OPT_SCREEN && screen && normal_left == 0)) {
-            if (!kj_queue_pop(cx, q, longest, val, pay)) break;
-            const bool cand = kj_mem_item<IdxT>(cx, q, pay, longest, nkept);
-            if (normal_left > 0) normal_left--;
-            screen = !cand;
-            continue;
-        }
-        // collect the next fragments in pop order while their chains fit two per lane
-        const uint32_t L = rp.m > longest ? rp.m : longest;
-        int nb = 0; uint32_t tot = 0; bool overflow = false;
-        while (nb < KJ_SCREEN_ITEMS) {
-            uint32_t slot; uint64_t key;
-            if (!kj_queue_pop(cx, q, longest, val, pay, &slot, &key)) break;
-            const uint32_t chains = (pay & 0x3fffu) - L + 1u;
-            if (tot + chains > KJ_SCREEN_CHAINS) { kj_queue_unpop(cx, q, slot, key); overflow = true; break; }
-            if (w.lane == 0) { bkey[nb] = key; bpay[nb] = pay; bslot[nb] = slot; bcum[nb] = tot; }
-            tot += chains; nb++;
-        }
-        if (nb == 0) {
-            if (!overflow) break;                                         // queue exhausted (or everything left is shorter than `longest`)
-            normal_left = 1; continue;                                    // one fragment with more than 64 chains: normal path
-        }
-        if (w.lane == 0) bcum[nb] = tot;
-        w.sync();
-        if (!kj_mem_screen<IdxT>(cx, bpay, bcum, nb, L)) continue;        // proven: none of them can matter
-        // some chain survived: put the fragments back and let the normal path take them one by one, in exact pop order
-        // (a SEG split may push pieces that belong between them)
-        for (int k = 0; k < nb; k++) kj_queue_unpop(cx, q, bslot[k], bkey[k]);
-        normal_left = nb;
-    }
+    while (kj_queue_pop(cx, q, longest, val, pay)) kj_mem_item<IdxT>(cx, q, pay, longest, nkept);
     best_out = 0;
     if (nkept == 0) return KJ_TAX_BAD;
-    w.sync();
+    cx.w.sync();
     uint32_t t = kj_ids_and_lca(cx, nkept);
     if (t != KJ_TAX_BAD) best_out = longest;
     return t;

@@ -110,13 +110,8 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
             // maxMatches_withStart (bwt.c:298-336): extend the stored interval leftwards from len - matchlen
             // one chain: lanes 0/1 compute the lower/upper interval end (kj_finish_paired on a one-chain selection)
             KjChain<IdxT> one; one.lo = (IdxT)si0; one.hi = (IdxT)si1; one.i = (int)len - (int)matchlen; one.done = false;
-#if KJ_OPT_PAIRED
-            kj_finish_paired<IdxT>(w, ix, frag, 1u, one);
-            const IdxT lo = (IdxT)w.shfl64((uint64_t)one.lo, 0), hi = (IdxT)w.shfl64((uint64_t)one.hi, 0); const int i = w.shfl(one.i, 0);
-#else
             kj_chain_finish<IdxT>(ix, frag, one);                          // every lane runs the same chain: identical addresses, one sector per step
             const IdxT lo = one.lo, hi = one.hi; const int i = one.i;
-#endif
             uint32_t l = len - (uint32_t)i;
             uint32_t Lreq = (num_mm == rp.e) ? rp.m : matchlen;           // ConsumerThread.cpp:445-450
             if (l >= Lreq) { if (w.lane == 0) { cls[0].lo = (uint64_t)lo; cls[0].len = (uint32_t)(hi - lo); cls[0].qi = (uint16_t)i; cls[0].ql = (uint16_t)l; } nrec = 1; }

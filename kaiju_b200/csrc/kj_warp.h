@@ -16,7 +16,6 @@ namespace kjemu {
 struct Sched;                         // defined in tests/emu/kj_emu.cpp
 uint64_t rendezvous(Sched* s, int lane, uint64_t v, int src_kind, int src_arg);
 uint32_t rendezvous_ballot(Sched* s, int lane, bool p);
-uint64_t pair_exchange(Sched* s, int lane, uint64_t v);
 }
 static inline int kj_popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int kj_popcll(uint64_t x) { return __builtin_popcountll(x); }
@@ -41,12 +40,9 @@ struct Warp {
     KJ_DEV uint32_t shfl_xor(uint32_t v, int m) const { return (uint32_t)shfl_xor64(v, m); }
     KJ_DEV int shfl_xor(int v, int m) const { return (int)(uint32_t)shfl_xor64((uint32_t)v, m); }
     KJ_DEV double shfl_d(double v, int src) const { uint64_t u; memcpy(&u, &v, 8); u = shfl64(u, src); memcpy(&v, &u, 8); return v; }
-    // exchange with lane^1; only the two lanes of a pair take part (they may be in a divergent region together)
-    KJ_DEV uint64_t pair_xchg64(uint64_t v) const { return kjemu::pair_exchange(s, lane, v); }
     KJ_DEV uint32_t redux_max(uint32_t v) const { for (int m = 16; m > 0; m >>= 1) { uint32_t o = shfl_xor(v, m); v = o > v ? o : v; } return v; }
     KJ_DEV uint32_t redux_min(uint32_t v) const { for (int m = 16; m > 0; m >>= 1) { uint32_t o = shfl_xor(v, m); v = o < v ? o : v; } return v; }
 };
-static inline int kj_fns(uint32_t mask, int n) { for (int b = 0; b < 32; b++) if ((mask >> b) & 1u) { if (n-- == 0) return b; } return -1; }
 #else
 // ------------------------------------------------------------------ device (product)
 #define KJ_DEV __device__ __forceinline__
@@ -75,13 +71,10 @@ struct Warp {
     KJ_DEV uint32_t shfl_xor(uint32_t v, int m) const { return __shfl_xor_sync(KJ_FULL, v, m); }
     KJ_DEV int shfl_xor(int v, int m) const { return __shfl_xor_sync(KJ_FULL, v, m); }
     KJ_DEV double shfl_d(double v, int src) const { return __shfl_sync(KJ_FULL, v, src); }
-    // exchange with lane^1; only the two lanes of a pair take part (they may be in a divergent region together)
-    KJ_DEV uint64_t pair_xchg64(uint64_t v) const { return __shfl_xor_sync(3u << (lane & 30), (unsigned long long)v, 1); }
     // redux.sync: one instruction per 32-bit warp reduction (sm_80+)
     KJ_DEV uint32_t redux_max(uint32_t v) const { return __reduce_max_sync(KJ_FULL, v); }
     KJ_DEV uint32_t redux_min(uint32_t v) const { return __reduce_min_sync(KJ_FULL, v); }
 };
-static KJ_DEV int kj_fns(uint32_t mask, int n) { return (int)__fns(mask, 0, n + 1); }     // index of the n-th (0-based) set bit
 #endif
 
 // collectives built on the primitives (identical in both builds)

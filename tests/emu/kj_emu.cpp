@@ -40,7 +40,6 @@ struct Sched {
     static const int NL = 32;
     void* sp[NL]; char* stack[NL]; bool done[NL]; void* main_sp;
     int cur; uint64_t slots[2][NL]; int arrived[2]; long gen[NL]; long complete; long progress; int ndone;
-    uint64_t pslot[2][NL]; long pgen[NL];
     void (*body)(Sched*, int, void*); void* arg;
     size_t stack_size;
     Sched() : stack_size(256 * 1024) { for (int i = 0; i < NL; i++) stack[i] = (char*)aligned_alloc(64, stack_size); }
@@ -78,7 +77,7 @@ static void fiber_entry() {
 static void run_warp(Sched* s, void (*body)(Sched*, int, void*), void* arg) {
     tls_sched = s; s->body = body; s->arg = arg; s->arrived[0] = s->arrived[1] = 0; s->complete = -1; s->progress = 0; s->ndone = 0;
     for (int i = 0; i < Sched::NL; i++) {
-        s->done[i] = false; s->gen[i] = 0; s->pgen[i] = 0;
+        s->done[i] = false; s->gen[i] = 0;
         uintptr_t top = ((uintptr_t)(s->stack[i] + s->stack_size)) & ~(uintptr_t)63;
         void** p = (void**)(top - 64);
         // layout popped by kjemu_ctx_switch: r15 r14 r13 r12 rbx rbp, then ret -> fiber_entry (rsp must be 8 mod 16 at entry)
@@ -98,13 +97,6 @@ uint64_t rendezvous(Sched* s, int lane, uint64_t v, int kind, int arg) {
     while (s->complete < g) { s->yield_from(lane); if (++spins > 100000) { fprintf(stderr, "kjemu: stuck collective\n"); abort(); } }
     int src = kind == 0 ? (arg & 31) : ((lane ^ arg) & 31);
     return s->slots[par][src];
-}
-uint64_t pair_exchange(Sched* s, int lane, uint64_t v) {
-    long g = s->pgen[lane]; int par = (int)(g & 1); int partner = lane ^ 1;
-    s->pslot[par][lane] = v; s->pgen[lane] = g + 1; s->progress++;
-    int spins = 0;
-    while (s->pgen[partner] <= g) { if (s->done[partner]) { fprintf(stderr, "kjemu: pair exchange with an exited lane\n"); abort(); } s->yield_from(lane); if (++spins > 100000) { fprintf(stderr, "kjemu: stuck pair exchange\n"); abort(); } }
-    return s->pslot[par][partner];
 }
 uint32_t rendezvous_ballot(Sched* s, int lane, bool p) {
     long g = s->gen[lane]++; int par = (int)(g & 1);
