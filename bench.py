@@ -240,7 +240,13 @@ def main():
             c = ctr.as_dict()
             alg = (c["fmindex"] * 10 + c["scanned_bytes"] + c["lf_steps"] * 11 + c["get_suffix"] * 6 + c["bases"] + 8 * n_or) / n_or   # SURVEY.md 8d definition
             ach = alg * n / (kernel_ms / 1000.0) / 1e9
-            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            traffic = None
+            try:   # dram__bytes_read.sum + dram__bytes_write.sum per item from the latest `ncu --set full` capture (profiles/traffic.json)
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.mode]
+                traffic = tj["dram_bytes_per_item"] * n
+            except Exception:
+                pass
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                                 "algorithmic_bytes_per_item": alg, "peak_source": peak_src,
                                 "note": "numerator = reference algorithm's bytes (instrumented oracle, %d-pair sample) x items per launch; kernel time from CUDA events on the launch stream" % n_or}
             n_cpu = args.cpu_sample or max(20000, min(3000000, 20000 * cores))

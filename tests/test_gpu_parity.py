@@ -132,3 +132,33 @@ def test_wide_index_kernels_and_no_kmer_table(kb, golden, monkeypatch):
             clf.close()
         for k in env:
             monkeypatch.delenv(k)
+
+
+def test_cli_matches_reference_output_format(kb, golden, tmp_path):
+    """kaiju-b200 (kj_cli.cpp) on the golden FASTQ files: same C/U lines as the reference, in input order."""
+    import gzip, shutil, subprocess
+    from conftest import ROOT
+    cli = os.path.join(ROOT, "kaiju_b200", "kaiju-b200")
+    assert os.path.exists(cli)
+    gold = os.path.join(ROOT, "tests", "golden")
+    fq = {}
+    for name in ("pe150_1", "pe150_2"):
+        fq[name] = str(tmp_path / (name + ".fq"))
+        with gzip.open(os.path.join(gold, name + ".fq.gz"), "rb") as a, open(fq[name], "wb") as b:
+            shutil.copyfileobj(a, b)
+    for mode, cfg, extra in (("mem", "mem_default", []), ("greedy", "greedy_default", []), ("mem", "mem_noseg", ["-X"]), ("greedy", "greedy_e5", ["-e", "5"])):
+        out = str(tmp_path / (cfg + ".tsv"))
+        # gz input for mate 1 (zlib path), plain for mate 2; -z is accepted and ignored
+        subprocess.check_call([cli, "-t", golden.nodes, "-f", golden.fmi, "-i", os.path.join(gold, "pe150_1.fq.gz"), "-j", fq["pe150_2"], "-a", mode, "-z", "4", "-v", "-o", out] + extra)
+        etax, ebest, _ = golden.expected(cfg, "pe150"); names = golden.reads("pe150")[0]
+        lines = open(out).read().splitlines()
+        assert len(lines) == len(names)
+        for ln, nm, t, b in zip(lines, names, etax, ebest):
+            p = ln.split("\t")
+            if t:
+                assert p[:4] == ["C", nm, str(int(t)), str(int(b))], (ln, nm, t, b)
+            else:
+                assert p == ["U", nm, "0"], ln
+    # error path: -p is refused, missing arguments print usage and exit non-zero
+    assert subprocess.call([cli, "-t", golden.nodes, "-f", golden.fmi, "-i", fq["pe150_1"], "-p"], stderr=subprocess.DEVNULL) != 0
+    assert subprocess.call([cli, "-f", golden.fmi], stderr=subprocess.DEVNULL) != 0
