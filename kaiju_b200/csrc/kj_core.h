@@ -21,10 +21,11 @@
 // per-warp shared-memory carve-up
 // ---------------------------------------------------------------------------------------------
 #define KJ_SEG_CAP(max_frag) ((max_frag) / 4u + 8u)
+#define KJ_VKEY_SMEM 64u
 struct KjKept { uint64_t lo; uint32_t len; uint32_t aux; };     // one suffix interval (an SI of bwt.h:25-34)
 
 struct KjSmemLayout {
-    uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, aa_off, aa_stride, frag_off, hflag_off,
+    uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, vkey_off, aa_off, aa_stride, frag_off, hflag_off,
              segcnt_off, seghist_off, segs_off, total;
 };
 static KJ_HD uint32_t kj_align(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -35,6 +36,7 @@ static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
     L.segs_off = o; o += 8u * KJ_SEG_CAP(p.max_frag);                     // {int begin,end}
     L.qpay_off = o; o += 4u * kj_align(p.item_cap, 2);
     L.ids_off = o; o += 4u * 24u;
+    L.vkey_off = o; o += (p.mode == 1 ? 8u * KJ_VKEY_SMEM : 0u);         // greedy: keys of the first variants (the rest live in global scratch)
     L.aa_stride = kj_align(p.max_len + 4, 8);
     L.aa_off = o; o += 4u * L.aa_stride;
     L.frag_off = o; o += kj_align(p.max_frag + 8, 8);

@@ -24,17 +24,19 @@ static KJ_HD uint32_t kj_greedy_scratch_bytes(const KjRunParams& rp) { return rp
 
 struct KjMatch { uint64_t lo; uint32_t len; uint16_t qi, ql; };    // one SI: interval + query position/length
 
-struct KjVQueue { uint64_t* key; KjVariant* v; uint32_t n; };      // key[s] = kj_qkey(score, order), 0 = free; n: high-water mark (uniform)
+// key(s) = kj_qkey(score, order), 0 = free; the first KJ_VKEY_SMEM keys sit in shared memory (the pop scans them every iteration)
+struct KjVQueue { uint64_t* skey; uint64_t* gkey; KjVariant* v; uint32_t n;      // n: high-water mark (uniform)
+    KJ_DEV uint64_t& key(uint32_t s) const { return s < KJ_VKEY_SMEM ? skey[s] : gkey[s]; } };
 
 // compact live variants to the front (called when the ring is full)
 static KJ_DEV void kj_vq_compact(KjWarpCtx& cx, KjVQueue& vq) {
     const Warp& w = cx.w; uint32_t out = 0;
     for (uint32_t b = 0; b < vq.n; b += 32) {
-        uint32_t s = b + (uint32_t)w.lane; bool live = s < vq.n && vq.key[s] != 0;
-        KjVariant tmp; uint64_t tk = 0; if (live) { tmp = vq.v[s]; tk = vq.key[s]; }
+        uint32_t s = b + (uint32_t)w.lane; bool live = s < vq.n && vq.key(s) != 0;
+        KjVariant tmp; uint64_t tk = 0; if (live) { tmp = vq.v[s]; tk = vq.key(s); }
         uint32_t mask = w.ballot(live);
         w.sync();
-        if (live) { const uint32_t d = out + (uint32_t)kj_popc(mask & lanemask_lt(w.lane)); vq.v[d] = tmp; vq.key[d] = tk; }
+        if (live) { const uint32_t d = out + (uint32_t)kj_popc(mask & lanemask_lt(w.lane)); vq.v[d] = tmp; vq.key(d) = tk; }
         out += (uint32_t)kj_popc(mask);
         w.sync();
     }
@@ -54,7 +56,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
     uint16_t* pre = (uint16_t*)(cx.smem + cx.L.pre_off);               // pre[t] = sum diag(frag[0..t))
     KjMatch* res = (KjMatch*)(cx.smem + cx.L.res_off);                  // per-j chain results, then recorded matches
     KjMatch* cls = (KjMatch*)(cx.smem + cx.L.res2_off);                 // recorded matches sorted into classes
-    KjVQueue vq; vq.key = (uint64_t*)cx.gscratch; vq.v = (KjVariant*)((uint8_t*)cx.gscratch + 8u * KJ_VARIANT_CAP); vq.n = 0;
+    KjVQueue vq; vq.skey = (uint64_t*)(cx.smem + cx.L.vkey_off); vq.gkey = (uint64_t*)cx.gscratch; vq.v = (KjVariant*)((uint8_t*)cx.gscratch + 8u * KJ_VARIANT_CAP); vq.n = 0;
     uint32_t best = 0, nbest = 0;                                        // best_match_score, best_matches_SI.size()  (uniform)
     best_out = 0;
 
@@ -62,7 +64,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
         // ---------------- getNextFragment(best): top of both queues (ConsumerThread.cpp:272-283)
         w.sync();
         uint64_t kb = 0; uint32_t slot_b = 0;
-        for (uint32_t s = (uint32_t)w.lane; s < vq.n; s += 32) { uint64_t k = vq.key[s]; if (k > kb) { kb = k; slot_b = s; } }
+        for (uint32_t s = (uint32_t)w.lane; s < vq.n; s += 32) { uint64_t k = vq.key(s); if (k > kb) { kb = k; slot_b = s; } }
         uint64_t gb = warp_max_u64(w, kb);
         uint64_t ka = 0; uint32_t slot_a = 0;
         for (uint32_t s = (uint32_t)w.lane; s < q.n; s += 32) { uint64_t k = q.key[s]; if (k > ka) { ka = k; slot_a = s; } }
@@ -83,7 +85,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
             num_mm = V.num_mm; matchlen = V.matchlen; diff = V.diff; si0 = V.lo; si1 = V.hi; nsub = num_mm;
             if ((uint32_t)w.lane < nsub) mysub = V.subs[w.lane];
             w.sync();
-            if (w.lane == 0) vq.key[sl] = 0;
+            if (w.lane == 0) vq.key(sl) = 0;
         }
         kj_load_frag(cx, arr, start, len);
         if ((uint32_t)w.lane < nsub) frag[mysub >> 5] = (uint8_t)(mysub & 31u);
@@ -211,7 +213,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
                                     V->lo = (uint64_t)lo; V->hi = (uint64_t)hi; V->pay = kj_qpay(arr, true, start, new_len);
                                     V->diff = diff + (int)tb.b62[o][sub] - (int)tb.b62[sub][sub];
                                     V->matchlen = (uint16_t)(sm.ql + 1u); V->num_mm = (uint8_t)(ns + 1u); V->pad = 0; V->pad2 = 0;
-                                    vq.key[vq.n + rk] = kj_qkey((uint32_t)after, KJ_ORDER_LATE + q.late + rk);
+                                    vq.key(vq.n + rk) = kj_qkey((uint32_t)after, KJ_ORDER_LATE + q.late + rk);
                                 }
                                 vq.n += cnt; q.late += cnt;
                             }
