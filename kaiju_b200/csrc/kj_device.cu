@@ -10,7 +10,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
-#include <mutex>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -163,12 +163,13 @@ extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, cons
     if (device < 0 || device >= ndev) { kj_err() = "device ordinal out of range"; return KJ_ERR_ARG; }
     CK(cudaSetDevice(device));
     kj_ctx* c = new kj_ctx(); c->device = device; c->params = *params;
+    std::unique_ptr<kj_ctx, void (*)(kj_ctx*)> guard(c, kj_destroy);      // every early return below releases what was allocated so far
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); c->sm_count = prop.multiProcessorCount;
-    rc = kj_build_host_index(*index, *taxonomy, c->H); if (rc) { delete c; return rc; }
+    rc = kj_build_host_index(*index, *taxonomy, c->H); if (rc) return rc;
     KjHostIndex& H = c->H; uint64_t tot = 0;
     if ((rc = upload(H.rank, &c->d_rank, tot)) || (rc = upload(H.letters, &c->d_letters, tot)) || (rc = upload(H.sa_tax, &c->d_sa_tax, tot)) ||
         (rc = upload(H.seq_tax, &c->d_seq_tax, tot)) || (rc = upload(H.tax_parent, &c->d_tax_parent, tot)) || (rc = upload(H.tax_depth, &c->d_tax_depth, tot)) ||
-        (rc = upload(H.tax_id, &c->d_tax_id, tot)) || (rc = upload(H.lnfact, &c->d_lnfact, tot)) || (rc = (H.wide ? upload(H.kmer, &c->d_kmer, tot) : upload(H.kmer32, &c->d_kmer, tot)))) { kj_destroy(c); return rc; }
+        (rc = upload(H.tax_id, &c->d_tax_id, tot)) || (rc = upload(H.lnfact, &c->d_lnfact, tot)) || (rc = (H.wide ? upload(H.kmer, &c->d_kmer, tot) : upload(H.kmer32, &c->d_kmer, tot)))) return rc;
     CK(cudaMalloc((void**)&c->d_tables, sizeof(KjTables))); CK(cudaMemcpy(c->d_tables, &H.tables, sizeof(KjTables), cudaMemcpyHostToDevice));
     KjDevIndex& D = c->dix; memset(&D, 0, sizeof D);
     D.rank = (const KjRankBlock*)c->d_rank; D.nb = H.nb; D.letters = (const uint64_t*)c->d_letters; D.bwtlen = H.bwtlen; D.alen = H.alen;
@@ -186,7 +187,7 @@ extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, cons
     CK(cudaMemset(c->d_err, 0, sizeof(uint32_t)));
     for (int s = 0; s < 2; s++) CK(cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev_a)); CK(cudaEventCreate(&c->ev_b));
-    *out = c; return KJ_OK;
+    *out = guard.release(); return KJ_OK;
 }
 
 extern "C" int kj_set_params(kj_ctx* c, const kj_params* p) {
