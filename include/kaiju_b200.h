@@ -99,6 +99,11 @@ void kj_destroy(kj_ctx *ctx);
  * match length (MEM) or score (Greedy) -- column 4 of the reference's -v output.  Blocking; H2D/D2H inside. */
 int kj_classify(kj_ctx *ctx, const char *seq1, const uint64_t *off1, const char *seq2, const uint64_t *off2,
                 uint64_t n_reads, uint64_t *taxon_out, uint32_t *best_out);
+/* Same, plus column 5 of the reference's -v output (ConsumerThread.cpp:527-536, 614-623): the match-id set of every classified read,
+ * ascending, ids_out[i*KJ_MAX_MATCH_IDS .. +nids_out[i]) (at most 21 ids: max_match_ids = 20 is checked before each insertion). */
+#define KJ_MAX_MATCH_IDS 21
+int kj_classify_verbose(kj_ctx *ctx, const char *seq1, const uint64_t *off1, const char *seq2, const uint64_t *off2,
+                        uint64_t n_reads, uint64_t *taxon_out, uint32_t *best_out, uint64_t *ids_out, uint8_t *nids_out);
 /* Device buffers (same layout, all pointers in the context's device memory), enqueued on `cuda_stream`
  * (a cudaStream_t, NULL = default stream); returns after the launch, results are ready when the stream is.
  * max_len1/max_len2: upper bounds of the mate lengths in the batch (0 = let the library compute them on the device). */

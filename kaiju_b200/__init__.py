@@ -60,6 +60,7 @@ def lib():
         L.kj_set_params.argtypes = [C.c_void_p, C.POINTER(KjParams)]
         L.kj_destroy.argtypes = [C.c_void_p]
         L.kj_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.kj_classify_verbose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kj_classify_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
         L.kj_kernel_launches.restype = C.c_uint64; L.kj_kernel_launches.argtypes = [C.c_void_p]
@@ -134,6 +135,20 @@ class Classifier:
         _check(lib().kj_classify(self._ctx, seq1.ctypes.data, off1.ctypes.data, p2, o2, n, tax.ctypes.data,
                                  best.ctypes.data if want_best else None))
         return (tax, best) if want_best else tax
+
+    def classify_verbose(self, seq1, off1, seq2=None, off2=None):
+        """taxon, best, and the ascending match-id set per read (columns 3-5 of `kaiju -v`)."""
+        n = len(off1) - 1
+        seq1 = np.ascontiguousarray(seq1, dtype=np.uint8); off1 = np.ascontiguousarray(off1, dtype=np.uint64)
+        p2 = o2 = None
+        if seq2 is not None:
+            seq2 = np.ascontiguousarray(seq2, dtype=np.uint8); off2 = np.ascontiguousarray(off2, dtype=np.uint64)
+            p2, o2 = seq2.ctypes.data, off2.ctypes.data
+        tax = np.zeros(n, dtype=np.uint64); best = np.zeros(n, dtype=np.uint32)
+        ids = np.zeros((n, 21), dtype=np.uint64); nids = np.zeros(n, dtype=np.uint8)
+        _check(lib().kj_classify_verbose(self._ctx, seq1.ctypes.data, off1.ctypes.data, p2, o2, n, tax.ctypes.data, best.ctypes.data,
+                                         ids.ctypes.data, nids.ctypes.data))
+        return tax, best, [tuple(int(x) for x in ids[i, :nids[i]]) for i in range(n)]
 
     def classify_ptrs(self, seq1_ptr, off1_ptr, seq2_ptr, off2_ptr, n, tax_ptr, best_ptr):
         """Host pointers (e.g. pinned torch tensors' data_ptr())."""

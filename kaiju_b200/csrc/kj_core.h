@@ -66,6 +66,7 @@ struct KjWarpCtx {
     KjSmemLayout L;
     KjKept* spill;                      // global scratch of this warp: rp->scratch_entries entries
     void* gscratch;                     // global scratch of this warp for the greedy variant queue
+    uint32_t nids;                      // size of the match-id set left in shared memory by the last item (uniform)
     uint32_t* err;                      // global error flags: 1 item-queue overflow, 2 spill overflow, 4 greedy queue overflow
 };
 static KJ_DEV void kj_flag_error(KjWarpCtx& cx, uint32_t bit) {
@@ -497,6 +498,7 @@ static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
             }
         }
     }
+    cx.nids = nids;
     if (nids == 0) return KJ_TAX_BAD;
     w.sync();
     if (nids == 1) return ids[0];                                         // returned without a nodes.dmp check (ConsumerThread.cpp:625)
@@ -637,7 +639,7 @@ template <class IdxT> static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, K
 template <int MODE, class IdxT>
 static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1, const uint8_t* s2, int n2, bool paired, uint32_t& best_out) {
     const KjRunParams& rp = *cx.rp;
-    best_out = 0;
+    best_out = 0; cx.nids = 0;
     const int m3 = (int)rp.m * 3;
     // short-read gate (648-653): SE len1 < 3m; PE only if BOTH mates are short
     if ((!paired && n1 < m3) || (paired && n1 < m3 && n2 < m3)) return KJ_TAX_BAD;

@@ -37,7 +37,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
                    const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
                    const uint8_t* __restrict__ seq2, const uint64_t* __restrict__ off2,
                    uint64_t base1, uint64_t base2, uint64_t n_reads,
-                   uint64_t* __restrict__ taxon_out, uint32_t* __restrict__ best_out,
+                   uint64_t* __restrict__ taxon_out, uint32_t* __restrict__ best_out, uint64_t* __restrict__ ids_out, uint8_t* __restrict__ nids_out,
                    unsigned long long* __restrict__ counter, KjKept* __restrict__ spill, uint8_t* __restrict__ gscratch,
                    uint32_t gscratch_bytes, uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -69,10 +69,19 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
         uint64_t b0 = 0, b1 = 0; if (paired) { b0 = off2[r] - base2; b1 = off2[r + 1] - base2; }
         uint32_t best = 0;
         uint32_t t = kj_classify_item<MODE, IdxT>(cx, seq1 + a0, (int)(a1 - a0), paired ? seq2 + b0 : nullptr, (int)(b1 - b0), paired, best);
+        const uint64_t id = t == KJ_TAX_BAD ? 0ull : sh->ix.tax_id[t];
         if (cx.w.lane == 0) {
-            uint64_t id = t == KJ_TAX_BAD ? 0ull : sh->ix.tax_id[t];
             taxon_out[r] = id;
             if (best_out) best_out[r] = id ? best : 0u;
+        }
+        if (ids_out) {   // column 5 of the reference's -v output: the match-id set in ascending order (std::set), classified reads only
+            const uint32_t nids = id ? cx.nids : 0u; const uint32_t* ids = (const uint32_t*)(cx.smem + cx.L.ids_off);
+            if ((uint32_t)cx.w.lane < nids) {
+                const uint64_t mine = sh->ix.tax_id[ids[cx.w.lane]]; uint32_t rank = 0;
+                for (uint32_t u = 0; u < nids; u++) rank += sh->ix.tax_id[ids[u]] < mine ? 1u : 0u;
+                ids_out[r * KJ_MAX_IDS + rank] = mine;
+            }
+            if (cx.w.lane == 0) nids_out[r] = (uint8_t)nids;
         }
         cx.w.sync();
     }
@@ -102,6 +111,7 @@ struct kj_ctx {
     // staging for kj_classify (host buffers)
     uint8_t* d_seq[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; size_t d_seq_cap[2][2] = {{0, 0}, {0, 0}};
     uint64_t* d_off[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; uint64_t* d_tax[2] = {nullptr, nullptr}; uint32_t* d_best[2] = {nullptr, nullptr};
+    uint64_t* d_ids[2] = {nullptr, nullptr}; uint8_t* d_nids[2] = {nullptr, nullptr}; size_t d_ids_cap = 0;
     size_t d_reads_cap = 0;
     uint64_t launches = 0; double last_kernel_ms = 0.0;
     int grid = 0; size_t smem_bytes = 0; int cfg_mode = -1;
@@ -202,7 +212,8 @@ extern "C" void kj_destroy(kj_ctx* c) {
     cudaSetDevice(c->device);
     void* ptrs[] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_tax_parent, c->d_tax_depth, c->d_tax_id, c->d_lnfact, c->d_kmer, c->d_tables, c->d_ix,
                     c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evtab, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
-                    c->d_seq[0][0], c->d_seq[0][1], c->d_seq[1][0], c->d_seq[1][1], c->d_off[0][0], c->d_off[0][1], c->d_off[1][0], c->d_off[1][1]};
+                    c->d_seq[0][0], c->d_seq[0][1], c->d_seq[1][0], c->d_seq[1][1], c->d_off[0][0], c->d_off[0][1], c->d_off[1][0], c->d_off[1][1],
+                    c->d_ids[0], c->d_ids[1], c->d_nids[0], c->d_nids[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int s = 0; s < 2; s++) if (c->stream[s]) cudaStreamDestroy(c->stream[s]);
     if (c->ev_a) cudaEventDestroy(c->ev_a); if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -211,7 +222,8 @@ extern "C" void kj_destroy(kj_ctx* c) {
 
 // one launch over reads [0,n) whose sequences/offsets are resident on the device
 static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_off1, const uint8_t* d_seq2, const uint64_t* d_off2, uint64_t base1, uint64_t base2,
-                  uint64_t n, uint32_t max1, uint32_t max2, uint64_t* d_tax, uint32_t* d_best, cudaStream_t st, bool time_it) {
+                  uint64_t n, uint32_t max1, uint32_t max2, uint64_t* d_tax, uint32_t* d_best, cudaStream_t st, bool time_it,
+                  uint64_t* d_ids = nullptr, uint8_t* d_nids = nullptr) {
     if (max1 > KJ_MAX_READ_LEN || max2 > KJ_MAX_READ_LEN) { kj_err() = "read longer than KJ_MAX_READ_LEN (381 bases) is not supported yet"; return KJ_ERR_UNSUPPORTED; }
     KjRunParams rp; kj_fill_run_params(c->params, std::max(max1, max2), rp);
     int rc = ensure_evalue_table(c, rp, max1, max2, st); if (rc) return rc;
@@ -221,7 +233,7 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
     if (time_it) CK(cudaEventRecord(c->ev_a, st));
     const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
-#define KJ_LAUNCH(M, T) kj_classify_kernel<M, T><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, \
+#define KJ_LAUNCH(M, T) kj_classify_kernel<M, T><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, \
             c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
             c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), c->d_err)
     if (rp.mode == 0) { if (c->H.wide) KJ_LAUNCH(0, uint64_t); else KJ_LAUNCH(0, uint32_t); }
@@ -272,9 +284,9 @@ static int ensure_staging(kj_ctx* c, int slot, size_t bytes1, size_t bytes2, siz
     return KJ_OK;
 }
 
-extern "C" int kj_classify(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
-                           uint64_t* taxon_out, uint32_t* best_out) {
-    if (!c || !seq1 || !off1 || !taxon_out || (seq2 && !off2)) { kj_err() = "kj_classify: null argument"; return KJ_ERR_ARG; }
+static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
+                         uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out) {
+    if (!c || !seq1 || !off1 || !taxon_out || (seq2 && !off2) || ((ids_out == nullptr) != (nids_out == nullptr))) { kj_err() = "kj_classify: null argument"; return KJ_ERR_ARG; }
     if (n == 0) return KJ_OK;
     CK(cudaSetDevice(c->device));
     const bool paired = seq2 != nullptr;
@@ -290,6 +302,13 @@ extern "C" int kj_classify(kj_ctx* c, const char* seq1, const uint64_t* off1, co
         for (unsigned t = 0; t < nthr; t++) { max1 = std::max(max1, m1[t]); max2 = std::max(max2, m2[t]); }
     }
     int rc = ensure_staging(c, 0, 0, 0, std::min<uint64_t>(n, KJ_CHUNK_READS)); if (rc) return rc;
+    if (ids_out && c->d_ids_cap < c->d_reads_cap) {
+        for (int s = 0; s < 2; s++) {
+            if (c->d_ids[s]) cudaFree(c->d_ids[s]); if (c->d_nids[s]) cudaFree(c->d_nids[s]); c->d_ids[s] = nullptr; c->d_nids[s] = nullptr;
+            CK(cudaMalloc((void**)&c->d_ids[s], c->d_reads_cap * KJ_MAX_IDS * sizeof(uint64_t))); CK(cudaMalloc((void**)&c->d_nids[s], c->d_reads_cap));
+        }
+        c->d_ids_cap = c->d_reads_cap;
+    }
     // software pipeline over chunks: H2D + kernel + D2H of chunk k on stream k&1 overlap with chunk k+1
     double kernel_ms = 0.0;
     for (uint64_t start = 0, k = 0; start < n; start += KJ_CHUNK_READS, k++) {
@@ -305,14 +324,28 @@ extern "C" int kj_classify(kj_ctx* c, const char* seq1, const uint64_t* off1, co
             CK(cudaMemcpyAsync(c->d_off[s][1], off2 + start, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         }
         rc = launch(c, s, c->d_seq[s][0], c->d_off[s][0], paired ? c->d_seq[s][1] : nullptr, paired ? c->d_off[s][1] : nullptr, b1, b2, cnt, max1, max2,
-                    c->d_tax[s], best_out ? c->d_best[s] : nullptr, st, false);
+                    c->d_tax[s], best_out ? c->d_best[s] : nullptr, st, false, ids_out ? c->d_ids[s] : nullptr, ids_out ? c->d_nids[s] : nullptr);
         if (rc) return rc;
         CK(cudaMemcpyAsync(taxon_out + start, c->d_tax[s], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         if (best_out) CK(cudaMemcpyAsync(best_out + start, c->d_best[s], cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (ids_out) {
+            CK(cudaMemcpyAsync(ids_out + start * KJ_MAX_IDS, c->d_ids[s], cnt * KJ_MAX_IDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(nids_out + start, c->d_nids[s], cnt, cudaMemcpyDeviceToHost, st));
+        }
     }
     CK(cudaStreamSynchronize(c->stream[0])); CK(cudaStreamSynchronize(c->stream[1]));
     (void)kernel_ms;
     return check_err_flag(c);
+}
+
+extern "C" int kj_classify(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
+                           uint64_t* taxon_out, uint32_t* best_out) {
+    return classify_host(c, seq1, off1, seq2, off2, n, taxon_out, best_out, nullptr, nullptr);
+}
+extern "C" int kj_classify_verbose(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
+                                   uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out) {
+    if (!ids_out || !nids_out) { kj_err() = "kj_classify_verbose: null argument"; return KJ_ERR_ARG; }
+    return classify_host(c, seq1, off1, seq2, off2, n, taxon_out, best_out, ids_out, nids_out);
 }
 
 extern "C" uint64_t kj_kernel_launches(const kj_ctx* c) { return c ? c->launches : 0; }

@@ -116,7 +116,7 @@ uint32_t rendezvous_ballot(Sched* s, int lane, bool p) {
 struct EmuCtx {
     KjHostIndex H; KjDevIndex D; kj_params P; std::vector<uint16_t> evtab; uint32_t ev1 = 0, ev2 = 0;
 };
-struct ItemArg { EmuCtx* c; KjRunParams* rp; uint8_t* smem; KjKept* spill; void* gscratch; uint32_t* err; const uint8_t* s1; int n1; const uint8_t* s2; int n2; bool paired; uint32_t tax[32]; uint32_t best[32]; };
+struct ItemArg { uint32_t nids; uint32_t ids[24]; EmuCtx* c; KjRunParams* rp; uint8_t* smem; KjKept* spill; void* gscratch; uint32_t* err; const uint8_t* s1; int n1; const uint8_t* s2; int n2; bool paired; uint32_t tax[32]; uint32_t best[32]; };
 
 static void item_body(kjemu::Sched* s, int lane, void* a) {
     ItemArg* A = (ItemArg*)a;
@@ -127,6 +127,7 @@ static void item_body(kjemu::Sched* s, int lane, void* a) {
     uint32_t t = A->rp->mode == 0 ? (wide ? kj_classify_item<0, uint64_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best) : kj_classify_item<0, uint32_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best))
         : wide ? kj_classify_item<1, uint64_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best) : kj_classify_item<1, uint32_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best);
     A->tax[lane] = t; A->best[lane] = best;
+    if (lane == 0) { A->nids = cx.nids; const uint32_t* ids = (const uint32_t*)(cx.smem + cx.L.ids_off); for (uint32_t u = 0; u < cx.nids && u < 24; u++) A->ids[u] = ids[u]; }
 }
 
 extern "C" {

@@ -162,3 +162,16 @@ def test_cli_matches_reference_output_format(kb, golden, tmp_path):
     # error path: -p is refused, missing arguments print usage and exit non-zero
     assert subprocess.call([cli, "-t", golden.nodes, "-f", golden.fmi, "-i", fq["pe150_1"], "-p"], stderr=subprocess.DEVNULL) != 0
     assert subprocess.call([cli, "-f", golden.fmi], stderr=subprocess.DEVNULL) != 0
+
+
+@pytest.mark.parametrize("cfg", ["mem_default", "mem_m5", "greedy_default", "greedy_e5"])
+def test_verbose_id_sets_match_reference_column5(kb, gclf, golden, cfg):
+    """kj_classify_verbose: the match-id set (column 5 of `kaiju -v`) incl. the 21-id cap case, ids missing from nodes.dmp, taxon 0."""
+    names, s1, o1, s2, o2 = golden.reads("pe150")
+    gclf.set_params(kb_params(kb, GOLDEN_CONFIGS[cfg]))
+    tax, best, ids = gclf.classify_verbose(s1, o1, s2, o2)
+    etax, ebest, eids = golden.expected(cfg, "pe150")
+    assert np.array_equal(tax, etax) and np.array_equal(best, ebest)
+    for i, nm in enumerate(names):
+        assert ids[i] == (eids[i] if etax[i] else ()), (nm, ids[i], eids[i])
+    assert max(len(x) for x in ids) == 21            # the capped read is in the fixture
