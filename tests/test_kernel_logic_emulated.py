@@ -39,3 +39,21 @@ def test_emulated_kernel_matches_reference_golden(emu, golden, cfg, tag):
     etax, ebest, _ = golden.expected(cfg, tag)
     bad = np.nonzero((tax != etax) | (best != ebest))[0]
     assert len(bad) == 0, [(names[i], int(tax[i]), int(etax[i]), int(best[i]), int(ebest[i])) for i in bad[:5]]
+
+
+def test_emulated_kernel_matches_oracle_on_random_parameters(emu, golden):
+    """Seeded sweep over the CLI parameter space (-a, -m, -e, -s, -E, -x/-X): kernel logic (emulated) == oracle (pinned to the reference)."""
+    import random
+    rnd = random.Random(7)
+    names, s1, o1, s2, o2 = golden.reads("pe150")
+    orc = Oracle(golden.fmi, golden.nodes)
+    for trial in range(10):
+        mode = rnd.choice(["mem", "greedy"])
+        kw = dict(mode=mode, m=rnd.choice([3, 6, 9, 11, 12, 15, 25]), seg=rnd.random() < 0.7)
+        if mode == "greedy":
+            kw.update(e=rnd.choice([0, 1, 2, 3, 4, 6, 8]), s=rnd.choice([20, 40, 65, 80, 110]), E=rnd.choice([10.0, 0.01, 1e-5, 1e-12]))
+        P = make_params(**kw)
+        otax, obest = orc.classify_batch(P, s1, o1, s2, o2)
+        tax, best = emu_classify(emu, golden.fmi, golden.nodes, P, s1, o1, s2, o2)
+        bad = np.nonzero((tax != otax) | (best != obest))[0]
+        assert len(bad) == 0, (kw, [(names[i], int(tax[i]), int(otax[i]), int(best[i]), int(obest[i])) for i in bad[:5]])
