@@ -241,20 +241,29 @@ static KJ_DEV uint32_t kj_nuc(uint8_t ch) {          // nuc2int (ConsumerThread.
     uint32_t u = ch & 0xDFu;
     return u == 'A' ? 0u : u == 'C' ? 1u : u == 'G' ? 2u : (u == 'T' || u == 'U') ? 3u : 4u;
 }
-static KJ_DEV void kj_translate_mate(KjWarpCtx& cx, KjQueue& q, int mate, const uint8_t* seq, int n, bool greedy) {
+// Both mates are translated and split in the SAME loops (array a = 2*mate + strand): the four arrays are independent, so
+// their load/ballot/bit-twiddling chains overlap instead of running back to back (the kernel is bound by dependent latency).
+static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s1, int n1, bool do1, const uint8_t* s2, int n2, bool do2, bool greedy) {
     const Warp& w = cx.w; const KjTables& tb = *cx.tb;
-    uint8_t* aaF = cx.smem + cx.L.aa_off + (uint32_t)(2 * mate) * cx.L.aa_stride;
-    uint8_t* aaR = aaF + cx.L.aa_stride;
-    const int na = n - 2;
-    // 30 codon positions per pass: every lane decodes ONE base, its two successors come from the next lanes
-    for (int b = 0; b < na; b += 30) {
+    uint8_t* aa = cx.smem + cx.L.aa_off; const uint32_t st = cx.L.aa_stride;
+    const int na1 = do1 ? n1 - 2 : 0, na2 = do2 ? n2 - 2 : 0;
+    const int namax = na1 > na2 ? na1 : na2;
+    // 30 codon positions per pass: every lane decodes ONE base per mate, its two successors come from the next lanes
+    for (int b = 0; b < namax; b += 30) {
         const int pos = b + w.lane;
-        const uint32_t c0 = pos < n ? kj_nuc(seq[pos]) : 4u;
-        const uint32_t c1 = w.shfl(c0, w.lane + 1), c2 = w.shfl(c0, w.lane + 2);
-        if (w.lane < 30 && pos < na) {
-            const bool ok = (c0 | c1 | c2) < 4u;
-            aaF[pos] = ok ? tb.codon_aa[c0 << 4 | c1 << 2 | c2] : (uint8_t)0;
-            aaR[na - 1 - pos] = ok ? tb.codon_aa[(3u - c2) << 4 | (3u - c1) << 2 | (3u - c0)] : (uint8_t)0;
+        const uint32_t x0 = (do1 && pos < n1) ? kj_nuc(s1[pos]) : 4u, y0 = (do2 && pos < n2) ? kj_nuc(s2[pos]) : 4u;
+        const uint32_t x1 = w.shfl(x0, w.lane + 1), x2 = w.shfl(x0, w.lane + 2), y1 = w.shfl(y0, w.lane + 1), y2 = w.shfl(y0, w.lane + 2);
+        if (w.lane < 30) {
+            if (pos < na1) {
+                const bool ok = (x0 | x1 | x2) < 4u;
+                aa[pos] = ok ? tb.codon_aa[x0 << 4 | x1 << 2 | x2] : (uint8_t)0;
+                aa[st + (uint32_t)(na1 - 1 - pos)] = ok ? tb.codon_aa[(3u - x2) << 4 | (3u - x1) << 2 | (3u - x0)] : (uint8_t)0;
+            }
+            if (pos < na2) {
+                const bool ok = (y0 | y1 | y2) < 4u;
+                aa[2u * st + (uint32_t)pos] = ok ? tb.codon_aa[y0 << 4 | y1 << 2 | y2] : (uint8_t)0;
+                aa[3u * st + (uint32_t)(na2 - 1 - pos)] = ok ? tb.codon_aa[(3u - y2) << 4 | (3u - y1) << 2 | (3u - y0)] : (uint8_t)0;
+            }
         }
     }
     w.sync();
@@ -263,33 +272,39 @@ static KJ_DEV void kj_translate_mate(KjWarpCtx& cx, KjQueue& q, int mate, const 
     // operations instead of a serial scan.  Insertion order (ConsumerThread.cpp:196-268): runs closed by a stop in scan
     // order of that stop; leftovers afterwards in frame order 0,1,2 where frame = count % 3 in FORWARD coordinates.
     const uint32_t m = cx.rp->m;
-    for (int strand = 0; strand < 2; strand++) {
-        const uint8_t* A = strand ? aaR : aaF; const uint32_t arr = (uint32_t)(2 * mate + strand);
-        for (int r = 0; r < 3; r++) {
-            const int nelem = (na - r + 2) / 3;                          // elements e: array index r + 3e
-            int run_open = 0;                                            // first element after the last stop of the earlier chunks (uniform)
-            for (int e0 = 0; e0 < nelem; e0 += 32) {
-                const int e = e0 + w.lane; const bool in = e < nelem;
-                const bool stop = in && A[r + 3 * e] == 0;
-                const uint32_t sm = w.ballot(stop);                       // stops of this 32-element chunk
-                // a run ends at e if e is a residue and e+1 is a stop or the end; runs crossing chunk borders are
-                // resolved by looking at the neighbouring elements directly
-                const bool is_res = in && !stop;
-                const bool next_stop = (e + 1 >= nelem) || (w.lane < 31 ? ((sm >> (w.lane + 1)) & 1u) != 0 : A[r + 3 * (e + 1)] == 0);
-                const bool is_end = is_res && next_stop;
-                uint32_t run_start = 0, run_len = 0, run_score = 0;
-                if (is_end) {
-                    const uint32_t below = sm & lanemask_lt(w.lane);
-                    const int s = below ? e0 + (32 - kj_clz(below)) : run_open;   // first element after the previous stop
-                    run_start = (uint32_t)(r + 3 * s); run_len = (uint32_t)(e - s + 1);
-                    if (greedy && run_len >= m) for (int t = s; t <= e; t++) { const uint32_t a = A[r + 3 * t]; run_score += (uint32_t)tb.b62[a][a]; }
+    for (int r = 0; r < 3; r++) {
+        const int ne1 = (na1 - r + 2) / 3, ne2 = (na2 - r + 2) / 3;      // elements e: array index r + 3e
+        const int nemax = ne1 > ne2 ? ne1 : ne2;
+        int run_open[4] = {0, 0, 0, 0};                                  // first element after the last stop of the earlier chunks (uniform)
+        for (int e0 = 0; e0 < nemax; e0 += 32) {
+            const int e = e0 + w.lane;
+            bool in[4], stop[4]; uint32_t sm[4];
+            #pragma unroll
+            for (int a = 0; a < 4; a++) { const int ne = a < 2 ? ne1 : ne2; in[a] = e < ne; stop[a] = in[a] && aa[(uint32_t)a * st + (uint32_t)(r + 3 * e)] == 0; }
+            #pragma unroll
+            for (int a = 0; a < 4; a++) sm[a] = w.ballot(stop[a]);
+            #pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int ne = a < 2 ? ne1 : ne2; const int n = a < 2 ? n1 : n2; const uint8_t* A = aa + (uint32_t)a * st;
+                if (e0 < ne) {                                           // uniform
+                    // a run ends at e if e is a residue and e+1 is a stop or the end
+                    const bool is_res = in[a] && !stop[a];
+                    const bool next_stop = (e + 1 >= ne) || (w.lane < 31 ? ((sm[a] >> (w.lane + 1)) & 1u) != 0 : A[r + 3 * (e + 1)] == 0);
+                    const bool is_end = is_res && next_stop;
+                    uint32_t run_start = 0, run_len = 0, run_score = 0;
+                    if (is_end) {
+                        const uint32_t below = sm[a] & lanemask_lt(w.lane);
+                        const int s = below ? e0 + (32 - kj_clz(below)) : run_open[a];   // first element after the previous stop
+                        run_start = (uint32_t)(r + 3 * s); run_len = (uint32_t)(e - s + 1);
+                        if (greedy && run_len >= m) for (int t = s; t <= e; t++) { const uint32_t c = A[r + 3 * t]; run_score += (uint32_t)tb.b62[c][c]; }
+                    }
+                    const bool leftover = e + 1 >= ne;
+                    const int frame = (a & 1) ? (((n - 3 - r) % 3) + 3) % 3 : r;
+                    const uint32_t order = ((uint32_t)a << 16) | (leftover ? 40000u + (uint32_t)frame : (uint32_t)(r + 3 * (e + 1)));
+                    const bool emit = is_end && run_len >= m && (!greedy || run_score >= cx.rp->min_score);
+                    kj_queue_emit(cx, q, emit, greedy ? run_score : run_len, order, kj_qpay((uint32_t)a, false, run_start, run_len));
+                    if (sm[a]) run_open[a] = e0 + (32 - kj_clz(sm[a]));
                 }
-                const bool leftover = e + 1 >= nelem;
-                const int frame = strand ? (((n - 3 - r) % 3) + 3) % 3 : r;
-                const uint32_t order = (arr << 16) | (leftover ? 40000u + (uint32_t)frame : (uint32_t)(r + 3 * (e + 1)));
-                const bool emit = is_end && run_len >= m && (!greedy || run_score >= cx.rp->min_score);
-                kj_queue_emit(cx, q, emit, greedy ? run_score : run_len, order, kj_qpay(arr, false, run_start, run_len));
-                if (sm) run_open = e0 + (32 - kj_clz(sm));
             }
         }
     }
@@ -646,8 +661,7 @@ static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1
     KjQueue q; q.key = (uint64_t*)(cx.smem + cx.L.qkey_off); q.pay = (uint32_t*)(cx.smem + cx.L.qpay_off);
     q.cap = rp.item_cap; q.n = 0; q.late = 0;
     const bool greedy = MODE == 1;
-    if (n1 >= m3) kj_translate_mate(cx, q, 0, s1, n1, greedy);            // a short mate is skipped individually (699, 705)
-    if (paired && n2 >= m3) kj_translate_mate(cx, q, 1, s2, n2, greedy);
+    kj_translate_pair(cx, q, s1, n1, n1 >= m3, s2, n2, paired && n2 >= m3, greedy);   // a short mate is skipped individually (699, 705)
     if (MODE == 0) return kj_classify_mem<IdxT>(cx, q, best_out);
     else return kj_classify_greedy<IdxT>(cx, q, n1, paired ? n2 : 0, best_out);
 }

@@ -26,6 +26,7 @@
 #define KJ_MIN_BLOCKS_GREEDY 4   // A/B: 8.30 vs 7.94 M pairs/s
 #endif
 #define KJ_CHUNK_READS (1u << 20)
+#define KJ_CLAIM 4               // read items claimed per atomic by a warp
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { kj_err() = std::string(#call) + ": " + cudaGetErrorString(e_); return KJ_ERR_CUDA; } } while (0)
 
@@ -60,30 +61,37 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
     cx.gscratch = gscratch + gwarp * gscratch_bytes;
     cx.err = err;
     const bool paired = seq2 != nullptr;
+    // work distribution: a warp claims KJ_CLAIM consecutive items per atomic and fetches their offsets with one coalesced load
     for (;;) {
-        unsigned long long r = 0;
-        if (cx.w.lane == 0) r = atomicAdd(counter, 1ull);
-        r = cx.w.shfl64(r, 0);
-        if (r >= n_reads) break;
-        const uint64_t a0 = off1[r] - base1, a1 = off1[r + 1] - base1;
-        uint64_t b0 = 0, b1 = 0; if (paired) { b0 = off2[r] - base2; b1 = off2[r + 1] - base2; }
-        uint32_t best = 0;
-        uint32_t t = kj_classify_item<MODE, IdxT>(cx, seq1 + a0, (int)(a1 - a0), paired ? seq2 + b0 : nullptr, (int)(b1 - b0), paired, best);
-        const uint64_t id = t == KJ_TAX_BAD ? 0ull : sh->ix.tax_id[t];
-        if (cx.w.lane == 0) {
-            taxon_out[r] = id;
-            if (best_out) best_out[r] = id ? best : 0u;
-        }
-        if (ids_out) {   // column 5 of the reference's -v output: the match-id set in ascending order (std::set), classified reads only
-            const uint32_t nids = id ? cx.nids : 0u; const uint32_t* ids = (const uint32_t*)(cx.smem + cx.L.ids_off);
-            if ((uint32_t)cx.w.lane < nids) {
-                const uint64_t mine = sh->ix.tax_id[ids[cx.w.lane]]; uint32_t rank = 0;
-                for (uint32_t u = 0; u < nids; u++) rank += sh->ix.tax_id[ids[u]] < mine ? 1u : 0u;
-                ids_out[r * KJ_MAX_IDS + rank] = mine;
+        unsigned long long r0 = 0;
+        if (cx.w.lane == 0) r0 = atomicAdd(counter, (unsigned long long)KJ_CLAIM);
+        r0 = cx.w.shfl64(r0, 0);
+        if (r0 >= n_reads) break;
+        const unsigned long long ri = r0 + (unsigned long long)cx.w.lane;
+        uint64_t o1 = 0, o2 = 0;
+        if (cx.w.lane <= KJ_CLAIM && ri <= n_reads) { o1 = off1[ri] - base1; if (paired) o2 = off2[ri] - base2; }
+        for (int k = 0; k < KJ_CLAIM; k++) {
+            const unsigned long long r = r0 + (unsigned long long)k;
+            if (r >= n_reads) break;
+            const uint64_t a0 = cx.w.shfl64(o1, k), a1 = cx.w.shfl64(o1, k + 1), b0 = cx.w.shfl64(o2, k), b1 = cx.w.shfl64(o2, k + 1);
+            uint32_t best = 0;
+            uint32_t t = kj_classify_item<MODE, IdxT>(cx, seq1 + a0, (int)(a1 - a0), paired ? seq2 + b0 : nullptr, (int)(b1 - b0), paired, best);
+            const uint64_t id = t == KJ_TAX_BAD ? 0ull : sh->ix.tax_id[t];
+            if (cx.w.lane == 0) {
+                taxon_out[r] = id;
+                if (best_out) best_out[r] = id ? best : 0u;
             }
-            if (cx.w.lane == 0) nids_out[r] = (uint8_t)nids;
+            if (ids_out) {   // column 5 of the reference's -v output: the match-id set in ascending order (std::set), classified reads only
+                const uint32_t nids = id ? cx.nids : 0u; const uint32_t* ids = (const uint32_t*)(cx.smem + cx.L.ids_off);
+                if ((uint32_t)cx.w.lane < nids) {
+                    const uint64_t mine = sh->ix.tax_id[ids[cx.w.lane]]; uint32_t rank = 0;
+                    for (uint32_t u = 0; u < nids; u++) rank += sh->ix.tax_id[ids[u]] < mine ? 1u : 0u;
+                    ids_out[r * KJ_MAX_IDS + rank] = mine;
+                }
+                if (cx.w.lane == 0) nids_out[r] = (uint8_t)nids;
+            }
+            cx.w.sync();
         }
-        cx.w.sync();
     }
 }
 
