@@ -21,11 +21,10 @@
 // per-warp shared-memory carve-up
 // ---------------------------------------------------------------------------------------------
 #define KJ_SEG_CAP(max_frag) ((max_frag) / 4u + 8u)
-#define KJ_VKEY_SMEM 64u
 struct KjKept { uint64_t lo; uint32_t len; uint32_t aux; };     // one suffix interval (an SI of bwt.h:25-34)
 
 struct KjSmemLayout {
-    uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, vkey_off, aa_off, aa_stride, frag_off, hflag_off,
+    uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, qord_off, aa_off, aa_stride, frag_off, hflag_off,
              segcnt_off, seghist_off, segs_off, total;
 };
 static KJ_HD uint32_t kj_align(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -35,8 +34,8 @@ static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
     L.kept_off = o; o += 16u * p.kept_cap_smem;
     L.segs_off = o; o += 8u * KJ_SEG_CAP(p.max_frag);                     // {int begin,end}
     L.qpay_off = o; o += 4u * kj_align(p.item_cap, 2);
+    L.qord_off = o; o += kj_align(p.item_cap, 8);                      // slots in pop order (valid while no SEG piece was pushed)
     L.ids_off = o; o += 4u * 24u;
-    L.vkey_off = o; o += (p.mode == 1 ? 8u * KJ_VKEY_SMEM : 0u);         // greedy: keys of the first variants (the rest live in global scratch)
     L.aa_stride = kj_align(p.max_len + 4, 8);
     L.aa_off = o; o += 4u * L.aa_stride;
     L.frag_off = o; o += kj_align(p.max_frag + 8, 8);
@@ -202,7 +201,7 @@ static KJ_DEV void kj_finish_selected(const Warp& w, const KjDevIndex& ix, const
 // insertion order, ConsumerThread.cpp:196-268); SEG pieces and greedy variants take a running counter.
 // ---------------------------------------------------------------------------------------------
 #define KJ_ORDER_LATE (1u << 20)
-struct KjQueue { uint64_t* key; uint32_t* pay; uint32_t cap, n, late; };    // n, late: uniform
+struct KjQueue { uint64_t* key; uint32_t* pay; uint8_t* ord; uint32_t cap, n, late, next, nsorted; bool dirty; };    // scalars: uniform
 static KJ_DEV uint64_t kj_qkey(uint32_t val, uint32_t order) { return ((uint64_t)val << 32) | ((uint64_t)(0xffffffu - order) << 8) | 1ull; }
 static KJ_DEV uint32_t kj_qpay(uint32_t arr, bool segchecked, uint32_t start, uint32_t len) { return (arr << 30) | ((segchecked ? 1u : 0u) << 29) | (start << 14) | len; }
 
@@ -215,8 +214,28 @@ static KJ_DEV void kj_queue_emit(KjWarpCtx& cx, KjQueue& q, bool emit, uint32_t 
     if (emit) { uint32_t s = q.n + (uint32_t)kj_popc(mask & lanemask_lt(cx.w.lane)); q.key[s] = kj_qkey(val, order); q.pay[s] = pay; }
     q.n += cnt;
 }
+// After translation the fragments are ranked once (keys are unique): ord[k] = slot of the k-th entry in pop order.  As long as
+// no SEG piece has been pushed (rare) a pop is three broadcast shared-memory reads instead of a warp arg-max.
+static KJ_DEV void kj_queue_sort(KjWarpCtx& cx, KjQueue& q) {
+    cx.w.sync();
+    for (uint32_t i = (uint32_t)cx.w.lane; i < q.n; i += 32) {
+        const uint64_t mine = q.key[i]; uint32_t rank = 0;
+        for (uint32_t j = 0; j < q.n; j++) rank += q.key[j] > mine ? 1u : 0u;
+        q.ord[rank] = (uint8_t)i;
+    }
+    q.nsorted = q.n <= 255u ? q.n : 0u; q.next = 0; q.dirty = q.n > 255u;
+    cx.w.sync();
+}
 // pop the top entry if its sort value is >= min_val (getNextFragment's gate, ConsumerThread.cpp:276-283)
 static KJ_DEV bool kj_queue_pop(KjWarpCtx& cx, KjQueue& q, uint32_t min_val, uint32_t& val, uint32_t& pay) {
+    if (!q.dirty) {
+        if (q.next >= q.nsorted) return false;
+        const uint32_t slot = q.ord[q.next]; const uint64_t k = q.key[slot];
+        val = (uint32_t)(k >> 32);
+        if (val < min_val) return false;
+        pay = q.pay[slot]; q.next++;
+        return true;
+    }
     cx.w.sync();
     uint64_t best = 0; uint32_t slot = 0;
     for (uint32_t s = (uint32_t)cx.w.lane; s < q.n; s += 32) { uint64_t k = q.key[s]; if (k > best) { best = k; slot = s; } }
@@ -232,6 +251,15 @@ static KJ_DEV bool kj_queue_pop(KjWarpCtx& cx, KjQueue& q, uint32_t min_val, uin
     cx.w.sync();
     return true;
 }
+// switch to scanning pops (a SEG piece is about to be pushed): consumed entries of the sorted prefix are cleared first
+static KJ_DEV void kj_queue_make_dirty(KjWarpCtx& cx, KjQueue& q) {
+    if (q.dirty) return;
+    cx.w.sync();
+    for (uint32_t k = (uint32_t)cx.w.lane; k < q.next; k += 32) q.key[q.ord[k]] = 0;
+    q.dirty = true;
+    cx.w.sync();
+}
+
 // ---------------------------------------------------------------------------------------------
 // six-frame translation + stop splitting of one mate  (getAllFragmentsBits, ConsumerThread.cpp:190-270)
 // arrays: aa[2*mate+0][count] forward codon starting at base `count`; aa[2*mate+1][r] reverse-strand codon
@@ -543,6 +571,7 @@ static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
 static KJ_DEV bool kj_seg_gate(KjWarpCtx& cx, KjQueue& q, uint32_t arr, uint32_t start, uint32_t len, bool greedy) {
     int ns = kj_seg(cx, (int)len);
     if (ns == 0) return false;
+    kj_queue_make_dirty(cx, q);
     const KjSeg* segs = (const KjSeg*)(cx.smem + cx.L.segs_off);
     const uint8_t* frag = cx.smem + cx.L.frag_off; const KjTables& tb = *cx.tb;
     uint32_t st = 0;
@@ -659,9 +688,10 @@ static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1
     // short-read gate (648-653): SE len1 < 3m; PE only if BOTH mates are short
     if ((!paired && n1 < m3) || (paired && n1 < m3 && n2 < m3)) return KJ_TAX_BAD;
     KjQueue q; q.key = (uint64_t*)(cx.smem + cx.L.qkey_off); q.pay = (uint32_t*)(cx.smem + cx.L.qpay_off);
-    q.cap = rp.item_cap; q.n = 0; q.late = 0;
+    q.ord = cx.smem + cx.L.qord_off; q.cap = rp.item_cap; q.n = 0; q.late = 0; q.next = 0; q.nsorted = 0; q.dirty = true;
     const bool greedy = MODE == 1;
     kj_translate_pair(cx, q, s1, n1, n1 >= m3, s2, n2, paired && n2 >= m3, greedy);   // a short mate is skipped individually (699, 705)
+    kj_queue_sort(cx, q);
     if (MODE == 0) return kj_classify_mem<IdxT>(cx, q, best_out);
     else return kj_classify_greedy<IdxT>(cx, q, n1, paired ? n2 : 0, best_out);
 }

@@ -24,9 +24,9 @@ static KJ_HD uint32_t kj_greedy_scratch_bytes(const KjRunParams& rp) { return rp
 
 struct KjMatch { uint64_t lo; uint32_t len; uint16_t qi, ql; };    // one SI: interval + query position/length
 
-// key(s) = kj_qkey(score, order), 0 = free; the first KJ_VKEY_SMEM keys sit in shared memory (the pop scans them every iteration)
-struct KjVQueue { uint64_t* skey; uint64_t* gkey; KjVariant* v; uint32_t n;      // n: high-water mark (uniform)
-    KJ_DEV uint64_t& key(uint32_t s) const { return s < KJ_VKEY_SMEM ? skey[s] : gkey[s]; } };
+// key(s) = kj_qkey(score, order), 0 = free.  (Keeping the first keys in shared memory was slower: A/B 7.7 vs 8.3 M pairs/s.)
+struct KjVQueue { uint64_t* gkey; KjVariant* v; uint32_t n;      // n: high-water mark (uniform)
+    KJ_DEV uint64_t& key(uint32_t s) const { return gkey[s]; } };
 
 // compact live variants to the front (called when the ring is full)
 static KJ_DEV void kj_vq_compact(KjWarpCtx& cx, KjVQueue& vq) {
@@ -56,7 +56,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
     uint16_t* pre = (uint16_t*)(cx.smem + cx.L.pre_off);               // pre[t] = sum diag(frag[0..t))
     KjMatch* res = (KjMatch*)(cx.smem + cx.L.res_off);                  // per-j chain results, then recorded matches
     KjMatch* cls = (KjMatch*)(cx.smem + cx.L.res2_off);                 // recorded matches sorted into classes
-    KjVQueue vq; vq.skey = (uint64_t*)(cx.smem + cx.L.vkey_off); vq.gkey = (uint64_t*)cx.gscratch; vq.v = (KjVariant*)((uint8_t*)cx.gscratch + 8u * KJ_VARIANT_CAP); vq.n = 0;
+    KjVQueue vq; vq.gkey = (uint64_t*)cx.gscratch; vq.v = (KjVariant*)((uint8_t*)cx.gscratch + 8u * KJ_VARIANT_CAP); vq.n = 0;
     uint32_t best = 0, nbest = 0;                                        // best_match_score, best_matches_SI.size()  (uniform)
     best_out = 0;
 
@@ -66,17 +66,24 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
         uint64_t kb = 0; uint32_t slot_b = 0;
         for (uint32_t s = (uint32_t)w.lane; s < vq.n; s += 32) { uint64_t k = vq.key(s); if (k > kb) { kb = k; slot_b = s; } }
         uint64_t gb = warp_max_u64(w, kb);
-        uint64_t ka = 0; uint32_t slot_a = 0;
-        for (uint32_t s = (uint32_t)w.lane; s < q.n; s += 32) { uint64_t k = q.key[s]; if (k > ka) { ka = k; slot_a = s; } }
-        uint64_t ga = warp_max_u64(w, ka);
+        uint64_t ka = 0, ga = 0; uint32_t slot_a = 0;
+        if (!q.dirty) { if (q.next < q.nsorted) { slot_a = q.ord[q.next]; ga = q.key[slot_a]; } }      // sorted prefix: the top is known
+        else {
+            for (uint32_t s = (uint32_t)w.lane; s < q.n; s += 32) { uint64_t k = q.key[s]; if (k > ka) { ka = k; slot_a = s; } }
+            ga = warp_max_u64(w, ka);
+        }
         const uint64_t g = ga > gb ? ga : gb;
         if (g == 0) break;
         if ((uint32_t)(g >> 32) < best) break;
         uint32_t arr, start, len, num_mm = 0, matchlen = 0; int diff = 0; uint64_t si0 = 0, si1 = 0; bool segchecked; uint32_t nsub = 0; uint16_t mysub = 0;
         if (ga >= gb) {
-            int src = kj_ffs(w.ballot(ka == g)) - 1; uint32_t p = 0;
-            if (w.lane == src) { p = q.pay[slot_a]; q.key[slot_a] = 0; }
-            p = w.shfl(p, src);
+            uint32_t p = 0;
+            if (!q.dirty) { p = q.pay[slot_a]; q.next++; }
+            else {
+                int src = kj_ffs(w.ballot(ka == g)) - 1;
+                if (w.lane == src) { p = q.pay[slot_a]; q.key[slot_a] = 0; }
+                p = w.shfl(p, src);
+            }
             arr = p >> 30; segchecked = (p >> 29) & 1u; start = (p >> 14) & 0x7fffu; len = p & 0x3fffu;
         } else {
             int src = kj_ffs(w.ballot(kb == g)) - 1; uint32_t sl = w.shfl(slot_b, src);
