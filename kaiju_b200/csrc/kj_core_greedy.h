@@ -25,7 +25,7 @@ static KJ_HD uint32_t kj_greedy_scratch_bytes(const KjRunParams& rp) { return rp
 struct KjMatch { uint64_t lo; uint32_t len; uint16_t qi, ql; };    // one SI: interval + query position/length
 
 // key(s) = kj_qkey(score, order), 0 = free.  (Keeping the first keys in shared memory was slower: A/B 7.7 vs 8.3 M pairs/s.)
-struct KjVQueue { uint64_t* gkey; KjVariant* v; uint32_t n;      // n: high-water mark (uniform)
+struct KjVQueue { uint64_t* gkey; KjVariant* v; uint32_t n, live;      // n: high-water mark, live: entries not yet popped (uniform)
     KJ_DEV uint64_t& key(uint32_t s) const { return gkey[s]; } };
 
 // compact live variants to the front (called when the ring is full)
@@ -40,7 +40,7 @@ static KJ_DEV void kj_vq_compact(KjWarpCtx& cx, KjVQueue& vq) {
         out += (uint32_t)kj_popc(mask);
         w.sync();
     }
-    vq.n = out;
+    vq.n = out; vq.live = out;
 }
 
 // inclusive warp scan helper (uint32)
@@ -56,7 +56,8 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
     uint16_t* pre = (uint16_t*)(cx.smem + cx.L.pre_off);               // pre[t] = sum diag(frag[0..t))
     KjMatch* res = (KjMatch*)(cx.smem + cx.L.res_off);                  // per-j chain results, then recorded matches
     KjMatch* cls = (KjMatch*)(cx.smem + cx.L.res2_off);                 // recorded matches sorted into classes
-    KjVQueue vq; vq.gkey = (uint64_t*)cx.gscratch; vq.v = (KjVariant*)((uint8_t*)cx.gscratch + 8u * KJ_VARIANT_CAP); vq.n = 0;
+    uint16_t* psub = (uint16_t*)(cx.smem + cx.L.ids_off + 64u);           // the id set is only filled after the loop
+    KjVQueue vq; vq.gkey = (uint64_t*)cx.gscratch; vq.v = (KjVariant*)((uint8_t*)cx.gscratch + 8u * KJ_VARIANT_CAP); vq.n = 0; vq.live = 0;
     uint32_t best = 0, nbest = 0;                                        // best_match_score, best_matches_SI.size()  (uniform)
     best_out = 0;
 
@@ -90,9 +91,10 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
             const KjVariant& V = vq.v[sl];
             uint32_t p = V.pay; arr = p >> 30; start = (p >> 14) & 0x7fffu; len = p & 0x3fffu; segchecked = true;
             num_mm = V.num_mm; matchlen = V.matchlen; diff = V.diff; si0 = V.lo; si1 = V.hi; nsub = num_mm;
-            if ((uint32_t)w.lane < nsub) mysub = V.subs[w.lane];
+            if ((uint32_t)w.lane < nsub) { mysub = V.subs[w.lane]; psub[w.lane] = mysub; }        // parent substitutions, re-read when variants are pushed
             w.sync();
             if (w.lane == 0) vq.key(sl) = 0;
+            vq.live--;
         }
         kj_load_frag(cx, arr, start, len);
         if ((uint32_t)w.lane < nsub) frag[mysub >> 5] = (uint8_t)(mysub & 31u);
@@ -204,7 +206,8 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
                         w.sync();
                         const uint32_t okmask = w.ballot(ok); const uint32_t cnt = (uint32_t)kj_popc(okmask);
                         if (cnt) {
-                            if (vq.n + cnt > KJ_VARIANT_CAP) { kj_vq_compact(cx, vq); }
+                            // the pop scans keys[0..n): squeeze out popped entries once the ring passes 64 slots and at least half are holes
+                            if (vq.n + cnt > KJ_VARIANT_CAP || (vq.n + cnt > 64u && vq.live * 2u <= vq.n)) { kj_vq_compact(cx, vq); }
                             if (vq.n + cnt > KJ_VARIANT_CAP) { if (w.lane == 0) kj_flag_error(cx, 4u); }
                             else {
                                 const uint32_t rk = (uint32_t)kj_popc(okmask & lanemask_lt(w.lane));
@@ -212,7 +215,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
                                 // the parent's substitutions that survive the truncation, then the new one
                                 uint32_t ns = 0;
                                 for (uint32_t u = 0; u < nsub; u++) {
-                                    uint32_t sv = w.shfl((uint32_t)mysub, (int)u);
+                                    const uint32_t sv = psub[u];
                                     if ((sv >> 5) < new_len) { if (ok) V->subs[ns] = (uint16_t)sv; ns++; }
                                 }
                                 if (ok) {
@@ -222,7 +225,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
                                     V->matchlen = (uint16_t)(sm.ql + 1u); V->num_mm = (uint8_t)(ns + 1u); V->pad = 0; V->pad2 = 0;
                                     vq.key(vq.n + rk) = kj_qkey((uint32_t)after, KJ_ORDER_LATE + q.late + rk);
                                 }
-                                vq.n += cnt; q.late += cnt;
+                                vq.n += cnt; vq.live += cnt; q.late += cnt;
                             }
                         }
                         w.sync();
