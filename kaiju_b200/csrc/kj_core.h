@@ -151,7 +151,9 @@ static KJ_DEV uint32_t kj_sa_taxon(const KjDevIndex& ix, uint64_t k) {
 //   phase B: the surviving chains are completed a few at a time in descending j, replaying the reference's
 //            sequential rules (growing L, `if (i<=1) break`) between groups.
 // ---------------------------------------------------------------------------------------------
+#ifndef KJ_PHASE_A_LETTERS
 #define KJ_PHASE_A_LETTERS 9      // letters matched in phase A (k-mer + single steps)
+#endif
 #ifndef KJ_GROUP_FIRST
 #define KJ_GROUP_FIRST 8            // (A/B: 29.0 with 8 vs 28.7 with 2; DRAM is at ~3 % of peak, speculation is cheap)
 #endif
@@ -304,13 +306,27 @@ static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s
         const int ne1 = (na1 - r + 2) / 3, ne2 = (na2 - r + 2) / 3;      // elements e: array index r + 3e
         const int nemax = ne1 > ne2 ? ne1 : ne2;
         int run_open[4] = {0, 0, 0, 0};                                  // first element after the last stop of the earlier chunks (uniform)
+        uint32_t p_open[4] = {0, 0, 0, 0}, p_carry[4] = {0, 0, 0, 0};    // greedy: score prefix at run_open-1 / at the end of the previous chunk (uniform)
         for (int e0 = 0; e0 < nemax; e0 += 32) {
             const int e = e0 + w.lane;
-            bool in[4], stop[4]; uint32_t sm[4];
+            bool in[4], stop[4]; uint32_t sm[4], pre[4];
             #pragma unroll
-            for (int a = 0; a < 4; a++) { const int ne = a < 2 ? ne1 : ne2; in[a] = e < ne; stop[a] = in[a] && aa[(uint32_t)a * st + (uint32_t)(r + 3 * e)] == 0; }
+            for (int a = 0; a < 4; a++) {
+                const int ne = a < 2 ? ne1 : ne2; in[a] = e < ne;
+                const uint32_t c = in[a] ? aa[(uint32_t)a * st + (uint32_t)(r + 3 * e)] : 0u;
+                stop[a] = in[a] && c == 0; pre[a] = (greedy && in[a]) ? (uint32_t)tb.b62[c][c] : 0u;     // BLOSUM62 diagonal (calcScore, 415-421); b62[0][0] = 0
+            }
             #pragma unroll
             for (int a = 0; a < 4; a++) sm[a] = w.ballot(stop[a]);
+            if (greedy) {
+                // fragment self-scores = differences of a running prefix sum over the frame (four independent scans interleaved)
+                for (int d = 1; d < 32; d <<= 1) {
+                    #pragma unroll
+                    for (int a = 0; a < 4; a++) { const uint32_t o = w.shfl(pre[a], w.lane - d); if (w.lane >= d) pre[a] += o; }
+                }
+                #pragma unroll
+                for (int a = 0; a < 4; a++) pre[a] += p_carry[a];
+            }
             #pragma unroll
             for (int a = 0; a < 4; a++) {
                 const int ne = a < 2 ? ne1 : ne2; const int n = a < 2 ? n1 : n2; const uint8_t* A = aa + (uint32_t)a * st;
@@ -319,19 +335,23 @@ static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s
                     const bool is_res = in[a] && !stop[a];
                     const bool next_stop = (e + 1 >= ne) || (w.lane < 31 ? ((sm[a] >> (w.lane + 1)) & 1u) != 0 : A[r + 3 * (e + 1)] == 0);
                     const bool is_end = is_res && next_stop;
+                    const uint32_t below = sm[a] & lanemask_lt(w.lane);
+                    const int prev_stop_lane = below ? 31 - kj_clz(below) : 0;
+                    uint32_t p_before = 0;
+                    if (greedy) { p_before = w.shfl(pre[a], prev_stop_lane); if (!below) p_before = p_open[a]; }    // prefix at the element before the run
                     uint32_t run_start = 0, run_len = 0, run_score = 0;
                     if (is_end) {
-                        const uint32_t below = sm[a] & lanemask_lt(w.lane);
-                        const int s = below ? e0 + (32 - kj_clz(below)) : run_open[a];   // first element after the previous stop
+                        const int s = below ? e0 + prev_stop_lane + 1 : run_open[a];    // first element after the previous stop
                         run_start = (uint32_t)(r + 3 * s); run_len = (uint32_t)(e - s + 1);
-                        if (greedy && run_len >= m) for (int t = s; t <= e; t++) { const uint32_t c = A[r + 3 * t]; run_score += (uint32_t)tb.b62[c][c]; }
+                        run_score = pre[a] - p_before;
                     }
                     const bool leftover = e + 1 >= ne;
                     const int frame = (a & 1) ? (((n - 3 - r) % 3) + 3) % 3 : r;
                     const uint32_t order = ((uint32_t)a << 16) | (leftover ? 40000u + (uint32_t)frame : (uint32_t)(r + 3 * (e + 1)));
                     const bool emit = is_end && run_len >= m && (!greedy || run_score >= cx.rp->min_score);
                     kj_queue_emit(cx, q, emit, greedy ? run_score : run_len, order, kj_qpay((uint32_t)a, false, run_start, run_len));
-                    if (sm[a]) run_open[a] = e0 + (32 - kj_clz(sm[a]));
+                    if (sm[a]) { const int last = 31 - kj_clz(sm[a]); run_open[a] = e0 + last + 1; if (greedy) p_open[a] = w.shfl(pre[a], last); }
+                    if (greedy) p_carry[a] = w.shfl(pre[a], 31);
                 }
             }
         }
