@@ -250,14 +250,14 @@ uint64_t ko_lca(const ko_tax *t, const uint64_t *ids, int n) {
 #define SEG_WINDOW 12
 static const double SEG_LOCUT = 2.2, SEG_HICUT = 2.5;
 #define SEG_MAXTRIM 50
-#define KO_LNFACT_N 2048
+#define KO_LNFACT_N 10001                /* entries of the reference table lnfact[0..10000] (blast_seg.c:53-1306) */
 static double g_lnfact[KO_LNFACT_N]; static int g_lnfact_ready = 0;
 double ko_lnfact(int n) {
     if (!g_lnfact_ready) {
         for (int i = 0; i < KO_LNFACT_N; i++) { char b[64]; snprintf(b, sizeof b, "%.6f", lgamma((double)i + 1.0)); g_lnfact[i] = strtod(b, NULL); }
         g_lnfact[0] = g_lnfact[1] = 0.0; g_lnfact_ready = 1;
     }
-    if (n < 1250) return g_lnfact[n];                               /* table length, blast_seg.c:53-1306 */
+    if (n < KO_LNFACT_N) return g_lnfact[n];                        /* s_lnfact, blast_seg.c:1852-1856: table first */
     return ((n + 0.5) * log((double)n) - n + 0.9189385332);         /* s_lnfact, blast_seg.c:1852-1856 */
 }
 typedef struct { int begin, end; } seg_t;
@@ -468,8 +468,8 @@ static int next_fragment(fragq *q, const ko_params *P, unsigned min_key, frag_t 
     if (q->v[t].key < min_key) return 0;
     frag_t f = fq_take(q, t);
     while (P->seg && !f.segchecked) {
-        int L[256], R[256]; if (ctr) ctr->seg_calls++;
-        int ns = ko_seg(f.seq, f.len, L, R, 256);
+        enum { KO_SEG_MAXREG = 8192 }; static __thread int L[KO_SEG_MAXREG], R[KO_SEG_MAXREG]; if (ctr) ctr->seg_calls++;
+        int ns = ko_seg(f.seq, f.len, L, R, KO_SEG_MAXREG);
         if (ns > 0) {
             if (ctr) ctr->seg_hits++;
             int start = 0;
@@ -522,12 +522,12 @@ static int max_matches(const ko_index *x, const uint8_t *str, int len, int L, si
     }
     out->n = 0; int ncls = 0;
     /* distinct lengths, descending */
-    int lens[512], nl = 0;
-    for (int k = 0; k < found.n; k++) { int seen = 0; for (int t = 0; t < nl; t++) if (lens[t] == found.v[k].ql) seen = 1; if (!seen && nl < 512) lens[nl++] = found.v[k].ql; }
+    int *lens = (int *)malloc(sizeof(int) * (size_t)(found.n + 1)), nl = 0;
+    for (int k = 0; k < found.n; k++) { int seen = 0; for (int t = 0; t < nl; t++) if (lens[t] == found.v[k].ql) seen = 1; if (!seen) lens[nl++] = found.v[k].ql; }
     for (int a = 1; a < nl; a++) { int v = lens[a], b = a; while (b > 0 && lens[b - 1] < v) { lens[b] = lens[b - 1]; b--; } lens[b] = v; }
     for (int t = 0; t < nl; t++) { cls_start[ncls++] = out->n; for (int k = 0; k < found.n; k++) if (found.v[k].ql == lens[t]) sl_push(out, found.v[k]); }
     cls_start[ncls] = out->n;
-    free(found.v); return ncls;
+    free(found.v); free(lens); return ncls;
 }
 /* maxMatches_withStart (bwt.c:298-336) */
 static int max_matches_with_start(const ko_index *x, const uint8_t *str, int len, int L, int64_t si0, int64_t si1, int offset, si_t *out, ko_counters *ctr) {
@@ -622,12 +622,12 @@ static void eval_classes(const ko_params *P, const frag_t *t, const silist *S, c
 
 /* classify_greedyblosum (ConsumerThread.cpp:424-541) */
 static uint64_t classify_greedy(const ko_index *x, const ko_tax *T, const ko_params *P, fragq *q, double query_len, uint32_t *best, idset *ids, ko_counters *ctr) {
-    bestlist B; B.n = 0; B.best = 0; frag_t t; silist S = {0, 0, 0}; int cls[520];
+    bestlist B; B.n = 0; B.best = 0; frag_t t; silist S = {0, 0, 0};
     while (next_fragment(q, P, B.best, &t, ctr)) {
         uint8_t *num = (uint8_t *)malloc((size_t)t.len + 1);
         for (int i = 0; i < t.len; i++) num[i] = x->trans[(uint8_t)t.seq[i]];
         if (ctr) ctr->fragments_searched++;
-        int ncls = 0;
+        int ncls = 0; int *cls = (int *)malloc(sizeof(int) * (size_t)(t.len + 2));   /* class boundaries: at most one class per match length */
         if (t.num_mm > 0) {
             si_t one; int L = (t.num_mm == P->mismatches) ? (int)P->min_fragment_length : t.matchlen;
             S.n = 0;
@@ -651,7 +651,7 @@ static uint64_t classify_greedy(const ko_index *x, const ko_tax *T, const ko_par
             }
             if (S.v[cls[0]].ql >= (int)P->min_fragment_length) eval_classes(P, &t, &S, cls, 0, ncls, &B);
         }
-        free(num); free(t.seq);
+        free(num); free(t.seq); free(cls);
     }
     free(S.v);
     ids->n = 0; *best = 0;

@@ -121,6 +121,8 @@ def kjgen_lib():
         L.kjgen_db_write.restype = C.c_int; L.kjgen_db_write.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.kjgen_reads_packed.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        for fn in (L.kjgen_long_reads_packed, L.kjgen_protein_reads_packed):
+            fn.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.kjgen_reads_write_fastq.restype = C.c_int
         L.kjgen_reads_write_fastq.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
         _kjgen = L
@@ -146,6 +148,19 @@ class SynthDB:
         if paired:
             return s1, o1, s2[:int(o2[n])], o2
         return s1, o1, None, None
+
+    def _varlen(self, fn, seed, first, n, minlen, maxlen):
+        s = np.empty(n * maxlen, dtype=np.uint8); o = np.empty(n + 1, dtype=np.uint64)
+        fn(self.h, seed, first, n, minlen, maxlen, s.ctypes.data, o.ctypes.data)
+        return s[:int(o[n])].copy(), o
+
+    def long_reads(self, seed, first, n, minlen, maxlen):
+        """Variable-length DNA reads (segments of coding / random / low-complexity sequence), single-end."""
+        return self._varlen(self.L.kjgen_long_reads_packed, seed, first, n, minlen, maxlen)
+
+    def protein_reads(self, seed, first, n, minlen, maxlen):
+        """Protein input for -p: residues plus the characters that split a read (X, *, B, Z, digits ...)."""
+        return self._varlen(self.L.kjgen_protein_reads_packed, seed, first, n, minlen, maxlen)
 
     def write_fastq(self, seed, first, n, readlen, paired, fq1, fq2=None):
         assert self.L.kjgen_reads_write_fastq(self.h, seed, first, n, readlen, 1 if paired else 0, fq1.encode(),

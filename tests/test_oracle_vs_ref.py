@@ -32,3 +32,52 @@ def test_oracle_equals_reference_cli(work, kw):
         tax, best = orc.classify_batch(make_params(**kw), s1, o1, s2, o2)
         for i, nm in enumerate(n1):
             assert (ref[nm][1], ref[nm][2]) == (int(tax[i]), int(best[i])), (nm, ref[nm], tax[i], best[i])
+
+
+def _write_fasta(path, seq, off):
+    with open(path, "w") as f:
+        for i in range(len(off) - 1):
+            f.write(">r%d\n%s\n" % (i, seq[int(off[i]):int(off[i + 1])].tobytes().decode()))
+
+
+@pytest.fixture(scope="module")
+def work_long(built):
+    """Long DNA reads (400 bp - 12 kb, incl. >127-residue low-complexity runs) and protein reads for -p."""
+    d = tempfile.mkdtemp(prefix="kjrefl_")
+    db = SynthDB(3000, 11)
+    db.write(d + "/db.faa", d + "/nodes.dmp")
+    fmi = build_fmi(d + "/db.faa", d + "/db", threads=4)
+    ls, lo = db.long_reads(31, 0, 300, 400, 12000)
+    ps, po = db.protein_reads(32, 0, 1500, 5, 1500)
+    _write_fasta(d + "/long.fa", ls, lo); _write_fasta(d + "/prot.fa", ps, po)
+    return d, fmi, (ls, lo), (ps, po)
+
+
+@pytest.mark.parametrize("kw", [dict(mode="mem"), dict(mode="mem", m=8, seg=False), dict(mode="greedy"), dict(mode="greedy", e=5, s=50), dict(mode="greedy", e=2, E=1e-9)])
+def test_oracle_equals_reference_long_reads(work_long, kw):
+    d, fmi, (ls, lo), _ = work_long
+    ref = run_ref_kaiju(d + "/nodes.dmp", fmi, d + "/long.fa", None, threads=8, **kw)
+    tax, best = Oracle(fmi, d + "/nodes.dmp").classify_batch(make_params(**kw), ls, lo)
+    for i in range(len(lo) - 1):
+        assert (ref["r%d" % i][1], ref["r%d" % i][2]) == (int(tax[i]), int(best[i])), (i, ref["r%d" % i], tax[i], best[i])
+    assert (tax > 0).sum() > 100
+
+
+@pytest.mark.parametrize("kw", [dict(mode="mem"), dict(mode="mem", m=6, seg=False), dict(mode="greedy"), dict(mode="greedy", e=4, s=40)])
+def test_oracle_equals_reference_protein_input(work_long, kw):
+    d, fmi, _, (ps, po) = work_long
+    ref = run_ref_kaiju(d + "/nodes.dmp", fmi, d + "/prot.fa", None, threads=8, protein=True, **kw)
+    tax, best = Oracle(fmi, d + "/nodes.dmp").classify_batch(make_params(protein=True, **kw), ps, po)
+    for i in range(len(po) - 1):
+        assert (ref["r%d" % i][1], ref["r%d" % i][2]) == (int(tax[i]), int(best[i])), (i, ref["r%d" % i], tax[i], best[i])
+    assert (tax > 0).sum() > 300
+
+
+def test_lnfact_table_matches_reference(built):
+    """ko_lnfact reproduces every entry of the reference's lnfact[0..10000] (blast_seg.c:53-1306), read from oracle/_ref/libkaijuref.so."""
+    import ctypes as C
+    from helpers import oracle_lib, REF_DIR
+    ref = C.CDLL(os.path.join(REF_DIR, "libkaijuref.so"))
+    tab = (C.c_double * 10001).in_dll(ref, "lnfact")
+    L = oracle_lib(); L.ko_lnfact.restype = C.c_double; L.ko_lnfact.argtypes = [C.c_int]
+    assert all(L.ko_lnfact(n) == tab[n] for n in range(10001))

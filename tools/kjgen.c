@@ -303,6 +303,88 @@ int kjgen_reads_write_fastq(const kjgen_db *db, uint64_t seed, uint64_t first, i
     return 0;
 }
 
+/* ---- variable-length inputs for the "any read length" and protein-input (-p) paths -------------------------------
+ * Long DNA read: a concatenation of segments until the drawn length is reached; a segment is a back-translated DB
+ * protein window (60 %), random DNA (25 %), a codon repeat (low complexity after translation, 10 %) or a homopolymer
+ * (5 %); then 1 % substitutions, rare N, lower-case, and reverse-complement with probability 1/2. */
+static int gen_long_item(const kjgen_db *db, uint64_t seed, uint64_t idx, int minlen, int maxlen, char *out) {
+    rng_t r = rng_make(seed, 0x6000000000ull + idx);
+    static const char NUC[4] = {'A','C','G','T'};
+    int target = minlen + (int)rng_below(&r, (uint32_t)(maxlen - minlen + 1)), n = 0;
+    while (n < target) {
+        double u = rng_unif(&r); int room = target - n;
+        if (u < 0.60) {
+            int64_t p = (int64_t)(rng_unif(&r) * db->nprot); if (p >= db->nprot) p = db->nprot - 1;
+            int64_t L = db->off[p+1] - db->off[p];
+            int naa = 20 + (int)rng_below(&r, 400); if (naa > L) naa = (int)L;
+            int64_t s0 = (int64_t)(rng_unif(&r) * (L - naa + 1));
+            int shift = (int)rng_below(&r, 3);
+            for (int k = 0; k < shift && room > 0; k++, room--) out[n++] = NUC[rng_below(&r, 4)];
+            const char *prot = db->seq + db->off[p] + s0;
+            for (int k = 0; k < naa && room >= 3; k++, room -= 3) {
+                const char *cs = CODONS[prot[k] - 'A']; int nc = (int)strlen(cs) / 3; const char *c = cs + 3 * rng_below(&r, nc);
+                out[n++] = c[0]; out[n++] = c[1]; out[n++] = c[2];
+            }
+        } else if (u < 0.85) {
+            int m = 10 + (int)rng_below(&r, 300); if (m > room) m = room;
+            for (int k = 0; k < m; k++) out[n++] = NUC[rng_below(&r, 4)];
+        } else if (u < 0.95) {
+            /* codon repeat of period 3 or 6: translates to a long run of one or two residues in some frames */
+            int per = rng_below(&r, 2) ? 3 : 6; char unit[6]; for (int k = 0; k < per; k++) unit[k] = NUC[rng_below(&r, 4)];
+            int m = 36 + (int)rng_below(&r, 900); if (m > room) m = room;
+            for (int k = 0; k < m; k++) out[n++] = unit[k % per];
+        } else {
+            char a = NUC[rng_below(&r, 4)]; int m = 20 + (int)rng_below(&r, 200); if (m > room) m = room;
+            for (int k = 0; k < m; k++) out[n++] = a;
+        }
+    }
+    for (int k = 0; k < n; k++) if (rng_unif(&r) < 0.01) out[k] = NUC[rng_below(&r, 4)];
+    if (rng_below(&r, 2)) revcomp_inplace(out, n);
+    if (rng_unif(&r) < 0.3) { int c = 1 + (int)rng_below(&r, 3); for (int k = 0; k < c; k++) out[rng_below(&r, (uint32_t)n)] = 'N'; }
+    if (rng_unif(&r) < 0.05) for (int k = 0; k < n; k++) out[k] = (char)(out[k] | 0x20);
+    return n;
+}
+/* seq must hold n*maxlen bytes; off has n+1 entries */
+void kjgen_long_reads_packed(const kjgen_db *db, uint64_t seed, uint64_t first, int64_t n, int minlen, int maxlen, char *seq, uint64_t *off) {
+    char *tmp = (char *)malloc((size_t)maxlen + 8); uint64_t o = 0;
+    for (int64_t i = 0; i < n; i++) { int l = gen_long_item(db, seed, first + (uint64_t)i, minlen, maxlen, tmp); off[i] = o; memcpy(seq + o, tmp, (size_t)l); o += (uint64_t)l; }
+    off[n] = o; free(tmp);
+}
+/* Protein input: DB protein windows with substitutions (70 %) or random residues, low-complexity inserts, and the
+ * letters that split a protein read in the reference (X, B, Z, J, U, O -- the reader strips non-letters before the
+ * consumer sees the read, kaiju.cpp:331, so only letters can split), some lower-case. */
+static int gen_protein_item(const kjgen_db *db, uint64_t seed, uint64_t idx, int minlen, int maxlen, char *out) {
+    rng_t r = rng_make(seed, 0x7000000000ull + idx);
+    int target = minlen + (int)rng_below(&r, (uint32_t)(maxlen - minlen + 1)), n = 0;
+    while (n < target) {
+        double u = rng_unif(&r); int room = target - n;
+        if (u < 0.70) {
+            int64_t p = (int64_t)(rng_unif(&r) * db->nprot); if (p >= db->nprot) p = db->nprot - 1;
+            int64_t L = db->off[p+1] - db->off[p];
+            int naa = 8 + (int)rng_below(&r, 500); if (naa > L) naa = (int)L; if (naa > room) naa = room;
+            int64_t s0 = (int64_t)(rng_unif(&r) * (L - naa + 1));
+            memcpy(out + n, db->seq + db->off[p] + s0, (size_t)naa); n += naa;
+        } else if (u < 0.85) {
+            int m = 5 + (int)rng_below(&r, 80); if (m > room) m = room;
+            for (int k = 0; k < m; k++) out[n++] = rand_aa(&r);
+        } else {
+            char a = rand_aa(&r), b = rand_aa(&r); int m = 12 + (int)rng_below(&r, 300); if (m > room) m = room;
+            int two = (int)rng_below(&r, 2);
+            for (int k = 0; k < m; k++) out[n++] = (two && (k & 1)) ? b : a;
+        }
+    }
+    for (int k = 0; k < n; k++) if (rng_unif(&r) < 0.03) out[k] = rand_aa(&r);
+    static const char BAD[8] = {'X', 'X', 'B', 'Z', 'J', 'X', 'U', 'O'};
+    if (rng_unif(&r) < 0.5) { int c = 1 + (int)rng_below(&r, 4); for (int k = 0; k < c; k++) out[rng_below(&r, (uint32_t)n)] = BAD[rng_below(&r, 8)]; }
+    if (rng_unif(&r) < 0.1) for (int k = 0; k < n; k++) if (out[k] >= 'A' && out[k] <= 'Z') out[k] = (char)(out[k] | 0x20);
+    return n;
+}
+void kjgen_protein_reads_packed(const kjgen_db *db, uint64_t seed, uint64_t first, int64_t n, int minlen, int maxlen, char *seq, uint64_t *off) {
+    char *tmp = (char *)malloc((size_t)maxlen + 8); uint64_t o = 0;
+    for (int64_t i = 0; i < n; i++) { int l = gen_protein_item(db, seed, first + (uint64_t)i, minlen, maxlen, tmp); off[i] = o; memcpy(seq + o, tmp, (size_t)l); o += (uint64_t)l; }
+    off[n] = o; free(tmp);
+}
+
 #ifdef KJGEN_MAIN
 static void usage(void) {
     fprintf(stderr, "kjgen db    <nprot> <seed> <out.faa> <out.nodes.dmp>\n"
