@@ -36,7 +36,8 @@ typedef enum {
     KJ_ERR_NOMEM = -7
 } kj_status;
 
-#define KJ_MAX_READ_LEN 381     /* bases per mate (SEG trim bookkeeping is sized for fragments <= 127 aa) */
+#define KJ_MAX_READ_LEN 16383   /* bases per mate (queue payloads carry 15-bit array positions; fragment scores stay below 2^16) */
+#define KJ_MAX_PROTEIN_LEN 5461 /* residues of a protein read (-p): stored like one reading frame of a KJ_MAX_READ_LEN read */
 
 /* Mode / Config fields consumed by the path (src/Config.hpp:31-66, set by kaiju.cpp:74-202) */
 typedef struct {
@@ -48,7 +49,7 @@ typedef struct {
     int32_t use_evalue;           /* Greedy: 1 unless disabled; MEM: must be 0           */
     double min_evalue;            /* -E, default 0.01                                    */
     int32_t seg;                  /* -x (1, default) / -X (0)                            */
-    int32_t input_is_protein;     /* -p: not supported yet (KJ_ERR_UNSUPPORTED)          */
+    int32_t input_is_protein;     /* -p: seq1 holds protein letters, seq2 must be NULL  */
 } kj_params;
 
 /* Host views straight out of a .fmi loader (the reference's BWT/FMI/suffixArray structs:
@@ -104,6 +105,8 @@ int kj_classify(kj_ctx *ctx, const char *seq1, const uint64_t *off1, const char 
 #define KJ_MAX_MATCH_IDS 21
 int kj_classify_verbose(kj_ctx *ctx, const char *seq1, const uint64_t *off1, const char *seq2, const uint64_t *off2,
                         uint64_t n_reads, uint64_t *taxon_out, uint32_t *best_out, uint64_t *ids_out, uint8_t *nids_out);
+/* With params.input_is_protein (-p) seq1 holds protein letters (split at every letter outside the 20 residues,
+ * ConsumerThread.cpp:659-696) and seq2 must be NULL.  Reads longer than KJ_MAX_READ_LEN / KJ_MAX_PROTEIN_LEN -> KJ_ERR_UNSUPPORTED. */
 /* Device buffers (same layout, all pointers in the context's device memory), enqueued on `cuda_stream`
  * (a cudaStream_t, NULL = default stream); returns after the launch, results are ready when the stream is.
  * max_len1/max_len2: upper bounds of the mate lengths in the batch (0 = let the library compute them on the device). */
@@ -111,11 +114,19 @@ int kj_classify_device(kj_ctx *ctx, const char *d_seq1, const uint64_t *d_off1, 
                        uint64_t n_reads, uint32_t max_len1, uint32_t max_len2, uint64_t *d_taxon_out, uint32_t *d_best_out,
                        void *cuda_stream);
 
+/* Per-read work queues on the device are sized from worst-case bounds; should one overflow anyway, the affected launch is
+ * flagged (never silently truncated).  kj_classify() checks this itself; after kj_classify_device() call kj_check_errors()
+ * once the stream has finished: KJ_OK, or KJ_ERR_OVERFLOW (the results of that launch are invalid).  When the overflow was
+ * the Greedy substituted-variant ring (the reference's heap is unbounded; pathological -e/-s settings on long reads), the
+ * library enlarges the ring, so repeating the call succeeds -- kj_classify() does that internally. */
+int kj_check_errors(kj_ctx *ctx);
+
 /* --- introspection --- */
 const char *kj_last_error(void);                  /* thread-local text of the last failure          */
 uint64_t kj_kernel_launches(const kj_ctx *ctx);   /* number of kernels this context has launched    */
 uint64_t kj_index_bytes(const kj_ctx *ctx);       /* bytes of HBM held by the index                 */
 double kj_last_kernel_ms(const kj_ctx *ctx);      /* device time of the last classify kernel (CUDA events) */
+int kj_launch_geometry(const kj_ctx *ctx, int *grid, int *block, int *dyn_smem_bytes);  /* of the last classify launch */
 int kj_version(void);
 
 #ifdef __cplusplus

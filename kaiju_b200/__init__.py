@@ -78,13 +78,13 @@ def _check(rc):
         raise KaijuError("kaiju_b200 error %d: %s" % (rc, lib().kj_last_error().decode()))
 
 
-def make_params(mode="mem", m=11, e=3, s=65, seed=7, E=0.01, seg=True, use_evalue=None):
-    """Config fields as the kaiju CLI sets them (kaiju.cpp:74-202): -a -m -e -s -l -E -x/-X."""
+def make_params(mode="mem", m=11, e=3, s=65, seed=7, E=0.01, seg=True, use_evalue=None, protein=False):
+    """Config fields as the kaiju CLI sets them (kaiju.cpp:74-202): -a -m -e -s -l -E -x/-X -p."""
     greedy = mode in ("greedy", GREEDY, 1)
     if use_evalue is None:
         use_evalue = greedy
     return KjParams(mode=1 if greedy else 0, min_fragment_length=m, mismatches=e, min_score=s, seed_length=seed,
-                    use_evalue=1 if (use_evalue and greedy) else 0, min_evalue=E, seg=1 if seg else 0, input_is_protein=0)
+                    use_evalue=1 if (use_evalue and greedy) else 0, min_evalue=E, seg=1 if seg else 0, input_is_protein=1 if protein else 0)
 
 
 class Classifier:

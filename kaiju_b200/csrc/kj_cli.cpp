@@ -2,8 +2,9 @@
 //   kaiju-b200 -t nodes.dmp -f db.fmi -i reads.fastq [-j reads2.fastq] [-a mem|greedy] [-m -s -e -E -l] [-x|-X] [-o out] [-z N] [-v]
 // Output: "C\t<name>\t<taxid>\n" / "U\t<name>\t0\n" (ConsumerThread.cpp:724-739), in INPUT order.
 // Host glue only: FASTA/FASTQ(.gz) parsing with the reference's name trimming (kaiju.cpp:318-335) and strip() (util.cpp:26-33),
-// batching, kj_classify().  -z is accepted and ignored (the GPU replaces the consumer threads); -p is rejected; with -v
-// column 4 (best length/score) is appended -- columns 5-7 of the reference's -v output are not produced.
+// batching, kj_classify().  -z is accepted and ignored (the GPU replaces the consumer threads); -p = protein input; with -v
+// columns 4 (best length/score) and 5 (match taxon ids) are appended -- columns 6-7 of the reference's -v output
+// (accession names, fragment sequences) are not produced.
 #include <getopt.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -22,7 +23,7 @@ static void usage(const char* prog) {
                     "   -z INT        accepted for compatibility (ignored: the GPU replaces the worker threads)\n   -a STRING     Run mode, either \"mem\"  or \"greedy\" (default: greedy)\n"
                     "   -e INT        Number of mismatches allowed in Greedy mode (default: 3)\n   -m INT        Minimum match length (default: 11)\n   -s INT        Minimum match score in Greedy mode (default: 65)\n"
                     "   -E FLOAT      Minimum E-value in Greedy mode (default: 0.01)\n   -x            Enable SEG low complexity filter (enabled by default)\n   -X            Disable SEG low complexity filter\n"
-                    "   -v            Enable verbose output (adds the match length/score column)\n   -d INT        CUDA device ordinal (default 0)\n", prog);
+                    "   -p            Input sequences are protein sequences\n   -v            Enable verbose output (adds the match length/score and the matching taxon ids)\n   -d INT        CUDA device ordinal (default 0)\n", prog);
     exit(EXIT_FAILURE);
 }
 
@@ -63,7 +64,7 @@ int main(int argc, char** argv) {
             case 'h': usage(argv[0]); break;
             case 'd': device = atoi(optarg); break;
             case 'v': verbose = true; break;
-            case 'p': die("Protein input (-p) is not supported by kaiju-b200 yet."); break;
+            case 'p': P.input_is_protein = 1; break;
             case 'x': P.seg = 1; break;
             case 'X': P.seg = 0; break;
             case 'o': out_fn = optarg; break;
@@ -85,6 +86,7 @@ int main(int argc, char** argv) {
     if (fmi_fn.empty()) { fprintf(stderr, "Error: Please specify the location of the FMI file, using the -f option.\n\n"); usage(argv[0]); }
     if (in1.empty()) { fprintf(stderr, "Error: Please specify the location of the input file, using the -i option.\n\n"); usage(argv[0]); }
     const bool paired = !in2.empty();
+    if (paired && P.input_is_protein) { fprintf(stderr, "Error: Protein input only supports one input file.\n\n"); usage(argv[0]); }      // kaiju.cpp:201
 
     kj_fmi* fmi = nullptr; kj_nodes* nodes = nullptr; kj_ctx* ctx = nullptr;
     if (kj_nodes_load(nodes_fn.c_str(), &nodes) != KJ_OK) die(kj_last_error());
@@ -98,14 +100,21 @@ int main(int argc, char** argv) {
     setvbuf(out, nullptr, _IOFBF, 1 << 22);
     Reader r1(in1); Reader* r2 = paired ? new Reader(in2) : nullptr;
     const size_t BATCH = 1u << 20;
-    std::string seq1, seq2, name, name2, s; std::vector<uint64_t> off1, off2, taxon; std::vector<uint32_t> best; std::vector<std::string> names;
+    std::string seq1, seq2, name, name2, s; std::vector<uint64_t> off1, off2, taxon, ids; std::vector<uint32_t> best; std::vector<uint8_t> nids; std::vector<std::string> names;
     auto flush = [&]() {
         size_t n = names.size(); if (!n) return;
         taxon.resize(n); best.resize(n);
-        int rc = kj_classify(ctx, seq1.data(), off1.data(), paired ? seq2.data() : nullptr, paired ? off2.data() : nullptr, n, taxon.data(), best.data());
+        int rc;
+        if (verbose) { ids.resize(n * KJ_MAX_MATCH_IDS); nids.resize(n);
+                       rc = kj_classify_verbose(ctx, seq1.data(), off1.data(), paired ? seq2.data() : nullptr, paired ? off2.data() : nullptr, n, taxon.data(), best.data(), ids.data(), nids.data()); }
+        else rc = kj_classify(ctx, seq1.data(), off1.data(), paired ? seq2.data() : nullptr, paired ? off2.data() : nullptr, n, taxon.data(), best.data());
         if (rc != KJ_OK) die(kj_last_error());
         for (size_t i = 0; i < n; i++) {
-            if (taxon[i]) { if (verbose) fprintf(out, "C\t%s\t%llu\t%u\n", names[i].c_str(), (unsigned long long)taxon[i], best[i]); else fprintf(out, "C\t%s\t%llu\n", names[i].c_str(), (unsigned long long)taxon[i]); }
+            if (taxon[i]) {
+                fprintf(out, "C\t%s\t%llu", names[i].c_str(), (unsigned long long)taxon[i]);
+                if (verbose) { fprintf(out, "\t%u\t", best[i]); for (unsigned k = 0; k < nids[i]; k++) fprintf(out, "%llu,", (unsigned long long)ids[i * KJ_MAX_MATCH_IDS + k]); }     // ConsumerThread.cpp:527-536
+                fputc('\n', out);
+            }
             else fprintf(out, "U\t%s\t0\n", names[i].c_str());
         }
         seq1.clear(); seq2.clear(); off1.assign(1, 0); off2.assign(1, 0); names.clear();
@@ -119,7 +128,7 @@ int main(int argc, char** argv) {
             seq2 += s; off2.push_back(seq2.size());
         }
         names.push_back(name);
-        if (names.size() >= BATCH) flush();
+        if (names.size() >= BATCH || seq1.size() >= (1u << 30)) flush();
     }
     flush();
     if (paired && r2->next(name2, s)) fprintf(stderr, "Warning: File %s has more reads then file %s\n", in2.c_str(), in1.c_str());

@@ -43,7 +43,10 @@ static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
     // union: SEG trim scratch (alive inside getNextFragment's SEG gate) | greedy search arrays (alive after the gate)
     const uint32_t u = o;
     L.segcnt_off = u; L.seghist_off = u + 20u * 32u;
-    const uint32_t seg_bytes = 20u * 32u + kj_align((p.max_frag + 2) * 32u, 8);
+    // count histograms of the lane-parallel trim search for regions <= 127 residues; longer regions use the sorted-composition
+    // variant (kj_seg_trim_long), whose per-lane state (20 x {uint16 count, letter, position}) fits in the same bytes
+    const uint32_t seg_rows = p.max_frag + 2 < 130u ? p.max_frag + 2 : 130u;
+    const uint32_t seg_bytes = 20u * 32u + kj_align(seg_rows * 32u, 8);
     uint32_t g_bytes = 0;
     L.res_off = u; L.res2_off = u; L.pre_off = u;
     if (p.mode == 1) {
@@ -271,38 +274,17 @@ static KJ_DEV uint32_t kj_nuc(uint8_t ch) {          // nuc2int (ConsumerThread.
     uint32_t u = ch & 0xDFu;
     return u == 'A' ? 0u : u == 'C' ? 1u : u == 'G' ? 2u : (u == 'T' || u == 'U') ? 3u : 4u;
 }
-// Both mates are translated and split in the SAME loops (array a = 2*mate + strand): the four arrays are independent, so
-// their load/ballot/bit-twiddling chains overlap instead of running back to back (the kernel is bound by dependent latency).
-static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s1, int n1, bool do1, const uint8_t* s2, int n2, bool do2, bool greedy) {
+// fragments = maximal stop-free runs of every frame (a stride-3 walk of an array); na1/na2 = array lengths of the two mates
+// (0 = mate absent), nframes = 3 for translated DNA, 1 for protein input (one "frame" whose residues sit at indices 3e).
+static KJ_DEV void kj_split_frames(KjWarpCtx& cx, KjQueue& q, const int na1, const int na2, const int n1, const int n2, const bool greedy, const int nframes) {
     const Warp& w = cx.w; const KjTables& tb = *cx.tb;
-    uint8_t* aa = cx.smem + cx.L.aa_off; const uint32_t st = cx.L.aa_stride;
-    const int na1 = do1 ? n1 - 2 : 0, na2 = do2 ? n2 - 2 : 0;
-    const int namax = na1 > na2 ? na1 : na2;
-    // 30 codon positions per pass: every lane decodes ONE base per mate, its two successors come from the next lanes
-    for (int b = 0; b < namax; b += 30) {
-        const int pos = b + w.lane;
-        const uint32_t x0 = (do1 && pos < n1) ? kj_nuc(s1[pos]) : 4u, y0 = (do2 && pos < n2) ? kj_nuc(s2[pos]) : 4u;
-        const uint32_t x1 = w.shfl(x0, w.lane + 1), x2 = w.shfl(x0, w.lane + 2), y1 = w.shfl(y0, w.lane + 1), y2 = w.shfl(y0, w.lane + 2);
-        if (w.lane < 30) {
-            if (pos < na1) {
-                const bool ok = (x0 | x1 | x2) < 4u;
-                aa[pos] = ok ? tb.codon_aa[x0 << 4 | x1 << 2 | x2] : (uint8_t)0;
-                aa[st + (uint32_t)(na1 - 1 - pos)] = ok ? tb.codon_aa[(3u - x2) << 4 | (3u - x1) << 2 | (3u - x0)] : (uint8_t)0;
-            }
-            if (pos < na2) {
-                const bool ok = (y0 | y1 | y2) < 4u;
-                aa[2u * st + (uint32_t)pos] = ok ? tb.codon_aa[y0 << 4 | y1 << 2 | y2] : (uint8_t)0;
-                aa[3u * st + (uint32_t)(na2 - 1 - pos)] = ok ? tb.codon_aa[(3u - y2) << 4 | (3u - y1) << 2 | (3u - y0)] : (uint8_t)0;
-            }
-        }
-    }
-    w.sync();
+    const uint8_t* aa = cx.smem + cx.L.aa_off; const uint32_t st = cx.L.aa_stride;
     // fragments = maximal stop-free runs of every frame (a stride-3 walk of an array).  Per frame the stop positions
     // become a bit mask (ballot), so each lane finds "am I the last residue of a run, and where does it start" with bit
     // operations instead of a serial scan.  Insertion order (ConsumerThread.cpp:196-268): runs closed by a stop in scan
     // order of that stop; leftovers afterwards in frame order 0,1,2 where frame = count % 3 in FORWARD coordinates.
     const uint32_t m = cx.rp->m;
-    for (int r = 0; r < 3; r++) {
+    for (int r = 0; r < nframes; r++) {
         const int ne1 = (na1 - r + 2) / 3, ne2 = (na2 - r + 2) / 3;      // elements e: array index r + 3e
         const int nemax = ne1 > ne2 ? ne1 : ne2;
         int run_open[4] = {0, 0, 0, 0};                                  // first element after the last stop of the earlier chunks (uniform)
@@ -312,7 +294,7 @@ static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s
             bool in[4], stop[4]; uint32_t sm[4], pre[4];
             #pragma unroll
             for (int a = 0; a < 4; a++) {
-                const int ne = a < 2 ? ne1 : ne2; in[a] = e < ne;
+                const int ne = (nframes == 1 && (a & 1)) ? 0 : (a < 2 ? ne1 : ne2); in[a] = e < ne;
                 const uint32_t c = in[a] ? aa[(uint32_t)a * st + (uint32_t)(r + 3 * e)] : 0u;
                 stop[a] = in[a] && c == 0; pre[a] = (greedy && in[a]) ? (uint32_t)tb.b62[c][c] : 0u;     // BLOSUM62 diagonal (calcScore, 415-421); b62[0][0] = 0
             }
@@ -329,7 +311,7 @@ static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s
             }
             #pragma unroll
             for (int a = 0; a < 4; a++) {
-                const int ne = a < 2 ? ne1 : ne2; const int n = a < 2 ? n1 : n2; const uint8_t* A = aa + (uint32_t)a * st;
+                const int ne = (nframes == 1 && (a & 1)) ? 0 : (a < 2 ? ne1 : ne2); const int n = a < 2 ? n1 : n2; const uint8_t* A = aa + (uint32_t)a * st;
                 if (e0 < ne) {                                           // uniform
                     // a run ends at e if e is a residue and e+1 is a stop or the end
                     const bool is_res = in[a] && !stop[a];
@@ -356,6 +338,35 @@ static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s
             }
         }
     }
+}
+
+// Both mates are translated and split in the SAME loops (array a = 2*mate + strand): the four arrays are independent, so
+// their load/ballot/bit-twiddling chains overlap instead of running back to back (the kernel is bound by dependent latency).
+static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s1, int n1, bool do1, const uint8_t* s2, int n2, bool do2, bool greedy) {
+    const Warp& w = cx.w; const KjTables& tb = *cx.tb;
+    uint8_t* aa = cx.smem + cx.L.aa_off; const uint32_t st = cx.L.aa_stride;
+    const int na1 = do1 ? n1 - 2 : 0, na2 = do2 ? n2 - 2 : 0;
+    const int namax = na1 > na2 ? na1 : na2;
+    // 30 codon positions per pass: every lane decodes ONE base per mate, its two successors come from the next lanes
+    for (int b = 0; b < namax; b += 30) {
+        const int pos = b + w.lane;
+        const uint32_t x0 = (do1 && pos < n1) ? kj_nuc(s1[pos]) : 4u, y0 = (do2 && pos < n2) ? kj_nuc(s2[pos]) : 4u;
+        const uint32_t x1 = w.shfl(x0, w.lane + 1), x2 = w.shfl(x0, w.lane + 2), y1 = w.shfl(y0, w.lane + 1), y2 = w.shfl(y0, w.lane + 2);
+        if (w.lane < 30) {
+            if (pos < na1) {
+                const bool ok = (x0 | x1 | x2) < 4u;
+                aa[pos] = ok ? tb.codon_aa[x0 << 4 | x1 << 2 | x2] : (uint8_t)0;
+                aa[st + (uint32_t)(na1 - 1 - pos)] = ok ? tb.codon_aa[(3u - x2) << 4 | (3u - x1) << 2 | (3u - x0)] : (uint8_t)0;
+            }
+            if (pos < na2) {
+                const bool ok = (y0 | y1 | y2) < 4u;
+                aa[2u * st + (uint32_t)pos] = ok ? tb.codon_aa[y0 << 4 | y1 << 2 | y2] : (uint8_t)0;
+                aa[3u * st + (uint32_t)(na2 - 1 - pos)] = ok ? tb.codon_aa[(3u - y2) << 4 | (3u - y1) << 2 | (3u - y0)] : (uint8_t)0;
+            }
+        }
+    }
+    w.sync();
+    kj_split_frames(cx, q, na1, na2, n1, n2, greedy, 3);
 }
 
 // copy the characters of item (arr,start,len) into the contiguous fragment buffer
@@ -409,9 +420,68 @@ static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
     return any_low;
 }
 
+// s_Trim for regions longer than 127 residues (long reads / protein input).  Same search, but each lane keeps the
+// composition of its sliding window as a descending-sorted count vector (the reference's state vector, s_StateOn
+// 1628-1650): a count changes by +-1 per step, so the vector stays sorted by swapping the changed letter to the edge
+// of its run of equal counts.  s_GetProb then walks the 20 sorted counts in the reference's order.
+static KJ_DEV void kj_seg_trim_long(KjWarpCtx& cx, const uint8_t* s, int n2, int& leftend, int& rightend) {
+    const Warp& w = cx.w;
+    uint16_t* sv = (uint16_t*)(cx.smem + cx.L.segcnt_off);            // [20][32] counts, descending per lane
+    uint8_t* at = (uint8_t*)(sv + 20 * 32);                            // [20][32] letter stored at sorted position k
+    uint8_t* where = at + 20 * 32;                                     // [20][32] sorted position of letter a
+    const double* lnf = cx.ix->lnfact;
+    int minlen = 1; if (n2 - KJ_SEG_MAXTRIM > minlen) minlen = n2 - KJ_SEG_MAXTRIM;
+    const int nlens = n2 - minlen;
+    double g_prob = 1.0; int g_lend = 0, g_rend = n2 - 1;            // uniform
+    const int ln = w.lane;
+    for (int pass = 0; pass * 32 < nlens; pass++) {
+        const int len = n2 - (pass * 32 + ln);
+        const bool act = (pass * 32 + ln) < nlens;
+        for (int k = 0; k < 20; k++) { sv[k * 32 + ln] = 0; at[k * 32 + ln] = (uint8_t)k; where[k * 32 + ln] = (uint8_t)k; }
+        double my_prob = 1.0; int my_i = 0;
+        if (act) {
+            #define KJ_SV_SWAP(p_, q_) { const uint32_t la_ = at[(p_) * 32 + ln], lb_ = at[(q_) * 32 + ln]; at[(p_) * 32 + ln] = (uint8_t)lb_; at[(q_) * 32 + ln] = (uint8_t)la_; \
+                where[la_ * 32 + ln] = (uint8_t)(q_); where[lb_ * 32 + ln] = (uint8_t)(p_); }
+            #define KJ_SV_ADD(letter) { const uint32_t a_ = (letter) - 1u; uint32_t p_ = where[a_ * 32 + ln]; const uint32_t v_ = sv[p_ * 32 + ln]; uint32_t q_ = p_; \
+                while (q_ > 0 && sv[(q_ - 1) * 32 + ln] == v_) q_--; if (q_ != p_) KJ_SV_SWAP(p_, q_); sv[q_ * 32 + ln] = (uint16_t)(v_ + 1u); }
+            #define KJ_SV_DEL(letter) { const uint32_t a_ = (letter) - 1u; uint32_t p_ = where[a_ * 32 + ln]; const uint32_t v_ = sv[p_ * 32 + ln]; uint32_t q_ = p_; \
+                while (q_ < 19 && sv[(q_ + 1) * 32 + ln] == v_) q_++; if (q_ != p_) KJ_SV_SWAP(p_, q_); sv[q_ * 32 + ln] = (uint16_t)(v_ - 1u); }
+            for (int t = 0; t < len; t++) KJ_SV_ADD(s[t]);
+            for (int i = 0; i + len <= n2; i++) {
+                // s_GetProb (1941-1962) = s_LnAss (1890-1930) + s_LnPerm (1865-1879) - len*ln20, same operation order
+                double ans1 = lnf[20], ans2 = lnf[len];
+                int k = 0;
+                while (k < 20) {
+                    const uint32_t v = sv[k * 32 + ln];
+                    int cls = 1; while (k + cls < 20 && sv[(k + cls) * 32 + ln] == v) cls++;
+                    ans1 = kj_dsub(ans1, lnf[cls]);                   // one class of equal counts (the zero class included)
+                    if (v) for (int rep = 0; rep < cls; rep++) ans2 = kj_dsub(ans2, lnf[v]);
+                    k += cls;
+                }
+                double prob = kj_dsub(kj_dadd(ans1, ans2), kj_dmul((double)len, 2.9957322735539909));
+                if (prob < my_prob) { my_prob = prob; my_i = i; }
+                if (i + len < n2) { KJ_SV_DEL(s[i]); KJ_SV_ADD(s[i + len]); }
+            }
+            #undef KJ_SV_ADD
+            #undef KJ_SV_DEL
+            #undef KJ_SV_SWAP
+        }
+        w.sync();
+        double mn = my_prob;
+        for (int mm = 16; mm > 0; mm >>= 1) { double o = w.shfl_d(mn, w.lane ^ mm); mn = o < mn ? o : mn; }
+        if (mn < g_prob) {
+            int src = kj_ffs(w.ballot(my_prob == mn)) - 1;
+            int wi = w.shfl(my_i, src); int wlen = n2 - (pass * 32 + src);
+            g_prob = mn; g_lend = wi; g_rend = wlen + wi - 1;
+        }
+    }
+    leftend += g_lend; rightend -= (n2 - g_rend - 1);
+}
+
 // s_Trim (blast_seg.c:1971-2015): the sub-window of s[0..n2) with minimal s_GetProb; first in
 // (len descending, start ascending) order wins ties.  One lane per window length, sliding start.
 static KJ_DEV void kj_seg_trim(KjWarpCtx& cx, const uint8_t* s, int n2, int& leftend, int& rightend) {
+    if (n2 > 127) { kj_seg_trim_long(cx, s, n2, leftend, rightend); return; }
     const Warp& w = cx.w;
     uint8_t* cnt = cx.smem + cx.L.segcnt_off;       // [20][32]
     uint8_t* hist = cx.smem + cx.L.seghist_off;     // [n2+1][32] number of letters having count v
@@ -700,18 +770,41 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
 // ---------------------------------------------------------------------------------------------
 template <class IdxT> static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int n2, uint32_t& best_out);
 
+// Protein input (-p, ConsumerThread.cpp:640-646, 659-696): the read is upper-cased and split at every letter outside
+// "ACDEFGHIKLMNPQRSTVWY"; pieces of at least m residues (Greedy: and score >= min_score) are queued in order, the tail last.
+// The residues are stored like one reading frame of a translated read (residue e at array index 3e), so the queue
+// payloads, kj_load_frag and the SEG pieces need no second addressing mode.
+static KJ_DEV void kj_protein_fragments(KjWarpCtx& cx, KjQueue& q, const uint8_t* s1, int n1, bool greedy) {
+    const Warp& w = cx.w; const KjTables& tb = *cx.tb;
+    uint8_t* aa = cx.smem + cx.L.aa_off;
+    for (int t = w.lane; t < n1; t += 32) {
+        const uint32_t u = s1[t] & 0xDFu;                                // in 'A'..'Z' exactly for ASCII letters (toupper)
+        aa[3 * t] = (u >= 'A' && u <= 'Z') ? tb.aa_index[u - 'A'] : (uint8_t)0;
+    }
+    w.sync();
+    kj_split_frames(cx, q, 3 * n1 - 2, 0, n1, 0, greedy, 1);
+}
+
 template <int MODE, class IdxT>
 static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1, const uint8_t* s2, int n2, bool paired, uint32_t& best_out) {
     const KjRunParams& rp = *cx.rp;
     best_out = 0; cx.nids = 0;
-    const int m3 = (int)rp.m * 3;
-    // short-read gate (648-653): SE len1 < 3m; PE only if BOTH mates are short
-    if ((!paired && n1 < m3) || (paired && n1 < m3 && n2 < m3)) return KJ_TAX_BAD;
     KjQueue q; q.key = (uint64_t*)(cx.smem + cx.L.qkey_off); q.pay = (uint32_t*)(cx.smem + cx.L.qpay_off);
     q.ord = cx.smem + cx.L.qord_off; q.cap = rp.item_cap; q.n = 0; q.late = 0; q.next = 0; q.nsorted = 0; q.dirty = true;
     const bool greedy = MODE == 1;
-    kj_translate_pair(cx, q, s1, n1, n1 >= m3, s2, n2, paired && n2 >= m3, greedy);   // a short mate is skipped individually (699, 705)
+    double query_len;                                                    // E-value query length (659, 698, 704)
+    if (rp.protein) {
+        if (n1 < (int)rp.m) return KJ_TAX_BAD;                           // (640-646)
+        query_len = (double)n1;
+        kj_protein_fragments(cx, q, s1, n1, greedy);
+    } else {
+        const int m3 = (int)rp.m * 3;
+        // short-read gate (648-653): SE len1 < 3m; PE only if BOTH mates are short
+        if ((!paired && n1 < m3) || (paired && n1 < m3 && n2 < m3)) return KJ_TAX_BAD;
+        query_len = (double)n1 / 3.0; if (paired) query_len += (double)n2 / 3.0;
+        kj_translate_pair(cx, q, s1, n1, n1 >= m3, s2, n2, paired && n2 >= m3, greedy);   // a short mate is skipped individually (699, 705)
+    }
     if (MODE == 1) kj_queue_sort(cx, q);     // greedy pops every fragment (and many variants): ranking once pays (A/B +9 %); MEM stops after a few pops (A/B -16 %)
     if (MODE == 0) return kj_classify_mem<IdxT>(cx, q, best_out);
-    else return kj_classify_greedy<IdxT>(cx, q, n1, paired ? n2 : 0, best_out);
+    else return kj_classify_greedy<IdxT>(cx, q, query_len, best_out);
 }

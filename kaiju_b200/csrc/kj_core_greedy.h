@@ -15,12 +15,12 @@ struct alignas(16) KjVariant {
     uint32_t pay;              // source run: arr(2) start(15) len(14) -- len already truncated
     int32_t diff;              // accumulated substitution score delta (Fragment::diff)
     uint16_t matchlen; uint8_t num_mm; uint8_t pad;
-    uint16_t subs[KJ_MAX_MM];  // pos << 5 | letter
-    uint32_t pad2; uint64_t pad3;
+    uint32_t subs[KJ_MAX_MM];  // pos << 5 | letter
+    uint32_t pad2;
 };
-#define KJ_VARIANT_CAP 256u
-// per-warp ring in global scratch: keys[CAP] (scanned, contiguous) followed by the payload records
-static KJ_HD uint32_t kj_greedy_scratch_bytes(const KjRunParams& rp) { return rp.mode == 1 ? KJ_VARIANT_CAP * (uint32_t)(sizeof(KjVariant) + 8u) : 64u; }
+static_assert(sizeof(KjVariant) == 64, "KjVariant is one 64-byte record");
+// per-warp ring in global scratch: keys[variant_cap] (scanned, contiguous) followed by the payload records
+static KJ_HD uint32_t kj_greedy_scratch_bytes(const KjRunParams& rp) { return rp.mode == 1 ? rp.variant_cap * (uint32_t)(sizeof(KjVariant) + 8u) : 64u; }
 
 struct KjMatch { uint64_t lo; uint32_t len; uint16_t qi, ql; };    // one SI: interval + query position/length
 
@@ -50,14 +50,14 @@ static KJ_DEV uint32_t kj_scan_incl(const Warp& w, uint32_t v) {
 }
 
 template <class IdxT>
-static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int n2, uint32_t& best_out) {
+static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double query_len, uint32_t& best_out) {
     const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix; const KjRunParams& rp = *cx.rp; const KjTables& tb = *cx.tb;
     uint8_t* frag = cx.smem + cx.L.frag_off;
     uint16_t* pre = (uint16_t*)(cx.smem + cx.L.pre_off);               // pre[t] = sum diag(frag[0..t))
     KjMatch* res = (KjMatch*)(cx.smem + cx.L.res_off);                  // per-j chain results, then recorded matches
     KjMatch* cls = (KjMatch*)(cx.smem + cx.L.res2_off);                 // recorded matches sorted into classes
-    uint16_t* psub = (uint16_t*)(cx.smem + cx.L.ids_off + 64u);           // the id set is only filled after the loop
-    KjVQueue vq; vq.gkey = (uint64_t*)cx.gscratch; vq.v = (KjVariant*)((uint8_t*)cx.gscratch + 8u * KJ_VARIANT_CAP); vq.n = 0; vq.live = 0;
+    uint32_t* psub = (uint32_t*)(cx.smem + cx.L.ids_off + 64u);           // the id set is only filled after the loop
+    KjVQueue vq; vq.gkey = (uint64_t*)cx.gscratch; vq.v = (KjVariant*)((uint8_t*)cx.gscratch + 8u * rp.variant_cap); vq.n = 0; vq.live = 0;
     uint32_t best = 0, nbest = 0;                                        // best_match_score, best_matches_SI.size()  (uniform)
     best_out = 0;
 
@@ -76,7 +76,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
         const uint64_t g = ga > gb ? ga : gb;
         if (g == 0) break;
         if ((uint32_t)(g >> 32) < best) break;
-        uint32_t arr, start, len, num_mm = 0, matchlen = 0; int diff = 0; uint64_t si0 = 0, si1 = 0; bool segchecked; uint32_t nsub = 0; uint16_t mysub = 0;
+        uint32_t arr, start, len, num_mm = 0, matchlen = 0; int diff = 0; uint64_t si0 = 0, si1 = 0; bool segchecked; uint32_t nsub = 0; uint32_t mysub = 0;
         if (ga >= gb) {
             uint32_t p = 0;
             if (!q.dirty) { p = q.pay[slot_a]; q.next++; }
@@ -207,8 +207,8 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
                         const uint32_t okmask = w.ballot(ok); const uint32_t cnt = (uint32_t)kj_popc(okmask);
                         if (cnt) {
                             // the pop scans keys[0..n): squeeze out popped entries once the ring passes 64 slots and at least half are holes
-                            if (vq.n + cnt > KJ_VARIANT_CAP || (vq.n + cnt > 64u && vq.live * 2u <= vq.n)) { kj_vq_compact(cx, vq); }
-                            if (vq.n + cnt > KJ_VARIANT_CAP) { if (w.lane == 0) kj_flag_error(cx, 4u); }
+                            if (vq.n + cnt > rp.variant_cap || (vq.n + cnt > 64u && vq.live * 2u <= vq.n)) { kj_vq_compact(cx, vq); }
+                            if (vq.n + cnt > rp.variant_cap) { if (w.lane == 0) kj_flag_error(cx, 4u); }
                             else {
                                 const uint32_t rk = (uint32_t)kj_popc(okmask & lanemask_lt(w.lane));
                                 KjVariant* V = vq.v + (vq.n + rk);                 // dereferenced by `ok` lanes only
@@ -216,10 +216,10 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
                                 uint32_t ns = 0;
                                 for (uint32_t u = 0; u < nsub; u++) {
                                     const uint32_t sv = psub[u];
-                                    if ((sv >> 5) < new_len) { if (ok) V->subs[ns] = (uint16_t)sv; ns++; }
+                                    if ((sv >> 5) < new_len) { if (ok) V->subs[ns] = sv; ns++; }
                                 }
                                 if (ok) {
-                                    V->subs[ns] = (uint16_t)((pos << 5) | sub);
+                                    V->subs[ns] = (pos << 5) | sub;
                                     V->lo = (uint64_t)lo; V->hi = (uint64_t)hi; V->pay = kj_qpay(arr, true, start, new_len);
                                     V->diff = diff + (int)tb.b62[o][sub] - (int)tb.b62[sub][sub];
                                     V->matchlen = (uint16_t)(sm.ql + 1u); V->num_mm = (uint8_t)(ns + 1u); V->pad = 0; V->pad2 = 0;
@@ -269,7 +269,14 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, int n1, int
 
     if (nbest == 0) return KJ_TAX_BAD;
     if (rp.use_evalue) {                                                   // E-value gate (500-513) as an integer threshold
-        uint32_t thr = rp.evalue_min_score[(uint32_t)n1 * rp.ev_stride + (uint32_t)n2];
+        // minimal passing score = number of score break points below the query length (kj_build_evalue_breaks)
+        uint32_t thr = 0;
+        for (uint32_t b = 0; b < rp.n_ev_breaks; b += 32) {
+            const uint32_t k = b + (uint32_t)w.lane;
+            const uint32_t below = w.ballot(k < rp.n_ev_breaks && rp.ev_breaks[k] < query_len);
+            thr += (uint32_t)kj_popc(below);
+            if (below != 0xffffffffu) break;                               // breaks ascend: the first lane that is not below ends the count
+        }
         if (best < thr) return KJ_TAX_BAD;
     }
     w.sync();

@@ -26,6 +26,7 @@
 #define KJ_MIN_BLOCKS_GREEDY 4   // A/B: 8.30 vs 7.94 M pairs/s
 #endif
 #define KJ_CHUNK_READS (1u << 20)
+#define KJ_CHUNK_BYTES (1ull << 28)  // and at most this many bases of one mate per chunk (long reads)
 #define KJ_CLAIM 4               // read items claimed per atomic by a warp
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { kj_err() = std::string(#call) + ": " + cudaGetErrorString(e_); return KJ_ERR_CUDA; } } while (0)
@@ -40,7 +41,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
                    uint64_t base1, uint64_t base2, uint64_t n_reads,
                    uint64_t* __restrict__ taxon_out, uint32_t* __restrict__ best_out, uint64_t* __restrict__ ids_out, uint8_t* __restrict__ nids_out,
                    unsigned long long* __restrict__ counter, KjKept* __restrict__ spill, uint8_t* __restrict__ gscratch,
-                   uint32_t gscratch_bytes, uint32_t* __restrict__ err) {
+                   uint32_t gscratch_bytes, uint8_t* __restrict__ gws, uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     KjCtaShared* sh = (KjCtaShared*)smem_raw;
     {   // stage the index descriptor (C[] etc.) and the small tables once per CTA
@@ -55,8 +56,10 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
     cx.w.lane = threadIdx.x & 31;
     cx.ix = &sh->ix; cx.rp = &rp; cx.tb = &sh->tb;
     cx.L = kj_smem_layout(rp);
-    cx.smem = smem_raw + kj_align((uint32_t)sizeof(KjCtaShared), 16) + (uint32_t)warp_in_cta * cx.L.total;
     const uint64_t gwarp = (uint64_t)blockIdx.x * KJ_WARPS_PER_CTA + (uint64_t)warp_in_cta;
+    // per-warp work space: shared memory, or (reads too long for it) a slice of a global buffer that stays L1/L2-resident
+    cx.smem = rp.ws_global ? gws + gwarp * cx.L.total
+                           : smem_raw + kj_align((uint32_t)sizeof(KjCtaShared), 16) + (uint32_t)warp_in_cta * cx.L.total;
     cx.spill = spill + gwarp * rp.scratch_entries;
     cx.gscratch = gscratch + gwarp * gscratch_bytes;
     cx.err = err;
@@ -114,7 +117,9 @@ struct kj_ctx {
     // run state
     unsigned long long* d_counter = nullptr; uint32_t* d_err = nullptr; unsigned int* d_maxlen = nullptr;
     KjKept* d_spill = nullptr; size_t spill_bytes = 0; uint8_t* d_gscratch = nullptr; size_t gscratch_bytes_total = 0;
-    uint16_t* d_evtab = nullptr; uint32_t ev1 = 0, ev2 = 0; std::vector<uint16_t> evtab;
+    double* d_evbreaks = nullptr; uint32_t n_evbreaks = 0;
+    uint32_t variant_boost = 1;    // Greedy variant-ring capacity multiplier, raised after an overflow (flag 4) so that a retry succeeds
+    uint8_t* d_ws = nullptr; size_t ws_bytes = 0;
     cudaStream_t stream[2] = {nullptr, nullptr}; cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // staging for kj_classify (host buffers)
     uint8_t* d_seq[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; size_t d_seq_cap[2][2] = {{0, 0}, {0, 0}};
@@ -132,10 +137,15 @@ template <class T> static int upload(const std::vector<T>& v, void** d, uint64_t
     total += bytes; return KJ_OK;
 }
 
-static int configure_launch(kj_ctx* c, const KjRunParams& rp, size_t& smem, int& grid) {
+// Shared-memory work space while two CTAs still fit on an SM; beyond that (reads of several hundred bases and more) the
+// same carve-up is addressed in a global buffer instead, which keeps the grid at full occupancy for any read length.
+#define KJ_SMEM_WS_LIMIT (113u * 1024u)
+static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid) {
     KjSmemLayout L = kj_smem_layout(rp);
-    smem = kj_align((uint32_t)sizeof(KjCtaShared), 16) + (size_t)KJ_WARPS_PER_CTA * L.total;
-    if (smem > 227 * 1024) { kj_err() = "per-CTA shared memory exceeds 227 KB (reads too long / -m too small)"; return KJ_ERR_UNSUPPORTED; }
+    const size_t head = kj_align((uint32_t)sizeof(KjCtaShared), 16);
+    smem = head + (size_t)KJ_WARPS_PER_CTA * L.total;
+    rp.ws_global = smem > KJ_SMEM_WS_LIMIT ? 1u : 0u;
+    if (rp.ws_global) smem = head;
     if (smem == c->smem_bytes && c->grid > 0 && c->cfg_mode == rp.mode) { grid = c->grid; return KJ_OK; }
     int per_sm = 0;
 #define KJ_CFG(M, T) { CK(cudaFuncSetAttribute(kj_classify_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -155,21 +165,19 @@ static int ensure_scratch(kj_ctx* c, const KjRunParams& rp, int grid) {
     if (need > c->spill_bytes) { if (c->d_spill) cudaFree(c->d_spill); c->d_spill = nullptr; CK(cudaMalloc((void**)&c->d_spill, need)); c->spill_bytes = need; }
     size_t gneed = warps * (size_t)kj_greedy_scratch_bytes(rp);
     if (gneed > c->gscratch_bytes_total) { if (c->d_gscratch) cudaFree(c->d_gscratch); c->d_gscratch = nullptr; CK(cudaMalloc((void**)&c->d_gscratch, gneed)); c->gscratch_bytes_total = gneed; }
+    size_t wneed = rp.ws_global ? warps * (size_t)kj_smem_layout(rp).total : 0;
+    if (wneed > c->ws_bytes) { if (c->d_ws) cudaFree(c->d_ws); c->d_ws = nullptr; CK(cudaMalloc((void**)&c->d_ws, wneed)); c->ws_bytes = wneed; }
     return KJ_OK;
 }
 
-static int ensure_evalue_table(kj_ctx* c, KjRunParams& rp, uint32_t max1, uint32_t max2, cudaStream_t st) {
-    if (!(c->params.mode == 1 && c->params.use_evalue)) { rp.evalue_min_score = nullptr; rp.ev_stride = 0; return KJ_OK; }
-    if (!c->d_evtab || max1 > c->ev1 || max2 > c->ev2) {
-        uint32_t n1 = std::max(max1, c->ev1), n2 = std::max(max2, c->ev2);
-        kj_build_evalue_table(c->params, c->H.db_length, n1, n2, c->evtab);
-        if (c->d_evtab) cudaFree(c->d_evtab); c->d_evtab = nullptr;
-        CK(cudaMalloc((void**)&c->d_evtab, c->evtab.size() * sizeof(uint16_t)));
-        CK(cudaMemcpyAsync(c->d_evtab, c->evtab.data(), c->evtab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
-        c->ev1 = n1; c->ev2 = n2;
-    }
-    rp.evalue_min_score = c->d_evtab; rp.ev_stride = c->ev2 + 1;
+// E-value gate: break points of the minimal passing score (kj_build_evalue_breaks), rebuilt when the parameters change
+static int upload_evalue_breaks(kj_ctx* c) {
+    if (c->d_evbreaks) { cudaFree(c->d_evbreaks); c->d_evbreaks = nullptr; } c->n_evbreaks = 0;
+    std::vector<double> br; int rc = kj_build_evalue_breaks(c->params, c->H.db_length, br); if (rc) return rc;
+    if (br.empty()) return KJ_OK;
+    CK(cudaMalloc((void**)&c->d_evbreaks, br.size() * sizeof(double)));
+    CK(cudaMemcpy(c->d_evbreaks, br.data(), br.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->n_evbreaks = (uint32_t)br.size();
     return KJ_OK;
 }
 
@@ -205,21 +213,23 @@ extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, cons
     CK(cudaMemset(c->d_err, 0, sizeof(uint32_t)));
     for (int s = 0; s < 2; s++) CK(cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev_a)); CK(cudaEventCreate(&c->ev_b));
+    if ((rc = upload_evalue_breaks(c))) return rc;
     *out = guard.release(); return KJ_OK;
 }
 
 extern "C" int kj_set_params(kj_ctx* c, const kj_params* p) {
     if (!c || !p) { kj_err() = "kj_set_params: null argument"; return KJ_ERR_ARG; }
     int rc = kj_check_params(*p); if (rc) return rc;
-    c->params = *p; c->ev1 = c->ev2 = 0; if (c->d_evtab) { cudaFree(c->d_evtab); c->d_evtab = nullptr; }
-    return KJ_OK;
+    CK(cudaSetDevice(c->device));
+    c->params = *p;
+    return upload_evalue_breaks(c);
 }
 
 extern "C" void kj_destroy(kj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     void* ptrs[] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_tax_parent, c->d_tax_depth, c->d_tax_id, c->d_lnfact, c->d_kmer, c->d_tables, c->d_ix,
-                    c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evtab, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
+                    c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evbreaks, c->d_ws, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
                     c->d_seq[0][0], c->d_seq[0][1], c->d_seq[1][0], c->d_seq[1][1], c->d_off[0][0], c->d_off[0][1], c->d_off[1][0], c->d_off[1][1],
                     c->d_ids[0], c->d_ids[1], c->d_nids[0], c->d_nids[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -232,10 +242,14 @@ extern "C" void kj_destroy(kj_ctx* c) {
 static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_off1, const uint8_t* d_seq2, const uint64_t* d_off2, uint64_t base1, uint64_t base2,
                   uint64_t n, uint32_t max1, uint32_t max2, uint64_t* d_tax, uint32_t* d_best, cudaStream_t st, bool time_it,
                   uint64_t* d_ids = nullptr, uint8_t* d_nids = nullptr) {
-    if (max1 > KJ_MAX_READ_LEN || max2 > KJ_MAX_READ_LEN) { kj_err() = "read longer than KJ_MAX_READ_LEN (381 bases) is not supported yet"; return KJ_ERR_UNSUPPORTED; }
+    if (c->params.input_is_protein) {
+        if (d_seq2) { kj_err() = "protein input only supports one input (kaiju.cpp:201)"; return KJ_ERR_ARG; }
+        if (max1 > KJ_MAX_PROTEIN_LEN) { kj_err() = "protein read longer than KJ_MAX_PROTEIN_LEN (5461 residues) is not supported"; return KJ_ERR_UNSUPPORTED; }
+    } else if (max1 > KJ_MAX_READ_LEN || max2 > KJ_MAX_READ_LEN) { kj_err() = "read longer than KJ_MAX_READ_LEN (16383 bases) is not supported"; return KJ_ERR_UNSUPPORTED; }
     KjRunParams rp; kj_fill_run_params(c->params, std::max(max1, max2), rp);
-    int rc = ensure_evalue_table(c, rp, max1, max2, st); if (rc) return rc;
-    size_t smem; int grid; rc = configure_launch(c, rp, smem, grid); if (rc) return rc;
+    rp.ev_breaks = c->d_evbreaks; rp.n_ev_breaks = c->n_evbreaks;
+    rp.variant_cap *= c->variant_boost;
+    size_t smem; int grid; int rc = configure_launch(c, rp, smem, grid); if (rc) return rc;
     rc = ensure_scratch(c, rp, grid); if (rc) return rc;
     c->grid = grid; c->smem_bytes = smem;
     CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
@@ -243,7 +257,8 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
 #define KJ_LAUNCH(M, T) kj_classify_kernel<M, T><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, \
             c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
-            c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), c->d_err)
+            c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), \
+            rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, c->d_err)
     if (rp.mode == 0) { if (c->H.wide) KJ_LAUNCH(0, uint64_t); else KJ_LAUNCH(0, uint32_t); }
     else { if (c->H.wide) KJ_LAUNCH(1, uint64_t); else KJ_LAUNCH(1, uint32_t); }
 #undef KJ_LAUNCH
@@ -255,7 +270,13 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
 
 static int check_err_flag(kj_ctx* c) {
     uint32_t e = 0; CK(cudaMemcpy(&e, c->d_err, sizeof e, cudaMemcpyDeviceToHost));
-    if (e) { CK(cudaMemset(c->d_err, 0, sizeof e)); char b[96]; snprintf(b, sizeof b, "per-read work queue overflow on the device (flags 0x%x)", e); kj_err() = b; return KJ_ERR_OVERFLOW; }
+    if (e) {
+        CK(cudaMemset(c->d_err, 0, sizeof e));
+        // flag 4 = the Greedy variant ring of some read was full: the next launch gets a ring 4x as large (the reference's heap is unbounded)
+        if ((e & 4u) && c->variant_boost < 256u) c->variant_boost *= 4u;
+        char b[160]; snprintf(b, sizeof b, "per-read work queue overflow on the device (flags 0x%x)%s", e, (e & 4u) ? "; the variant ring was enlarged, call again" : ""); kj_err() = b;
+        return KJ_ERR_OVERFLOW;
+    }
     return KJ_OK;
 }
 
@@ -318,10 +339,16 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
         c->d_ids_cap = c->d_reads_cap;
     }
     // software pipeline over chunks: H2D + kernel + D2H of chunk k on stream k&1 overlap with chunk k+1
-    double kernel_ms = 0.0;
-    for (uint64_t start = 0, k = 0; start < n; start += KJ_CHUNK_READS, k++) {
+    for (uint64_t start = 0, k = 0, cnt = 0; start < n; start += cnt, k++) {
         const int s = (int)(k & 1); cudaStream_t st = c->stream[s];
-        const uint64_t cnt = std::min<uint64_t>(KJ_CHUNK_READS, n - start);
+        cnt = std::min<uint64_t>(KJ_CHUNK_READS, n - start);
+        // long reads: bound the bases per chunk as well (at least one read)
+        {
+            const uint64_t* e1p = std::upper_bound(off1 + start + 1, off1 + start + cnt + 1, off1[start] + KJ_CHUNK_BYTES);
+            uint64_t lim = std::max<uint64_t>(1, (uint64_t)(e1p - (off1 + start + 1)));
+            if (paired) { const uint64_t* e2p = std::upper_bound(off2 + start + 1, off2 + start + cnt + 1, off2[start] + KJ_CHUNK_BYTES); lim = std::min(lim, std::max<uint64_t>(1, (uint64_t)(e2p - (off2 + start + 1)))); }
+            cnt = std::min(cnt, lim);
+        }
         CK(cudaStreamSynchronize(st));                      // slot s free again (its previous D2H has landed)
         const uint64_t b1 = off1[start], e1 = off1[start + cnt], b2 = paired ? off2[start] : 0, e2 = paired ? off2[start + cnt] : 0;
         rc = ensure_staging(c, s, (size_t)(e1 - b1), (size_t)(e2 - b2), c->d_reads_cap); if (rc) return rc;
@@ -342,18 +369,27 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
         }
     }
     CK(cudaStreamSynchronize(c->stream[0])); CK(cudaStreamSynchronize(c->stream[1]));
-    (void)kernel_ms;
     return check_err_flag(c);
+}
+
+// A full Greedy variant ring (flag 4) enlarges the ring for the next launch: repeat the call until it fits (bounded).
+static int classify_host_retry(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
+                               uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out) {
+    for (;;) {
+        const uint32_t boost = c ? c->variant_boost : 0;
+        int rc = classify_host(c, seq1, off1, seq2, off2, n, taxon_out, best_out, ids_out, nids_out);
+        if (rc != KJ_ERR_OVERFLOW || !c || c->variant_boost == boost) return rc;
+    }
 }
 
 extern "C" int kj_classify(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
                            uint64_t* taxon_out, uint32_t* best_out) {
-    return classify_host(c, seq1, off1, seq2, off2, n, taxon_out, best_out, nullptr, nullptr);
+    return classify_host_retry(c, seq1, off1, seq2, off2, n, taxon_out, best_out, nullptr, nullptr);
 }
 extern "C" int kj_classify_verbose(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
                                    uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out) {
     if (!ids_out || !nids_out) { kj_err() = "kj_classify_verbose: null argument"; return KJ_ERR_ARG; }
-    return classify_host(c, seq1, off1, seq2, off2, n, taxon_out, best_out, ids_out, nids_out);
+    return classify_host_retry(c, seq1, off1, seq2, off2, n, taxon_out, best_out, ids_out, nids_out);
 }
 
 extern "C" uint64_t kj_kernel_launches(const kj_ctx* c) { return c ? c->launches : 0; }

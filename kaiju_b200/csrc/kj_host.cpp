@@ -118,6 +118,7 @@ int build_tables(const std::string& alphabet, KjTables& tb) {
     uint8_t trans[256]; memset(trans, (uint8_t)(alen - 1), sizeof trans);
     for (int a = 0; a < alen; a++) trans[(uint8_t)alphabet[(size_t)a]] = (uint8_t)a;
     for (int c = 0; c < 64; c++) tb.codon_aa[c] = kCode[c] == '*' ? 0 : trans[(uint8_t)kCode[c]];
+    for (const char* v = "ACDEFGHIKLMNPQRSTVWY"; *v; v++) tb.aa_index[*v - 'A'] = trans[(uint8_t)*v];     // the valid set of a protein read (ConsumerThread.cpp:664)
     int ai_of[256]; for (int i = 0; i < 256; i++) ai_of[i] = -1;
     for (int i = 0; i < 20; i++) ai_of[(uint8_t)kAaOrder[i]] = i;
     for (int a = 0; a < alen; a++) for (int b = 0; b < alen; b++) {
@@ -159,7 +160,6 @@ int kj_check_params(const kj_params& p) {
     if (p.mode == 0 && p.use_evalue) { kj_err() = "E-value calculation is only possible in Greedy mode"; return KJ_ERR_ARG; }   // kaiju.cpp:202
     if (p.mode == 1 && p.mismatches > KJ_MAX_MM) { kj_err() = "more than 8 mismatches (-e) are not supported"; return KJ_ERR_UNSUPPORTED; }
     if (p.mode == 1 && (p.min_score == 0 || p.seed_length == 0)) { kj_err() = "min_score and seed_length must be > 0"; return KJ_ERR_ARG; }
-    if (p.input_is_protein) { kj_err() = "protein input (-p) is not supported yet"; return KJ_ERR_UNSUPPORTED; }
     if (p.use_evalue && !(p.min_evalue > 0.0)) { kj_err() = "E-value threshold must be greater than 0"; return KJ_ERR_ARG; }
     return KJ_OK;
 }
@@ -284,8 +284,8 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
     }
     { const char* ek = getenv("KJ_KMER_K"); kj_build_kmer_table(H, ek ? atoi(ek) : 5); }
     // ---- ln(n!) exactly as the reference's literals (blast_seg.c:53-1306 are "%.6f" prints of lgamma)
-    H.lnfact.resize(256);
-    for (int i = 0; i < 256; i++) { char b[64]; snprintf(b, sizeof b, "%.6f", lgamma((double)i + 1.0)); H.lnfact[(size_t)i] = strtod(b, nullptr); }
+    H.lnfact.resize(10001);                                             // the reference's table lnfact[0..10000] (blast_seg.c:53-1306)
+    for (int i = 0; i < 10001; i++) { char b[64]; snprintf(b, sizeof b, "%.6f", lgamma((double)i + 1.0)); H.lnfact[(size_t)i] = strtod(b, nullptr); }
     H.lnfact[0] = H.lnfact[1] = 0.0;
     return KJ_OK;
 }
@@ -324,27 +324,37 @@ void kj_build_kmer_table(KjHostIndex& H, int k) {
     H.kmer_k = k;
 }
 
-void kj_build_evalue_table(const kj_params& p, double db_length, uint32_t max1, uint32_t max2, std::vector<uint16_t>& tab) {
-    tab.assign((size_t)(max1 + 1) * (max2 + 1), 0);
+// E-value gate (ConsumerThread.cpp:500-513): Evalue = db_length * query_len * 2^-bitscore(best) must not exceed min_Evalue.
+// For a fixed score k the left-hand side is a monotone function of query_len in IEEE arithmetic (two multiplications by
+// positive constants), so "score k passes" <=> query_len <= breaks[k], where breaks[k] is found by bisection over the
+// bit patterns of the positive doubles with the reference's own expression.  The device computes query_len with the same
+// IEEE divisions/additions as the reference and counts the breaks below it: an exact integer threshold, any read length.
+int kj_build_evalue_breaks(const kj_params& p, double db_length, std::vector<double>& breaks) {
+    breaks.clear();
+    if (!(p.mode == 1 && p.use_evalue)) return KJ_OK;
     auto passes = [&](double query_len, unsigned best) {
         double bitscore = (0.3176 * best - (-2.009915479)) / 0.6931471805;                  // LAMBDA, LN_K, LN_2 (ConsumerThread.hpp:41-44)
         double Evalue = db_length * query_len * pow(2, -1 * bitscore);
         return !(Evalue > p.min_evalue);
     };
-    for (uint32_t a = 0; a <= max1; a++) for (uint32_t b = 0; b <= max2; b++) {
-        double q = static_cast<double>(a) / 3.0; q += static_cast<double>(b) / 3.0;         // ConsumerThread.cpp:698, 704
-        unsigned lo = 0, hi = 65535;
-        if (!passes(q, hi)) { tab[(size_t)a * (max2 + 1) + b] = 65535; continue; }
-        while (lo < hi) { unsigned mid = (lo + hi) / 2; if (passes(q, mid)) hi = mid; else lo = mid + 1; }
-        while (lo > 0 && passes(q, lo - 1)) lo--;
-        tab[(size_t)a * (max2 + 1) + b] = (uint16_t)lo;
+    double prev = 0.0;
+    for (unsigned k = 0; k < 65536; k++) {
+        uint64_t lo = 0, hi; const double top = 1e300; memcpy(&hi, &top, 8);                // passes(0) holds, passes(1e300) cannot
+        if (passes(top, k)) { breaks.push_back(top); break; }
+        while (hi - lo > 1) { uint64_t mid = lo + (hi - lo) / 2; double q; memcpy(&q, &mid, 8); if (passes(q, k)) lo = mid; else hi = mid; }
+        double q; memcpy(&q, &lo, 8);
+        if (q < prev) { kj_err() = "E-value threshold is not monotone in the score"; return KJ_ERR_UNSUPPORTED; }
+        breaks.push_back(q); prev = q;
+        if (q > 1e12) break;                                                                 // longer queries than any supported read
     }
+    return KJ_OK;
 }
 
 void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp) {
     memset(&rp, 0, sizeof rp);
     rp.mode = p.mode; rp.m = p.min_fragment_length; rp.e = p.mismatches; rp.min_score = p.min_score; rp.seed_length = p.seed_length;
     rp.use_evalue = p.use_evalue; rp.seg = p.seg; rp.protein = p.input_is_protein;
+    if (p.input_is_protein) max_len *= 3;  // a protein read is laid out like one reading frame: residue e at array index 3e
     if (max_len < 24) max_len = 24;
     rp.max_len = (max_len + 7) / 8 * 8;
     rp.max_frag = rp.max_len / 3 + 1;
@@ -352,4 +362,6 @@ void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp) {
     rp.item_cap = 2 * 12 * per_class + 8; rp.item_cap = (rp.item_cap + 1) & ~1u;
     rp.kept_cap_smem = 24;                 // >= max_matches_SI (20): greedy keeps its best list here
     rp.scratch_entries = 4 * rp.max_len + 64;
+    rp.variant_cap = rp.max_len <= 512 ? 256u : 4096u;
+    if (const char* v = getenv("KJ_VARIANT_CAP")) { long x = atol(v); if (x >= 32 && x <= (1 << 20)) rp.variant_cap = (uint32_t)x; }   // test hook: provoke the overflow/retry path
 }

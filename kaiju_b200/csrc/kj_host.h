@@ -36,6 +36,6 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
 void kj_build_kmer_table(KjHostIndex& H, int k);
 int kj_check_params(const kj_params& p);
 // E-value gate (ConsumerThread.cpp:500-513) as the minimal passing integer score per (len1,len2)
-void kj_build_evalue_table(const kj_params& p, double db_length, uint32_t max1, uint32_t max2, std::vector<uint16_t>& tab);
+int kj_build_evalue_breaks(const kj_params& p, double db_length, std::vector<double>& breaks);
 // per-warp scratch geometry for a batch whose longest mate has max_len bases
 void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp);

@@ -44,6 +44,7 @@ struct KjTables {
     uint8_t subst[KJ_MAX_ALEN][20];  // substitution try-order per residue, alphabet indices (ConsumerThread.cpp:10-30)
     int32_t seg_logfix[KJ_SEG_WINDOW + 1];  // round(2^24 log2(12/c)) : entropy of a 12-window in fixed point
     int32_t seg_locut_fix, seg_hicut_fix;   // 12*2.2*2^24, 12*2.5*2^24 (margins checked on host against FP64)
+    uint8_t aa_index[32];            // protein input: upper-case letter - 'A' -> alphabet index, 0 = splits the read (ConsumerThread.cpp:664)
 };
 
 struct KjDevIndex {
@@ -65,12 +66,15 @@ struct KjRunParams {
     int mode;                       // 0 MEM, 1 GREEDY
     uint32_t m, e, min_score, seed_length;
     int use_evalue, seg, protein;
-    // E-value gate as an integer threshold table: min passing best score for (len1,len2)
-    const uint16_t* evalue_min_score; uint32_t ev_stride;   // [len1*(ev_stride)+len2]
+    // E-value gate as an integer threshold: ev_breaks[k] = the largest query length (double) for which score k passes,
+    // so the minimal passing score of a read is the number of breaks below its query length (kj_build_evalue_breaks)
+    const double* ev_breaks; uint32_t n_ev_breaks;
     // per-warp scratch geometry
     uint32_t max_len;               // longest read (bases) in the batch, rounded up
     uint32_t max_frag;              // longest fragment (residues)
     uint32_t item_cap;              // fragment-queue capacity per warp
     uint32_t kept_cap_smem;         // winners kept in shared memory before spilling
     uint32_t scratch_entries;       // global spill entries per warp
+    uint32_t variant_cap;           // Greedy: entries of the per-warp substituted-variant ring
+    uint32_t ws_global;             // 1: the per-warp work space lives in global memory (reads too long for shared memory)
 };

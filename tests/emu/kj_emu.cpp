@@ -114,7 +114,7 @@ uint32_t rendezvous_ballot(Sched* s, int lane, bool p) {
 #include "../../kaiju_b200/csrc/kj_host.h"
 
 struct EmuCtx {
-    KjHostIndex H; KjDevIndex D; kj_params P; std::vector<uint16_t> evtab; uint32_t ev1 = 0, ev2 = 0;
+    KjHostIndex H; KjDevIndex D; kj_params P; std::vector<double> evbreaks;
 };
 struct ItemArg { uint32_t nids; uint32_t ids[24]; EmuCtx* c; KjRunParams* rp; uint8_t* smem; KjKept* spill; void* gscratch; uint32_t* err; const uint8_t* s1; int n1; const uint8_t* s2; int n2; bool paired; uint32_t tax[32]; uint32_t best[32]; };
 
@@ -139,6 +139,7 @@ void* kjemu_create(const char* fmi_path, const char* nodes_path, const kj_params
     EmuCtx* c = new EmuCtx(); c->P = *p;
     if (kj_check_params(*p) != KJ_OK || kj_build_host_index(iv, tv, c->H) != KJ_OK) { fprintf(stderr, "kjemu: %s\n", kj_last_error()); delete c; return nullptr; }
     kj_fmi_free(f); kj_nodes_free(t);
+    if (kj_build_evalue_breaks(*p, c->H.db_length, c->evbreaks) != KJ_OK) { fprintf(stderr, "kjemu: %s\n", kj_last_error()); delete c; return nullptr; }
     KjDevIndex& D = c->D; KjHostIndex& H = c->H; memset(&D, 0, sizeof D);
     D.rank = H.rank.data(); D.nb = H.nb; D.letters = H.letters.data(); D.bwtlen = H.bwtlen; D.alen = H.alen;
     for (int a = 0; a <= H.alen; a++) D.C[a] = H.C[a];
@@ -156,9 +157,10 @@ int kjemu_classify(void* h, const char* seq1, const uint64_t* off1, const char* 
     EmuCtx* c = (EmuCtx*)h; bool paired = seq2 != nullptr;
     uint32_t max1 = 0, max2 = 0;
     for (uint64_t i = 0; i < n; i++) { max1 = std::max<uint32_t>(max1, (uint32_t)(off1[i + 1] - off1[i])); if (paired) max2 = std::max<uint32_t>(max2, (uint32_t)(off2[i + 1] - off2[i])); }
-    if (max1 > KJ_MAX_READ_LEN || max2 > KJ_MAX_READ_LEN) return KJ_ERR_UNSUPPORTED;
+    if (c->P.input_is_protein ? (paired || max1 > KJ_MAX_PROTEIN_LEN) : (max1 > KJ_MAX_READ_LEN || max2 > KJ_MAX_READ_LEN)) return KJ_ERR_UNSUPPORTED;
     KjRunParams rp; kj_fill_run_params(c->P, std::max(max1, max2), rp);
-    if (c->P.mode == 1 && c->P.use_evalue) { kj_build_evalue_table(c->P, c->H.db_length, max1, max2, c->evtab); rp.evalue_min_score = c->evtab.data(); rp.ev_stride = max2 + 1; }
+    rp.ev_breaks = c->evbreaks.data(); rp.n_ev_breaks = (uint32_t)c->evbreaks.size();
+    rp.ws_global = 1;          // host memory either way; the device-only pointer switch is covered by the GPU tests
     KjSmemLayout L = kj_smem_layout(rp);
     std::atomic<uint64_t> next(0); std::atomic<uint32_t> errs(0);
     if (nthreads < 1) nthreads = 1;

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 
 
 def kb_params(kb, kw):
-    return kb.make_params(kw.get("mode", "mem"), m=kw.get("m", 11), e=kw.get("e", 3), s=kw.get("s", 65), E=kw.get("E", 0.01), seg=kw.get("seg", True))
+    return kb.make_params(kw.get("mode", "mem"), m=kw.get("m", 11), e=kw.get("e", 3), s=kw.get("s", 65), seed=kw.get("seed", 7), E=kw.get("E", 0.01), seg=kw.get("seg", True),
+                          protein=kw.get("protein", False))
 
 
 @pytest.fixture(scope="module")
@@ -71,16 +72,25 @@ def test_edge_cases(kb, gclf, golden):
     assert len(t) == 0
     # ragged batch: empty reads, reads shorter than 3m, one long read at the supported maximum
     rng = np.random.default_rng(3)
-    reads = [b"", b"ACGT", b"ACGTACGTACGTACGTACGTACGTACGTACGT", bytes(rng.choice(list(b"ACGT"), 381).astype(np.uint8)), b"N" * 200, b"acgtn" * 30]
+    reads = [b"", b"ACGT", b"ACGTACGTACGTACGTACGTACGTACGTACGT", bytes(rng.choice(list(b"ACGT"), 381).astype(np.uint8)), b"N" * 200, b"acgtn" * 30,
+             bytes(rng.choice(list(b"ACGT"), 16383).astype(np.uint8)), b"GCA" * 5461]
     s = np.frombuffer(b"".join(reads), dtype=np.uint8); o = np.zeros(len(reads) + 1, np.uint64); o[1:] = np.cumsum([len(r) for r in reads])
     t, b = gclf.classify(s, o)
     orc = Oracle(golden.fmi, golden.nodes)
     ot, ob = orc.classify_batch(make_params("mem"), s, o)
     assert np.array_equal(t, ot) and np.array_equal(b, ob)
     # a read beyond KJ_MAX_READ_LEN is refused with an error code, not misclassified
-    s2 = np.frombuffer(b"A" * 500, dtype=np.uint8); o2 = np.array([0, 500], np.uint64)
+    s2 = np.frombuffer(b"A" * 16384, dtype=np.uint8); o2 = np.array([0, 16384], np.uint64)
     with pytest.raises(kb.KaijuError):
         gclf.classify(s2, o2)
+    # protein input takes one file only (kaiju.cpp:201) and at most KJ_MAX_PROTEIN_LEN residues
+    gclf.set_params(kb.make_params("mem", protein=True))
+    pr = np.frombuffer(b"MKV" * 40, dtype=np.uint8); po = np.array([0, 120], np.uint64)
+    with pytest.raises(kb.KaijuError):
+        gclf.classify(pr, po, pr, po)
+    with pytest.raises(kb.KaijuError):
+        gclf.classify(np.frombuffer(b"A" * 5462, dtype=np.uint8), np.array([0, 5462], np.uint64))
+    gclf.set_params(kb.make_params("mem"))
 
 
 def test_properties_at_scale(kb, fresh):
@@ -175,3 +185,87 @@ def test_verbose_id_sets_match_reference_column5(kb, gclf, golden, cfg):
     for i, nm in enumerate(names):
         assert ids[i] == (eids[i] if etax[i] else ()), (nm, ids[i], eids[i])
     assert max(len(x) for x in ids) == 21            # the capped read is in the fixture
+
+
+LONG_CONFIGS = [dict(mode="mem"), dict(mode="mem", m=7, seg=False), dict(mode="greedy"), dict(mode="greedy", e=5, s=40, E=1e-3), dict(mode="greedy", e=1, s=100, seg=False, E=1e-30)]
+
+
+@pytest.mark.parametrize("kw", LONG_CONFIGS)
+def test_long_reads_match_oracle(kb, fresh, kw):
+    """Reads of 0.3-16 kb (work space in global memory, >127-residue low-complexity runs, thousands of queued fragments) and the
+    lengths around the shared-memory/global-memory switch, single-end and paired."""
+    db, fmi, nodes = fresh
+    orc = Oracle(fmi, nodes)
+    clf = kb.Classifier(fmi, nodes, device=0, params=kb_params(kb, kw))
+    for seed, n, lo, hi in ((41, 1500, 300, 16383), (42, 3000, 200, 700), (43, 3000, 380, 1200)):
+        s, o = db.long_reads(seed, 0, n, lo, hi)
+        otax, obest = orc.classify_batch(make_params(**kw), s, o)
+        tax, best = clf.classify(s, o)
+        bad = np.nonzero((tax != otax) | (best != obest))[0]
+        assert len(bad) == 0, (kw, seed, [(int(i), int(tax[i]), int(otax[i]), int(best[i]), int(obest[i])) for i in bad[:5]])
+        assert (tax != 0).mean() > 0.5
+    # paired: a long mate 1 with a short mate 2 (mixed lengths inside one batch)
+    s1, o1 = db.long_reads(44, 0, 1000, 150, 2500); s2, o2, _, _ = db.reads(45, 0, 1000, 150, False)
+    otax, obest = orc.classify_batch(make_params(**kw), s1, o1, s2, o2)
+    tax, best = clf.classify(s1, o1, s2, o2)
+    assert np.array_equal(tax, otax) and np.array_equal(best, obest)
+    clf.close()
+
+
+@pytest.mark.parametrize("kw", [dict(mode="mem"), dict(mode="mem", m=6, seg=False), dict(mode="greedy"), dict(mode="greedy", e=4, s=40), dict(mode="greedy", e=8, s=30, m=9, seed=5, E=1e-9)])
+def test_protein_input_matches_oracle(kb, fresh, kw):
+    """-p: protein reads of 5-5461 residues, split at non-residue letters, lower case, long low-complexity runs."""
+    db, fmi, nodes = fresh
+    orc = Oracle(fmi, nodes)
+    clf = kb.Classifier(fmi, nodes, device=0, params=kb_params(kb, dict(kw, protein=True)))
+    for seed, n, lo, hi in ((51, 6000, 5, 400), (52, 2000, 100, 5461)):
+        s, o = db.protein_reads(seed, 0, n, lo, hi)
+        otax, obest = orc.classify_batch(make_params(protein=True, **kw), s, o)
+        tax, best = clf.classify(s, o)
+        bad = np.nonzero((tax != otax) | (best != obest))[0]
+        assert len(bad) == 0, (kw, seed, [(int(i), int(tax[i]), int(otax[i]), int(best[i]), int(obest[i])) for i in bad[:5]])
+        assert (tax != 0).mean() > 0.5
+    clf.close()
+
+
+def test_variant_ring_overflow_is_retried(kb, golden, monkeypatch):
+    """Greedy -e 8 with a low score threshold on long reads that match nothing explores thousands of substituted variants per read;
+    a full per-read ring is reported by the kernel, enlarged by the library and the call repeated -- the result equals the oracle's."""
+    other = SynthDB(3000, 777)                                   # reads from proteins that are not in the golden index
+    s, o = other.long_reads(61, 0, 120, 3000, 16383)
+    kw = dict(mode="greedy", e=8, s=30, m=9, seed=5, E=1e-9)
+    monkeypatch.setenv("KJ_VARIANT_CAP", "128")                  # test hook: start from a ring that is too small (the emulated test shows it overflows)
+    clf = kb.Classifier(golden.fmi, golden.nodes, device=0, params=kb_params(kb, kw))
+    tax, best = clf.classify(s, o)                               # overflow -> ring x4 -> repeated inside kj_classify
+    otax, obest = Oracle(golden.fmi, golden.nodes).classify_batch(make_params(**kw), s, o)
+    assert np.array_equal(tax, otax) and np.array_equal(best, obest)
+    # the device-buffer entry point reports the overflow through kj_check_errors and succeeds when called again
+    import torch
+    clf2 = kb.Classifier(golden.fmi, golden.nodes, device=0, params=kb_params(kb, kw))
+    ds = torch.from_numpy(s).cuda(); do = torch.from_numpy(o.view(np.int64)).cuda(); dt = torch.zeros(len(o) - 1, dtype=torch.int64, device="cuda")
+    clf2.classify_device(ds.data_ptr(), do.data_ptr(), None, None, len(o) - 1, dt.data_ptr()); torch.cuda.synchronize()
+    with pytest.raises(kb.KaijuError):
+        clf2.check_errors()
+    clf2.classify_device(ds.data_ptr(), do.data_ptr(), None, None, len(o) - 1, dt.data_ptr()); torch.cuda.synchronize(); clf2.check_errors()
+    assert np.array_equal(dt.cpu().numpy().view(np.uint64), otax)
+    clf.close(); clf2.close()
+
+
+def test_cli_protein_and_verbose_columns(kb, golden, tmp_path):
+    """kaiju-b200 -p -v: columns 1-5 equal the oracle's (name, taxon, best, ascending id set)."""
+    import subprocess
+    from conftest import ROOT
+    db = SynthDB(800, 3)
+    s, o = db.protein_reads(71, 0, 400, 5, 900)
+    fa = tmp_path / "p.fa"
+    with open(fa, "w") as f:
+        for i in range(len(o) - 1):
+            f.write(">q%d some description\n%s\n" % (i, s[int(o[i]):int(o[i + 1])].tobytes().decode()))
+    out = subprocess.run([os.path.join(ROOT, "kaiju_b200", "kaiju-b200"), "-t", golden.nodes, "-f", golden.fmi, "-i", str(fa), "-p", "-v", "-a", "greedy", "-e", "2"],
+                         capture_output=True, text=True, check=True).stdout.splitlines()
+    orc = Oracle(golden.fmi, golden.nodes); P = make_params("greedy", e=2, protein=True)
+    assert len(out) == len(o) - 1
+    for i, line in enumerate(out):
+        t, b, ids = orc.classify_one(P, s[int(o[i]):int(o[i + 1])].tobytes())
+        exp = "C\tq%d\t%d\t%d\t%s" % (i, t, b, "".join("%d," % x for x in sorted(ids))) if t else "U\tq%d\t0" % i
+        assert line == exp, (i, line, exp)

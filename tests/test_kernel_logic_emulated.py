@@ -57,3 +57,37 @@ def test_emulated_kernel_matches_oracle_on_random_parameters(emu, golden):
         tax, best = emu_classify(emu, golden.fmi, golden.nodes, P, s1, o1, s2, o2)
         bad = np.nonzero((tax != otax) | (best != obest))[0]
         assert len(bad) == 0, (kw, [(names[i], int(tax[i]), int(otax[i]), int(best[i]), int(obest[i])) for i in bad[:5]])
+
+
+def emu_classify_rc(E, fmi, nodes, P, s1, o1):
+    kp = KjParams(**P); h = E.kjemu_create(fmi.encode(), nodes.encode(), C.byref(kp)); assert h
+    n = len(o1) - 1; tax = np.zeros(n, dtype=np.uint64); best = np.zeros(n, dtype=np.uint32)
+    rc = E.kjemu_classify(h, s1.ctypes.data, o1.ctypes.data, None, None, n, tax.ctypes.data, best.ctypes.data, 4)
+    E.kjemu_destroy(h)
+    return rc, tax, best
+
+
+@pytest.mark.parametrize("kw", [dict(mode="mem"), dict(mode="greedy"), dict(mode="mem", m=7, seg=False), dict(mode="greedy", e=5, s=40, E=1e-3)])
+def test_emulated_kernel_long_reads_and_protein_input(emu, golden, kw):
+    """Reads up to KJ_MAX_READ_LEN (16383 bases) and protein input (-p, up to 5461 residues): kernel logic (emulated) == oracle."""
+    db = SynthDB(800, 3); orc = Oracle(golden.fmi, golden.nodes)
+    for prot, (s, o) in ((False, db.long_reads(41, 0, 250, 300, 16383)), (True, db.protein_reads(42, 0, 1200, 5, 5461))):
+        P = make_params(protein=prot, **kw)
+        otax, obest = orc.classify_batch(P, s, o)
+        rc, tax, best = emu_classify_rc(emu, golden.fmi, golden.nodes, P, s, o)
+        bad = np.nonzero((tax != otax) | (best != obest))[0]
+        assert rc == 0 and len(bad) == 0, (kw, prot, rc, [(int(i), int(tax[i]), int(otax[i]), int(best[i]), int(obest[i])) for i in bad[:5]])
+        assert (otax != 0).mean() > 0.5
+
+
+def test_emulated_kernel_reports_variant_ring_overflow(emu, golden, monkeypatch):
+    """A full Greedy variant ring is flagged (never silently truncated); the library reacts by enlarging the ring (GPU test)."""
+    s, o = SynthDB(3000, 777).long_reads(61, 0, 120, 3000, 16383)
+    P = make_params(mode="greedy", e=8, s=30, m=9, seed=5, E=1e-9)
+    monkeypatch.setenv("KJ_VARIANT_CAP", "128")           # test hook: a ring of 128 entries is too small for these reads
+    rc, _, _ = emu_classify_rc(emu, golden.fmi, golden.nodes, P, s, o)
+    assert rc == -406                                     # KJ_ERR_OVERFLOW - 100 * flag 4
+    monkeypatch.setenv("KJ_VARIANT_CAP", "512")
+    rc, tax, best = emu_classify_rc(emu, golden.fmi, golden.nodes, P, s, o)
+    otax, obest = Oracle(golden.fmi, golden.nodes).classify_batch(P, s, o)
+    assert rc == 0 and np.array_equal(tax, otax) and np.array_equal(best, obest)
