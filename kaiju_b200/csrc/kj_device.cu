@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -33,7 +34,9 @@
 
 struct KjCtaShared { KjDevIndex ix; KjTables tb; };
 
-template <int MODE, class IdxT>
+// GWS = false: the per-warp work space is carved out of shared memory (the compiler keeps every access in the shared
+// address space); GWS = true (reads too long for that): the same carve-up in a global buffer, generic loads and stores.
+template <int MODE, class IdxT, bool GWS>
 __global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32, MODE == 0 ? KJ_MIN_BLOCKS : KJ_MIN_BLOCKS_GREEDY)
 kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ KjRunParams rp,
                    const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
@@ -58,8 +61,8 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
     cx.L = kj_smem_layout(rp);
     const uint64_t gwarp = (uint64_t)blockIdx.x * KJ_WARPS_PER_CTA + (uint64_t)warp_in_cta;
     // per-warp work space: shared memory, or (reads too long for it) a slice of a global buffer that stays L1/L2-resident
-    cx.smem = rp.ws_global ? gws + gwarp * cx.L.total
-                           : smem_raw + kj_align((uint32_t)sizeof(KjCtaShared), 16) + (uint32_t)warp_in_cta * cx.L.total;
+    if (GWS) cx.smem = gws + gwarp * cx.L.total;
+    else cx.smem = smem_raw + kj_align((uint32_t)sizeof(KjCtaShared), 16) + (uint32_t)warp_in_cta * cx.L.total;
     cx.spill = spill + gwarp * rp.scratch_entries;
     cx.gscratch = gscratch + gwarp * gscratch_bytes;
     cx.err = err;
@@ -137,23 +140,29 @@ template <class T> static int upload(const std::vector<T>& v, void** d, uint64_t
     total += bytes; return KJ_OK;
 }
 
-// Shared-memory work space while two CTAs still fit on an SM; beyond that (reads of several hundred bases and more) the
-// same carve-up is addressed in a global buffer instead, which keeps the grid at full occupancy for any read length.
-#define KJ_SMEM_WS_LIMIT (113u * 1024u)
+// Shared-memory work space while three CTAs still fit on an SM; beyond that (mates longer than ~280 bases) the same
+// carve-up is addressed in a global buffer instead, which keeps the grid at full occupancy for any read length.
+// Measured (MEM, kernel-only, M pairs/s, shared vs global): PE150 57.8 vs 45.8, PE250 29.4 (3 CTAs/SM) vs 28.2, PE350 14.3 (2 CTAs/SM) vs 18.3.
+#define KJ_SMEM_WS_LIMIT (75u * 1024u)
 static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid) {
     KjSmemLayout L = kj_smem_layout(rp);
     const size_t head = kj_align((uint32_t)sizeof(KjCtaShared), 16);
     smem = head + (size_t)KJ_WARPS_PER_CTA * L.total;
-    rp.ws_global = smem > KJ_SMEM_WS_LIMIT ? 1u : 0u;
+    size_t limit = KJ_SMEM_WS_LIMIT;
+    if (const char* v = getenv("KJ_WS_LIMIT_KB")) { long x = atol(v); if (x >= 0 && x <= 227) limit = (size_t)x * 1024u; }    // tuning hook (A/B of the switch point)
+    rp.ws_global = smem > limit ? 1u : 0u;
     if (rp.ws_global) smem = head;
-    if (smem == c->smem_bytes && c->grid > 0 && c->cfg_mode == rp.mode) { grid = c->grid; return KJ_OK; }
+    const int cfg = rp.mode * 2 + (int)rp.ws_global;
+    if (smem == c->smem_bytes && c->grid > 0 && c->cfg_mode == cfg) { grid = c->grid; return KJ_OK; }
     int per_sm = 0;
-#define KJ_CFG(M, T) { CK(cudaFuncSetAttribute(kj_classify_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<M, T>, KJ_WARPS_PER_CTA * 32, smem)); }
-    if (rp.mode == 0) { if (c->H.wide) KJ_CFG(0, uint64_t) else KJ_CFG(0, uint32_t) }
-    else { if (c->H.wide) KJ_CFG(1, uint64_t) else KJ_CFG(1, uint32_t) }
+#define KJ_CFG(M, T, G) { CK(cudaFuncSetAttribute(kj_classify_kernel<M, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<M, T, G>, KJ_WARPS_PER_CTA * 32, smem)); }
+#define KJ_CFG2(M, T) { if (rp.ws_global) KJ_CFG(M, T, true) else KJ_CFG(M, T, false) }
+    if (rp.mode == 0) { if (c->H.wide) KJ_CFG2(0, uint64_t) else KJ_CFG2(0, uint32_t) }
+    else { if (c->H.wide) KJ_CFG2(1, uint64_t) else KJ_CFG2(1, uint32_t) }
+#undef KJ_CFG2
 #undef KJ_CFG
-    c->cfg_mode = rp.mode;
+    c->cfg_mode = cfg;
     if (per_sm < 1) { kj_err() = "kernel does not fit on an SM"; return KJ_ERR_UNSUPPORTED; }
     grid = c->sm_count * per_sm;             // persistent grid: a whole number of CTAs per SM
     return KJ_OK;
@@ -255,13 +264,15 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
     if (time_it) CK(cudaEventRecord(c->ev_a, st));
     const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
-#define KJ_LAUNCH(M, T) kj_classify_kernel<M, T><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, \
+#define KJ_LAUNCH(M, T) if (rp.ws_global) KJ_LAUNCH3(M, T, true); else KJ_LAUNCH3(M, T, false)
+#define KJ_LAUNCH3(M, T, G) kj_classify_kernel<M, T, G><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, \
             c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
             c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), \
             rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, c->d_err)
     if (rp.mode == 0) { if (c->H.wide) KJ_LAUNCH(0, uint64_t); else KJ_LAUNCH(0, uint32_t); }
     else { if (c->H.wide) KJ_LAUNCH(1, uint64_t); else KJ_LAUNCH(1, uint32_t); }
 #undef KJ_LAUNCH
+#undef KJ_LAUNCH3
     CK(cudaGetLastError());
     if (time_it) CK(cudaEventRecord(c->ev_b, st));
     c->launches++;

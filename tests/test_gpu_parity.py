@@ -160,17 +160,17 @@ def test_cli_matches_reference_output_format(kb, golden, tmp_path):
         out = str(tmp_path / (cfg + ".tsv"))
         # gz input for mate 1 (zlib path), plain for mate 2; -z is accepted and ignored
         subprocess.check_call([cli, "-t", golden.nodes, "-f", golden.fmi, "-i", os.path.join(gold, "pe150_1.fq.gz"), "-j", fq["pe150_2"], "-a", mode, "-z", "4", "-v", "-o", out] + extra)
-        etax, ebest, _ = golden.expected(cfg, "pe150"); names = golden.reads("pe150")[0]
+        etax, ebest, eids = golden.expected(cfg, "pe150"); names = golden.reads("pe150")[0]
         lines = open(out).read().splitlines()
         assert len(lines) == len(names)
-        for ln, nm, t, b in zip(lines, names, etax, ebest):
+        for ln, nm, t, b, ids in zip(lines, names, etax, ebest, eids):
             p = ln.split("\t")
-            if t:
-                assert p[:4] == ["C", nm, str(int(t)), str(int(b))], (ln, nm, t, b)
+            if t:      # columns 1-5 of the reference's -v output (ids: std::set order, each followed by a comma)
+                assert p == ["C", nm, str(int(t)), str(int(b)), "".join("%d," % x for x in sorted(ids))], (ln, nm, t, b, ids)
             else:
                 assert p == ["U", nm, "0"], ln
-    # error path: -p is refused, missing arguments print usage and exit non-zero
-    assert subprocess.call([cli, "-t", golden.nodes, "-f", golden.fmi, "-i", fq["pe150_1"], "-p"], stderr=subprocess.DEVNULL) != 0
+    # error paths: -p with a second input file (kaiju.cpp:201), missing arguments: usage + non-zero exit
+    assert subprocess.call([cli, "-t", golden.nodes, "-f", golden.fmi, "-i", fq["pe150_1"], "-j", fq["pe150_2"], "-p"], stderr=subprocess.DEVNULL) != 0
     assert subprocess.call([cli, "-f", golden.fmi], stderr=subprocess.DEVNULL) != 0
 
 
