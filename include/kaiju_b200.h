@@ -114,6 +114,15 @@ int kj_classify_device(kj_ctx *ctx, const char *d_seq1, const uint64_t *d_off1, 
                        uint64_t n_reads, uint32_t max_len1, uint32_t max_len2, uint64_t *d_taxon_out, uint32_t *d_best_out,
                        void *cuda_stream);
 
+/* Whole files (replaces the reader loop of kaiju.cpp:288-394 and the output formatting of
+ * ConsumerThread.cpp:724-739): FASTA or FASTQ, plain or gzip, in2 = second file of paired-end reads or NULL.  The text is
+ * parsed on the device (line splitting, name trimming at " /\t\r", strip() of non-letters), classified, and the output
+ * lines "C\t<name>\t<taxid>" / "U\t<name>\t0" (verbose: plus "\t<best>\t<id,id,...,>") are formatted on the device and
+ * written to out_path (NULL or "" = stdout) in INPUT order.  FASTQ must be 4-line records.  Errors mirror the
+ * reference's messages (file type detection, differing read names, file 1 longer than file 2) as KJ_ERR_IO. */
+int kj_classify_files(kj_ctx *ctx, const char *in1, const char *in2, const char *out_path, int verbose,
+                      uint64_t *n_reads_out, uint64_t *n_classified_out);
+
 /* Per-read work queues on the device are sized from worst-case bounds; should one overflow anyway, the affected launch is
  * flagged (never silently truncated).  kj_classify() checks this itself; after kj_classify_device() call kj_check_errors()
  * once the stream has finished: KJ_OK, or KJ_ERR_OVERFLOW (the results of that launch are invalid).  When the overflow was

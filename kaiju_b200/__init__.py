@@ -66,6 +66,7 @@ def lib():
         L.kj_kernel_launches.restype = C.c_uint64; L.kj_kernel_launches.argtypes = [C.c_void_p]
         L.kj_index_bytes.restype = C.c_uint64; L.kj_index_bytes.argtypes = [C.c_void_p]
         L.kj_last_kernel_ms.restype = C.c_double; L.kj_last_kernel_ms.argtypes = [C.c_void_p]
+        L.kj_classify_files.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.kj_check_errors.argtypes = [C.c_void_p]
         L.kj_launch_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.kj_version.restype = C.c_int
@@ -157,6 +158,13 @@ class Classifier:
     # ---- device buffers (raw device pointers, e.g. torch tensors' data_ptr()); asynchronous on `stream`
     def classify_device(self, d_seq1, d_off1, d_seq2, d_off2, n, d_tax, d_best=None, max_len1=0, max_len2=0, stream=None):
         _check(lib().kj_classify_device(self._ctx, d_seq1, d_off1, d_seq2, d_off2, n, max_len1, max_len2, d_tax, d_best, stream))
+
+    def classify_files(self, in1, in2=None, out_path=None, verbose=False):
+        """FASTA/FASTQ(.gz) files -> kaiju output file, parsed / classified / formatted on the device.  Returns (reads, classified)."""
+        n = C.c_uint64(); k = C.c_uint64()
+        _check(lib().kj_classify_files(self._ctx, in1.encode(), in2.encode() if in2 else None, out_path.encode() if out_path else None,
+                                       1 if verbose else 0, C.byref(n), C.byref(k)))
+        return int(n.value), int(k.value)
 
     def check_errors(self):
         _check(lib().kj_check_errors(self._ctx))

@@ -1,13 +1,12 @@
 // kj_cli.cpp -- `kaiju-b200`: the reference's command-line surface (src/kaiju.cpp:74-202, usage 430-451) on top of the C ABI.
 //   kaiju-b200 -t nodes.dmp -f db.fmi -i reads.fastq [-j reads2.fastq] [-a mem|greedy] [-m -s -e -E -l] [-x|-X] [-o out] [-z N] [-v]
 // Output: "C\t<name>\t<taxid>\n" / "U\t<name>\t0\n" (ConsumerThread.cpp:724-739), in INPUT order.
-// Host glue only: FASTA/FASTQ(.gz) parsing with the reference's name trimming (kaiju.cpp:318-335) and strip() (util.cpp:26-33),
-// batching, kj_classify().  -z is accepted and ignored (the GPU replaces the consumer threads); -p = protein input; with -v
+// Host glue only: option parsing; kj_classify_files() reads FASTA/FASTQ(.gz), parses it on the device with the reference's name
+// trimming (kaiju.cpp:318-335) and strip() (util.cpp:26-33), classifies and formats the output.  -z is accepted and ignored (the GPU replaces the consumer threads); -p = protein input; with -v
 // columns 4 (best length/score) and 5 (match taxon ids) are appended -- columns 6-7 of the reference's -v output
 // (accession names, fragment sequences) are not produced.
 #include <getopt.h>
 #include <unistd.h>
-#include <zlib.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,34 +25,6 @@ static void usage(const char* prog) {
                     "   -p            Input sequences are protein sequences\n   -v            Enable verbose output (adds the match length/score and the matching taxon ids)\n   -d INT        CUDA device ordinal (default 0)\n", prog);
     exit(EXIT_FAILURE);
 }
-
-struct Reader {
-    gzFile fp = nullptr; std::string path; bool first = true, fastq = false; std::string line, pending; bool has_pending = false; std::vector<char> buf;
-    explicit Reader(const std::string& p) : path(p), buf(1 << 16) { fp = gzopen(p.c_str(), "rb"); if (!fp) die("Could not open file " + p); gzbuffer(fp, 1 << 20); }
-    ~Reader() { if (fp) gzclose(fp); }
-    bool getline(std::string& out) {
-        if (has_pending) { out.swap(pending); has_pending = false; return true; }
-        out.clear();
-        for (;;) {
-            if (!gzgets(fp, buf.data(), (int)buf.size())) return !out.empty();
-            size_t l = strlen(buf.data()); out.append(buf.data(), l);
-            if (l && out.back() == '\n') { out.pop_back(); return true; }
-            if (l + 1 < buf.size()) return true;          // EOF without newline
-        }
-    }
-    void unget(std::string& l) { pending.swap(l); has_pending = true; }
-    // next record: name (trimmed at " /\t\r") + sequence stripped of non-letters; false at EOF
-    bool next(std::string& name, std::string& seq) {
-        do { if (!getline(line)) return false; } while (line.empty());
-        if (first) { if (line[0] == '@') fastq = true; else if (line[0] != '>') die("Auto-detection of file type for file " + path + " failed."); first = false; }
-        line.erase(0, 1); size_t n = line.find_first_of(" /\t\r"); if (n != std::string::npos) line.erase(n);
-        name = line; seq.clear();
-        if (fastq) { std::string s, skip; getline(s); getline(skip); getline(skip); append_stripped(seq, s); }
-        else { std::string s; while (getline(s)) { if (!s.empty() && s[0] == '>') { unget(s); break; } append_stripped(seq, s); } }
-        return true;
-    }
-    static void append_stripped(std::string& dst, const std::string& s) { for (char c : s) if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z')) dst.push_back(c); }
-};
 
 int main(int argc, char** argv) {
     kj_params P; P.mode = 1; P.min_fragment_length = 11; P.mismatches = 3; P.min_score = 65; P.seed_length = 7; P.use_evalue = 1; P.min_evalue = 0.01; P.seg = 1; P.input_is_protein = 0;
@@ -95,44 +66,10 @@ int main(int argc, char** argv) {
     if (kj_create(&ctx, device, &P, &iv, &tv) != KJ_OK) die(kj_last_error());
     kj_fmi_free(fmi); kj_nodes_free(nodes);
 
-    FILE* out = stdout;
-    if (!out_fn.empty()) { out = fopen(out_fn.c_str(), "w"); if (!out) die("Could not open file " + out_fn + " for writing"); }
-    setvbuf(out, nullptr, _IOFBF, 1 << 22);
-    Reader r1(in1); Reader* r2 = paired ? new Reader(in2) : nullptr;
-    const size_t BATCH = 1u << 20;
-    std::string seq1, seq2, name, name2, s; std::vector<uint64_t> off1, off2, taxon, ids; std::vector<uint32_t> best; std::vector<uint8_t> nids; std::vector<std::string> names;
-    auto flush = [&]() {
-        size_t n = names.size(); if (!n) return;
-        taxon.resize(n); best.resize(n);
-        int rc;
-        if (verbose) { ids.resize(n * KJ_MAX_MATCH_IDS); nids.resize(n);
-                       rc = kj_classify_verbose(ctx, seq1.data(), off1.data(), paired ? seq2.data() : nullptr, paired ? off2.data() : nullptr, n, taxon.data(), best.data(), ids.data(), nids.data()); }
-        else rc = kj_classify(ctx, seq1.data(), off1.data(), paired ? seq2.data() : nullptr, paired ? off2.data() : nullptr, n, taxon.data(), best.data());
-        if (rc != KJ_OK) die(kj_last_error());
-        for (size_t i = 0; i < n; i++) {
-            if (taxon[i]) {
-                fprintf(out, "C\t%s\t%llu", names[i].c_str(), (unsigned long long)taxon[i]);
-                if (verbose) { fprintf(out, "\t%u\t", best[i]); for (unsigned k = 0; k < nids[i]; k++) fprintf(out, "%llu,", (unsigned long long)ids[i * KJ_MAX_MATCH_IDS + k]); }     // ConsumerThread.cpp:527-536
-                fputc('\n', out);
-            }
-            else fprintf(out, "U\t%s\t0\n", names[i].c_str());
-        }
-        seq1.clear(); seq2.clear(); off1.assign(1, 0); off2.assign(1, 0); names.clear();
-    };
-    off1.assign(1, 0); off2.assign(1, 0);
-    while (r1.next(name, s)) {
-        seq1 += s; off1.push_back(seq1.size());
-        if (paired) {
-            if (!r2->next(name2, s)) die("File " + in1 + " contains more reads then file " + in2);
-            if (name != name2) die("Read names are not identical between the two input files. Probably reads are not in the same order in both files.");
-            seq2 += s; off2.push_back(seq2.size());
-        }
-        names.push_back(name);
-        if (names.size() >= BATCH || seq1.size() >= (1u << 30)) flush();
-    }
-    flush();
-    if (paired && r2->next(name2, s)) fprintf(stderr, "Warning: File %s has more reads then file %s\n", in2.c_str(), in1.c_str());
-    if (out != stdout) fclose(out); else fflush(out);
-    delete r2; kj_destroy(ctx);
+    // parsing, classification and output formatting all run on the device; the host moves bytes (kj_ingest.h)
+    uint64_t n_reads = 0, n_classified = 0;
+    if (kj_classify_files(ctx, in1.c_str(), paired ? in2.c_str() : nullptr, out_fn.empty() ? nullptr : out_fn.c_str(), verbose ? 1 : 0, &n_reads, &n_classified) != KJ_OK) die(kj_last_error());
+    if (verbose) fprintf(stderr, "%llu reads, %llu classified\n", (unsigned long long)n_reads, (unsigned long long)n_classified);
+    kj_destroy(ctx);
     return EXIT_SUCCESS;
 }

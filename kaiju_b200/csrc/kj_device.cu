@@ -413,3 +413,5 @@ extern "C" double kj_last_kernel_ms(const kj_ctx* c) {
 }
 extern "C" int kj_check_errors(kj_ctx* c) { if (!c) return KJ_ERR_ARG; cudaSetDevice(c->device); return check_err_flag(c); }
 extern "C" int kj_launch_geometry(const kj_ctx* c, int* grid, int* block, int* smem) { if (!c) return KJ_ERR_ARG; if (grid) *grid = c->grid; if (block) *block = KJ_WARPS_PER_CTA * 32; if (smem) *smem = (int)c->smem_bytes; return KJ_OK; }
+
+#include "kj_ingest.h"

@@ -269,3 +269,72 @@ def test_cli_protein_and_verbose_columns(kb, golden, tmp_path):
         t, b, ids = orc.classify_one(P, s[int(o[i]):int(o[i + 1])].tobytes())
         exp = "C\tq%d\t%d\t%d\t%s" % (i, t, b, "".join("%d," % x for x in sorted(ids))) if t else "U\tq%d\t0" % i
         assert line == exp, (i, line, exp)
+
+
+def _expected_lines(orc, P, names, seqs1, seqs2=None, verbose=False):
+    out = []
+    for i, nm in enumerate(names):
+        t, b, ids = orc.classify_one(P, seqs1[i], seqs2[i] if seqs2 else None)
+        if t:
+            out.append("C\t%s\t%d" % (nm, t) + ("\t%d\t%s" % (b, "".join("%d," % x for x in sorted(ids))) if verbose else ""))
+        else:
+            out.append("U\t%s\t0" % nm)
+    return out
+
+
+@pytest.mark.parametrize("chunk", ["4096", "65536", ""])
+def test_file_ingest_on_device(kb, golden, tmp_path, monkeypatch, chunk):
+    """kj_classify_files: FASTA (wrapped lines, CRLF, no final newline), FASTQ (gz), mixed file types for the two mates, name trimming
+    at ' /\\t\\r', stripping of non-letters -- parsed, classified and formatted on the device, across many chunk boundaries."""
+    import gzip, random
+    if chunk:
+        monkeypatch.setenv("KJ_INGEST_CHUNK", chunk)
+    rnd = random.Random(5); db = SynthDB(800, 3)
+    s1, o1, s2, o2 = db.reads(91, 0, 700, 150, True)
+    ls, lo = db.long_reads(92, 0, 60, 300, 9000)
+    r1 = [s1[int(o1[i]):int(o1[i + 1])].tobytes() for i in range(700)]; r2 = [s2[int(o2[i]):int(o2[i + 1])].tobytes() for i in range(700)]
+    lr = [ls[int(lo[i]):int(lo[i + 1])].tobytes() for i in range(60)]
+    orc = Oracle(golden.fmi, golden.nodes)
+    # --- paired: mate 1 as gzipped FASTQ with decorated names, mate 2 as wrapped FASTA with CRLF and dirt inside the sequence lines
+    names = ["read%d" % i for i in range(700)]
+    deco1 = [" 1:N:0:ACGT", "/1", "\tx", "", " desc/1"]; deco2 = [" 2:N:0:ACGT", "/2", "\ty", "", " other"]
+    f1 = tmp_path / "m1.fq.gz"; f2 = tmp_path / "m2.fa"
+    with gzip.open(f1, "wt") as f:
+        for i, nm in enumerate(names):
+            f.write("@%s%s\n%s\n+\n%s\n" % (nm, deco1[i % 5], r1[i].decode(), "I" * len(r1[i])))
+    with open(f2, "wb") as f:
+        for i, nm in enumerate(names):
+            sq = r2[i].decode(); w = rnd.choice([40, 60, 70, 200]); body = "\r\n".join(sq[k:k + w] for k in range(0, len(sq), w))
+            if i % 7 == 0:
+                body = body[:10] + " 12-*" + body[10:]                        # strip() removes everything that is not a letter
+            f.write((">%s%s\r\n%s%s" % (nm, deco2[i % 5], body, "" if i == 699 else "\r\n")).encode())      # no newline at the end of the file
+    clf = kb.Classifier(golden.fmi, golden.nodes, device=0, params=kb.make_params("greedy", e=2))
+    out = tmp_path / "pe.tsv"
+    n, k = clf.classify_files(str(f1), str(f2), str(out), verbose=True)
+    exp = _expected_lines(orc, make_params("greedy", e=2), names, r1, r2, verbose=True)
+    got = open(out).read().splitlines()
+    assert n == 700 and got == exp and k == sum(1 for l in exp if l[0] == "C")
+    # --- single-end long reads as FASTA, MEM
+    f3 = tmp_path / "long.fa"
+    with open(f3, "w") as f:
+        for i, sq in enumerate(lr):
+            f.write(">L%d some text\n%s\n" % (i, "\n".join(sq.decode()[k:k + 80] for k in range(0, len(sq), 80))))
+    clf.set_params(kb.make_params("mem"))
+    out3 = tmp_path / "long.tsv"
+    n, k = clf.classify_files(str(f3), None, str(out3))
+    assert n == 60 and open(out3).read().splitlines() == _expected_lines(orc, make_params("mem"), ["L%d" % i for i in range(60)], lr)
+    # --- errors mirror the reference's front end
+    bad = tmp_path / "bad.fq"; bad.write_text("ACGT\n")
+    with pytest.raises(kb.KaijuError, match="Auto-detection"):
+        clf.classify_files(str(bad), None, str(tmp_path / "x.tsv"))
+    f4 = tmp_path / "m2_renamed.fa"
+    f4.write_bytes(open(f2, "rb").read().replace(b">read350", b">readX350"))
+    with pytest.raises(kb.KaijuError, match="not identical"):
+        clf.classify_files(str(f1), str(f4), str(tmp_path / "x.tsv"))
+    f5 = tmp_path / "m2_short.fa"
+    f5.write_bytes(open(f2, "rb").read().split(b">read600")[0])
+    with pytest.raises(kb.KaijuError, match="contains more reads"):
+        clf.classify_files(str(f1), str(f5), str(tmp_path / "x.tsv"))
+    n, k = clf.classify_files(str(f5), None, str(tmp_path / "y.tsv"))           # the truncated file alone is fine
+    assert n == 600
+    clf.close()
