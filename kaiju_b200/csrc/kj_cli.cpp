@@ -7,6 +7,7 @@
 // (accession names, fragment sequences) are not produced.
 #include <getopt.h>
 #include <unistd.h>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -68,8 +69,10 @@ int main(int argc, char** argv) {
 
     // parsing, classification and output formatting all run on the device; the host moves bytes (kj_ingest.h)
     uint64_t n_reads = 0, n_classified = 0;
+    const auto t0 = std::chrono::steady_clock::now();
     if (kj_classify_files(ctx, in1.c_str(), paired ? in2.c_str() : nullptr, out_fn.empty() ? nullptr : out_fn.c_str(), verbose ? 1 : 0, &n_reads, &n_classified) != KJ_OK) die(kj_last_error());
-    if (verbose) fprintf(stderr, "%llu reads, %llu classified\n", (unsigned long long)n_reads, (unsigned long long)n_classified);
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (verbose || getenv("KJ_CLI_TIMING")) fprintf(stderr, "%llu reads, %llu classified, %.4f s from the first byte read to the last byte written\n", (unsigned long long)n_reads, (unsigned long long)n_classified, secs);
     kj_destroy(ctx);
     return EXIT_SUCCESS;
 }

@@ -10,6 +10,8 @@
 // The host only moves bytes: file -> pinned buffer -> device, device -> pinned buffer -> file (kj_classify_files).
 // Included by kj_device.cu (one translation unit: it uses kj_ctx and launch()).
 #pragma once
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
 #include <condition_variable>
 #include <deque>
@@ -268,13 +270,19 @@ static int kj_parse_consumed(KjParsed& P, uint64_t n, uint64_t headers_total_hin
 }
 
 struct KjChunk { char* p = nullptr; size_t n = 0; bool eof = false; std::string error; };
-struct KjFileReader {   // one thread per input file: gz or plain -> pinned chunks
-    gzFile fp = nullptr; std::string path; size_t chunk; std::vector<char*> pool; std::deque<KjChunk> ready; std::deque<char*> free_;
+struct KjFileReader {   // one thread per input file: gz (zlib) or plain (read(2)) -> pinned chunks
+    gzFile fp = nullptr; int fd = -1; uint64_t file_off = 0; std::string path; size_t chunk; std::vector<char*> pool; std::deque<KjChunk> ready; std::deque<char*> free_;
     std::mutex mu; std::condition_variable cv; std::thread th; bool stop = false;
     int open(const std::string& p, size_t chunk_bytes, int nbuf) {
-        path = p; chunk = chunk_bytes; fp = gzopen(p.c_str(), "rb");
-        if (!fp) { kj_err() = "Could not open file " + p; return KJ_ERR_IO; }
-        gzbuffer(fp, 1 << 20);
+        path = p; chunk = chunk_bytes;
+        fd = ::open(p.c_str(), O_RDONLY);
+        if (fd < 0) { kj_err() = "Could not open file " + p; return KJ_ERR_IO; }
+        unsigned char magic[2] = {0, 0}; const ssize_t got = ::pread(fd, magic, 2, 0);
+        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {             // gzip: inflate through zlib; everything else is read as it is
+            ::close(fd); fd = -1; fp = gzopen(p.c_str(), "rb");
+            if (!fp) { kj_err() = "Could not open file " + p; return KJ_ERR_IO; }
+            gzbuffer(fp, 1 << 20);
+        } else posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
         for (int i = 0; i < nbuf; i++) { char* b = nullptr; if (cudaMallocHost((void**)&b, chunk) != cudaSuccess) { kj_err() = "cudaMallocHost failed"; return KJ_ERR_NOMEM; } pool.push_back(b); free_.push_back(b); }
         th = std::thread([this] { run(); });
         return KJ_OK;
@@ -284,7 +292,28 @@ struct KjFileReader {   // one thread per input file: gz or plain -> pinned chun
             char* b;
             { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || !free_.empty(); }); if (stop) return; b = free_.front(); free_.pop_front(); }
             KjChunk ck; ck.p = b; size_t got = 0;
-            while (got < chunk) { int r = gzread(fp, b + got, (unsigned)std::min<size_t>(chunk - got, 1u << 30)); if (r < 0) { ck.error = "read error in file " + path; break; } if (r == 0) { ck.eof = true; break; } got += (size_t)r; }
+            if (fd >= 0) {
+                // plain file: four threads pread() a quarter of the chunk each (one page-cache copy stream per thread)
+                const int NT = 4; const size_t part = (chunk + NT - 1) / NT; ssize_t res[NT]; std::thread th4[NT];
+                for (int t = 0; t < NT; t++) th4[t] = std::thread([&, t] {
+                    const size_t o = (size_t)t * part, want = o < chunk ? std::min(part, chunk - o) : 0; size_t g = 0; res[t] = 0;
+                    while (g < want) { const ssize_t r = ::pread(fd, b + o + g, want - g, (off_t)(file_off + o + g)); if (r < 0) { res[t] = -1; return; } if (r == 0) break; g += (size_t)r; }
+                    res[t] = (ssize_t)g; });
+                for (int t = 0; t < NT; t++) th4[t].join();
+                for (int t = 0; t < NT; t++) {
+                    if (res[t] < 0) { ck.error = "read error in file " + path; break; }
+                    got += (size_t)res[t];
+                    const size_t o = (size_t)t * part, want = o < chunk ? std::min(part, chunk - o) : 0;
+                    if ((size_t)res[t] < want) { ck.eof = true; break; }          // short part = end of file (later parts read nothing)
+                }
+                if (got == chunk && !ck.eof) { char probe; if (::pread(fd, &probe, 1, (off_t)(file_off + chunk)) == 0) ck.eof = true; }
+                file_off += got;
+            } else while (got < chunk) {
+                const ssize_t r = (ssize_t)gzread(fp, b + got, (unsigned)std::min<size_t>(chunk - got, 1u << 30));
+                if (r < 0) { ck.error = "read error in file " + path; break; }
+                if (r == 0) { ck.eof = true; break; }
+                got += (size_t)r;
+            }
             ck.n = got;
             const bool last = ck.eof || !ck.error.empty();
             { std::lock_guard<std::mutex> lk(mu); ready.push_back(ck); }
@@ -298,6 +327,7 @@ struct KjFileReader {   // one thread per input file: gz or plain -> pinned chun
         { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_all();
         if (th.joinable()) th.join();
         if (fp) gzclose(fp); fp = nullptr;
+        if (fd >= 0) ::close(fd); fd = -1;
         for (char* b : pool) cudaFreeHost(b); pool.clear();
     }
 };
@@ -330,15 +360,32 @@ struct KjWriter {   // ordered output: pinned buffers filled by D2H copies, writ
     }
 };
 
+struct KjPrefetch { KjDevBuf stage[2]; int cur = 0; cudaEvent_t done = nullptr; bool pending = false, eof = false; char* host = nullptr; size_t n = 0; char last = 0; };
 struct KjFilesState {
-    KjParsed side[2]; KjFileReader rd[2]; KjWriter wr; int nfiles = 1; bool rd_open[2] = {false, false}, wr_open = false;
+    KjParsed side[2]; KjFileReader rd[2]; KjWriter wr; KjPrefetch pf[2]; int nfiles = 1; bool rd_open[2] = {false, false}, wr_open = false;
     KjDevBuf tax, best, ids, nids, len, out, scan_tmp, totals;
     void cleanup() {
-        for (int f = 0; f < 2; f++) { if (rd_open[f]) rd[f].close(); side[f].release(); }
+        for (int f = 0; f < 2; f++) {
+            if (pf[f].pending && pf[f].done) cudaEventSynchronize(pf[f].done);
+            if (rd_open[f]) rd[f].close(); side[f].release(); pf[f].stage[0].release(); pf[f].stage[1].release(); if (pf[f].done) cudaEventDestroy(pf[f].done);
+        }
         if (wr_open) wr.close();
         for (KjDevBuf* b : {&tax, &best, &ids, &nids, &len, &out, &scan_tmp, &totals}) b->release();
     }
 };
+
+// next chunk of file f: pinned buffer -> device staging buffer, asynchronously on the context's second stream
+static int kj_prefetch(kj_ctx* c, KjFilesState& S, int f) {
+    KjPrefetch& F = S.pf[f];
+    KjChunk ck = S.rd[f].next();
+    if (!ck.error.empty()) { kj_err() = ck.error; return KJ_ERR_IO; }
+    F.cur ^= 1; int rc = F.stage[F.cur].need(ck.n + 16); if (rc) return rc;
+    if (!F.done) CK(cudaEventCreateWithFlags(&F.done, cudaEventDisableTiming));
+    if (ck.n) CK(cudaMemcpyAsync(F.stage[F.cur].p, ck.p, ck.n, cudaMemcpyHostToDevice, c->stream[1]));
+    CK(cudaEventRecord(F.done, c->stream[1]));
+    F.pending = true; F.eof = ck.eof; F.host = ck.p; F.n = ck.n; F.last = ck.n ? ck.p[ck.n - 1] : 0;
+    return KJ_OK;
+}
 
 static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, const char* in2, const char* out_path, int verbose, uint64_t* n_reads_out, uint64_t* n_class_out) {
     size_t chunk = 32u << 20;
@@ -354,27 +401,30 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
     uint64_t n_reads = 0; unsigned long long n_class = 0;
     CK(cudaMemsetAsync(S.totals.p, 0, 64, st));
     unsigned long long* d_nclass = (unsigned long long*)((char*)S.totals.p + 16);
+    for (int f = 0; f < S.nfiles; f++) if ((rc = kj_prefetch(c, S, f))) return rc;
     for (;;) {
-        // 1. top up both sides: carry (already at the front of the device text) + the next chunk of the file
+        // 1. top up both sides: carry (already at the front of the device text) + the chunk that was prefetched into the staging buffer
         for (int f = 0; f < S.nfiles; f++) {
-            KjParsed& P = S.side[f];
-            if (P.eof) continue;
-            KjChunk ck = S.rd[f].next();
-            if (!ck.error.empty()) { kj_err() = ck.error; return KJ_ERR_IO; }
-            if ((P.nbytes + ck.n + 1) > P.text[P.cur].cap) {        // grow: move the carry into the larger buffer
-                KjDevBuf nb; if ((rc = nb.need(P.nbytes + ck.n + chunk + 1))) return rc;
+            KjParsed& P = S.side[f]; KjPrefetch& F = S.pf[f];
+            if (!F.pending) continue;
+            CK(cudaEventSynchronize(F.done));                          // H2D finished: the pinned chunk goes back to the reader
+            S.rd[f].give_back(F.host); F.pending = false;
+            if ((P.nbytes + F.n + 1) > P.text[P.cur].cap) {            // grow: move the carry into the larger buffer
+                KjDevBuf nb; if ((rc = nb.need(P.nbytes + F.n + chunk + 1))) return rc;
                 if (P.nbytes) CK(cudaMemcpyAsync(nb.p, P.text[P.cur].p, P.nbytes, cudaMemcpyDeviceToDevice, st));
                 CK(cudaStreamSynchronize(st)); P.text[P.cur].release(); P.text[P.cur] = nb;
             }
-            char* dst = P.text[P.cur].as<char>() + P.nbytes;
-            if (ck.n) CK(cudaMemcpyAsync(dst, ck.p, ck.n, cudaMemcpyHostToDevice, st));
+            if (F.n) CK(cudaMemcpyAsync(P.text[P.cur].as<char>() + P.nbytes, F.stage[F.cur].p, F.n, cudaMemcpyDeviceToDevice, st));
             bool need_nl = false;
-            if (ck.eof) { P.eof = true; const uint64_t tot = P.nbytes + ck.n; if (tot) { char last; if (ck.n) last = ck.p[ck.n - 1]; else { CK(cudaMemcpyAsync(&last, P.text[P.cur].as<char>() + tot - 1, 1, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); } need_nl = last != '\n'; } }
-            P.nbytes += ck.n;
+            if (F.eof) {
+                P.eof = true; const uint64_t tot = P.nbytes + F.n;
+                if (tot) { char last = F.last; if (!F.n) { CK(cudaMemcpyAsync(&last, P.text[P.cur].as<char>() + tot - 1, 1, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); } need_nl = last != '\n'; }
+            }
+            P.nbytes += F.n;
             if (need_nl) { CK(cudaMemsetAsync(P.text[P.cur].as<char>() + P.nbytes, '\n', 1, st)); P.nbytes += 1; }      // the last line of a file may lack its newline
-            CK(cudaStreamSynchronize(st));                            // the pinned chunk is free again
-            S.rd[f].give_back(ck.p);
         }
+        // ... and start the host-to-device copy of the following chunks on the second stream: it overlaps with the kernels below
+        for (int f = 0; f < S.nfiles; f++) if (!S.side[f].eof && (rc = kj_prefetch(c, S, f))) return rc;
         // 2. parse
         for (int f = 0; f < S.nfiles; f++) if ((rc = kj_parse_side(c, S.side[f], fn[f], st))) return rc;
         uint64_t n = S.side[0].n_rec; if (paired) n = std::min(n, S.side[1].n_rec);
