@@ -123,6 +123,17 @@ int kj_classify_device(kj_ctx *ctx, const char *d_seq1, const uint64_t *d_off1, 
 int kj_classify_files(kj_ctx *ctx, const char *in1, const char *in2, const char *out_path, int verbose,
                       uint64_t *n_reads_out, uint64_t *n_classified_out);
 
+/* --- per-taxon read counts (what kaiju2table's first pass computes, src/kaiju2table.cpp:186-245) --- */
+/* Every successful kj_classify / kj_classify_verbose / kj_classify_files call adds its reads to a dense count vector in HBM:
+ * one slot per taxon known to the context (all ids of nodes.dmp ascending, then DB taxa missing from it) + a last slot for
+ * unclassified reads.  After kj_classify_device() the caller adds explicitly (kj_counts_add_device) once the launch is known
+ * to be good.  With several GPUs the vectors are summed with one all-reduce over kj_counts_device_ptr() (uint64[kj_counts_size()]). */
+int kj_counts_reset(kj_ctx *ctx);
+uint64_t kj_counts_size(const kj_ctx *ctx);
+void *kj_counts_device_ptr(kj_ctx *ctx);
+int kj_counts_add_device(kj_ctx *ctx, const uint64_t *d_taxon, uint64_t n_reads, void *cuda_stream);
+int kj_counts_get(kj_ctx *ctx, uint64_t *taxon_ids_out /* [size] or NULL; last = 0 */, uint64_t *counts_out /* [size] */);
+
 /* Per-read work queues on the device are sized from worst-case bounds; should one overflow anyway, the affected launch is
  * flagged (never silently truncated).  kj_classify() checks this itself; after kj_classify_device() call kj_check_errors()
  * once the stream has finished: KJ_OK, or KJ_ERR_OVERFLOW (the results of that launch are invalid).  When the overflow was

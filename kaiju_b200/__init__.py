@@ -67,6 +67,11 @@ def lib():
         L.kj_index_bytes.restype = C.c_uint64; L.kj_index_bytes.argtypes = [C.c_void_p]
         L.kj_last_kernel_ms.restype = C.c_double; L.kj_last_kernel_ms.argtypes = [C.c_void_p]
         L.kj_classify_files.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.kj_counts_reset.argtypes = [C.c_void_p]
+        L.kj_counts_size.restype = C.c_uint64; L.kj_counts_size.argtypes = [C.c_void_p]
+        L.kj_counts_device_ptr.restype = C.c_void_p; L.kj_counts_device_ptr.argtypes = [C.c_void_p]
+        L.kj_counts_add_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.kj_counts_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.kj_check_errors.argtypes = [C.c_void_p]
         L.kj_launch_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.kj_version.restype = C.c_int
@@ -165,6 +170,25 @@ class Classifier:
         _check(lib().kj_classify_files(self._ctx, in1.encode(), in2.encode() if in2 else None, out_path.encode() if out_path else None,
                                        1 if verbose else 0, C.byref(n), C.byref(k)))
         return int(n.value), int(k.value)
+
+    # ---- per-taxon read counts accumulated in HBM by the successful classify calls (input of kaiju2table)
+    def counts_reset(self):
+        _check(lib().kj_counts_reset(self._ctx))
+
+    def counts(self, nonzero=True):
+        """(taxon ids, read counts); the last entry (id 0) counts the unclassified reads."""
+        n = int(lib().kj_counts_size(self._ctx)); ids = np.zeros(n, dtype=np.uint64); cnt = np.zeros(n, dtype=np.uint64)
+        _check(lib().kj_counts_get(self._ctx, ids.ctypes.data, cnt.ctypes.data))
+        if nonzero:
+            k = cnt != 0; return ids[k], cnt[k]
+        return ids, cnt
+
+    def counts_add_device(self, d_tax, n, stream=None):
+        _check(lib().kj_counts_add_device(self._ctx, d_tax, n, stream))
+
+    @property
+    def counts_device_ptr(self):
+        return lib().kj_counts_device_ptr(self._ctx), int(lib().kj_counts_size(self._ctx))
 
     def check_errors(self):
         _check(lib().kj_check_errors(self._ctx))

@@ -108,6 +108,25 @@ __global__ void kj_maxlen_kernel(const uint64_t* __restrict__ off, uint64_t n, u
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
+// Per-taxon read counts (the input of kaiju2table, src/kaiju2table.cpp:186-245): dense index of each result by binary search in the
+// two ascending runs of tax_id (nodes.dmp ids | DB taxa absent from it); slot n_tax = unclassified.
+__global__ void kj_count_kernel(const uint64_t* __restrict__ taxon, uint64_t n, const uint64_t* __restrict__ tax_id, uint32_t n_present, uint32_t n_tax,
+                                unsigned long long* __restrict__ counts) {
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t id = taxon[r]; uint32_t slot = n_tax;
+        if (id) {
+            uint32_t lo = 0, hi = n_present;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (tax_id[mid] < id) lo = mid + 1; else hi = mid; }
+            if (lo < n_present && tax_id[lo] == id) slot = lo;
+            else { lo = n_present; hi = n_tax; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (tax_id[mid] < id) lo = mid + 1; else hi = mid; } if (lo < n_tax && tax_id[lo] == id) slot = lo; }
+        }
+        atomicAdd(counts + slot, 1ull);
+    }
+}
+__global__ void kj_count_commit(unsigned long long* __restrict__ total, unsigned long long* __restrict__ pending, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { total[i] += pending[i]; pending[i] = 0; }
+}
+
 // ------------------------------------------------------------------------------------------------
 struct kj_ctx {
     int device = 0; kj_params params{}; int sm_count = 0;
@@ -121,6 +140,7 @@ struct kj_ctx {
     unsigned long long* d_counter = nullptr; uint32_t* d_err = nullptr; unsigned int* d_maxlen = nullptr;
     KjKept* d_spill = nullptr; size_t spill_bytes = 0; uint8_t* d_gscratch = nullptr; size_t gscratch_bytes_total = 0;
     double* d_evbreaks = nullptr; uint32_t n_evbreaks = 0;
+    unsigned long long* d_counts = nullptr; unsigned long long* d_counts_pending = nullptr; uint32_t n_counts = 0, n_present = 0;   // per-taxon read counts (+1 slot: unclassified)
     uint32_t variant_boost = 1;    // Greedy variant-ring capacity multiplier, raised after an overflow (flag 4) so that a retry succeeds
     uint8_t* d_ws = nullptr; size_t ws_bytes = 0;
     cudaStream_t stream[2] = {nullptr, nullptr}; cudaEvent_t ev_a = nullptr, ev_b = nullptr;
@@ -223,6 +243,9 @@ extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, cons
     for (int s = 0; s < 2; s++) CK(cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev_a)); CK(cudaEventCreate(&c->ev_b));
     if ((rc = upload_evalue_breaks(c))) return rc;
+    c->n_counts = (uint32_t)H.tax_id.size() + 1u; c->n_present = H.n_present;
+    CK(cudaMalloc((void**)&c->d_counts, (size_t)c->n_counts * 8)); CK(cudaMalloc((void**)&c->d_counts_pending, (size_t)c->n_counts * 8));
+    CK(cudaMemset(c->d_counts, 0, (size_t)c->n_counts * 8)); CK(cudaMemset(c->d_counts_pending, 0, (size_t)c->n_counts * 8));
     *out = guard.release(); return KJ_OK;
 }
 
@@ -238,7 +261,7 @@ extern "C" void kj_destroy(kj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     void* ptrs[] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_tax_parent, c->d_tax_depth, c->d_tax_id, c->d_lnfact, c->d_kmer, c->d_tables, c->d_ix,
-                    c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evbreaks, c->d_ws, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
+                    c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evbreaks, c->d_ws, c->d_counts, c->d_counts_pending, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
                     c->d_seq[0][0], c->d_seq[0][1], c->d_seq[1][0], c->d_seq[1][1], c->d_off[0][0], c->d_off[0][1], c->d_off[1][0], c->d_off[1][1],
                     c->d_ids[0], c->d_ids[1], c->d_nids[0], c->d_nids[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -276,6 +299,13 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     CK(cudaGetLastError());
     if (time_it) CK(cudaEventRecord(c->ev_b, st));
     c->launches++;
+    return KJ_OK;
+}
+
+static int count_taxa(kj_ctx* c, const uint64_t* d_tax, uint64_t n, unsigned long long* d_dst, cudaStream_t st) {
+    if (!n) return KJ_OK;
+    kj_count_kernel<<<c->sm_count * 4, 256, 0, st>>>(d_tax, n, c->dix.tax_id, c->n_present, c->n_counts - 1u, d_dst);
+    CK(cudaGetLastError()); c->launches++;
     return KJ_OK;
 }
 
@@ -372,6 +402,7 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
         rc = launch(c, s, c->d_seq[s][0], c->d_off[s][0], paired ? c->d_seq[s][1] : nullptr, paired ? c->d_off[s][1] : nullptr, b1, b2, cnt, max1, max2,
                     c->d_tax[s], best_out ? c->d_best[s] : nullptr, st, false, ids_out ? c->d_ids[s] : nullptr, ids_out ? c->d_nids[s] : nullptr);
         if (rc) return rc;
+        if ((rc = count_taxa(c, c->d_tax[s], cnt, c->d_counts_pending, st))) return rc;
         CK(cudaMemcpyAsync(taxon_out + start, c->d_tax[s], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         if (best_out) CK(cudaMemcpyAsync(best_out + start, c->d_best[s], cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (ids_out) {
@@ -380,7 +411,12 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
         }
     }
     CK(cudaStreamSynchronize(c->stream[0])); CK(cudaStreamSynchronize(c->stream[1]));
-    return check_err_flag(c);
+    rc = check_err_flag(c);
+    // the per-taxon counts of this call become visible only if the whole call succeeded (a repeated call must not count twice)
+    if (rc) { CK(cudaMemset(c->d_counts_pending, 0, (size_t)c->n_counts * 8)); return rc; }
+    kj_count_commit<<<c->sm_count, 256, 0, c->stream[0]>>>(c->d_counts, c->d_counts_pending, c->n_counts); c->launches++;
+    CK(cudaStreamSynchronize(c->stream[0]));
+    return KJ_OK;
 }
 
 // A full Greedy variant ring (flag 4) enlarges the ring for the next launch: repeat the call until it fits (bounded).
@@ -410,6 +446,23 @@ extern "C" double kj_last_kernel_ms(const kj_ctx* c) {
     float ms = 0.f; if (cudaEventSynchronize(c->ev_b) != cudaSuccess) return 0.0;
     if (cudaEventElapsedTime(&ms, c->ev_a, c->ev_b) != cudaSuccess) return 0.0;
     return (double)ms;
+}
+extern "C" int kj_counts_reset(kj_ctx* c) {
+    if (!c) return KJ_ERR_ARG; CK(cudaSetDevice(c->device));
+    CK(cudaMemset(c->d_counts, 0, (size_t)c->n_counts * 8)); return KJ_OK;
+}
+extern "C" uint64_t kj_counts_size(const kj_ctx* c) { return c ? c->n_counts : 0; }
+extern "C" void* kj_counts_device_ptr(kj_ctx* c) { return c ? (void*)c->d_counts : nullptr; }
+extern "C" int kj_counts_add_device(kj_ctx* c, const uint64_t* d_taxon, uint64_t n, void* cuda_stream) {
+    if (!c || (!d_taxon && n)) { kj_err() = "kj_counts_add_device: null argument"; return KJ_ERR_ARG; }
+    CK(cudaSetDevice(c->device)); return count_taxa(c, d_taxon, n, c->d_counts, (cudaStream_t)cuda_stream);
+}
+extern "C" int kj_counts_get(kj_ctx* c, uint64_t* taxon_ids_out, uint64_t* counts_out) {
+    if (!c || !counts_out) { kj_err() = "kj_counts_get: null argument"; return KJ_ERR_ARG; }
+    CK(cudaSetDevice(c->device)); CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(counts_out, c->d_counts, (size_t)c->n_counts * 8, cudaMemcpyDeviceToHost));
+    if (taxon_ids_out) { for (uint32_t i = 0; i + 1 < c->n_counts; i++) taxon_ids_out[i] = c->H.tax_id[i]; taxon_ids_out[c->n_counts - 1] = 0; }
+    return KJ_OK;
 }
 extern "C" int kj_check_errors(kj_ctx* c) { if (!c) return KJ_ERR_ARG; cudaSetDevice(c->device); return check_err_flag(c); }
 extern "C" int kj_launch_geometry(const kj_ctx* c, int* grid, int* block, int* smem) { if (!c) return KJ_ERR_ARG; if (grid) *grid = c->grid; if (block) *block = KJ_WARPS_PER_CTA * 32; if (smem) *smem = (int)c->smem_bytes; return KJ_OK; }

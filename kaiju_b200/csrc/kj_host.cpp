@@ -234,7 +234,7 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
     std::sort(extra.begin(), extra.end()); extra.erase(std::unique(extra.begin(), extra.end()), extra.end());
     const size_t np = present.size(), nt = np + extra.size();
     if (nt >= 0xfffffff0ull) { kj_err() = "too many taxa"; return KJ_ERR_UNSUPPORTED; }
-    H.tax_id = present; H.tax_id.insert(H.tax_id.end(), extra.begin(), extra.end());
+    H.tax_id = present; H.tax_id.insert(H.tax_id.end(), extra.begin(), extra.end()); H.n_present = (uint32_t)np;
     auto index_of = [&](uint64_t id) -> uint32_t {
         auto it = std::lower_bound(present.begin(), present.end(), id);
         if (it != present.end() && *it == id) return (uint32_t)(it - present.begin());

@@ -23,7 +23,7 @@ struct KjHostIndex {
     uint64_t bwtlen = 0; int alen = 0; uint64_t C[KJ_MAX_ALEN + 1] = {0};
     std::vector<uint32_t> sa_tax, seq_tax;
     uint64_t sa_check = 0; int sa_exp = 0; int64_t sa_bias = 0; uint32_t nseq = 0;
-    std::vector<uint32_t> tax_parent, tax_depth; std::vector<uint64_t> tax_id;
+    std::vector<uint32_t> tax_parent, tax_depth; std::vector<uint64_t> tax_id; uint32_t n_present = 0;   // tax_id = [ids of nodes.dmp, ascending | DB taxa absent from it, ascending]
     std::vector<double> lnfact;
     std::vector<KjKmer> kmer; std::vector<KjKmer32> kmer32; int kmer_k = 0; int wide = 0;   // k-mer suffix intervals (letters 1..20)
     KjTables tables;

@@ -454,6 +454,7 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
                 if (rc) return rc;
                 break;
             }
+            if ((rc = count_taxa(c, S.tax.as<uint64_t>(), n, c->d_counts, st))) return rc;          // this chunk succeeded: its reads join the per-taxon counts
             kj_fmt_len<<<c->sm_count * 4, 256, 0, st>>>(S.tax.as<uint64_t>(), S.best.as<uint32_t>(), S.ids.as<uint64_t>(), S.nids.as<uint8_t>(), S.side[0].name_off.as<uint32_t>(), n, verbose, S.len.as<uint32_t>(), d_nclass);
             if ((rc = kj_scan_u32(S.len.as<uint32_t>(), n + 1, S.scan_tmp, (uint32_t*)S.totals.p, st))) return rc;
             uint32_t out_bytes = 0; CK(cudaMemcpyAsync(&out_bytes, S.totals.p, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));

@@ -338,3 +338,45 @@ def test_file_ingest_on_device(kb, golden, tmp_path, monkeypatch, chunk):
     n, k = clf.classify_files(str(f5), None, str(tmp_path / "y.tsv"))           # the truncated file alone is fine
     assert n == 600
     clf.close()
+
+
+def test_per_taxon_counts(kb, golden, tmp_path, monkeypatch):
+    """The dense per-taxon count vector in HBM (kaiju2table's input): equals a histogram of the per-read results for the host-buffer,
+    device-buffer and file entry points; a call repeated after a variant-ring overflow is counted once."""
+    import torch
+    names, s1, o1, s2, o2 = golden.reads("pe150"); n = len(names)
+    clf = kb.Classifier(golden.fmi, golden.nodes, device=0, params=kb.make_params("mem"))
+    def hist(t):
+        u, c = np.unique(t, return_counts=True); return dict(zip(u.tolist(), c.tolist()))
+    tax, _ = clf.classify(s1, o1, s2, o2)
+    ids, cnt = clf.counts()
+    assert dict(zip(ids.tolist(), cnt.tolist())) == hist(tax) and int(cnt.sum()) == n
+    tax2, _ = clf.classify(s1, o1)                                  # a second call accumulates
+    ids, cnt = clf.counts(); exp = hist(np.concatenate([tax, tax2]))
+    assert dict(zip(ids.tolist(), cnt.tolist())) == exp
+    clf.counts_reset()
+    d = [torch.from_numpy(x.view(np.int64) if x.dtype == np.uint64 else x).cuda() for x in (s1, o1, s2, o2)]
+    dt = torch.zeros(n, dtype=torch.int64, device="cuda")
+    clf.classify_device(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), n, dt.data_ptr()); torch.cuda.synchronize(); clf.check_errors()
+    assert int(clf.counts()[1].sum()) == 0                          # the device entry point leaves counting to the caller
+    clf.counts_add_device(dt.data_ptr(), n); ids, cnt = clf.counts()
+    assert dict(zip(ids.tolist(), cnt.tolist())) == hist(tax)
+    # the count vector is a plain device array: torch (and therefore NCCL all-reduce) can address it in place
+    from kaiju_b200.sharding import _DevArray
+    ptr, m = clf.counts_device_ptr
+    view = torch.as_tensor(_DevArray(ptr, m, "<i8"), device="cuda:0")
+    assert int(view.sum().item()) == n
+    # files
+    clf.counts_reset()
+    gold = os.path.dirname(golden.fmi)
+    k, _ = clf.classify_files(os.path.join(gold, "pe150_1.fq.gz"), os.path.join(gold, "pe150_2.fq.gz"), str(tmp_path / "o.tsv"))
+    ids, cnt = clf.counts()
+    assert k == n and dict(zip(ids.tolist(), cnt.tolist())) == hist(tax)
+    clf.close()
+    # overflow + retry counts once
+    other = SynthDB(3000, 777); s, o = other.long_reads(61, 0, 120, 3000, 16383)
+    monkeypatch.setenv("KJ_VARIANT_CAP", "128")
+    clf = kb.Classifier(golden.fmi, golden.nodes, device=0, params=kb.make_params("greedy", m=9, e=8, s=30, seed=5, E=1e-9))
+    t, _ = clf.classify(s, o); ids, cnt = clf.counts()
+    assert int(cnt.sum()) == 120 and dict(zip(ids.tolist(), cnt.tolist())) == hist(t)
+    clf.close()

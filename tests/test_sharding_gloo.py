@@ -12,7 +12,7 @@ WORKER = textwrap.dedent('''
     from conftest import Golden
     from helpers import make_params
     from test_kernel_logic_emulated import KjParams, emu_classify
-    from kaiju_b200.sharding import shard_bounds, slice_packed, all_gather_taxa
+    from kaiju_b200.sharding import shard_bounds, slice_packed, all_gather_taxa, all_reduce_counts
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
     rank, world = dist.get_rank(), dist.get_world_size()
     g = Golden(); names, s1, o1, s2, o2 = g.reads("pe150"); n = len(names)
@@ -25,6 +25,12 @@ WORKER = textwrap.dedent('''
     full = all_gather_taxa(torch.from_numpy(tax.view(np.int64)), n, rank, world, dist)
     etax, _, _ = g.expected("mem_default", "pe150")
     ok = np.array_equal(full.numpy().view(np.uint64), etax)
+    # per-taxon summary: every rank histograms its shard over a common id table, one all-reduce gives the job-wide counts
+    table = np.unique(etax); local = np.zeros(len(table), dtype=np.int64)
+    u, c = np.unique(tax, return_counts=True); local[np.searchsorted(table, u)] = c
+    total = all_reduce_counts(torch.from_numpy(local), dist).numpy()
+    eu, ec = np.unique(etax, return_counts=True)
+    ok = ok and np.array_equal(total, ec) and int(total.sum()) == n
     print("RANK", rank, "shard", lo, hi, "OK" if ok else "MISMATCH", flush=True)
     dist.barrier(); dist.destroy_process_group()
     sys.exit(0 if ok else 1)
