@@ -208,6 +208,13 @@ def main():
     ms_host, _ = timed(step_host, max(2, args.steps // 2), 1)
     clf.check_errors()
     assert torch.equal(h_tax, d_tax.cpu()), "host-buffer and device-buffer entry points disagree"
+    # untimed: the kaiju2table-style summary -- per-taxon read counts in HBM, one all-reduce across the ranks
+    clf.counts_reset(); clf.counts_add_device(d_tax.data_ptr(), n); torch.cuda.synchronize()
+    if dist:
+        from kaiju_b200.sharding import all_reduce_counts
+        all_reduce_counts(None, dist, clf); torch.cuda.synchronize()
+    ids_c, cnt_c = clf.counts()
+    assert int(cnt_c.sum()) == n * world, "per-taxon counts do not add up to the number of reads"
     total = n * world
     value = total * args.steps / (ms_dev / 1000.0)
     e2e_steps = max(2, args.steps // 2)
@@ -226,7 +233,8 @@ def main():
                 "config": {"workload": "configs[1]: %s -m 11 (SEG on), %d synthetic PE150 pairs per GPU per step vs synth-viruses .fmi (%d proteins, bwtlen %d)" % (args.mode.upper(), n, args.nprot, clf.bwtlen),
                            "parallelism": "read-sharded x%d, index replicated, NCCL all-gather of taxon ids per step" % world if world > 1 else "single GPU",
                            "l2": "inputs (%.1f GB/step) and index (%.2f GB) exceed the 126 MB L2" % ((s1.nbytes + s2.nbytes + o1.nbytes + o2.nbytes) / 1e9, clf.index_bytes / 1e9),
-                           "launch": dict(zip(("grid", "block", "dyn_smem"), clf.launch_geometry))},
+                           "launch": dict(zip(("grid", "block", "dyn_smem"), clf.launch_geometry)),
+                           "per_taxon_counts": "%d taxa with reads, counts sum to %d reads (untimed; all-reduce over %d rank(s))" % (len(ids_c) - 1, int(cnt_c.sum()), world)},
                 "e2e": {"value": e2e, "unit": "read pairs/s", "h2d_bytes_per_step": int(s1.nbytes + s2.nbytes + o1.nbytes + o2.nbytes), "d2h_bytes_per_step": int(n * 12),
                         "note": "kj_classify() with pinned host buffers, chunked H2D/kernel/D2H pipeline inside"},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "kernel_ms": kernel_ms}

@@ -363,7 +363,7 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
     // batch-wide length bounds (fixes the shared-memory carve-up for all chunks)
     uint32_t max1 = 0, max2 = 0;
     {
-        unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency())); std::vector<uint32_t> m1(nthr, 0), m2(nthr, 0); std::vector<std::thread> th;
+        unsigned nthr = std::max(1u, std::min(64u, std::thread::hardware_concurrency())); if (n < 65536) nthr = 1; std::vector<uint32_t> m1(nthr, 0), m2(nthr, 0); std::vector<std::thread> th;
         for (unsigned t = 0; t < nthr; t++) th.emplace_back([&, t] { uint64_t a = n * t / nthr, b = n * (t + 1) / nthr; uint32_t x = 0, y = 0;
             for (uint64_t i = a; i < b; i++) { uint64_t l = off1[i + 1] - off1[i]; if (l > 0xffffffffull) l = 0xffffffffull; x = std::max(x, (uint32_t)l);
                                                if (paired) { uint64_t k = off2[i + 1] - off2[i]; if (k > 0xffffffffull) k = 0xffffffffull; y = std::max(y, (uint32_t)k); } }
@@ -371,7 +371,9 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
         for (auto& x : th) x.join();
         for (unsigned t = 0; t < nthr; t++) { max1 = std::max(max1, m1[t]); max2 = std::max(max2, m2[t]); }
     }
-    int rc = ensure_staging(c, 0, 0, 0, std::min<uint64_t>(n, KJ_CHUNK_READS)); if (rc) return rc;
+    uint64_t chunk_reads = KJ_CHUNK_READS;
+    if (const char* v = getenv("KJ_CHUNK_READS")) { long x = atol(v); if (x >= 1024 && x <= (1 << 24)) chunk_reads = (uint64_t)x; }       // tuning hook
+    int rc = ensure_staging(c, 0, 0, 0, std::min<uint64_t>(n, chunk_reads)); if (rc) return rc;
     if (ids_out && c->d_ids_cap < c->d_reads_cap) {
         for (int s = 0; s < 2; s++) {
             if (c->d_ids[s]) cudaFree(c->d_ids[s]); if (c->d_nids[s]) cudaFree(c->d_nids[s]); c->d_ids[s] = nullptr; c->d_nids[s] = nullptr;
@@ -382,7 +384,7 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
     // software pipeline over chunks: H2D + kernel + D2H of chunk k on stream k&1 overlap with chunk k+1
     for (uint64_t start = 0, k = 0, cnt = 0; start < n; start += cnt, k++) {
         const int s = (int)(k & 1); cudaStream_t st = c->stream[s];
-        cnt = std::min<uint64_t>(KJ_CHUNK_READS, n - start);
+        cnt = std::min<uint64_t>(chunk_reads, n - start);
         // long reads: bound the bases per chunk as well (at least one read)
         {
             const uint64_t* e1p = std::upper_bound(off1 + start + 1, off1 + start + cnt + 1, off1[start] + KJ_CHUNK_BYTES);
