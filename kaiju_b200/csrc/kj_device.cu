@@ -8,6 +8,7 @@
 // There is no CPU fallback: without a GPU kj_create() fails with KJ_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,7 +45,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
                    uint64_t base1, uint64_t base2, uint64_t n_reads,
                    uint64_t* __restrict__ taxon_out, uint32_t* __restrict__ best_out, uint64_t* __restrict__ ids_out, uint8_t* __restrict__ nids_out,
                    unsigned long long* __restrict__ counter, KjKept* __restrict__ spill, uint8_t* __restrict__ gscratch,
-                   uint32_t gscratch_bytes, uint8_t* __restrict__ gws, uint32_t* __restrict__ err) {
+                   uint32_t gscratch_bytes, uint8_t* __restrict__ gws, unsigned long long* __restrict__ counts, uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     KjCtaShared* sh = (KjCtaShared*)smem_raw;
     {   // stage the index descriptor (C[] etc.) and the small tables once per CTA
@@ -86,6 +87,8 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
             if (cx.w.lane == 0) {
                 taxon_out[r] = id;
                 if (best_out) best_out[r] = id ? best : 0u;
+                // per-taxon read counts (kaiju2table's first pass), fused: a separate counting kernel behind a persistent grid would stall the chunk pipeline
+                if (counts) atomicAdd(counts + (id ? t : sh->ix.n_tax), 1ull);
             }
             if (ids_out) {   // column 5 of the reference's -v output: the match-id set in ascending order (std::set), classified reads only
                 const uint32_t nids = id ? cx.nids : 0u; const uint32_t* ids = (const uint32_t*)(cx.smem + cx.L.ids_off);
@@ -273,7 +276,7 @@ extern "C" void kj_destroy(kj_ctx* c) {
 // one launch over reads [0,n) whose sequences/offsets are resident on the device
 static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_off1, const uint8_t* d_seq2, const uint64_t* d_off2, uint64_t base1, uint64_t base2,
                   uint64_t n, uint32_t max1, uint32_t max2, uint64_t* d_tax, uint32_t* d_best, cudaStream_t st, bool time_it,
-                  uint64_t* d_ids = nullptr, uint8_t* d_nids = nullptr) {
+                  uint64_t* d_ids = nullptr, uint8_t* d_nids = nullptr, unsigned long long* d_count_dst = nullptr) {
     if (c->params.input_is_protein) {
         if (d_seq2) { kj_err() = "protein input only supports one input (kaiju.cpp:201)"; return KJ_ERR_ARG; }
         if (max1 > KJ_MAX_PROTEIN_LEN) { kj_err() = "protein read longer than KJ_MAX_PROTEIN_LEN (5461 residues) is not supported"; return KJ_ERR_UNSUPPORTED; }
@@ -291,7 +294,7 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
 #define KJ_LAUNCH3(M, T, G) kj_classify_kernel<M, T, G><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, \
             c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
             c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), \
-            rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, c->d_err)
+            rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err)
     if (rp.mode == 0) { if (c->H.wide) KJ_LAUNCH(0, uint64_t); else KJ_LAUNCH(0, uint32_t); }
     else { if (c->H.wide) KJ_LAUNCH(1, uint64_t); else KJ_LAUNCH(1, uint32_t); }
 #undef KJ_LAUNCH
@@ -371,6 +374,7 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
         for (auto& x : th) x.join();
         for (unsigned t = 0; t < nthr; t++) { max1 = std::max(max1, m1[t]); max2 = std::max(max2, m2[t]); }
     }
+    CK(cudaMemset(c->d_counts_pending, 0, (size_t)c->n_counts * 8));                // counts of this call: committed only if the whole call succeeds
     uint64_t chunk_reads = KJ_CHUNK_READS;
     if (const char* v = getenv("KJ_CHUNK_READS")) { long x = atol(v); if (x >= 1024 && x <= (1 << 24)) chunk_reads = (uint64_t)x; }       // tuning hook
     int rc = ensure_staging(c, 0, 0, 0, std::min<uint64_t>(n, chunk_reads)); if (rc) return rc;
@@ -382,6 +386,9 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
         c->d_ids_cap = c->d_reads_cap;
     }
     // software pipeline over chunks: H2D + kernel + D2H of chunk k on stream k&1 overlap with chunk k+1
+    const bool trace = getenv("KJ_TRACE") != nullptr;            // developer hook: per-chunk timeline on stderr
+    struct Tr { cudaEvent_t e[4]; double host_ms; uint64_t cnt; }; std::vector<Tr> tr; cudaEvent_t tr0 = nullptr; const auto th0 = std::chrono::steady_clock::now();
+    if (trace) { cudaEventCreate(&tr0); cudaEventRecord(tr0, c->stream[0]); }
     for (uint64_t start = 0, k = 0, cnt = 0; start < n; start += cnt, k++) {
         const int s = (int)(k & 1); cudaStream_t st = c->stream[s];
         cnt = std::min<uint64_t>(chunk_reads, n - start);
@@ -393,6 +400,7 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
             cnt = std::min(cnt, lim);
         }
         CK(cudaStreamSynchronize(st));                      // slot s free again (its previous D2H has landed)
+        if (trace) { Tr t; for (auto& e : t.e) cudaEventCreate(&e); t.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count(); t.cnt = 0; tr.push_back(t); cudaEventRecord(tr.back().e[0], st); }
         const uint64_t b1 = off1[start], e1 = off1[start + cnt], b2 = paired ? off2[start] : 0, e2 = paired ? off2[start + cnt] : 0;
         rc = ensure_staging(c, s, (size_t)(e1 - b1), (size_t)(e2 - b2), c->d_reads_cap); if (rc) return rc;
         CK(cudaMemcpyAsync(c->d_seq[s][0], seq1 + b1, (size_t)(e1 - b1), cudaMemcpyHostToDevice, st));
@@ -401,10 +409,11 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
             CK(cudaMemcpyAsync(c->d_seq[s][1], seq2 + b2, (size_t)(e2 - b2), cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(c->d_off[s][1], off2 + start, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         }
+        if (trace) { tr.back().cnt = cnt; cudaEventRecord(tr.back().e[1], st); }
         rc = launch(c, s, c->d_seq[s][0], c->d_off[s][0], paired ? c->d_seq[s][1] : nullptr, paired ? c->d_off[s][1] : nullptr, b1, b2, cnt, max1, max2,
-                    c->d_tax[s], best_out ? c->d_best[s] : nullptr, st, false, ids_out ? c->d_ids[s] : nullptr, ids_out ? c->d_nids[s] : nullptr);
+                    c->d_tax[s], best_out ? c->d_best[s] : nullptr, st, true, ids_out ? c->d_ids[s] : nullptr, ids_out ? c->d_nids[s] : nullptr, c->d_counts_pending);
         if (rc) return rc;
-        if ((rc = count_taxa(c, c->d_tax[s], cnt, c->d_counts_pending, st))) return rc;
+        if (trace) cudaEventRecord(tr.back().e[2], st);
         CK(cudaMemcpyAsync(taxon_out + start, c->d_tax[s], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         if (best_out) CK(cudaMemcpyAsync(best_out + start, c->d_best[s], cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (ids_out) {
@@ -412,7 +421,14 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
             CK(cudaMemcpyAsync(nids_out + start, c->d_nids[s], cnt, cudaMemcpyDeviceToHost, st));
         }
     }
+    if (trace && !tr.empty()) cudaEventRecord(tr.back().e[3], c->stream[(tr.size() - 1) & 1]);
     CK(cudaStreamSynchronize(c->stream[0])); CK(cudaStreamSynchronize(c->stream[1]));
+    if (trace) {
+        fprintf(stderr, "KJ_TRACE chunk reads host_issue_ms h2d_start h2d_end kernel_end (ms since call start, device)\n");
+        for (size_t k = 0; k < tr.size(); k++) { float a = 0, b = 0, d = 0; cudaEventElapsedTime(&a, tr0, tr[k].e[0]); cudaEventElapsedTime(&b, tr0, tr[k].e[1]); cudaEventElapsedTime(&d, tr0, tr[k].e[2]);
+            fprintf(stderr, "KJ_TRACE %zu %llu %.2f %.2f %.2f %.2f\n", k, (unsigned long long)tr[k].cnt, tr[k].host_ms, a, b, d); }
+        fprintf(stderr, "KJ_TRACE end host %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - th0).count());
+    }
     rc = check_err_flag(c);
     // the per-taxon counts of this call become visible only if the whole call succeeded (a repeated call must not count twice)
     if (rc) { CK(cudaMemset(c->d_counts_pending, 0, (size_t)c->n_counts * 8)); return rc; }

@@ -400,6 +400,7 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
     if ((rc = S.totals.need(64))) return rc;
     uint64_t n_reads = 0; unsigned long long n_class = 0;
     CK(cudaMemsetAsync(S.totals.p, 0, 64, st));
+    CK(cudaMemsetAsync(c->d_counts_pending, 0, (size_t)c->n_counts * 8, st));
     unsigned long long* d_nclass = (unsigned long long*)((char*)S.totals.p + 16);
     for (int f = 0; f < S.nfiles; f++) if ((rc = kj_prefetch(c, S, f))) return rc;
     for (;;) {
@@ -442,7 +443,7 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
                 if (paired) kj_maxlen_kernel<<<256, 256, 0, st>>>(S.side[1].off.as<uint64_t>(), n, c->d_maxlen + 1);
                 unsigned int h[2] = {0, 0}; CK(cudaMemcpyAsync(h, c->d_maxlen, sizeof h, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
                 rc = launch(c, 0, S.side[0].seq.as<uint8_t>(), S.side[0].off.as<uint64_t>(), paired ? S.side[1].seq.as<uint8_t>() : nullptr, paired ? S.side[1].off.as<uint64_t>() : nullptr, 0, 0, n, h[0], h[1],
-                            S.tax.as<uint64_t>(), S.best.as<uint32_t>(), st, false, verbose ? S.ids.as<uint64_t>() : nullptr, verbose ? S.nids.as<uint8_t>() : nullptr);
+                            S.tax.as<uint64_t>(), S.best.as<uint32_t>(), st, false, verbose ? S.ids.as<uint64_t>() : nullptr, verbose ? S.nids.as<uint8_t>() : nullptr, c->d_counts_pending);
                 if (rc) return rc;
                 CK(cudaStreamSynchronize(st));
                 uint32_t e = 0; CK(cudaMemcpy(&e, c->d_err, sizeof e, cudaMemcpyDeviceToHost));
@@ -450,11 +451,12 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
                 if (e & 32u) { CK(cudaMemset(c->d_err, 0, 4)); kj_err() = "Read names are not identical between the two input files. Probably reads are not in the same order in both files."; return KJ_ERR_IO; }
                 const uint32_t boost = c->variant_boost;
                 rc = check_err_flag(c);
+                if (rc) CK(cudaMemsetAsync(c->d_counts_pending, 0, (size_t)c->n_counts * 8, st));     // a failed launch does not count
                 if (rc == KJ_ERR_OVERFLOW && c->variant_boost != boost) continue;
                 if (rc) return rc;
                 break;
             }
-            if ((rc = count_taxa(c, S.tax.as<uint64_t>(), n, c->d_counts, st))) return rc;          // this chunk succeeded: its reads join the per-taxon counts
+            kj_count_commit<<<c->sm_count, 256, 0, st>>>(c->d_counts, c->d_counts_pending, c->n_counts); c->launches++;     // this chunk succeeded: its reads join the per-taxon counts
             kj_fmt_len<<<c->sm_count * 4, 256, 0, st>>>(S.tax.as<uint64_t>(), S.best.as<uint32_t>(), S.ids.as<uint64_t>(), S.nids.as<uint8_t>(), S.side[0].name_off.as<uint32_t>(), n, verbose, S.len.as<uint32_t>(), d_nclass);
             if ((rc = kj_scan_u32(S.len.as<uint32_t>(), n + 1, S.scan_tmp, (uint32_t*)S.totals.p, st))) return rc;
             uint32_t out_bytes = 0; CK(cudaMemcpyAsync(&out_bytes, S.totals.p, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
