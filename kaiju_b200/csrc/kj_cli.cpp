@@ -60,6 +60,13 @@ int main(int argc, char** argv) {
     const bool paired = !in2.empty();
     if (paired && P.input_is_protein) { fprintf(stderr, "Error: Protein input only supports one input file.\n\n"); usage(argv[0]); }      // kaiju.cpp:201
 
+    auto split = [](const std::string& v) { std::vector<std::string> out; size_t b = 0; while (b <= v.size()) { size_t e = v.find(',', b); if (e == std::string::npos) e = v.size(); if (e > b) out.push_back(v.substr(b, e - b)); b = e + 1; } return out; };
+    const std::vector<std::string> l1 = split(in1), l2 = split(in2), lo = split(out_fn);
+    if (l1.empty()) die("Please specify the location of the input file, using the -i option.");
+    if (paired && l2.size() != l1.size()) die("Length of input file lists differ");                      // kaiju-multi.cpp:255-258
+    if (!lo.empty() && lo.size() != l1.size()) die("Length of input and output file lists differ");
+    if (lo.empty() && l1.size() > 1) die("Several input files need a list of output files (-o)");
+
     kj_fmi* fmi = nullptr; kj_nodes* nodes = nullptr; kj_ctx* ctx = nullptr;
     if (kj_nodes_load(nodes_fn.c_str(), &nodes) != KJ_OK) die(kj_last_error());
     if (kj_fmi_load(fmi_fn.c_str(), &fmi) != KJ_OK) die(kj_last_error());
@@ -67,12 +74,15 @@ int main(int argc, char** argv) {
     if (kj_create(&ctx, device, &P, &iv, &tv) != KJ_OK) die(kj_last_error());
     kj_fmi_free(fmi); kj_nodes_free(nodes);
 
-    // parsing, classification and output formatting all run on the device; the host moves bytes (kj_ingest.h)
-    uint64_t n_reads = 0, n_classified = 0;
-    const auto t0 = std::chrono::steady_clock::now();
-    if (kj_classify_files(ctx, in1.c_str(), paired ? in2.c_str() : nullptr, out_fn.empty() ? nullptr : out_fn.c_str(), verbose ? 1 : 0, &n_reads, &n_classified) != KJ_OK) die(kj_last_error());
-    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (verbose || getenv("KJ_CLI_TIMING")) fprintf(stderr, "%llu reads, %llu classified, %.4f s from the first byte read to the last byte written\n", (unsigned long long)n_reads, (unsigned long long)n_classified, secs);
+    // parsing, classification and output formatting all run on the device; the host moves bytes (kj_ingest.h).
+    // Comma-separated lists for -i / -j / -o process several data sets against the index loaded once (kaiju-multi.cpp:220-330).
+    for (size_t k = 0; k < l1.size(); k++) {
+        uint64_t n_reads = 0, n_classified = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (kj_classify_files(ctx, l1[k].c_str(), paired ? l2[k].c_str() : nullptr, lo.empty() ? nullptr : lo[k].c_str(), verbose ? 1 : 0, &n_reads, &n_classified) != KJ_OK) die(kj_last_error());
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (verbose || getenv("KJ_CLI_TIMING")) fprintf(stderr, "%s: %llu reads, %llu classified, %.4f s from the first byte read to the last byte written\n", l1[k].c_str(), (unsigned long long)n_reads, (unsigned long long)n_classified, secs);
+    }
     kj_destroy(ctx);
     return EXIT_SUCCESS;
 }

@@ -269,6 +269,11 @@ def test_cli_protein_and_verbose_columns(kb, golden, tmp_path):
         t, b, ids = orc.classify_one(P, s[int(o[i]):int(o[i + 1])].tobytes())
         exp = "C\tq%d\t%d\t%d\t%s" % (i, t, b, "".join("%d," % x for x in sorted(ids))) if t else "U\tq%d\t0" % i
         assert line == exp, (i, line, exp)
+    # kaiju-multi style: comma-separated lists of inputs and outputs against the index loaded once
+    oa, ob = tmp_path / "a.tsv", tmp_path / "b.tsv"
+    subprocess.run([os.path.join(ROOT, "kaiju_b200", "kaiju-b200"), "-t", golden.nodes, "-f", golden.fmi, "-i", "%s,%s" % (fa, fa), "-o", "%s,%s" % (oa, ob),
+                    "-p", "-v", "-a", "greedy", "-e", "2"], check=True, stderr=subprocess.DEVNULL)
+    assert open(oa).read().splitlines() == out and open(ob).read().splitlines() == out
 
 
 def _expected_lines(orc, P, names, seqs1, seqs2=None, verbose=False):
