@@ -90,6 +90,12 @@ void kj_nodes_free(kj_nodes *t);
 /* --- context --- */
 /* Transcodes the index into the device layout, uploads it and the taxonomy to HBM of `device`. */
 int kj_create(kj_ctx **out, int device, const kj_params *params, const kj_index_view *index, const kj_taxonomy_view *taxonomy);
+/* Device-native index file: kj_native_index_write() transcodes once (the .fmi + nodes.dmp views as for kj_create) and
+ * stores the arrays exactly as they are uploaded (one-hot rank records, packed letters, taxon-reduced suffix array, re-indexed
+ * taxonomy, k-mer table); kj_create_from_native() then needs one sequential read and the upload -- no transcode at load time.
+ * The file is specific to this library version (checked; KJ_ERR_IO otherwise). */
+int kj_native_index_write(const kj_index_view *index, const kj_taxonomy_view *taxonomy, const char *path);
+int kj_create_from_native(kj_ctx **out, int device, const kj_params *params, const char *path);
 /* Change the run parameters of an existing context (index stays resident). */
 int kj_set_params(kj_ctx *ctx, const kj_params *params);
 void kj_destroy(kj_ctx *ctx);

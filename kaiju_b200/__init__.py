@@ -57,6 +57,8 @@ def lib():
         L.kj_nodes_view.argtypes = [C.c_void_p, C.POINTER(KjTaxonomyView)]
         L.kj_nodes_free.argtypes = [C.c_void_p]
         L.kj_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(KjParams), C.POINTER(KjIndexView), C.POINTER(KjTaxonomyView)]
+        L.kj_native_index_write.argtypes = [C.POINTER(KjIndexView), C.POINTER(KjTaxonomyView), C.c_char_p]
+        L.kj_create_from_native.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(KjParams), C.c_char_p]
         L.kj_set_params.argtypes = [C.c_void_p, C.POINTER(KjParams)]
         L.kj_destroy.argtypes = [C.c_void_p]
         L.kj_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -93,12 +95,33 @@ def make_params(mode="mem", m=11, e=3, s=65, seed=7, E=0.01, seg=True, use_evalu
                     use_evalue=1 if (use_evalue and greedy) else 0, min_evalue=E, seg=1 if seg else 0, input_is_protein=1 if protein else 0)
 
 
+def write_native_index(fmi_path, nodes_path, out_path):
+    """Transcode a reference .fmi + nodes.dmp once into the device-native index file (no GPU needed)."""
+    L = lib(); fmi = C.c_void_p(); nodes = C.c_void_p()
+    _check(L.kj_fmi_load(fmi_path.encode(), C.byref(fmi)))
+    try:
+        _check(L.kj_nodes_load(nodes_path.encode(), C.byref(nodes)))
+        try:
+            iv = KjIndexView(); tv = KjTaxonomyView(); L.kj_fmi_view(fmi, C.byref(iv)); L.kj_nodes_view(nodes, C.byref(tv))
+            _check(L.kj_native_index_write(C.byref(iv), C.byref(tv), out_path.encode()))
+        finally:
+            L.kj_nodes_free(nodes)
+    finally:
+        L.kj_fmi_free(fmi)
+
+
 class Classifier:
-    """One GPU context: the .fmi index and nodes.dmp taxonomy resident in HBM + run parameters."""
+    """One GPU context: the .fmi index and nodes.dmp taxonomy resident in HBM + run parameters.
+    `Classifier(native_path, None)` loads a device-native index file written by write_native_index()."""
 
     def __init__(self, fmi_path, nodes_path, device=0, params=None, **kw):
         L = lib()
         self._ctx = C.c_void_p()
+        if nodes_path is None:
+            self.params = params if params is not None else make_params(**kw)
+            _check(L.kj_create_from_native(C.byref(self._ctx), device, C.byref(self.params), fmi_path.encode()))
+            self.device = device; self.bwtlen = self.nseq = None
+            return
         fmi = C.c_void_p(); nodes = C.c_void_p()
         _check(L.kj_fmi_load(fmi_path.encode(), C.byref(fmi)))
         try:

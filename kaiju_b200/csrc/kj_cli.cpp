@@ -23,14 +23,14 @@ static void usage(const char* prog) {
                     "   -z INT        accepted for compatibility (ignored: the GPU replaces the worker threads)\n   -a STRING     Run mode, either \"mem\"  or \"greedy\" (default: greedy)\n"
                     "   -e INT        Number of mismatches allowed in Greedy mode (default: 3)\n   -m INT        Minimum match length (default: 11)\n   -s INT        Minimum match score in Greedy mode (default: 65)\n"
                     "   -E FLOAT      Minimum E-value in Greedy mode (default: 0.01)\n   -x            Enable SEG low complexity filter (enabled by default)\n   -X            Disable SEG low complexity filter\n"
-                    "   -p            Input sequences are protein sequences\n   -v            Enable verbose output (adds the match length/score and the matching taxon ids)\n   -d INT        CUDA device ordinal (default 0)\n", prog);
+                    "   -w FILENAME   Write the device-native index file for -t/-f and exit; such a file can then be given as -f (no -t needed, no transcode at start-up)\n   -p            Input sequences are protein sequences\n   -v            Enable verbose output (adds the match length/score and the matching taxon ids)\n   -d INT        CUDA device ordinal (default 0)\n", prog);
     exit(EXIT_FAILURE);
 }
 
 int main(int argc, char** argv) {
     kj_params P; P.mode = 1; P.min_fragment_length = 11; P.mismatches = 3; P.min_score = 65; P.seed_length = 7; P.use_evalue = 1; P.min_evalue = 0.01; P.seg = 1; P.input_is_protein = 0;
-    std::string nodes_fn, fmi_fn, in1, in2, out_fn; bool verbose = false; int device = 0; int c;
-    while ((c = getopt(argc, argv, "a:hd:pxXvn:m:e:E:l:t:f:i:j:s:z:o:")) != -1) {
+    std::string nodes_fn, fmi_fn, in1, in2, out_fn, native_out; bool verbose = false; int device = 0; int c;
+    while ((c = getopt(argc, argv, "a:hd:pxXvn:m:e:E:l:t:f:i:j:s:z:o:w:")) != -1) {
         switch (c) {
             case 'a': if (!strcmp(optarg, "mem")) { P.mode = 0; P.use_evalue = 0; } else if (!strcmp(optarg, "greedy")) P.mode = 1; else { fprintf(stderr, "-a must be a valid mode.\n"); usage(argv[0]); } break;
             case 'h': usage(argv[0]); break;
@@ -40,6 +40,7 @@ int main(int argc, char** argv) {
             case 'x': P.seg = 1; break;
             case 'X': P.seg = 0; break;
             case 'o': out_fn = optarg; break;
+            case 'w': native_out = optarg; break;
             case 'f': fmi_fn = optarg; break;
             case 't': nodes_fn = optarg; break;
             case 'i': in1 = optarg; break;
@@ -54,8 +55,20 @@ int main(int argc, char** argv) {
             default: usage(argv[0]);
         }
     }
-    if (nodes_fn.empty()) { fprintf(stderr, "Error: Please specify the location of the nodes.dmp file, using the -t option.\n\n"); usage(argv[0]); }
     if (fmi_fn.empty()) { fprintf(stderr, "Error: Please specify the location of the FMI file, using the -f option.\n\n"); usage(argv[0]); }
+    // -f may name a device-native index file (written with -w): it holds the taxonomy too, so -t is not needed then
+    bool native_in = false;
+    { FILE* f = fopen(fmi_fn.c_str(), "rb"); char m[8] = {0}; if (f) { native_in = fread(m, 1, 8, f) == 8 && memcmp(m, "KJB200IX", 8) == 0; fclose(f); } }
+    if (nodes_fn.empty() && !native_in) { fprintf(stderr, "Error: Please specify the location of the nodes.dmp file, using the -t option.\n\n"); usage(argv[0]); }
+    if (!native_out.empty()) {              // -w FILE: transcode .fmi + nodes.dmp into the device-native index file and exit (no GPU needed)
+        if (native_in) die("-w needs the reference's .fmi as -f");
+        kj_fmi* fmi = nullptr; kj_nodes* nodes = nullptr;
+        if (kj_nodes_load(nodes_fn.c_str(), &nodes) != KJ_OK || kj_fmi_load(fmi_fn.c_str(), &fmi) != KJ_OK) die(kj_last_error());
+        kj_index_view iv; kj_taxonomy_view tv; kj_fmi_view(fmi, &iv); kj_nodes_view(nodes, &tv);
+        if (kj_native_index_write(&iv, &tv, native_out.c_str()) != KJ_OK) die(kj_last_error());
+        kj_fmi_free(fmi); kj_nodes_free(nodes);
+        return EXIT_SUCCESS;
+    }
     if (in1.empty()) { fprintf(stderr, "Error: Please specify the location of the input file, using the -i option.\n\n"); usage(argv[0]); }
     const bool paired = !in2.empty();
     if (paired && P.input_is_protein) { fprintf(stderr, "Error: Protein input only supports one input file.\n\n"); usage(argv[0]); }      // kaiju.cpp:201
@@ -68,11 +81,14 @@ int main(int argc, char** argv) {
     if (lo.empty() && l1.size() > 1) die("Several input files need a list of output files (-o)");
 
     kj_fmi* fmi = nullptr; kj_nodes* nodes = nullptr; kj_ctx* ctx = nullptr;
-    if (kj_nodes_load(nodes_fn.c_str(), &nodes) != KJ_OK) die(kj_last_error());
-    if (kj_fmi_load(fmi_fn.c_str(), &fmi) != KJ_OK) die(kj_last_error());
-    kj_index_view iv; kj_taxonomy_view tv; kj_fmi_view(fmi, &iv); kj_nodes_view(nodes, &tv);
-    if (kj_create(&ctx, device, &P, &iv, &tv) != KJ_OK) die(kj_last_error());
-    kj_fmi_free(fmi); kj_nodes_free(nodes);
+    if (native_in) { if (kj_create_from_native(&ctx, device, &P, fmi_fn.c_str()) != KJ_OK) die(kj_last_error()); }
+    else {
+        if (kj_nodes_load(nodes_fn.c_str(), &nodes) != KJ_OK) die(kj_last_error());
+        if (kj_fmi_load(fmi_fn.c_str(), &fmi) != KJ_OK) die(kj_last_error());
+        kj_index_view iv; kj_taxonomy_view tv; kj_fmi_view(fmi, &iv); kj_nodes_view(nodes, &tv);
+        if (kj_create(&ctx, device, &P, &iv, &tv) != KJ_OK) die(kj_last_error());
+        kj_fmi_free(fmi); kj_nodes_free(nodes);
+    }
 
     // parsing, classification and output formatting all run on the device; the host moves bytes (kj_ingest.h).
     // Comma-separated lists for -i / -j / -o process several data sets against the index loaded once (kaiju-multi.cpp:220-330).

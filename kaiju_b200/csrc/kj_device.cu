@@ -213,8 +213,8 @@ static int upload_evalue_breaks(kj_ctx* c) {
     return KJ_OK;
 }
 
-extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, const kj_index_view* index, const kj_taxonomy_view* taxonomy) {
-    if (!out || !params || !index || !taxonomy) { kj_err() = "kj_create: null argument"; return KJ_ERR_ARG; }
+// common part of kj_create / kj_create_from_native: `fill` produces the host arrays of the device layout, the rest uploads them
+template <class Fill> static int create_ctx(kj_ctx** out, int device, const kj_params* params, Fill fill) {
     int rc = kj_check_params(*params); if (rc) return rc;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { kj_err() = "no CUDA device available (this library has no CPU fallback)"; return KJ_ERR_NO_DEVICE; }
@@ -223,7 +223,7 @@ extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, cons
     kj_ctx* c = new kj_ctx(); c->device = device; c->params = *params;
     std::unique_ptr<kj_ctx, void (*)(kj_ctx*)> guard(c, kj_destroy);      // every early return below releases what was allocated so far
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); c->sm_count = prop.multiProcessorCount;
-    rc = kj_build_host_index(*index, *taxonomy, c->H); if (rc) return rc;
+    rc = fill(c->H); if (rc) return rc;
     KjHostIndex& H = c->H; uint64_t tot = 0;
     if ((rc = upload(H.rank, &c->d_rank, tot)) || (rc = upload(H.letters, &c->d_letters, tot)) || (rc = upload(H.sa_tax, &c->d_sa_tax, tot)) ||
         (rc = upload(H.seq_tax, &c->d_seq_tax, tot)) || (rc = upload(H.tax_parent, &c->d_tax_parent, tot)) || (rc = upload(H.tax_depth, &c->d_tax_depth, tot)) ||
@@ -250,6 +250,21 @@ extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, cons
     CK(cudaMalloc((void**)&c->d_counts, (size_t)c->n_counts * 8)); CK(cudaMalloc((void**)&c->d_counts_pending, (size_t)c->n_counts * 8));
     CK(cudaMemset(c->d_counts, 0, (size_t)c->n_counts * 8)); CK(cudaMemset(c->d_counts_pending, 0, (size_t)c->n_counts * 8));
     *out = guard.release(); return KJ_OK;
+}
+
+extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, const kj_index_view* index, const kj_taxonomy_view* taxonomy) {
+    if (!out || !params || !index || !taxonomy) { kj_err() = "kj_create: null argument"; return KJ_ERR_ARG; }
+    return create_ctx(out, device, params, [&](KjHostIndex& H) { return kj_build_host_index(*index, *taxonomy, H); });
+}
+// device-native index file: written once from the reference's .fmi + nodes.dmp, loaded without the transcode
+extern "C" int kj_native_index_write(const kj_index_view* index, const kj_taxonomy_view* taxonomy, const char* path) {
+    if (!index || !taxonomy || !path) { kj_err() = "kj_native_index_write: null argument"; return KJ_ERR_ARG; }
+    KjHostIndex H; int rc = kj_build_host_index(*index, *taxonomy, H); if (rc) return rc;
+    return kj_host_index_write(H, path);
+}
+extern "C" int kj_create_from_native(kj_ctx** out, int device, const kj_params* params, const char* path) {
+    if (!out || !params || !path) { kj_err() = "kj_create_from_native: null argument"; return KJ_ERR_ARG; }
+    return create_ctx(out, device, params, [&](KjHostIndex& H) { return kj_host_index_read(path, H); });
 }
 
 extern "C" int kj_set_params(kj_ctx* c, const kj_params* p) {

@@ -365,3 +365,54 @@ void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp) {
     rp.variant_cap = rp.max_len <= 512 ? 256u : 4096u;
     if (const char* v = getenv("KJ_VARIANT_CAP")) { long x = atol(v); if (x >= 32 && x <= (1 << 20)) rp.variant_cap = (uint32_t)x; }   // test hook: provoke the overflow/retry path
 }
+
+// ------------------------------------------------------------------------------------------------
+// device-native index file: "KJB200IX" | version | fixed header | raw arrays in upload order.  Little-endian, host layout of
+// this build (the version changes with any layout change); replaces the load-time transcode of large indexes (mkfmi.c:63-78
+// writes the reference's byte-recoded BWT + index1/index2; this file holds the one-hot rank records etc. of kj_layout.h).
+// ------------------------------------------------------------------------------------------------
+namespace {
+const char kNativeMagic[8] = {'K', 'J', 'B', '2', '0', '0', 'I', 'X'};
+const uint32_t kNativeVersion = 1;
+struct NativeHeader {
+    uint32_t version, sizeof_tables, sizeof_rank, alen;
+    uint64_t nb, bwtlen, C[KJ_MAX_ALEN + 1], sa_check; int64_t sa_bias; int32_t sa_exp; uint32_t nseq, n_present; int32_t kmer_k, wide, pad;
+    double db_length;
+    uint64_t n_rank, n_letters, n_sa_tax, n_seq_tax, n_tax, n_lnfact, n_kmer, n_kmer32;
+};
+template <class T> bool put(FILE* f, const std::vector<T>& v) { return v.empty() || fwrite(v.data(), sizeof(T), v.size(), f) == v.size(); }
+template <class T> bool get(FILE* f, std::vector<T>& v, uint64_t n) { v.resize((size_t)n); return n == 0 || fread(v.data(), sizeof(T), (size_t)n, f) == (size_t)n; }
+}  // namespace
+
+int kj_host_index_write(const KjHostIndex& H, const char* path) {
+    FILE* f = fopen(path, "wb"); if (!f) { kj_err() = std::string("Could not open file ") + path + " for writing"; return KJ_ERR_IO; }
+    NativeHeader h; memset(&h, 0, sizeof h);
+    h.version = kNativeVersion; h.sizeof_tables = (uint32_t)sizeof(KjTables); h.sizeof_rank = (uint32_t)sizeof(KjRankBlock); h.alen = (uint32_t)H.alen;
+    h.nb = H.nb; h.bwtlen = H.bwtlen; memcpy(h.C, H.C, sizeof h.C); h.sa_check = H.sa_check; h.sa_bias = H.sa_bias; h.sa_exp = H.sa_exp; h.nseq = H.nseq; h.n_present = H.n_present;
+    h.kmer_k = H.kmer_k; h.wide = H.wide; h.db_length = H.db_length;
+    h.n_rank = H.rank.size(); h.n_letters = H.letters.size(); h.n_sa_tax = H.sa_tax.size(); h.n_seq_tax = H.seq_tax.size(); h.n_tax = H.tax_id.size(); h.n_lnfact = H.lnfact.size();
+    h.n_kmer = H.kmer.size(); h.n_kmer32 = H.kmer32.size();
+    bool ok = fwrite(kNativeMagic, 1, 8, f) == 8 && fwrite(&h, sizeof h, 1, f) == 1 && fwrite(&H.tables, sizeof(KjTables), 1, f) == 1 &&
+              put(f, H.rank) && put(f, H.letters) && put(f, H.sa_tax) && put(f, H.seq_tax) && put(f, H.tax_parent) && put(f, H.tax_depth) && put(f, H.tax_id) &&
+              put(f, H.lnfact) && put(f, H.kmer) && put(f, H.kmer32);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { kj_err() = std::string("write error on ") + path; return KJ_ERR_IO; }
+    return KJ_OK;
+}
+
+int kj_host_index_read(const char* path, KjHostIndex& H) {
+    FILE* f = fopen(path, "rb"); if (!f) { kj_err() = std::string("Could not open file ") + path; return KJ_ERR_IO; }
+    char magic[8]; NativeHeader h;
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, kNativeMagic, 8) == 0 && fread(&h, sizeof h, 1, f) == 1;
+    if (!ok || h.version != kNativeVersion || h.sizeof_tables != sizeof(KjTables) || h.sizeof_rank != sizeof(KjRankBlock) || h.alen < 2 || h.alen > KJ_MAX_ALEN ||
+        h.n_rank != h.nb * h.alen || h.n_lnfact != 10001) { fclose(f); kj_err() = std::string(path) + " is not a device-native index of this library version"; return KJ_ERR_IO; }
+    H = KjHostIndex();
+    H.alen = (int)h.alen; H.nb = h.nb; H.bwtlen = h.bwtlen; memcpy(H.C, h.C, sizeof h.C); H.sa_check = h.sa_check; H.sa_bias = h.sa_bias; H.sa_exp = h.sa_exp; H.nseq = h.nseq; H.n_present = h.n_present;
+    H.kmer_k = h.kmer_k; H.wide = h.wide; H.db_length = h.db_length;
+    ok = fread(&H.tables, sizeof(KjTables), 1, f) == 1 && get(f, H.rank, h.n_rank) && get(f, H.letters, h.n_letters) && get(f, H.sa_tax, h.n_sa_tax) && get(f, H.seq_tax, h.n_seq_tax) &&
+         get(f, H.tax_parent, h.n_tax) && get(f, H.tax_depth, h.n_tax) && get(f, H.tax_id, h.n_tax) && get(f, H.lnfact, h.n_lnfact) && get(f, H.kmer, h.n_kmer) && get(f, H.kmer32, h.n_kmer32);
+    char extra; const bool at_end = fread(&extra, 1, 1, f) == 0;
+    fclose(f);
+    if (!ok || !at_end || h.n_present > h.n_tax) { kj_err() = std::string(path) + " is truncated or corrupt"; return KJ_ERR_IO; }
+    return KJ_OK;
+}

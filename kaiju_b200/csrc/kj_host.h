@@ -34,6 +34,9 @@ std::string& kj_err();             // thread-local last error text
 int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHostIndex& out);
 // SA intervals of all 20^k k-mers over the 20 residue letters (exactness-preserving shortcut for the first k LF steps)
 void kj_build_kmer_table(KjHostIndex& H, int k);
+// device-native index file: the transcoded arrays as they are uploaded, so that loading is one sequential read
+int kj_host_index_write(const KjHostIndex& H, const char* path);
+int kj_host_index_read(const char* path, KjHostIndex& H);
 int kj_check_params(const kj_params& p);
 // E-value gate (ConsumerThread.cpp:500-513) as the minimal passing integer score per (len1,len2)
 int kj_build_evalue_breaks(const kj_params& p, double db_length, std::vector<double>& breaks);

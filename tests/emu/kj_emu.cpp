@@ -152,6 +152,23 @@ void* kjemu_create(const char* fmi_path, const char* nodes_path, const kj_params
 }
 void kjemu_destroy(void* h) { delete (EmuCtx*)h; }
 
+// device-native index file: write the transcoded index of (fmi, nodes), read it back, compare every field.  0 = identical.
+int kjemu_native_roundtrip(const char* fmi_path, const char* nodes_path, const char* out_path) {
+    kj_fmi* f = nullptr; kj_nodes* t = nullptr;
+    if (kj_fmi_load(fmi_path, &f) != KJ_OK || kj_nodes_load(nodes_path, &t) != KJ_OK) return -1;
+    kj_index_view iv; kj_taxonomy_view tv; kj_fmi_view(f, &iv); kj_nodes_view(t, &tv);
+    KjHostIndex A, B; int rc = kj_build_host_index(iv, tv, A); kj_fmi_free(f); kj_nodes_free(t);
+    if (rc || kj_host_index_write(A, out_path) != KJ_OK || kj_host_index_read(out_path, B) != KJ_OK) { fprintf(stderr, "kjemu: %s\n", kj_last_error()); return -2; }
+    auto same = [](const auto& x, const auto& y) { return x.size() == y.size() && (x.empty() || memcmp(x.data(), y.data(), x.size() * sizeof(x[0])) == 0); };
+    bool ok = same(A.rank, B.rank) && same(A.letters, B.letters) && same(A.sa_tax, B.sa_tax) && same(A.seq_tax, B.seq_tax) && same(A.tax_parent, B.tax_parent) &&
+              same(A.tax_depth, B.tax_depth) && same(A.tax_id, B.tax_id) && same(A.lnfact, B.lnfact) && same(A.kmer, B.kmer) && same(A.kmer32, B.kmer32) &&
+              A.nb == B.nb && A.bwtlen == B.bwtlen && A.alen == B.alen && memcmp(A.C, B.C, sizeof A.C) == 0 && A.sa_check == B.sa_check && A.sa_exp == B.sa_exp &&
+              A.sa_bias == B.sa_bias && A.nseq == B.nseq && A.n_present == B.n_present && A.kmer_k == B.kmer_k && A.wide == B.wide && A.db_length == B.db_length &&
+              memcmp(&A.tables, &B.tables, sizeof(KjTables)) == 0;
+    return ok ? 0 : 1;
+}
+int kjemu_native_read(const char* path) { KjHostIndex H; return kj_host_index_read(path, H); }
+
 int kjemu_classify(void* h, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
                    uint64_t* taxon_out, uint32_t* best_out, int nthreads) {
     EmuCtx* c = (EmuCtx*)h; bool paired = seq2 != nullptr;

@@ -385,3 +385,29 @@ def test_per_taxon_counts(kb, golden, tmp_path, monkeypatch):
     t, _ = clf.classify(s, o); ids, cnt = clf.counts()
     assert int(cnt.sum()) == 120 and dict(zip(ids.tolist(), cnt.tolist())) == hist(t)
     clf.close()
+
+
+def test_native_index_file(kb, golden, tmp_path):
+    """A context created from the device-native index file classifies exactly like one created from .fmi + nodes.dmp (API and CLI)."""
+    import subprocess
+    from conftest import ROOT
+    native = str(tmp_path / "db.kjb")
+    kb.write_native_index(golden.fmi, golden.nodes, native)
+    names, s1, o1, s2, o2 = golden.reads("pe150")
+    for cfg in ("mem_default", "greedy_default"):
+        clf = kb.Classifier(native, None, device=0, params=kb_params(kb, GOLDEN_CONFIGS[cfg]))
+        tax, best = clf.classify(s1, o1, s2, o2)
+        etax, ebest, _ = golden.expected(cfg, "pe150")
+        assert np.array_equal(tax, etax) and np.array_equal(best, ebest)
+        clf.close()
+    cli = os.path.join(ROOT, "kaiju_b200", "kaiju-b200"); gold = os.path.dirname(golden.fmi)
+    native2 = str(tmp_path / "db2.kjb")
+    subprocess.check_call([cli, "-t", golden.nodes, "-f", golden.fmi, "-w", native2])
+    assert open(native, "rb").read() == open(native2, "rb").read()
+    out = str(tmp_path / "o.tsv")
+    subprocess.check_call([cli, "-f", native2, "-i", os.path.join(gold, "pe150_1.fq.gz"), "-j", os.path.join(gold, "pe150_2.fq.gz"), "-a", "mem", "-o", out])
+    etax, _, _ = golden.expected("mem_default", "pe150")
+    got = [l.split("\t") for l in open(out).read().splitlines()]
+    assert [int(p[2]) for p in got] == [int(t) for t in etax] and [p[1] for p in got] == list(names)
+    with pytest.raises(kb.KaijuError):
+        kb.Classifier(golden.fmi, None, device=0, params=kb.make_params("mem"))        # a reference .fmi is not a native index

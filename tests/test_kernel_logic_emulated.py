@@ -91,3 +91,19 @@ def test_emulated_kernel_reports_variant_ring_overflow(emu, golden, monkeypatch)
     rc, tax, best = emu_classify_rc(emu, golden.fmi, golden.nodes, P, s, o)
     otax, obest = Oracle(golden.fmi, golden.nodes).classify_batch(P, s, o)
     assert rc == 0 and np.array_equal(tax, otax) and np.array_equal(best, obest)
+
+
+def test_native_index_file_roundtrip(emu, golden, tmp_path, monkeypatch):
+    """Device-native index file (kj_native_index_write / kj_create_from_native): every array survives write + read bit for bit,
+    for the 32-bit and the 64-bit interval layouts; truncated or foreign files are refused."""
+    emu.kjemu_native_roundtrip.argtypes = [C.c_char_p] * 3; emu.kjemu_native_read.argtypes = [C.c_char_p]
+    p = str(tmp_path / "db.kjb")
+    assert emu.kjemu_native_roundtrip(golden.fmi.encode(), golden.nodes.encode(), p.encode()) == 0
+    assert os.path.getsize(p) > 1000
+    blob = open(p, "rb").read()
+    open(p + ".trunc", "wb").write(blob[:len(blob) // 2]); open(p + ".long", "wb").write(blob + b"x"); open(p + ".bad", "wb").write(b"NOTANIDX" + blob[8:])
+    for suffix in (".trunc", ".long", ".bad"):
+        assert emu.kjemu_native_read((p + suffix).encode()) != 0
+    assert emu.kjemu_native_read(golden.fmi.encode()) != 0            # a reference .fmi is not a native index
+    monkeypatch.setenv("KJ_FORCE_WIDE", "1")
+    assert emu.kjemu_native_roundtrip(golden.fmi.encode(), golden.nodes.encode(), p.encode()) == 0
