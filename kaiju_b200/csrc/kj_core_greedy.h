@@ -179,13 +179,24 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
             w.sync();
         }
         if (nrec == 0) continue;                                           // "No match for this fragment" (457-462)
+        // class structure of the (usually few) recorded matches as a bit mask: bit t set <=> cls[t] opens a class of equal length
+        const bool small = nrec <= 32u;
+        uint32_t heads = 0, my_ql = 0;
+        if (small) {
+            const bool in = (uint32_t)w.lane < nrec;
+            my_ql = in ? cls[w.lane].ql : 0u;
+            const uint32_t prev_ql = w.shfl(my_ql, w.lane - 1);
+            heads = w.ballot(in && (w.lane == 0 || my_ql != prev_ql));
+        }
 
         // ---------------- substitution variants (465-479 + addAllMismatchVariantsAtPosSI 346-395)
         if (rp.e > 0 && num_mm < rp.e) {
             // walk: class head, then its samelen chain fn..f2 if the class has >1 member (and stop), else the next class head
             uint32_t c0 = 0;
             while (c0 < nrec) {
-                uint32_t c1 = c0 + 1; const uint32_t qlc = cls[c0].ql; while (c1 < nrec && cls[c1].ql == qlc) c1++;
+                uint32_t c1;
+                if (small) { const uint32_t rest = heads & ~((2u << c0) - 1u); c1 = rest ? (uint32_t)kj_ffs(rest) - 1u : nrec; }
+                else { c1 = c0 + 1; const uint32_t qlc = cls[c0].ql; while (c1 < nrec && cls[c1].ql == qlc) c1++; }
                 const uint32_t nmem = c1 - c0;
                 for (uint32_t wi = 0; wi < nmem; wi++) {
                     const KjMatch sm = cls[wi == 0 ? c0 : c1 - wi];
@@ -239,10 +250,37 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
         if (cls[0].ql < rp.m) continue;                                    // "Match ... is too short" (482-488)
 
         // ---------------- eval_match_scores (751-797): [class0: f2..fn][class1: f2..fn]...[heads, last class first]
-        {
+        KjKept* bl = (KjKept*)(cx.smem + cx.L.kept_off);                   // best_matches_SI (<= 20)
+        if (small) {
+            // candidates = the classes with ql >= m, a prefix of cls (sorted by descending length)
+            const uint32_t candmask = w.ballot((uint32_t)w.lane < nrec && my_ql >= rp.m);
+            const uint32_t ncand = (uint32_t)kj_popc(candmask), K = (uint32_t)kj_popc(heads & candmask);
+            // evaluation position of candidate t: non-heads keep their relative order, heads go last in reverse class order
+            const uint32_t t = (uint32_t)w.lane;
+            if (t < ncand) {
+                const KjMatch r = cls[t]; const bool head = (heads >> t) & 1u;
+                const uint32_t cidx = (uint32_t)kj_popc(heads & ((2u << t) - 1u)) - 1u;           // class index of t
+                const uint32_t pos = head ? (ncand - K) + (K - 1u - cidx) : t - (cidx + 1u);
+                int sc = (int)pre[r.qi + r.ql] - (int)pre[r.qi] + diff; if (sc < 0) sc = 0;
+                res[pos].lo = r.lo; res[pos].len = r.len; res[pos].qi = (uint16_t)(sc > 65535 ? 65535 : sc); res[pos].ql = r.ql;
+            }
+            w.sync();
+            // the sequential best-list update of the reference, closed form: the list ends up holding the entries that equal the final
+            // maximum, in evaluation order, as long as fewer than 20 are held (a higher score empties the list first)
+            KjMatch e; e.lo = 0; e.len = 0; e.qi = 0; e.ql = 0; if (t < ncand) e = res[t];
+            const uint32_t sc = t < ncand ? (uint32_t)e.qi : 0u; const bool valid = t < ncand && sc >= rp.min_score;
+            const uint32_t mx = warp_max_u32(w, valid ? sc : 0u);
+            if (mx > 0 && mx >= best) {
+                if (mx > best) { best = mx; nbest = 0; }
+                const uint32_t eq = w.ballot(valid && sc == mx);
+                const uint32_t slot = nbest + (uint32_t)kj_popc(eq & lanemask_lt(w.lane));
+                if (valid && sc == mx && slot < KJ_MAX_BEST_SI) { bl[slot].lo = e.lo; bl[slot].len = e.len; bl[slot].aux = 0; }
+                nbest += (uint32_t)kj_popc(eq); if (nbest > KJ_MAX_BEST_SI) nbest = KJ_MAX_BEST_SI;
+            }
+            w.sync();
+        } else {
             uint32_t K = 0, ncand = 0;                                     // classes with ql >= m, members in them
             { uint32_t c0 = 0; while (c0 < nrec && cls[c0].ql >= rp.m) { uint32_t c1 = c0 + 1; while (c1 < nrec && cls[c1].ql == cls[c0].ql) c1++; K++; ncand = c1; c0 = c1; } }
-            // evaluation position of candidate t (index into cls): non-heads keep their relative order, heads go last in reverse class order
             for (uint32_t b = 0; b < ncand; b += 32) {
                 uint32_t t = b + (uint32_t)w.lane;
                 if (t < ncand) {
@@ -256,7 +294,6 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
                 }
             }
             w.sync();
-            KjKept* bl = (KjKept*)(cx.smem + cx.L.kept_off);               // best_matches_SI (<= 20)
             for (uint32_t t = 0; t < ncand; t++) {
                 const KjMatch r = res[t]; const uint32_t sc = r.qi;
                 if (sc < rp.min_score) continue;
