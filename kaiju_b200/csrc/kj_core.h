@@ -127,7 +127,9 @@ static KJ_DEV IdxT kj_rank(const KjDevIndex& ix, uint32_t c, IdxT k) { return kj
 template <class IdxT>
 static KJ_DEV bool kj_update_si(const KjDevIndex& ix, uint32_t c, IdxT& lo, IdxT& hi) {
     const KjRankBlock* base = kj_letter_base(ix, c);
-    const IdxT nlo = kj_rank_at<IdxT>(base, lo), nhi = kj_rank_at<IdxT>(base, hi);
+    IdxT nlo = kj_rank_at<IdxT>(base, lo), nhi = kj_rank_at<IdxT>(base, hi);
+    // the reference's checkpoint quirk (indexes with bwtlen = m * 2^16 only, kj_host.cpp): the last 129 positions rank lower by a per-letter constant
+    if (hi >= (IdxT)ix.quirk_lo) { const IdxT d = (IdxT)ix.quirk_d[c]; nhi -= d; if (lo >= (IdxT)ix.quirk_lo) nlo -= d; }
     if (nlo >= nhi) return false;
     lo = nlo; hi = nhi; return true;
 }
@@ -139,7 +141,7 @@ static KJ_DEV uint32_t kj_letter(const KjDevIndex& ix, uint64_t k) {
 // get_suffix (bwt.c:105-121) reduced to the taxon of the sequence the suffix lies in
 static KJ_DEV uint32_t kj_sa_taxon(const KjDevIndex& ix, uint64_t k) {
     uint32_t c = 1;
-    while (c != 0 && (k & ix.sa_check)) { c = kj_letter(ix, k); k = kj_rank<uint64_t>(ix, c, k); }
+    while (c != 0 && (k & ix.sa_check)) { c = kj_letter(ix, k); const bool q = k >= ix.quirk_lo; k = kj_rank<uint64_t>(ix, c, k); if (q) k -= ix.quirk_d[c]; }
     if (c != 0) return ix.sa_tax[(uint64_t)((int64_t)(k >> ix.sa_exp) - ix.sa_bias)];
     return ix.seq_tax[k];
 }

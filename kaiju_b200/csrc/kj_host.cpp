@@ -167,6 +167,7 @@ int kj_check_params(const kj_params& p) {
 // ------------------------------------------------------------------------------------------------
 // transcoder: reference in-memory index -> device layout
 // ------------------------------------------------------------------------------------------------
+static inline uint64_t host_rank(const KjHostIndex& H, uint32_t c, uint64_t k);
 int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHostIndex& H) {
     if (!v.bwt || !v.startLcode || !v.alphabet || !v.sa || !v.seq_taxon || v.bwtlen <= 0) { kj_err() = "kj_create: incomplete index view"; return KJ_ERR_ARG; }
     if (v.alen < 2 || v.alen > KJ_MAX_ALEN) { kj_err() = "alphabet size not supported"; return KJ_ERR_UNSUPPORTED; }
@@ -282,6 +283,15 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
         for (auto& x : th) x.join();
         if (bad) { kj_err() = "corrupt suffix array (sequence number out of range)"; return KJ_ERR_IO; }
     }
+    // The reference's checkpoint quirk (fmicommon.h:60-73, 88-89, 114-158; pinned against the reference's own FMindex/get_suffix and CLI in
+    // tests/test_oracle_vs_ref.py::test_bwtlen_multiple_of_65536):
+    // with bwtlen = m * 2^16, m >= 2, positions k >= bwtlen - 128 resolve to the first-level row that holds C[] instead of counts, so
+    // FMindex(c, k) comes out smaller by #c in BWT[0, bwtlen - 2^16).  Reproduced, not fixed: results must equal the reference's.
+    H.quirk_lo = ~0ull; memset(H.quirk_d, 0, sizeof H.quirk_d);
+    if ((n & 65535ull) == 0 && n >= 131072ull) {
+        for (int a = 0; a < alen; a++) H.quirk_d[a] = host_rank(H, (uint32_t)a, n - 65536ull) - H.C[a];
+        H.quirk_lo = n - 128ull;
+    }
     { const char* ek = getenv("KJ_KMER_K"); kj_build_kmer_table(H, ek ? atoi(ek) : 5); }
     // ---- ln(n!) exactly as the reference's literals (blast_seg.c:53-1306 are "%.6f" prints of lgamma)
     H.lnfact.resize(10001);                                             // the reference's table lnfact[0..10000] (blast_seg.c:53-1306)
@@ -295,7 +305,8 @@ static inline uint64_t host_rank(const KjHostIndex& H, uint32_t c, uint64_t k) {
     uint64_t b = k / KJ_RANK_BLOCK; uint32_t r = (uint32_t)(k - b * KJ_RANK_BLOCK); const KjRankBlock& B = H.rank[(size_t)c * H.nb + b];
     uint32_t wi = r >> 6, bit = r & 63u; uint64_t ww = wi == 0 ? B.w0 : (wi == 1 ? B.w1 : B.w2);
     uint64_t add = wi == 0 ? 0 : ((B.hdr >> (32 + 8 * wi)) & 0xff);
-    return (B.hdr & KJ_CNT_MASK) + add + (uint64_t)__builtin_popcountll(ww & ((1ull << bit) - 1ull));
+    const uint64_t v = (B.hdr & KJ_CNT_MASK) + add + (uint64_t)__builtin_popcountll(ww & ((1ull << bit) - 1ull));
+    return k >= H.quirk_lo ? v - H.quirk_d[c] : v;                  // the reference's checkpoint quirk (kj_build_host_index)
 }
 // index = a0*20^(k-1) + a1*20^(k-2) + ... + a(k-1), a_t = letter consumed t-th by the backward search (end of the k-mer first), letters 1..20 -> 0..19
 void kj_build_kmer_table(KjHostIndex& H, int k) {
@@ -373,11 +384,11 @@ void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 const char kNativeMagic[8] = {'K', 'J', 'B', '2', '0', '0', 'I', 'X'};
-const uint32_t kNativeVersion = 1;
+const uint32_t kNativeVersion = 2;
 struct NativeHeader {
     uint32_t version, sizeof_tables, sizeof_rank, alen;
     uint64_t nb, bwtlen, C[KJ_MAX_ALEN + 1], sa_check; int64_t sa_bias; int32_t sa_exp; uint32_t nseq, n_present; int32_t kmer_k, wide, pad;
-    double db_length;
+    double db_length; uint64_t quirk_lo, quirk_d[KJ_MAX_ALEN];
     uint64_t n_rank, n_letters, n_sa_tax, n_seq_tax, n_tax, n_lnfact, n_kmer, n_kmer32;
 };
 template <class T> bool put(FILE* f, const std::vector<T>& v) { return v.empty() || fwrite(v.data(), sizeof(T), v.size(), f) == v.size(); }
@@ -389,7 +400,7 @@ int kj_host_index_write(const KjHostIndex& H, const char* path) {
     NativeHeader h; memset(&h, 0, sizeof h);
     h.version = kNativeVersion; h.sizeof_tables = (uint32_t)sizeof(KjTables); h.sizeof_rank = (uint32_t)sizeof(KjRankBlock); h.alen = (uint32_t)H.alen;
     h.nb = H.nb; h.bwtlen = H.bwtlen; memcpy(h.C, H.C, sizeof h.C); h.sa_check = H.sa_check; h.sa_bias = H.sa_bias; h.sa_exp = H.sa_exp; h.nseq = H.nseq; h.n_present = H.n_present;
-    h.kmer_k = H.kmer_k; h.wide = H.wide; h.db_length = H.db_length;
+    h.kmer_k = H.kmer_k; h.wide = H.wide; h.db_length = H.db_length; h.quirk_lo = H.quirk_lo; memcpy(h.quirk_d, H.quirk_d, sizeof h.quirk_d);
     h.n_rank = H.rank.size(); h.n_letters = H.letters.size(); h.n_sa_tax = H.sa_tax.size(); h.n_seq_tax = H.seq_tax.size(); h.n_tax = H.tax_id.size(); h.n_lnfact = H.lnfact.size();
     h.n_kmer = H.kmer.size(); h.n_kmer32 = H.kmer32.size();
     bool ok = fwrite(kNativeMagic, 1, 8, f) == 8 && fwrite(&h, sizeof h, 1, f) == 1 && fwrite(&H.tables, sizeof(KjTables), 1, f) == 1 &&
@@ -408,7 +419,7 @@ int kj_host_index_read(const char* path, KjHostIndex& H) {
         h.n_rank != h.nb * h.alen || h.n_lnfact != 10001) { fclose(f); kj_err() = std::string(path) + " is not a device-native index of this library version"; return KJ_ERR_IO; }
     H = KjHostIndex();
     H.alen = (int)h.alen; H.nb = h.nb; H.bwtlen = h.bwtlen; memcpy(H.C, h.C, sizeof h.C); H.sa_check = h.sa_check; H.sa_bias = h.sa_bias; H.sa_exp = h.sa_exp; H.nseq = h.nseq; H.n_present = h.n_present;
-    H.kmer_k = h.kmer_k; H.wide = h.wide; H.db_length = h.db_length;
+    H.kmer_k = h.kmer_k; H.wide = h.wide; H.db_length = h.db_length; H.quirk_lo = h.quirk_lo; memcpy(H.quirk_d, h.quirk_d, sizeof h.quirk_d);
     ok = fread(&H.tables, sizeof(KjTables), 1, f) == 1 && get(f, H.rank, h.n_rank) && get(f, H.letters, h.n_letters) && get(f, H.sa_tax, h.n_sa_tax) && get(f, H.seq_tax, h.n_seq_tax) &&
          get(f, H.tax_parent, h.n_tax) && get(f, H.tax_depth, h.n_tax) && get(f, H.tax_id, h.n_tax) && get(f, H.lnfact, h.n_lnfact) && get(f, H.kmer, h.n_kmer) && get(f, H.kmer32, h.n_kmer32);
     char extra; const bool at_end = fread(&extra, 1, 1, f) == 0;

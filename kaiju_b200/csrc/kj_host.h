@@ -28,6 +28,7 @@ struct KjHostIndex {
     std::vector<KjKmer> kmer; std::vector<KjKmer32> kmer32; int kmer_k = 0; int wide = 0;   // k-mer suffix intervals (letters 1..20)
     KjTables tables;
     double db_length = 0;          // bwt.len - bwt.nseq (Config.cpp:20)
+    uint64_t quirk_lo = ~0ull, quirk_d[KJ_MAX_ALEN] = {0};   // the reference's checkpoint quirk for bwtlen = m * 2^16, m >= 2 (kj_build_host_index)
 };
 
 std::string& kj_err();             // thread-local last error text

@@ -35,6 +35,7 @@ struct ko_index {
     uint8_t lcode[256], ncode[256];
     /* derived */
     uint8_t *letters; int64_t C[64]; int64_t *occ; int64_t nocc;
+    int64_t quirk_lo, quirk_d[64];   /* checkpoint quirk of indexes with bwtlen = m * 65536, m >= 2 (see rank_) */
     uint8_t trans[256];
 };
 
@@ -99,6 +100,17 @@ ko_index *ko_index_load(const char *path) {
         uint8_t c = x->lcode[x->bwt[k]]; x->letters[k] = c; run[c]++;
     }
     if ((x->bwtlen & (KO_OCC_SIZE - 1)) == 0) memcpy(x->occ + (x->bwtlen >> KO_OCC_SHIFT) * x->alen, run, sizeof(int64_t) * x->alen);
+    /* Checkpoint quirk of the reference (fmicommon.h:60-73, 88-89, 114-158): when bwtlen is a multiple of 2^16 the first-level
+     * checkpoint that positions k >= bwtlen - 128 resolve to (chpt1 = bwtlen >> 16) is the row that holds the letter starts C[]
+     * (index1[N1-1]), not a count row, and the last index2 row is relative to the previous first-level checkpoint: FMindex then
+     * returns C[c] + #c in the last 2^16 rows before k, i.e. the true value minus #c in BWT[0, bwtlen - 2^16).  Verified against the
+     * reference binary (tests/test_oracle_vs_ref.py::test_bwtlen_multiple_of_65536); no effect for bwtlen = 2^16. */
+    x->quirk_lo = INT64_MAX; memset(x->quirk_d, 0, sizeof x->quirk_d);
+    if ((x->bwtlen & 65535) == 0 && x->bwtlen >= 131072) {
+        x->quirk_lo = x->bwtlen - 128;
+        const int64_t b = (x->bwtlen - 65536) >> KO_OCC_SHIFT;
+        for (int a = 0; a < x->alen; a++) x->quirk_d[a] = x->occ[b * x->alen + a];
+    }
     /* alphabet translation, sequence.c:68-97,125-134: unknown letters -> last index */
     memset(x->trans, (uint8_t)(x->alen - 1), 256);
     for (int a = 0; a < x->alen; a++) x->trans[(uint8_t)x->alphabet[a]] = (uint8_t)a;
@@ -124,6 +136,7 @@ uint64_t ko_index_seq_taxon(const ko_index *x, int i) { return x->seq_taxon[i]; 
 static inline int64_t rank_(const ko_index *x, int c, int64_t k) {
     int64_t b = k >> KO_OCC_SHIFT, r = x->C[c] + x->occ[b * x->alen + c];
     const uint8_t *L = x->letters; for (int64_t p = b << KO_OCC_SHIFT; p < k; p++) r += (L[p] == c);
+    if (k >= x->quirk_lo) r -= x->quirk_d[c];                      /* the reference's checkpoint quirk, see ko_index_load */
     return r;
 }
 int64_t ko_fmindex(const ko_index *x, int c, int64_t k) { return rank_(x, c, k); }

@@ -147,7 +147,7 @@ void* kjemu_create(const char* fmi_path, const char* nodes_path, const kj_params
     D.sa_tax = H.sa_tax.data(); D.seq_tax = H.seq_tax.data(); D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
     D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
     D.tax_parent = H.tax_parent.data(); D.tax_depth = H.tax_depth.data(); D.tax_id = H.tax_id.data(); D.n_tax = (uint32_t)H.tax_id.size();
-    D.lnfact = H.lnfact.data(); D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? (H.wide ? (const void*)H.kmer.data() : (const void*)H.kmer32.data()) : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = &H.tables;
+    D.lnfact = H.lnfact.data(); D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? (H.wide ? (const void*)H.kmer.data() : (const void*)H.kmer32.data()) : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = &H.tables; D.quirk_lo = H.quirk_lo; memcpy(D.quirk_d, H.quirk_d, sizeof D.quirk_d);
     return c;
 }
 void kjemu_destroy(void* h) { delete (EmuCtx*)h; }
@@ -163,7 +163,7 @@ int kjemu_native_roundtrip(const char* fmi_path, const char* nodes_path, const c
     bool ok = same(A.rank, B.rank) && same(A.letters, B.letters) && same(A.sa_tax, B.sa_tax) && same(A.seq_tax, B.seq_tax) && same(A.tax_parent, B.tax_parent) &&
               same(A.tax_depth, B.tax_depth) && same(A.tax_id, B.tax_id) && same(A.lnfact, B.lnfact) && same(A.kmer, B.kmer) && same(A.kmer32, B.kmer32) &&
               A.nb == B.nb && A.bwtlen == B.bwtlen && A.alen == B.alen && memcmp(A.C, B.C, sizeof A.C) == 0 && A.sa_check == B.sa_check && A.sa_exp == B.sa_exp &&
-              A.sa_bias == B.sa_bias && A.nseq == B.nseq && A.n_present == B.n_present && A.kmer_k == B.kmer_k && A.wide == B.wide && A.db_length == B.db_length &&
+              A.sa_bias == B.sa_bias && A.nseq == B.nseq && A.n_present == B.n_present && A.kmer_k == B.kmer_k && A.wide == B.wide && A.db_length == B.db_length && A.quirk_lo == B.quirk_lo && memcmp(A.quirk_d, B.quirk_d, sizeof A.quirk_d) == 0 &&
               memcmp(&A.tables, &B.tables, sizeof(KjTables)) == 0;
     return ok ? 0 : 1;
 }

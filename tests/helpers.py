@@ -236,3 +236,38 @@ def read_fastq_packed(path):
     off[1:] = np.cumsum([len(s) for s in seqs])
     data = np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy()
     return names, data, off
+
+
+def make_quirk_db(d, nprot=512, plen=255, seed=9, nreads=3000):
+    """A DB whose BWT length is an exact multiple of 2^16 (nprot * (plen + 1) = 131072 rows by default): the case in which the
+    reference's FM-index checkpoints misbehave for the last 129 positions (fmicommon.h:60-73, 88-89).  Returns (fmi, nodes, read
+    strings).  Needs oracle/_ref (index builder)."""
+    import random
+    rnd = random.Random(seed); aa = "ACDEFGHIKLMNPQRSTVWY"
+    assert (nprot * (plen + 1)) % 65536 == 0
+    prots = ["".join(rnd.choice(aa) for _ in range(plen)) for _ in range(nprot)]
+    with open(d + "/db.faa", "w") as f:
+        for i, p in enumerate(prots):
+            f.write(">P%d_%d\n%s\n" % (i, 100 + i % 7, p))
+    with open(d + "/nodes.dmp", "w") as f:
+        f.write("1\t|\t1\t|\tno rank\t|\n")
+        for t in range(100, 107):
+            f.write("%d\t|\t1\t|\tspecies\t|\n" % t)
+    fmi = build_fmi(d + "/db.faa", d + "/db", threads=2)
+    codon = {'A': 'GCT', 'R': 'CGT', 'N': 'AAT', 'D': 'GAT', 'C': 'TGT', 'Q': 'CAA', 'E': 'GAA', 'G': 'GGT', 'H': 'CAT', 'I': 'ATT',
+             'L': 'CTG', 'K': 'AAA', 'M': 'ATG', 'F': 'TTT', 'P': 'CCT', 'S': 'TCT', 'T': 'ACT', 'W': 'TGG', 'Y': 'TAT', 'V': 'GTT'}
+    reads = []
+    for i in range(nreads):
+        p = rnd.choice(prots); s0 = rnd.randrange(0, len(p) - 50)
+        dna = "".join(codon[c] for c in p[s0:s0 + 50])
+        dna = "".join(ch if rnd.random() > 0.02 else rnd.choice("ACGT") for ch in dna)
+        if rnd.random() < 0.5:
+            dna = dna[::-1].translate(str.maketrans("ACGT", "TGCA"))
+        reads.append(dna)
+    return fmi, d + "/nodes.dmp", reads
+
+
+def pack_reads(reads):
+    seq = np.frombuffer("".join(reads).encode(), dtype=np.uint8)
+    off = np.zeros(len(reads) + 1, np.uint64); off[1:] = np.cumsum([len(r) for r in reads])
+    return seq, off

@@ -411,3 +411,21 @@ def test_native_index_file(kb, golden, tmp_path):
     assert [int(p[2]) for p in got] == [int(t) for t in etax] and [p[1] for p in got] == list(names)
     with pytest.raises(kb.KaijuError):
         kb.Classifier(golden.fmi, None, device=0, params=kb.make_params("mem"))        # a reference .fmi is not a native index
+
+
+def test_index_with_bwtlen_multiple_of_65536(kb, tmp_path):
+    """The reference's FM-index checkpoint quirk for bwtlen = m * 2^16 is reproduced on the GPU (oracle pinned to the reference for this
+    case in tests/test_oracle_vs_ref.py), for the 32-bit, 64-bit and table-free kernels and through the device-native index file."""
+    from helpers import make_quirk_db, pack_reads
+    if not have_ref():
+        pytest.skip("oracle/_ref (index builder) not available")
+    fmi, nodes, reads = make_quirk_db(str(tmp_path))
+    seq, off = pack_reads(reads); orc = Oracle(fmi, nodes)
+    native = str(tmp_path / "q.kjb"); kb.write_native_index(fmi, nodes, native)
+    for kw in (dict(mode="mem"), dict(mode="greedy"), dict(mode="greedy", e=5, s=40)):
+        otax, obest = orc.classify_batch(make_params(**kw), seq, off)
+        for src in ((fmi, nodes), (native, None)):
+            clf = kb.Classifier(src[0], src[1], device=0, params=kb_params(kb, kw))
+            tax, best = clf.classify(seq, off)
+            assert np.array_equal(tax, otax) and np.array_equal(best, obest), (kw, src)
+            clf.close()

@@ -107,3 +107,22 @@ def test_native_index_file_roundtrip(emu, golden, tmp_path, monkeypatch):
     assert emu.kjemu_native_read(golden.fmi.encode()) != 0            # a reference .fmi is not a native index
     monkeypatch.setenv("KJ_FORCE_WIDE", "1")
     assert emu.kjemu_native_roundtrip(golden.fmi.encode(), golden.nodes.encode(), p.encode()) == 0
+
+
+def test_emulated_kernel_on_index_with_bwtlen_multiple_of_65536(emu, built, tmp_path, monkeypatch):
+    """The reference's checkpoint quirk (tests/test_oracle_vs_ref.py::test_bwtlen_multiple_of_65536) is reproduced by the device code:
+    rank correction for the last 129 rows, in the k-mer table, in the SA walk, and the general 'recorded match' rule of maxMatches."""
+    from helpers import have_ref, make_quirk_db, pack_reads
+    if not have_ref():
+        pytest.skip("oracle/_ref (index builder) not available")
+    fmi, nodes, reads = make_quirk_db(str(tmp_path))
+    seq, off = pack_reads(reads); orc = Oracle(fmi, nodes)
+    for env in ({}, {"KJ_FORCE_WIDE": "1"}, {"KJ_KMER_K": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for kw in (dict(mode="mem"), dict(mode="greedy"), dict(mode="greedy", e=5, s=40)):
+            P = make_params(**kw); otax, obest = orc.classify_batch(P, seq, off)
+            rc, tax, best = emu_classify_rc(emu, fmi, nodes, P, seq, off)
+            assert rc == 0 and np.array_equal(tax, otax) and np.array_equal(best, obest), (env, kw)
+        for k in env:
+            monkeypatch.delenv(k)

@@ -3,7 +3,7 @@
 import os, tempfile
 import numpy as np
 import pytest
-from helpers import SynthDB, build_fmi, run_ref_kaiju, Oracle, make_params, have_ref, read_fastq_packed
+from helpers import SynthDB, build_fmi, run_ref_kaiju, Oracle, make_params, have_ref, read_fastq_packed, make_quirk_db, pack_reads
 
 pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
 
@@ -81,3 +81,47 @@ def test_lnfact_table_matches_reference(built):
     tab = (C.c_double * 10001).in_dll(ref, "lnfact")
     L = oracle_lib(); L.ko_lnfact.restype = C.c_double; L.ko_lnfact.argtypes = [C.c_int]
     assert all(L.ko_lnfact(n) == tab[n] for n in range(10001))
+
+
+def test_bwtlen_multiple_of_65536(built):
+    """SURVEY.md 8a exactness note (a): with bwtlen = m * 2^16 (m >= 2) the reference's FMindex resolves the last 129 positions to the
+    index1 row that holds C[] instead of counts and returns values that are too small by a per-letter constant; matches that pass
+    through those rows (e.g. every match ending in the last letter of the alphabet) behave differently from a "clean" FM index.
+    The oracle reproduces that: function level (FMindex, get_suffix of the reference's own C code) and end to end (CLI)."""
+    import ctypes as C
+    from helpers import oracle_lib, REF_DIR
+    d = tempfile.mkdtemp(prefix="kjq_")
+    fmi, nodes, reads = make_quirk_db(d)
+    R = C.CDLL(os.path.join(REF_DIR, "libkaijuref.so")); libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p; libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    R.readIndexes.restype = C.c_void_p; R.readIndexes.argtypes = [C.c_void_p]
+
+    class BWT(C.Structure):   # bwt/bwt.h:13-23
+        _fields_ = [("len", C.c_long), ("nseq", C.c_int), ("bwt", C.c_void_p), ("alen", C.c_int), ("alphabet", C.c_char_p), ("f", C.c_void_p), ("s", C.c_void_p)]
+
+    class FMI(C.Structure):   # bwt/compactfmi.h:10-19
+        _fields_ = [("alen", C.c_int), ("bwtlen", C.c_long), ("bwt", C.c_void_p), ("N1", C.c_int), ("N2", C.c_int), ("index1", C.c_void_p), ("index2", C.c_void_p), ("startLcode", C.c_void_p)]
+    b = BWT.from_address(R.readIndexes(libc.fopen(fmi.encode(), b"r"))); fm = FMI.from_address(b.f); n = fm.bwtlen
+    assert n == 131072
+    R.FMindex.restype = C.c_long; R.FMindex.argtypes = [C.c_void_p, C.c_ubyte, C.c_long]
+    R.get_suffix.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_long)]
+    orc = Oracle(fmi, nodes); L = oracle_lib()
+    L.ko_fmindex.restype = C.c_int64; L.ko_fmindex.argtypes = [C.c_void_p, C.c_int, C.c_int64]
+    L.ko_get_suffix.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    ks = list(range(n - 400, n + 1)) + list(range(65536 - 200, 65536 + 200)) + list(range(0, n, 997))
+    for k in ks:
+        for c in range(fm.alen):
+            assert L.ko_fmindex(orc.idx, c, k) == R.FMindex(b.f, c, k), (k, c)
+    iseq = C.c_int(); pos = C.c_long(); oseq = C.c_int(); opos = C.c_int64()
+    for k in list(range(n - 300, n)) + list(range(b.nseq, n, 511)):          # rows below nseq are terminator suffixes: never inside a match interval
+        R.get_suffix(b.f, b.s, k, C.byref(iseq), C.byref(pos)); L.ko_get_suffix(orc.idx, k, C.byref(oseq), C.byref(opos))
+        assert (iseq.value, pos.value) == (oseq.value, opos.value), k
+    with open(d + "/r.fa", "w") as f:
+        for i, r in enumerate(reads):
+            f.write(">r%d\n%s\n" % (i, r))
+    seq, off = pack_reads(reads)
+    for kw in (dict(mode="mem"), dict(mode="greedy"), dict(mode="greedy", e=5, s=40), dict(mode="mem", m=5, seg=False)):
+        ref = run_ref_kaiju(nodes, fmi, d + "/r.fa", None, threads=4, **kw)
+        tax, best = orc.classify_batch(make_params(**kw), seq, off)
+        for i in range(len(reads)):
+            assert (ref["r%d" % i][1], ref["r%d" % i][2]) == (int(tax[i]), int(best[i])), (kw, i)
