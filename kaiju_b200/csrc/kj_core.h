@@ -128,8 +128,9 @@ template <class IdxT>
 static KJ_DEV bool kj_update_si(const KjDevIndex& ix, uint32_t c, IdxT& lo, IdxT& hi) {
     const KjRankBlock* base = kj_letter_base(ix, c);
     IdxT nlo = kj_rank_at<IdxT>(base, lo), nhi = kj_rank_at<IdxT>(base, hi);
-    // the reference's checkpoint quirk (indexes with bwtlen = m * 2^16 only, kj_host.cpp): the last 129 positions rank lower by a per-letter constant
-    if (hi >= (IdxT)ix.quirk_lo) { const IdxT d = (IdxT)ix.quirk_d[c]; nhi -= d; if (lo >= (IdxT)ix.quirk_lo) nlo -= d; }
+    // the reference's checkpoint quirk (indexes with bwtlen = m * 2^16 only, kj_host.cpp): the last 129 positions rank lower by a per-letter
+    // constant.  Such indexes are routed to the 64-bit kernels, so the 32-bit ones do not carry the test.
+    if (sizeof(IdxT) == 8) { if (hi >= (IdxT)ix.quirk_lo) { const IdxT d = (IdxT)ix.quirk_d[c]; nhi -= d; if (lo >= (IdxT)ix.quirk_lo) nlo -= d; } }
     if (nlo >= nhi) return false;
     lo = nlo; hi = nhi; return true;
 }

@@ -153,23 +153,28 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
                 jlow = jhi - (broke ? cut + 1 : nact) + 1;
             }
             w.sync();
-            // recorded matches: l >= L and start strictly left of the previously recorded one (bwt.c:276-281).  Recorded starts
-            // decrease strictly, so "previously recorded" = the minimum start of the qualifying chains seen so far (j descending):
-            // an exclusive prefix minimum.  (With a true FM index starts are monotone in j and this reduces to "differs from j+1";
-            // the reference's checkpoint quirk for bwtlen = m * 2^16 can break chains early, so the general rule is kept.)
+            // recorded matches: l >= L and start strictly left of the previously recorded one (bwt.c:276-281).  With a true FM index
+            // the starts are monotone in j, so "same start as j+1" is the only way to be skipped (32-bit kernels).  The reference's
+            // checkpoint quirk for bwtlen = m * 2^16 can break chains early; those indexes run on the 64-bit kernels, which keep the
+            // general rule: recorded starts decrease strictly, so "previously recorded" = the minimum start of the qualifying chains
+            // seen so far (j descending), an exclusive prefix minimum.
             // pass 1: flags + found order (j descending); pass 2: class position = (#longer) + (#same length found earlier)
             const int nproc = (int)len - jlow;                             // processed j = len-1-t, t in [0,nproc)
             uint32_t cur_qi = 0xffffffffu;                                 // start of the last recorded match (uniform)
             for (int b = 0; b < nproc; b += 32) {
                 int t = b + w.lane; int j = (int)len - 1 - t; bool rec = false;
-                uint32_t mine = 0xffffffffu;                               // my start if my chain qualifies
-                if (t < nproc) { KjMatch r = res[j]; if (r.ql >= (uint32_t)L) mine = r.qi; }
-                uint32_t pm = mine;                                        // inclusive prefix minimum over the lanes
-                for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = w.shfl(pm, w.lane - dd); if (w.lane >= dd && o < pm) pm = o; }
-                uint32_t ex = w.shfl(pm, w.lane - 1); if (w.lane == 0) ex = 0xffffffffu;     // exclusive
-                if (cur_qi < ex) ex = cur_qi;
-                rec = mine != 0xffffffffu && mine < ex;
-                { const uint32_t last = w.shfl(pm, 31); if (last < cur_qi) cur_qi = last; }
+                if (sizeof(IdxT) == 4) {
+                    if (t < nproc) { KjMatch r = res[j]; rec = r.ql >= (uint32_t)L && !(t > 0 && res[j + 1].qi == r.qi); }
+                } else {
+                    uint32_t mine = 0xffffffffu;                           // my start if my chain qualifies
+                    if (t < nproc) { KjMatch r = res[j]; if (r.ql >= (uint32_t)L) mine = r.qi; }
+                    uint32_t pm = mine;                                    // inclusive prefix minimum over the lanes
+                    for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = w.shfl(pm, w.lane - dd); if (w.lane >= dd && o < pm) pm = o; }
+                    uint32_t ex = w.shfl(pm, w.lane - 1); if (w.lane == 0) ex = 0xffffffffu;     // exclusive
+                    if (cur_qi < ex) ex = cur_qi;
+                    rec = mine != 0xffffffffu && mine < ex;
+                    { const uint32_t last = w.shfl(pm, 31); if (last < cur_qi) cur_qi = last; }
+                }
                 uint32_t mk = w.ballot(rec);
                 if (rec) { KjMatch r = res[j]; cls[nrec + (uint32_t)kj_popc(mk & lanemask_lt(w.lane))] = r; }   // found order, temporarily in cls
                 nrec += (uint32_t)kj_popc(mk);
