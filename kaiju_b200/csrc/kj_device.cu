@@ -142,7 +142,7 @@ struct kj_ctx {
     // run state
     unsigned long long* d_counter = nullptr; uint32_t* d_err = nullptr; unsigned int* d_maxlen = nullptr;
     KjKept* d_spill = nullptr; size_t spill_bytes = 0; uint8_t* d_gscratch = nullptr; size_t gscratch_bytes_total = 0;
-    double* d_evbreaks = nullptr; uint32_t n_evbreaks = 0;
+    double* d_evbreaks = nullptr; uint32_t n_evbreaks = 0; uint64_t* d_quirk = nullptr;
     unsigned long long* d_counts = nullptr; unsigned long long* d_counts_pending = nullptr; uint32_t n_counts = 0, n_present = 0;   // per-taxon read counts (+1 slot: unclassified)
     uint32_t variant_boost = 1;    // Greedy variant-ring capacity multiplier, raised after an overflow (flag 4) so that a retry succeeds
     uint8_t* d_ws = nullptr; size_t ws_bytes = 0;
@@ -236,7 +236,8 @@ template <class Fill> static int create_ctx(kj_ctx** out, int device, const kj_p
     D.sa_tax = (const uint32_t*)c->d_sa_tax; D.seq_tax = (const uint32_t*)c->d_seq_tax; D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
     D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
     D.tax_parent = (const uint32_t*)c->d_tax_parent; D.tax_depth = (const uint32_t*)c->d_tax_depth; D.tax_id = (const uint64_t*)c->d_tax_id; D.n_tax = (uint32_t)H.tax_id.size();
-    D.lnfact = (const double*)c->d_lnfact; D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? c->d_kmer : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = c->d_tables; D.quirk_lo = H.quirk_lo; memcpy(D.quirk_d, H.quirk_d, sizeof D.quirk_d);
+    D.lnfact = (const double*)c->d_lnfact; D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? c->d_kmer : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = c->d_tables; D.quirk_lo = H.quirk_lo;
+    CK(cudaMalloc((void**)&c->d_quirk, sizeof H.quirk_d)); CK(cudaMemcpy(c->d_quirk, H.quirk_d, sizeof H.quirk_d, cudaMemcpyHostToDevice)); D.quirk_d = c->d_quirk;
     CK(cudaMalloc((void**)&c->d_ix, sizeof(KjDevIndex))); CK(cudaMemcpy(c->d_ix, &D, sizeof(KjDevIndex), cudaMemcpyHostToDevice));
     c->index_bytes = tot;
     // host copies of the big arrays are no longer needed
@@ -279,7 +280,7 @@ extern "C" void kj_destroy(kj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     void* ptrs[] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_tax_parent, c->d_tax_depth, c->d_tax_id, c->d_lnfact, c->d_kmer, c->d_tables, c->d_ix,
-                    c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evbreaks, c->d_ws, c->d_counts, c->d_counts_pending, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
+                    c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evbreaks, c->d_ws, c->d_counts, c->d_counts_pending, c->d_quirk, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
                     c->d_seq[0][0], c->d_seq[0][1], c->d_seq[1][0], c->d_seq[1][1], c->d_off[0][0], c->d_off[0][1], c->d_off[1][0], c->d_off[1][1],
                     c->d_ids[0], c->d_ids[1], c->d_nids[0], c->d_nids[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
