@@ -107,7 +107,19 @@ def ref_cpu_run(db, fmi, nodes, args, n_sample, seed, first, cores):
     return n_sample / dt, dt
 
 
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else printed by libraries (NCCL's version banner,
+    build output) was diverted to stderr in main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1); os.dup2(2, 1)          # fd 1 -> stderr for the rest of the process; emit() writes to the saved descriptor
     args = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     import __graft_entry__ as ge
@@ -133,7 +145,7 @@ def main():
                 "config": {"workload": "configs[1]: %s -m 11, synthetic PE150 pairs vs synth-viruses .fmi (%d proteins); bounded sample of %d pairs per step" % (args.mode.upper(), args.nprot, n_sample)},
                 "cpu_baseline": {"value": v, "unit": "read pairs/s", "cores": cores, "kind": "reference", "sample": "%d pairs per step, kaiju -z %d, index load excluded by differential" % (n_sample, cores)},
                 "e2e": {"value": v, "unit": "read pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line)); return
+        emit(line); return
 
     # ------------------------------------------------------------------ B200 arm
     import torch
@@ -262,7 +274,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "read pairs/s", "cores": cores, "kind": "reference",
                                     "sample": "first %d pairs of the same workload, oracle/_ref/kaiju -z %d, %.1f s, index load excluded by differential" % (n_cpu, cores, dt),
                                     "oracle_port_value": n_or / t_or}
-        print(json.dumps(line))
+        emit(line)
     if dist:
         dist.destroy_process_group()
 
