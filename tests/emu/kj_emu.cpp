@@ -167,6 +167,13 @@ int kjemu_native_roundtrip(const char* fmi_path, const char* nodes_path, const c
               memcmp(&A.tables, &B.tables, sizeof(KjTables)) == 0;
     return ok ? 0 : 1;
 }
+// E-value gate: the break points (largest passing query length per score) the device counts against
+int kjemu_evalue_breaks(double min_evalue, double db_length, double* out, int cap) {
+    kj_params p; memset(&p, 0, sizeof p); p.mode = 1; p.use_evalue = 1; p.min_evalue = min_evalue; p.min_fragment_length = 11; p.min_score = 65; p.seed_length = 7;
+    std::vector<double> b; if (kj_build_evalue_breaks(p, db_length, b) != KJ_OK) return -1;
+    for (size_t i = 0; i < b.size() && (int)i < cap; i++) out[i] = b[i];
+    return (int)b.size();
+}
 int kjemu_native_read(const char* path) { KjHostIndex H; return kj_host_index_read(path, H); }
 
 int kjemu_classify(void* h, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,

@@ -126,3 +126,29 @@ def test_emulated_kernel_on_index_with_bwtlen_multiple_of_65536(emu, built, tmp_
             assert rc == 0 and np.array_equal(tax, otax) and np.array_equal(best, obest), (env, kw)
         for k in env:
             monkeypatch.delenv(k)
+
+
+def test_evalue_break_points_equal_the_reference_expression(emu):
+    """The E-value gate on the device = number of break points below the query length.  For every score k and query lengths around and
+    far from the break points, that integer threshold must agree with the reference's expression (ConsumerThread.cpp:500-513)
+    evaluated directly: Evalue = db_length * query_len * 2^-((0.3176 * k + 2.009915479) / 0.6931471805) > min_Evalue -> rejected."""
+    import math, random
+    emu.kjemu_evalue_breaks.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int]
+    rnd = random.Random(3)
+    def rejected(db, q, k, E):
+        bitscore = (0.3176 * k - (-2.009915479)) / 0.6931471805
+        return db * q * math.pow(2, -1 * bitscore) > E
+    for E in (10.0, 0.01, 1e-5, 1e-12, 1e-30):
+        for db in (8.2e5, 1.99e8, 2.7e10):
+            buf = (C.c_double * 4096)(); n = emu.kjemu_evalue_breaks(E, db, buf, 4096); assert 0 < n <= 4096
+            br = [buf[i] for i in range(n)]
+            assert all(br[i] <= br[i + 1] for i in range(n - 1))
+            qs = [a / 3.0 + b / 3.0 for a in (33, 100, 150, 151, 301, 5000, 16383) for b in (0, 149, 150, 16383)] + [float(x) for x in (11, 300, 5461)]
+            for k in range(0, min(n, 400), 7):        # doubles right at a break point
+                if 0 < br[k] < 1e11:
+                    qs += [br[k], math.nextafter(br[k], math.inf), math.nextafter(br[k], 0.0)]
+            for q in qs:
+                thr = sum(1 for x in br if x < q)                       # what the device computes
+                ks = sorted(set([max(0, thr - 2), max(0, thr - 1), thr, thr + 1, thr + 5] + [rnd.randrange(0, 2000) for _ in range(6)]))
+                for k in ks:
+                    assert (k >= thr) == (not rejected(db, q, k, E)), (E, db, q, k, thr)
