@@ -105,6 +105,13 @@ static KJ_DEV void kj_split(IdxT k, uint32_t& blk, uint32_t& wi, uint32_t& bit) 
 // 32-byte sector, one 64-bit popcount, no data-dependent branches.  `base` = records of letter c.
 template <class IdxT>
 static KJ_DEV IdxT kj_rank_at(const KjRankBlock* base, IdxT k) {
+#ifdef KJ_RANK64
+    const uint8_t* rec64 = (const uint8_t*)(base + (k >> 6));
+    const uint64_t h64 = kj_ld64(rec64), w64 = kj_ld64(rec64 + 8u);
+    const uint32_t pc64 = (uint32_t)kj_popcll(w64 & ((1ull << ((uint32_t)k & 63u)) - 1ull));
+    if (sizeof(IdxT) == 4) return (IdxT)((uint32_t)h64 + pc64);
+    return (IdxT)(h64 + (uint64_t)pc64);
+#endif
     uint32_t blk, wi, bit; kj_split<IdxT>(k, blk, wi, bit);
     const uint8_t* rec = (const uint8_t*)(base + blk);
     const uint64_t hdr = kj_ld64(rec);

@@ -183,7 +183,7 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
     }
     // rank records + packed letters, chunked over threads
     const uint64_t nb = n / KJ_RANK_BLOCK + 1; H.nb = nb;
-    const uint64_t CH = (uint64_t)KJ_RANK_BLOCK * 2048;                 // positions per chunk (multiple of 192 and 12)
+    const uint64_t CH = 192ull * 2048;                                  // positions per chunk (multiple of 192, 64 and 12)
     const uint64_t nch = (n + CH - 1) / CH;
     std::vector<uint64_t> ccount((size_t)(nch + 1) * alen, 0);
     unsigned nthr = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
@@ -196,7 +196,7 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
     const uint64_t* total = &ccount[(size_t)nch * alen];
     H.C[0] = 0; for (int a = 0; a < alen; a++) H.C[a + 1] = H.C[a] + total[a];
     if (H.C[alen] != n) { kj_err() = "letter counts do not add up"; return KJ_ERR_IO; }
-    try { H.rank.assign((size_t)alen * nb, KjRankBlock{0, 0, 0, 0}); H.letters.assign((size_t)(n / KJ_LETTERS_PER_WORD + 2), 0); }
+    try { H.rank.assign((size_t)alen * nb, KjRankBlock{}); H.letters.assign((size_t)(n / KJ_LETTERS_PER_WORD + 2), 0); }
     catch (...) { kj_err() = "out of host memory building the rank table"; return KJ_ERR_NOMEM; }
     par([&](uint64_t c) {
         uint64_t run[KJ_MAX_ALEN]; for (int a = 0; a < alen; a++) run[a] = H.C[a] + ccount[(size_t)c * alen + a];
@@ -206,7 +206,11 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
             for (int a = 0; a < alen; a++) H.rank[(size_t)a * nb + b].hdr = run[a];
             for (uint64_t k = b0; k < be; k++) {
                 uint32_t a = lcode[v.bwt[k]], r = (uint32_t)(k - b0); KjRankBlock& B = H.rank[(size_t)a * nb + b];
+#ifdef KJ_RANK64
+                B.w0 |= 1ull << r;
+#else
                 (r < 64 ? B.w0 : r < 128 ? B.w1 : B.w2) |= 1ull << (r & 63);
+#endif
                 run[a]++;
             }
         }
@@ -219,12 +223,14 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
     // take the 64-bit kernels: only those carry the rank correction, so that ordinary indexes pay nothing for the 1-in-65536 case.
     const bool quirk = (n & 65535ull) == 0 && n >= 131072ull;
     H.wide = (n >= 0xffffff00ull || getenv("KJ_FORCE_WIDE") || quirk) ? 1 : 0;
+#ifndef KJ_RANK64
     {   // fold the in-block prefix popcounts into the header
         std::vector<std::thread> th; const size_t tot = (size_t)alen * nb;
         for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] { for (size_t i = tI; i < tot; i += nthr) { KjRankBlock& B = H.rank[i];
             uint64_t p1 = (uint64_t)__builtin_popcountll(B.w0), p2 = p1 + (uint64_t)__builtin_popcountll(B.w1); B.hdr = (B.hdr & KJ_CNT_MASK) | (p1 << KJ_P1_SHIFT) | (p2 << KJ_P2_SHIFT); } });
         for (auto& x : th) x.join();
     }
+#endif
 
     // ---- taxonomy re-indexing
     std::unordered_map<uint64_t, uint64_t> par_of; par_of.reserve((size_t)t.n * 2 + 16);
@@ -306,8 +312,12 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
 // host-side rank on the device layout (used only to fill the k-mer table)
 static inline uint64_t host_rank(const KjHostIndex& H, uint32_t c, uint64_t k) {
     uint64_t b = k / KJ_RANK_BLOCK; uint32_t r = (uint32_t)(k - b * KJ_RANK_BLOCK); const KjRankBlock& B = H.rank[(size_t)c * H.nb + b];
+#ifdef KJ_RANK64
+    uint32_t bit = r; uint64_t ww = B.w0, add = 0;
+#else
     uint32_t wi = r >> 6, bit = r & 63u; uint64_t ww = wi == 0 ? B.w0 : (wi == 1 ? B.w1 : B.w2);
     uint64_t add = wi == 0 ? 0 : ((B.hdr >> (32 + 8 * wi)) & 0xff);
+#endif
     const uint64_t v = (B.hdr & KJ_CNT_MASK) + add + (uint64_t)__builtin_popcountll(ww & ((1ull << bit) - 1ull));
     return k >= H.quirk_lo ? v - H.quirk_d[c] : v;                  // the reference's checkpoint quirk (kj_build_host_index)
 }

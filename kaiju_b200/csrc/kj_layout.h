@@ -19,7 +19,11 @@
 #pragma once
 #include <stdint.h>
 
+#ifdef KJ_RANK64
+#define KJ_RANK_BLOCK 64           // A/B variant: one 16-byte record (header + one bitmap word) per 64 positions: no /3, +50 % index memory
+#else
 #define KJ_RANK_BLOCK 192          // positions per rank record (3 x 64-bit words)
+#endif
 #define KJ_LETTERS_PER_WORD 12
 #define KJ_MAX_ALEN 24
 #define KJ_MAX_IDS 21              // max_match_ids = 20 -> the set holds at most 21 (ConsumerThread.cpp:805)
@@ -30,7 +34,11 @@
 
 // hdr = cnt (40 bit: C[c] + #c before the block) | popc(w0) << 40 | (popc(w0)+popc(w1)) << 48 ; w0..w2 = one-hot bitmap.
 // For indexes below 2^32 rows byte 4 is zero, so (hdr >> 32 >> 8*word) & 0xff is the in-block prefix for word 0,1,2 without a select.
+#ifdef KJ_RANK64
+struct alignas(16) KjRankBlock { uint64_t hdr, w0; };
+#else
 struct alignas(32) KjRankBlock { uint64_t hdr, w0, w1, w2; };
+#endif
 #define KJ_CNT_MASK 0xffffffffffull
 #define KJ_P1_SHIFT 40
 #define KJ_P2_SHIFT 48
