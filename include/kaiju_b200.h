@@ -140,6 +140,24 @@ void *kj_counts_device_ptr(kj_ctx *ctx);
 int kj_counts_add_device(kj_ctx *ctx, const uint64_t *d_taxon, uint64_t n_reads, void *cuda_stream);
 int kj_counts_get(kj_ctx *ctx, uint64_t *taxon_ids_out /* [size] or NULL; last = 0 */, uint64_t *counts_out /* [size] */);
 
+/* kaiju2table's report (src/kaiju2table.cpp:150-365: header row, one row per taxon of `rank` by descending read count, then the
+ * Viruses / "cannot be assigned" / threshold / unclassified rows) written from per-taxon counts instead of the per-read output file.
+ * kj_table_write is host-only (ids[i] = 0 marks the unclassified reads); kj_counts_table feeds it the context's count vector.
+ * label = the "file" column; append != 0 adds the rows of another data set to an existing report (no second header). */
+typedef struct {
+    const char *rank;             /* -r: phylum, class, order, family, genus or species           */
+    double min_percent;           /* -m (default 0)                                               */
+    int32_t min_read_count;       /* -c (default 0); only one of -m / -c                          */
+    int32_t expand_viruses;       /* -e                                                           */
+    int32_t filter_unclassified;  /* -u                                                           */
+    int32_t full_path;            /* -p                                                           */
+    const char *rank_list;        /* -l: comma-separated ranks, or NULL                           */
+} kj_table_opts;
+int kj_table_write(const uint64_t *taxon_ids, const uint64_t *counts, uint64_t n, const char *nodes_dmp, const char *names_dmp,
+                   const char *label, const kj_table_opts *opts, const char *out_path, int append);
+int kj_counts_table(kj_ctx *ctx, const char *nodes_dmp, const char *names_dmp, const char *label, const kj_table_opts *opts,
+                    const char *out_path, int append);
+
 /* Per-read work queues on the device are sized from worst-case bounds; should one overflow anyway, the affected launch is
  * flagged (never silently truncated).  kj_classify() checks this itself; after kj_classify_device() call kj_check_errors()
  * once the stream has finished: KJ_OK, or KJ_ERR_OVERFLOW (the results of that launch are invalid).  When the overflow was

@@ -34,6 +34,11 @@ class KjTaxonomyView(C.Structure):
     _fields_ = [("n", C.c_uint64), ("node", C.c_void_p), ("parent", C.c_void_p)]
 
 
+class KjTableOpts(C.Structure):
+    _fields_ = [("rank", C.c_char_p), ("min_percent", C.c_double), ("min_read_count", C.c_int32), ("expand_viruses", C.c_int32),
+                ("filter_unclassified", C.c_int32), ("full_path", C.c_int32), ("rank_list", C.c_char_p)]
+
+
 class KaijuError(RuntimeError):
     pass
 
@@ -74,6 +79,8 @@ def lib():
         L.kj_counts_device_ptr.restype = C.c_void_p; L.kj_counts_device_ptr.argtypes = [C.c_void_p]
         L.kj_counts_add_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.kj_counts_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kj_table_write.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(KjTableOpts), C.c_char_p, C.c_int]
+        L.kj_counts_table.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(KjTableOpts), C.c_char_p, C.c_int]
         L.kj_check_errors.argtypes = [C.c_void_p]
         L.kj_launch_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.kj_version.restype = C.c_int
@@ -93,6 +100,19 @@ def make_params(mode="mem", m=11, e=3, s=65, seed=7, E=0.01, seg=True, use_evalu
         use_evalue = greedy
     return KjParams(mode=1 if greedy else 0, min_fragment_length=m, mismatches=e, min_score=s, seed_length=seed,
                     use_evalue=1 if (use_evalue and greedy) else 0, min_evalue=E, seg=1 if seg else 0, input_is_protein=1 if protein else 0)
+
+
+def _table_opts(rank, min_percent=0.0, min_read_count=0, expand_viruses=False, filter_unclassified=False, full_path=False, rank_list=None):
+    return KjTableOpts(rank.encode(), float(min_percent), int(min_read_count), int(expand_viruses), int(filter_unclassified), int(full_path),
+                       rank_list.encode() if rank_list else None)
+
+
+def write_table(taxon_ids, counts, nodes_path, names_path, label, out_path, rank="species", append=False, **kw):
+    """kaiju2table's report from per-taxon read counts (taxon id 0 = unclassified reads).  Host-only, no GPU needed."""
+    ids = np.ascontiguousarray(taxon_ids, dtype=np.uint64); cnt = np.ascontiguousarray(counts, dtype=np.uint64)
+    o = _table_opts(rank, **kw)
+    _check(lib().kj_table_write(ids.ctypes.data, cnt.ctypes.data, len(ids), nodes_path.encode(), names_path.encode(), label.encode(), C.byref(o),
+                                out_path.encode(), 1 if append else 0))
 
 
 def write_native_index(fmi_path, nodes_path, out_path):
@@ -212,6 +232,11 @@ class Classifier:
     @property
     def counts_device_ptr(self):
         return lib().kj_counts_device_ptr(self._ctx), int(lib().kj_counts_size(self._ctx))
+
+    def counts_table(self, nodes_path, names_path, label, out_path, rank="species", append=False, **kw):
+        """kaiju2table's report for the reads counted so far."""
+        o = _table_opts(rank, **kw)
+        _check(lib().kj_counts_table(self._ctx, nodes_path.encode(), names_path.encode(), label.encode(), C.byref(o), out_path.encode(), 1 if append else 0))
 
     def check_errors(self):
         _check(lib().kj_check_errors(self._ctx))

@@ -23,14 +23,14 @@ static void usage(const char* prog) {
                     "   -z INT        accepted for compatibility (ignored: the GPU replaces the worker threads)\n   -a STRING     Run mode, either \"mem\"  or \"greedy\" (default: greedy)\n"
                     "   -e INT        Number of mismatches allowed in Greedy mode (default: 3)\n   -m INT        Minimum match length (default: 11)\n   -s INT        Minimum match score in Greedy mode (default: 65)\n"
                     "   -E FLOAT      Minimum E-value in Greedy mode (default: 0.01)\n   -x            Enable SEG low complexity filter (enabled by default)\n   -X            Disable SEG low complexity filter\n"
-                    "   -w FILENAME   Write the device-native index file for -t/-f and exit; such a file can then be given as -f (no -t needed, no transcode at start-up)\n   -p            Input sequences are protein sequences\n   -v            Enable verbose output (adds the match length/score and the matching taxon ids)\n   -d INT        CUDA device ordinal (default 0)\n", prog);
+                    "   -w FILENAME   Write the device-native index file for -t/-f and exit; such a file can then be given as -f (no -t needed, no transcode at start-up)\n   -T FILENAME   Also write kaiju2table's summary (reads per taxon of rank -r, default species; needs -N names.dmp) from the counts kept on the GPU\n   -p            Input sequences are protein sequences\n   -v            Enable verbose output (adds the match length/score and the matching taxon ids)\n   -d INT        CUDA device ordinal (default 0)\n", prog);
     exit(EXIT_FAILURE);
 }
 
 int main(int argc, char** argv) {
     kj_params P; P.mode = 1; P.min_fragment_length = 11; P.mismatches = 3; P.min_score = 65; P.seed_length = 7; P.use_evalue = 1; P.min_evalue = 0.01; P.seg = 1; P.input_is_protein = 0;
-    std::string nodes_fn, fmi_fn, in1, in2, out_fn, native_out; bool verbose = false; int device = 0; int c;
-    while ((c = getopt(argc, argv, "a:hd:pxXvn:m:e:E:l:t:f:i:j:s:z:o:w:")) != -1) {
+    std::string nodes_fn, fmi_fn, in1, in2, out_fn, native_out, table_fn, table_rank = "species", names_fn; bool verbose = false; int device = 0; int c;
+    while ((c = getopt(argc, argv, "a:hd:pxXvn:m:e:E:l:t:f:i:j:s:z:o:w:T:r:N:")) != -1) {
         switch (c) {
             case 'a': if (!strcmp(optarg, "mem")) { P.mode = 0; P.use_evalue = 0; } else if (!strcmp(optarg, "greedy")) P.mode = 1; else { fprintf(stderr, "-a must be a valid mode.\n"); usage(argv[0]); } break;
             case 'h': usage(argv[0]); break;
@@ -41,6 +41,9 @@ int main(int argc, char** argv) {
             case 'X': P.seg = 0; break;
             case 'o': out_fn = optarg; break;
             case 'w': native_out = optarg; break;
+            case 'T': table_fn = optarg; break;
+            case 'r': table_rank = optarg; break;
+            case 'N': names_fn = optarg; break;
             case 'f': fmi_fn = optarg; break;
             case 't': nodes_fn = optarg; break;
             case 'i': in1 = optarg; break;
@@ -92,11 +95,18 @@ int main(int argc, char** argv) {
 
     // parsing, classification and output formatting all run on the device; the host moves bytes (kj_ingest.h).
     // Comma-separated lists for -i / -j / -o process several data sets against the index loaded once (kaiju-multi.cpp:220-330).
+    if (!table_fn.empty() && (names_fn.empty() || nodes_fn.empty())) die("The summary table (-T) needs names.dmp (-N) and nodes.dmp (-t).");
     for (size_t k = 0; k < l1.size(); k++) {
         uint64_t n_reads = 0, n_classified = 0;
+        if (!table_fn.empty() && kj_counts_reset(ctx) != KJ_OK) die(kj_last_error());
         const auto t0 = std::chrono::steady_clock::now();
         if (kj_classify_files(ctx, l1[k].c_str(), paired ? l2[k].c_str() : nullptr, lo.empty() ? nullptr : lo[k].c_str(), verbose ? 1 : 0, &n_reads, &n_classified) != KJ_OK) die(kj_last_error());
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (!table_fn.empty()) {     // kaiju2table's report straight from the per-taxon counts in HBM (one block of rows per data set)
+            kj_table_opts to; memset(&to, 0, sizeof to); to.rank = table_rank.c_str();
+            const std::string label = lo.empty() ? l1[k] : lo[k];
+            if (kj_counts_table(ctx, nodes_fn.c_str(), names_fn.c_str(), label.c_str(), &to, table_fn.c_str(), k > 0) != KJ_OK) die(kj_last_error());
+        }
         if (verbose || getenv("KJ_CLI_TIMING")) fprintf(stderr, "%s: %llu reads, %llu classified, %.4f s from the first byte read to the last byte written\n", l1[k].c_str(), (unsigned long long)n_reads, (unsigned long long)n_classified, secs);
     }
     kj_destroy(ctx);

@@ -498,6 +498,12 @@ extern "C" int kj_counts_get(kj_ctx* c, uint64_t* taxon_ids_out, uint64_t* count
     if (taxon_ids_out) { for (uint32_t i = 0; i + 1 < c->n_counts; i++) taxon_ids_out[i] = c->H.tax_id[i]; taxon_ids_out[c->n_counts - 1] = 0; }
     return KJ_OK;
 }
+extern "C" int kj_counts_table(kj_ctx* c, const char* nodes_dmp, const char* names_dmp, const char* label, const kj_table_opts* opts, const char* out_path, int append) {
+    if (!c) { kj_err() = "kj_counts_table: null argument"; return KJ_ERR_ARG; }
+    std::vector<uint64_t> ids(c->n_counts), cnt(c->n_counts);
+    int rc = kj_counts_get(c, ids.data(), cnt.data()); if (rc) return rc;
+    return kj_table_write(ids.data(), cnt.data(), c->n_counts, nodes_dmp, names_dmp, label, opts, out_path, append);
+}
 extern "C" int kj_check_errors(kj_ctx* c) { if (!c) return KJ_ERR_ARG; cudaSetDevice(c->device); return check_err_flag(c); }
 extern "C" int kj_launch_geometry(const kj_ctx* c, int* grid, int* block, int* smem) { if (!c) return KJ_ERR_ARG; if (grid) *grid = c->grid; if (block) *block = KJ_WARPS_PER_CTA * 32; if (smem) *smem = (int)c->smem_bytes; return KJ_OK; }
 

@@ -429,3 +429,35 @@ def test_index_with_bwtlen_multiple_of_65536(kb, tmp_path):
             tax, best = clf.classify(seq, off)
             assert np.array_equal(tax, otax) and np.array_equal(best, obest), (kw, src)
             clf.close()
+
+
+def test_counts_table_equals_reference_kaiju2table(kb, golden, tmp_path):
+    """reads -> per-taxon counts in HBM -> kaiju2table report (kj_counts_table) == the reference's kaiju2table run on the per-read output file."""
+    import subprocess
+    from helpers import REF_DIR
+    k2t = os.path.join(REF_DIR, "kaiju2table")
+    if not os.path.exists(k2t):
+        pytest.skip("oracle/_ref/kaiju2table not built")
+    gold = os.path.dirname(golden.fmi); d = str(tmp_path)
+    # the golden taxonomy has no ranks: give every node a rank by depth and a name
+    par = {}
+    for l in open(golden.nodes):
+        p = l.split("\t|\t"); par[int(p[0])] = int(p[1])
+    ranks = ["no rank", "superkingdom", "phylum", "class", "order", "family", "genus", "species"]
+    def depth(x):
+        k = 0
+        while par[x] != x:
+            x = par[x]; k += 1
+        return k
+    with open(d + "/nodes.dmp", "w") as f, open(d + "/names.dmp", "w") as g:
+        for x in par:
+            f.write("%d\t|\t%d\t|\t%s\t|\n" % (x, par[x], ranks[min(depth(x), 7)])); g.write("%d\t|\ttaxon %d\t|\t\t|\tscientific name\t|\n" % (x, x))
+    clf = kb.Classifier(golden.fmi, golden.nodes, device=0, params=kb.make_params("mem"))
+    out = d + "/reads.tsv"
+    clf.classify_files(os.path.join(gold, "pe150_1.fq.gz"), os.path.join(gold, "pe150_2.fq.gz"), out)
+    for o, flags in ((dict(rank="species"), ["-r", "species"]), (dict(rank="genus", filter_unclassified=True, full_path=True), ["-r", "genus", "-u", "-p"]),
+                     (dict(rank="phylum", min_read_count=5), ["-r", "phylum", "-c", "5"])):
+        subprocess.run([k2t, "-t", d + "/nodes.dmp", "-n", d + "/names.dmp", "-o", d + "/ref.tsv"] + flags + [out], check=True, stderr=subprocess.DEVNULL)
+        clf.counts_table(d + "/nodes.dmp", d + "/names.dmp", out, d + "/ours.tsv", **o)
+        assert open(d + "/ours.tsv").read() == open(d + "/ref.tsv").read(), o
+    clf.close()
