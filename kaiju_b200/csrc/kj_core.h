@@ -26,20 +26,31 @@ struct KjKept { uint64_t lo; uint32_t len; uint32_t aux; };     // one suffix in
 struct KjSmemLayout {
     uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, qord_off, aa_off, aa_stride, frag_off, hflag_off,
              segcnt_off, seghist_off, segs_off, total;
+#if defined(KJ_EMU)
+    uint32_t guard[16], nguard;         // emulator only: 64-byte red zones between the sub-arrays, checked after every read item
+#endif
 };
+#if defined(KJ_EMU)
+#define KJ_GUARD(L, o) { (L).guard[(L).nguard++] = (o); (o) += 64u; }
+#else
+#define KJ_GUARD(L, o)
+#endif
 static KJ_HD uint32_t kj_align(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
     KjSmemLayout L; uint32_t o = 0;
-    L.qkey_off = o; o += 8u * p.item_cap;
-    L.kept_off = o; o += 16u * p.kept_cap_smem;
-    L.segs_off = o; o += 8u * KJ_SEG_CAP(p.max_frag);                     // {int begin,end}
-    L.qpay_off = o; o += 4u * kj_align(p.item_cap, 2);
-    L.qord_off = o; o += kj_align(p.item_cap, 8);                      // slots in pop order (valid while no SEG piece was pushed)
-    L.ids_off = o; o += 4u * 24u;
+#if defined(KJ_EMU)
+    L.nguard = 0;
+#endif
+    L.qkey_off = o; o += 8u * p.item_cap; KJ_GUARD(L, o)
+    L.kept_off = o; o += 16u * p.kept_cap_smem; KJ_GUARD(L, o)
+    L.segs_off = o; o += 8u * KJ_SEG_CAP(p.max_frag); KJ_GUARD(L, o)          // {int begin,end}
+    L.qpay_off = o; o += 4u * kj_align(p.item_cap, 2); KJ_GUARD(L, o)
+    L.qord_off = o; o += kj_align(p.item_cap, 8); KJ_GUARD(L, o)           // slots in pop order (valid while no SEG piece was pushed)
+    L.ids_off = o; o += 4u * 24u; KJ_GUARD(L, o)
     L.aa_stride = kj_align(p.max_len + 4, 8);
-    L.aa_off = o; o += 4u * L.aa_stride;
-    L.frag_off = o; o += kj_align(p.max_frag + 8, 8);
-    L.hflag_off = o; o += kj_align(p.max_frag + 8, 8);
+    L.aa_off = o; o += 4u * L.aa_stride; KJ_GUARD(L, o)
+    L.frag_off = o; o += kj_align(p.max_frag + 8, 8); KJ_GUARD(L, o)
+    L.hflag_off = o; o += kj_align(p.max_frag + 8, 8); KJ_GUARD(L, o)
     // union: SEG trim scratch (alive inside getNextFragment's SEG gate) | greedy search arrays (alive after the gate)
     const uint32_t u = o;
     L.segcnt_off = u; L.seghist_off = u + 20u * 32u;
@@ -55,6 +66,7 @@ static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
         L.pre_off = u + g_bytes; g_bytes += 2u * kj_align(p.max_frag + 2, 4);    // prefix sums of the BLOSUM62 diagonal
     }
     o = u + (seg_bytes > g_bytes ? seg_bytes : g_bytes);
+    KJ_GUARD(L, o)
     L.total = kj_align(o, 16);
     return L;
 }

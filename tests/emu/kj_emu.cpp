@@ -200,6 +200,10 @@ int kjemu_classify(void* h, const char* seq1, const uint64_t* off1, const char* 
             A.s2 = paired ? (const uint8_t*)seq2 + off2[i] : nullptr; A.n2 = paired ? (int)(off2[i + 1] - off2[i]) : 0; A.paired = paired;
             memset(smem.data(), 0xA5, smem.size());      // poison: the kernel must not rely on zeroed shared memory
             kjemu::run_warp(s, item_body, &A);
+            // the red zones between the work-space arrays must be untouched (a stray store would silently corrupt a neighbour on the GPU)
+            for (uint32_t g = 0; g < L.nguard; g++) for (uint32_t b = 0; b < 64; b++) if (smem[L.guard[g] + b] != 0xA5) {
+                fprintf(stderr, "kjemu: work-space red zone %u (offset %u) overwritten at read %llu\n", g, L.guard[g], (unsigned long long)i); abort(); }
+            for (size_t b = L.total; b < smem.size(); b++) if (smem[b] != 0xA5) { fprintf(stderr, "kjemu: store past the work space at read %llu\n", (unsigned long long)i); abort(); }
             for (int l = 1; l < 32; l++) if (A.tax[l] != A.tax[0] || A.best[l] != A.best[0]) { fprintf(stderr, "kjemu: non-uniform result at read %llu\n", (unsigned long long)i); abort(); }
             taxon_out[i] = A.tax[0] == KJ_TAX_BAD ? 0 : c->H.tax_id[A.tax[0]];
             if (best_out) best_out[i] = taxon_out[i] ? A.best[0] : 0;
