@@ -37,6 +37,8 @@ extern "C" int kj_fmi_load(const char* path, kj_fmi** out) {
     if (!path || !out) { kj_err() = "kj_fmi_load: null argument"; return KJ_ERR_ARG; }
     FILE* fp = fopen(path, "rb");
     if (!fp) { kj_err() = std::string("could not open ") + path; return KJ_ERR_IO; }
+    // every count read from the file is checked against the file size before memory is allocated for it (corrupt headers)
+    fseeko(fp, 0, SEEK_END); const int64_t fsize = (int64_t)ftello(fp); fseeko(fp, 0, SEEK_SET);
     kj_fmi* f = new kj_fmi(); Reader r(fp);
     f->len = r.get<int64_t>(); f->nseq = r.get<int32_t>(); f->alen = r.get<int32_t>();
     if (!r.ok || f->alen <= 1 || f->alen > 64 || f->nseq < 0 || f->len <= 0) { fclose(fp); delete f; kj_err() = "not a .fmi file (BWT header)"; return KJ_ERR_IO; }
@@ -44,7 +46,8 @@ extern "C" int kj_fmi_load(const char* path, kj_fmi** out) {
     f->sa_len = r.get<int64_t>(); f->ncheck = r.get<int64_t>(); f->chpt_exp = r.get<int32_t>(); f->nbytes = r.get<int32_t>();
     f->sbits = r.get<int32_t>(); f->pbits = r.get<int32_t>(); f->mask = r.get<int64_t>(); f->check = r.get<int64_t>();
     int32_t nseq2 = r.get<int32_t>();
-    if (!r.ok || nseq2 != f->nseq || f->nbytes <= 0 || f->nbytes > 8 || f->ncheck < 0 || f->chpt_exp < 0 || f->chpt_exp > 30) { fclose(fp); delete f; kj_err() = "not a .fmi file (suffix-array header)"; return KJ_ERR_IO; }
+    if (!r.ok || nseq2 != f->nseq || f->nbytes <= 0 || f->nbytes > 8 || f->ncheck < 0 || f->chpt_exp < 0 || f->chpt_exp > 30 ||
+        (int64_t)f->nseq * 13 > fsize || f->ncheck > fsize / f->nbytes) { fclose(fp); delete f; kj_err() = "not a .fmi file (suffix-array header)"; return KJ_ERR_IO; }
     f->ids.resize((size_t)f->nseq); f->seq_taxon.resize((size_t)f->nseq);
     for (int32_t i = 0; i < f->nseq && r.ok; i++) {
         uint8_t l = r.get<uint8_t>(); std::string& s = f->ids[(size_t)i]; s.resize(l); r.bytes(l ? &s[0] : nullptr, l);
@@ -53,7 +56,7 @@ extern "C" int kj_fmi_load(const char* path, kj_fmi** out) {
     r.skip((int64_t)f->nseq * 4); r.skip((int64_t)f->nseq * 8);          // seqTermOrder, seqlengths: not needed for classification
     f->sa.resize((size_t)(f->ncheck * f->nbytes)); r.bytes(f->sa.data(), f->sa.size());
     int32_t alen2 = r.get<int32_t>(); f->bwtlen = r.get<int64_t>(); f->N1 = r.get<int32_t>(); f->N2 = r.get<int32_t>();
-    if (!r.ok || alen2 != f->alen || f->bwtlen <= 0) { fclose(fp); delete f; kj_err() = "not a .fmi file (FMI header)"; return KJ_ERR_IO; }
+    if (!r.ok || alen2 != f->alen || f->bwtlen <= 0 || f->bwtlen > fsize || f->N1 < 0 || f->N2 < 0) { fclose(fp); delete f; kj_err() = "not a .fmi file (FMI header)"; return KJ_ERR_IO; }
     f->bwt.resize((size_t)f->bwtlen); r.bytes(f->bwt.data(), f->bwt.size());
     r.skip((int64_t)f->N1 * f->alen * 8); r.skip((int64_t)f->N2 * f->alen * 2);   // index1/index2: rank tables are rebuilt in the device layout
     f->startLcode.resize((size_t)f->alen + 1); r.bytes(f->startLcode.data(), sizeof(int32_t) * ((size_t)f->alen + 1));
@@ -397,13 +400,28 @@ void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 const char kNativeMagic[8] = {'K', 'J', 'B', '2', '0', '0', 'I', 'X'};
-const uint32_t kNativeVersion = 2;
+const uint32_t kNativeVersion = 3;
 struct NativeHeader {
     uint32_t version, sizeof_tables, sizeof_rank, alen;
     uint64_t nb, bwtlen, C[KJ_MAX_ALEN + 1], sa_check; int64_t sa_bias; int32_t sa_exp; uint32_t nseq, n_present; int32_t kmer_k, wide, pad;
     double db_length; uint64_t quirk_lo, quirk_d[KJ_MAX_ALEN];
     uint64_t n_rank, n_letters, n_sa_tax, n_seq_tax, n_tax, n_lnfact, n_kmer, n_kmer32;
+    uint64_t checksum;          // over the bytes of all arrays, in file order (detects a damaged file before it reaches the GPU)
 };
+// order-sensitive 64-bit checksum (multiply-rotate over 8-byte words; not cryptographic)
+uint64_t mix_bytes(uint64_t h, const void* p, size_t n) {
+    const uint8_t* b = (const uint8_t*)p; size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, b + i, 8); h = (h ^ w) * 0x9E3779B97F4A7C15ull; h = (h << 29) | (h >> 35); }
+    uint64_t w = 0; if (i < n) memcpy(&w, b + i, n - i);
+    h = (h ^ w ^ (uint64_t)n) * 0x9E3779B97F4A7C15ull; return (h << 29) | (h >> 35);
+}
+template <class T> uint64_t mix_vec(uint64_t h, const std::vector<T>& v) { return mix_bytes(h, v.data(), v.size() * sizeof(T)); }
+uint64_t index_checksum(const KjHostIndex& H) {
+    uint64_t h = 0x6b616a755f623230ull;
+    h = mix_bytes(h, &H.tables, sizeof(KjTables)); h = mix_vec(h, H.rank); h = mix_vec(h, H.letters); h = mix_vec(h, H.sa_tax); h = mix_vec(h, H.seq_tax);
+    h = mix_vec(h, H.tax_parent); h = mix_vec(h, H.tax_depth); h = mix_vec(h, H.tax_id); h = mix_vec(h, H.lnfact); h = mix_vec(h, H.kmer); h = mix_vec(h, H.kmer32);
+    return h;
+}
 template <class T> bool put(FILE* f, const std::vector<T>& v) { return v.empty() || fwrite(v.data(), sizeof(T), v.size(), f) == v.size(); }
 template <class T> bool get(FILE* f, std::vector<T>& v, uint64_t n) { v.resize((size_t)n); return n == 0 || fread(v.data(), sizeof(T), (size_t)n, f) == (size_t)n; }
 }  // namespace
@@ -415,7 +433,7 @@ int kj_host_index_write(const KjHostIndex& H, const char* path) {
     h.nb = H.nb; h.bwtlen = H.bwtlen; memcpy(h.C, H.C, sizeof h.C); h.sa_check = H.sa_check; h.sa_bias = H.sa_bias; h.sa_exp = H.sa_exp; h.nseq = H.nseq; h.n_present = H.n_present;
     h.kmer_k = H.kmer_k; h.wide = H.wide; h.db_length = H.db_length; h.quirk_lo = H.quirk_lo; memcpy(h.quirk_d, H.quirk_d, sizeof h.quirk_d);
     h.n_rank = H.rank.size(); h.n_letters = H.letters.size(); h.n_sa_tax = H.sa_tax.size(); h.n_seq_tax = H.seq_tax.size(); h.n_tax = H.tax_id.size(); h.n_lnfact = H.lnfact.size();
-    h.n_kmer = H.kmer.size(); h.n_kmer32 = H.kmer32.size();
+    h.n_kmer = H.kmer.size(); h.n_kmer32 = H.kmer32.size(); h.checksum = index_checksum(H);
     bool ok = fwrite(kNativeMagic, 1, 8, f) == 8 && fwrite(&h, sizeof h, 1, f) == 1 && fwrite(&H.tables, sizeof(KjTables), 1, f) == 1 &&
               put(f, H.rank) && put(f, H.letters) && put(f, H.sa_tax) && put(f, H.seq_tax) && put(f, H.tax_parent) && put(f, H.tax_depth) && put(f, H.tax_id) &&
               put(f, H.lnfact) && put(f, H.kmer) && put(f, H.kmer32);
@@ -426,10 +444,13 @@ int kj_host_index_write(const KjHostIndex& H, const char* path) {
 
 int kj_host_index_read(const char* path, KjHostIndex& H) {
     FILE* f = fopen(path, "rb"); if (!f) { kj_err() = std::string("Could not open file ") + path; return KJ_ERR_IO; }
+    fseeko(f, 0, SEEK_END); const uint64_t fsize = (uint64_t)ftello(f); fseeko(f, 0, SEEK_SET);
     char magic[8]; NativeHeader h;
     bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, kNativeMagic, 8) == 0 && fread(&h, sizeof h, 1, f) == 1;
     if (!ok || h.version != kNativeVersion || h.sizeof_tables != sizeof(KjTables) || h.sizeof_rank != sizeof(KjRankBlock) || h.alen < 2 || h.alen > KJ_MAX_ALEN ||
-        h.n_rank != h.nb * h.alen || h.n_lnfact != 10001) { fclose(f); kj_err() = std::string(path) + " is not a device-native index of this library version"; return KJ_ERR_IO; }
+        h.n_rank != h.nb * h.alen || h.n_lnfact != 10001 ||
+        h.n_rank > fsize / sizeof(KjRankBlock) || h.n_letters > fsize / 8 || h.n_sa_tax > fsize / 4 || h.n_seq_tax > fsize / 4 || h.n_tax > fsize / 16 ||
+        h.n_kmer > fsize / sizeof(KjKmer) || h.n_kmer32 > fsize / sizeof(KjKmer32)) { fclose(f); kj_err() = std::string(path) + " is not a device-native index of this library version"; return KJ_ERR_IO; }
     H = KjHostIndex();
     H.alen = (int)h.alen; H.nb = h.nb; H.bwtlen = h.bwtlen; memcpy(H.C, h.C, sizeof h.C); H.sa_check = h.sa_check; H.sa_bias = h.sa_bias; H.sa_exp = h.sa_exp; H.nseq = h.nseq; H.n_present = h.n_present;
     H.kmer_k = h.kmer_k; H.wide = h.wide; H.db_length = h.db_length; H.quirk_lo = h.quirk_lo; memcpy(H.quirk_d, h.quirk_d, sizeof h.quirk_d);
@@ -437,6 +458,6 @@ int kj_host_index_read(const char* path, KjHostIndex& H) {
          get(f, H.tax_parent, h.n_tax) && get(f, H.tax_depth, h.n_tax) && get(f, H.tax_id, h.n_tax) && get(f, H.lnfact, h.n_lnfact) && get(f, H.kmer, h.n_kmer) && get(f, H.kmer32, h.n_kmer32);
     char extra; const bool at_end = fread(&extra, 1, 1, f) == 0;
     fclose(f);
-    if (!ok || !at_end || h.n_present > h.n_tax) { kj_err() = std::string(path) + " is truncated or corrupt"; return KJ_ERR_IO; }
+    if (!ok || !at_end || h.n_present > h.n_tax || index_checksum(H) != h.checksum) { kj_err() = std::string(path) + " is truncated or corrupt"; return KJ_ERR_IO; }
     return KJ_OK;
 }
