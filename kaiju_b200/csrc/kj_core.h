@@ -161,6 +161,7 @@ static KJ_DEV uint32_t kj_letter(const KjDevIndex& ix, uint64_t k) {
 // get_suffix (bwt.c:105-121) reduced to the taxon of the sequence the suffix lies in
 static KJ_DEV uint32_t kj_sa_taxon(const KjDevIndex& ix, uint64_t k) {
     uint32_t c = 1;
+    KJ_ROLLED
     while (c != 0 && (k & ix.sa_check)) { c = kj_letter(ix, k); const bool q = k >= ix.quirk_lo; k = kj_rank<uint64_t>(ix, c, k); if (q) k -= ix.quirk_d[c]; }
     if (c != 0) return ix.sa_tax[(uint64_t)((int64_t)(k >> ix.sa_exp) - ix.sa_bias)];
     return ix.seq_tax[k];
@@ -179,47 +180,100 @@ static KJ_DEV uint32_t kj_sa_taxon(const KjDevIndex& ix, uint64_t k) {
 #ifndef KJ_PHASE_A_LETTERS
 #define KJ_PHASE_A_LETTERS 9      // letters matched in phase A (k-mer + single steps)
 #endif
-#ifndef KJ_GROUP_FIRST
-#define KJ_GROUP_FIRST 8            // (A/B: 29.0 with 8 vs 28.7 with 2; DRAM is at ~3 % of peak, speculation is cheap)
+// chain state: OPEN = alive but not finished (phase-A survivor); EXACT = finished, i = leftmost start of the match ending at j and
+// [lo,hi) its interval; KDEAD = failed inside the k-mer look-up: the match is shorter than k letters, its start lies in [j-k+2, j+1]
+#define KJ_ST_OPEN 0
+#define KJ_ST_EXACT 1
+#define KJ_ST_KDEAD 2
+template <class IdxT> struct KjChain { IdxT lo, hi; int i; int st; };
+#if defined(KJ_EMU)
+struct KjEmuStats { unsigned long long rounds, round_steps, lane_steps, chains, blocks, lookaheads, pops_frag, pops_var, var_steps, var_pushed; };
+extern thread_local KjEmuStats kj_emu_stats;
 #endif
-#ifndef KJ_GROUP_NEXT
-#define KJ_GROUP_NEXT 8
-#endif
-//      KJ_GROUP_FIRST            // chains completed first in phase B: a full-length hit (i<=1) or a long match usually ends the fragment
-//      KJ_GROUP_NEXT             // then this many at a time
-template <class IdxT> struct KjChain { IdxT lo, hi; int i; bool done; };
 
 template <class IdxT>
 static KJ_DEV void kj_chain_start(const KjDevIndex& ix, const uint8_t* frag, int j, uint32_t Lmin, KjChain<IdxT>& ch) {
     const int k = ix.kmer_k; int i = j; int budget = KJ_PHASE_A_LETTERS - 1;
-    ch.done = false;
+    ch.st = KJ_ST_OPEN;
     if (k > 0 && j >= k && Lmin >= (uint32_t)k) {
         uint32_t idx = 0;
+        KJ_ROLLED
         for (int t = 0; t < k; t++) idx = idx * 20u + (uint32_t)(frag[j - t] - 1u);
         IdxT lo, hi;
         if (sizeof(IdxT) == 4) { const KjKmer32 e = ((const KjKmer32*)ix.kmer)[idx]; lo = (IdxT)e.lo; hi = (IdxT)e.hi; }
         else { const KjKmer e = ((const KjKmer*)ix.kmer)[idx]; lo = (IdxT)e.lo; hi = (IdxT)e.hi; }
-        if (lo >= hi) { ch.lo = 0; ch.hi = 0; ch.i = j + 1; ch.done = true; return; }       // failed inside the k-mer: length 0
+        if (lo >= hi) { ch.lo = 0; ch.hi = 0; ch.i = j + 1; ch.st = KJ_ST_KDEAD; return; }       // failed inside the k-mer: reported as length 0
         ch.lo = lo; ch.hi = hi; i = j - k + 1; budget = KJ_PHASE_A_LETTERS - k;
     } else {
         const uint32_t c = frag[j]; ch.lo = (IdxT)ix.C[c]; ch.hi = (IdxT)ix.C[c + 1];      // InitialSI (bwt.c:146-152)
     }
-    while (i > 0 && budget > 0) { if (!kj_update_si<IdxT>(ix, frag[i - 1], ch.lo, ch.hi)) { ch.done = true; break; } i--; budget--; }
-    if (i == 0) ch.done = true;
+    KJ_ROLLED
+    while (i > 0 && budget > 0) { if (!kj_update_si<IdxT>(ix, frag[i - 1], ch.lo, ch.hi)) { ch.st = KJ_ST_EXACT; break; } i--; budget--; }
+    if (i == 0) ch.st = KJ_ST_EXACT;
     ch.i = i;
 }
 template <class IdxT>
 static KJ_DEV void kj_chain_finish(const KjDevIndex& ix, const uint8_t* frag, KjChain<IdxT>& ch) {
     int i = ch.i;
+    KJ_ROLLED
     while (i > 0) { if (!kj_update_si<IdxT>(ix, frag[i - 1], ch.lo, ch.hi)) break; i--; }
-    ch.i = i; ch.done = true;
+    ch.i = i; ch.st = KJ_ST_EXACT;
 }
 // complete the selected chains (one lane each)
 template <class IdxT>
 static KJ_DEV void kj_finish_selected(const Warp& w, const KjDevIndex& ix, const uint8_t* frag, bool sel, KjChain<IdxT>& ch) {
+#if defined(KJ_EMU)
+    const int i0 = ch.i;
+#endif
     if (sel) kj_chain_finish<IdxT>(ix, frag, ch);
     w.sync();
+#if defined(KJ_EMU)
+    { const uint32_t st = sel ? (uint32_t)(i0 - ch.i) + 1u : 0u; const uint32_t mx = warp_max_u32(w, st); const uint32_t nsel = (uint32_t)kj_popc(w.ballot(sel));
+      uint32_t sum = st; for (int m = 16; m > 0; m >>= 1) sum += w.shfl_xor(sum, m);
+      if (w.lane == 0) { kj_emu_stats.rounds++; kj_emu_stats.round_steps += mx; kj_emu_stats.lane_steps += sum; kj_emu_stats.chains += nsel; } }
+#endif
 }
+
+// ---------------------------------------------------------------------------------------------
+// Which open chains of a block have to be completed at all?  On a true FM index the leftmost match start i_j is
+// monotone in the end position (item[i..j+1] occurs => item[i..j] occurs, so i_j <= i_{j+1}).  Every chain that ENDED below
+// an open chain therefore bounds its start from below: an exact chain j' < j gives i_j >= i_j', a chain that failed inside the
+// k-mer gives i_j >= j'-k+2.  lb = that bound from the nearest ended chain below (it is the largest one), taken from this block or
+// from the phase-A results of the next lower block (lb_ext).  With lb, many open chains are provably irrelevant without running
+// them (their match cannot reach the current L / cannot start left of an already recorded match, and lb >= 2 excludes the
+// `i<=1` break), which is exact: skipped chains are the ones whose result the reference computes and then discards.
+// The reference's checkpoint quirk (bwtlen = m * 2^16) breaks the monotonicity; such indexes run with ix.mono = 0 (no bounds).
+// ---------------------------------------------------------------------------------------------
+template <class IdxT>
+static KJ_DEV int kj_chain_lbval(const KjChain<IdxT>& ch, int j, int kk) { return ch.st == KJ_ST_EXACT ? ch.i : (j - kk + 2 > 0 ? j - kk + 2 : 0); }
+template <class IdxT>
+static KJ_DEV int kj_chain_lb(const Warp& w, const KjChain<IdxT>& ch, bool probe, int j, int kk, int lb_ext) {
+    const uint32_t inf = w.ballot(probe && ch.st != KJ_ST_OPEN);
+    const uint32_t below = w.lane < 31 ? inf & ~((2u << w.lane) - 1u) : 0u;
+    const int v = w.shfl(kj_chain_lbval<IdxT>(ch, j, kk), below ? kj_ffs(below) - 1 : 0);
+    return below ? v : lb_ext;
+}
+// the bound a block hands to the block above it: lbval of its first ended chain (0 if it has none)
+template <class IdxT>
+static KJ_DEV int kj_block_lb_ext(const Warp& w, const KjChain<IdxT>& ch, bool probe, int j, int kk) {
+    const uint32_t inf = w.ballot(probe && ch.st != KJ_ST_OPEN);
+    const int v = w.shfl(kj_chain_lbval<IdxT>(ch, j, kk), inf ? kj_ffs(inf) - 1 : 0);
+    return inf ? v : 0;
+}
+// exclusive prefix maximum / minimum over the lanes (lane 0 gets `init`)
+static KJ_DEV uint32_t kj_prefix_max_excl(const Warp& w, uint32_t v, uint32_t init) {
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = w.shfl(v, w.lane - d); if (w.lane >= d && o > v) v = o; }
+    const uint32_t e = w.shfl(v, w.lane - 1);
+    return w.lane == 0 ? init : (e > init ? e : init);
+}
+static KJ_DEV uint32_t kj_prefix_min_excl(const Warp& w, uint32_t v, uint32_t init) {
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = w.shfl(v, w.lane - d); if (w.lane >= d && o < v) v = o; }
+    const uint32_t e = w.shfl(v, w.lane - 1);
+    return w.lane == 0 ? init : (e < init ? e : init);
+}
+#ifndef KJ_GROUP_LATE
+#define KJ_GROUP_LATE 8            // chains completed per round once the first round (segment tops only) did not settle a block
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // fragment queue (std::multimap<unsigned,Fragment*,greater>, ConsumerThread.hpp:83): highest key first,
@@ -245,8 +299,10 @@ static KJ_DEV void kj_queue_emit(KjWarpCtx& cx, KjQueue& q, bool emit, uint32_t 
 // no SEG piece has been pushed (rare) a pop is three broadcast shared-memory reads instead of a warp arg-max.
 static KJ_DEV void kj_queue_sort(KjWarpCtx& cx, KjQueue& q) {
     cx.w.sync();
+    KJ_ROLLED
     for (uint32_t i = (uint32_t)cx.w.lane; i < q.n; i += 32) {
         const uint64_t mine = q.key[i]; uint32_t rank = 0;
+        KJ_ROLLED
         for (uint32_t j = 0; j < q.n; j++) rank += q.key[j] > mine ? 1u : 0u;
         q.ord[rank] = (uint8_t)i;
     }
@@ -265,6 +321,7 @@ static KJ_DEV bool kj_queue_pop(KjWarpCtx& cx, KjQueue& q, uint32_t min_val, uin
     }
     cx.w.sync();
     uint64_t best = 0; uint32_t slot = 0;
+    KJ_ROLLED
     for (uint32_t s = (uint32_t)cx.w.lane; s < q.n; s += 32) { uint64_t k = q.key[s]; if (k > best) { best = k; slot = s; } }
     uint64_t g = warp_max_u64(cx.w, best);
     if (g == 0) return false;
@@ -282,6 +339,7 @@ static KJ_DEV bool kj_queue_pop(KjWarpCtx& cx, KjQueue& q, uint32_t min_val, uin
 static KJ_DEV void kj_queue_make_dirty(KjWarpCtx& cx, KjQueue& q) {
     if (q.dirty) return;
     cx.w.sync();
+    KJ_ROLLED
     for (uint32_t k = (uint32_t)cx.w.lane; k < q.next; k += 32) q.key[q.ord[k]] = 0;
     q.dirty = true;
     cx.w.sync();
@@ -306,11 +364,13 @@ static KJ_DEV void kj_split_frames(KjWarpCtx& cx, KjQueue& q, const int na1, con
     // operations instead of a serial scan.  Insertion order (ConsumerThread.cpp:196-268): runs closed by a stop in scan
     // order of that stop; leftovers afterwards in frame order 0,1,2 where frame = count % 3 in FORWARD coordinates.
     const uint32_t m = cx.rp->m;
+    KJ_ROLLED
     for (int r = 0; r < nframes; r++) {
         const int ne1 = (na1 - r + 2) / 3, ne2 = (na2 - r + 2) / 3;      // elements e: array index r + 3e
         const int nemax = ne1 > ne2 ? ne1 : ne2;
         int run_open[4] = {0, 0, 0, 0};                                  // first element after the last stop of the earlier chunks (uniform)
         uint32_t p_open[4] = {0, 0, 0, 0}, p_carry[4] = {0, 0, 0, 0};    // greedy: score prefix at run_open-1 / at the end of the previous chunk (uniform)
+        KJ_ROLLED
         for (int e0 = 0; e0 < nemax; e0 += 32) {
             const int e = e0 + w.lane;
             bool in[4], stop[4]; uint32_t sm[4], pre[4];
@@ -370,6 +430,7 @@ static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s
     const int na1 = do1 ? n1 - 2 : 0, na2 = do2 ? n2 - 2 : 0;
     const int namax = na1 > na2 ? na1 : na2;
     // 30 codon positions per pass: every lane decodes ONE base per mate, its two successors come from the next lanes
+    KJ_ROLLED
     for (int b = 0; b < namax; b += 30) {
         const int pos = b + w.lane;
         const uint32_t x0 = (do1 && pos < n1) ? kj_nuc(s1[pos]) : 4u, y0 = (do2 && pos < n2) ? kj_nuc(s2[pos]) : 4u;
@@ -395,6 +456,7 @@ static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s
 static KJ_DEV void kj_load_frag(KjWarpCtx& cx, uint32_t arr, uint32_t start, uint32_t len) {
     const uint8_t* A = cx.smem + cx.L.aa_off + arr * cx.L.aa_stride;
     uint8_t* frag = cx.smem + cx.L.frag_off;
+    KJ_ROLLED
     for (uint32_t t = (uint32_t)cx.w.lane; t < len; t += 32) frag[t] = A[start + 3u * t];
     cx.w.sync();
 }
@@ -416,6 +478,7 @@ struct KjSeg { int begin, end; };
 static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
     const uint8_t* frag = cx.smem + cx.L.frag_off; uint8_t* hf = cx.smem + cx.L.hflag_off; const KjTables& tb = *cx.tb;
     bool any_low = false;
+    KJ_ROLLED
     for (int p0 = 0; p0 + KJ_SEG_WINDOW <= n; p0 += 32) {
         const int p = p0 + cx.w.lane; uint32_t flags = 0;
         if (p + KJ_SEG_WINDOW <= n) {
@@ -426,6 +489,7 @@ static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
             for (int t = 0; t < 4; t++) { seen |= 1u << ((w0 >> (8 * t)) & 0xffu); seen |= 1u << ((w1 >> (8 * t)) & 0xffu); seen |= 1u << ((w2 >> (8 * t)) & 0xffu); }
             if (kj_popc(seen) < 8) {
                 int32_t x = 0;
+                KJ_ROLLED
                 while (seen) {
                     const uint32_t a = (uint32_t)kj_ffs(seen) - 1u; seen &= seen - 1u;
                     const uint32_t a4 = a * 0x01010101u;
@@ -446,19 +510,21 @@ static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
 // composition of its sliding window as a descending-sorted count vector (the reference's state vector, s_StateOn
 // 1628-1650): a count changes by +-1 per step, so the vector stays sorted by swapping the changed letter to the edge
 // of its run of equal counts.  s_GetProb then walks the 20 sorted counts in the reference's order.
-static KJ_DEV void kj_seg_trim_long(KjWarpCtx& cx, const uint8_t* s, int n2, int& leftend, int& rightend) {
-    const Warp& w = cx.w;
-    uint16_t* sv = (uint16_t*)(cx.smem + cx.L.segcnt_off);            // [20][32] counts, descending per lane
+// (a real function, like kj_seg_trim: the trim search is large and rarely the warp's hot path -- inlined copies of it cost
+// instruction-cache space in every kernel.  Returns best_start << 16 | best_end inside s[0..n2).)
+KJ_NOINLINE uint32_t kj_seg_trim_long(const Warp w, uint8_t* scratch, const uint8_t* s, int n2, const double* lnf) {
+    uint16_t* sv = (uint16_t*)scratch;                                // [20][32] counts, descending per lane
     uint8_t* at = (uint8_t*)(sv + 20 * 32);                            // [20][32] letter stored at sorted position k
     uint8_t* where = at + 20 * 32;                                     // [20][32] sorted position of letter a
-    const double* lnf = cx.ix->lnfact;
     int minlen = 1; if (n2 - KJ_SEG_MAXTRIM > minlen) minlen = n2 - KJ_SEG_MAXTRIM;
     const int nlens = n2 - minlen;
     double g_prob = 1.0; int g_lend = 0, g_rend = n2 - 1;            // uniform
     const int ln = w.lane;
+    KJ_ROLLED
     for (int pass = 0; pass * 32 < nlens; pass++) {
         const int len = n2 - (pass * 32 + ln);
         const bool act = (pass * 32 + ln) < nlens;
+        KJ_ROLLED
         for (int k = 0; k < 20; k++) { sv[k * 32 + ln] = 0; at[k * 32 + ln] = (uint8_t)k; where[k * 32 + ln] = (uint8_t)k; }
         double my_prob = 1.0; int my_i = 0;
         if (act) {
@@ -468,11 +534,14 @@ static KJ_DEV void kj_seg_trim_long(KjWarpCtx& cx, const uint8_t* s, int n2, int
                 while (q_ > 0 && sv[(q_ - 1) * 32 + ln] == v_) q_--; if (q_ != p_) KJ_SV_SWAP(p_, q_); sv[q_ * 32 + ln] = (uint16_t)(v_ + 1u); }
             #define KJ_SV_DEL(letter) { const uint32_t a_ = (letter) - 1u; uint32_t p_ = where[a_ * 32 + ln]; const uint32_t v_ = sv[p_ * 32 + ln]; uint32_t q_ = p_; \
                 while (q_ < 19 && sv[(q_ + 1) * 32 + ln] == v_) q_++; if (q_ != p_) KJ_SV_SWAP(p_, q_); sv[q_ * 32 + ln] = (uint16_t)(v_ - 1u); }
+            KJ_ROLLED
             for (int t = 0; t < len; t++) KJ_SV_ADD(s[t]);
+            KJ_ROLLED
             for (int i = 0; i + len <= n2; i++) {
                 // s_GetProb (1941-1962) = s_LnAss (1890-1930) + s_LnPerm (1865-1879) - len*ln20, same operation order
                 double ans1 = lnf[20], ans2 = lnf[len];
                 int k = 0;
+                KJ_ROLLED
                 while (k < 20) {
                     const uint32_t v = sv[k * 32 + ln];
                     int cls = 1; while (k + cls < 20 && sv[(k + cls) * 32 + ln] == v) cls++;
@@ -497,24 +566,25 @@ static KJ_DEV void kj_seg_trim_long(KjWarpCtx& cx, const uint8_t* s, int n2, int
             g_prob = mn; g_lend = wi; g_rend = wlen + wi - 1;
         }
     }
-    leftend += g_lend; rightend -= (n2 - g_rend - 1);
+    return ((uint32_t)g_lend << 16) | (uint32_t)g_rend;
 }
 
 // s_Trim (blast_seg.c:1971-2015): the sub-window of s[0..n2) with minimal s_GetProb; first in
 // (len descending, start ascending) order wins ties.  One lane per window length, sliding start.
-static KJ_DEV void kj_seg_trim(KjWarpCtx& cx, const uint8_t* s, int n2, int& leftend, int& rightend) {
-    if (n2 > 127) { kj_seg_trim_long(cx, s, n2, leftend, rightend); return; }
-    const Warp& w = cx.w;
-    uint8_t* cnt = cx.smem + cx.L.segcnt_off;       // [20][32]
-    uint8_t* hist = cx.smem + cx.L.seghist_off;     // [n2+1][32] number of letters having count v
-    const double* lnf = cx.ix->lnfact;
+KJ_NOINLINE uint32_t kj_seg_trim(const Warp w, uint8_t* scratch, const uint8_t* s, int n2, const double* lnf) {
+    if (n2 > 127) return kj_seg_trim_long(w, scratch, s, n2, lnf);
+    uint8_t* cnt = scratch;                         // [20][32]
+    uint8_t* hist = scratch + 20u * 32u;            // [n2+1][32] number of letters having count v
     int minlen = 1; if (n2 - KJ_SEG_MAXTRIM > minlen) minlen = n2 - KJ_SEG_MAXTRIM;
     const int nlens = n2 - minlen;
     double g_prob = 1.0; int g_lend = 0, g_rend = n2 - 1;            // uniform
+    KJ_ROLLED
     for (int pass = 0; pass * 32 < nlens; pass++) {
         const int len = n2 - (pass * 32 + w.lane);
         const bool act = (pass * 32 + w.lane) < nlens;
+        KJ_ROLLED
         for (int a = 0; a < 20; a++) cnt[a * 32 + w.lane] = 0;
+        KJ_ROLLED
         for (int v = 0; v <= n2; v++) hist[v * 32 + w.lane] = 0;
         uint64_t m0 = 0, m1 = 0; int nz = 0;                          // bit v set <=> hist[v] > 0 (v < 128)
         double my_prob = 1.0; int my_i = 0;
@@ -525,17 +595,21 @@ static KJ_DEV void kj_seg_trim(KjWarpCtx& cx, const uint8_t* s, int n2, int& lef
             #define KJ_SEG_DEL(letter) { uint32_t a_ = (letter) - 1u; uint32_t c_ = cnt[a_ * 32 + w.lane]; \
                 { uint8_t h_ = --hist[c_ * 32 + w.lane]; if (h_ == 0) { if (c_ < 64) m0 &= ~(1ull << c_); else m1 &= ~(1ull << (c_ - 64)); } } \
                 cnt[a_ * 32 + w.lane] = (uint8_t)(c_ - 1); if (c_ > 1) { hist[(c_ - 1) * 32 + w.lane]++; if (c_ - 1 < 64) m0 |= 1ull << (c_ - 1); else m1 |= 1ull << (c_ - 1 - 64); } else nz--; }
+            KJ_ROLLED
             for (int t = 0; t < len; t++) KJ_SEG_ADD(s[t]);
+            KJ_ROLLED
             for (int i = 0; i + len <= n2; i++) {
                 // s_GetProb (1941-1962) = s_LnAss (1890-1930) + s_LnPerm (1865-1879) - len*ln20, same operation order
                 double ans1 = lnf[20], ans2 = lnf[len];
                 uint64_t a0 = m0, a1 = m1;
+                KJ_ROLLED
                 while (a0 | a1) {
                     int v;                                           // highest set bit of the 128-bit mask = next larger count
                     if (a1) { v = 64 + kj_hibit64(a1); a1 &= ~(1ull << (v - 64)); }
                     else { v = kj_hibit64(a0); a0 &= ~(1ull << v); }
                     int cls = hist[v * 32 + w.lane];
                     ans1 = kj_dsub(ans1, lnf[cls]);
+                    KJ_ROLLED
                     for (int rep = 0; rep < cls; rep++) ans2 = kj_dsub(ans2, lnf[v]);
                 }
                 if (nz < 20) ans1 = kj_dsub(ans1, lnf[20 - nz]);
@@ -556,7 +630,7 @@ static KJ_DEV void kj_seg_trim(KjWarpCtx& cx, const uint8_t* s, int n2, int& lef
             g_prob = mn; g_lend = wi; g_rend = wlen + wi - 1;
         }
     }
-    leftend += g_lend; rightend -= (n2 - g_rend - 1);
+    return ((uint32_t)g_lend << 16) | (uint32_t)g_rend;
 }
 
 // s_SegSeq (blast_seg.c:2027-2113) on frag[s0 .. s0+n).  LEVEL 0 collects regions; LEVEL 1 is the
@@ -567,12 +641,14 @@ static KJ_DEV int kj_seg_level(KjWarpCtx& cx, int s0, int n, KjSeg* segs, int ns
     const uint8_t* frag = cx.smem + cx.L.frag_off; const uint8_t* hf = cx.smem + cx.L.hflag_off;
     if (KJ_SEG_WINDOW > n) return nsegs;
     const int first = KJ_SEG_DOWNSET, last = n - KJ_SEG_UPSET; int lowlim = first;
+    KJ_ROLLED
     for (int i = first; i <= last; i++) {
         if (hf[s0 + i - KJ_SEG_DOWNSET] & 1) {
             int j = i; while (j >= lowlim && (hf[s0 + j - KJ_SEG_DOWNSET] & 2)) j--; const int loi = j + 1;         // s_FindLow
             j = i; while (j <= last && (hf[s0 + j - KJ_SEG_DOWNSET] & 2)) j++; const int hii = j - 1;               // s_FindHigh
             int leftend = loi - KJ_SEG_DOWNSET, rightend = hii + KJ_SEG_UPSET - 1;
-            kj_seg_trim(cx, frag + s0 + leftend, rightend - leftend + 1, leftend, rightend);
+            { const int n2 = rightend - leftend + 1; const uint32_t tr = kj_seg_trim(cx.w, cx.smem + cx.L.segcnt_off, frag + s0 + leftend, n2, cx.ix->lnfact);
+              leftend += (int)(tr >> 16); rightend -= n2 - (int)(tr & 0xffffu) - 1; }
             if (LEVEL == 0 && i + KJ_SEG_UPSET - 1 < leftend) {
                 const int lend = loi - KJ_SEG_DOWNSET, rend = leftend - 1;
                 KjSeg tmp; tmp.begin = -1; tmp.end = -1;
@@ -604,6 +680,7 @@ static KJ_DEV int kj_seg(KjWarpCtx& cx, int n) {
             // emulate on an index-linked view: nxt[i] = i-1
             // merged entries are marked begin = -1
             int nx = cur - 1;
+            KJ_ROLLED
             while (nx >= 0) {
                 if (segs[cur].begin - segs[nx].end - 1 < 0) {
                     if (segs[cur].end < segs[nx].end) segs[cur].end = segs[nx].end;
@@ -639,12 +716,15 @@ static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
     const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix;
     uint32_t* ids = (uint32_t*)(cx.smem + cx.L.ids_off);
     uint32_t nids = 0;                                                    // uniform
+    KJ_ROLLED
     for (uint32_t e = 0; e < nkept && nids <= 20; e++) {
         KjKept kk = *kj_kept_ptr(cx, e);
+        KJ_ROLLED
         for (uint32_t base = 0; base < kk.len && nids <= 20; base += 32) {
             uint32_t t = base + (uint32_t)w.lane; bool act = t < kk.len;
             uint32_t tax = act ? kj_sa_taxon(ix, kk.lo + t) : KJ_TAX_BAD;
             uint32_t nact = kk.len - base < 32u ? kk.len - base : 32u;
+            KJ_ROLLED
             for (uint32_t s = 0; s < nact && nids <= 20; s++) {
                 uint32_t id = w.shfl(tax, (int)s);
                 if (id == KJ_TAX_BAD) continue;
@@ -666,6 +746,7 @@ static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
     uint32_t shallow = warp_min_u32(w, present ? depth : 0xffffffffu);
     if (present) for (uint32_t d = depth; d > shallow; d--) id = ix.tax_parent[id];
     int first = kj_ffs(pm) - 1;
+    KJ_ROLLED
     for (uint32_t guard = 0; guard <= shallow + 1; guard++) {
         uint32_t f = w.shfl(id, first);
         bool diff = present && id != f;
@@ -687,6 +768,7 @@ static KJ_DEV bool kj_seg_gate(KjWarpCtx& cx, KjQueue& q, uint32_t arr, uint32_t
     const KjSeg* segs = (const KjSeg*)(cx.smem + cx.L.segs_off);
     const uint8_t* frag = cx.smem + cx.L.frag_off; const KjTables& tb = *cx.tb;
     uint32_t st = 0;
+    KJ_ROLLED
     for (int s = 0; s <= ns; s++) {
         int plen = (s < ns ? segs[s].begin : (int)len) - (int)st;         // non-masked piece [st, st+plen)
         if (plen > (int)cx.rp->m) {                                        // strict '>' for pieces (298, 312)
@@ -714,37 +796,77 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
         // greedyExact(f, seq, len, max(m,longest), -1) (bwt.c:347-380): chains for j = len-1 .. L-1, L growing
         uint32_t L = rp.m > longest ? rp.m : longest;
         uint32_t item_best = 0, item_cnt = 0;                             // uniform
-        bool broke = false;
-        for (int jhi = (int)len - 1; !broke && jhi >= (int)L - 1; jhi -= 32) {
-            const int j = jhi - w.lane; const bool act = j >= (int)L - 1;
-            KjChain<IdxT> ch; ch.lo = 0; ch.hi = 0; ch.i = 0; ch.done = true;
-            if (act) kj_chain_start<IdxT>(ix, frag, j, rp.m, ch);                         // phase A
-            w.sync();
-            uint32_t Lc = L; bool valid = false; int group = KJ_GROUP_FIRST;
-            for (;;) {                                                                      // phase B
-                // `if (i<=1) break` (bwt.c:376): lanes below the first finished lane with i<=1 were never run by the reference
-                const uint32_t brk = w.ballot(act && ch.done && ch.i <= 1);
-                const int cut = brk ? kj_ffs(brk) - 1 : 31; broke = brk != 0;
-                valid = act && w.lane <= cut;
-                const uint32_t ldone = (valid && ch.done) ? (uint32_t)(j - ch.i + 1) : 0u;
-                const uint32_t lmax = warp_max_u32(w, ldone);
-                Lc = lmax > L ? lmax : L;                                                   // L after the finished chains
-                const bool elig = valid && !ch.done && j >= (int)Lc - 1;                    // the j-loop bound with the grown L
-                const uint32_t em = w.ballot(elig);
-                if (!em) break;
-                const bool sel = elig && kj_popc(em & lanemask_lt(w.lane)) < group;
-                kj_finish_selected<IdxT>(w, ix, frag, sel, ch);
-                group = KJ_GROUP_NEXT;
+        const bool mono = ix.mono != 0; const int kk = ix.kmer_k;
+        // blocks of 32 end positions, j descending.  Every lane with j >= 0 runs phase A (chains below the scan range j >= L-1 only
+        // serve as bounds); the block below is started early only when the lowest open chains of this block need its bound.
+        // One loop with a single phase-A site and a single completion site (code size: the instruction cache is the scarce resource).
+        int jhi = (int)len - 1, jstart = jhi, round = 0; bool start_la = false, have_nxt = false;
+        KjChain<IdxT> cur, nxt;
+        cur.lo = 0; cur.hi = 0; cur.i = 0; cur.st = KJ_ST_EXACT; nxt = cur;
+        KJ_ROLLED
+        for (;;) {
+            if (jstart >= 0) {                                                              // phase A of the block whose top end position is jstart
+                KjChain<IdxT> t; t.lo = 0; t.hi = 0; t.i = 0; t.st = KJ_ST_EXACT;
+                if (jstart - w.lane >= 0) kj_chain_start<IdxT>(ix, frag, jstart - w.lane, rp.m, t);
+                w.sync();
+                if (start_la) { nxt = t; have_nxt = true; } else { cur = t; round = 0; }
+                jstart = -1;
+#if defined(KJ_EMU)
+                if (w.lane == 0) { if (start_la) kj_emu_stats.lookaheads++; else kj_emu_stats.blocks++; }
+#endif
             }
-            const uint32_t l = (valid && ch.done) ? (uint32_t)(j - ch.i + 1) : 0u;
-            if (Lc >= L && warp_max_u32(w, l) >= L) {
-                const uint32_t lmax = Lc;
+            const int j = jhi - w.lane; const bool probe = j >= 0; const bool act = j >= (int)L - 1;
+            // `if (i<=1) break` (bwt.c:376): lanes below the first finished lane with i<=1 were never run by the reference
+            const uint32_t brk = w.ballot(act && cur.st == KJ_ST_EXACT && cur.i <= 1);
+            const int cut = brk ? kj_ffs(brk) - 1 : 31;
+            const bool open = act && cur.st == KJ_ST_OPEN && w.lane <= cut;
+            const uint32_t om = w.ballot(open);
+            uint32_t nm = 0; bool need = false;
+            if (om) {                                                                       // phase B: which open chains have to be completed?
+                int lb = 0;
+                if (mono) {
+                    int lb_ext = 0;
+                    if (round > 0 && !have_nxt && jhi - 32 >= 0) {
+                        // (not before the first round: a full-length match ends the fragment with one chain.)  The lowest open chain
+                        // has no ended chain below it in this block: fetch the bound from the next block's phase A
+                        const uint32_t inf = w.ballot(probe && cur.st != KJ_ST_OPEN);
+                        if ((31 - kj_clz(om)) > (inf ? 31 - kj_clz(inf) : -1)) { jstart = jhi - 32; start_la = true; continue; }
+                    }
+                    if (have_nxt) lb_ext = kj_block_lb_ext<IdxT>(w, nxt, jhi - 32 - w.lane >= 0, jhi - 32 - w.lane, kk);
+                    lb = kj_chain_lb<IdxT>(w, cur, probe, j, kk, lb_ext);
+                }
+                // L as the reference holds it when it reaches lane x: the finished chains above x (the open ones above x are completed
+                // before x can be skipped for good: the test is repeated every round)
+                const uint32_t exl = (act && cur.st == KJ_ST_EXACT && w.lane <= cut) ? (uint32_t)(j - cur.i + 1) : 0u;
+                const uint32_t Lb = kj_prefix_max_excl(w, exl, L);
+                need = open && j >= (int)Lb - 1 && !(lb >= 2 && (uint32_t)(j - lb + 1) < Lb);
+                nm = w.ballot(need);
+            }
+            if (nm) {
+                // first round: only the top chain of every run of open chains (it settles the whole run when it reaches the bound);
+                // later rounds: the next few chains in descending j as well
+                const bool top = need && !(w.lane > 0 && ((nm >> (w.lane - 1)) & 1u));
+                const int group = (round == 0 && mono) ? 0 : KJ_GROUP_LATE;
+                const bool sel = need && (top || kj_popc(nm & lanemask_lt(w.lane)) < group);
+                kj_finish_selected<IdxT>(w, ix, frag, sel, cur);
+                round++;
+                continue;
+            }
+            // the block is settled
+            const bool valid = act && w.lane <= cut;
+            const uint32_t l = (valid && cur.st == KJ_ST_EXACT) ? (uint32_t)(j - cur.i + 1) : 0u;
+            const uint32_t lmax = warp_max_u32(w, l);
+            if (lmax >= L) {
                 if (lmax > item_best) { item_best = lmax; item_cnt = 0; }
                 L = lmax;
                 const uint32_t wm = w.ballot(l == item_best && l > 0);
-                if (l == item_best && l > 0) { KjKept* k = kj_kept_ptr(cx, nkept + item_cnt + (uint32_t)kj_popc(wm & lanemask_lt(w.lane))); k->lo = (uint64_t)ch.lo; k->len = (uint32_t)(ch.hi - ch.lo); k->aux = 0; }
+                if (l == item_best && l > 0) { KjKept* k = kj_kept_ptr(cx, nkept + item_cnt + (uint32_t)kj_popc(wm & lanemask_lt(w.lane))); k->lo = (uint64_t)cur.lo; k->len = (uint32_t)(cur.hi - cur.lo); k->aux = 0; }
                 item_cnt += (uint32_t)kj_popc(wm);
             }
+            jhi -= 32;
+            if (brk || jhi < (int)L - 1) break;
+            round = 0;
+            if (have_nxt) { cur = nxt; have_nxt = false; } else { jstart = jhi; start_la = false; }
         }
         w.sync();
         // the SEG gate of getNextFragment (ConsumerThread.cpp:285-339), now that the fragment has a match >= L: if SEG masks
@@ -752,6 +874,7 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
         if (item_cnt > 0 && rp.seg && !segchecked && kj_seg_gate(cx, q, arr, start, len, false)) return true;
         if (item_cnt > 0) {
             // winners were appended j-descending; the reference's chain is newest (smallest j) first
+            KJ_ROLLED
             for (uint32_t t = (uint32_t)w.lane; t < item_cnt / 2; t += 32) {
                 KjKept* a = kj_kept_ptr(cx, nkept + t); KjKept* b = kj_kept_ptr(cx, nkept + item_cnt - 1 - t);
                 KjKept x = *a; *a = *b; *b = x;
@@ -759,6 +882,7 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
             w.sync();
             if (item_best > longest) {                                    // replace (ConsumerThread.cpp:574-585)
                 if (nkept > 0) {
+                    KJ_ROLLED
                     for (uint32_t t0 = 0; t0 < item_cnt; t0 += 32) {      // move down, chunk by chunk (src index > dst index)
                         uint32_t t = t0 + (uint32_t)w.lane; KjKept x; x.lo = 0; x.len = 0; x.aux = 0;
                         if (t < item_cnt) x = *kj_kept_ptr(cx, nkept + t);
@@ -777,6 +901,7 @@ template <class IdxT>
 static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best_out) {
     uint32_t longest = 0, nkept = 0;                                      // uniform
     uint32_t val, pay;
+    KJ_ROLLED
     while (kj_queue_pop(cx, q, longest, val, pay)) kj_mem_item<IdxT>(cx, q, pay, longest, nkept);
     best_out = 0;
     if (nkept == 0) return KJ_TAX_BAD;
@@ -799,6 +924,7 @@ template <class IdxT> static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, K
 static KJ_DEV void kj_protein_fragments(KjWarpCtx& cx, KjQueue& q, const uint8_t* s1, int n1, bool greedy) {
     const Warp& w = cx.w; const KjTables& tb = *cx.tb;
     uint8_t* aa = cx.smem + cx.L.aa_off;
+    KJ_ROLLED
     for (int t = w.lane; t < n1; t += 32) {
         const uint32_t u = s1[t] & 0xDFu;                                // in 'A'..'Z' exactly for ASCII letters (toupper)
         aa[3 * t] = (u >= 'A' && u <= 'Z') ? tb.aa_index[u - 'A'] : (uint8_t)0;

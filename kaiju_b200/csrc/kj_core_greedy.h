@@ -31,6 +31,7 @@ struct KjVQueue { uint64_t* gkey; KjVariant* v; uint32_t n, live;      // n: hig
 // compact live variants to the front (called when the ring is full)
 static KJ_DEV void kj_vq_compact(KjWarpCtx& cx, KjVQueue& vq) {
     const Warp& w = cx.w; uint32_t out = 0;
+    KJ_ROLLED
     for (uint32_t b = 0; b < vq.n; b += 32) {
         uint32_t s = b + (uint32_t)w.lane; bool live = s < vq.n && vq.key(s) != 0;
         KjVariant tmp; uint64_t tk = 0; if (live) { tmp = vq.v[s]; tk = vq.key(s); }
@@ -61,15 +62,18 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
     uint32_t best = 0, nbest = 0;                                        // best_match_score, best_matches_SI.size()  (uniform)
     best_out = 0;
 
+    KJ_ROLLED
     for (;;) {
         // ---------------- getNextFragment(best): top of both queues (ConsumerThread.cpp:272-283)
         w.sync();
         uint64_t kb = 0; uint32_t slot_b = 0;
+        KJ_ROLLED
         for (uint32_t s = (uint32_t)w.lane; s < vq.n; s += 32) { uint64_t k = vq.key(s); if (k > kb) { kb = k; slot_b = s; } }
         uint64_t gb = warp_max_u64(w, kb);
         uint64_t ka = 0, ga = 0; uint32_t slot_a = 0;
         if (!q.dirty) { if (q.next < q.nsorted) { slot_a = q.ord[q.next]; ga = q.key[slot_a]; } }      // sorted prefix: the top is known
         else {
+            KJ_ROLLED
             for (uint32_t s = (uint32_t)w.lane; s < q.n; s += 32) { uint64_t k = q.key[s]; if (k > ka) { ka = k; slot_a = s; } }
             ga = warp_max_u64(w, ka);
         }
@@ -86,7 +90,13 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
                 p = w.shfl(p, src);
             }
             arr = p >> 30; segchecked = (p >> 29) & 1u; start = (p >> 14) & 0x7fffu; len = p & 0x3fffu;
+#if defined(KJ_EMU)
+            if (w.lane == 0) kj_emu_stats.pops_frag++;
+#endif
         } else {
+#if defined(KJ_EMU)
+            if (w.lane == 0) kj_emu_stats.pops_var++;
+#endif
             int src = kj_ffs(w.ballot(kb == g)) - 1; uint32_t sl = w.shfl(slot_b, src);
             const KjVariant& V = vq.v[sl];
             uint32_t p = V.pay; arr = p >> 30; start = (p >> 14) & 0x7fffu; len = p & 0x3fffu; segchecked = true;
@@ -104,6 +114,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
         // prefix sums of the BLOSUM62 diagonal (calcScore, ConsumerThread.cpp:397-421)
         {
             uint32_t carry = 0;
+            KJ_ROLLED
             for (uint32_t b = 0; b < len; b += 32) {
                 uint32_t t = b + (uint32_t)w.lane; uint32_t a = t < len ? frag[t] : 0u;
                 uint32_t d = t < len ? (uint32_t)tb.b62[a][a] : 0u;
@@ -120,37 +131,81 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
         if (num_mm > 0) {
             // maxMatches_withStart (bwt.c:298-336): extend the stored interval leftwards from len - matchlen
             // one chain: lanes 0/1 compute the lower/upper interval end (kj_finish_paired on a one-chain selection)
-            KjChain<IdxT> one; one.lo = (IdxT)si0; one.hi = (IdxT)si1; one.i = (int)len - (int)matchlen; one.done = false;
+            KjChain<IdxT> one; one.lo = (IdxT)si0; one.hi = (IdxT)si1; one.i = (int)len - (int)matchlen; one.st = KJ_ST_OPEN;
+#if defined(KJ_EMU)
+            const int i0_ = one.i;
+#endif
             kj_chain_finish<IdxT>(ix, frag, one);                          // every lane runs the same chain: identical addresses, one sector per step
+#if defined(KJ_EMU)
+            if (w.lane == 0) kj_emu_stats.var_steps += (unsigned long long)(i0_ - one.i + 1);
+#endif
             const IdxT lo = one.lo, hi = one.hi; const int i = one.i;
             uint32_t l = len - (uint32_t)i;
             uint32_t Lreq = (num_mm == rp.e) ? rp.m : matchlen;           // ConsumerThread.cpp:445-450
             if (l >= Lreq) { if (w.lane == 0) { cls[0].lo = (uint64_t)lo; cls[0].len = (uint32_t)(hi - lo); cls[0].qi = (uint16_t)i; cls[0].ql = (uint16_t)l; } nrec = 1; }
             w.sync();
         } else {
-            // maxMatches(f, seq, len, seed_length, 0) (bwt.c:261-296): one chain per end position j
+            // maxMatches(f, seq, len, seed_length, 0) (bwt.c:261-296): one chain per end position j.  Every chain above the `i<=1` break
+            // is run by the reference, but only those whose match starts left of every longer-ending recorded match are kept: with the
+            // bounds of kj_chain_lb most open chains are known not to be recorded without completing them.
             const int L = (int)rp.seed_length;
-            int jlow = (int)len; bool broke = false, first_group = true;          // processed range [jlow, len-1]
-            for (int jhi = (int)len - 1; !broke && jhi >= L - 1; jhi -= 32) {
-                const int j = jhi - w.lane; const bool act = j >= L - 1;
-                KjChain<IdxT> ch; ch.lo = 0; ch.hi = 0; ch.i = 0; ch.done = true;
-                if (act) kj_chain_start<IdxT>(ix, frag, j, rp.seed_length, ch);
-                w.sync();
-                bool valid = false; int cut = 31;
-                for (;;) {
-                    const uint32_t brk = w.ballot(act && ch.done && ch.i <= 1);    // `if (i<=1) break` (bwt.c:292)
-                    cut = brk ? kj_ffs(brk) - 1 : 31; broke = brk != 0;
-                    valid = act && w.lane <= cut;
-                    const bool elig = valid && !ch.done;                            // every chain above the break is needed
-                    const uint32_t em = w.ballot(elig);
-                    if (!em) break;
-                    const int G = first_group ? KJ_GROUP_FIRST : 16; first_group = false;   // a full-length hit ends the fragment after the first group
-                    const bool sel = elig && kj_popc(em & lanemask_lt(w.lane)) < G;
-                    kj_finish_selected<IdxT>(w, ix, frag, sel, ch);
+            const bool mono = ix.mono != 0; const int kk = ix.kmer_k;
+            int jlow = (int)len; uint32_t qi_above = 0xffffffffu;                  // processed range [jlow, len-1]; smallest start of a qualifying finished chain of the blocks above
+            int jhi = (int)len - 1, jstart = jhi, round = 0; bool start_la = false, have_nxt = false;
+            KjChain<IdxT> cur, nxt;
+            cur.lo = 0; cur.hi = 0; cur.i = 0; cur.st = KJ_ST_EXACT; nxt = cur;
+            KJ_ROLLED
+            for (;;) {                                                             // same skeleton as kj_mem_item: one phase-A site, one completion site
+                if (jstart >= 0) {
+                    KjChain<IdxT> t; t.lo = 0; t.hi = 0; t.i = 0; t.st = KJ_ST_EXACT;
+                    if (jstart - w.lane >= 0) kj_chain_start<IdxT>(ix, frag, jstart - w.lane, rp.seed_length, t);
+                    w.sync();
+                    if (start_la) { nxt = t; have_nxt = true; } else { cur = t; round = 0; }
+                    jstart = -1;
                 }
-                if (valid) { res[j].lo = (uint64_t)ch.lo; res[j].len = (uint32_t)(ch.hi - ch.lo); res[j].qi = (uint16_t)ch.i; res[j].ql = (uint16_t)(j - ch.i + 1); }
+                const int j = jhi - w.lane; const bool probe = j >= 0; const bool act = j >= L - 1;
+                const uint32_t brk = w.ballot(act && cur.st == KJ_ST_EXACT && cur.i <= 1);        // `if (i<=1) break` (bwt.c:292)
+                const int cut = brk ? kj_ffs(brk) - 1 : 31;
+                const bool open = act && cur.st == KJ_ST_OPEN && w.lane <= cut;
+                const uint32_t om = w.ballot(open);
+                uint32_t nm = 0; bool need = false;
+                if (om) {
+                    int lb = 0;
+                    if (mono) {
+                        int lb_ext = 0;
+                        if (round > 0 && !have_nxt && jhi - 32 >= 0) {
+                            const uint32_t inf = w.ballot(probe && cur.st != KJ_ST_OPEN);
+                            if ((31 - kj_clz(om)) > (inf ? 31 - kj_clz(inf) : -1)) { jstart = jhi - 32; start_la = true; continue; }
+                        }
+                        if (have_nxt) lb_ext = kj_block_lb_ext<IdxT>(w, nxt, jhi - 32 - w.lane >= 0, jhi - 32 - w.lane, kk);
+                        lb = kj_chain_lb<IdxT>(w, cur, probe, j, kk, lb_ext);
+                    }
+                    // an open chain is not recorded if its match is shorter than L or cannot start left of a qualifying finished chain above it
+                    const bool qual = act && cur.st == KJ_ST_EXACT && w.lane <= cut && j - cur.i + 1 >= L;
+                    const uint32_t pmin = kj_prefix_min_excl(w, qual ? (uint32_t)cur.i : 0xffffffffu, qi_above);
+                    need = open && !(lb >= 2 && (j - lb + 1 < L || (uint32_t)lb >= pmin));
+                    nm = w.ballot(need);
+                }
+                if (nm) {
+                    const bool top = need && !(w.lane > 0 && ((nm >> (w.lane - 1)) & 1u));
+                    const int group = (round == 0 && mono) ? 0 : KJ_GROUP_LATE;
+                    const bool sel = need && (top || kj_popc(nm & lanemask_lt(w.lane)) < group);
+                    kj_finish_selected<IdxT>(w, ix, frag, sel, cur);
+                    round++;
+                    continue;
+                }
+                const bool valid = act && w.lane <= cut;
+                if (valid) {
+                    if (cur.st == KJ_ST_OPEN) { res[j].lo = 0; res[j].len = 0; res[j].qi = 0; res[j].ql = 0; }       // skipped: provably not recorded
+                    else { res[j].lo = (uint64_t)cur.lo; res[j].len = (uint32_t)(cur.hi - cur.lo); res[j].qi = (uint16_t)cur.i; res[j].ql = (uint16_t)(j - cur.i + 1); }
+                }
+                { const bool qual = valid && cur.st == KJ_ST_EXACT && j - cur.i + 1 >= L; const uint32_t mn = warp_min_u32(w, qual ? (uint32_t)cur.i : 0xffffffffu); if (mn < qi_above) qi_above = mn; }
                 const int nact = (jhi - (L - 1) + 1) < 32 ? (jhi - (L - 1) + 1) : 32;
-                jlow = jhi - (broke ? cut + 1 : nact) + 1;
+                jlow = jhi - (brk ? cut + 1 : nact) + 1;
+                jhi -= 32;
+                if (brk || jhi < L - 1) break;
+                round = 0;
+                if (have_nxt) { cur = nxt; have_nxt = false; } else { jstart = jhi; start_la = false; }
             }
             w.sync();
             // recorded matches: l >= L and start strictly left of the previously recorded one (bwt.c:276-281).  With a true FM index
@@ -161,11 +216,10 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
             // pass 1: flags + found order (j descending); pass 2: class position = (#longer) + (#same length found earlier)
             const int nproc = (int)len - jlow;                             // processed j = len-1-t, t in [0,nproc)
             uint32_t cur_qi = 0xffffffffu;                                 // start of the last recorded match (uniform)
+            KJ_ROLLED
             for (int b = 0; b < nproc; b += 32) {
                 int t = b + w.lane; int j = (int)len - 1 - t; bool rec = false;
-                if (sizeof(IdxT) == 4) {
-                    if (t < nproc) { KjMatch r = res[j]; rec = r.ql >= (uint32_t)L && !(t > 0 && res[j + 1].qi == r.qi); }
-                } else {
+                {
                     uint32_t mine = 0xffffffffu;                           // my start if my chain qualifies
                     if (t < nproc) { KjMatch r = res[j]; if (r.ql >= (uint32_t)L) mine = r.qi; }
                     uint32_t pm = mine;                                    // inclusive prefix minimum over the lanes
@@ -181,15 +235,18 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
             }
             w.sync();
             // stable sort by ql descending into res (insert_SI_sorted, bwt.c:225-252)
+            KJ_ROLLED
             for (uint32_t b = 0; b < nrec; b += 32) {
                 uint32_t t = b + (uint32_t)w.lane;
                 if (t < nrec) {
                     KjMatch r = cls[t]; uint32_t pos = 0;
+                    KJ_ROLLED
                     for (uint32_t u = 0; u < nrec; u++) { uint32_t q2 = cls[u].ql; pos += (q2 > r.ql || (q2 == r.ql && u < t)) ? 1u : 0u; }
                     res[pos] = r;
                 }
             }
             w.sync();
+            KJ_ROLLED
             for (uint32_t t = (uint32_t)w.lane; t < nrec; t += 32) cls[t] = res[t];
             w.sync();
         }
@@ -208,11 +265,13 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
         if (rp.e > 0 && num_mm < rp.e) {
             // walk: class head, then its samelen chain fn..f2 if the class has >1 member (and stop), else the next class head
             uint32_t c0 = 0;
+            KJ_ROLLED
             while (c0 < nrec) {
                 uint32_t c1;
                 if (small) { const uint32_t rest = heads & ~((2u << c0) - 1u); c1 = rest ? (uint32_t)kj_ffs(rest) - 1u : nrec; }
                 else { c1 = c0 + 1; const uint32_t qlc = cls[c0].ql; while (c1 < nrec && cls[c1].ql == qlc) c1++; }
                 const uint32_t nmem = c1 - c0;
+                KJ_ROLLED
                 for (uint32_t wi = 0; wi < nmem; wi++) {
                     const KjMatch sm = cls[wi == 0 ? c0 : c1 - wi];
                     const uint32_t mre1 = (uint32_t)sm.qi + sm.ql;         // match_right_end + 1
@@ -240,6 +299,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
                                 KjVariant* V = vq.v + (vq.n + rk);                 // dereferenced by `ok` lanes only
                                 // the parent's substitutions that survive the truncation, then the new one
                                 uint32_t ns = 0;
+                                KJ_ROLLED
                                 for (uint32_t u = 0; u < nsub; u++) {
                                     const uint32_t sv = psub[u];
                                     if ((sv >> 5) < new_len) { if (ok) V->subs[ns] = sv; ns++; }
@@ -252,6 +312,9 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
                                     vq.key(vq.n + rk) = kj_qkey((uint32_t)after, KJ_ORDER_LATE + q.late + rk);
                                 }
                                 vq.n += cnt; vq.live += cnt; q.late += cnt;
+#if defined(KJ_EMU)
+                                if (w.lane == 0) kj_emu_stats.var_pushed += cnt;
+#endif
                             }
                         }
                         w.sync();
@@ -296,11 +359,13 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
         } else {
             uint32_t K = 0, ncand = 0;                                     // classes with ql >= m, members in them
             { uint32_t c0 = 0; while (c0 < nrec && cls[c0].ql >= rp.m) { uint32_t c1 = c0 + 1; while (c1 < nrec && cls[c1].ql == cls[c0].ql) c1++; K++; ncand = c1; c0 = c1; } }
+            KJ_ROLLED
             for (uint32_t b = 0; b < ncand; b += 32) {
                 uint32_t t = b + (uint32_t)w.lane;
                 if (t < ncand) {
                     KjMatch r = cls[t]; bool head = (t == 0) || cls[t - 1].ql != r.ql;
                     uint32_t cidx = 0, heads_before = 0;                   // class index of t, number of heads at indices < t
+                    KJ_ROLLED
                     for (uint32_t u = 1; u <= t; u++) if (cls[u].ql != cls[u - 1].ql) cidx++;
                     heads_before = cidx + (head ? 0u : 1u);
                     uint32_t pos = head ? (ncand - K) + (K - 1u - cidx) : t - heads_before;
@@ -309,6 +374,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
                 }
             }
             w.sync();
+            KJ_ROLLED
             for (uint32_t t = 0; t < ncand; t++) {
                 const KjMatch r = res[t]; const uint32_t sc = r.qi;
                 if (sc < rp.min_score) continue;
@@ -323,6 +389,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
     if (rp.use_evalue) {                                                   // E-value gate (500-513) as an integer threshold
         // minimal passing score = number of score break points below the query length (kj_build_evalue_breaks)
         uint32_t thr = 0;
+        KJ_ROLLED
         for (uint32_t b = 0; b < rp.n_ev_breaks; b += 32) {
             const uint32_t k = b + (uint32_t)w.lane;
             const uint32_t below = w.ballot(k < rp.n_ev_breaks && rp.ev_breaks[k] < query_len);

@@ -50,8 +50,10 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
     KjCtaShared* sh = (KjCtaShared*)smem_raw;
     {   // stage the index descriptor (C[] etc.) and the small tables once per CTA
         const uint32_t* src = (const uint32_t*)g_ix; uint32_t* dst = (uint32_t*)&sh->ix;
+        KJ_ROLLED
         for (uint32_t i = threadIdx.x; i < sizeof(KjDevIndex) / 4; i += blockDim.x) dst[i] = src[i];
         const uint32_t* ts = (const uint32_t*)g_ix->tables; uint32_t* td = (uint32_t*)&sh->tb;
+        KJ_ROLLED
         for (uint32_t i = threadIdx.x; i < sizeof(KjTables) / 4; i += blockDim.x) td[i] = ts[i];
     }
     __syncthreads();
@@ -77,6 +79,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
         const unsigned long long ri = r0 + (unsigned long long)cx.w.lane;
         uint64_t o1 = 0, o2 = 0;
         if (cx.w.lane <= KJ_CLAIM && ri <= n_reads) { o1 = off1[ri] - base1; if (paired) o2 = off2[ri] - base2; }
+        KJ_ROLLED
         for (int k = 0; k < KJ_CLAIM; k++) {
             const unsigned long long r = r0 + (unsigned long long)k;
             if (r >= n_reads) break;
@@ -94,6 +97,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
                 const uint32_t nids = id ? cx.nids : 0u; const uint32_t* ids = (const uint32_t*)(cx.smem + cx.L.ids_off);
                 if ((uint32_t)cx.w.lane < nids) {
                     const uint64_t mine = sh->ix.tax_id[ids[cx.w.lane]]; uint32_t rank = 0;
+                    KJ_ROLLED
                     for (uint32_t u = 0; u < nids; u++) rank += sh->ix.tax_id[ids[u]] < mine ? 1u : 0u;
                     ids_out[r * KJ_MAX_IDS + rank] = mine;
                 }
@@ -236,7 +240,7 @@ template <class Fill> static int create_ctx(kj_ctx** out, int device, const kj_p
     D.sa_tax = (const uint32_t*)c->d_sa_tax; D.seq_tax = (const uint32_t*)c->d_seq_tax; D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
     D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
     D.tax_parent = (const uint32_t*)c->d_tax_parent; D.tax_depth = (const uint32_t*)c->d_tax_depth; D.tax_id = (const uint64_t*)c->d_tax_id; D.n_tax = (uint32_t)H.tax_id.size();
-    D.lnfact = (const double*)c->d_lnfact; D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? c->d_kmer : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = c->d_tables; D.quirk_lo = H.quirk_lo;
+    D.lnfact = (const double*)c->d_lnfact; D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? c->d_kmer : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = c->d_tables; D.quirk_lo = H.quirk_lo; D.mono = H.quirk_lo == ~0ull ? 1 : 0;
     CK(cudaMalloc((void**)&c->d_quirk, sizeof H.quirk_d)); CK(cudaMemcpy(c->d_quirk, H.quirk_d, sizeof H.quirk_d, cudaMemcpyHostToDevice)); D.quirk_d = c->d_quirk;
     CK(cudaMalloc((void**)&c->d_ix, sizeof(KjDevIndex))); CK(cudaMemcpy(c->d_ix, &D, sizeof(KjDevIndex), cudaMemcpyHostToDevice));
     c->index_bytes = tot;

@@ -67,6 +67,7 @@ struct KjDevIndex {
     const double* lnfact; int n_lnfact;
     const void* kmer; int kmer_k;               // direct-address table of k-mer intervals (KjKmer32 if !wide else KjKmer; 0 = off)
     int wide;                                   // 1 if bwtlen >= 2^32 (64-bit interval arithmetic in the kernels)
+    int mono;                                   // 1: true FM index (match starts monotone in the end position); 0: the reference's checkpoint quirk applies (no chain bounds)
     uint64_t quirk_lo; const uint64_t* quirk_d;         // rows k >= quirk_lo: FMindex(c,k) -= quirk_d[c] (reference checkpoint quirk, ~0 = none; [KJ_MAX_ALEN] in global memory)
     const KjTables* tables;
 };

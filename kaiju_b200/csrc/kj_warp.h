@@ -12,6 +12,8 @@
 #include <string.h>
 #define KJ_DEV inline
 #define KJ_HD inline
+#define KJ_ROLLED
+#define KJ_NOINLINE static
 namespace kjemu {
 struct Sched;                         // defined in tests/emu/kj_emu.cpp
 uint64_t rendezvous(Sched* s, int lane, uint64_t v, int src_kind, int src_arg);
@@ -48,6 +50,10 @@ struct Warp {
 #define KJ_DEV __device__ __forceinline__
 #define KJ_HD __host__ __device__ __forceinline__
 #define KJ_FULL 0xffffffffu
+// Code size is a first-order cost here (the Greedy kernel stalled 58 % of its time on instruction fetch, profiles/README.md):
+// loops are kept rolled unless unrolling was measured to pay, and cold paths are real functions.
+#define KJ_ROLLED _Pragma("unroll 1")
+#define KJ_NOINLINE static __device__ __noinline__
 static KJ_DEV int kj_popc(uint32_t x) { return __popc(x); }
 static KJ_DEV int kj_popcll(uint64_t x) { return __popcll(x); }
 static KJ_DEV int kj_ffs(uint32_t x) { return __ffs((int)x); }

@@ -109,7 +109,10 @@ uint32_t rendezvous_ballot(Sched* s, int lane, bool p) {
 }
 }  // namespace kjemu
 
+struct KjEmuStats;
 #include "../../kaiju_b200/csrc/kj_core.h"
+thread_local KjEmuStats kj_emu_stats;
+static KjEmuStats g_emu_total; static std::atomic<int> g_emu_lock(0);
 #include "../../kaiju_b200/csrc/kj_core_greedy.h"
 #include "../../kaiju_b200/csrc/kj_host.h"
 
@@ -147,7 +150,7 @@ void* kjemu_create(const char* fmi_path, const char* nodes_path, const kj_params
     D.sa_tax = H.sa_tax.data(); D.seq_tax = H.seq_tax.data(); D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
     D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
     D.tax_parent = H.tax_parent.data(); D.tax_depth = H.tax_depth.data(); D.tax_id = H.tax_id.data(); D.n_tax = (uint32_t)H.tax_id.size();
-    D.lnfact = H.lnfact.data(); D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? (H.wide ? (const void*)H.kmer.data() : (const void*)H.kmer32.data()) : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = &H.tables; D.quirk_lo = H.quirk_lo; D.quirk_d = H.quirk_d;
+    D.lnfact = H.lnfact.data(); D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? (H.wide ? (const void*)H.kmer.data() : (const void*)H.kmer32.data()) : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = &H.tables; D.quirk_lo = H.quirk_lo; D.quirk_d = H.quirk_d; D.mono = (H.quirk_lo == ~0ull && !getenv("KJ_EMU_NOMONO")) ? 1 : 0;
     return c;
 }
 void kjemu_destroy(void* h) { delete (EmuCtx*)h; }
@@ -173,6 +176,13 @@ int kjemu_evalue_breaks(double min_evalue, double db_length, double* out, int ca
     std::vector<double> b; if (kj_build_evalue_breaks(p, db_length, b) != KJ_OK) return -1;
     for (size_t i = 0; i < b.size() && (int)i < cap; i++) out[i] = b[i];
     return (int)b.size();
+}
+// developer counters of the chain-resolution loops (rounds, warp-steps, lane-steps, chains completed, blocks, look-aheads, pops ...)
+int kjemu_stats(unsigned long long* out, int cap, int reset) {
+    const unsigned long long* a = (const unsigned long long*)&g_emu_total; int n = (int)(sizeof(KjEmuStats) / 8);
+    for (int k = 0; k < n && k < cap; k++) out[k] = a[k];
+    if (reset) memset(&g_emu_total, 0, sizeof g_emu_total);
+    return n;
 }
 int kjemu_native_read(const char* path) { KjHostIndex H; return kj_host_index_read(path, H); }
 
@@ -209,6 +219,12 @@ int kjemu_classify(void* h, const char* seq1, const uint64_t* off1, const char* 
             if (best_out) best_out[i] = taxon_out[i] ? A.best[0] : 0;
         }
         errs |= err; delete s;
+        {   // fold this thread's counters into the process-wide totals
+            while (g_emu_lock.exchange(1)) {}
+            unsigned long long* a = (unsigned long long*)&g_emu_total; const unsigned long long* b = (const unsigned long long*)&kj_emu_stats;
+            for (size_t k = 0; k < sizeof(KjEmuStats) / 8; k++) a[k] += b[k];
+            memset(&kj_emu_stats, 0, sizeof kj_emu_stats); g_emu_lock.store(0);
+        }
     });
     for (auto& x : th) x.join();
     return errs.load() ? KJ_ERR_OVERFLOW - 100 * (int)errs.load() : KJ_OK;
