@@ -94,9 +94,6 @@ static KJ_DEV void kj_flag_error(KjWarpCtx& cx, uint32_t bit) {
 // A/B-tested on the B200 (profiles/README.md): one warp's time is dominated by chains of dependent short-latency instructions,
 // so shorter dependence chains beat fewer instructions.  Tried and rejected: two lanes per chain in phase B (-7 %),
 // compaction of low-diversity SEG windows (-10 %), screening several queued fragments at once with two chains per lane (-29 %).
-#ifndef KJ_OPT_RANKBASE
-#define KJ_OPT_RANKBASE 1         // 1: per-letter record base from shared memory, 0: multiply (A/B: +3 %)
-#endif
 // ---------------------------------------------------------------------------------------------
 // FM index primitives.  IdxT = uint32_t for indexes with bwtlen < 2^32 (all interval arithmetic in 32 bit), uint64_t otherwise.
 // ---------------------------------------------------------------------------------------------
@@ -107,45 +104,38 @@ static KJ_DEV uint64_t kj_ld64(const void* p) {
     uint64_t v; asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p)); return v;
 #endif
 }
-// position k -> (block, word in block, bit in word); k < 2^38 so k >> 6 fits 32 bits
-template <class IdxT>
-static KJ_DEV void kj_split(IdxT k, uint32_t& blk, uint32_t& wi, uint32_t& bit) {
-    const uint32_t q = (uint32_t)(k >> 6); blk = q / 3u; wi = q - 3u * blk; bit = (uint32_t)k & 63u;
-}
-// FMindex(f, c, k) = C[c] + rank_c(BWT[0..k))        (compactfmi.c:267-307) for one end of an interval:
-// header (count + in-block prefix bytes) and the ONE bitmap word holding row k -- two 8-byte loads from the same
-// 32-byte sector, one 64-bit popcount, no data-dependent branches.  `base` = records of letter c.
-template <class IdxT>
-static KJ_DEV IdxT kj_rank_at(const KjRankBlock* base, IdxT k) {
-#ifdef KJ_RANK64
-    const uint8_t* rec64 = (const uint8_t*)(base + (k >> 6));
-    const uint64_t h64 = kj_ld64(rec64), w64 = kj_ld64(rec64 + 8u);
-    const uint32_t pc64 = (uint32_t)kj_popcll(w64 & ((1ull << ((uint32_t)k & 63u)) - 1ull));
-    if (sizeof(IdxT) == 4) return (IdxT)((uint32_t)h64 + pc64);
-    return (IdxT)(h64 + (uint64_t)pc64);
+static KJ_DEV void kj_ld128(const void* p, uint64_t& a, uint64_t& b) {
+#if defined(KJ_EMU)
+    a = ((const uint64_t*)p)[0]; b = ((const uint64_t*)p)[1];
+#else
+    asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 #endif
-    uint32_t blk, wi, bit; kj_split<IdxT>(k, blk, wi, bit);
-    const uint8_t* rec = (const uint8_t*)(base + blk);
+}
+// FMindex(f, c, k) = C[c] + rank_c(BWT[0..k))        (compactfmi.c:267-307) for one end of an interval.  `base` = records of letter c.
+// 32-bit kernels (narrow layout): ONE 16-byte load (header + the bitmap word of k's 64-row block) and one popcount.
+// 64-bit kernels (wide layout): header + the one bitmap word holding row k -- two 8-byte loads from the same 32-byte sector,
+// one popcount, no data-dependent branches; k < 2^38 so k >> 6 fits 32 bits.
+template <class IdxT>
+static KJ_DEV IdxT kj_rank_at(const uint64_t* base, IdxT k) {
+    if (sizeof(IdxT) == 4) {
+        uint64_t h, wd; kj_ld128(base + 2u * (size_t)((uint32_t)k >> 6), h, wd);
+        return (IdxT)((uint32_t)h + (uint32_t)kj_popcll(wd & ((1ull << ((uint32_t)k & 63u)) - 1ull)));
+    }
+    const uint32_t q = (uint32_t)((uint64_t)k >> 6), blk = q / 3u, wi = q - 3u * blk, bit = (uint32_t)k & 63u;
+    const uint64_t* rec = base + 4u * (size_t)blk;
     const uint64_t hdr = kj_ld64(rec);
-    const uint64_t ww = kj_ld64(rec + 8u + 8u * wi);
+    const uint64_t ww = kj_ld64(rec + 1u + wi);
     const uint32_t pc = (uint32_t)kj_popcll(ww & ((1ull << bit) - 1ull));
-    if (sizeof(IdxT) == 4) return (IdxT)((uint32_t)hdr + (((uint32_t)(hdr >> 32) >> (8u * wi)) & 0xffu) + pc);   // byte 4 of hdr is 0 below 2^32 rows
     const uint32_t add = wi == 0 ? 0u : ((uint32_t)(hdr >> (32u + 8u * wi)) & 0xffu);
     return (IdxT)((hdr & KJ_CNT_MASK) + (uint64_t)(add + pc));
 }
-static KJ_DEV const KjRankBlock* kj_letter_base(const KjDevIndex& ix, uint32_t c) {
-#if KJ_OPT_RANKBASE
-    return ix.rank_base[c];
-#else
-    return ix.rank + (uint64_t)c * ix.nb;
-#endif
-}
+static KJ_DEV const uint64_t* kj_letter_base(const KjDevIndex& ix, uint32_t c) { return ix.rank_base[c]; }
 template <class IdxT>
 static KJ_DEV IdxT kj_rank(const KjDevIndex& ix, uint32_t c, IdxT k) { return kj_rank_at<IdxT>(kj_letter_base(ix, c), k); }
 // UpdateSI (bwt.c:160-173)
 template <class IdxT>
 static KJ_DEV bool kj_update_si(const KjDevIndex& ix, uint32_t c, IdxT& lo, IdxT& hi) {
-    const KjRankBlock* base = kj_letter_base(ix, c);
+    const uint64_t* base = kj_letter_base(ix, c);
     IdxT nlo = kj_rank_at<IdxT>(base, lo), nhi = kj_rank_at<IdxT>(base, hi);
     // the reference's checkpoint quirk (indexes with bwtlen = m * 2^16 only, kj_host.cpp): the last 129 positions rank lower by a per-letter
     // constant.  Such indexes are routed to the 64-bit kernels, so the 32-bit ones do not carry the test.
@@ -159,10 +149,11 @@ static KJ_DEV uint32_t kj_letter(const KjDevIndex& ix, uint64_t k) {
     return (uint32_t)(ix.letters[wd] >> s) & 31u;
 }
 // get_suffix (bwt.c:105-121) reduced to the taxon of the sequence the suffix lies in
+template <class IdxT>
 static KJ_DEV uint32_t kj_sa_taxon(const KjDevIndex& ix, uint64_t k) {
     uint32_t c = 1;
     KJ_ROLLED
-    while (c != 0 && (k & ix.sa_check)) { c = kj_letter(ix, k); const bool q = k >= ix.quirk_lo; k = kj_rank<uint64_t>(ix, c, k); if (q) k -= ix.quirk_d[c]; }
+    while (c != 0 && (k & ix.sa_check)) { c = kj_letter(ix, k); const bool q = k >= ix.quirk_lo; k = (uint64_t)kj_rank<IdxT>(ix, c, (IdxT)k); if (q) k -= ix.quirk_d[c]; }
     if (c != 0) return ix.sa_tax[(uint64_t)((int64_t)(k >> ix.sa_exp) - ix.sa_bias)];
     return ix.seq_tax[k];
 }
@@ -712,6 +703,7 @@ static KJ_DEV KjKept* kj_kept_ptr(KjWarpCtx& cx, uint32_t idx) {
 
 // taxon ids of the kept intervals in order, k ascending, stop once the set exceeds 20 entries
 // (ids_from_SI, ConsumerThread.cpp:799-835); then LCA (util.cpp:194-263).  Returns compact taxon or KJ_TAX_BAD for "none".
+template <class IdxT>
 static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
     const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix;
     uint32_t* ids = (uint32_t*)(cx.smem + cx.L.ids_off);
@@ -722,7 +714,7 @@ static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
         KJ_ROLLED
         for (uint32_t base = 0; base < kk.len && nids <= 20; base += 32) {
             uint32_t t = base + (uint32_t)w.lane; bool act = t < kk.len;
-            uint32_t tax = act ? kj_sa_taxon(ix, kk.lo + t) : KJ_TAX_BAD;
+            uint32_t tax = act ? kj_sa_taxon<IdxT>(ix, kk.lo + t) : KJ_TAX_BAD;
             uint32_t nact = kk.len - base < 32u ? kk.len - base : 32u;
             KJ_ROLLED
             for (uint32_t s = 0; s < nact && nids <= 20; s++) {
@@ -906,7 +898,7 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
     best_out = 0;
     if (nkept == 0) return KJ_TAX_BAD;
     cx.w.sync();
-    uint32_t t = kj_ids_and_lca(cx, nkept);
+    uint32_t t = kj_ids_and_lca<IdxT>(cx, nkept);
     if (t != KJ_TAX_BAD) best_out = longest;
     return t;
 }

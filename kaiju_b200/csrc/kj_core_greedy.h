@@ -399,7 +399,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
         if (best < thr) return KJ_TAX_BAD;
     }
     w.sync();
-    uint32_t t = kj_ids_and_lca(cx, nbest);
+    uint32_t t = kj_ids_and_lca<IdxT>(cx, nbest);
     if (t != KJ_TAX_BAD) best_out = best;
     return t;
 }

@@ -234,9 +234,9 @@ template <class Fill> static int create_ctx(kj_ctx** out, int device, const kj_p
         (rc = upload(H.tax_id, &c->d_tax_id, tot)) || (rc = upload(H.lnfact, &c->d_lnfact, tot)) || (rc = (H.wide ? upload(H.kmer, &c->d_kmer, tot) : upload(H.kmer32, &c->d_kmer, tot)))) return rc;
     CK(cudaMalloc((void**)&c->d_tables, sizeof(KjTables))); CK(cudaMemcpy(c->d_tables, &H.tables, sizeof(KjTables), cudaMemcpyHostToDevice));
     KjDevIndex& D = c->dix; memset(&D, 0, sizeof D);
-    D.rank = (const KjRankBlock*)c->d_rank; D.nb = H.nb; D.letters = (const uint64_t*)c->d_letters; D.bwtlen = H.bwtlen; D.alen = H.alen;
+    D.rank = (const uint64_t*)c->d_rank; D.nb = H.nb; D.letters = (const uint64_t*)c->d_letters; D.bwtlen = H.bwtlen; D.alen = H.alen;
     for (int a = 0; a <= H.alen; a++) D.C[a] = H.C[a];
-    for (int a = 0; a < H.alen; a++) D.rank_base[a] = D.rank + (uint64_t)a * H.nb;
+    for (int a = 0; a < H.alen; a++) D.rank_base[a] = D.rank + (uint64_t)a * H.nb * kj_rank_words(H.wide);
     D.sa_tax = (const uint32_t*)c->d_sa_tax; D.seq_tax = (const uint32_t*)c->d_seq_tax; D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
     D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
     D.tax_parent = (const uint32_t*)c->d_tax_parent; D.tax_depth = (const uint32_t*)c->d_tax_depth; D.tax_id = (const uint64_t*)c->d_tax_id; D.n_tax = (uint32_t)H.tax_id.size();
@@ -245,7 +245,7 @@ template <class Fill> static int create_ctx(kj_ctx** out, int device, const kj_p
     CK(cudaMalloc((void**)&c->d_ix, sizeof(KjDevIndex))); CK(cudaMemcpy(c->d_ix, &D, sizeof(KjDevIndex), cudaMemcpyHostToDevice));
     c->index_bytes = tot;
     // host copies of the big arrays are no longer needed
-    std::vector<KjRankBlock>().swap(H.rank); std::vector<uint64_t>().swap(H.letters); std::vector<uint32_t>().swap(H.sa_tax); std::vector<KjKmer>().swap(H.kmer); std::vector<KjKmer32>().swap(H.kmer32);
+    std::vector<uint64_t>().swap(H.rank); std::vector<uint64_t>().swap(H.letters); std::vector<uint32_t>().swap(H.sa_tax); std::vector<KjKmer>().swap(H.kmer); std::vector<KjKmer32>().swap(H.kmer32);
     CK(cudaMalloc((void**)&c->d_counter, 2 * sizeof(unsigned long long))); CK(cudaMalloc((void**)&c->d_err, sizeof(uint32_t))); CK(cudaMalloc((void**)&c->d_maxlen, 2 * sizeof(unsigned int)));
     CK(cudaMemset(c->d_err, 0, sizeof(uint32_t)));
     for (int s = 0; s < 2; s++) CK(cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking));

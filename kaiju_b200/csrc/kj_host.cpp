@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <climits>
+#include <atomic>
 #include <thread>
 #include <unordered_map>
 
@@ -184,8 +185,14 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
         if (s < 0 || e > 256 || s > e) { kj_err() = "corrupt startLcode"; return KJ_ERR_IO; }
         for (int k = s; k < e; k++) lcode[k] = (uint8_t)a;
     }
+    if (n >= (1ull << 38)) { kj_err() = "index too large (>= 2^38 rows)"; return KJ_ERR_UNSUPPORTED; }
+    // KJ_FORCE_WIDE: exercise the 64-bit kernels on small test indexes.  Indexes with the reference's checkpoint quirk (below) also
+    // take the 64-bit kernels: only those carry the rank correction, so that ordinary indexes pay nothing for the 1-in-65536 case.
+    const bool quirk = (n & 65535ull) == 0 && n >= 131072ull;
+    H.wide = (n >= 0xffffff00ull || getenv("KJ_FORCE_WIDE") || quirk) ? 1 : 0;
     // rank records + packed letters, chunked over threads
-    const uint64_t nb = n / KJ_RANK_BLOCK + 1; H.nb = nb;
+    const uint32_t RB = kj_rank_rows(H.wide), RW = kj_rank_words(H.wide);
+    const uint64_t nb = n / RB + 1; H.nb = nb;
     const uint64_t CH = 192ull * 2048;                                  // positions per chunk (multiple of 192, 64 and 12)
     const uint64_t nch = (n + CH - 1) / CH;
     std::vector<uint64_t> ccount((size_t)(nch + 1) * alen, 0);
@@ -199,41 +206,30 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
     const uint64_t* total = &ccount[(size_t)nch * alen];
     H.C[0] = 0; for (int a = 0; a < alen; a++) H.C[a + 1] = H.C[a] + total[a];
     if (H.C[alen] != n) { kj_err() = "letter counts do not add up"; return KJ_ERR_IO; }
-    try { H.rank.assign((size_t)alen * nb, KjRankBlock{}); H.letters.assign((size_t)(n / KJ_LETTERS_PER_WORD + 2), 0); }
+    try { H.rank.assign((size_t)alen * nb * RW, 0ull); H.letters.assign((size_t)(n / KJ_LETTERS_PER_WORD + 2), 0); }
     catch (...) { kj_err() = "out of host memory building the rank table"; return KJ_ERR_NOMEM; }
     par([&](uint64_t c) {
         uint64_t run[KJ_MAX_ALEN]; for (int a = 0; a < alen; a++) run[a] = H.C[a] + ccount[(size_t)c * alen + a];
         uint64_t e = std::min(n, (c + 1) * CH);
-        for (uint64_t b0 = c * CH; b0 < e; b0 += KJ_RANK_BLOCK) {
-            uint64_t b = b0 / KJ_RANK_BLOCK, be = std::min(n, b0 + KJ_RANK_BLOCK);
-            for (int a = 0; a < alen; a++) H.rank[(size_t)a * nb + b].hdr = run[a];
+        for (uint64_t b0 = c * CH; b0 < e; b0 += RB) {
+            uint64_t b = b0 / RB, be = std::min(n, b0 + RB);
+            for (int a = 0; a < alen; a++) H.rank[((size_t)a * nb + b) * RW] = run[a];
             for (uint64_t k = b0; k < be; k++) {
-                uint32_t a = lcode[v.bwt[k]], r = (uint32_t)(k - b0); KjRankBlock& B = H.rank[(size_t)a * nb + b];
-#ifdef KJ_RANK64
-                B.w0 |= 1ull << r;
-#else
-                (r < 64 ? B.w0 : r < 128 ? B.w1 : B.w2) |= 1ull << (r & 63);
-#endif
+                uint32_t a = lcode[v.bwt[k]], r = (uint32_t)(k - b0);
+                H.rank[((size_t)a * nb + b) * RW + 1u + (r >> 6)] |= 1ull << (r & 63);
                 run[a]++;
             }
         }
         for (uint64_t k = c * CH; k < e; k++) H.letters[k / KJ_LETTERS_PER_WORD] |= (uint64_t)lcode[v.bwt[k]] << (5 * (k % KJ_LETTERS_PER_WORD));
     });
-    // the record after the last letter (k == bwtlen lands there when bwtlen % 192 == 0; otherwise the last partial block already exists)
-    if (n % KJ_RANK_BLOCK == 0) for (int a = 0; a < alen; a++) H.rank[(size_t)a * nb + (nb - 1)].hdr = H.C[a] + total[a];
-    if (n >= (1ull << 38)) { kj_err() = "index too large (>= 2^38 rows)"; return KJ_ERR_UNSUPPORTED; }
-    // KJ_FORCE_WIDE: exercise the 64-bit kernels on small test indexes.  Indexes with the reference's checkpoint quirk (below) also
-    // take the 64-bit kernels: only those carry the rank correction, so that ordinary indexes pay nothing for the 1-in-65536 case.
-    const bool quirk = (n & 65535ull) == 0 && n >= 131072ull;
-    H.wide = (n >= 0xffffff00ull || getenv("KJ_FORCE_WIDE") || quirk) ? 1 : 0;
-#ifndef KJ_RANK64
-    {   // fold the in-block prefix popcounts into the header
+    // the record after the last letter (k == bwtlen lands there when bwtlen % RB == 0; otherwise the last partial block already exists)
+    if (n % RB == 0) for (int a = 0; a < alen; a++) H.rank[((size_t)a * nb + (nb - 1)) * RW] = H.C[a] + total[a];
+    if (H.wide) {   // fold the in-block prefix popcounts into the header
         std::vector<std::thread> th; const size_t tot = (size_t)alen * nb;
-        for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] { for (size_t i = tI; i < tot; i += nthr) { KjRankBlock& B = H.rank[i];
-            uint64_t p1 = (uint64_t)__builtin_popcountll(B.w0), p2 = p1 + (uint64_t)__builtin_popcountll(B.w1); B.hdr = (B.hdr & KJ_CNT_MASK) | (p1 << KJ_P1_SHIFT) | (p2 << KJ_P2_SHIFT); } });
+        for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] { for (size_t i = tI; i < tot; i += nthr) { uint64_t* B = &H.rank[i * 4];
+            uint64_t p1 = (uint64_t)__builtin_popcountll(B[1]), p2 = p1 + (uint64_t)__builtin_popcountll(B[2]); B[0] = (B[0] & KJ_CNT_MASK) | (p1 << KJ_P1_SHIFT) | (p2 << KJ_P2_SHIFT); } });
         for (auto& x : th) x.join();
     }
-#endif
 
     // ---- taxonomy re-indexing
     std::unordered_map<uint64_t, uint64_t> par_of; par_of.reserve((size_t)t.n * 2 + 16);
@@ -282,7 +278,7 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
     H.sa_bias = ((int64_t)(v.nseq - 1) >> v.chpt_exp) + 1;                                   // bwt.c:115-116
     H.sa_tax.resize((size_t)v.ncheck);
     {
-        std::vector<std::thread> th; const uint64_t nc = (uint64_t)v.ncheck; bool bad = false;
+        std::vector<std::thread> th; const uint64_t nc = (uint64_t)v.ncheck; std::atomic<bool> bad(false);
         for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] {
             for (uint64_t e = tI; e < nc; e += nthr) {
                 const uint8_t* p = v.sa + e * (uint64_t)v.nbytes; uint64_t val = 0;
@@ -314,14 +310,11 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
 
 // host-side rank on the device layout (used only to fill the k-mer table)
 static inline uint64_t host_rank(const KjHostIndex& H, uint32_t c, uint64_t k) {
-    uint64_t b = k / KJ_RANK_BLOCK; uint32_t r = (uint32_t)(k - b * KJ_RANK_BLOCK); const KjRankBlock& B = H.rank[(size_t)c * H.nb + b];
-#ifdef KJ_RANK64
-    uint32_t bit = r; uint64_t ww = B.w0, add = 0;
-#else
-    uint32_t wi = r >> 6, bit = r & 63u; uint64_t ww = wi == 0 ? B.w0 : (wi == 1 ? B.w1 : B.w2);
-    uint64_t add = wi == 0 ? 0 : ((B.hdr >> (32 + 8 * wi)) & 0xff);
-#endif
-    const uint64_t v = (B.hdr & KJ_CNT_MASK) + add + (uint64_t)__builtin_popcountll(ww & ((1ull << bit) - 1ull));
+    const uint32_t RB = kj_rank_rows(H.wide), RW = kj_rank_words(H.wide);
+    uint64_t b = k / RB; uint32_t r = (uint32_t)(k - b * RB); const uint64_t* B = &H.rank[((size_t)c * H.nb + b) * RW];
+    uint32_t wi = r >> 6, bit = r & 63u; uint64_t ww = B[1 + wi];
+    uint64_t add = (H.wide && wi) ? ((B[0] >> (32 + 8 * wi)) & 0xff) : 0;
+    const uint64_t v = (H.wide ? (B[0] & KJ_CNT_MASK) : B[0]) + add + (uint64_t)__builtin_popcountll(ww & ((1ull << bit) - 1ull));
     return k >= H.quirk_lo ? v - H.quirk_d[c] : v;                  // the reference's checkpoint quirk (kj_build_host_index)
 }
 // index = a0*20^(k-1) + a1*20^(k-2) + ... + a(k-1), a_t = letter consumed t-th by the backward search (end of the k-mer first), letters 1..20 -> 0..19
@@ -400,7 +393,7 @@ void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 const char kNativeMagic[8] = {'K', 'J', 'B', '2', '0', '0', 'I', 'X'};
-const uint32_t kNativeVersion = 3;
+const uint32_t kNativeVersion = 4;
 struct NativeHeader {
     uint32_t version, sizeof_tables, sizeof_rank, alen;
     uint64_t nb, bwtlen, C[KJ_MAX_ALEN + 1], sa_check; int64_t sa_bias; int32_t sa_exp; uint32_t nseq, n_present; int32_t kmer_k, wide, pad;
@@ -429,7 +422,7 @@ template <class T> bool get(FILE* f, std::vector<T>& v, uint64_t n) { v.resize((
 int kj_host_index_write(const KjHostIndex& H, const char* path) {
     FILE* f = fopen(path, "wb"); if (!f) { kj_err() = std::string("Could not open file ") + path + " for writing"; return KJ_ERR_IO; }
     NativeHeader h; memset(&h, 0, sizeof h);
-    h.version = kNativeVersion; h.sizeof_tables = (uint32_t)sizeof(KjTables); h.sizeof_rank = (uint32_t)sizeof(KjRankBlock); h.alen = (uint32_t)H.alen;
+    h.version = kNativeVersion; h.sizeof_tables = (uint32_t)sizeof(KjTables); h.sizeof_rank = 8u * kj_rank_words(H.wide); h.alen = (uint32_t)H.alen;
     h.nb = H.nb; h.bwtlen = H.bwtlen; memcpy(h.C, H.C, sizeof h.C); h.sa_check = H.sa_check; h.sa_bias = H.sa_bias; h.sa_exp = H.sa_exp; h.nseq = H.nseq; h.n_present = H.n_present;
     h.kmer_k = H.kmer_k; h.wide = H.wide; h.db_length = H.db_length; h.quirk_lo = H.quirk_lo; memcpy(h.quirk_d, H.quirk_d, sizeof h.quirk_d);
     h.n_rank = H.rank.size(); h.n_letters = H.letters.size(); h.n_sa_tax = H.sa_tax.size(); h.n_seq_tax = H.seq_tax.size(); h.n_tax = H.tax_id.size(); h.n_lnfact = H.lnfact.size();
@@ -447,9 +440,9 @@ int kj_host_index_read(const char* path, KjHostIndex& H) {
     fseeko(f, 0, SEEK_END); const uint64_t fsize = (uint64_t)ftello(f); fseeko(f, 0, SEEK_SET);
     char magic[8]; NativeHeader h;
     bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, kNativeMagic, 8) == 0 && fread(&h, sizeof h, 1, f) == 1;
-    if (!ok || h.version != kNativeVersion || h.sizeof_tables != sizeof(KjTables) || h.sizeof_rank != sizeof(KjRankBlock) || h.alen < 2 || h.alen > KJ_MAX_ALEN ||
-        h.n_rank != h.nb * h.alen || h.n_lnfact != 10001 ||
-        h.n_rank > fsize / sizeof(KjRankBlock) || h.n_letters > fsize / 8 || h.n_sa_tax > fsize / 4 || h.n_seq_tax > fsize / 4 || h.n_tax > fsize / 16 ||
+    if (!ok || h.version != kNativeVersion || h.sizeof_tables != sizeof(KjTables) || h.sizeof_rank != 8u * kj_rank_words(h.wide) || (h.wide != 0 && h.wide != 1) || h.alen < 2 || h.alen > KJ_MAX_ALEN ||
+        h.n_rank != h.nb * h.alen * kj_rank_words(h.wide) || h.nb != h.bwtlen / kj_rank_rows(h.wide) + 1 || h.n_lnfact != 10001 ||
+        h.n_rank > fsize / 8 || h.n_letters > fsize / 8 || h.n_sa_tax > fsize / 4 || h.n_seq_tax > fsize / 4 || h.n_tax > fsize / 16 ||
         h.n_kmer > fsize / sizeof(KjKmer) || h.n_kmer32 > fsize / sizeof(KjKmer32)) { fclose(f); kj_err() = std::string(path) + " is not a device-native index of this library version"; return KJ_ERR_IO; }
     H = KjHostIndex();
     H.alen = (int)h.alen; H.nb = h.nb; H.bwtlen = h.bwtlen; memcpy(H.C, h.C, sizeof h.C); H.sa_check = h.sa_check; H.sa_bias = h.sa_bias; H.sa_exp = h.sa_exp; H.nseq = h.nseq; H.n_present = h.n_present;

@@ -18,7 +18,7 @@ struct kj_nodes { std::vector<uint64_t> node, parent; };
 
 // device-layout arrays, built on the host
 struct KjHostIndex {
-    std::vector<KjRankBlock> rank; uint64_t nb = 0;
+    std::vector<uint64_t> rank; uint64_t nb = 0;   // [alen][nb] records of kj_rank_words(wide) words over kj_rank_rows(wide) rows
     std::vector<uint64_t> letters;
     uint64_t bwtlen = 0; int alen = 0; uint64_t C[KJ_MAX_ALEN + 1] = {0};
     std::vector<uint32_t> sa_tax, seq_tax;

@@ -6,7 +6,7 @@
 // ~18-30 bytes.  Rank values are a pure function of the decoded letters (SURVEY.md 8a exactness note a),
 // so the device uses its own layout, built at load time from the decoded letters:
 //
-//   rank[c][b] : one 32-byte record per (letter c, block b of 192 BWT positions)
+//   rank[c][b] : one record per (letter c, block b of 64 or 192 BWT positions; two layouts, below); the 192-row one:
 //                { hdr = C[c] + #{p < 192 b : L[p] == c} (40 bit) + the popcounts of w0 and w0|w1 (2 x 8 bit),
 //                  w0,w1,w2 = one-hot bitmap of L[p]==c }
 //                -> FMindex(c,k) touches exactly ONE 32-byte DRAM sector and needs ONE 64-bit popcount.
@@ -19,11 +19,17 @@
 #pragma once
 #include <stdint.h>
 
-#ifdef KJ_RANK64
-#define KJ_RANK_BLOCK 64           // A/B variant: one 16-byte record (header + one bitmap word) per 64 positions: no /3, +50 % index memory
-#else
-#define KJ_RANK_BLOCK 192          // positions per rank record (3 x 64-bit words)
-#endif
+// Two record layouts, chosen per index at load time:
+//   narrow (bwtlen < 2^32, 32-bit interval kernels): 16-byte records per 64 rows  { hdr = C[c] + #c before the block, w0 = one-hot bitmap }
+//          -> one 16-byte load + one popcount per rank query, no division; 5.25 B per BWT row (measured +6 % over the 192-row layout)
+//   wide   (bwtlen >= 2^32, 64-bit interval kernels): 32-byte records per 192 rows { hdr (40-bit count | popc(w0) | popc(w0)+popc(w1)), w0, w1, w2 }
+//          -> 3.5 B per row: a refseq_ref-scale index (2.7e10 rows) takes 95 GB of the 180 GB HBM instead of 142 GB
+#define KJ_RANK_ROWS_NARROW 64
+#define KJ_RANK_ROWS_WIDE 192
+#define KJ_RANK_WORDS_NARROW 2
+#define KJ_RANK_WORDS_WIDE 4
+static inline uint32_t kj_rank_rows(int wide) { return wide ? KJ_RANK_ROWS_WIDE : KJ_RANK_ROWS_NARROW; }
+static inline uint32_t kj_rank_words(int wide) { return wide ? KJ_RANK_WORDS_WIDE : KJ_RANK_WORDS_NARROW; }
 #define KJ_LETTERS_PER_WORD 12
 #define KJ_MAX_ALEN 24
 #define KJ_MAX_IDS 21              // max_match_ids = 20 -> the set holds at most 21 (ConsumerThread.cpp:805)
@@ -32,13 +38,7 @@
 #define KJ_MAX_MM 8                // max supported -e
 #define KJ_SEG_WINDOW 12
 
-// hdr = cnt (40 bit: C[c] + #c before the block) | popc(w0) << 40 | (popc(w0)+popc(w1)) << 48 ; w0..w2 = one-hot bitmap.
-// For indexes below 2^32 rows byte 4 is zero, so (hdr >> 32 >> 8*word) & 0xff is the in-block prefix for word 0,1,2 without a select.
-#ifdef KJ_RANK64
-struct alignas(16) KjRankBlock { uint64_t hdr, w0; };
-#else
-struct alignas(32) KjRankBlock { uint64_t hdr, w0, w1, w2; };
-#endif
+// wide records: hdr = cnt (40 bit: C[c] + #c before the block) | popc(w0) << 40 | (popc(w0)+popc(w1)) << 48 ; w0..w2 = one-hot bitmap.
 #define KJ_CNT_MASK 0xffffffffffull
 #define KJ_P1_SHIFT 40
 #define KJ_P2_SHIFT 48
@@ -56,8 +56,8 @@ struct KjTables {
 };
 
 struct KjDevIndex {
-    const KjRankBlock* rank; uint64_t nb;       // [alen][nb]
-    const KjRankBlock* rank_base[KJ_MAX_ALEN];  // rank + c*nb per letter (saves the multiply in the inner loop)
+    const uint64_t* rank; uint64_t nb;          // [alen][nb] records of 2 (narrow) or 4 (wide) 64-bit words
+    const uint64_t* rank_base[KJ_MAX_ALEN];     // records of letter c (saves the multiply in the inner loop)
     const uint64_t* letters;
     uint64_t bwtlen; int alen;
     uint64_t C[KJ_MAX_ALEN + 1];                // C[c] = first SA row of letter c; C[alen] = bwtlen

@@ -146,7 +146,7 @@ void* kjemu_create(const char* fmi_path, const char* nodes_path, const kj_params
     KjDevIndex& D = c->D; KjHostIndex& H = c->H; memset(&D, 0, sizeof D);
     D.rank = H.rank.data(); D.nb = H.nb; D.letters = H.letters.data(); D.bwtlen = H.bwtlen; D.alen = H.alen;
     for (int a = 0; a <= H.alen; a++) D.C[a] = H.C[a];
-    for (int a = 0; a < H.alen; a++) D.rank_base[a] = D.rank + (uint64_t)a * H.nb;
+    for (int a = 0; a < H.alen; a++) D.rank_base[a] = D.rank + (uint64_t)a * H.nb * kj_rank_words(H.wide);
     D.sa_tax = H.sa_tax.data(); D.seq_tax = H.seq_tax.data(); D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
     D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
     D.tax_parent = H.tax_parent.data(); D.tax_depth = H.tax_depth.data(); D.tax_id = H.tax_id.data(); D.n_tax = (uint32_t)H.tax_id.size();

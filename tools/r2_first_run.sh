@@ -3,8 +3,8 @@
 o=gpurun_out; mkdir -p $o; tag=${1:-r2a}
 (nproc; free -g; df -h /tmp /dev/shm . ; nvidia-smi --query-gpu=name,memory.total --format=csv; lscpu | head -20) > $o/boxinfo.txt 2>&1
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee $o/pytest_gpu_$tag.log
-bash tools/ab_bench.sh mem 5000000 "" _r64 > $o/ab_$tag.txt 2>&1
-bash tools/ab_bench.sh greedy 3000000 "" _r64 >> $o/ab_$tag.txt 2>&1
+bash tools/ab_bench.sh mem 5000000 "" > $o/ab_$tag.txt 2>&1
+bash tools/ab_bench.sh greedy 3000000 "" >> $o/ab_$tag.txt 2>&1
 cat $o/ab_$tag.txt
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:kj_classify -s 3 -c 1 -f -o $o/prof_greedy_$tag python bench.py --mode greedy --reads 1000000 --steps 1 --warmup 3 --skip-cpu > $o/ncu_greedy_$tag.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:kj_classify -s 3 -c 1 -f -o $o/prof_mem_$tag python bench.py --reads 2000000 --steps 1 --warmup 3 --skip-cpu > $o/ncu_mem_$tag.log 2>&1
