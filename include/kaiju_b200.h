@@ -90,6 +90,14 @@ void kj_nodes_free(kj_nodes *t);
 /* --- context --- */
 /* Transcodes the index into the device layout, uploads it and the taxonomy to HBM of `device`. */
 int kj_create(kj_ctx **out, int device, const kj_params *params, const kj_index_view *index, const kj_taxonomy_view *taxonomy);
+/* The large arrays (rank records, packed letters, taxon-reduced suffix array, k-mer table) are built ON THE DEVICE from the raw BWT bytes and
+ * suffix-array samples of the view (replaces the table construction of mkfmi.c:63-78 / fmicommon.h:104-184).
+ * kj_create_scaled: the index of the collection in which every sequence of `index` occurs `copies` times in a row -- identical to what
+ * kaiju-mkbwt/-mkfmi produce for the K-fold FASTA (identical suffixes are ordered by sequence number), derived on the device without a
+ * suffix sort.  With all copies carrying the taxon of their original, MEM results equal those on the base index; it exists to bring
+ * refseq_ref-scale indexes (2.7e10 rows, ~126 GB in HBM) onto a GPU for capacity and throughput measurements.  copies = 1 == kj_create. */
+int kj_create_scaled(kj_ctx **out, int device, const kj_params *params, const kj_index_view *index, const kj_taxonomy_view *taxonomy, uint32_t copies);
+double kj_index_build_ms(const kj_ctx *ctx);      /* wall time of the index construction inside kj_create / kj_create_scaled */
 /* Device-native index file: kj_native_index_write() transcodes once (the .fmi + nodes.dmp views as for kj_create) and
  * stores the arrays exactly as they are uploaded (one-hot rank records, packed letters, taxon-reduced suffix array, re-indexed
  * taxonomy, k-mer table); kj_create_from_native() then needs one sequential read and the upload -- no transcode at load time.
@@ -119,6 +127,15 @@ int kj_classify_verbose(kj_ctx *ctx, const char *seq1, const uint64_t *off1, con
 int kj_classify_device(kj_ctx *ctx, const char *d_seq1, const uint64_t *d_off1, const char *d_seq2, const uint64_t *d_off2,
                        uint64_t n_reads, uint32_t max_len1, uint32_t max_len2, uint64_t *d_taxon_out, uint32_t *d_best_out,
                        void *cuda_stream);
+
+/* Variants with a DEVICE array d_compact_out[n_reads] (optional, may be NULL): the dense taxon index of every read as uint32 (position of
+ * the taxon in kj_counts_get()'s id list, 0xffffffff = unclassified) -- what the ranks of a multi-GPU job all-gather instead of the
+ * 64-bit NCBI ids.  kj_classify_device2 accepts d_taxon_out == NULL when d_compact_out is given. */
+int kj_classify2(kj_ctx *ctx, const char *seq1, const uint64_t *off1, const char *seq2, const uint64_t *off2,
+                 uint64_t n_reads, uint64_t *taxon_out, uint32_t *best_out, uint32_t *d_compact_out);
+int kj_classify_device2(kj_ctx *ctx, const char *d_seq1, const uint64_t *d_off1, const char *d_seq2, const uint64_t *d_off2,
+                        uint64_t n_reads, uint32_t max_len1, uint32_t max_len2, uint64_t *d_taxon_out, uint32_t *d_best_out,
+                        uint32_t *d_compact_out, void *cuda_stream);
 
 /* Whole files (replaces the reader loop of kaiju.cpp:288-394 and the output formatting of
  * ConsumerThread.cpp:724-739): FASTA or FASTQ, plain or gzip, in2 = second file of paired-end reads or NULL.  The text is
@@ -172,6 +189,10 @@ uint64_t kj_index_bytes(const kj_ctx *ctx);       /* bytes of HBM held by the in
 double kj_last_kernel_ms(const kj_ctx *ctx);      /* device time of the last classify kernel (CUDA events) */
 int kj_launch_geometry(const kj_ctx *ctx, int *grid, int *block, int *dyn_smem_bytes);  /* of the last classify launch */
 int kj_version(void);
+/* test hooks: checksums of the index arrays (rank, letters, sa_tax, seq_tax, kmer | bwtlen, wide, n_sa) as held in HBM by a context,
+ * and the same from the host transcoder (no GPU needed) -- the device construction is tested against the host one array for array */
+int kj_debug_index_checksums(kj_ctx *ctx, uint64_t out[8]);
+int kj_debug_host_index_checksums(const kj_index_view *index, const kj_taxonomy_view *taxonomy, uint64_t out[8]);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,14 @@ def lib():
         L.kj_nodes_view.argtypes = [C.c_void_p, C.POINTER(KjTaxonomyView)]
         L.kj_nodes_free.argtypes = [C.c_void_p]
         L.kj_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(KjParams), C.POINTER(KjIndexView), C.POINTER(KjTaxonomyView)]
+        if hasattr(L, "kj_create_scaled"):      # (A/B runs may load an older build of the library)
+            L.kj_create_scaled.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(KjParams), C.POINTER(KjIndexView), C.POINTER(KjTaxonomyView), C.c_uint32]
+            L.kj_index_build_ms.restype = C.c_double; L.kj_index_build_ms.argtypes = [C.c_void_p]
+            L.kj_debug_index_checksums.argtypes = [C.c_void_p, C.c_void_p]
+            L.kj_debug_host_index_checksums.argtypes = [C.POINTER(KjIndexView), C.POINTER(KjTaxonomyView), C.c_void_p]
+            L.kj_classify2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.kj_classify_device2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kj_native_index_write.argtypes = [C.POINTER(KjIndexView), C.POINTER(KjTaxonomyView), C.c_char_p]
         L.kj_create_from_native.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(KjParams), C.c_char_p]
         L.kj_set_params.argtypes = [C.c_void_p, C.POINTER(KjParams)]
@@ -115,6 +123,22 @@ def write_table(taxon_ids, counts, nodes_path, names_path, label, out_path, rank
                                 out_path.encode(), 1 if append else 0))
 
 
+def host_index_checksums(fmi_path, nodes_path):
+    """Test hook: the checksums Classifier.debug_index_checksums() must report, from the host transcoder (no GPU needed)."""
+    L = lib(); fmi = C.c_void_p(); nodes = C.c_void_p(); out = np.zeros(8, dtype=np.uint64)
+    _check(L.kj_fmi_load(fmi_path.encode(), C.byref(fmi)))
+    try:
+        _check(L.kj_nodes_load(nodes_path.encode(), C.byref(nodes)))
+        try:
+            iv = KjIndexView(); tv = KjTaxonomyView(); L.kj_fmi_view(fmi, C.byref(iv)); L.kj_nodes_view(nodes, C.byref(tv))
+            _check(L.kj_debug_host_index_checksums(C.byref(iv), C.byref(tv), out.ctypes.data))
+        finally:
+            L.kj_nodes_free(nodes)
+    finally:
+        L.kj_fmi_free(fmi)
+    return out
+
+
 def write_native_index(fmi_path, nodes_path, out_path):
     """Transcode a reference .fmi + nodes.dmp once into the device-native index file (no GPU needed)."""
     L = lib(); fmi = C.c_void_p(); nodes = C.c_void_p()
@@ -134,7 +158,8 @@ class Classifier:
     """One GPU context: the .fmi index and nodes.dmp taxonomy resident in HBM + run parameters.
     `Classifier(native_path, None)` loads a device-native index file written by write_native_index()."""
 
-    def __init__(self, fmi_path, nodes_path, device=0, params=None, **kw):
+    def __init__(self, fmi_path, nodes_path, device=0, params=None, copies=1, **kw):
+        """copies > 1: the index of the collection in which every sequence occurs `copies` times (kj_create_scaled)."""
         L = lib()
         self._ctx = C.c_void_p()
         if nodes_path is None:
@@ -151,7 +176,11 @@ class Classifier:
                 L.kj_fmi_view(fmi, C.byref(iv)); L.kj_nodes_view(nodes, C.byref(tv))
                 self.params = params if params is not None else make_params(**kw)
                 self.bwtlen = int(iv.bwtlen); self.nseq = int(iv.nseq)
-                _check(L.kj_create(C.byref(self._ctx), device, C.byref(self.params), C.byref(iv), C.byref(tv)))
+                self.bwtlen *= int(copies); self.nseq *= int(copies)
+                if int(copies) == 1:
+                    _check(L.kj_create(C.byref(self._ctx), device, C.byref(self.params), C.byref(iv), C.byref(tv)))
+                else:
+                    _check(L.kj_create_scaled(C.byref(self._ctx), device, C.byref(self.params), C.byref(iv), C.byref(tv), int(copies)))
             finally:
                 L.kj_nodes_free(nodes)
         finally:
@@ -207,6 +236,18 @@ class Classifier:
     def classify_device(self, d_seq1, d_off1, d_seq2, d_off2, n, d_tax, d_best=None, max_len1=0, max_len2=0, stream=None):
         _check(lib().kj_classify_device(self._ctx, d_seq1, d_off1, d_seq2, d_off2, n, max_len1, max_len2, d_tax, d_best, stream))
 
+    def classify_device2(self, d_seq1, d_off1, d_seq2, d_off2, n, d_tax, d_best, d_compact, max_len1=0, max_len2=0, stream=None):
+        """As classify_device, plus a device uint32 array of dense taxon indices (see compact_ids); d_tax may be None."""
+        _check(lib().kj_classify_device2(self._ctx, d_seq1, d_off1, d_seq2, d_off2, n, max_len1, max_len2, d_tax, d_best, d_compact, stream))
+
+    def classify2_ptrs(self, seq1_ptr, off1_ptr, seq2_ptr, off2_ptr, n, tax_ptr, best_ptr, d_compact):
+        """Host buffers in and out (kj_classify) plus the dense taxon indices left in the DEVICE array d_compact."""
+        _check(lib().kj_classify2(self._ctx, seq1_ptr, off1_ptr, seq2_ptr, off2_ptr, n, tax_ptr, best_ptr, d_compact))
+
+    def compact_ids(self):
+        """NCBI taxon id of every dense taxon index (the id list of counts(); the last entry, 0, stands for unclassified)."""
+        return self.counts(nonzero=False)[0]
+
     def classify_files(self, in1, in2=None, out_path=None, verbose=False):
         """FASTA/FASTQ(.gz) files -> kaiju output file, parsed / classified / formatted on the device.  Returns (reads, classified)."""
         n = C.c_uint64(); k = C.c_uint64()
@@ -248,6 +289,13 @@ class Classifier:
     @property
     def index_bytes(self):
         return int(lib().kj_index_bytes(self._ctx))
+
+    @property
+    def index_build_ms(self):
+        return float(lib().kj_index_build_ms(self._ctx))
+
+    def debug_index_checksums(self):
+        out = np.zeros(8, dtype=np.uint64); _check(lib().kj_debug_index_checksums(self._ctx, out.ctypes.data)); return out
 
     @property
     def last_kernel_ms(self):

@@ -9,10 +9,12 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -43,7 +45,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
                    const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
                    const uint8_t* __restrict__ seq2, const uint64_t* __restrict__ off2,
                    uint64_t base1, uint64_t base2, uint64_t n_reads,
-                   uint64_t* __restrict__ taxon_out, uint32_t* __restrict__ best_out, uint64_t* __restrict__ ids_out, uint8_t* __restrict__ nids_out,
+                   uint64_t* __restrict__ taxon_out, uint32_t* __restrict__ best_out, uint64_t* __restrict__ ids_out, uint8_t* __restrict__ nids_out, uint32_t* __restrict__ compact_out,
                    unsigned long long* __restrict__ counter, KjKept* __restrict__ spill, uint8_t* __restrict__ gscratch,
                    uint32_t gscratch_bytes, uint8_t* __restrict__ gws, unsigned long long* __restrict__ counts, uint32_t* __restrict__ err) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -88,7 +90,8 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
             uint32_t t = kj_classify_item<MODE, IdxT>(cx, seq1 + a0, (int)(a1 - a0), paired ? seq2 + b0 : nullptr, (int)(b1 - b0), paired, best);
             const uint64_t id = t == KJ_TAX_BAD ? 0ull : sh->ix.tax_id[t];
             if (cx.w.lane == 0) {
-                taxon_out[r] = id;
+                if (taxon_out) taxon_out[r] = id;
+                if (compact_out) compact_out[r] = id ? t : KJ_TAX_BAD;
                 if (best_out) best_out[r] = id ? best : 0u;
                 // per-taxon read counts (kaiju2table's first pass), fused: a separate counting kernel behind a persistent grid would stall the chunk pipeline
                 if (counts) atomicAdd(counts + (id ? t : sh->ix.n_tax), 1ull);
@@ -142,7 +145,7 @@ struct kj_ctx {
     KjDevIndex* d_ix = nullptr; KjTables* d_tables = nullptr;
     void* d_rank = nullptr; void* d_letters = nullptr; void* d_sa_tax = nullptr; void* d_seq_tax = nullptr;
     void* d_tax_parent = nullptr; void* d_tax_depth = nullptr; void* d_tax_id = nullptr; void* d_lnfact = nullptr; void* d_kmer = nullptr;
-    uint64_t index_bytes = 0;
+    uint64_t index_bytes = 0; uint64_t n_sa = 0; double build_ms = 0.0;
     // run state
     unsigned long long* d_counter = nullptr; uint32_t* d_err = nullptr; unsigned int* d_maxlen = nullptr;
     KjKept* d_spill = nullptr; size_t spill_bytes = 0; uint8_t* d_gscratch = nullptr; size_t gscratch_bytes_total = 0;
@@ -180,9 +183,15 @@ static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid)
     rp.ws_global = smem > limit ? 1u : 0u;
     if (rp.ws_global) smem = head;
     const int cfg = rp.mode * 2 + (int)rp.ws_global;
-    if (smem == c->smem_bytes && c->grid > 0 && c->cfg_mode == cfg) { grid = c->grid; return KJ_OK; }
+    // The max-dynamic-shared-memory attribute belongs to the kernel instantiation on the device, not to a context: several contexts
+    // (or batches with different read lengths) share it, so it is only ever raised (process-wide table), never lowered.
+    static std::mutex attr_mu; static size_t attr_set[64][8];
+    const int inst = rp.mode * 4 + (c->H.wide ? 2 : 0) + (int)rp.ws_global;
+    bool raise = false;
+    { std::lock_guard<std::mutex> lk(attr_mu); if (c->device < 64 && smem > attr_set[c->device][inst]) { attr_set[c->device][inst] = smem; raise = true; } else if (c->device >= 64) raise = true; }
+    if (!raise && smem == c->smem_bytes && c->grid > 0 && c->cfg_mode == cfg) { grid = c->grid; return KJ_OK; }
     int per_sm = 0;
-#define KJ_CFG(M, T, G) { CK(cudaFuncSetAttribute(kj_classify_kernel<M, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+#define KJ_CFG(M, T, G) { if (raise) CK(cudaFuncSetAttribute(kj_classify_kernel<M, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
                           CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<M, T, G>, KJ_WARPS_PER_CTA * 32, smem)); }
 #define KJ_CFG2(M, T) { if (rp.ws_global) KJ_CFG(M, T, true) else KJ_CFG(M, T, false) }
     if (rp.mode == 0) { if (c->H.wide) KJ_CFG2(0, uint64_t) else KJ_CFG2(0, uint32_t) }
@@ -217,50 +226,118 @@ static int upload_evalue_breaks(kj_ctx* c) {
     return KJ_OK;
 }
 
-// common part of kj_create / kj_create_from_native: `fill` produces the host arrays of the device layout, the rest uploads them
-template <class Fill> static int create_ctx(kj_ctx** out, int device, const kj_params* params, Fill fill) {
+static int new_ctx(kj_ctx** out, int device, const kj_params* params) {
     int rc = kj_check_params(*params); if (rc) return rc;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { kj_err() = "no CUDA device available (this library has no CPU fallback)"; return KJ_ERR_NO_DEVICE; }
     if (device < 0 || device >= ndev) { kj_err() = "device ordinal out of range"; return KJ_ERR_ARG; }
     CK(cudaSetDevice(device));
     kj_ctx* c = new kj_ctx(); c->device = device; c->params = *params;
-    std::unique_ptr<kj_ctx, void (*)(kj_ctx*)> guard(c, kj_destroy);      // every early return below releases what was allocated so far
+    std::unique_ptr<kj_ctx, void (*)(kj_ctx*)> guard(c, kj_destroy);
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); c->sm_count = prop.multiProcessorCount;
-    rc = fill(c->H); if (rc) return rc;
-    KjHostIndex& H = c->H; uint64_t tot = 0;
-    if ((rc = upload(H.rank, &c->d_rank, tot)) || (rc = upload(H.letters, &c->d_letters, tot)) || (rc = upload(H.sa_tax, &c->d_sa_tax, tot)) ||
-        (rc = upload(H.seq_tax, &c->d_seq_tax, tot)) || (rc = upload(H.tax_parent, &c->d_tax_parent, tot)) || (rc = upload(H.tax_depth, &c->d_tax_depth, tot)) ||
-        (rc = upload(H.tax_id, &c->d_tax_id, tot)) || (rc = upload(H.lnfact, &c->d_lnfact, tot)) || (rc = (H.wide ? upload(H.kmer, &c->d_kmer, tot) : upload(H.kmer32, &c->d_kmer, tot)))) return rc;
-    CK(cudaMalloc((void**)&c->d_tables, sizeof(KjTables))); CK(cudaMemcpy(c->d_tables, &H.tables, sizeof(KjTables), cudaMemcpyHostToDevice));
-    KjDevIndex& D = c->dix; memset(&D, 0, sizeof D);
+    CK(cudaMalloc((void**)&c->d_err, sizeof(uint32_t))); CK(cudaMemset(c->d_err, 0, sizeof(uint32_t)));
+    CK(cudaMalloc((void**)&c->d_quirk, sizeof c->H.quirk_d)); CK(cudaMemset(c->d_quirk, 0, sizeof c->H.quirk_d));
+    *out = guard.release(); return KJ_OK;
+}
+// device descriptor from the context's device arrays + meta data
+static int upload_descriptor(kj_ctx* c) {
+    KjHostIndex& H = c->H; KjDevIndex& D = c->dix; memset(&D, 0, sizeof D);
     D.rank = (const uint64_t*)c->d_rank; D.nb = H.nb; D.letters = (const uint64_t*)c->d_letters; D.bwtlen = H.bwtlen; D.alen = H.alen;
     for (int a = 0; a <= H.alen; a++) D.C[a] = H.C[a];
     for (int a = 0; a < H.alen; a++) D.rank_base[a] = D.rank + (uint64_t)a * H.nb * kj_rank_words(H.wide);
     D.sa_tax = (const uint32_t*)c->d_sa_tax; D.seq_tax = (const uint32_t*)c->d_seq_tax; D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
-    D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
+    D.n_sa = c->n_sa; D.nseq = H.nseq;
     D.tax_parent = (const uint32_t*)c->d_tax_parent; D.tax_depth = (const uint32_t*)c->d_tax_depth; D.tax_id = (const uint64_t*)c->d_tax_id; D.n_tax = (uint32_t)H.tax_id.size();
-    D.lnfact = (const double*)c->d_lnfact; D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? c->d_kmer : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = c->d_tables; D.quirk_lo = H.quirk_lo; D.mono = H.quirk_lo == ~0ull ? 1 : 0;
-    CK(cudaMalloc((void**)&c->d_quirk, sizeof H.quirk_d)); CK(cudaMemcpy(c->d_quirk, H.quirk_d, sizeof H.quirk_d, cudaMemcpyHostToDevice)); D.quirk_d = c->d_quirk;
-    CK(cudaMalloc((void**)&c->d_ix, sizeof(KjDevIndex))); CK(cudaMemcpy(c->d_ix, &D, sizeof(KjDevIndex), cudaMemcpyHostToDevice));
+    D.lnfact = (const double*)c->d_lnfact; D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? c->d_kmer : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = c->d_tables;
+    D.quirk_lo = H.quirk_lo; D.mono = H.quirk_lo == ~0ull ? 1 : 0; D.quirk_d = c->d_quirk;
+    if (!c->d_ix) CK(cudaMalloc((void**)&c->d_ix, sizeof(KjDevIndex)));
+    CK(cudaMemcpy(c->d_ix, &D, sizeof(KjDevIndex), cudaMemcpyHostToDevice));
+    return KJ_OK;
+}
+static int upload_small(kj_ctx* c, uint64_t& tot) {
+    KjHostIndex& H = c->H; int rc;
+    if ((rc = upload(H.tax_parent, &c->d_tax_parent, tot)) || (rc = upload(H.tax_depth, &c->d_tax_depth, tot)) || (rc = upload(H.tax_id, &c->d_tax_id, tot)) || (rc = upload(H.lnfact, &c->d_lnfact, tot))) return rc;
+    CK(cudaMalloc((void**)&c->d_tables, sizeof(KjTables))); CK(cudaMemcpy(c->d_tables, &H.tables, sizeof(KjTables), cudaMemcpyHostToDevice));
+    return KJ_OK;
+}
+static int finish_ctx(kj_ctx* c, uint64_t tot) {
+    KjHostIndex& H = c->H; int rc;
+    CK(cudaMemcpy(c->d_quirk, H.quirk_d, sizeof H.quirk_d, cudaMemcpyHostToDevice));
+    if ((rc = upload_descriptor(c))) return rc;
     c->index_bytes = tot;
-    // host copies of the big arrays are no longer needed
-    std::vector<uint64_t>().swap(H.rank); std::vector<uint64_t>().swap(H.letters); std::vector<uint32_t>().swap(H.sa_tax); std::vector<KjKmer>().swap(H.kmer); std::vector<KjKmer32>().swap(H.kmer32);
-    CK(cudaMalloc((void**)&c->d_counter, 2 * sizeof(unsigned long long))); CK(cudaMalloc((void**)&c->d_err, sizeof(uint32_t))); CK(cudaMalloc((void**)&c->d_maxlen, 2 * sizeof(unsigned int)));
-    CK(cudaMemset(c->d_err, 0, sizeof(uint32_t)));
+    CK(cudaMalloc((void**)&c->d_counter, 2 * sizeof(unsigned long long))); CK(cudaMalloc((void**)&c->d_maxlen, 2 * sizeof(unsigned int)));
     for (int s = 0; s < 2; s++) CK(cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev_a)); CK(cudaEventCreate(&c->ev_b));
     if ((rc = upload_evalue_breaks(c))) return rc;
     c->n_counts = (uint32_t)H.tax_id.size() + 1u; c->n_present = H.n_present;
     CK(cudaMalloc((void**)&c->d_counts, (size_t)c->n_counts * 8)); CK(cudaMalloc((void**)&c->d_counts_pending, (size_t)c->n_counts * 8));
     CK(cudaMemset(c->d_counts, 0, (size_t)c->n_counts * 8)); CK(cudaMemset(c->d_counts_pending, 0, (size_t)c->n_counts * 8));
+    return KJ_OK;
+}
+
+// kj_create_from_native (and kj_create with KJ_HOST_BUILD=1): `fill` produces the host arrays of the device layout, the rest uploads them
+template <class Fill> static int create_ctx(kj_ctx** out, int device, const kj_params* params, Fill fill) {
+    kj_ctx* c = nullptr; int rc = new_ctx(&c, device, params); if (rc) return rc;
+    std::unique_ptr<kj_ctx, void (*)(kj_ctx*)> guard(c, kj_destroy);      // every early return below releases what was allocated so far
+    rc = fill(c->H); if (rc) return rc;
+    KjHostIndex& H = c->H; uint64_t tot = 0;
+    // one guard entry: the reference's header counts one sampled row less than kaiju-mkbwt writes (suffixArray.c:160 vs 206-216), so the last
+    // sampled row of an index has no entry; the reference reads past its array there, the device reads "no taxon"
+    c->n_sa = H.sa_tax.size(); H.sa_tax.push_back(KJ_TAX_BAD);
+    if ((rc = upload(H.rank, &c->d_rank, tot)) || (rc = upload(H.letters, &c->d_letters, tot)) || (rc = upload(H.sa_tax, &c->d_sa_tax, tot)) ||
+        (rc = upload(H.seq_tax, &c->d_seq_tax, tot)) || (rc = upload_small(c, tot)) || (rc = (H.wide ? upload(H.kmer, &c->d_kmer, tot) : upload(H.kmer32, &c->d_kmer, tot)))) return rc;
+    // host copies of the big arrays are no longer needed
+    std::vector<uint64_t>().swap(H.rank); std::vector<uint64_t>().swap(H.letters); std::vector<uint32_t>().swap(H.sa_tax); std::vector<KjKmer>().swap(H.kmer); std::vector<KjKmer32>().swap(H.kmer32);
+    if ((rc = finish_ctx(c, tot))) return rc;
+    *out = guard.release(); return KJ_OK;
+}
+
+#include "kj_build.h"
+// kj_create / kj_create_scaled: the large arrays are built on the device from the raw BWT bytes and suffix-array samples (kj_build.h)
+static int create_ctx_device(kj_ctx** out, int device, const kj_params* params, const kj_index_view& v, const kj_taxonomy_view& t, uint32_t copies, const kj_ctx* base) {
+    kj_ctx* c = nullptr; int rc = new_ctx(&c, device, params); if (rc) return rc;
+    std::unique_ptr<kj_ctx, void (*)(kj_ctx*)> guard(c, kj_destroy);
+    const auto t0 = std::chrono::steady_clock::now();
+    uint8_t lcode[256]; rc = kj_build_host_meta(v, t, copies, c->H, lcode); if (rc) return rc;
+    uint64_t tot = 0;
+    if ((rc = upload_small(c, tot)) || (rc = kj_device_build(c, v, lcode, copies, base, tot))) return rc;
+    c->H.kmer_k = 0;
+    if ((rc = upload_descriptor(c))) return rc;
+    { const char* ek = getenv("KJ_KMER_K"); if ((rc = kj_device_build_kmer(c, ek ? atoi(ek) : 5, tot))) return rc; }
+    std::vector<uint32_t>().swap(c->H.seq_tax);
+    if ((rc = finish_ctx(c, tot))) return rc;
+    CK(cudaDeviceSynchronize());
+    c->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = guard.release(); return KJ_OK;
 }
 
 extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, const kj_index_view* index, const kj_taxonomy_view* taxonomy) {
     if (!out || !params || !index || !taxonomy) { kj_err() = "kj_create: null argument"; return KJ_ERR_ARG; }
-    return create_ctx(out, device, params, [&](KjHostIndex& H) { return kj_build_host_index(*index, *taxonomy, H); });
+    if (getenv("KJ_HOST_BUILD")) return create_ctx(out, device, params, [&](KjHostIndex& H) { return kj_build_host_index(*index, *taxonomy, H); });   // developer hook: host transcoder + upload
+    return create_ctx_device(out, device, params, *index, *taxonomy, 1, nullptr);
 }
+extern "C" int kj_create_scaled(kj_ctx** out, int device, const kj_params* params, const kj_index_view* index, const kj_taxonomy_view* taxonomy, uint32_t copies) {
+    if (!out || !params || !index || !taxonomy) { kj_err() = "kj_create_scaled: null argument"; return KJ_ERR_ARG; }
+    if (copies <= 1) return kj_create(out, device, params, index, taxonomy);
+    kj_ctx* base = nullptr; int rc = create_ctx_device(&base, device, params, *index, *taxonomy, 1, nullptr); if (rc) return rc;
+    rc = create_ctx_device(out, device, params, *index, *taxonomy, copies, base);
+    kj_destroy(base);
+    return rc;
+}
+extern "C" double kj_index_build_ms(const kj_ctx* c) { return c ? c->build_ms : 0.0; }
+// test hook: checksums of the index arrays as they sit in HBM (rank, letters, sa_tax, seq_tax, kmer), to compare the device construction
+// with the host transcoder array for array
+extern "C" int kj_debug_index_checksums(kj_ctx* c, uint64_t out[8]) {
+    if (!c || !out) return KJ_ERR_ARG; CK(cudaSetDevice(c->device)); CK(cudaDeviceSynchronize());
+    const KjHostIndex& H = c->H; memset(out, 0, 64);
+    const size_t sz[5] = {(size_t)H.alen * H.nb * kj_rank_words(H.wide) * 8, (size_t)(H.bwtlen / KJ_LETTERS_PER_WORD + 2) * 8, (size_t)c->n_sa * 4, (size_t)H.nseq * 4,
+                          H.kmer_k ? (size_t)pow(20.0, H.kmer_k) * (H.wide ? sizeof(KjKmer) : sizeof(KjKmer32)) : 0};
+    const void* ptr[5] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_kmer};
+    for (int i = 0; i < 5; i++) { std::vector<uint8_t> h(sz[i]); if (sz[i]) CK(cudaMemcpy(h.data(), ptr[i], sz[i], cudaMemcpyDeviceToHost)); out[i] = kj_mix_bytes(0x6b616a75ull + i, h.data(), h.size()); }
+    out[5] = H.bwtlen; out[6] = (uint64_t)H.wide; out[7] = c->n_sa;
+    return KJ_OK;
+}
+
 // device-native index file: written once from the reference's .fmi + nodes.dmp, loaded without the transcode
 extern "C" int kj_native_index_write(const kj_index_view* index, const kj_taxonomy_view* taxonomy, const char* path) {
     if (!index || !taxonomy || !path) { kj_err() = "kj_native_index_write: null argument"; return KJ_ERR_ARG; }
@@ -296,7 +373,7 @@ extern "C" void kj_destroy(kj_ctx* c) {
 // one launch over reads [0,n) whose sequences/offsets are resident on the device
 static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_off1, const uint8_t* d_seq2, const uint64_t* d_off2, uint64_t base1, uint64_t base2,
                   uint64_t n, uint32_t max1, uint32_t max2, uint64_t* d_tax, uint32_t* d_best, cudaStream_t st, bool time_it,
-                  uint64_t* d_ids = nullptr, uint8_t* d_nids = nullptr, unsigned long long* d_count_dst = nullptr) {
+                  uint64_t* d_ids = nullptr, uint8_t* d_nids = nullptr, unsigned long long* d_count_dst = nullptr, uint32_t* d_compact = nullptr) {
     if (c->params.input_is_protein) {
         if (d_seq2) { kj_err() = "protein input only supports one input (kaiju.cpp:201)"; return KJ_ERR_ARG; }
         if (max1 > KJ_MAX_PROTEIN_LEN) { kj_err() = "protein read longer than KJ_MAX_PROTEIN_LEN (5461 residues) is not supported"; return KJ_ERR_UNSUPPORTED; }
@@ -311,7 +388,7 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     if (time_it) CK(cudaEventRecord(c->ev_a, st));
     const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
 #define KJ_LAUNCH(M, T) if (rp.ws_global) KJ_LAUNCH3(M, T, true); else KJ_LAUNCH3(M, T, false)
-#define KJ_LAUNCH3(M, T, G) kj_classify_kernel<M, T, G><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, \
+#define KJ_LAUNCH3(M, T, G) kj_classify_kernel<M, T, G><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, d_compact, \
             c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
             c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), \
             rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err)
@@ -344,9 +421,9 @@ static int check_err_flag(kj_ctx* c) {
     return KJ_OK;
 }
 
-extern "C" int kj_classify_device(kj_ctx* c, const char* d_seq1, const uint64_t* d_off1, const char* d_seq2, const uint64_t* d_off2, uint64_t n,
-                                  uint32_t max_len1, uint32_t max_len2, uint64_t* d_tax, uint32_t* d_best, void* cuda_stream) {
-    if (!c || !d_seq1 || !d_off1 || !d_tax || (d_seq2 && !d_off2)) { kj_err() = "kj_classify_device: null argument"; return KJ_ERR_ARG; }
+extern "C" int kj_classify_device2(kj_ctx* c, const char* d_seq1, const uint64_t* d_off1, const char* d_seq2, const uint64_t* d_off2, uint64_t n,
+                                   uint32_t max_len1, uint32_t max_len2, uint64_t* d_tax, uint32_t* d_best, uint32_t* d_compact, void* cuda_stream) {
+    if (!c || !d_seq1 || !d_off1 || (!d_tax && !d_compact) || (d_seq2 && !d_off2)) { kj_err() = "kj_classify_device: null argument"; return KJ_ERR_ARG; }
     if (n == 0) return KJ_OK;
     CK(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -357,7 +434,13 @@ extern "C" int kj_classify_device(kj_ctx* c, const char* d_seq1, const uint64_t*
         unsigned int h[2] = {0, 0}; CK(cudaMemcpyAsync(h, c->d_maxlen, sizeof h, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
         max_len1 = h[0]; max_len2 = h[1];
     }
-    return launch(c, 0, (const uint8_t*)d_seq1, d_off1, (const uint8_t*)d_seq2, d_off2, 0, 0, n, max_len1, max_len2, d_tax, d_best, st, true);
+    return launch(c, 0, (const uint8_t*)d_seq1, d_off1, (const uint8_t*)d_seq2, d_off2, 0, 0, n, max_len1, max_len2, d_tax, d_best, st, true, nullptr, nullptr, nullptr, d_compact);
+}
+
+extern "C" int kj_classify_device(kj_ctx* c, const char* d_seq1, const uint64_t* d_off1, const char* d_seq2, const uint64_t* d_off2, uint64_t n,
+                                  uint32_t max_len1, uint32_t max_len2, uint64_t* d_tax, uint32_t* d_best, void* cuda_stream) {
+    if (!d_tax) { kj_err() = "kj_classify_device: null argument"; return KJ_ERR_ARG; }
+    return kj_classify_device2(c, d_seq1, d_off1, d_seq2, d_off2, n, max_len1, max_len2, d_tax, d_best, nullptr, cuda_stream);
 }
 
 static int ensure_staging(kj_ctx* c, int slot, size_t bytes1, size_t bytes2, size_t reads) {
@@ -378,7 +461,7 @@ static int ensure_staging(kj_ctx* c, int slot, size_t bytes1, size_t bytes2, siz
 }
 
 static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
-                         uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out) {
+                         uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out, uint32_t* d_compact = nullptr) {
     if (!c || !seq1 || !off1 || !taxon_out || (seq2 && !off2) || ((ids_out == nullptr) != (nids_out == nullptr))) { kj_err() = "kj_classify: null argument"; return KJ_ERR_ARG; }
     if (n == 0) return KJ_OK;
     CK(cudaSetDevice(c->device));
@@ -431,7 +514,7 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
         }
         if (trace) { tr.back().cnt = cnt; cudaEventRecord(tr.back().e[1], st); }
         rc = launch(c, s, c->d_seq[s][0], c->d_off[s][0], paired ? c->d_seq[s][1] : nullptr, paired ? c->d_off[s][1] : nullptr, b1, b2, cnt, max1, max2,
-                    c->d_tax[s], best_out ? c->d_best[s] : nullptr, st, true, ids_out ? c->d_ids[s] : nullptr, ids_out ? c->d_nids[s] : nullptr, c->d_counts_pending);
+                    c->d_tax[s], best_out ? c->d_best[s] : nullptr, st, true, ids_out ? c->d_ids[s] : nullptr, ids_out ? c->d_nids[s] : nullptr, c->d_counts_pending, d_compact ? d_compact + start : nullptr);
         if (rc) return rc;
         if (trace) cudaEventRecord(tr.back().e[2], st);
         CK(cudaMemcpyAsync(taxon_out + start, c->d_tax[s], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -459,10 +542,10 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
 
 // A full Greedy variant ring (flag 4) enlarges the ring for the next launch: repeat the call until it fits (bounded).
 static int classify_host_retry(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
-                               uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out) {
+                               uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out, uint32_t* d_compact = nullptr) {
     for (;;) {
         const uint32_t boost = c ? c->variant_boost : 0;
-        int rc = classify_host(c, seq1, off1, seq2, off2, n, taxon_out, best_out, ids_out, nids_out);
+        int rc = classify_host(c, seq1, off1, seq2, off2, n, taxon_out, best_out, ids_out, nids_out, d_compact);
         if (rc != KJ_ERR_OVERFLOW || !c || c->variant_boost == boost) return rc;
     }
 }
@@ -470,6 +553,10 @@ static int classify_host_retry(kj_ctx* c, const char* seq1, const uint64_t* off1
 extern "C" int kj_classify(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
                            uint64_t* taxon_out, uint32_t* best_out) {
     return classify_host_retry(c, seq1, off1, seq2, off2, n, taxon_out, best_out, nullptr, nullptr);
+}
+extern "C" int kj_classify2(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
+                            uint64_t* taxon_out, uint32_t* best_out, uint32_t* d_compact_out) {
+    return classify_host_retry(c, seq1, off1, seq2, off2, n, taxon_out, best_out, nullptr, nullptr, d_compact_out);
 }
 extern "C" int kj_classify_verbose(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
                                    uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out) {

@@ -172,65 +172,37 @@ int kj_check_params(const kj_params& p) {
 // transcoder: reference in-memory index -> device layout
 // ------------------------------------------------------------------------------------------------
 static inline uint64_t host_rank(const KjHostIndex& H, uint32_t c, uint64_t k);
-int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHostIndex& H) {
-    if (!v.bwt || !v.startLcode || !v.alphabet || !v.sa || !v.seq_taxon || v.bwtlen <= 0) { kj_err() = "kj_create: incomplete index view"; return KJ_ERR_ARG; }
+// Everything of the device index that is small or independent of the BWT body: tables, byte-code -> letter map, geometry (layout choice,
+// quirk flag), the re-indexed taxonomy, sequence -> taxon, suffix-array sampling parameters, ln(n!) table.  `copies` > 1 describes the
+// collection in which every sequence occurs `copies` times in a row (kj_create_scaled): bwtlen, nseq and db_len scale, sequence
+// K*s + c inherits the taxon of sequence s.
+int kj_build_host_meta(const kj_index_view& v, const kj_taxonomy_view& t, uint32_t copies, KjHostIndex& H, uint8_t lcode[256]) {
+    if (!v.bwt || !v.startLcode || !v.alphabet || !v.sa || !v.seq_taxon || v.bwtlen <= 0 || v.nseq < 0 || v.ncheck < 0 || v.chpt_exp < 0 || v.chpt_exp > 30 || v.nbytes <= 0 || v.nbytes > 8) {
+        kj_err() = "kj_create: incomplete index view"; return KJ_ERR_ARG; }
     if (v.alen < 2 || v.alen > KJ_MAX_ALEN) { kj_err() = "alphabet size not supported"; return KJ_ERR_UNSUPPORTED; }
-    const int alen = v.alen; const uint64_t n = (uint64_t)v.bwtlen;
-    H.alen = alen; H.bwtlen = n; H.nseq = (uint32_t)v.nseq; H.db_length = (double)(v.db_len - v.nseq);
+    if (copies < 1 || copies > 65536) { kj_err() = "copies out of range"; return KJ_ERR_ARG; }
+    const int alen = v.alen; const uint64_t n = (uint64_t)v.bwtlen * copies;
+    if (n >= (1ull << 38)) { kj_err() = "index too large (>= 2^38 rows)"; return KJ_ERR_UNSUPPORTED; }      // checked before anything large is built
+    if ((uint64_t)v.nseq * copies >= 0x7fffffffull) { kj_err() = "too many sequences"; return KJ_ERR_UNSUPPORTED; }
+    H.alen = alen; H.bwtlen = n; H.nseq = (uint32_t)((uint64_t)v.nseq * copies); H.db_length = (double)(v.db_len - v.nseq) * (double)copies;
     int rc = build_tables(std::string(v.alphabet, (size_t)alen), H.tables); if (rc) return rc;
     // byte code -> letter (fmi_fill_codes, compactfmi.c:75-89)
-    uint8_t lcode[256]; memset(lcode, 0, sizeof lcode);
+    memset(lcode, 0, 256);
     for (int a = 0; a < alen; a++) {
         int s = v.startLcode[a], e = v.startLcode[a + 1];
         if (s < 0 || e > 256 || s > e) { kj_err() = "corrupt startLcode"; return KJ_ERR_IO; }
         for (int k = s; k < e; k++) lcode[k] = (uint8_t)a;
     }
-    if (n >= (1ull << 38)) { kj_err() = "index too large (>= 2^38 rows)"; return KJ_ERR_UNSUPPORTED; }
     // KJ_FORCE_WIDE: exercise the 64-bit kernels on small test indexes.  Indexes with the reference's checkpoint quirk (below) also
     // take the 64-bit kernels: only those carry the rank correction, so that ordinary indexes pay nothing for the 1-in-65536 case.
     const bool quirk = (n & 65535ull) == 0 && n >= 131072ull;
     H.wide = (n >= 0xffffff00ull || getenv("KJ_FORCE_WIDE") || quirk) ? 1 : 0;
-    // rank records + packed letters, chunked over threads
-    const uint32_t RB = kj_rank_rows(H.wide), RW = kj_rank_words(H.wide);
-    const uint64_t nb = n / RB + 1; H.nb = nb;
-    const uint64_t CH = 192ull * 2048;                                  // positions per chunk (multiple of 192, 64 and 12)
-    const uint64_t nch = (n + CH - 1) / CH;
-    std::vector<uint64_t> ccount((size_t)(nch + 1) * alen, 0);
-    unsigned nthr = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-    auto par = [&](auto fn) {
-        std::vector<std::thread> th; for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] { for (uint64_t c = tI; c < nch; c += nthr) fn(c); });
-        for (auto& x : th) x.join();
-    };
-    par([&](uint64_t c) { uint64_t* cc = &ccount[(size_t)(c + 1) * alen]; uint64_t e = std::min(n, (c + 1) * CH); for (uint64_t k = c * CH; k < e; k++) cc[lcode[v.bwt[k]]]++; });
-    for (uint64_t c = 1; c <= nch; c++) for (int a = 0; a < alen; a++) ccount[(size_t)c * alen + a] += ccount[(size_t)(c - 1) * alen + a];
-    const uint64_t* total = &ccount[(size_t)nch * alen];
-    H.C[0] = 0; for (int a = 0; a < alen; a++) H.C[a + 1] = H.C[a] + total[a];
-    if (H.C[alen] != n) { kj_err() = "letter counts do not add up"; return KJ_ERR_IO; }
-    try { H.rank.assign((size_t)alen * nb * RW, 0ull); H.letters.assign((size_t)(n / KJ_LETTERS_PER_WORD + 2), 0); }
-    catch (...) { kj_err() = "out of host memory building the rank table"; return KJ_ERR_NOMEM; }
-    par([&](uint64_t c) {
-        uint64_t run[KJ_MAX_ALEN]; for (int a = 0; a < alen; a++) run[a] = H.C[a] + ccount[(size_t)c * alen + a];
-        uint64_t e = std::min(n, (c + 1) * CH);
-        for (uint64_t b0 = c * CH; b0 < e; b0 += RB) {
-            uint64_t b = b0 / RB, be = std::min(n, b0 + RB);
-            for (int a = 0; a < alen; a++) H.rank[((size_t)a * nb + b) * RW] = run[a];
-            for (uint64_t k = b0; k < be; k++) {
-                uint32_t a = lcode[v.bwt[k]], r = (uint32_t)(k - b0);
-                H.rank[((size_t)a * nb + b) * RW + 1u + (r >> 6)] |= 1ull << (r & 63);
-                run[a]++;
-            }
-        }
-        for (uint64_t k = c * CH; k < e; k++) H.letters[k / KJ_LETTERS_PER_WORD] |= (uint64_t)lcode[v.bwt[k]] << (5 * (k % KJ_LETTERS_PER_WORD));
-    });
-    // the record after the last letter (k == bwtlen lands there when bwtlen % RB == 0; otherwise the last partial block already exists)
-    if (n % RB == 0) for (int a = 0; a < alen; a++) H.rank[((size_t)a * nb + (nb - 1)) * RW] = H.C[a] + total[a];
-    if (H.wide) {   // fold the in-block prefix popcounts into the header
-        std::vector<std::thread> th; const size_t tot = (size_t)alen * nb;
-        for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] { for (size_t i = tI; i < tot; i += nthr) { uint64_t* B = &H.rank[i * 4];
-            uint64_t p1 = (uint64_t)__builtin_popcountll(B[1]), p2 = p1 + (uint64_t)__builtin_popcountll(B[2]); B[0] = (B[0] & KJ_CNT_MASK) | (p1 << KJ_P1_SHIFT) | (p2 << KJ_P2_SHIFT); } });
-        for (auto& x : th) x.join();
-    }
-
+    H.nb = n / kj_rank_rows(H.wide) + 1;
+    // The reference's checkpoint quirk (fmicommon.h:60-73, 88-89, 114-158; pinned against the reference's own FMindex/get_suffix and CLI in
+    // tests/test_oracle_vs_ref.py::test_bwtlen_multiple_of_65536):
+    // with bwtlen = m * 2^16, m >= 2, positions k >= bwtlen - 128 resolve to the first-level row that holds C[] instead of counts, so
+    // FMindex(c, k) comes out smaller by #c in BWT[0, bwtlen - 2^16).  Reproduced, not fixed: results must equal the reference's.
+    H.quirk_lo = quirk ? n - 128ull : ~0ull; memset(H.quirk_d, 0, sizeof H.quirk_d);      // quirk_d is filled once ranks exist
     // ---- taxonomy re-indexing
     std::unordered_map<uint64_t, uint64_t> par_of; par_of.reserve((size_t)t.n * 2 + 16);
     for (uint64_t i = 0; i < t.n; i++) par_of.emplace(t.node[i], t.parent[i]);          // emplace keeps the first (util.cpp:91)
@@ -272,10 +244,62 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
         }
     }
     // ---- sequence -> compact taxon; sampled SA -> compact taxon
-    H.seq_tax.resize((size_t)v.nseq);
-    for (int32_t i = 0; i < v.nseq; i++) H.seq_tax[(size_t)i] = v.seq_taxon[i] == UINT64_MAX ? KJ_TAX_BAD : index_of(v.seq_taxon[i]);
+    H.seq_tax.resize((size_t)v.nseq * copies);
+    for (int32_t i = 0; i < v.nseq; i++) { const uint32_t x = v.seq_taxon[i] == UINT64_MAX ? KJ_TAX_BAD : index_of(v.seq_taxon[i]); for (uint32_t c = 0; c < copies; c++) H.seq_tax[(size_t)i * copies + c] = x; }
     H.sa_exp = v.chpt_exp; H.sa_check = (1ull << v.chpt_exp) - 1ull;                         // suffixArray_set_masks (suffixArray.c:34-37)
-    H.sa_bias = ((int64_t)(v.nseq - 1) >> v.chpt_exp) + 1;                                   // bwt.c:115-116
+    H.sa_bias = ((int64_t)((int64_t)H.nseq - 1) >> v.chpt_exp) + 1;                          // bwt.c:115-116
+    // ---- ln(n!) exactly as the reference's literals (blast_seg.c:53-1306 are "%.6f" prints of lgamma)
+    H.lnfact.resize(10001);                                             // the reference's table lnfact[0..10000] (blast_seg.c:53-1306)
+    for (int i = 0; i < 10001; i++) { char b[64]; snprintf(b, sizeof b, "%.6f", lgamma((double)i + 1.0)); H.lnfact[(size_t)i] = strtod(b, nullptr); }
+    H.lnfact[0] = H.lnfact[1] = 0.0;
+    return KJ_OK;
+}
+
+int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHostIndex& H) {
+    uint8_t lcode[256];
+    int rc = kj_build_host_meta(v, t, 1, H, lcode); if (rc) return rc;
+    const int alen = v.alen; const uint64_t n = (uint64_t)v.bwtlen; const uint64_t nb = H.nb;
+    const bool quirk = H.quirk_lo != ~0ull;
+    // rank records + packed letters, chunked over threads
+    const uint32_t RB = kj_rank_rows(H.wide), RW = kj_rank_words(H.wide);
+    const uint64_t CH = 192ull * 2048;                                  // positions per chunk (multiple of 192, 64 and 12)
+    const uint64_t nch = (n + CH - 1) / CH;
+    std::vector<uint64_t> ccount((size_t)(nch + 1) * alen, 0);
+    unsigned nthr = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    auto par = [&](auto fn) {
+        std::vector<std::thread> th; for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] { for (uint64_t c = tI; c < nch; c += nthr) fn(c); });
+        for (auto& x : th) x.join();
+    };
+    par([&](uint64_t c) { uint64_t* cc = &ccount[(size_t)(c + 1) * alen]; uint64_t e = std::min(n, (c + 1) * CH); for (uint64_t k = c * CH; k < e; k++) cc[lcode[v.bwt[k]]]++; });
+    for (uint64_t c = 1; c <= nch; c++) for (int a = 0; a < alen; a++) ccount[(size_t)c * alen + a] += ccount[(size_t)(c - 1) * alen + a];
+    const uint64_t* total = &ccount[(size_t)nch * alen];
+    H.C[0] = 0; for (int a = 0; a < alen; a++) H.C[a + 1] = H.C[a] + total[a];
+    if (H.C[alen] != n) { kj_err() = "letter counts do not add up"; return KJ_ERR_IO; }
+    try { H.rank.assign((size_t)alen * nb * RW, 0ull); H.letters.assign((size_t)(n / KJ_LETTERS_PER_WORD + 2), 0); }
+    catch (...) { kj_err() = "out of host memory building the rank table"; return KJ_ERR_NOMEM; }
+    par([&](uint64_t c) {
+        uint64_t run[KJ_MAX_ALEN]; for (int a = 0; a < alen; a++) run[a] = H.C[a] + ccount[(size_t)c * alen + a];
+        uint64_t e = std::min(n, (c + 1) * CH);
+        for (uint64_t b0 = c * CH; b0 < e; b0 += RB) {
+            uint64_t b = b0 / RB, be = std::min(n, b0 + RB);
+            for (int a = 0; a < alen; a++) H.rank[((size_t)a * nb + b) * RW] = run[a];
+            for (uint64_t k = b0; k < be; k++) {
+                uint32_t a = lcode[v.bwt[k]], r = (uint32_t)(k - b0);
+                H.rank[((size_t)a * nb + b) * RW + 1u + (r >> 6)] |= 1ull << (r & 63);
+                run[a]++;
+            }
+        }
+        for (uint64_t k = c * CH; k < e; k++) H.letters[k / KJ_LETTERS_PER_WORD] |= (uint64_t)lcode[v.bwt[k]] << (5 * (k % KJ_LETTERS_PER_WORD));
+    });
+    // the record after the last letter (k == bwtlen lands there when bwtlen % RB == 0; otherwise the last partial block already exists)
+    if (n % RB == 0) for (int a = 0; a < alen; a++) H.rank[((size_t)a * nb + (nb - 1)) * RW] = H.C[a] + total[a];
+    if (H.wide) {   // fold the in-block prefix popcounts into the header
+        std::vector<std::thread> th; const size_t tot = (size_t)alen * nb;
+        for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] { for (size_t i = tI; i < tot; i += nthr) { uint64_t* B = &H.rank[i * 4];
+            uint64_t p1 = (uint64_t)__builtin_popcountll(B[1]), p2 = p1 + (uint64_t)__builtin_popcountll(B[2]); B[0] = (B[0] & KJ_CNT_MASK) | (p1 << KJ_P1_SHIFT) | (p2 << KJ_P2_SHIFT); } });
+        for (auto& x : th) x.join();
+    }
+
     H.sa_tax.resize((size_t)v.ncheck);
     {
         std::vector<std::thread> th; const uint64_t nc = (uint64_t)v.ncheck; std::atomic<bool> bad(false);
@@ -291,20 +315,10 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
         for (auto& x : th) x.join();
         if (bad) { kj_err() = "corrupt suffix array (sequence number out of range)"; return KJ_ERR_IO; }
     }
-    // The reference's checkpoint quirk (fmicommon.h:60-73, 88-89, 114-158; pinned against the reference's own FMindex/get_suffix and CLI in
-    // tests/test_oracle_vs_ref.py::test_bwtlen_multiple_of_65536):
-    // with bwtlen = m * 2^16, m >= 2, positions k >= bwtlen - 128 resolve to the first-level row that holds C[] instead of counts, so
-    // FMindex(c, k) comes out smaller by #c in BWT[0, bwtlen - 2^16).  Reproduced, not fixed: results must equal the reference's.
-    H.quirk_lo = ~0ull; memset(H.quirk_d, 0, sizeof H.quirk_d);
     if (quirk) {
         for (int a = 0; a < alen; a++) H.quirk_d[a] = host_rank(H, (uint32_t)a, n - 65536ull) - H.C[a];
-        H.quirk_lo = n - 128ull;
     }
     { const char* ek = getenv("KJ_KMER_K"); kj_build_kmer_table(H, ek ? atoi(ek) : 5); }
-    // ---- ln(n!) exactly as the reference's literals (blast_seg.c:53-1306 are "%.6f" prints of lgamma)
-    H.lnfact.resize(10001);                                             // the reference's table lnfact[0..10000] (blast_seg.c:53-1306)
-    for (int i = 0; i < 10001; i++) { char b[64]; snprintf(b, sizeof b, "%.6f", lgamma((double)i + 1.0)); H.lnfact[(size_t)i] = strtod(b, nullptr); }
-    H.lnfact[0] = H.lnfact[1] = 0.0;
     return KJ_OK;
 }
 
@@ -408,6 +422,9 @@ uint64_t mix_bytes(uint64_t h, const void* p, size_t n) {
     uint64_t w = 0; if (i < n) memcpy(&w, b + i, n - i);
     h = (h ^ w ^ (uint64_t)n) * 0x9E3779B97F4A7C15ull; return (h << 29) | (h >> 35);
 }
+}  // namespace
+uint64_t kj_mix_bytes(uint64_t h, const void* p, size_t n) { return mix_bytes(h, p, n); }
+namespace {
 template <class T> uint64_t mix_vec(uint64_t h, const std::vector<T>& v) { return mix_bytes(h, v.data(), v.size() * sizeof(T)); }
 uint64_t index_checksum(const KjHostIndex& H) {
     uint64_t h = 0x6b616a755f623230ull;
@@ -452,5 +469,42 @@ int kj_host_index_read(const char* path, KjHostIndex& H) {
     char extra; const bool at_end = fread(&extra, 1, 1, f) == 0;
     fclose(f);
     if (!ok || !at_end || h.n_present > h.n_tax || index_checksum(H) != h.checksum) { kj_err() = std::string(path) + " is truncated or corrupt"; return KJ_ERR_IO; }
+    // internal consistency (a crafted file with a recomputed checksum must not lead to out-of-bounds reads on the device)
+    uint64_t nk = 1; for (int d = 0; d < H.kmer_k; d++) nk *= 20;
+    bool good = H.bwtlen > 0 && H.bwtlen < (1ull << 38) && h.n_letters >= H.bwtlen / KJ_LETTERS_PER_WORD + 1 && h.n_seq_tax == H.nseq && H.sa_exp >= 0 && H.sa_exp <= 30 &&
+                H.sa_check == (1ull << H.sa_exp) - 1ull && H.sa_bias == ((int64_t)((int64_t)H.nseq - 1) >> H.sa_exp) + 1 && H.kmer_k >= 0 && H.kmer_k <= 6 &&
+                (H.kmer_k == 0 ? (h.n_kmer == 0 && h.n_kmer32 == 0) : (H.wide ? (h.n_kmer == nk && h.n_kmer32 == 0) : (h.n_kmer32 == nk && h.n_kmer == 0))) &&
+                (H.wide || H.bwtlen < 0xffffff00ull) && H.C[0] == 0 && H.C[H.alen] == H.bwtlen &&
+                (H.bwtlen >> H.sa_exp) < (uint64_t)H.sa_bias + h.n_sa_tax + 1 && (H.quirk_lo == ~0ull || (H.wide && H.quirk_lo == H.bwtlen - 128ull));
+    for (int a = 0; good && a < H.alen; a++) good = H.C[a] <= H.C[a + 1];
+    if (good) {
+        const uint32_t nt = (uint32_t)h.n_tax; std::atomic<bool> bad(false);
+        unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency())); std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthr; t++) th.emplace_back([&, t] {
+            bool b = false;
+            for (size_t i = t; i < H.sa_tax.size(); i += nthr) b |= H.sa_tax[i] >= nt && H.sa_tax[i] != KJ_TAX_BAD;
+            for (size_t i = t; i < H.seq_tax.size(); i += nthr) b |= H.seq_tax[i] >= nt && H.seq_tax[i] != KJ_TAX_BAD;
+            for (size_t i = t; i < H.tax_parent.size(); i += nthr) b |= H.tax_parent[i] >= nt;
+            if (H.wide) { for (size_t i = t; i < H.kmer.size(); i += nthr) b |= H.kmer[i].hi > H.bwtlen || H.kmer[i].lo > H.kmer[i].hi; }
+            else for (size_t i = t; i < H.kmer32.size(); i += nthr) b |= H.kmer32[i].hi > H.bwtlen || H.kmer32[i].lo > H.kmer32[i].hi;
+            if (b) bad = true; });
+        for (auto& x : th) x.join();
+        good = !bad;
+    }
+    if (!good) { kj_err() = std::string(path) + " is internally inconsistent"; return KJ_ERR_IO; }
+    return KJ_OK;
+}
+
+// test hook (host only): the checksums kj_debug_index_checksums() reports for a context, computed from the host transcoder's arrays
+extern "C" int kj_debug_host_index_checksums(const kj_index_view* index, const kj_taxonomy_view* taxonomy, uint64_t out[8]) {
+    if (!index || !taxonomy || !out) return KJ_ERR_ARG;
+    KjHostIndex H; int rc = kj_build_host_index(*index, *taxonomy, H); if (rc) return rc;
+    memset(out, 0, 64);
+    out[0] = kj_mix_bytes(0x6b616a75ull + 0, H.rank.data(), H.rank.size() * 8);
+    out[1] = kj_mix_bytes(0x6b616a75ull + 1, H.letters.data(), H.letters.size() * 8);
+    out[2] = kj_mix_bytes(0x6b616a75ull + 2, H.sa_tax.data(), H.sa_tax.size() * 4);
+    out[3] = kj_mix_bytes(0x6b616a75ull + 3, H.seq_tax.data(), H.seq_tax.size() * 4);
+    out[4] = H.wide ? kj_mix_bytes(0x6b616a75ull + 4, H.kmer.data(), H.kmer.size() * sizeof(KjKmer)) : kj_mix_bytes(0x6b616a75ull + 4, H.kmer32.data(), H.kmer32.size() * sizeof(KjKmer32));
+    out[5] = H.bwtlen; out[6] = (uint64_t)H.wide; out[7] = H.sa_tax.size();
     return KJ_OK;
 }

@@ -32,7 +32,10 @@ struct KjHostIndex {
 };
 
 std::string& kj_err();             // thread-local last error text
+uint64_t kj_mix_bytes(uint64_t h, const void* p, size_t n);   // order-sensitive 64-bit checksum (index files, test hooks)
 int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHostIndex& out);
+// the small / BWT-independent part only (the large arrays are then built on the device, kj_build.h); lcode = byte code -> letter
+int kj_build_host_meta(const kj_index_view& v, const kj_taxonomy_view& t, uint32_t copies, KjHostIndex& out, uint8_t lcode[256]);
 // SA intervals of all 20^k k-mers over the 20 residue letters (exactness-preserving shortcut for the first k LF steps)
 void kj_build_kmer_table(KjHostIndex& H, int k);
 // device-native index file: the transcoded arrays as they are uploaded, so that loading is one sequential read

@@ -484,6 +484,11 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
             if (paired && S.side[1].n_rec > n) fprintf(stderr, "Warning: File %s has more reads then file %s\n", fn[1].c_str(), fn[0].c_str());        // kaiju.cpp:400-404
             break;
         }
+        // file 1 is exhausted (end of file, nothing carried over): the reference's loop ends here, whatever file 2 still holds (kaiju.cpp:288, 396-404)
+        if (paired && S.side[0].eof && S.side[0].nbytes == 0) {
+            if (S.side[1].nbytes > 0 || !S.side[1].eof) fprintf(stderr, "Warning: File %s has more reads then file %s\n", fn[1].c_str(), fn[0].c_str());
+            break;
+        }
     }
     CK(cudaMemcpyAsync(&n_class, d_nclass, 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
     if (n_reads_out) *n_reads_out = n_reads; if (n_class_out) *n_class_out = n_class;

@@ -27,7 +27,7 @@ taxon indices (uint32) per step on a side stream, overlapped with the next step;
 """
 import argparse, json, os, subprocess, sys, tempfile, threading, time
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np
