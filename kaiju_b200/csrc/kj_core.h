@@ -21,11 +21,14 @@
 // per-warp shared-memory carve-up
 // ---------------------------------------------------------------------------------------------
 #define KJ_SEG_CAP(max_frag) ((max_frag) / 4u + 8u)
+#ifndef KJ_CLAIM
+#define KJ_CLAIM 4               // read items claimed per atomic by a warp
+#endif
 struct KjKept { uint64_t lo; uint32_t len; uint32_t aux; };     // one suffix interval (an SI of bwt.h:25-34)
 
 struct KjSmemLayout {
     uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, qord_off, aa_off, aa_stride, frag_off, hflag_off,
-             segcnt_off, seghist_off, segs_off, total;
+             segcnt_off, seghist_off, segs_off, stage_off, stage_stride, mbar_off, total;
 #if defined(KJ_EMU)
     uint32_t guard[16], nguard;         // emulator only: 64-byte red zones between the sub-arrays, checked after every read item
 #endif
@@ -67,6 +70,9 @@ static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
     }
     o = u + (seg_bytes > g_bytes ? seg_bytes : g_bytes);
     KJ_GUARD(L, o)
+    // staging area of the claimed reads' bases (cp.async.bulk target: 16-byte aligned) + the warp's mbarrier
+    L.stage_off = L.stage_stride = L.mbar_off = 0;
+    if (p.stage) { o = kj_align(o, 16); L.mbar_off = o; o += 16u; L.stage_off = o; L.stage_stride = kj_align(KJ_CLAIM * p.max_len + 32u, 16); o += 2u * L.stage_stride; }
     L.total = kj_align(o, 16);
     return L;
 }

@@ -31,11 +31,30 @@
 #endif
 #define KJ_CHUNK_READS (1u << 20)
 #define KJ_CHUNK_BYTES (1ull << 28)  // and at most this many bases of one mate per chunk (long reads)
-#define KJ_CLAIM 4               // read items claimed per atomic by a warp
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { kj_err() = std::string(#call) + ": " + cudaGetErrorString(e_); return KJ_ERR_CUDA; } } while (0)
 
 struct KjCtaShared { KjDevIndex ix; KjTables tb; };
+
+// ---- bulk copy (the Blackwell/Hopper copy engine, "TMA" in its 1-D form) of a warp's claimed reads into shared memory: one elected lane
+// arms the warp's mbarrier with the byte count and issues cp.async.bulk; the 32 lanes wait on the barrier's phase.  The translation
+// passes then read the bases from shared memory instead of waiting on global loads pass by pass.
+static __device__ __forceinline__ uint32_t kj_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ void kj_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(kj_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+static __device__ __forceinline__ void kj_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(kj_smem_u32(bar)), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void kj_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(kj_smem_u32(dst)), "l"(src), "r"(bytes), "r"(kj_smem_u32(bar)) : "memory");
+}
+static __device__ __forceinline__ void kj_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n .reg .pred p;\n KJ_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra KJ_DONE;\n bra KJ_WAIT;\n KJ_DONE:\n}"
+                 :: "r"(kj_smem_u32(bar)), "r"(parity) : "memory");
+}
 
 // GWS = false: the per-warp work space is carved out of shared memory (the compiler keeps every access in the shared
 // address space); GWS = true (reads too long for that): the same carve-up in a global buffer, generic loads and stores.
@@ -72,7 +91,11 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
     cx.gscratch = gscratch + gwarp * gscratch_bytes;
     cx.err = err;
     const bool paired = seq2 != nullptr;
+    const bool stage = !GWS && rp.stage != 0;
+    uint64_t* mbar = (uint64_t*)(cx.smem + cx.L.mbar_off); uint8_t* stg = cx.smem + cx.L.stage_off; uint32_t phase = 0;
+    if (stage) { if (cx.w.lane == 0) kj_mbar_init(mbar, 1); cx.w.sync(); }
     // work distribution: a warp claims KJ_CLAIM consecutive items per atomic and fetches their offsets with one coalesced load
+    KJ_ROLLED
     for (;;) {
         unsigned long long r0 = 0;
         if (cx.w.lane == 0) r0 = atomicAdd(counter, (unsigned long long)KJ_CLAIM);
@@ -81,13 +104,30 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
         const unsigned long long ri = r0 + (unsigned long long)cx.w.lane;
         uint64_t o1 = 0, o2 = 0;
         if (cx.w.lane <= KJ_CLAIM && ri <= n_reads) { o1 = off1[ri] - base1; if (paired) o2 = off2[ri] - base2; }
+        uint32_t al1 = 0, al2 = 0; uint64_t f1 = 0, f2 = 0;
+        if (stage) {
+            // the claimed reads are contiguous in the packed arrays: one bulk copy per mate, source and size rounded to 16 bytes
+            const int nk = (int)(n_reads - r0 < (unsigned long long)KJ_CLAIM ? n_reads - r0 : (unsigned long long)KJ_CLAIM);
+            f1 = cx.w.shfl64(o1, 0); f2 = cx.w.shfl64(o2, 0);
+            const uint64_t l1 = cx.w.shfl64(o1, nk), l2 = cx.w.shfl64(o2, nk);
+            al1 = (uint32_t)((uintptr_t)(seq1 + f1) & 15u); al2 = paired ? (uint32_t)((uintptr_t)(seq2 + f2) & 15u) : 0u;
+            const uint32_t b1 = (al1 + (uint32_t)(l1 - f1) + 15u) & ~15u, b2 = paired ? (al2 + (uint32_t)(l2 - f2) + 15u) & ~15u : 0u;
+            if (cx.w.lane == 0) {
+                kj_mbar_expect_tx(mbar, b1 + b2);
+                if (b1) kj_bulk_g2s(stg, seq1 + f1 - al1, b1, mbar);
+                if (b2) kj_bulk_g2s(stg + cx.L.stage_stride, seq2 + f2 - al2, b2, mbar);
+            }
+            kj_mbar_wait(mbar, phase); phase ^= 1u;
+        }
         KJ_ROLLED
         for (int k = 0; k < KJ_CLAIM; k++) {
             const unsigned long long r = r0 + (unsigned long long)k;
             if (r >= n_reads) break;
             const uint64_t a0 = cx.w.shfl64(o1, k), a1 = cx.w.shfl64(o1, k + 1), b0 = cx.w.shfl64(o2, k), b1 = cx.w.shfl64(o2, k + 1);
+            const uint8_t* p1 = stage ? stg + al1 + (uint32_t)(a0 - f1) : seq1 + a0;
+            const uint8_t* p2 = !paired ? nullptr : stage ? stg + cx.L.stage_stride + al2 + (uint32_t)(b0 - f2) : seq2 + b0;
             uint32_t best = 0;
-            uint32_t t = kj_classify_item<MODE, IdxT>(cx, seq1 + a0, (int)(a1 - a0), paired ? seq2 + b0 : nullptr, (int)(b1 - b0), paired, best);
+            uint32_t t = kj_classify_item<MODE, IdxT>(cx, p1, (int)(a1 - a0), p2, (int)(b1 - b0), paired, best);
             const uint64_t id = t == KJ_TAX_BAD ? 0ull : sh->ix.tax_id[t];
             if (cx.w.lane == 0) {
                 if (taxon_out) taxon_out[r] = id;
@@ -175,13 +215,14 @@ template <class T> static int upload(const std::vector<T>& v, void** d, uint64_t
 // Measured (MEM, kernel-only, M pairs/s, shared vs global): PE150 57.8 vs 45.8, PE250 29.4 (3 CTAs/SM) vs 28.2, PE350 14.3 (2 CTAs/SM) vs 18.3.
 #define KJ_SMEM_WS_LIMIT (75u * 1024u)
 static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid) {
+    rp.stage = getenv("KJ_NO_STAGE") ? 0u : 1u;            // developer hook: A/B of the bulk-copy staging of the bases
     KjSmemLayout L = kj_smem_layout(rp);
     const size_t head = kj_align((uint32_t)sizeof(KjCtaShared), 16);
     smem = head + (size_t)KJ_WARPS_PER_CTA * L.total;
     size_t limit = KJ_SMEM_WS_LIMIT;
     if (const char* v = getenv("KJ_WS_LIMIT_KB")) { long x = atol(v); if (x >= 0 && x <= 227) limit = (size_t)x * 1024u; }    // tuning hook (A/B of the switch point)
     rp.ws_global = smem > limit ? 1u : 0u;
-    if (rp.ws_global) smem = head;
+    if (rp.ws_global) { smem = head; rp.stage = 0; }
     const int cfg = rp.mode * 2 + (int)rp.ws_global;
     // The max-dynamic-shared-memory attribute belongs to the kernel instantiation on the device, not to a context: several contexts
     // (or batches with different read lengths) share it, so it is only ever raised (process-wide table), never lowered.

@@ -87,4 +87,5 @@ struct KjRunParams {
     uint32_t scratch_entries;       // global spill entries per warp
     uint32_t variant_cap;           // Greedy: entries of the per-warp substituted-variant ring
     uint32_t ws_global;             // 1: the per-warp work space lives in global memory (reads too long for shared memory)
+    uint32_t stage;                 // 1: the bases of the reads a warp has claimed are brought into shared memory with one bulk copy per mate (kj_device.cu)
 };
