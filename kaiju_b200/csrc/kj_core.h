@@ -805,7 +805,11 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
         for (;;) {
             if (jstart >= 0) {                                                              // phase A of the block whose top end position is jstart
                 KjChain<IdxT> t; t.lo = 0; t.hi = 0; t.i = 0; t.st = KJ_ST_EXACT;
+#ifdef KJ_NO_PROBE
+                if (jstart - w.lane >= (int)L - 1 || (start_la && jstart - w.lane >= 0)) kj_chain_start<IdxT>(ix, frag, jstart - w.lane, rp.m, t);
+#else
                 if (jstart - w.lane >= 0) kj_chain_start<IdxT>(ix, frag, jstart - w.lane, rp.m, t);
+#endif
                 w.sync();
                 if (start_la) { nxt = t; have_nxt = true; } else { cur = t; round = 0; }
                 jstart = -1;
@@ -813,7 +817,11 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
                 if (w.lane == 0) { if (start_la) kj_emu_stats.lookaheads++; else kj_emu_stats.blocks++; }
 #endif
             }
+#ifdef KJ_NO_PROBE
+            const int j = jhi - w.lane; const bool act = j >= (int)L - 1; const bool probe = act;
+#else
             const int j = jhi - w.lane; const bool probe = j >= 0; const bool act = j >= (int)L - 1;
+#endif
             // `if (i<=1) break` (bwt.c:376): lanes below the first finished lane with i<=1 were never run by the reference
             const uint32_t brk = w.ballot(act && cur.st == KJ_ST_EXACT && cur.i <= 1);
             const int cut = brk ? kj_ffs(brk) - 1 : 31;

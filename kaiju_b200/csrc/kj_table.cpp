@@ -1,83 +1,109 @@
-// kj_table.cpp -- kaiju2table's summary report (src/kaiju2table.cpp:150-365) written from per-taxon read counts
+// kj_table.cpp -- kaiju2table's summary report (the observable contract of src/kaiju2table.cpp:150-365) written from per-taxon read counts
 // (the vector a context accumulates in HBM, kj_counts_get) instead of re-reading the per-read output file.
-// Host code: the count vector is tiny; what is replaced is the reference's pass over every output line.
-// Own implementation of the observable rules:
-//   * nodes.dmp with ranks / names.dmp ("scientific name" lines) parsed with the reference's tolerant rules (util.cpp:123-178);
-//   * reads of taxa missing from nodes.dmp are warned about and only count towards the total (kaiju2table.cpp:197-200);
-//   * counts are rolled up to all ancestors except below Viruses (taxon 10239), which are listed on their own (218-229);
-//   * rows = taxa of the requested rank, by descending count (ties: ascending taxon id), filtered by -m / -c; then the
-//     Viruses / "cannot be assigned" / threshold / unclassified rows, with the reference's float arithmetic for the percentages.
+//
+// Own design: the taxonomy is loaded into DENSE arrays (ids sorted, parent / rank / name by index), nodes are ordered by depth, and the
+// report follows from two sweeps over that order -- top-down: "lies below Viruses (taxon 10239)"; bottom-up: reads of a taxon plus the
+// reads of its non-viral descendants (the reference's per-hit ancestor walk, summed the other way round).  What has to match the
+// reference byte for byte is the output: the row set, the order (descending reads, ties by ascending id), the float expressions of the
+// percentages and the printf formats; tests/test_table.py pins that against the unmodified tool.
+// Observable rules kept: nodes.dmp / names.dmp are parsed with the reference's tolerant rules (util.cpp:123-178); reads of taxa missing
+// from nodes.dmp only count towards the total (with a warning); viral taxa are listed on their own, never rolled up; the root never gets
+// a row; -m / -c thresholds, -u, -e, -p / -l as in the tool.
+#include <algorithm>
 #include <cinttypes>
 #include <cstdio>
 #include <cstring>
-#include <deque>
 #include <fstream>
-#include <list>
-#include <map>
-#include <set>
 #include <string>
-#include <unordered_map>
+#include <set>
 #include <vector>
 #include "kj_host.h"
 
 namespace {
 const uint64_t kViruses = 10239;
-typedef std::unordered_map<uint64_t, uint64_t> NodeMap;
 
-bool parse_uint(const std::string& s, size_t b, size_t e, uint64_t& v) {
+bool digits(const std::string& s, size_t b, size_t e, uint64_t& v) {
     if (b == std::string::npos || b >= s.size()) return false;
     if (e == std::string::npos) e = s.size();
     if (e <= b) return false;
     v = 0; for (size_t i = b; i < e; i++) { if (s[i] < '0' || s[i] > '9') return false; v = v * 10 + (uint64_t)(s[i] - '0'); }
     return true;
 }
-int load_nodes(const char* path, NodeMap& nodes, std::unordered_map<uint64_t, std::string>& rank) {
-    std::ifstream f(path); if (!f.is_open()) { kj_err() = std::string("Could not open file ") + path; return KJ_ERR_IO; }
-    std::string line;
-    while (std::getline(f, line)) {
-        if (line.empty()) continue;
-        size_t end = line.find_first_not_of("0123456789"); uint64_t node, parent;
-        if (!parse_uint(line, 0, end, node)) continue;
-        size_t start = line.find_first_of("0123456789", end); if (start == std::string::npos) continue;
-        end = line.find_first_not_of("0123456789", start + 1);
-        if (!parse_uint(line, start, end, parent)) continue;
-        start = line.find_first_of("abcdefghijklmnopqrstuvwxyz", end);
-        if (start == std::string::npos) continue;                  // the reference's substr() throws here and the line is dropped
-        size_t e2 = line.find_first_not_of("abcdefghijklmnopqrstuvwxyz ", start);
-        nodes.emplace(node, parent); rank.emplace(node, line.substr(start, e2 == std::string::npos ? std::string::npos : e2 - start));
+struct Taxonomy {
+    std::vector<uint64_t> id;            // ascending
+    std::vector<int32_t> parent;         // index of the parent; own index for a self-parent root; -1 if the parent is not in nodes.dmp
+    std::vector<std::string> rank, name; std::vector<uint8_t> has_name;
+    std::vector<uint32_t> order;         // indices by increasing depth (parents before children)
+    std::vector<uint8_t> viral;          // at or below Viruses
+    int find(uint64_t x) const { auto it = std::lower_bound(id.begin(), id.end(), x); return (it != id.end() && *it == x) ? (int)(it - id.begin()) : -1; }
+};
+int load_taxonomy(const char* nodes_path, const char* names_path, Taxonomy& T) {
+    struct Row { uint64_t id, parent; std::string rank; };
+    std::vector<Row> rows;
+    {
+        std::ifstream f(nodes_path); if (!f.is_open()) { kj_err() = std::string("Could not open file ") + nodes_path; return KJ_ERR_IO; }
+        std::string line;
+        while (std::getline(f, line)) {
+            if (line.empty()) continue;
+            size_t end = line.find_first_not_of("0123456789"); uint64_t node, par;
+            if (!digits(line, 0, end, node)) continue;
+            size_t start = line.find_first_of("0123456789", end); if (start == std::string::npos) continue;
+            end = line.find_first_not_of("0123456789", start + 1);
+            if (!digits(line, start, end, par)) continue;
+            start = line.find_first_of("abcdefghijklmnopqrstuvwxyz", end);
+            if (start == std::string::npos) continue;              // a line without a rank is dropped by the reference as well
+            size_t e2 = line.find_first_not_of("abcdefghijklmnopqrstuvwxyz ", start);
+            rows.push_back({node, par, line.substr(start, e2 == std::string::npos ? std::string::npos : e2 - start)});
+        }
     }
+    // first occurrence of an id wins (the reference's emplace): stable sort, then unique
+    std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.id < b.id; });
+    rows.erase(std::unique(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.id == b.id; }), rows.end());
+    const size_t n = rows.size();
+    T.id.resize(n); T.parent.resize(n); T.rank.resize(n); T.name.assign(n, std::string()); T.has_name.assign(n, 0);
+    for (size_t i = 0; i < n; i++) { T.id[i] = rows[i].id; T.rank[i].swap(rows[i].rank); }
+    for (size_t i = 0; i < n; i++) T.parent[i] = T.find(rows[i].parent);
+    {
+        std::ifstream f(names_path); if (!f.is_open()) { kj_err() = std::string("Could not open file ") + names_path; return KJ_ERR_IO; }
+        std::string line;
+        while (std::getline(f, line)) {
+            if (line.empty() || line.find("scientific name") == std::string::npos) continue;
+            size_t start = line.find_first_of("0123456789"); if (start == std::string::npos) continue;
+            size_t end = line.find_first_not_of("0123456789", start); uint64_t x;
+            if (!digits(line, start, end, x)) continue;
+            start = line.find_first_not_of("\t|", end); if (start == std::string::npos) continue;
+            end = line.find_first_of("\t|", start + 1);
+            const int i = T.find(x);
+            if (i >= 0 && !T.has_name[(size_t)i]) { T.name[(size_t)i] = line.substr(start, end == std::string::npos ? std::string::npos : end - start); T.has_name[(size_t)i] = 1; }
+        }
+    }
+    // depth by memoised climbing (a missing parent or a cycle ends the climb); order = counting sort by depth
+    std::vector<int32_t> depth(n, -1); std::vector<uint8_t> visiting(n, 0); std::vector<uint32_t> path;
+    for (size_t i = 0; i < n; i++) {
+        if (depth[i] >= 0) continue;
+        path.clear(); size_t cur = i; int32_t d = 0;
+        for (;;) {
+            if (depth[cur] >= 0) { d = depth[cur]; break; }
+            if (visiting[cur]) { d = 0; break; }
+            const int32_t p = T.parent[cur];
+            if (p < 0 || (size_t)p == cur) { depth[cur] = 0; d = 0; break; }
+            visiting[cur] = 1; path.push_back((uint32_t)cur); cur = (size_t)p;
+        }
+        for (size_t k = path.size(); k-- > 0;) depth[path[k]] = ++d;
+    }
+    int32_t maxd = 0; for (size_t i = 0; i < n; i++) maxd = std::max(maxd, depth[i]);
+    std::vector<uint32_t> start((size_t)maxd + 2, 0);
+    for (size_t i = 0; i < n; i++) start[(size_t)depth[i] + 1]++;
+    for (size_t d = 1; d < start.size(); d++) start[d] += start[d - 1];
+    T.order.resize(n); for (size_t i = 0; i < n; i++) T.order[start[(size_t)depth[i]]++] = (uint32_t)i;
+    T.viral.assign(n, 0);
+    for (uint32_t i : T.order) { const int32_t p = T.parent[i]; T.viral[i] = (T.id[i] == kViruses || (p >= 0 && p != (int32_t)i && T.viral[(size_t)p])) ? 1 : 0; }
     return KJ_OK;
 }
-int load_names(const char* path, std::unordered_map<uint64_t, std::string>& names) {
-    std::ifstream f(path); if (!f.is_open()) { kj_err() = std::string("Could not open file ") + path; return KJ_ERR_IO; }
-    std::string line;
-    while (std::getline(f, line)) {
-        if (line.empty() || line.find("scientific name") == std::string::npos) continue;
-        size_t start = line.find_first_of("0123456789"); if (start == std::string::npos) continue;
-        size_t end = line.find_first_not_of("0123456789", start); uint64_t id;
-        if (!parse_uint(line, start, end, id)) continue;
-        start = line.find_first_not_of("\t|", end); if (start == std::string::npos) continue;
-        end = line.find_first_of("\t|", start + 1);
-        names.emplace(id, line.substr(start, end == std::string::npos ? std::string::npos : end - start));
-    }
-    return KJ_OK;
-}
-// node1 is node2 or one of its ancestors (util.cpp:63-77); false (with the reference's message) if either is unknown
-// (the reference prints its "not found in taxonomy" message on every call; here it is said once per report)
-bool is_ancestor(const NodeMap& nodes, uint64_t node1, uint64_t node2, bool* warned) {
-    if (!nodes.count(node1) || !nodes.count(node2)) {
-        if (warned && !*warned) { fprintf(stderr, "Taxon ID %" PRIu64 " not found in taxonomy!\n", nodes.count(node1) ? node2 : node1); *warned = true; }
-        return false;
-    }
-    if (node1 == node2) return true;
-    for (auto it = nodes.find(node2); it != nodes.end() && it->second != node2; it = nodes.find(node2)) { node2 = it->second; if (node2 == node1) return true; }
-    return false;
-}
-std::string taxon_name(const std::unordered_map<uint64_t, std::string>& names, uint64_t id, const char* names_path) {
-    auto it = names.find(id);
-    if (it != names.end()) return it->second;
-    fprintf(stderr, "Warning: Taxon ID %" PRIu64 " is not found in file %s.\n", id, names_path);
-    return "taxonid:" + std::to_string(id);
+std::string display_name(const Taxonomy& T, uint32_t i, const char* names_path) {
+    if (T.has_name[i]) return T.name[i];
+    fprintf(stderr, "Warning: Taxon ID %" PRIu64 " is not found in file %s.\n", T.id[i], names_path);
+    return "taxonid:" + std::to_string(T.id[i]);
 }
 }  // namespace
 
@@ -94,74 +120,74 @@ extern "C" int kj_table_write(const uint64_t* taxon_ids, const uint64_t* counts,
     if (min_percent > 0.0f && min_read_count > 0) { kj_err() = "Either specify minimum percent with -m or minimum read count with -c."; return KJ_ERR_ARG; }
     const bool specified_ranks = o->rank_list && *o->rank_list;
     if (specified_ranks && o->full_path) { kj_err() = "Please use either option -p or -l, but not both of them."; return KJ_ERR_ARG; }
-    std::list<std::string> ranks_list; std::set<std::string> ranks_set;
+    std::vector<std::string> ranks_list; std::set<std::string> ranks_set;
     if (specified_ranks) {
         const std::string a = o->rank_list; size_t b = 0;
         while (b <= a.size()) { size_t e = a.find(',', b); if (e == std::string::npos) e = a.size(); if (e > b) { ranks_list.push_back(a.substr(b, e - b)); ranks_set.insert(a.substr(b, e - b)); } b = e + 1; }
         if (!ranks_set.count(rank)) { kj_err() = "Specified rank " + rank + " is not contained in rank list supplied with option -l"; return KJ_ERR_ARG; }
     }
-    NodeMap nodes; std::unordered_map<uint64_t, std::string> node2rank, node2name;
-    int rc = load_nodes(nodes_path, nodes, node2rank); if (rc) return rc;
-    rc = load_names(names_path, node2name); if (rc) return rc;
+    Taxonomy T;
+    int rc = load_taxonomy(nodes_path, names_path, T); if (rc) return rc;
+    const size_t nt = T.id.size();
+    if (T.find(kViruses) < 0) fprintf(stderr, "Taxon ID %" PRIu64 " not found in taxonomy!\n", kViruses);
 
-    // per-read pass of the reference (186-214), on counts
-    bool warned = false;
-    std::map<uint64_t, uint64_t> hits; uint64_t unclassified = 0, totalreads = 0, total_virus_reads = 0;
+    // reads per taxon index; reads of unknown taxa and unclassified reads only enter the totals
+    std::vector<uint64_t> direct(nt, 0); uint64_t unclassified = 0, totalreads = 0, total_virus_reads = 0;
     for (uint64_t i = 0; i < n; i++) {
-        const uint64_t id = taxon_ids[i], c = counts[i]; if (!c) continue;
+        const uint64_t c = counts[i]; if (!c) continue;
         totalreads += c;
-        if (id == 0) { unclassified += c; continue; }
-        if (!nodes.count(id)) { fprintf(stderr, "Warning: Taxon ID %" PRIu64 " is not contained in %s.\n", id, nodes_path); continue; }
-        if (is_ancestor(nodes, kViruses, id, &warned)) total_virus_reads += c;
-        hits[id] += c;
+        if (taxon_ids[i] == 0) { unclassified += c; continue; }
+        const int k = T.find(taxon_ids[i]);
+        if (k < 0) { fprintf(stderr, "Warning: Taxon ID %" PRIu64 " is not contained in %s.\n", taxon_ids[i], nodes_path); continue; }
+        direct[(size_t)k] += c;
+        if (T.viral[(size_t)k]) total_virus_reads += c;
     }
-    // ancestors get the reads of their descendants, except below Viruses (216-229)
-    std::map<uint64_t, uint64_t> summarized;
-    for (const auto& h : hits) {
-        uint64_t id = h.first; const uint64_t reads = h.second;
-        if (is_ancestor(nodes, kViruses, id, &warned)) { summarized[id] = reads; continue; }
-        for (auto it = nodes.find(id); it != nodes.end() && it->second != id; it = nodes.find(id)) { summarized[id] += reads; id = it->second; }
+    // bottom-up: a non-viral taxon holds its own reads and those of its descendants; viral taxa keep their own reads only
+    std::vector<uint64_t> reads(direct);
+    for (size_t k = nt; k-- > 0;) {
+        const uint32_t i = T.order[k]; const int32_t p = T.parent[i];
+        if (!T.viral[i] && reads[i] && p >= 0 && p != (int32_t)i) reads[(size_t)p] += reads[i];
     }
     if (o->filter_unclassified) totalreads -= unclassified;
-    uint64_t at_rank = 0, below_percent = 0, below_count = 0;
-    std::multimap<uint64_t, uint64_t, std::greater<uint64_t>> sorted;
-    for (const auto& s : summarized) {
-        const uint64_t id = s.first, count = s.second;
-        if (is_ancestor(nodes, kViruses, id, &warned)) { sorted.emplace(count, id); continue; }       // viruses are always listed
-        auto rk = node2rank.find(id);
-        if (rk == node2rank.end()) { fprintf(stderr, "Error: No rank specified for taxonid %" PRIu64 "\n", id); continue; }
-        if (rank == rk->second) {
-            if ((int)count >= min_read_count) {
-                const float percent = (float)count / (float)totalreads * 100;
-                if (percent >= min_percent) sorted.emplace(count, id); else below_percent += count;
-            } else below_count += count;
-            at_rank += count;
-        }
+    // rows: viral taxa with reads (always), taxa of the requested rank above the thresholds; a self-parent root never gets a row
+    struct RowOut { uint64_t count; uint32_t idx; };
+    std::vector<RowOut> out_rows; uint64_t at_rank = 0, below_percent = 0, below_count = 0;
+    for (uint32_t i = 0; i < nt; i++) {                       // ascending id: equal counts keep this order (stable sort below)
+        if (T.viral[i]) { if (direct[i]) out_rows.push_back({direct[i], i}); continue; }
+        if (!reads[i] || T.parent[i] == (int32_t)i || T.rank[i] != rank) continue;
+        const uint64_t count = reads[i];
+        if ((int)count >= min_read_count) {
+            const float percent = (float)count / (float)totalreads * 100;
+            if (percent >= min_percent) out_rows.push_back({count, i}); else below_percent += count;
+        } else below_count += count;
+        at_rank += count;
     }
+    std::stable_sort(out_rows.begin(), out_rows.end(), [](const RowOut& a, const RowOut& b) { return a.count > b.count; });
     uint64_t above = o->filter_unclassified ? totalreads - at_rank : totalreads - unclassified - at_rank;
     above -= total_virus_reads;
 
     FILE* f = fopen(out_path, append ? "a" : "w");
     if (!f) { kj_err() = std::string("Could not open file ") + out_path + " for writing"; return KJ_ERR_IO; }
     if (!append) fprintf(f, "file\tpercent\treads\ttaxon_id\ttaxon_name\n");
-    for (const auto& e : sorted) {
-        if (!o->expand_viruses && is_ancestor(nodes, kViruses, e.second, &warned)) continue;
-        const float percent = (float)e.first / (float)totalreads * 100.0f;
-        fprintf(f, "%s\t%.6f\t%" PRIu64 "\t%" PRIu64, label, percent, e.first, e.second);
+    std::vector<std::string> ranks_vec(ranks_list.begin(), ranks_list.end()), field;
+    for (const RowOut& e : out_rows) {
+        if (!o->expand_viruses && T.viral[e.idx]) continue;
+        const float percent = (float)e.count / (float)totalreads * 100.0f;
+        fprintf(f, "%s\t%.6f\t%" PRIu64 "\t%" PRIu64, label, percent, e.count, T.id[e.idx]);
         if (o->full_path || specified_ranks) {
-            uint64_t id = e.second; std::deque<std::string> lineage; std::map<std::string, std::string> cur;
-            if (specified_ranks) for (const auto& r : ranks_list) cur.emplace(r, "NA");
-            for (auto it = nodes.find(id); it != nodes.end() && it->second != id; it = nodes.find(id)) {
-                if (specified_ranks) {
-                    auto rk = node2rank.find(id);
-                    if (rk != node2rank.end() && rk->second != "no rank" && ranks_set.count(rk->second)) cur[rk->second] = taxon_name(node2name, id, names_path);
-                } else lineage.push_front(taxon_name(node2name, id, names_path));
-                id = it->second;
-            }
+            // the lineage from the taxon up to (not including) the root / a missing parent
+            std::vector<uint32_t> lin; for (int32_t i = (int32_t)e.idx; i >= 0 && T.parent[(size_t)i] != i && lin.size() <= nt; i = T.parent[(size_t)i]) lin.push_back((uint32_t)i);
             fprintf(f, "\t");
-            if (specified_ranks) for (const auto& r : ranks_list) fprintf(f, "%s;", cur[r].c_str());
-            else for (const auto& s : lineage) fprintf(f, "%s;", s.c_str());
-        } else fprintf(f, "\t%s", taxon_name(node2name, e.second, names_path).c_str());
+            if (specified_ranks) {
+                field.assign(ranks_vec.size(), "NA");
+                for (uint32_t i : lin) {                              // a rank occurring twice in a lineage: the node nearer to the root is reported
+                    if (T.rank[i] == "no rank" || !ranks_set.count(T.rank[i])) continue;
+                    const std::string nm = display_name(T, i, names_path);
+                    for (size_t r = 0; r < ranks_vec.size(); r++) if (ranks_vec[r] == T.rank[i]) field[r] = nm;
+                }
+                for (const auto& x : field) fprintf(f, "%s;", x.c_str());
+            } else for (size_t k = lin.size(); k-- > 0;) fprintf(f, "%s;", display_name(T, lin[k], names_path).c_str());
+        } else fprintf(f, "\t%s", display_name(T, e.idx, names_path).c_str());
         fprintf(f, "\n");
     }
     if (!o->expand_viruses) {
