@@ -5,7 +5,7 @@
 // libkaijub200.so.  The stock main() of kaiju.cpp then runs unchanged: it parses the command line, loads nodes.dmp and the .fmi
 // with parseNodesDmp / readFMI, starts `-z` ConsumerThreads and feeds them ReadItems; only what a ConsumerThread DOES with the
 // items changes -- it collects them into batches and hands the batches to kj_classify() / kj_classify_verbose()
-// (replaces ConsumerThread::doWork, ConsumerThread.cpp:630-749).  oracle/Makefile builds it as oracle/_ref/kaiju-gpu; the GPU test
+// (replaces ConsumerThread::doWork, ConsumerThread.cpp:630-749).  The test-infrastructure Makefile builds it as `kaiju-gpu` next to the reference binaries; the GPU test
 // tests/test_gpu_binding.py requires its output to equal the stock binary's.  No reference source is copied: the two member
 // functions kaiju.cpp references (constructor, doWork) are defined here, the search members of the class are simply not linked.
 #include "ConsumerThread.hpp"
