@@ -50,6 +50,9 @@ typedef struct {
     double min_evalue;            /* -E, default 0.01                                    */
     int32_t seg;                  /* -x (1, default) / -X (0)                            */
     int32_t input_is_protein;     /* -p: seq1 holds protein letters, seq2 must be NULL  */
+    int32_t name_mode;            /* 1: search as the kaijux / kaijup front-ends do (ConsumerThreadx.cpp:117-190): MEM keeps the matches of a
+                                     fragment in maxMatches order (bwt.c:225-296) instead of greedyExact order; Greedy is unchanged.
+                                     The caller passes an index view whose seq_taxon numbers the sequences. */
 } kj_params;
 
 /* Host views straight out of a .fmi loader (the reference's BWT/FMI/suffixArray structs:
@@ -83,6 +86,7 @@ typedef struct kj_ctx kj_ctx;           /* one GPU context: index + taxonomy in 
 int kj_fmi_load(const char *path, kj_fmi **out);
 void kj_fmi_view(const kj_fmi *f, kj_index_view *view);
 void kj_fmi_free(kj_fmi *f);
+const char *kj_fmi_seq_name(const kj_fmi *f, int32_t i);   /* suffixArray.ids[i]: the database name of sequence i (in the index's own order) */
 int kj_nodes_load(const char *path, kj_nodes **out);
 void kj_nodes_view(const kj_nodes *t, kj_taxonomy_view *view);
 void kj_nodes_free(kj_nodes *t);
@@ -136,6 +140,13 @@ int kj_classify2(kj_ctx *ctx, const char *seq1, const uint64_t *off1, const char
 int kj_classify_device2(kj_ctx *ctx, const char *d_seq1, const uint64_t *d_off1, const char *d_seq2, const uint64_t *d_off2,
                         uint64_t n_reads, uint32_t max_len1, uint32_t max_len2, uint64_t *d_taxon_out, uint32_t *d_best_out,
                         uint32_t *d_compact_out, void *cuda_stream);
+
+/* Several GPUs in ONE process (the counterpart of the reference's `-z N` consumer threads, kaiju.cpp:250-257): contexts created on different
+ * devices over the same index and parameters; the batch is cut into contiguous shards, one host thread drives each context, results land
+ * in the caller's arrays in input order.  Per-taxon counts stay per context (sum them, or all-reduce kj_counts_device_ptr()). */
+int kj_classify_multi(kj_ctx **ctxs, int n_ctx, const char *seq1, const uint64_t *off1, const char *seq2, const uint64_t *off2,
+                      uint64_t n_reads, uint64_t *taxon_out, uint32_t *best_out);
+int kj_device_count(void);                        /* number of usable CUDA devices (0 = none) */
 
 /* Whole files (replaces the reader loop of kaiju.cpp:288-394 and the output formatting of
  * ConsumerThread.cpp:724-739): FASTA or FASTQ, plain or gzip, in2 = second file of paired-end reads or NULL.  The text is

@@ -20,7 +20,7 @@ MEM, GREEDY = 0, 1
 class KjParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("min_fragment_length", C.c_uint32), ("mismatches", C.c_uint32),
                 ("min_score", C.c_uint32), ("seed_length", C.c_uint32), ("use_evalue", C.c_int32),
-                ("min_evalue", C.c_double), ("seg", C.c_int32), ("input_is_protein", C.c_int32)]
+                ("min_evalue", C.c_double), ("seg", C.c_int32), ("input_is_protein", C.c_int32), ("name_mode", C.c_int32)]
 
 
 class KjIndexView(C.Structure):
@@ -67,6 +67,8 @@ def lib():
             L.kj_index_build_ms.restype = C.c_double; L.kj_index_build_ms.argtypes = [C.c_void_p]
             L.kj_debug_index_checksums.argtypes = [C.c_void_p, C.c_void_p]
             L.kj_debug_host_index_checksums.argtypes = [C.POINTER(KjIndexView), C.POINTER(KjTaxonomyView), C.c_void_p]
+            L.kj_classify_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+            L.kj_device_count.restype = C.c_int
             L.kj_classify2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
             L.kj_classify_device2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -101,13 +103,13 @@ def _check(rc):
         raise KaijuError("kaiju_b200 error %d: %s" % (rc, lib().kj_last_error().decode()))
 
 
-def make_params(mode="mem", m=11, e=3, s=65, seed=7, E=0.01, seg=True, use_evalue=None, protein=False):
+def make_params(mode="mem", m=11, e=3, s=65, seed=7, E=0.01, seg=True, use_evalue=None, protein=False, name_mode=False):
     """Config fields as the kaiju CLI sets them (kaiju.cpp:74-202): -a -m -e -s -l -E -x/-X -p."""
     greedy = mode in ("greedy", GREEDY, 1)
     if use_evalue is None:
         use_evalue = greedy
     return KjParams(mode=1 if greedy else 0, min_fragment_length=m, mismatches=e, min_score=s, seed_length=seed,
-                    use_evalue=1 if (use_evalue and greedy) else 0, min_evalue=E, seg=1 if seg else 0, input_is_protein=1 if protein else 0)
+                    use_evalue=1 if (use_evalue and greedy) else 0, min_evalue=E, seg=1 if seg else 0, input_is_protein=1 if protein else 0, name_mode=1 if name_mode else 0)
 
 
 def _table_opts(rank, min_percent=0.0, min_read_count=0, expand_viruses=False, filter_unclassified=False, full_path=False, rank_list=None):
@@ -152,6 +154,25 @@ def write_native_index(fmi_path, nodes_path, out_path):
             L.kj_nodes_free(nodes)
     finally:
         L.kj_fmi_free(fmi)
+
+
+def device_count():
+    return int(lib().kj_device_count())
+
+
+def classify_multi(classifiers, seq1, off1, seq2=None, off2=None, want_best=True):
+    """One batch over several Classifiers (one per GPU, same index and parameters) in this process: contiguous shards, results in
+    input order (kj_classify_multi -- the counterpart of the reference's `-z N`)."""
+    n = len(off1) - 1
+    seq1 = np.ascontiguousarray(seq1, dtype=np.uint8); off1 = np.ascontiguousarray(off1, dtype=np.uint64)
+    p2 = o2 = None
+    if seq2 is not None:
+        seq2 = np.ascontiguousarray(seq2, dtype=np.uint8); off2 = np.ascontiguousarray(off2, dtype=np.uint64)
+        p2, o2 = seq2.ctypes.data, off2.ctypes.data
+    tax = np.zeros(n, dtype=np.uint64); best = np.zeros(n, dtype=np.uint32) if want_best else None
+    arr = (C.c_void_p * len(classifiers))(*[c._ctx for c in classifiers])
+    _check(lib().kj_classify_multi(arr, len(classifiers), seq1.ctypes.data, off1.ctypes.data, p2, o2, n, tax.ctypes.data, best.ctypes.data if want_best else None))
+    return (tax, best) if want_best else tax
 
 
 class Classifier:

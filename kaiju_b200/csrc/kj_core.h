@@ -633,28 +633,43 @@ KJ_NOINLINE uint32_t kj_seg_trim(const Warp w, uint8_t* scratch, const uint8_t* 
 // s_SegSeq (blast_seg.c:2027-2113) on frag[s0 .. s0+n).  LEVEL 0 collects regions; LEVEL 1 is the
 // "trigger window fell into the left trim" recursion, of which the caller keeps only the last region
 // created (the list head, 2093-2097), so deeper recursion levels can never influence the result.
+// Everything behind the window flags runs out of line (kj_seg_regions): a fragment with a low-complexity window is the exception, and
+// inlined copies of the region search cost instruction-cache space in the hot loop of every kernel.
+struct KjSegArgs { Warp w; const uint8_t* frag; const uint8_t* hf; KjSeg* segs; uint8_t* scratch; const double* lnf; int cap; uint32_t* err; };
 template <int LEVEL>
-static KJ_DEV int kj_seg_level(KjWarpCtx& cx, int s0, int n, KjSeg* segs, int nsegs) {
-    const uint8_t* frag = cx.smem + cx.L.frag_off; const uint8_t* hf = cx.smem + cx.L.hflag_off;
+static KJ_DEV int kj_seg_level(const KjSegArgs& A, int s0, int n, KjSeg* segs, int nsegs) {
+    const uint8_t* frag = A.frag; const uint8_t* hf = A.hf;
     if (KJ_SEG_WINDOW > n) return nsegs;
     const int first = KJ_SEG_DOWNSET, last = n - KJ_SEG_UPSET; int lowlim = first;
     KJ_ROLLED
     for (int i = first; i <= last; i++) {
         if (hf[s0 + i - KJ_SEG_DOWNSET] & 1) {
-            int j = i; while (j >= lowlim && (hf[s0 + j - KJ_SEG_DOWNSET] & 2)) j--; const int loi = j + 1;         // s_FindLow
-            j = i; while (j <= last && (hf[s0 + j - KJ_SEG_DOWNSET] & 2)) j++; const int hii = j - 1;               // s_FindHigh
+            int j = i;
+            KJ_ROLLED
+            while (j >= lowlim && (hf[s0 + j - KJ_SEG_DOWNSET] & 2)) j--;
+            const int loi = j + 1;         // s_FindLow
+            j = i;
+            KJ_ROLLED
+            while (j <= last && (hf[s0 + j - KJ_SEG_DOWNSET] & 2)) j++;
+            const int hii = j - 1;               // s_FindHigh
             int leftend = loi - KJ_SEG_DOWNSET, rightend = hii + KJ_SEG_UPSET - 1;
-            { const int n2 = rightend - leftend + 1; const uint32_t tr = kj_seg_trim(cx.w, cx.smem + cx.L.segcnt_off, frag + s0 + leftend, n2, cx.ix->lnfact);
+            { const int n2 = rightend - leftend + 1; const uint32_t tr = kj_seg_trim(A.w, A.scratch, frag + s0 + leftend, n2, A.lnf);
               leftend += (int)(tr >> 16); rightend -= n2 - (int)(tr & 0xffffu) - 1; }
             if (LEVEL == 0 && i + KJ_SEG_UPSET - 1 < leftend) {
                 const int lend = loi - KJ_SEG_DOWNSET, rend = leftend - 1;
                 KjSeg tmp; tmp.begin = -1; tmp.end = -1;
-                int got = kj_seg_level<1>(cx, s0 + lend, rend - lend + 1, &tmp, 0);
-                if (got > 0 && nsegs + 2 < (int)KJ_SEG_CAP(cx.rp->max_frag)) { if (cx.w.lane == 0) segs[nsegs] = tmp; nsegs++; }
+                int got = kj_seg_level<1>(A, s0 + lend, rend - lend + 1, &tmp, 0);
+                if (got > 0 && nsegs + 2 < A.cap) { if (A.w.lane == 0) segs[nsegs] = tmp; nsegs++; }
             }
             if (LEVEL == 0) {
-                if (nsegs + 2 < (int)KJ_SEG_CAP(cx.rp->max_frag)) { if (cx.w.lane == 0) { segs[nsegs].begin = leftend + s0; segs[nsegs].end = rightend + s0; } nsegs++; }
-                else if (cx.w.lane == 0) kj_flag_error(cx, 8u);
+                if (nsegs + 2 < A.cap) { if (A.w.lane == 0) { segs[nsegs].begin = leftend + s0; segs[nsegs].end = rightend + s0; } nsegs++; }
+                else if (A.w.lane == 0) {
+#if defined(KJ_EMU)
+                    *A.err |= 8u;
+#else
+                    atomicOr(A.err, 8u);
+#endif
+                }
             }
             else { segs[0].begin = leftend + s0; segs[0].end = rightend + s0; nsegs = 1; }      // LEVEL 1: register struct, keep the last
             i = hii < rightend + KJ_SEG_DOWNSET ? hii : rightend + KJ_SEG_DOWNSET;
@@ -663,38 +678,42 @@ static KJ_DEV int kj_seg_level(KjWarpCtx& cx, int s0, int n, KjSeg* segs, int ns
     }
     return nsegs;
 }
-// full SEG on frag[0..n): flags, regions, s_MergeSegs (2122-2152); returns number of regions (ascending)
-static KJ_DEV int kj_seg(KjWarpCtx& cx, int n) {
-    KjSeg* segs = (KjSeg*)(cx.smem + cx.L.segs_off);
-    if (n < KJ_SEG_WINDOW) return 0;
-    if (!kj_seg_flags(cx, n)) return 0;                      // no window at or below locut: s_SegSeq cannot trigger
-    int ns = kj_seg_level<0>(cx, 0, n, segs, 0);
-    cx.w.sync();
+// regions + s_MergeSegs (2122-2152) for a fragment whose window flags are set; returns the number of regions (ascending)
+KJ_NOINLINE int kj_seg_regions(const KjSegArgs A, int n) {
+    KjSeg* segs = A.segs;
+    int ns = kj_seg_level<0>(A, 0, n, segs, 0);
+    A.w.sync();
     if (ns > 1) {
         // creation order == ascending; the reference walks the reversed list from its head
-        if (cx.w.lane == 0) {
-            int cur = ns - 1, cnt = ns;
-            // emulate on an index-linked view: nxt[i] = i-1
-            // merged entries are marked begin = -1
-            int nx = cur - 1;
+        if (A.w.lane == 0) {
+            int cur = ns - 1, nx = cur - 1;                      // merged entries are marked begin = -1
             KJ_ROLLED
             while (nx >= 0) {
                 if (segs[cur].begin - segs[nx].end - 1 < 0) {
                     if (segs[cur].end < segs[nx].end) segs[cur].end = segs[nx].end;
                     if (segs[cur].begin > segs[nx].begin) segs[cur].begin = segs[nx].begin;
-                    segs[nx].begin = -1; cnt--;
+                    segs[nx].begin = -1;
                 } else cur = nx;
                 nx--;
             }
-            // compact
-            int o = 0; for (int t = 0; t < ns; t++) if (segs[t].begin >= 0) segs[o++] = segs[t];
+            int o = 0;
+            KJ_ROLLED
+            for (int t = 0; t < ns; t++) if (segs[t].begin >= 0) segs[o++] = segs[t];
             segs[ns].begin = o;                                  // pass the count through shared memory
         }
-        cx.w.sync();
+        A.w.sync();
         ns = segs[ns].begin;
-        cx.w.sync();
+        A.w.sync();
     }
     return ns;
+}
+// full SEG on frag[0..n): flags (inline, every fragment), regions (out of line, rare)
+static KJ_DEV int kj_seg(KjWarpCtx& cx, int n) {
+    if (n < KJ_SEG_WINDOW) return 0;
+    if (!kj_seg_flags(cx, n)) return 0;                      // no window at or below locut: s_SegSeq cannot trigger
+    KjSegArgs A; A.w = cx.w; A.frag = cx.smem + cx.L.frag_off; A.hf = cx.smem + cx.L.hflag_off; A.segs = (KjSeg*)(cx.smem + cx.L.segs_off);
+    A.scratch = cx.smem + cx.L.segcnt_off; A.lnf = cx.ix->lnfact; A.cap = (int)KJ_SEG_CAP(cx.rp->max_frag); A.err = cx.err;
+    return kj_seg_regions(A, n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -708,15 +727,18 @@ static KJ_DEV KjKept* kj_kept_ptr(KjWarpCtx& cx, uint32_t idx) {
 }
 
 // taxon ids of the kept intervals in order, k ascending, stop once the set exceeds 20 entries
-// (ids_from_SI, ConsumerThread.cpp:799-835); then LCA (util.cpp:194-263).  Returns compact taxon or KJ_TAX_BAD for "none".
+// (ids_from_SI, ConsumerThread.cpp:799-835); then LCA (util.cpp:194-263).  Runs once per read, out of line.
+// Returns compact taxon (KJ_TAX_BAD for "none") | number of ids << 32.
+struct KjIdsArgs { Warp w; const KjDevIndex* ix; const KjKept* kept_smem; const KjKept* spill; uint32_t kept_cap, spill_cap; uint32_t* ids; };
 template <class IdxT>
-static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
-    const Warp& w = cx.w; const KjDevIndex& ix = *cx.ix;
-    uint32_t* ids = (uint32_t*)(cx.smem + cx.L.ids_off);
+KJ_NOINLINE uint64_t kj_ids_and_lca_fn(const KjIdsArgs A, uint32_t nkept) {
+    const Warp& w = A.w; const KjDevIndex& ix = *A.ix;
+    uint32_t* ids = A.ids;
     uint32_t nids = 0;                                                    // uniform
     KJ_ROLLED
     for (uint32_t e = 0; e < nkept && nids <= 20; e++) {
-        KjKept kk = *kj_kept_ptr(cx, e);
+        const uint32_t se = e - A.kept_cap;
+        const KjKept kk = e < A.kept_cap ? A.kept_smem[e] : A.spill[se < A.spill_cap ? se : A.spill_cap - 1];
         KJ_ROLLED
         for (uint32_t base = 0; base < kk.len && nids <= 20; base += 32) {
             uint32_t t = base + (uint32_t)w.lane; bool act = t < kk.len;
@@ -731,16 +753,16 @@ static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
             }
         }
     }
-    cx.nids = nids;
-    if (nids == 0) return KJ_TAX_BAD;
+    const uint64_t hi = (uint64_t)nids << 32;
+    if (nids == 0) return hi | KJ_TAX_BAD;
     w.sync();
-    if (nids == 1) return ids[0];                                         // returned without a nodes.dmp check (ConsumerThread.cpp:625)
+    if (nids == 1) return hi | ids[0];                                    // returned without a nodes.dmp check (ConsumerThread.cpp:625)
     // lca_from_ids: drop ids absent from nodes.dmp (depth 0), lift to the shallowest depth, climb in lockstep
     uint32_t id = (uint32_t)w.lane < nids ? ids[w.lane] : KJ_TAX_BAD;
     uint32_t depth = id != KJ_TAX_BAD ? ix.tax_depth[id] : 0u;
     bool present = depth > 0;
     uint32_t pm = w.ballot(present);
-    if (!pm) return KJ_TAX_BAD;
+    if (!pm) return hi | KJ_TAX_BAD;
     uint32_t shallow = warp_min_u32(w, present ? depth : 0xffffffffu);
     if (present) for (uint32_t d = depth; d > shallow; d--) id = ix.tax_parent[id];
     int first = kj_ffs(pm) - 1;
@@ -748,10 +770,18 @@ static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
     for (uint32_t guard = 0; guard <= shallow + 1; guard++) {
         uint32_t f = w.shfl(id, first);
         bool diff = present && id != f;
-        if (!w.any(diff)) return f;
+        if (!w.any(diff)) return hi | f;
         if (present) id = ix.tax_parent[id];
     }
-    return KJ_TAX_BAD;
+    return hi | KJ_TAX_BAD;
+}
+template <class IdxT>
+static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
+    KjIdsArgs A; A.w = cx.w; A.ix = cx.ix; A.kept_smem = (const KjKept*)(cx.smem + cx.L.kept_off); A.spill = cx.spill;
+    A.kept_cap = cx.rp->kept_cap_smem; A.spill_cap = cx.rp->scratch_entries; A.ids = (uint32_t*)(cx.smem + cx.L.ids_off);
+    const uint64_t r = kj_ids_and_lca_fn<IdxT>(A, nkept);
+    cx.nids = (uint32_t)(r >> 32);
+    return (uint32_t)r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -805,7 +835,7 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
         for (;;) {
             if (jstart >= 0) {                                                              // phase A of the block whose top end position is jstart
                 KjChain<IdxT> t; t.lo = 0; t.hi = 0; t.i = 0; t.st = KJ_ST_EXACT;
-#ifdef KJ_NO_PROBE
+#ifndef KJ_PROBE
                 if (jstart - w.lane >= (int)L - 1 || (start_la && jstart - w.lane >= 0)) kj_chain_start<IdxT>(ix, frag, jstart - w.lane, rp.m, t);
 #else
                 if (jstart - w.lane >= 0) kj_chain_start<IdxT>(ix, frag, jstart - w.lane, rp.m, t);
@@ -817,7 +847,7 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
                 if (w.lane == 0) { if (start_la) kj_emu_stats.lookaheads++; else kj_emu_stats.blocks++; }
 #endif
             }
-#ifdef KJ_NO_PROBE
+#ifndef KJ_PROBE     // chains below the scan range as extra bounds: measured -9 % (their rank traffic costs more than the skipped chains save)
             const int j = jhi - w.lane; const bool act = j >= (int)L - 1; const bool probe = act;
 #else
             const int j = jhi - w.lane; const bool probe = j >= 0; const bool act = j >= (int)L - 1;
@@ -879,10 +909,13 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
         // something the fragment is replaced by its pieces exactly as in the reference and this search result is dropped
         if (item_cnt > 0 && rp.seg && !segchecked && kj_seg_gate(cx, q, arr, start, len, false)) return true;
         if (item_cnt > 0) {
-            // winners were appended j-descending; the reference's chain is newest (smallest j) first
+            // winners were appended j-descending; the reference's chain (greedyExact, bwt.c:347-380) is newest (smallest j) first.  The
+            // kaijux / kaijup front-ends search with maxMatches(..., 1) instead, whose list keeps the first-found match at the head and
+            // the others newest first behind it (insert_SI_sorted, bwt.c:225-252): there only the entries after the first are reversed.
+            const uint32_t keep = rp.name_mode ? 1u : 0u;
             KJ_ROLLED
-            for (uint32_t t = (uint32_t)w.lane; t < item_cnt / 2; t += 32) {
-                KjKept* a = kj_kept_ptr(cx, nkept + t); KjKept* b = kj_kept_ptr(cx, nkept + item_cnt - 1 - t);
+            for (uint32_t t = (uint32_t)w.lane; t < (item_cnt - keep) / 2; t += 32) {
+                KjKept* a = kj_kept_ptr(cx, nkept + keep + t); KjKept* b = kj_kept_ptr(cx, nkept + item_cnt - 1 - t);
                 KjKept x = *a; *a = *b; *b = x;
             }
             w.sync();

@@ -28,21 +28,22 @@ struct KjMatch { uint64_t lo; uint32_t len; uint16_t qi, ql; };    // one SI: in
 struct KjVQueue { uint64_t* gkey; KjVariant* v; uint32_t n, live;      // n: high-water mark, live: entries not yet popped (uniform)
     KJ_DEV uint64_t& key(uint32_t s) const { return gkey[s]; } };
 
-// compact live variants to the front (called when the ring is full)
-static KJ_DEV void kj_vq_compact(KjWarpCtx& cx, KjVQueue& vq) {
-    const Warp& w = cx.w; uint32_t out = 0;
+// compact live variants to the front (called when the ring is full); out of line: rare.  Returns the number of live entries.
+KJ_NOINLINE uint32_t kj_vq_compact_fn(const Warp w, uint64_t* gkey, KjVariant* v, uint32_t n) {
+    uint32_t out = 0;
     KJ_ROLLED
-    for (uint32_t b = 0; b < vq.n; b += 32) {
-        uint32_t s = b + (uint32_t)w.lane; bool live = s < vq.n && vq.key(s) != 0;
-        KjVariant tmp; uint64_t tk = 0; if (live) { tmp = vq.v[s]; tk = vq.key(s); }
+    for (uint32_t b = 0; b < n; b += 32) {
+        uint32_t s = b + (uint32_t)w.lane; bool live = s < n && gkey[s] != 0;
+        KjVariant tmp; uint64_t tk = 0; if (live) { tmp = v[s]; tk = gkey[s]; }
         uint32_t mask = w.ballot(live);
         w.sync();
-        if (live) { const uint32_t d = out + (uint32_t)kj_popc(mask & lanemask_lt(w.lane)); vq.v[d] = tmp; vq.key(d) = tk; }
+        if (live) { const uint32_t d = out + (uint32_t)kj_popc(mask & lanemask_lt(w.lane)); v[d] = tmp; gkey[d] = tk; }
         out += (uint32_t)kj_popc(mask);
         w.sync();
     }
-    vq.n = out; vq.live = out;
+    return out;
 }
+static KJ_DEV void kj_vq_compact(KjWarpCtx& cx, KjVQueue& vq) { vq.n = kj_vq_compact_fn(cx.w, vq.gkey, vq.v, vq.n); vq.live = vq.n; }
 
 // inclusive warp scan helper (uint32)
 static KJ_DEV uint32_t kj_scan_incl(const Warp& w, uint32_t v) {
@@ -158,12 +159,20 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
             for (;;) {                                                             // same skeleton as kj_mem_item: one phase-A site, one completion site
                 if (jstart >= 0) {
                     KjChain<IdxT> t; t.lo = 0; t.hi = 0; t.i = 0; t.st = KJ_ST_EXACT;
+#ifndef KJ_PROBE
+                    if (jstart - w.lane >= L - 1 || (start_la && jstart - w.lane >= 0)) kj_chain_start<IdxT>(ix, frag, jstart - w.lane, rp.seed_length, t);
+#else
                     if (jstart - w.lane >= 0) kj_chain_start<IdxT>(ix, frag, jstart - w.lane, rp.seed_length, t);
+#endif
                     w.sync();
                     if (start_la) { nxt = t; have_nxt = true; } else { cur = t; round = 0; }
                     jstart = -1;
                 }
+#ifndef KJ_PROBE
+                const int j = jhi - w.lane; const bool act = j >= L - 1; const bool probe = act;
+#else
                 const int j = jhi - w.lane; const bool probe = j >= 0; const bool act = j >= L - 1;
+#endif
                 const uint32_t brk = w.ballot(act && cur.st == KJ_ST_EXACT && cur.i <= 1);        // `if (i<=1) break` (bwt.c:292)
                 const int cut = brk ? kj_ffs(brk) - 1 : 31;
                 const bool open = act && cur.st == KJ_ST_OPEN && w.lane <= cut;

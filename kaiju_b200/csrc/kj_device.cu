@@ -27,7 +27,7 @@
 #define KJ_MIN_BLOCKS 4          // resident CTAs per SM the register allocation is tuned for (ncu: latency-bound, see profiles/)
 #endif
 #ifndef KJ_MIN_BLOCKS_GREEDY
-#define KJ_MIN_BLOCKS_GREEDY 4   // A/B: 8.30 vs 7.94 M pairs/s
+#define KJ_MIN_BLOCKS_GREEDY 5   // 48 registers, 40 warps per SM: Greedy waits on instruction fetch and local memory, more warps hide it (A/B round 2: +5 %; MEM: -8 %)
 #endif
 #define KJ_CHUNK_READS (1u << 20)
 #define KJ_CHUNK_BYTES (1ull << 28)  // and at most this many bases of one mate per chunk (long reads)
@@ -91,7 +91,11 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
     cx.gscratch = gscratch + gwarp * gscratch_bytes;
     cx.err = err;
     const bool paired = seq2 != nullptr;
+#ifdef KJ_STAGE
     const bool stage = !GWS && rp.stage != 0;
+#else
+    const bool stage = false;          // measured: -10 % (the larger shared-memory carve-out shrinks the L1 that serves the rank loads), see profiles/README.md
+#endif
     uint64_t* mbar = (uint64_t*)(cx.smem + cx.L.mbar_off); uint8_t* stg = cx.smem + cx.L.stage_off; uint32_t phase = 0;
     if (stage) { if (cx.w.lane == 0) kj_mbar_init(mbar, 1); cx.w.sync(); }
     // work distribution: a warp claims KJ_CLAIM consecutive items per atomic and fetches their offsets with one coalesced load
@@ -215,7 +219,11 @@ template <class T> static int upload(const std::vector<T>& v, void** d, uint64_t
 // Measured (MEM, kernel-only, M pairs/s, shared vs global): PE150 57.8 vs 45.8, PE250 29.4 (3 CTAs/SM) vs 28.2, PE350 14.3 (2 CTAs/SM) vs 18.3.
 #define KJ_SMEM_WS_LIMIT (75u * 1024u)
 static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid) {
-    rp.stage = getenv("KJ_NO_STAGE") ? 0u : 1u;            // developer hook: A/B of the bulk-copy staging of the bases
+#ifdef KJ_STAGE
+    rp.stage = getenv("KJ_NO_STAGE") ? 0u : 1u;            // build with -DKJ_STAGE: bulk-copy staging of the bases (A/B; not the default, see the kernel)
+#else
+    rp.stage = 0u;
+#endif
     KjSmemLayout L = kj_smem_layout(rp);
     const size_t head = kj_align((uint32_t)sizeof(KjCtaShared), 16);
     smem = head + (size_t)KJ_WARPS_PER_CTA * L.total;
@@ -290,7 +298,7 @@ static int upload_descriptor(kj_ctx* c) {
     D.n_sa = c->n_sa; D.nseq = H.nseq;
     D.tax_parent = (const uint32_t*)c->d_tax_parent; D.tax_depth = (const uint32_t*)c->d_tax_depth; D.tax_id = (const uint64_t*)c->d_tax_id; D.n_tax = (uint32_t)H.tax_id.size();
     D.lnfact = (const double*)c->d_lnfact; D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? c->d_kmer : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = c->d_tables;
-    D.quirk_lo = H.quirk_lo; D.mono = H.quirk_lo == ~0ull ? 1 : 0; D.quirk_d = c->d_quirk;
+    D.quirk_lo = H.quirk_lo; D.mono = (H.quirk_lo == ~0ull && !getenv("KJ_NOMONO")) ? 1 : 0; D.quirk_d = c->d_quirk;      // KJ_NOMONO: developer hook (A/B of the chain bounds)
     if (!c->d_ix) CK(cudaMalloc((void**)&c->d_ix, sizeof(KjDevIndex)));
     CK(cudaMemcpy(c->d_ix, &D, sizeof(KjDevIndex), cudaMemcpyHostToDevice));
     return KJ_OK;
@@ -599,6 +607,24 @@ extern "C" int kj_classify2(kj_ctx* c, const char* seq1, const uint64_t* off1, c
                             uint64_t* taxon_out, uint32_t* best_out, uint32_t* d_compact_out) {
     return classify_host_retry(c, seq1, off1, seq2, off2, n, taxon_out, best_out, nullptr, nullptr, d_compact_out);
 }
+// In-process multi-GPU (the drop-in counterpart of the reference's `-z N` consumer threads, kaiju.cpp:250-257): contiguous shards of the batch,
+// one host thread per context, results written straight into the caller's arrays.  No exchange between the GPUs: reads are independent.
+extern "C" int kj_classify_multi(kj_ctx** ctxs, int n_ctx, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
+                                 uint64_t* taxon_out, uint32_t* best_out) {
+    if (!ctxs || n_ctx < 1 || !seq1 || !off1 || !taxon_out || (seq2 && !off2)) { kj_err() = "kj_classify_multi: null argument"; return KJ_ERR_ARG; }
+    for (int i = 0; i < n_ctx; i++) if (!ctxs[i]) { kj_err() = "kj_classify_multi: null context"; return KJ_ERR_ARG; }
+    if (n_ctx == 1) return kj_classify(ctxs[0], seq1, off1, seq2, off2, n, taxon_out, best_out);
+    std::vector<int> rc((size_t)n_ctx, KJ_OK); std::vector<std::string> msg((size_t)n_ctx); std::vector<std::thread> th;
+    for (int i = 0; i < n_ctx; i++) th.emplace_back([&, i] {
+        const uint64_t lo = n * (uint64_t)i / (uint64_t)n_ctx, hi = n * (uint64_t)(i + 1) / (uint64_t)n_ctx;
+        if (hi > lo) rc[(size_t)i] = kj_classify(ctxs[i], seq1, off1 + lo, seq2, seq2 ? off2 + lo : nullptr, hi - lo, taxon_out + lo, best_out ? best_out + lo : nullptr);
+        if (rc[(size_t)i]) msg[(size_t)i] = kj_err();
+    });
+    for (auto& x : th) x.join();
+    for (int i = 0; i < n_ctx; i++) if (rc[(size_t)i]) { kj_err() = "device " + std::to_string(ctxs[i]->device) + ": " + msg[(size_t)i]; return rc[(size_t)i]; }
+    return KJ_OK;
+}
+extern "C" int kj_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 extern "C" int kj_classify_verbose(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
                                    uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out) {
     if (!ids_out || !nids_out) { kj_err() = "kj_classify_verbose: null argument"; return KJ_ERR_ARG; }

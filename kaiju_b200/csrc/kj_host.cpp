@@ -71,6 +71,7 @@ extern "C" void kj_fmi_view(const kj_fmi* f, kj_index_view* v) {
     v->sa = f->sa.data(); v->seq_taxon = f->seq_taxon.data();
 }
 extern "C" void kj_fmi_free(kj_fmi* f) { delete f; }
+extern "C" const char* kj_fmi_seq_name(const kj_fmi* f, int32_t i) { return (f && i >= 0 && i < f->nseq) ? f->ids[(size_t)i].c_str() : nullptr; }
 
 // nodes.dmp (parseNodesDmp, util.cpp:79-99): first integer = node, next integer = parent; bad lines skipped
 extern "C" int kj_nodes_load(const char* path, kj_nodes** out) {
@@ -387,7 +388,7 @@ int kj_build_evalue_breaks(const kj_params& p, double db_length, std::vector<dou
 void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp) {
     memset(&rp, 0, sizeof rp);
     rp.mode = p.mode; rp.m = p.min_fragment_length; rp.e = p.mismatches; rp.min_score = p.min_score; rp.seed_length = p.seed_length;
-    rp.use_evalue = p.use_evalue; rp.seg = p.seg; rp.protein = p.input_is_protein;
+    rp.use_evalue = p.use_evalue; rp.seg = p.seg; rp.protein = p.input_is_protein; rp.name_mode = p.name_mode ? 1 : 0;
     if (p.input_is_protein) max_len *= 3;  // a protein read is laid out like one reading frame: residue e at array index 3e
     if (max_len < 24) max_len = 24;
     rp.max_len = (max_len + 7) / 8 * 8;
@@ -395,9 +396,9 @@ void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp) {
     uint32_t per_class = (rp.max_frag + 1 + rp.m) / (rp.m + 1);
     rp.item_cap = 2 * 12 * per_class + 8; rp.item_cap = (rp.item_cap + 1) & ~1u;
 #ifndef KJ_KEPT_SMEM
-#define KJ_KEPT_SMEM 24
+#define KJ_KEPT_SMEM 20
 #endif
-    rp.kept_cap_smem = KJ_KEPT_SMEM;       // >= max_matches_SI (20): greedy keeps its best list here
+    rp.kept_cap_smem = KJ_KEPT_SMEM;       // = max_matches_SI (20): greedy keeps its best list here; 5 Greedy CTAs per SM fit with it
     rp.scratch_entries = 4 * rp.max_len + 64;
     rp.variant_cap = rp.max_len <= 160 ? 256u : rp.max_len <= 512 ? 1024u : 4096u;    // entries of the Greedy variant ring (it grows x4 and the call is repeated if a read fills it)
     if (const char* v = getenv("KJ_VARIANT_CAP")) { long x = atol(v); if (x >= 32 && x <= (1 << 20)) rp.variant_cap = (uint32_t)x; }   // test hook: provoke the overflow/retry path

@@ -270,9 +270,33 @@ static int kj_parse_consumed(KjParsed& P, uint64_t n, uint64_t headers_total_hin
 }
 
 struct KjChunk { char* p = nullptr; size_t n = 0; bool eof = false; std::string error; };
-struct KjFileReader {   // one thread per input file: gz (zlib) or plain (read(2)) -> pinned chunks
+struct KjFileReader {   // per input file: gz (zlib, one thread) or plain (a pool of pread() threads) -> pinned chunks
     gzFile fp = nullptr; int fd = -1; uint64_t file_off = 0; std::string path; size_t chunk; std::vector<char*> pool; std::deque<KjChunk> ready; std::deque<char*> free_;
     std::mutex mu; std::condition_variable cv; std::thread th; bool stop = false;
+    // plain files: NT worker threads copy 1 MB slices of the current chunk out of the page cache in parallel (one copy stream per thread;
+    // a single thread moves ~1-3 GB/s, the device pipeline wants > 20 GB/s)
+    static constexpr size_t SLICE = 1u << 20;
+    std::vector<std::thread> workers; std::mutex wmu; std::condition_variable wcv, wdone; char* wbuf = nullptr; size_t wnext = 0, wslices = 0, wleft = 0; uint64_t wgen = 0; bool wstop = false, werr = false;
+    std::vector<size_t> wgot;
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(wmu);
+            wcv.wait(lk, [&] { return wstop || (wgen != seen && wnext < wslices); });
+            if (wstop) return;
+            const uint64_t gen = wgen;
+            while (wgen == gen && wnext < wslices) {
+                const size_t sl = wnext++; char* b = wbuf; const uint64_t base = file_off;
+                lk.unlock();
+                const size_t o = sl * SLICE, want = std::min(SLICE, chunk - o); size_t g = 0; bool bad = false;
+                while (g < want) { const ssize_t r = ::pread(fd, b + o + g, want - g, (off_t)(base + o + g)); if (r < 0) { bad = true; break; } if (r == 0) break; g += (size_t)r; }
+                lk.lock();
+                wgot[sl] = g; if (bad) werr = true;
+                if (--wleft == 0) wdone.notify_all();
+            }
+            seen = gen;
+        }
+    }
     int open(const std::string& p, size_t chunk_bytes, int nbuf) {
         path = p; chunk = chunk_bytes;
         fd = ::open(p.c_str(), O_RDONLY);
@@ -282,7 +306,13 @@ struct KjFileReader {   // one thread per input file: gz (zlib) or plain (read(2
             ::close(fd); fd = -1; fp = gzopen(p.c_str(), "rb");
             if (!fp) { kj_err() = "Could not open file " + p; return KJ_ERR_IO; }
             gzbuffer(fp, 1 << 20);
-        } else posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+        } else {
+            posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+            unsigned nt = std::max(2u, std::min(16u, std::thread::hardware_concurrency() / 4u));
+            if (const char* v = getenv("KJ_IO_THREADS")) { const long x = atol(v); if (x >= 1 && x <= 64) nt = (unsigned)x; }      // tuning hook
+            wgot.assign((chunk + SLICE - 1) / SLICE, 0);
+            for (unsigned t = 0; t < nt; t++) workers.emplace_back([this] { worker(); });
+        }
         for (int i = 0; i < nbuf; i++) { char* b = nullptr; if (cudaMallocHost((void**)&b, chunk) != cudaSuccess) { kj_err() = "cudaMallocHost failed"; return KJ_ERR_NOMEM; } pool.push_back(b); free_.push_back(b); }
         th = std::thread([this] { run(); });
         return KJ_OK;
@@ -293,20 +323,20 @@ struct KjFileReader {   // one thread per input file: gz (zlib) or plain (read(2
             { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || !free_.empty(); }); if (stop) return; b = free_.front(); free_.pop_front(); }
             KjChunk ck; ck.p = b; size_t got = 0;
             if (fd >= 0) {
-                // plain file: four threads pread() a quarter of the chunk each (one page-cache copy stream per thread)
-                const int NT = 4; const size_t part = (chunk + NT - 1) / NT; ssize_t res[NT]; std::thread th4[NT];
-                for (int t = 0; t < NT; t++) th4[t] = std::thread([&, t] {
-                    const size_t o = (size_t)t * part, want = o < chunk ? std::min(part, chunk - o) : 0; size_t g = 0; res[t] = 0;
-                    while (g < want) { const ssize_t r = ::pread(fd, b + o + g, want - g, (off_t)(file_off + o + g)); if (r < 0) { res[t] = -1; return; } if (r == 0) break; g += (size_t)r; }
-                    res[t] = (ssize_t)g; });
-                for (int t = 0; t < NT; t++) th4[t].join();
-                for (int t = 0; t < NT; t++) {
-                    if (res[t] < 0) { ck.error = "read error in file " + path; break; }
-                    got += (size_t)res[t];
-                    const size_t o = (size_t)t * part, want = o < chunk ? std::min(part, chunk - o) : 0;
-                    if ((size_t)res[t] < want) { ck.eof = true; break; }          // short part = end of file (later parts read nothing)
+                const size_t ns = (chunk + SLICE - 1) / SLICE;
+                {
+                    std::unique_lock<std::mutex> lk(wmu);
+                    wbuf = b; wnext = 0; wslices = ns; wleft = ns; werr = false; wgen++;
+                    wcv.notify_all();
+                    wdone.wait(lk, [&] { return wleft == 0; });
+                    wslices = 0;
                 }
-                if (got == chunk && !ck.eof) { char probe; if (::pread(fd, &probe, 1, (off_t)(file_off + chunk)) == 0) ck.eof = true; }
+                if (werr) ck.error = "read error in file " + path;
+                else for (size_t sl = 0; sl < ns; sl++) {
+                    got += wgot[sl];
+                    if (wgot[sl] < std::min(SLICE, chunk - sl * SLICE)) { ck.eof = true; break; }          // short slice = end of file (later slices read nothing)
+                }
+                if (got == chunk && !ck.eof && ck.error.empty()) { char probe; if (::pread(fd, &probe, 1, (off_t)(file_off + chunk)) == 0) ck.eof = true; }
                 file_off += got;
             } else while (got < chunk) {
                 const ssize_t r = (ssize_t)gzread(fp, b + got, (unsigned)std::min<size_t>(chunk - got, 1u << 30));
@@ -326,6 +356,9 @@ struct KjFileReader {   // one thread per input file: gz (zlib) or plain (read(2
     void close() {
         { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_all();
         if (th.joinable()) th.join();
+        { std::lock_guard<std::mutex> lk(wmu); wstop = true; } wcv.notify_all();
+        for (auto& w : workers) if (w.joinable()) w.join();
+        workers.clear();
         if (fp) gzclose(fp); fp = nullptr;
         if (fd >= 0) ::close(fd); fd = -1;
         for (char* b : pool) cudaFreeHost(b); pool.clear();
@@ -388,7 +421,7 @@ static int kj_prefetch(kj_ctx* c, KjFilesState& S, int f) {
 }
 
 static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, const char* in2, const char* out_path, int verbose, uint64_t* n_reads_out, uint64_t* n_class_out) {
-    size_t chunk = 32u << 20;
+    size_t chunk = 64u << 20;
     if (const char* v = getenv("KJ_INGEST_CHUNK")) { long x = atol(v); if (x >= 256 && x <= (1l << 30)) chunk = (size_t)x; }       // test hook: many small chunks
     const bool paired = in2 && *in2; S.nfiles = paired ? 2 : 1;
     const std::string fn[2] = {in1, paired ? in2 : ""};

@@ -75,7 +75,7 @@ struct KjDevIndex {
 struct KjRunParams {
     int mode;                       // 0 MEM, 1 GREEDY
     uint32_t m, e, min_score, seed_length;
-    int use_evalue, seg, protein;
+    int use_evalue, seg, protein, name_mode;
     // E-value gate as an integer threshold: ev_breaks[k] = the largest query length (double) for which score k passes,
     // so the minimal passing score of a read is the number of breaks below its query length (kj_build_evalue_breaks)
     const double* ev_breaks; uint32_t n_ev_breaks;

@@ -9,6 +9,7 @@
 #include <thread>
 #include <vector>
 #include <atomic>
+#include <algorithm>
 #define KJ_EMU 1
 #include "../../kaiju_b200/csrc/kj_warp.h"
 
@@ -137,11 +138,19 @@ extern "C" {
 void* kjemu_create(const char* fmi_path, const char* nodes_path, const kj_params* p) {
     kj_fmi* f = nullptr; kj_nodes* t = nullptr;
     if (kj_fmi_load(fmi_path, &f) != KJ_OK) { fprintf(stderr, "kjemu: %s\n", kj_last_error()); return nullptr; }
-    if (kj_nodes_load(nodes_path, &t) != KJ_OK) { fprintf(stderr, "kjemu: %s\n", kj_last_error()); return nullptr; }
-    kj_index_view iv; kj_taxonomy_view tv; kj_fmi_view(f, &iv); kj_nodes_view(t, &tv);
+    kj_index_view iv; kj_taxonomy_view tv; kj_fmi_view(f, &iv);
+    std::vector<uint64_t> st, node, parent;
+    if (nodes_path && *nodes_path) {
+        if (kj_nodes_load(nodes_path, &t) != KJ_OK) { fprintf(stderr, "kjemu: %s\n", kj_last_error()); return nullptr; }
+        kj_nodes_view(t, &tv);
+    } else {   // the name front-ends' view (kj_cli.cpp run_name_frontend): sequences numbered 2.. under the root 1
+        st.resize((size_t)iv.nseq); node.resize((size_t)iv.nseq + 1); parent.assign((size_t)iv.nseq + 1, 1); node[0] = 1;
+        for (int32_t i = 0; i < iv.nseq; i++) { st[(size_t)i] = (uint64_t)i + 2; node[(size_t)i + 1] = (uint64_t)i + 2; }
+        iv.seq_taxon = st.data(); tv.n = node.size(); tv.node = node.data(); tv.parent = parent.data();
+    }
     EmuCtx* c = new EmuCtx(); c->P = *p;
     if (kj_check_params(*p) != KJ_OK || kj_build_host_index(iv, tv, c->H) != KJ_OK) { fprintf(stderr, "kjemu: %s\n", kj_last_error()); delete c; return nullptr; }
-    kj_fmi_free(f); kj_nodes_free(t);
+    kj_fmi_free(f); if (t) kj_nodes_free(t);
     if (kj_build_evalue_breaks(*p, c->H.db_length, c->evbreaks) != KJ_OK) { fprintf(stderr, "kjemu: %s\n", kj_last_error()); delete c; return nullptr; }
     KjDevIndex& D = c->D; KjHostIndex& H = c->H; memset(&D, 0, sizeof D);
     D.rank = H.rank.data(); D.nb = H.nb; D.letters = H.letters.data(); D.bwtlen = H.bwtlen; D.alen = H.alen;
@@ -186,8 +195,13 @@ int kjemu_stats(unsigned long long* out, int cap, int reset) {
 }
 int kjemu_native_read(const char* path) { KjHostIndex H; return kj_host_index_read(path, H); }
 
+int kjemu_classify_ids(void* h, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
+                       uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out, int nthreads);
 int kjemu_classify(void* h, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
-                   uint64_t* taxon_out, uint32_t* best_out, int nthreads) {
+                   uint64_t* taxon_out, uint32_t* best_out, int nthreads) { return kjemu_classify_ids(h, seq1, off1, seq2, off2, n, taxon_out, best_out, nullptr, nullptr, nthreads); }
+// ids_out[i*21 .. +nids_out[i]): the match-id set of read i, ascending (what kj_classify_verbose delivers)
+int kjemu_classify_ids(void* h, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
+                       uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out, int nthreads) {
     EmuCtx* c = (EmuCtx*)h; bool paired = seq2 != nullptr;
     uint32_t max1 = 0, max2 = 0;
     for (uint64_t i = 0; i < n; i++) { max1 = std::max<uint32_t>(max1, (uint32_t)(off1[i + 1] - off1[i])); if (paired) max2 = std::max<uint32_t>(max2, (uint32_t)(off2[i + 1] - off2[i])); }
@@ -217,6 +231,8 @@ int kjemu_classify(void* h, const char* seq1, const uint64_t* off1, const char* 
             for (int l = 1; l < 32; l++) if (A.tax[l] != A.tax[0] || A.best[l] != A.best[0]) { fprintf(stderr, "kjemu: non-uniform result at read %llu\n", (unsigned long long)i); abort(); }
             taxon_out[i] = A.tax[0] == KJ_TAX_BAD ? 0 : c->H.tax_id[A.tax[0]];
             if (best_out) best_out[i] = taxon_out[i] ? A.best[0] : 0;
+            if (ids_out) { std::vector<uint64_t> v; if (taxon_out[i]) for (uint32_t u = 0; u < A.nids && u < 24; u++) v.push_back(c->H.tax_id[A.ids[u]]); std::sort(v.begin(), v.end());
+                           for (size_t u = 0; u < v.size() && u < 21; u++) ids_out[i * 21 + u] = v[u]; nids_out[i] = (uint8_t)std::min<size_t>(v.size(), 21); }
         }
         errs |= err; delete s;
         {   // fold this thread's counters into the process-wide totals

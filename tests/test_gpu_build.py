@@ -143,3 +143,33 @@ def test_index_beyond_2_pow_32_rows(kb, tmp_path):
     assert np.array_equal(a[0][:5000], otax) and np.array_equal(a[1][:5000], obest)
     assert (a[0] != 0).mean() > 0.5
     small.close(); big.close()
+
+
+def test_classify_multi_and_cli_device_list(kb, golden, tmp_path):
+    """Several contexts in one process (kj_classify_multi: contiguous shards, one host thread per context) give the single-context result;
+    the CLI hands the data sets of its -i/-j/-o lists to the devices of -d (here: every visible device, or device 0 twice over the ABI)."""
+    import gzip, shutil, subprocess
+    from conftest import ROOT
+    if not hasattr(kb.lib(), "kj_classify_multi"):
+        pytest.skip("library build without kj_classify_multi")
+    names, s1, o1, s2, o2 = golden.reads("pe150")
+    nd = max(1, kb.device_count())
+    one = kb.Classifier(golden.fmi, golden.nodes, device=0, params=kb.make_params("greedy"))
+    want = one.classify(s1, o1, s2, o2)
+    ctxs = [kb.Classifier(golden.fmi, golden.nodes, device=d % nd, params=kb.make_params("greedy")) for d in range(3)]
+    got = kb.classify_multi(ctxs, s1, o1, s2, o2)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    for c in ctxs + [one]:
+        c.close()
+    g = os.path.dirname(golden.fmi); d = str(tmp_path)
+    def plain(src, dst):
+        with gzip.open(src, "rb") as f, open(dst, "wb") as h:
+            shutil.copyfileobj(f, h)
+        return dst
+    a = plain(g + "/pe150_1.fq.gz", d + "/a.fq"); b = plain(g + "/pe150_2.fq.gz", d + "/b.fq"); c1 = plain(g + "/se100.fq.gz", d + "/c.fq")
+    cli = os.path.join(ROOT, "kaiju_b200", "kaiju-b200")
+    base = [cli, "-t", golden.nodes, "-f", golden.fmi, "-a", "mem"]
+    subprocess.run(base + ["-i", ",".join([a, c1, a]), "-o", ",".join([d + "/o1", d + "/o2", d + "/o3"]), "-d", "all"], check=True, stderr=subprocess.DEVNULL)
+    subprocess.run(base + ["-i", a, "-o", d + "/r1", "-d", "0"], check=True, stderr=subprocess.DEVNULL)
+    subprocess.run(base + ["-i", c1, "-o", d + "/r2"], check=True, stderr=subprocess.DEVNULL)
+    assert open(d + "/o1").read() == open(d + "/r1").read() == open(d + "/o3").read() and open(d + "/o2").read() == open(d + "/r2").read()

@@ -10,7 +10,7 @@ from helpers import Oracle, make_params, SynthDB
 
 class KjParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("min_fragment_length", C.c_uint32), ("mismatches", C.c_uint32), ("min_score", C.c_uint32),
-                ("seed_length", C.c_uint32), ("use_evalue", C.c_int32), ("min_evalue", C.c_double), ("seg", C.c_int32), ("input_is_protein", C.c_int32)]
+                ("seed_length", C.c_uint32), ("use_evalue", C.c_int32), ("min_evalue", C.c_double), ("seg", C.c_int32), ("input_is_protein", C.c_int32), ("name_mode", C.c_int32)]
 
 
 @pytest.fixture(scope="module")
@@ -152,3 +152,42 @@ def test_evalue_break_points_equal_the_reference_expression(emu):
                 ks = sorted(set([max(0, thr - 2), max(0, thr - 1), thr, thr + 1, thr + 5] + [rnd.randrange(0, 2000) for _ in range(6)]))
                 for k in ks:
                     assert (k >= thr) == (not rejected(db, q, k, E)), (E, db, q, k, thr)
+
+
+XP_CONFIGS = {"mem_default": dict(mode="mem"), "mem_m5_noseg": dict(mode="mem", m=5, seg=False), "greedy_default": dict(mode="greedy"),
+              "greedy_e5_s40": dict(mode="greedy", e=5, s=40), "greedy_e0": dict(mode="greedy", e=0)}
+
+
+@pytest.mark.parametrize("cfg", sorted(XP_CONFIGS))
+def test_emulated_name_frontend_matches_reference_kaijux(emu, golden, cfg):
+    """kaijux semantics (name_mode: sequences numbered under one root, MEM matches in maxMatches order) on the emulated kernel logic ==
+    the committed output of the reference's own kaijux binary (tests/golden/make_golden_xp.py), line by line."""
+    import gzip
+    import kaiju_b200 as kb
+    from conftest import GOLD
+    L = kb.lib(); L.kj_fmi_seq_name.restype = C.c_char_p; L.kj_fmi_seq_name.argtypes = [C.c_void_p, C.c_int32]
+    f = C.c_void_p(); assert L.kj_fmi_load(golden.fmi.encode(), C.byref(f)) == 0
+    emu.kjemu_classify_ids.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64] + [C.c_void_p] * 4 + [C.c_int]
+    kw = XP_CONFIGS[cfg]
+    for tag in ("se100", "pe150"):
+        names, s1, o1, s2, o2 = golden.reads(tag)
+        P = make_params(**kw); P["name_mode"] = 1
+        kp = KjParams(**P); h = emu.kjemu_create(golden.fmi.encode(), None, C.byref(kp)); assert h
+        n = len(o1) - 1; tax = np.zeros(n, np.uint64); best = np.zeros(n, np.uint32); ids = np.zeros((n, 21), np.uint64); nids = np.zeros(n, np.uint8)
+        rc = emu.kjemu_classify_ids(h, s1.ctypes.data, o1.ctypes.data, s2.ctypes.data if s2 is not None else None, o2.ctypes.data if s2 is not None else None,
+                                    n, tax.ctypes.data, best.ctypes.data, ids.ctypes.data, nids.ctypes.data, 4)
+        emu.kjemu_destroy(h); assert rc == 0
+        want = gzip.open(os.path.join(GOLD, "expected_x_%s_%s.tsv.gz" % (cfg, tag)), "rt").read().split("\n")
+        m3 = 3 * kw.get("m", 11); bad = []
+        for i in range(n):
+            l1 = int(o1[i + 1] - o1[i]); gate = l1 < m3 if s2 is None else (l1 < m3 and int(o2[i + 1] - o2[i]) < m3)
+            if gate:
+                line = "U\t%s\t0" % names[i]
+            elif not tax[i] or not nids[i]:
+                line = "U\t%s" % names[i]
+            else:
+                line = "C\t%s\t%d\t%s,\t" % (names[i], best[i], ",".join(L.kj_fmi_seq_name(f, int(x) - 2).decode() for x in ids[i, :nids[i]]))
+            if line != want[i]:
+                bad.append((line[:120], want[i][:120]))
+        assert not bad, bad[:3]
+    L.kj_fmi_free(f)
