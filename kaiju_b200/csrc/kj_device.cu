@@ -60,7 +60,7 @@ static __device__ __forceinline__ void kj_mbar_wait(uint64_t* bar, uint32_t pari
 // address space); GWS = true (reads too long for that): the same carve-up in a global buffer, generic loads and stores.
 template <int MODE, class IdxT, bool GWS>
 __global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32, MODE == 0 ? KJ_MIN_BLOCKS : KJ_MIN_BLOCKS_GREEDY)
-kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ KjRunParams rp,
+kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ KjRunParams rp, const __grid_constant__ KjSmemLayout lay,
                    const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
                    const uint8_t* __restrict__ seq2, const uint64_t* __restrict__ off2,
                    uint64_t base1, uint64_t base2, uint64_t n_reads,
@@ -82,7 +82,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
     KjWarpCtx cx;
     cx.w.lane = threadIdx.x & 31;
     cx.ix = &sh->ix; cx.rp = &rp; cx.tb = &sh->tb;
-    cx.L = kj_smem_layout(rp);
+    cx.L = lay;                                  // the carve-up is computed on the host and read from the parameter bank: no registers held for it
     const uint64_t gwarp = (uint64_t)blockIdx.x * KJ_WARPS_PER_CTA + (uint64_t)warp_in_cta;
     // per-warp work space: shared memory, or (reads too long for it) a slice of a global buffer that stays L1/L2-resident
     if (GWS) cx.smem = gws + gwarp * cx.L.total;
@@ -436,8 +436,9 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
     if (time_it) CK(cudaEventRecord(c->ev_a, st));
     const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
+    const KjSmemLayout lay = kj_smem_layout(rp);
 #define KJ_LAUNCH(M, T) if (rp.ws_global) KJ_LAUNCH3(M, T, true); else KJ_LAUNCH3(M, T, false)
-#define KJ_LAUNCH3(M, T, G) kj_classify_kernel<M, T, G><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, d_compact, \
+#define KJ_LAUNCH3(M, T, G) kj_classify_kernel<M, T, G><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, lay, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, d_compact, \
             c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
             c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), \
             rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err)
