@@ -11,11 +11,14 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum"]
 
 
 def main():
     rep, out, note = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
+    srcdir = sys.argv[4] if len(sys.argv) > 4 else None          # the csrc directory the profiled library was built from (default: the working tree)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -44,11 +47,11 @@ def main():
         import os, re
         fmap = {}
         for fn in ("kj_core.h", "kj_core_greedy.h"):
-            path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "kaiju_b200", "csrc", fn)
+            path = os.path.join(srcdir or os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "kaiju_b200", "csrc"), fn)
             cur = "(top)"; m = {}
             try:
                 for i, l in enumerate(open(path).read().split("\n"), 1):
-                    mm = re.match(r"^static KJ_DEV .*?\b(kj_\w+)\s*\(", l)
+                    mm = re.match(r"^(?:template <[^>]*>\s*)?(?:static )?(?:KJ_DEV|KJ_NOINLINE) .*?\b(kj_\w+)\s*\(", l)
                     if mm:
                         cur = mm.group(1)
                     m[i] = cur
@@ -69,5 +72,29 @@ def main():
             f.write("| %.1f | %.1f | %.1f | %d | %s:%d | `%s` |\n" % (100.0 * x[0] / tot, 100.0 * x[1] / ts, x[2] / max(x[0], 1), x[3], x[4], x[5], x[6].replace("|", "\\|")))
 
 
+def footprint(rep, out):
+    """hot code footprint: how many 128-byte instruction lines hold 90 / 95 / 99 % of the executed warp instructions"""
+    sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
+    rows = list(csv.reader(io.StringIO(sass)))
+    if len(rows) < 3:
+        return
+    h = rows[1]; ia, ie = h.index("Address"), h.index("Instructions Executed"); ins = []
+    for x in rows[2:]:
+        try:
+            ins.append((int(x[ia], 16), int(x[ie])))
+        except Exception:
+            pass
+    if not ins:
+        return
+    base = ins[0][0]; tot = sum(e for _, e in ins) or 1; acc = 0; lines = set(); marks = [0.9, 0.95, 0.99]; res = []
+    for a, e in sorted(ins, key=lambda t: -t[1]):
+        acc += e; lines.add((a - base) // 128)
+        while marks and acc >= marks[0] * tot:
+            res.append("%.0f %% of the executed instructions come from %.1f KB" % (marks[0] * 100, len(lines) * 128 / 1024)); marks.pop(0)
+    with open(out, "a") as f:
+        f.write("\n## instruction footprint (kernel: %d instructions = %.1f KB of SASS)\n\n%s\n" % (len(ins), len(ins) * 16 / 1024, "; ".join(res)))
+
+
 if __name__ == "__main__":
     main()
+    footprint(sys.argv[1], sys.argv[2])
