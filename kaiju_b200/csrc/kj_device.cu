@@ -27,8 +27,9 @@
 #define KJ_MIN_BLOCKS 4          // resident CTAs per SM the register allocation is tuned for (ncu: latency-bound, see profiles/)
 #endif
 #ifndef KJ_MIN_BLOCKS_GREEDY
-#define KJ_MIN_BLOCKS_GREEDY 5   // 48 registers, 40 warps per SM: Greedy waits on instruction fetch and local memory, more warps hide it (A/B round 2: +5 %; MEM: -8 %)
+#define KJ_MIN_BLOCKS_GREEDY 4   // A/B round 2 (5 CTAs = 48 registers): 12.0 vs 12.3 M pairs/s -- more warps, but more spill traffic and more instruction-fetch stalls
 #endif
+#define KJ_KEPT_SMEM_FIXED 20      // = KJ_KEPT_SMEM of kj_host.cpp (checked at launch: the fixed profile is only used when the layouts agree)
 #define KJ_CHUNK_READS (1u << 20)
 #define KJ_CHUNK_BYTES (1ull << 28)  // and at most this many bases of one mate per chunk (long reads)
 
@@ -58,7 +59,13 @@ static __device__ __forceinline__ void kj_mbar_wait(uint64_t* bar, uint32_t pari
 
 // GWS = false: the per-warp work space is carved out of shared memory (the compiler keeps every access in the shared
 // address space); GWS = true (reads too long for that): the same carve-up in a global buffer, generic loads and stores.
-template <int MODE, class IdxT, bool GWS>
+// FIX = true: the work-space carve-up of the standard short-read case (mates up to 152 bases, -m 11) as compile-time constants: every offset
+// becomes an immediate of the shared-memory instructions instead of a value that is kept in (or re-derived into) registers.
+static __host__ __device__ __forceinline__ KjRunParams kj_fixed_profile(int mode) {
+    KjRunParams p{}; p.mode = mode; p.m = 11; p.max_len = 152; p.max_frag = 152 / 3 + 1; p.item_cap = 128; p.kept_cap_smem = KJ_KEPT_SMEM_FIXED; p.stage = 0;
+    return p;
+}
+template <int MODE, class IdxT, bool GWS, bool FIX>
 __global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32, MODE == 0 ? KJ_MIN_BLOCKS : KJ_MIN_BLOCKS_GREEDY)
 kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ KjRunParams rp, const __grid_constant__ KjSmemLayout lay,
                    const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
@@ -82,7 +89,8 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
     KjWarpCtx cx;
     cx.w.lane = threadIdx.x & 31;
     cx.ix = &sh->ix; cx.rp = &rp; cx.tb = &sh->tb;
-    cx.L = lay;                                  // the carve-up is computed on the host and read from the parameter bank: no registers held for it
+    if (FIX) cx.L = kj_smem_layout(kj_fixed_profile(MODE));      // folded at compile time
+    else cx.L = lay;                                 // computed on the host, read from the parameter bank
     const uint64_t gwarp = (uint64_t)blockIdx.x * KJ_WARPS_PER_CTA + (uint64_t)warp_in_cta;
     // per-warp work space: shared memory, or (reads too long for it) a slice of a global buffer that stays L1/L2-resident
     if (GWS) cx.smem = gws + gwarp * cx.L.total;
@@ -218,6 +226,12 @@ template <class T> static int upload(const std::vector<T>& v, void** d, uint64_t
 // carve-up is addressed in a global buffer instead, which keeps the grid at full occupancy for any read length.
 // Measured (MEM, kernel-only, M pairs/s, shared vs global): PE150 57.8 vs 45.8, PE250 29.4 (3 CTAs/SM) vs 28.2, PE350 14.3 (2 CTAs/SM) vs 18.3.
 #define KJ_SMEM_WS_LIMIT (75u * 1024u)
+// the fixed-profile kernels apply when the batch's carve-up is exactly the compiled-in one
+static bool kj_use_fixed(const KjRunParams& rp) {
+    if (rp.ws_global || getenv("KJ_NO_FIXED")) return false;
+    const KjSmemLayout a = kj_smem_layout(rp), b = kj_smem_layout(kj_fixed_profile(rp.mode));
+    return memcmp(&a, &b, sizeof a) == 0 && rp.max_len == 152 && rp.kept_cap_smem == KJ_KEPT_SMEM_FIXED;
+}
 static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid) {
 #ifdef KJ_STAGE
     rp.stage = getenv("KJ_NO_STAGE") ? 0u : 1u;            // build with -DKJ_STAGE: bulk-copy staging of the bases (A/B; not the default, see the kernel)
@@ -231,18 +245,19 @@ static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid)
     if (const char* v = getenv("KJ_WS_LIMIT_KB")) { long x = atol(v); if (x >= 0 && x <= 227) limit = (size_t)x * 1024u; }    // tuning hook (A/B of the switch point)
     rp.ws_global = smem > limit ? 1u : 0u;
     if (rp.ws_global) { smem = head; rp.stage = 0; }
-    const int cfg = rp.mode * 2 + (int)rp.ws_global;
+    const int cfg = rp.mode * 2 + (int)rp.ws_global + (kj_use_fixed(rp) ? 4 : 0);
     // The max-dynamic-shared-memory attribute belongs to the kernel instantiation on the device, not to a context: several contexts
     // (or batches with different read lengths) share it, so it is only ever raised (process-wide table), never lowered.
-    static std::mutex attr_mu; static size_t attr_set[64][8];
-    const int inst = rp.mode * 4 + (c->H.wide ? 2 : 0) + (int)rp.ws_global;
+    static std::mutex attr_mu; static size_t attr_set[64][16];
+    const bool fixed = kj_use_fixed(rp);
+    const int inst = rp.mode * 4 + (c->H.wide ? 2 : 0) + (int)rp.ws_global + (fixed ? 8 : 0);
     bool raise = false;
     { std::lock_guard<std::mutex> lk(attr_mu); if (c->device < 64 && smem > attr_set[c->device][inst]) { attr_set[c->device][inst] = smem; raise = true; } else if (c->device >= 64) raise = true; }
     if (!raise && smem == c->smem_bytes && c->grid > 0 && c->cfg_mode == cfg) { grid = c->grid; return KJ_OK; }
     int per_sm = 0;
-#define KJ_CFG(M, T, G) { if (raise) CK(cudaFuncSetAttribute(kj_classify_kernel<M, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<M, T, G>, KJ_WARPS_PER_CTA * 32, smem)); }
-#define KJ_CFG2(M, T) { if (rp.ws_global) KJ_CFG(M, T, true) else KJ_CFG(M, T, false) }
+#define KJ_CFG(M, T, G, F) { if (raise) CK(cudaFuncSetAttribute(kj_classify_kernel<M, T, G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<M, T, G, F>, KJ_WARPS_PER_CTA * 32, smem)); }
+#define KJ_CFG2(M, T) { if (rp.ws_global) KJ_CFG(M, T, true, false) else if (fixed) KJ_CFG(M, T, false, true) else KJ_CFG(M, T, false, false) }
     if (rp.mode == 0) { if (c->H.wide) KJ_CFG2(0, uint64_t) else KJ_CFG2(0, uint32_t) }
     else { if (c->H.wide) KJ_CFG2(1, uint64_t) else KJ_CFG2(1, uint32_t) }
 #undef KJ_CFG2
@@ -352,7 +367,7 @@ static int create_ctx_device(kj_ctx** out, int device, const kj_params* params, 
     if ((rc = upload_small(c, tot)) || (rc = kj_device_build(c, v, lcode, copies, base, tot))) return rc;
     c->H.kmer_k = 0;
     if ((rc = upload_descriptor(c))) return rc;
-    { const char* ek = getenv("KJ_KMER_K"); if ((rc = kj_device_build_kmer(c, ek ? atoi(ek) : 5, tot))) return rc; }
+    { const char* ek = getenv("KJ_KMER_K"); if ((rc = kj_device_build_kmer(c, ek ? atoi(ek) : kj_default_kmer_k(c->H.bwtlen), tot))) return rc; }
     std::vector<uint32_t>().swap(c->H.seq_tax);
     if ((rc = finish_ctx(c, tot))) return rc;
     CK(cudaDeviceSynchronize());
@@ -437,8 +452,9 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     if (time_it) CK(cudaEventRecord(c->ev_a, st));
     const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
     const KjSmemLayout lay = kj_smem_layout(rp);
-#define KJ_LAUNCH(M, T) if (rp.ws_global) KJ_LAUNCH3(M, T, true); else KJ_LAUNCH3(M, T, false)
-#define KJ_LAUNCH3(M, T, G) kj_classify_kernel<M, T, G><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, lay, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, d_compact, \
+    const bool fixed = kj_use_fixed(rp);
+#define KJ_LAUNCH(M, T) if (rp.ws_global) KJ_LAUNCH3(M, T, true, false); else if (fixed) KJ_LAUNCH3(M, T, false, true); else KJ_LAUNCH3(M, T, false, false)
+#define KJ_LAUNCH3(M, T, G, F) kj_classify_kernel<M, T, G, F><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, lay, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, d_compact, \
             c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
             c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), \
             rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err)

@@ -319,7 +319,7 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
     if (quirk) {
         for (int a = 0; a < alen; a++) H.quirk_d[a] = host_rank(H, (uint32_t)a, n - 65536ull) - H.C[a];
     }
-    { const char* ek = getenv("KJ_KMER_K"); kj_build_kmer_table(H, ek ? atoi(ek) : 5); }
+    { const char* ek = getenv("KJ_KMER_K"); kj_build_kmer_table(H, ek ? atoi(ek) : kj_default_kmer_k(H.bwtlen)); }
     return KJ_OK;
 }
 

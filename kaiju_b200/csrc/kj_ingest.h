@@ -421,6 +421,10 @@ static int kj_prefetch(kj_ctx* c, KjFilesState& S, int f) {
 }
 
 static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, const char* in2, const char* out_path, int verbose, uint64_t* n_reads_out, uint64_t* n_class_out) {
+    // developer hook KJ_FILES_TRACE: where the wall time of the file pipeline goes (ms per stage, summed over the chunks)
+    const bool ftrace = getenv("KJ_FILES_TRACE") != nullptr; double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint64_t nchunks = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); }; auto t_last = now();
+    auto lap = [&](int k) { if (!ftrace) return; cudaStreamSynchronize(c->stream[0]); const auto t = now(); tm[k] += std::chrono::duration<double, std::milli>(t - t_last).count(); t_last = t; };
     size_t chunk = 64u << 20;
     if (const char* v = getenv("KJ_INGEST_CHUNK")) { long x = atol(v); if (x >= 256 && x <= (1l << 30)) chunk = (size_t)x; }       // test hook: many small chunks
     const bool paired = in2 && *in2; S.nfiles = paired ? 2 : 1;
@@ -437,6 +441,7 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
     unsigned long long* d_nclass = (unsigned long long*)((char*)S.totals.p + 16);
     for (int f = 0; f < S.nfiles; f++) if ((rc = kj_prefetch(c, S, f))) return rc;
     for (;;) {
+        nchunks++; lap(7);
         // 1. top up both sides: carry (already at the front of the device text) + the chunk that was prefetched into the staging buffer
         for (int f = 0; f < S.nfiles; f++) {
             KjParsed& P = S.side[f]; KjPrefetch& F = S.pf[f];
@@ -457,13 +462,16 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
             P.nbytes += F.n;
             if (need_nl) { CK(cudaMemsetAsync(P.text[P.cur].as<char>() + P.nbytes, '\n', 1, st)); P.nbytes += 1; }      // the last line of a file may lack its newline
         }
+        lap(0);
         // ... and start the host-to-device copy of the following chunks on the second stream: it overlaps with the kernels below
         for (int f = 0; f < S.nfiles; f++) if (!S.side[f].eof && (rc = kj_prefetch(c, S, f))) return rc;
+        lap(1);
         // 2. parse
         for (int f = 0; f < S.nfiles; f++) if ((rc = kj_parse_side(c, S.side[f], fn[f], st))) return rc;
         uint64_t n = S.side[0].n_rec; if (paired) n = std::min(n, S.side[1].n_rec);
         const bool all_eof = S.side[0].eof && (!paired || S.side[1].eof);
         if (paired && all_eof && S.side[0].n_rec > S.side[1].n_rec) { kj_err() = "File " + fn[0] + " contains more reads then file " + fn[1]; return KJ_ERR_IO; }   // kaiju.cpp:337-340
+        lap(2);
         // 3. classify + format the first n records
         if (n) {
             if (n >= (1ull << 31)) { kj_err() = "kj_classify_files: chunk with too many records"; return KJ_ERR_UNSUPPORTED; }
@@ -489,6 +497,7 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
                 if (rc) return rc;
                 break;
             }
+            lap(3);
             kj_count_commit<<<c->sm_count, 256, 0, st>>>(c->d_counts, c->d_counts_pending, c->n_counts); c->launches++;     // this chunk succeeded: its reads join the per-taxon counts
             kj_fmt_len<<<c->sm_count * 4, 256, 0, st>>>(S.tax.as<uint64_t>(), S.best.as<uint32_t>(), S.ids.as<uint64_t>(), S.nids.as<uint8_t>(), S.side[0].name_off.as<uint32_t>(), n, verbose, S.len.as<uint32_t>(), d_nclass);
             if ((rc = kj_scan_u32(S.len.as<uint32_t>(), n + 1, S.scan_tmp, (uint32_t*)S.totals.p, st))) return rc;
@@ -497,12 +506,13 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
             kj_fmt_write<<<c->sm_count * 4, 256, 0, st>>>(S.tax.as<uint64_t>(), S.best.as<uint32_t>(), S.ids.as<uint64_t>(), S.nids.as<uint8_t>(), S.side[0].names.as<char>(), S.side[0].name_off.as<uint32_t>(), n, verbose,
                                                        S.len.as<uint32_t>(), S.out.as<char>());
             CK(cudaGetLastError()); c->launches += 6;
+            lap(4);
             for (size_t o = 0; o < out_bytes; o += out_cap) {
                 const size_t m = std::min<size_t>(out_cap, out_bytes - o); char* hb = S.wr.get();
                 CK(cudaMemcpyAsync(hb, S.out.as<char>() + o, m, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
                 S.wr.put(hb, m);
             }
-            n_reads += n;
+            n_reads += n; lap(5);
         }
         // 4. carry the unconsumed tail to the front of the other text buffer
         for (int f = 0; f < S.nfiles; f++) {
@@ -524,6 +534,7 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
         }
     }
     CK(cudaMemcpyAsync(&n_class, d_nclass, 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    if (ftrace) fprintf(stderr, "KJ_FILES_TRACE chunks %llu  wait-chunk+h2d %.1f  prefetch-issue(reader wait) %.1f  parse %.1f  classify %.1f  format %.1f  d2h+writer %.1f  carry %.1f ms\n", (unsigned long long)nchunks, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[7]);
     if (n_reads_out) *n_reads_out = n_reads; if (n_class_out) *n_class_out = n_class;
     return KJ_OK;
 }

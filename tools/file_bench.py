@@ -30,6 +30,8 @@ def main():
     def run(cmd, files, out):
         t = time.time(); r = subprocess.run(cmd + ["-i", files[0], "-j", files[1], "-o", out], stderr=subprocess.PIPE, text=True, check=True, env=dict(os.environ, KJ_CLI_TIMING="1"))
         run.inner = [float(l.split(" classified, ")[1].split(" s")[0]) for l in r.stderr.splitlines() if " classified, " in l]
+        for l in r.stderr.splitlines():
+            if "KJ_FILES_TRACE" in l: print(l, file=sys.stderr)
         return time.time() - t
     ours = [os.path.join(ROOT, "kaiju_b200", "kaiju-b200"), "-t", nodes, "-f", fmi, "-a", a.mode]
     ref = [os.path.join(REF_DIR, "kaiju"), "-t", nodes, "-f", fmi, "-a", a.mode, "-z", str(os.cpu_count())]
