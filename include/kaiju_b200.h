@@ -70,6 +70,9 @@ typedef struct {
     const uint8_t *sa;            /* suffixArray.sa : ncheck * nbytes big-endian packed (seq,pos)     */
     const uint64_t *seq_taxon;    /* [nseq] taxon id parsed from suffixArray.ids[i] with the rule of
                                      ConsumerThread.cpp:812-832 (UINT64_MAX = "bad number", skipped) */
+    const uint32_t *seq_accession;/* optional [nseq] (NULL = not given): rank of the sequence's accession -- its name up to the last '_' --
+                                     among the distinct accessions in lexicographic order, 0xffffffff for names without '_'
+                                     (ConsumerThread.cpp:809-823); only kj_classify_verbose2() needs it (column 6 of `kaiju -v`) */
 } kj_index_view;
 
 typedef struct {
@@ -86,7 +89,9 @@ typedef struct kj_ctx kj_ctx;           /* one GPU context: index + taxonomy in 
 int kj_fmi_load(const char *path, kj_fmi **out);
 void kj_fmi_view(const kj_fmi *f, kj_index_view *view);
 void kj_fmi_free(kj_fmi *f);
-const char *kj_fmi_seq_name(const kj_fmi *f, int32_t i);   /* suffixArray.ids[i]: the database name of sequence i (in the index's own order) */
+const char *kj_fmi_seq_name(const kj_fmi *f, int32_t i);
+/* accession ranks of the sequences (what kj_index_view.seq_accession takes; kj_fmi_view() fills it in) and the accession string of a rank */
+const char *kj_fmi_accession(const kj_fmi *f, uint32_t rank);   /* suffixArray.ids[i]: the database name of sequence i (in the index's own order) */
 int kj_nodes_load(const char *path, kj_nodes **out);
 void kj_nodes_view(const kj_nodes *t, kj_taxonomy_view *view);
 void kj_nodes_free(kj_nodes *t);
@@ -123,6 +128,16 @@ int kj_classify(kj_ctx *ctx, const char *seq1, const uint64_t *off1, const char 
 #define KJ_MAX_MATCH_IDS 21
 int kj_classify_verbose(kj_ctx *ctx, const char *seq1, const uint64_t *off1, const char *seq2, const uint64_t *off2,
                         uint64_t n_reads, uint64_t *taxon_out, uint32_t *best_out, uint64_t *ids_out, uint8_t *nids_out);
+/* All seven columns of `kaiju -v` (ConsumerThread.cpp:527-536, 614-623): additionally the accession set of the visited database sequences
+ * (acc_out[i*KJ_MAX_MATCH_ACC .. +nacc_out[i]), ranks as given in kj_index_view.seq_accession, ascending = the reference's std::set<string>
+ * order; the context must have been created from a view with seq_accession) and the matched fragment strings, ready to print
+ * ("IGEYVEMMNGVVLSYIES,..." in frag_out[i*frag_stride .. +frag_len_out[i])): MEM = the longest match of every fragment that reached the
+ * longest length, Greedy = the sequences (with substitutions) of the best matches.  A read whose strings exceed frag_stride bytes makes the
+ * call fail with KJ_ERR_OVERFLOW. */
+#define KJ_MAX_MATCH_ACC 20
+int kj_classify_verbose2(kj_ctx *ctx, const char *seq1, const uint64_t *off1, const char *seq2, const uint64_t *off2,
+                         uint64_t n_reads, uint64_t *taxon_out, uint32_t *best_out, uint64_t *ids_out, uint8_t *nids_out,
+                         uint32_t *acc_out, uint8_t *nacc_out, char *frag_out, uint32_t frag_stride, uint32_t *frag_len_out);
 /* With params.input_is_protein (-p) seq1 holds protein letters (split at every letter outside the 20 residues,
  * ConsumerThread.cpp:659-696) and seq2 must be NULL.  Reads longer than KJ_MAX_READ_LEN / KJ_MAX_PROTEIN_LEN -> KJ_ERR_UNSUPPORTED. */
 /* Device buffers (same layout, all pointers in the context's device memory), enqueued on `cuda_stream`

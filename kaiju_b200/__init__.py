@@ -27,7 +27,7 @@ class KjIndexView(C.Structure):
     _fields_ = [("alen", C.c_int32), ("alphabet", C.c_char_p), ("bwtlen", C.c_int64), ("bwt", C.c_void_p),
                 ("startLcode", C.c_void_p), ("db_len", C.c_int64), ("nseq", C.c_int32), ("ncheck", C.c_int64),
                 ("chpt_exp", C.c_int32), ("nbytes", C.c_int32), ("pbits", C.c_int32), ("sa", C.c_void_p),
-                ("seq_taxon", C.c_void_p)]
+                ("seq_taxon", C.c_void_p), ("seq_accession", C.c_void_p)]
 
 
 class KjTaxonomyView(C.Structure):

@@ -221,17 +221,20 @@ static int kj_device_build(kj_ctx* c, const kj_index_view& v, const uint8_t lcod
     c->launches += 4;
     // ---- sequence -> taxon, sampled suffix array -> taxon
     { size_t b = std::max<size_t>(H.seq_tax.size() * 4, 16); CK(cudaMalloc(&c->d_seq_tax, b)); tot += b; if (!H.seq_tax.empty()) CK(cudaMemcpy(c->d_seq_tax, H.seq_tax.data(), H.seq_tax.size() * 4, cudaMemcpyHostToDevice)); }
+    if (!H.seq_acc.empty()) { CK(cudaMalloc(&c->d_seq_acc, H.seq_acc.size() * 4)); tot += H.seq_acc.size() * 4; CK(cudaMemcpy(c->d_seq_acc, H.seq_acc.data(), H.seq_acc.size() * 4, cudaMemcpyHostToDevice)); }
     uint64_t n_sa;
     if (rep == 1) {
         n_sa = (uint64_t)v.ncheck;
         CK(cudaMalloc(&c->d_sa_tax, (n_sa + 1) * 4)); tot += (n_sa + 1) * 4;
         CK(cudaMemset((uint32_t*)c->d_sa_tax + n_sa, 0xff, 4));       // guard entry (see create_ctx): the last sampled row has no entry in a reference-built index
+        if (c->d_seq_acc) { CK(cudaMalloc(&c->d_sa_acc, (n_sa + 1) * 4)); tot += (n_sa + 1) * 4; CK(cudaMemset((uint32_t*)c->d_sa_acc + n_sa, 0xff, 4)); }
         const uint64_t CHE = (uint64_t)1 << 26;                        // entries per upload chunk
         uint8_t* d_sa = nullptr; CK(cudaMalloc((void**)&d_sa, (size_t)std::min<uint64_t>(CHE, std::max<uint64_t>(n_sa, 1)) * (size_t)v.nbytes)); Free f4{d_sa};
         for (uint64_t e0 = 0; e0 < n_sa; e0 += CHE) {
             const uint64_t m = std::min(CHE, n_sa - e0);
             CK(cudaMemcpy(d_sa, v.sa + e0 * (uint64_t)v.nbytes, (size_t)m * (size_t)v.nbytes, cudaMemcpyHostToDevice));
             kj_bld_sa_tax<<<grid_big, 256>>>(d_sa, m, e0, v.nbytes, v.pbits, (uint32_t)v.nseq, (const uint32_t*)c->d_seq_tax, (uint32_t*)c->d_sa_tax, c->d_err);
+            if (c->d_sa_acc) kj_bld_sa_tax<<<grid_big, 256>>>(d_sa, m, e0, v.nbytes, v.pbits, (uint32_t)v.nseq, (const uint32_t*)c->d_seq_acc, (uint32_t*)c->d_sa_acc, c->d_err);
             CK(cudaGetLastError()); CK(cudaDeviceSynchronize()); c->launches++;
         }
         uint32_t e = 0; CK(cudaMemcpy(&e, c->d_err, 4, cudaMemcpyDeviceToHost));

@@ -3,8 +3,8 @@
 // Output: "C\t<name>\t<taxid>\n" / "U\t<name>\t0\n" (ConsumerThread.cpp:724-739), in INPUT order.
 // Host glue only: option parsing; kj_classify_files() reads FASTA/FASTQ(.gz), parses it on the device with the reference's name
 // trimming (kaiju.cpp:318-335) and strip() (util.cpp:26-33), classifies and formats the output.  -z is accepted and ignored (the GPU replaces the consumer threads); -p = protein input; with -v
-// columns 4 (best length/score) and 5 (match taxon ids) are appended -- columns 6-7 of the reference's -v output
-// (accession names, fragment sequences) are not produced.
+// all seven columns of the reference's -v output are printed (best length/score, taxon ids, accessions, fragment strings); from a device-native
+// index file (no sequence names) -v prints columns 1-5.
 #include <getopt.h>
 #include <unistd.h>
 #include <chrono>
@@ -17,6 +17,7 @@
 #include <thread>
 #include <vector>
 #include <zlib.h>
+#include <algorithm>
 #include "kaiju_b200.h"
 
 static void die(const std::string& m);
@@ -112,6 +113,48 @@ int run_name_frontend(bool protein, kj_params P, const std::string& fmi_fn, cons
     kj_destroy(ctx); kj_fmi_free(fmi);
     return EXIT_SUCCESS;
 }
+// `kaiju -v`: all seven columns (ConsumerThread.cpp:527-536, 614-623: best, taxon ids, accessions, fragment strings).  A debugging output in the
+// reference too; here it takes the host-side reader and kj_classify_verbose2 rather than the device-side text pipeline.
+int run_verbose(kj_ctx* ctx, kj_fmi* fmi, const kj_params& P, const std::string& in1, const std::string& in2, const std::string& out_fn, uint64_t& n_reads, uint64_t& n_class) {
+    LineReader r1, r2; const bool paired = !in2.empty(); const bool protein = P.input_is_protein != 0;
+    if (!r1.open(in1)) die("Could not open file " + in1);
+    if (paired && !r2.open(in2)) die("Could not open file " + in2);
+    FILE* out = out_fn.empty() ? stdout : fopen(out_fn.c_str(), "w"); if (!out) die("Could not open file " + out_fn + " for writing");
+    bool first1 = true, first2 = true, fq1 = false, fq2 = false;
+    std::vector<std::string> names; std::string s1, s2; std::vector<uint64_t> o1{0}, o2{0}; size_t maxlen = 0;
+    auto flush = [&]() {
+        const size_t n = names.size(); if (!n) return;
+        const uint32_t stride = (uint32_t)(32u * ((protein ? maxlen : maxlen / 3u) + 2u) + 64u);
+        std::vector<uint64_t> tax(n), ids(n * KJ_MAX_MATCH_IDS); std::vector<uint32_t> best(n), acc(n * KJ_MAX_MATCH_ACC), flen(n); std::vector<uint8_t> nids(n), nacc(n); std::vector<char> frag(n * (size_t)stride);
+        if (kj_classify_verbose2(ctx, s1.data(), o1.data(), paired ? s2.data() : nullptr, paired ? o2.data() : nullptr, n, tax.data(), best.data(), ids.data(), nids.data(),
+                                 acc.data(), nacc.data(), frag.data(), stride, flen.data()) != KJ_OK) die(kj_last_error());
+        for (size_t i = 0; i < n; i++) {
+            if (!tax[i]) { fprintf(out, "U\t%s\t0\n", names[i].c_str()); continue; }
+            n_class++;
+            fprintf(out, "C\t%s\t%llu\t%u\t", names[i].c_str(), (unsigned long long)tax[i], best[i]);
+            for (uint8_t k = 0; k < nids[i]; k++) fprintf(out, "%llu,", (unsigned long long)ids[i * KJ_MAX_MATCH_IDS + k]);
+            fputc('\t', out);
+            for (uint8_t k = 0; k < nacc[i]; k++) fprintf(out, "%s,", kj_fmi_accession(fmi, acc[i * KJ_MAX_MATCH_ACC + k]));
+            fputc('\t', out);
+            fwrite(frag.data() + i * (size_t)stride, 1, flen[i], out);
+            fputc('\n', out);
+        }
+        n_reads += n; names.clear(); s1.clear(); s2.clear(); o1.assign(1, 0); o2.assign(1, 0); maxlen = 0;
+    };
+    std::string name, seq, name2, seq2;
+    while (next_record(r1, first1, fq1, true, true, in1, name, seq)) {
+        if (paired) {
+            if (!next_record(r2, first2, fq2, true, true, in2, name2, seq2)) die("File " + in1 + " contains more reads then file " + in2);
+            if (name != name2) die("Read names are not identical between the two input files. Probably reads are not in the same order in both files.");
+        }
+        names.push_back(name); s1 += seq; o1.push_back(s1.size()); maxlen = std::max(maxlen, seq.size());
+        if (paired) { s2 += seq2; o2.push_back(s2.size()); maxlen = std::max(maxlen, seq2.size()); }
+        if (names.size() >= (1u << 17)) flush();
+    }
+    flush();
+    if (out != stdout) fclose(out);
+    return EXIT_SUCCESS;
+}
 }  // namespace
 
 static void die(const std::string& m) { fprintf(stderr, "Error: %s\n\n", m.c_str()); exit(EXIT_FAILURE); }
@@ -122,7 +165,7 @@ static void usage(const char* prog) {
                     "   -z INT        accepted for compatibility (ignored: the GPU replaces the worker threads)\n   -a STRING     Run mode, either \"mem\"  or \"greedy\" (default: greedy)\n"
                     "   -e INT        Number of mismatches allowed in Greedy mode (default: 3)\n   -m INT        Minimum match length (default: 11)\n   -s INT        Minimum match score in Greedy mode (default: 65)\n"
                     "   -E FLOAT      Minimum E-value in Greedy mode (default: 0.01)\n   -x            Enable SEG low complexity filter (enabled by default)\n   -X            Disable SEG low complexity filter\n"
-                    "   -w FILENAME   Write the device-native index file for -t/-f and exit; such a file can then be given as -f (no -t needed, no transcode at start-up)\n   -T FILENAME   Also write kaiju2table's summary (reads per taxon of rank -r, default species; needs -N names.dmp) from the counts kept on the GPU\n   -p            Input sequences are protein sequences\n   -v            Enable verbose output (adds the match length/score and the matching taxon ids)\n   -M STRING     front-end: \"kaijux\" (as kaiju, but reports the names of the matching database sequences; no -t) or \"kaijup\" (the same for protein reads)\n   -d LIST       CUDA device ordinal(s): one number, a comma-separated list, or \"all\" (default 0).  With several devices the data sets of the\n                 -i/-j/-o lists are classified in parallel, one context (index replica) per device\n", prog);
+                    "   -w FILENAME   Write the device-native index file for -t/-f and exit; such a file can then be given as -f (no -t needed, no transcode at start-up)\n   -T FILENAME   Also write kaiju2table's summary (reads per taxon of rank -r, default species; needs -N names.dmp) from the counts kept on the GPU\n   -p            Input sequences are protein sequences\n   -v            Enable verbose output (adds the match length/score, the matching taxon ids, accession numbers and fragment sequences)\n   -M STRING     front-end: \"kaijux\" (as kaiju, but reports the names of the matching database sequences; no -t) or \"kaijup\" (the same for protein reads)\n   -d LIST       CUDA device ordinal(s): one number, a comma-separated list, or \"all\" (default 0).  With several devices the data sets of the\n                 -i/-j/-o lists are classified in parallel, one context (index replica) per device\n", prog);
     exit(EXIT_FAILURE);
 }
 
@@ -214,7 +257,7 @@ int main(int argc, char** argv) {
         for (auto& x : th) x.join();
         if (!err.empty()) die(err);
     }
-    if (fmi) kj_fmi_free(fmi);
+    if (fmi && !verbose) { kj_fmi_free(fmi); fmi = nullptr; }      // -v prints accession strings: the loader's names stay
     if (nodes) kj_nodes_free(nodes);
 
     // parsing, classification and output formatting all run on the device; the host moves bytes (kj_ingest.h).
@@ -229,7 +272,8 @@ int main(int argc, char** argv) {
             Done& r = done[k]; kj_ctx* ctx = ctxs[d]; int rc = KJ_OK;
             if (!table_fn.empty()) rc = kj_counts_reset(ctx);
             const auto t0 = std::chrono::steady_clock::now();
-            if (rc == KJ_OK) rc = kj_classify_files(ctx, l1[k].c_str(), paired ? l2[k].c_str() : nullptr, lo.empty() ? nullptr : lo[k].c_str(), verbose ? 1 : 0, &r.n_reads, &r.n_classified);
+            if (rc == KJ_OK && verbose && fmi) run_verbose(ctx, fmi, P, l1[k], paired ? l2[k] : std::string(), lo.empty() ? std::string() : lo[k], r.n_reads, r.n_classified);
+            else if (rc == KJ_OK) rc = kj_classify_files(ctx, l1[k].c_str(), paired ? l2[k].c_str() : nullptr, lo.empty() ? nullptr : lo[k].c_str(), verbose ? 1 : 0, &r.n_reads, &r.n_classified);
             r.secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             if (rc == KJ_OK && !table_fn.empty()) { r.ids.resize(kj_counts_size(ctx)); r.counts.resize(r.ids.size()); rc = kj_counts_get(ctx, r.ids.data(), r.counts.data()); }
             if (rc != KJ_OK) { std::lock_guard<std::mutex> lk(mu); if (err.empty()) err = kj_last_error(); return; }
@@ -246,5 +290,6 @@ int main(int argc, char** argv) {
         if (verbose || getenv("KJ_CLI_TIMING")) fprintf(stderr, "%s: %llu reads, %llu classified, %.4f s from the first byte read to the last byte written\n", l1[k].c_str(), (unsigned long long)done[k].n_reads, (unsigned long long)done[k].n_classified, done[k].secs);
     }
     for (kj_ctx* ctx : ctxs) kj_destroy(ctx);
+    if (fmi) kj_fmi_free(fmi);
     return EXIT_SUCCESS;
 }

@@ -28,7 +28,7 @@ struct KjKept { uint64_t lo; uint32_t len; uint32_t aux; };     // one suffix in
 
 struct KjSmemLayout {
     uint32_t qkey_off, qpay_off, kept_off, res_off, res2_off, pre_off, ids_off, qord_off, aa_off, aa_stride, frag_off, hflag_off,
-             segcnt_off, seghist_off, segs_off, stage_off, stage_stride, mbar_off, total;
+             segcnt_off, seghist_off, segs_off, stage_off, stage_stride, mbar_off, accs_off, total;
 #if defined(KJ_EMU)
     uint32_t guard[16], nguard;         // emulator only: 64-byte red zones between the sub-arrays, checked after every read item
 #endif
@@ -50,6 +50,7 @@ static KJ_HD KjSmemLayout kj_smem_layout(const KjRunParams& p) {
     L.qpay_off = o; o += 4u * kj_align(p.item_cap, 2); KJ_GUARD(L, o)
     L.qord_off = o; o += kj_align(p.item_cap, 8); KJ_GUARD(L, o)           // slots in pop order (valid while no SEG piece was pushed)
     L.ids_off = o; o += 4u * 24u; KJ_GUARD(L, o)
+    L.accs_off = o; o += 4u * 24u; KJ_GUARD(L, o)                            // accession ranks of the visited sequences (verbose output) + their count
     L.aa_stride = kj_align(p.max_len + 4, 8);
     L.aa_off = o; o += 4u * L.aa_stride; KJ_GUARD(L, o)
     L.frag_off = o; o += kj_align(p.max_frag + 8, 8); KJ_GUARD(L, o)
@@ -87,7 +88,9 @@ struct KjWarpCtx {
     KjKept* spill;                      // global scratch of this warp: rp->scratch_entries entries
     void* gscratch;                     // global scratch of this warp for the greedy variant queue
     uint32_t nids;                      // size of the match-id set left in shared memory by the last item (uniform)
-    uint32_t* err;                      // global error flags: 1 item-queue overflow, 2 spill overflow, 4 greedy queue overflow
+    uint32_t* err;                      // global error flags: 1 item-queue overflow, 2 spill overflow, 4 greedy queue overflow, 128 fragment text overflow
+    char* text; uint32_t text_cap, text_len;   // verbose output: the read's fragment-string area (nullptr = not requested), bytes used (uniform)
+    bool want_acc;                       // verbose output: collect accession ranks
 };
 static KJ_DEV void kj_flag_error(KjWarpCtx& cx, uint32_t bit) {
 #if defined(KJ_EMU)
@@ -155,13 +158,19 @@ static KJ_DEV uint32_t kj_letter(const KjDevIndex& ix, uint64_t k) {
     return (uint32_t)(ix.letters[wd] >> s) & 31u;
 }
 // get_suffix (bwt.c:105-121) reduced to the taxon of the sequence the suffix lies in
+// get_suffix (bwt.c:105-121): entry of the sampled suffix array (is_seq = false) or sequence number (walk ended on a terminator)
 template <class IdxT>
-static KJ_DEV uint32_t kj_sa_taxon(const KjDevIndex& ix, uint64_t k) {
+static KJ_DEV uint64_t kj_sa_locate(const KjDevIndex& ix, uint64_t k, bool& is_seq) {
     uint32_t c = 1;
     KJ_ROLLED
     while (c != 0 && (k & ix.sa_check)) { c = kj_letter(ix, k); const bool q = k >= ix.quirk_lo; k = (uint64_t)kj_rank<IdxT>(ix, c, (IdxT)k); if (q) k -= ix.quirk_d[c]; }
-    if (c != 0) return ix.sa_tax[(uint64_t)((int64_t)(k >> ix.sa_exp) - ix.sa_bias)];
-    return ix.seq_tax[k];
+    is_seq = c == 0;
+    return is_seq ? k : (uint64_t)((int64_t)(k >> ix.sa_exp) - ix.sa_bias);
+}
+template <class IdxT>
+static KJ_DEV uint32_t kj_sa_taxon(const KjDevIndex& ix, uint64_t k) {
+    bool is_seq; const uint64_t e = kj_sa_locate<IdxT>(ix, k, is_seq);
+    return is_seq ? ix.seq_tax[e] : ix.sa_tax[e];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -729,12 +738,13 @@ static KJ_DEV KjKept* kj_kept_ptr(KjWarpCtx& cx, uint32_t idx) {
 // taxon ids of the kept intervals in order, k ascending, stop once the set exceeds 20 entries
 // (ids_from_SI, ConsumerThread.cpp:799-835); then LCA (util.cpp:194-263).  Runs once per read, out of line.
 // Returns compact taxon (KJ_TAX_BAD for "none") | number of ids << 32.
-struct KjIdsArgs { Warp w; const KjDevIndex* ix; const KjKept* kept_smem; const KjKept* spill; uint32_t kept_cap, spill_cap; uint32_t* ids; };
+struct KjIdsArgs { Warp w; const KjDevIndex* ix; const KjKept* kept_smem; const KjKept* spill; uint32_t kept_cap, spill_cap; uint32_t* ids; uint32_t* accs; };     // accs: nullptr or [20] + count at [20]
 template <class IdxT>
 KJ_NOINLINE uint64_t kj_ids_and_lca_fn(const KjIdsArgs A, uint32_t nkept) {
     const Warp& w = A.w; const KjDevIndex& ix = *A.ix;
     uint32_t* ids = A.ids;
-    uint32_t nids = 0;                                                    // uniform
+    uint32_t nids = 0, nacc = 0;                                          // uniform
+    uint32_t* accs = A.accs;
     KJ_ROLLED
     for (uint32_t e = 0; e < nkept && nids <= 20; e++) {
         const uint32_t se = e - A.kept_cap;
@@ -742,17 +752,23 @@ KJ_NOINLINE uint64_t kj_ids_and_lca_fn(const KjIdsArgs A, uint32_t nkept) {
         KJ_ROLLED
         for (uint32_t base = 0; base < kk.len && nids <= 20; base += 32) {
             uint32_t t = base + (uint32_t)w.lane; bool act = t < kk.len;
-            uint32_t tax = act ? kj_sa_taxon<IdxT>(ix, kk.lo + t) : KJ_TAX_BAD;
+            uint32_t tax = KJ_TAX_BAD, acc = 0xffffffffu;
+            if (act) { bool is_seq; const uint64_t en = kj_sa_locate<IdxT>(ix, kk.lo + t, is_seq); tax = is_seq ? ix.seq_tax[en] : ix.sa_tax[en]; if (accs) acc = is_seq ? ix.seq_acc[en] : ix.sa_acc[en]; }
             uint32_t nact = kk.len - base < 32u ? kk.len - base : 32u;
             KJ_ROLLED
             for (uint32_t s = 0; s < nact && nids <= 20; s++) {
                 uint32_t id = w.shfl(tax, (int)s);
                 if (id == KJ_TAX_BAD) continue;
+                if (accs) {          // match_dbnames (ConsumerThread.cpp:821-823): first 20 distinct accessions of the visited sequences
+                    const uint32_t a = w.shfl(acc, (int)s);
+                    if (a != 0xffffffffu && nacc < 20u) { const bool dupa = (uint32_t)w.lane < nacc && accs[w.lane] == a; if (!w.any(dupa)) { if (w.lane == 0) accs[nacc] = a; nacc++; w.sync(); } }
+                }
                 bool dup = (uint32_t)w.lane < nids && ids[w.lane] == id;
                 if (!w.any(dup)) { if (w.lane == 0) ids[nids] = id; nids++; w.sync(); }
             }
         }
     }
+    if (accs && w.lane == 0) accs[20] = nacc;
     const uint64_t hi = (uint64_t)nids << 32;
     if (nids == 0) return hi | KJ_TAX_BAD;
     w.sync();
@@ -779,6 +795,7 @@ template <class IdxT>
 static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
     KjIdsArgs A; A.w = cx.w; A.ix = cx.ix; A.kept_smem = (const KjKept*)(cx.smem + cx.L.kept_off); A.spill = cx.spill;
     A.kept_cap = cx.rp->kept_cap_smem; A.spill_cap = cx.rp->scratch_entries; A.ids = (uint32_t*)(cx.smem + cx.L.ids_off);
+    A.accs = cx.want_acc ? (uint32_t*)(cx.smem + cx.L.accs_off) : nullptr;
     const uint64_t r = kj_ids_and_lca_fn<IdxT>(A, nkept);
     cx.nids = (uint32_t)(r >> 32);
     return (uint32_t)r;
@@ -896,7 +913,7 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
                 if (lmax > item_best) { item_best = lmax; item_cnt = 0; }
                 L = lmax;
                 const uint32_t wm = w.ballot(l == item_best && l > 0);
-                if (l == item_best && l > 0) { KjKept* k = kj_kept_ptr(cx, nkept + item_cnt + (uint32_t)kj_popc(wm & lanemask_lt(w.lane))); k->lo = (uint64_t)cur.lo; k->len = (uint32_t)(cur.hi - cur.lo); k->aux = 0; }
+                if (l == item_best && l > 0) { KjKept* k = kj_kept_ptr(cx, nkept + item_cnt + (uint32_t)kj_popc(wm & lanemask_lt(w.lane))); k->lo = (uint64_t)cur.lo; k->len = (uint32_t)(cur.hi - cur.lo); k->aux = (arr << 29) | ((start + 3u * (uint32_t)cur.i) << 14) | l; }      // aux: where the matched text lies (verbose output)
                 item_cnt += (uint32_t)kj_popc(wm);
             }
             jhi -= 32;
@@ -919,6 +936,8 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
                 KjKept x = *a; *a = *b; *b = x;
             }
             w.sync();
+            if (w.lane == 0) kj_kept_ptr(cx, nkept)->aux |= 0x80000000u;  // the head of this fragment's list: its text goes to the fragment column (longest_fragments, 579-590)
+            w.sync();
             if (item_best > longest) {                                    // replace (ConsumerThread.cpp:574-585)
                 if (nkept > 0) {
                     KJ_ROLLED
@@ -936,6 +955,26 @@ static KJ_DEV bool kj_mem_item(KjWarpCtx& cx, KjQueue& q, uint32_t pay, uint32_t
     return item_cnt > 0;
 }
 
+// fragment column of the verbose output in MEM mode: the text of the head match of every contributing fragment, "TEXT,TEXT," (614-623)
+KJ_NOINLINE uint32_t kj_emit_text(const Warp w, char* text, uint32_t at, uint32_t cap, const uint8_t* src, uint32_t stride, uint32_t len, const char* letters) {
+    if (at + len + 1u > cap) return 0xffffffffu;
+    KJ_ROLLED
+    for (uint32_t t = (uint32_t)w.lane; t < len; t += 32) text[at + t] = letters[src[stride * t]];
+    if (w.lane == 0) text[at + len] = ',';
+    return at + len + 1u;
+}
+static KJ_DEV void kj_emit_fragments_mem(KjWarpCtx& cx, uint32_t nkept) {
+    KJ_ROLLED
+    for (uint32_t e = 0; e < nkept; e++) {
+        const uint32_t aux = kj_kept_ptr(cx, e)->aux;
+        if (!(aux >> 31)) continue;
+        const uint32_t arr = (aux >> 29) & 3u, pos = (aux >> 14) & 0x7fffu, len = aux & 0x3fffu;
+        const uint32_t at = kj_emit_text(cx.w, cx.text, cx.text_len, cx.text_cap, cx.smem + cx.L.aa_off + arr * cx.L.aa_stride + pos, 3u, len, cx.tb->letters);
+        if (at == 0xffffffffu) { if (cx.w.lane == 0) kj_flag_error(cx, 128u); return; }
+        cx.text_len = at;
+    }
+    cx.w.sync();
+}
 template <class IdxT>
 static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best_out) {
     uint32_t longest = 0, nkept = 0;                                      // uniform
@@ -947,6 +986,7 @@ static KJ_DEV uint32_t kj_classify_mem(KjWarpCtx& cx, KjQueue& q, uint32_t& best
     cx.w.sync();
     uint32_t t = kj_ids_and_lca<IdxT>(cx, nkept);
     if (t != KJ_TAX_BAD) best_out = longest;
+    if (cx.text && t != KJ_TAX_BAD) kj_emit_fragments_mem(cx, nkept);
     return t;
 }
 

@@ -349,7 +349,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
                 const uint32_t cidx = (uint32_t)kj_popc(heads & ((2u << t) - 1u)) - 1u;           // class index of t
                 const uint32_t pos = head ? (ncand - K) + (K - 1u - cidx) : t - (cidx + 1u);
                 int sc = (int)pre[r.qi + r.ql] - (int)pre[r.qi] + diff; if (sc < 0) sc = 0;
-                res[pos].lo = r.lo; res[pos].len = r.len; res[pos].qi = (uint16_t)(sc > 65535 ? 65535 : sc); res[pos].ql = r.ql;
+                res[pos].lo = r.lo | ((uint64_t)r.qi << 48); res[pos].len = r.len; res[pos].qi = (uint16_t)(sc > 65535 ? 65535 : sc); res[pos].ql = r.ql;      // (the match start rides in the free top bits of lo: the verbose output needs it)
             }
             w.sync();
             // the sequential best-list update of the reference, closed form: the list ends up holding the entries that equal the final
@@ -358,10 +358,20 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
             const uint32_t sc = t < ncand ? (uint32_t)e.qi : 0u; const bool valid = t < ncand && sc >= rp.min_score;
             const uint32_t mx = warp_max_u32(w, valid ? sc : 0u);
             if (mx > 0 && mx >= best) {
-                if (mx > best) { best = mx; nbest = 0; }
+                if (mx > best) { best = mx; nbest = 0; cx.text_len = 0; }
                 const uint32_t eq = w.ballot(valid && sc == mx);
                 const uint32_t slot = nbest + (uint32_t)kj_popc(eq & lanemask_lt(w.lane));
-                if (valid && sc == mx && slot < KJ_MAX_BEST_SI) { bl[slot].lo = e.lo; bl[slot].len = e.len; bl[slot].aux = 0; }
+                const bool take = valid && sc == mx && slot < KJ_MAX_BEST_SI;
+                if (take) { bl[slot].lo = e.lo & 0xffffffffffffull; bl[slot].len = e.len; bl[slot].aux = 0; }
+                if (cx.text) {       // best_matches (ConsumerThread.cpp:779-790): the matched text of every entry of the best list, in list order
+                    const uint32_t mylen = take ? (uint32_t)e.ql + 1u : 0u; const uint32_t endp = kj_scan_incl(w, mylen);
+                    const uint32_t at = cx.text_len + endp - mylen, tot = w.shfl(endp, 31);
+                    if (cx.text_len + tot > cx.text_cap) { if (w.lane == 0) kj_flag_error(cx, 128u); }
+                    else {
+                        if (take) { const uint32_t qi0 = (uint32_t)(e.lo >> 48); for (uint32_t u = 0; u + 1u < mylen; u++) cx.text[at + u] = tb.letters[frag[qi0 + u]]; cx.text[at + mylen - 1u] = ','; }
+                        cx.text_len += tot;
+                    }
+                }
                 nbest += (uint32_t)kj_popc(eq); if (nbest > KJ_MAX_BEST_SI) nbest = KJ_MAX_BEST_SI;
             }
             w.sync();
@@ -379,7 +389,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
                     heads_before = cidx + (head ? 0u : 1u);
                     uint32_t pos = head ? (ncand - K) + (K - 1u - cidx) : t - heads_before;
                     int sc = (int)pre[r.qi + r.ql] - (int)pre[r.qi] + diff; if (sc < 0) sc = 0;
-                    res[pos].lo = r.lo; res[pos].len = r.len; res[pos].qi = (uint16_t)(sc > 65535 ? 65535 : sc); res[pos].ql = r.ql;
+                    res[pos].lo = r.lo | ((uint64_t)r.qi << 48); res[pos].len = r.len; res[pos].qi = (uint16_t)(sc > 65535 ? 65535 : sc); res[pos].ql = r.ql;
                 }
             }
             w.sync();
@@ -387,8 +397,13 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
             for (uint32_t t = 0; t < ncand; t++) {
                 const KjMatch r = res[t]; const uint32_t sc = r.qi;
                 if (sc < rp.min_score) continue;
-                if (sc > best) { best = sc; nbest = 0; if (w.lane == 0) { bl[0].lo = r.lo; bl[0].len = r.len; bl[0].aux = 0; } nbest = 1; }
-                else if (sc == best && nbest < KJ_MAX_BEST_SI) { if (w.lane == 0) { bl[nbest].lo = r.lo; bl[nbest].len = r.len; bl[nbest].aux = 0; } nbest++; }
+                bool took = false;
+                if (sc > best) { best = sc; nbest = 0; cx.text_len = 0; if (w.lane == 0) { bl[0].lo = r.lo & 0xffffffffffffull; bl[0].len = r.len; bl[0].aux = 0; } nbest = 1; took = true; }
+                else if (sc == best && nbest < KJ_MAX_BEST_SI) { if (w.lane == 0) { bl[nbest].lo = r.lo & 0xffffffffffffull; bl[nbest].len = r.len; bl[nbest].aux = 0; } nbest++; took = true; }
+                if (took && cx.text) {
+                    const uint32_t at = kj_emit_text(w, cx.text, cx.text_len, cx.text_cap, frag + (uint32_t)(r.lo >> 48), 1u, r.ql, tb.letters);
+                    if (at == 0xffffffffu) { if (w.lane == 0) kj_flag_error(cx, 128u); } else cx.text_len = at;
+                }
             }
             w.sync();
         }

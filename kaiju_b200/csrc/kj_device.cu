@@ -65,7 +65,8 @@ static __host__ __device__ __forceinline__ KjRunParams kj_fixed_profile(int mode
     KjRunParams p{}; p.mode = mode; p.m = 11; p.max_len = 152; p.max_frag = 152 / 3 + 1; p.item_cap = 128; p.kept_cap_smem = KJ_KEPT_SMEM_FIXED; p.stage = 0;
     return p;
 }
-template <int MODE, class IdxT, bool GWS, bool FIX>
+// VB = true: the verbose outputs (id sets, accession sets, fragment strings) are compiled in; the kernels of the normal path carry none of it.
+template <int MODE, class IdxT, bool GWS, bool FIX, bool VB>
 __global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32, MODE == 0 ? KJ_MIN_BLOCKS : KJ_MIN_BLOCKS_GREEDY)
 kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ KjRunParams rp, const __grid_constant__ KjSmemLayout lay,
                    const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
@@ -73,7 +74,8 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
                    uint64_t base1, uint64_t base2, uint64_t n_reads,
                    uint64_t* __restrict__ taxon_out, uint32_t* __restrict__ best_out, uint64_t* __restrict__ ids_out, uint8_t* __restrict__ nids_out, uint32_t* __restrict__ compact_out,
                    unsigned long long* __restrict__ counter, KjKept* __restrict__ spill, uint8_t* __restrict__ gscratch,
-                   uint32_t gscratch_bytes, uint8_t* __restrict__ gws, unsigned long long* __restrict__ counts, uint32_t* __restrict__ err) {
+                   uint32_t gscratch_bytes, uint8_t* __restrict__ gws, unsigned long long* __restrict__ counts, uint32_t* __restrict__ err,
+                   uint32_t* __restrict__ acc_out, uint8_t* __restrict__ nacc_out, char* __restrict__ frag_out, uint32_t frag_stride, uint32_t* __restrict__ frag_len_out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     KjCtaShared* sh = (KjCtaShared*)smem_raw;
     {   // stage the index descriptor (C[] etc.) and the small tables once per CTA
@@ -97,7 +99,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
     else cx.smem = smem_raw + kj_align((uint32_t)sizeof(KjCtaShared), 16) + (uint32_t)warp_in_cta * cx.L.total;
     cx.spill = spill + gwarp * rp.scratch_entries;
     cx.gscratch = gscratch + gwarp * gscratch_bytes;
-    cx.err = err;
+    cx.err = err; cx.text = nullptr; cx.text_cap = frag_stride; cx.text_len = 0; cx.want_acc = VB && acc_out != nullptr;
     const bool paired = seq2 != nullptr;
 #ifdef KJ_STAGE
     const bool stage = !GWS && rp.stage != 0;
@@ -139,6 +141,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
             const uint8_t* p1 = stage ? stg + al1 + (uint32_t)(a0 - f1) : seq1 + a0;
             const uint8_t* p2 = !paired ? nullptr : stage ? stg + cx.L.stage_stride + al2 + (uint32_t)(b0 - f2) : seq2 + b0;
             uint32_t best = 0;
+            if (VB && frag_out) { cx.text = frag_out + r * frag_stride; cx.text_len = 0; }
             uint32_t t = kj_classify_item<MODE, IdxT>(cx, p1, (int)(a1 - a0), p2, (int)(b1 - b0), paired, best);
             const uint64_t id = t == KJ_TAX_BAD ? 0ull : sh->ix.tax_id[t];
             if (cx.w.lane == 0) {
@@ -148,7 +151,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
                 // per-taxon read counts (kaiju2table's first pass), fused: a separate counting kernel behind a persistent grid would stall the chunk pipeline
                 if (counts) atomicAdd(counts + (id ? t : sh->ix.n_tax), 1ull);
             }
-            if (ids_out) {   // column 5 of the reference's -v output: the match-id set in ascending order (std::set), classified reads only
+            if (VB && ids_out) {   // column 5 of the reference's -v output: the match-id set in ascending order (std::set), classified reads only
                 const uint32_t nids = id ? cx.nids : 0u; const uint32_t* ids = (const uint32_t*)(cx.smem + cx.L.ids_off);
                 if ((uint32_t)cx.w.lane < nids) {
                     const uint64_t mine = sh->ix.tax_id[ids[cx.w.lane]]; uint32_t rank = 0;
@@ -158,6 +161,17 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
                 }
                 if (cx.w.lane == 0) nids_out[r] = (uint8_t)nids;
             }
+            if (VB && acc_out) {   // column 6: accession ranks of the visited sequences, ascending (the reference's std::set<std::string> order)
+                const uint32_t* accs = (const uint32_t*)(cx.smem + cx.L.accs_off); const uint32_t nacc = id ? accs[20] : 0u;
+                if ((uint32_t)cx.w.lane < nacc) {
+                    const uint32_t mine = accs[cx.w.lane]; uint32_t rank = 0;
+                    KJ_ROLLED
+                    for (uint32_t u = 0; u < nacc; u++) rank += accs[u] < mine ? 1u : 0u;
+                    acc_out[r * KJ_MAX_MATCH_ACC + rank] = mine;
+                }
+                if (cx.w.lane == 0) nacc_out[r] = (uint8_t)nacc;
+            }
+            if (VB && frag_len_out && cx.w.lane == 0) frag_len_out[r] = id ? cx.text_len : 0u;
             cx.w.sync();
         }
     }
@@ -196,6 +210,8 @@ struct kj_ctx {
     KjDevIndex dix{};              // host copy of the descriptor (device pointers inside)
     KjDevIndex* d_ix = nullptr; KjTables* d_tables = nullptr;
     void* d_rank = nullptr; void* d_letters = nullptr; void* d_sa_tax = nullptr; void* d_seq_tax = nullptr;
+    void* d_sa_acc = nullptr; void* d_seq_acc = nullptr;
+    uint32_t* d_acc[2] = {nullptr, nullptr}; uint8_t* d_nacc[2] = {nullptr, nullptr}; char* d_frag[2] = {nullptr, nullptr}; uint32_t* d_fraglen[2] = {nullptr, nullptr}; size_t d_v2_cap = 0, d_frag_stride = 0;
     void* d_tax_parent = nullptr; void* d_tax_depth = nullptr; void* d_tax_id = nullptr; void* d_lnfact = nullptr; void* d_kmer = nullptr;
     uint64_t index_bytes = 0; uint64_t n_sa = 0; double build_ms = 0.0;
     // run state
@@ -232,7 +248,7 @@ static bool kj_use_fixed(const KjRunParams& rp) {
     const KjSmemLayout a = kj_smem_layout(rp), b = kj_smem_layout(kj_fixed_profile(rp.mode));
     return memcmp(&a, &b, sizeof a) == 0 && rp.max_len == 152 && rp.kept_cap_smem == KJ_KEPT_SMEM_FIXED;
 }
-static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid) {
+static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid, bool verbose) {
 #ifdef KJ_STAGE
     rp.stage = getenv("KJ_NO_STAGE") ? 0u : 1u;            // build with -DKJ_STAGE: bulk-copy staging of the bases (A/B; not the default, see the kernel)
 #else
@@ -245,19 +261,20 @@ static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid)
     if (const char* v = getenv("KJ_WS_LIMIT_KB")) { long x = atol(v); if (x >= 0 && x <= 227) limit = (size_t)x * 1024u; }    // tuning hook (A/B of the switch point)
     rp.ws_global = smem > limit ? 1u : 0u;
     if (rp.ws_global) { smem = head; rp.stage = 0; }
-    const int cfg = rp.mode * 2 + (int)rp.ws_global + (kj_use_fixed(rp) ? 4 : 0);
+    const int cfg = rp.mode * 2 + (int)rp.ws_global + ((!verbose && kj_use_fixed(rp)) ? 4 : 0) + (verbose ? 8 : 0);
     // The max-dynamic-shared-memory attribute belongs to the kernel instantiation on the device, not to a context: several contexts
     // (or batches with different read lengths) share it, so it is only ever raised (process-wide table), never lowered.
-    static std::mutex attr_mu; static size_t attr_set[64][16];
-    const bool fixed = kj_use_fixed(rp);
-    const int inst = rp.mode * 4 + (c->H.wide ? 2 : 0) + (int)rp.ws_global + (fixed ? 8 : 0);
+    static std::mutex attr_mu; static size_t attr_set[64][32];
+    const bool fixed = !verbose && kj_use_fixed(rp);
+    const int inst = rp.mode * 4 + (c->H.wide ? 2 : 0) + (int)rp.ws_global + (fixed ? 8 : 0) + (verbose ? 16 : 0);
     bool raise = false;
     { std::lock_guard<std::mutex> lk(attr_mu); if (c->device < 64 && smem > attr_set[c->device][inst]) { attr_set[c->device][inst] = smem; raise = true; } else if (c->device >= 64) raise = true; }
     if (!raise && smem == c->smem_bytes && c->grid > 0 && c->cfg_mode == cfg) { grid = c->grid; return KJ_OK; }
     int per_sm = 0;
-#define KJ_CFG(M, T, G, F) { if (raise) CK(cudaFuncSetAttribute(kj_classify_kernel<M, T, G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<M, T, G, F>, KJ_WARPS_PER_CTA * 32, smem)); }
-#define KJ_CFG2(M, T) { if (rp.ws_global) KJ_CFG(M, T, true, false) else if (fixed) KJ_CFG(M, T, false, true) else KJ_CFG(M, T, false, false) }
+#define KJ_CFG(M, T, G, F, V) { if (raise) CK(cudaFuncSetAttribute(kj_classify_kernel<M, T, G, F, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<M, T, G, F, V>, KJ_WARPS_PER_CTA * 32, smem)); }
+#define KJ_CFG2(M, T) { if (verbose) { if (rp.ws_global) KJ_CFG(M, T, true, false, true) else KJ_CFG(M, T, false, false, true) } \
+                        else if (rp.ws_global) KJ_CFG(M, T, true, false, false) else if (fixed) KJ_CFG(M, T, false, true, false) else KJ_CFG(M, T, false, false, false) }
     if (rp.mode == 0) { if (c->H.wide) KJ_CFG2(0, uint64_t) else KJ_CFG2(0, uint32_t) }
     else { if (c->H.wide) KJ_CFG2(1, uint64_t) else KJ_CFG2(1, uint32_t) }
 #undef KJ_CFG2
@@ -309,6 +326,7 @@ static int upload_descriptor(kj_ctx* c) {
     D.rank = (const uint64_t*)c->d_rank; D.nb = H.nb; D.letters = (const uint64_t*)c->d_letters; D.bwtlen = H.bwtlen; D.alen = H.alen;
     for (int a = 0; a <= H.alen; a++) D.C[a] = H.C[a];
     for (int a = 0; a < H.alen; a++) D.rank_base[a] = D.rank + (uint64_t)a * H.nb * kj_rank_words(H.wide);
+    D.sa_acc = (const uint32_t*)c->d_sa_acc; D.seq_acc = (const uint32_t*)c->d_seq_acc;
     D.sa_tax = (const uint32_t*)c->d_sa_tax; D.seq_tax = (const uint32_t*)c->d_seq_tax; D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
     D.n_sa = c->n_sa; D.nseq = H.nseq;
     D.tax_parent = (const uint32_t*)c->d_tax_parent; D.tax_depth = (const uint32_t*)c->d_tax_depth; D.tax_id = (const uint64_t*)c->d_tax_id; D.n_tax = (uint32_t)H.tax_id.size();
@@ -348,6 +366,7 @@ template <class Fill> static int create_ctx(kj_ctx** out, int device, const kj_p
     // one guard entry: the reference's header counts one sampled row less than kaiju-mkbwt writes (suffixArray.c:160 vs 206-216), so the last
     // sampled row of an index has no entry; the reference reads past its array there, the device reads "no taxon"
     c->n_sa = H.sa_tax.size(); H.sa_tax.push_back(KJ_TAX_BAD);
+    if (!H.seq_acc.empty()) { H.sa_acc.push_back(0xffffffffu); if ((rc = upload(H.sa_acc, &c->d_sa_acc, tot)) || (rc = upload(H.seq_acc, &c->d_seq_acc, tot))) return rc; }
     if ((rc = upload(H.rank, &c->d_rank, tot)) || (rc = upload(H.letters, &c->d_letters, tot)) || (rc = upload(H.sa_tax, &c->d_sa_tax, tot)) ||
         (rc = upload(H.seq_tax, &c->d_seq_tax, tot)) || (rc = upload_small(c, tot)) || (rc = (H.wide ? upload(H.kmer, &c->d_kmer, tot) : upload(H.kmer32, &c->d_kmer, tot)))) return rc;
     // host copies of the big arrays are no longer needed
@@ -427,7 +446,8 @@ extern "C" void kj_destroy(kj_ctx* c) {
     void* ptrs[] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_tax_parent, c->d_tax_depth, c->d_tax_id, c->d_lnfact, c->d_kmer, c->d_tables, c->d_ix,
                     c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evbreaks, c->d_ws, c->d_counts, c->d_counts_pending, c->d_quirk, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
                     c->d_seq[0][0], c->d_seq[0][1], c->d_seq[1][0], c->d_seq[1][1], c->d_off[0][0], c->d_off[0][1], c->d_off[1][0], c->d_off[1][1],
-                    c->d_ids[0], c->d_ids[1], c->d_nids[0], c->d_nids[1]};
+                    c->d_ids[0], c->d_ids[1], c->d_nids[0], c->d_nids[1], c->d_sa_acc, c->d_seq_acc, c->d_acc[0], c->d_acc[1], c->d_nacc[0], c->d_nacc[1],
+                    c->d_frag[0], c->d_frag[1], c->d_fraglen[0], c->d_fraglen[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int s = 0; s < 2; s++) if (c->stream[s]) cudaStreamDestroy(c->stream[s]);
     if (c->ev_a) cudaEventDestroy(c->ev_a); if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -437,7 +457,8 @@ extern "C" void kj_destroy(kj_ctx* c) {
 // one launch over reads [0,n) whose sequences/offsets are resident on the device
 static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_off1, const uint8_t* d_seq2, const uint64_t* d_off2, uint64_t base1, uint64_t base2,
                   uint64_t n, uint32_t max1, uint32_t max2, uint64_t* d_tax, uint32_t* d_best, cudaStream_t st, bool time_it,
-                  uint64_t* d_ids = nullptr, uint8_t* d_nids = nullptr, unsigned long long* d_count_dst = nullptr, uint32_t* d_compact = nullptr) {
+                  uint64_t* d_ids = nullptr, uint8_t* d_nids = nullptr, unsigned long long* d_count_dst = nullptr, uint32_t* d_compact = nullptr,
+                  uint32_t* d_acc = nullptr, uint8_t* d_nacc = nullptr, char* d_frag = nullptr, uint32_t frag_stride = 0, uint32_t* d_fraglen = nullptr) {
     if (c->params.input_is_protein) {
         if (d_seq2) { kj_err() = "protein input only supports one input (kaiju.cpp:201)"; return KJ_ERR_ARG; }
         if (max1 > KJ_MAX_PROTEIN_LEN) { kj_err() = "protein read longer than KJ_MAX_PROTEIN_LEN (5461 residues) is not supported"; return KJ_ERR_UNSUPPORTED; }
@@ -445,19 +466,21 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     KjRunParams rp; kj_fill_run_params(c->params, std::max(max1, max2), rp);
     rp.ev_breaks = c->d_evbreaks; rp.n_ev_breaks = c->n_evbreaks;
     rp.variant_cap *= c->variant_boost;
-    size_t smem; int grid; int rc = configure_launch(c, rp, smem, grid); if (rc) return rc;
+    const bool verbose = d_ids || d_acc || d_frag;
+    size_t smem; int grid; int rc = configure_launch(c, rp, smem, grid, verbose); if (rc) return rc;
     rc = ensure_scratch(c, rp, grid); if (rc) return rc;
     c->grid = grid; c->smem_bytes = smem;
     CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
     if (time_it) CK(cudaEventRecord(c->ev_a, st));
     const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
     const KjSmemLayout lay = kj_smem_layout(rp);
-    const bool fixed = kj_use_fixed(rp);
-#define KJ_LAUNCH(M, T) if (rp.ws_global) KJ_LAUNCH3(M, T, true, false); else if (fixed) KJ_LAUNCH3(M, T, false, true); else KJ_LAUNCH3(M, T, false, false)
-#define KJ_LAUNCH3(M, T, G, F) kj_classify_kernel<M, T, G, F><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, lay, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, d_compact, \
+    const bool fixed = !verbose && kj_use_fixed(rp);
+#define KJ_LAUNCH(M, T) if (verbose) { if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, true); else KJ_LAUNCH3(M, T, false, false, true); } \
+                        else if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, false); else if (fixed) KJ_LAUNCH3(M, T, false, true, false); else KJ_LAUNCH3(M, T, false, false, false)
+#define KJ_LAUNCH3(M, T, G, F, V) kj_classify_kernel<M, T, G, F, V><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, lay, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, d_compact, \
             c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
             c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), \
-            rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err)
+            rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err, d_acc, d_nacc, d_frag, frag_stride, d_fraglen)
     if (rp.mode == 0) { if (c->H.wide) KJ_LAUNCH(0, uint64_t); else KJ_LAUNCH(0, uint32_t); }
     else { if (c->H.wide) KJ_LAUNCH(1, uint64_t); else KJ_LAUNCH(1, uint32_t); }
 #undef KJ_LAUNCH
@@ -481,7 +504,7 @@ static int check_err_flag(kj_ctx* c) {
         CK(cudaMemset(c->d_err, 0, sizeof e));
         // flag 4 = the Greedy variant ring of some read was full: the next launch gets a ring 4x as large (the reference's heap is unbounded)
         if ((e & 4u) && c->variant_boost < 256u) c->variant_boost *= 4u;
-        char b[160]; snprintf(b, sizeof b, "per-read work queue overflow on the device (flags 0x%x)%s", e, (e & 4u) ? "; the variant ring was enlarged, call again" : ""); kj_err() = b;
+        char b[160]; snprintf(b, sizeof b, "per-read work queue overflow on the device (flags 0x%x)%s", e, (e & 4u) ? "; the variant ring was enlarged, call again" : (e & 128u) ? "; the fragment strings of a read exceed frag_stride" : ""); kj_err() = b;
         return KJ_ERR_OVERFLOW;
     }
     return KJ_OK;
@@ -527,7 +550,8 @@ static int ensure_staging(kj_ctx* c, int slot, size_t bytes1, size_t bytes2, siz
 }
 
 static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
-                         uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out, uint32_t* d_compact = nullptr) {
+                         uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out, uint32_t* d_compact = nullptr,
+                         uint32_t* acc_out = nullptr, uint8_t* nacc_out = nullptr, char* frag_out = nullptr, uint32_t frag_stride = 0, uint32_t* frag_len_out = nullptr) {
     if (!c || !seq1 || !off1 || !taxon_out || (seq2 && !off2) || ((ids_out == nullptr) != (nids_out == nullptr))) { kj_err() = "kj_classify: null argument"; return KJ_ERR_ARG; }
     if (n == 0) return KJ_OK;
     CK(cudaSetDevice(c->device));
@@ -553,6 +577,19 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
             CK(cudaMalloc((void**)&c->d_ids[s], c->d_reads_cap * KJ_MAX_IDS * sizeof(uint64_t))); CK(cudaMalloc((void**)&c->d_nids[s], c->d_reads_cap));
         }
         c->d_ids_cap = c->d_reads_cap;
+    }
+    if (acc_out || frag_out) {
+        if (acc_out && !c->d_sa_acc) { kj_err() = "kj_classify_verbose2: the context was created without kj_index_view.seq_accession"; return KJ_ERR_UNSUPPORTED; }
+        if ((acc_out && !nacc_out) || (frag_out && (!frag_len_out || frag_stride < 16))) { kj_err() = "kj_classify_verbose2: null argument"; return KJ_ERR_ARG; }
+        if (c->d_v2_cap < c->d_reads_cap || c->d_frag_stride < frag_stride) {
+            for (int s = 0; s < 2; s++) {
+                if (c->d_acc[s]) cudaFree(c->d_acc[s]); if (c->d_nacc[s]) cudaFree(c->d_nacc[s]); if (c->d_frag[s]) cudaFree(c->d_frag[s]); if (c->d_fraglen[s]) cudaFree(c->d_fraglen[s]);
+                c->d_acc[s] = nullptr; c->d_nacc[s] = nullptr; c->d_frag[s] = nullptr; c->d_fraglen[s] = nullptr;
+                CK(cudaMalloc((void**)&c->d_acc[s], c->d_reads_cap * KJ_MAX_MATCH_ACC * 4)); CK(cudaMalloc((void**)&c->d_nacc[s], c->d_reads_cap));
+                CK(cudaMalloc((void**)&c->d_frag[s], c->d_reads_cap * (size_t)frag_stride)); CK(cudaMalloc((void**)&c->d_fraglen[s], c->d_reads_cap * 4));
+            }
+            c->d_v2_cap = c->d_reads_cap; c->d_frag_stride = frag_stride;
+        }
     }
     // software pipeline over chunks: H2D + kernel + D2H of chunk k on stream k&1 overlap with chunk k+1
     const bool trace = getenv("KJ_TRACE") != nullptr;            // developer hook: per-chunk timeline on stderr
@@ -580,7 +617,8 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
         }
         if (trace) { tr.back().cnt = cnt; cudaEventRecord(tr.back().e[1], st); }
         rc = launch(c, s, c->d_seq[s][0], c->d_off[s][0], paired ? c->d_seq[s][1] : nullptr, paired ? c->d_off[s][1] : nullptr, b1, b2, cnt, max1, max2,
-                    c->d_tax[s], best_out ? c->d_best[s] : nullptr, st, true, ids_out ? c->d_ids[s] : nullptr, ids_out ? c->d_nids[s] : nullptr, c->d_counts_pending, d_compact ? d_compact + start : nullptr);
+                    c->d_tax[s], best_out ? c->d_best[s] : nullptr, st, true, ids_out ? c->d_ids[s] : nullptr, ids_out ? c->d_nids[s] : nullptr, c->d_counts_pending, d_compact ? d_compact + start : nullptr,
+                    acc_out ? c->d_acc[s] : nullptr, acc_out ? c->d_nacc[s] : nullptr, frag_out ? c->d_frag[s] : nullptr, frag_stride, frag_out ? c->d_fraglen[s] : nullptr);
         if (rc) return rc;
         if (trace) cudaEventRecord(tr.back().e[2], st);
         CK(cudaMemcpyAsync(taxon_out + start, c->d_tax[s], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -588,6 +626,14 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
         if (ids_out) {
             CK(cudaMemcpyAsync(ids_out + start * KJ_MAX_IDS, c->d_ids[s], cnt * KJ_MAX_IDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(nids_out + start, c->d_nids[s], cnt, cudaMemcpyDeviceToHost, st));
+        }
+        if (acc_out) {
+            CK(cudaMemcpyAsync(acc_out + start * KJ_MAX_MATCH_ACC, c->d_acc[s], cnt * KJ_MAX_MATCH_ACC * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(nacc_out + start, c->d_nacc[s], cnt, cudaMemcpyDeviceToHost, st));
+        }
+        if (frag_out) {
+            CK(cudaMemcpyAsync(frag_out + start * (size_t)frag_stride, c->d_frag[s], cnt * (size_t)frag_stride, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(frag_len_out + start, c->d_fraglen[s], cnt * 4, cudaMemcpyDeviceToHost, st));
         }
     }
     if (trace && !tr.empty()) cudaEventRecord(tr.back().e[3], c->stream[(tr.size() - 1) & 1]);
@@ -608,10 +654,11 @@ static int classify_host(kj_ctx* c, const char* seq1, const uint64_t* off1, cons
 
 // A full Greedy variant ring (flag 4) enlarges the ring for the next launch: repeat the call until it fits (bounded).
 static int classify_host_retry(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
-                               uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out, uint32_t* d_compact = nullptr) {
+                               uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out, uint32_t* d_compact = nullptr,
+                               uint32_t* acc_out = nullptr, uint8_t* nacc_out = nullptr, char* frag_out = nullptr, uint32_t frag_stride = 0, uint32_t* frag_len_out = nullptr) {
     for (;;) {
         const uint32_t boost = c ? c->variant_boost : 0;
-        int rc = classify_host(c, seq1, off1, seq2, off2, n, taxon_out, best_out, ids_out, nids_out, d_compact);
+        int rc = classify_host(c, seq1, off1, seq2, off2, n, taxon_out, best_out, ids_out, nids_out, d_compact, acc_out, nacc_out, frag_out, frag_stride, frag_len_out);
         if (rc != KJ_ERR_OVERFLOW || !c || c->variant_boost == boost) return rc;
     }
 }
@@ -648,6 +695,11 @@ extern "C" int kj_classify_verbose(kj_ctx* c, const char* seq1, const uint64_t* 
     return classify_host_retry(c, seq1, off1, seq2, off2, n, taxon_out, best_out, ids_out, nids_out);
 }
 
+extern "C" int kj_classify_verbose2(kj_ctx* c, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n, uint64_t* taxon_out, uint32_t* best_out,
+                                    uint64_t* ids_out, uint8_t* nids_out, uint32_t* acc_out, uint8_t* nacc_out, char* frag_out, uint32_t frag_stride, uint32_t* frag_len_out) {
+    if (!ids_out || !nids_out || !best_out) { kj_err() = "kj_classify_verbose2: null argument"; return KJ_ERR_ARG; }
+    return classify_host_retry(c, seq1, off1, seq2, off2, n, taxon_out, best_out, ids_out, nids_out, nullptr, acc_out, nacc_out, frag_out, frag_stride, frag_len_out);
+}
 extern "C" uint64_t kj_kernel_launches(const kj_ctx* c) { return c ? c->launches : 0; }
 extern "C" uint64_t kj_index_bytes(const kj_ctx* c) { return c ? c->index_bytes : 0; }
 extern "C" double kj_last_kernel_ms(const kj_ctx* c) {

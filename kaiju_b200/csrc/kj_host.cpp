@@ -54,6 +54,14 @@ extern "C" int kj_fmi_load(const char* path, kj_fmi** out) {
         uint8_t l = r.get<uint8_t>(); std::string& s = f->ids[(size_t)i]; s.resize(l); r.bytes(l ? &s[0] : nullptr, l);
         f->seq_taxon[(size_t)i] = taxon_of_name(s);
     }
+    {   // accessions (ConsumerThread.cpp:809-823): the name up to its last '_'; ranks in lexicographic order of the distinct strings
+        std::vector<std::string> acc; acc.reserve((size_t)f->nseq);
+        for (const std::string& s : f->ids) { const size_t u = s.rfind('_'); if (u != std::string::npos) acc.push_back(s.substr(0, u)); }
+        std::sort(acc.begin(), acc.end()); acc.erase(std::unique(acc.begin(), acc.end()), acc.end());
+        f->acc_names.swap(acc); f->seq_acc.assign((size_t)f->nseq, 0xffffffffu);
+        for (int32_t i = 0; i < f->nseq; i++) { const std::string& s = f->ids[(size_t)i]; const size_t u = s.rfind('_');
+            if (u != std::string::npos) f->seq_acc[(size_t)i] = (uint32_t)(std::lower_bound(f->acc_names.begin(), f->acc_names.end(), s.substr(0, u)) - f->acc_names.begin()); }
+    }
     r.skip((int64_t)f->nseq * 4); r.skip((int64_t)f->nseq * 8);          // seqTermOrder, seqlengths: not needed for classification
     f->sa.resize((size_t)(f->ncheck * f->nbytes)); r.bytes(f->sa.data(), f->sa.size());
     int32_t alen2 = r.get<int32_t>(); f->bwtlen = r.get<int64_t>(); f->N1 = r.get<int32_t>(); f->N2 = r.get<int32_t>();
@@ -68,9 +76,10 @@ extern "C" int kj_fmi_load(const char* path, kj_fmi** out) {
 extern "C" void kj_fmi_view(const kj_fmi* f, kj_index_view* v) {
     v->alen = f->alen; v->alphabet = f->alphabet.c_str(); v->bwtlen = f->bwtlen; v->bwt = f->bwt.data(); v->startLcode = f->startLcode.data();
     v->db_len = f->len; v->nseq = f->nseq; v->ncheck = f->ncheck; v->chpt_exp = f->chpt_exp; v->nbytes = f->nbytes; v->pbits = f->pbits;
-    v->sa = f->sa.data(); v->seq_taxon = f->seq_taxon.data();
+    v->sa = f->sa.data(); v->seq_taxon = f->seq_taxon.data(); v->seq_accession = f->seq_acc.empty() ? nullptr : f->seq_acc.data();
 }
 extern "C" void kj_fmi_free(kj_fmi* f) { delete f; }
+extern "C" const char* kj_fmi_accession(const kj_fmi* f, uint32_t rank) { return (f && rank < f->acc_names.size()) ? f->acc_names[rank].c_str() : nullptr; }
 extern "C" const char* kj_fmi_seq_name(const kj_fmi* f, int32_t i) { return (f && i >= 0 && i < f->nseq) ? f->ids[(size_t)i].c_str() : nullptr; }
 
 // nodes.dmp (parseNodesDmp, util.cpp:79-99): first integer = node, next integer = parent; bad lines skipped
@@ -123,6 +132,7 @@ int build_tables(const std::string& alphabet, KjTables& tb) {
     uint8_t trans[256]; memset(trans, (uint8_t)(alen - 1), sizeof trans);
     for (int a = 0; a < alen; a++) trans[(uint8_t)alphabet[(size_t)a]] = (uint8_t)a;
     for (int c = 0; c < 64; c++) tb.codon_aa[c] = kCode[c] == '*' ? 0 : trans[(uint8_t)kCode[c]];
+    for (int a = 0; a < alen && a < KJ_MAX_ALEN; a++) tb.letters[a] = alphabet[(size_t)a];
     for (const char* v = "ACDEFGHIKLMNPQRSTVWY"; *v; v++) tb.aa_index[*v - 'A'] = trans[(uint8_t)*v];     // the valid set of a protein read (ConsumerThread.cpp:664)
     int ai_of[256]; for (int i = 0; i < 256; i++) ai_of[i] = -1;
     for (int i = 0; i < 20; i++) ai_of[(uint8_t)kAaOrder[i]] = i;
@@ -247,6 +257,8 @@ int kj_build_host_meta(const kj_index_view& v, const kj_taxonomy_view& t, uint32
     // ---- sequence -> compact taxon; sampled SA -> compact taxon
     H.seq_tax.resize((size_t)v.nseq * copies);
     for (int32_t i = 0; i < v.nseq; i++) { const uint32_t x = v.seq_taxon[i] == UINT64_MAX ? KJ_TAX_BAD : index_of(v.seq_taxon[i]); for (uint32_t c = 0; c < copies; c++) H.seq_tax[(size_t)i * copies + c] = x; }
+    H.seq_acc.clear(); H.sa_acc.clear();
+    if (v.seq_accession && copies == 1) H.seq_acc.assign(v.seq_accession, v.seq_accession + v.nseq);
     H.sa_exp = v.chpt_exp; H.sa_check = (1ull << v.chpt_exp) - 1ull;                         // suffixArray_set_masks (suffixArray.c:34-37)
     H.sa_bias = ((int64_t)((int64_t)H.nseq - 1) >> v.chpt_exp) + 1;                          // bwt.c:115-116
     // ---- ln(n!) exactly as the reference's literals (blast_seg.c:53-1306 are "%.6f" prints of lgamma)
@@ -301,7 +313,7 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
         for (auto& x : th) x.join();
     }
 
-    H.sa_tax.resize((size_t)v.ncheck);
+    H.sa_tax.resize((size_t)v.ncheck); if (!H.seq_acc.empty()) H.sa_acc.resize((size_t)v.ncheck);
     {
         std::vector<std::thread> th; const uint64_t nc = (uint64_t)v.ncheck; std::atomic<bool> bad(false);
         for (unsigned tI = 0; tI < nthr; tI++) th.emplace_back([&, tI] {
@@ -311,6 +323,7 @@ int kj_build_host_index(const kj_index_view& v, const kj_taxonomy_view& t, KjHos
                 uint64_t seq = val >> v.pbits;
                 if (seq >= (uint64_t)v.nseq) { bad = true; continue; }
                 H.sa_tax[e] = H.seq_tax[seq];
+                if (!H.seq_acc.empty()) H.sa_acc[e] = H.seq_acc[seq];
             }
         });
         for (auto& x : th) x.join();
@@ -411,7 +424,7 @@ void kj_fill_run_params(const kj_params& p, uint32_t max_len, KjRunParams& rp) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 const char kNativeMagic[8] = {'K', 'J', 'B', '2', '0', '0', 'I', 'X'};
-const uint32_t kNativeVersion = 4;
+const uint32_t kNativeVersion = 5;
 struct NativeHeader {
     uint32_t version, sizeof_tables, sizeof_rank, alen;
     uint64_t nb, bwtlen, C[KJ_MAX_ALEN + 1], sa_check; int64_t sa_bias; int32_t sa_exp; uint32_t nseq, n_present; int32_t kmer_k, wide, pad;

@@ -12,6 +12,7 @@ struct kj_fmi {
     int64_t len = 0; int32_t nseq = 0, alen = 0; std::string alphabet;
     int64_t sa_len = 0, ncheck = 0; int32_t chpt_exp = 0, nbytes = 0, sbits = 0, pbits = 0; int64_t mask = 0, check = 0;
     std::vector<std::string> ids; std::vector<uint64_t> seq_taxon; std::vector<uint8_t> sa;
+    std::vector<uint32_t> seq_acc; std::vector<std::string> acc_names;       // accession rank per sequence (0xffffffff = none), distinct accessions sorted
     int64_t bwtlen = 0; int32_t N1 = 0, N2 = 0; std::vector<uint8_t> bwt; std::vector<int32_t> startLcode;
 };
 struct kj_nodes { std::vector<uint64_t> node, parent; };
@@ -22,6 +23,7 @@ struct KjHostIndex {
     std::vector<uint64_t> letters;
     uint64_t bwtlen = 0; int alen = 0; uint64_t C[KJ_MAX_ALEN + 1] = {0};
     std::vector<uint32_t> sa_tax, seq_tax;
+    std::vector<uint32_t> sa_acc, seq_acc;      // accession rank per sampled suffix / per sequence (only when the view carries seq_accession)
     uint64_t sa_check = 0; int sa_exp = 0; int64_t sa_bias = 0; uint32_t nseq = 0;
     std::vector<uint32_t> tax_parent, tax_depth; std::vector<uint64_t> tax_id; uint32_t n_present = 0;   // tax_id = [ids of nodes.dmp, ascending | DB taxa absent from it, ascending]
     std::vector<double> lnfact;

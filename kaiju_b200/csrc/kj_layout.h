@@ -52,6 +52,7 @@ struct KjTables {
     uint8_t subst[KJ_MAX_ALEN][20];  // substitution try-order per residue, alphabet indices (ConsumerThread.cpp:10-30)
     int32_t seg_logfix[KJ_SEG_WINDOW + 1];  // round(2^24 log2(12/c)) : entropy of a 12-window in fixed point
     int32_t seg_locut_fix, seg_hicut_fix;   // 12*2.2*2^24, 12*2.5*2^24 (margins checked on host against FP64)
+    char letters[KJ_MAX_ALEN];       // alphabet index -> letter (fragment strings of the verbose output)
     uint8_t aa_index[32];            // protein input: upper-case letter - 'A' -> alphabet index, 0 = splits the read (ConsumerThread.cpp:664)
 };
 
@@ -62,6 +63,7 @@ struct KjDevIndex {
     uint64_t bwtlen; int alen;
     uint64_t C[KJ_MAX_ALEN + 1];                // C[c] = first SA row of letter c; C[alen] = bwtlen
     const uint32_t* sa_tax; const uint32_t* seq_tax;
+    const uint32_t* sa_acc; const uint32_t* seq_acc;     // accession rank per sampled suffix / sequence (NULL unless the index view carried seq_accession)
     uint64_t sa_check; int sa_exp; int64_t sa_bias; uint64_t n_sa; uint32_t nseq;
     const uint32_t* tax_parent; const uint32_t* tax_depth; const uint64_t* tax_id; uint32_t n_tax;
     const double* lnfact; int n_lnfact;

@@ -120,18 +120,20 @@ static KjEmuStats g_emu_total; static std::atomic<int> g_emu_lock(0);
 struct EmuCtx {
     KjHostIndex H; KjDevIndex D; kj_params P; std::vector<double> evbreaks;
 };
-struct ItemArg { uint32_t nids; uint32_t ids[24]; EmuCtx* c; KjRunParams* rp; uint8_t* smem; KjKept* spill; void* gscratch; uint32_t* err; const uint8_t* s1; int n1; const uint8_t* s2; int n2; bool paired; uint32_t tax[32]; uint32_t best[32]; };
+struct ItemArg { char* text; uint32_t text_cap, text_len; bool want_acc; uint32_t nacc; uint32_t accs[24]; uint32_t nids; uint32_t ids[24]; EmuCtx* c; KjRunParams* rp; uint8_t* smem; KjKept* spill; void* gscratch; uint32_t* err; const uint8_t* s1; int n1; const uint8_t* s2; int n2; bool paired; uint32_t tax[32]; uint32_t best[32]; };
 
 static void item_body(kjemu::Sched* s, int lane, void* a) {
     ItemArg* A = (ItemArg*)a;
     KjWarpCtx cx; cx.w.lane = lane; cx.w.s = s; cx.ix = &A->c->D; cx.rp = A->rp; cx.tb = &A->c->H.tables; cx.smem = A->smem;
     cx.L = kj_smem_layout(*A->rp); cx.spill = A->spill; cx.gscratch = A->gscratch; cx.err = A->err;
+    cx.text = A->text; cx.text_cap = A->text_cap; cx.text_len = 0; cx.want_acc = A->want_acc;
     uint32_t best = 0;
     const bool wide = A->c->D.wide != 0;
     uint32_t t = A->rp->mode == 0 ? (wide ? kj_classify_item<0, uint64_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best) : kj_classify_item<0, uint32_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best))
         : wide ? kj_classify_item<1, uint64_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best) : kj_classify_item<1, uint32_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best);
     A->tax[lane] = t; A->best[lane] = best;
-    if (lane == 0) { A->nids = cx.nids; const uint32_t* ids = (const uint32_t*)(cx.smem + cx.L.ids_off); for (uint32_t u = 0; u < cx.nids && u < 24; u++) A->ids[u] = ids[u]; }
+    if (lane == 0) { A->nids = cx.nids; const uint32_t* ids = (const uint32_t*)(cx.smem + cx.L.ids_off); for (uint32_t u = 0; u < cx.nids && u < 24; u++) A->ids[u] = ids[u];
+                     A->text_len = cx.text_len; const uint32_t* accs = (const uint32_t*)(cx.smem + cx.L.accs_off); A->nacc = (A->want_acc && t != KJ_TAX_BAD) ? accs[20] : 0; for (uint32_t u = 0; u < A->nacc && u < 20; u++) A->accs[u] = accs[u]; }
 }
 
 extern "C" {
@@ -156,7 +158,7 @@ void* kjemu_create(const char* fmi_path, const char* nodes_path, const kj_params
     D.rank = H.rank.data(); D.nb = H.nb; D.letters = H.letters.data(); D.bwtlen = H.bwtlen; D.alen = H.alen;
     for (int a = 0; a <= H.alen; a++) D.C[a] = H.C[a];
     for (int a = 0; a < H.alen; a++) D.rank_base[a] = D.rank + (uint64_t)a * H.nb * kj_rank_words(H.wide);
-    D.sa_tax = H.sa_tax.data(); D.seq_tax = H.seq_tax.data(); D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
+    D.sa_tax = H.sa_tax.data(); D.seq_tax = H.seq_tax.data(); D.sa_acc = H.sa_acc.empty() ? nullptr : H.sa_acc.data(); D.seq_acc = H.seq_acc.empty() ? nullptr : H.seq_acc.data(); D.sa_check = H.sa_check; D.sa_exp = H.sa_exp; D.sa_bias = H.sa_bias;
     D.n_sa = H.sa_tax.size(); D.nseq = H.nseq;
     D.tax_parent = H.tax_parent.data(); D.tax_depth = H.tax_depth.data(); D.tax_id = H.tax_id.data(); D.n_tax = (uint32_t)H.tax_id.size();
     D.lnfact = H.lnfact.data(); D.n_lnfact = (int)H.lnfact.size(); D.kmer = H.kmer_k ? (H.wide ? (const void*)H.kmer.data() : (const void*)H.kmer32.data()) : nullptr; D.kmer_k = H.kmer_k; D.wide = H.wide; D.tables = &H.tables; D.quirk_lo = H.quirk_lo; D.quirk_d = H.quirk_d; D.mono = (H.quirk_lo == ~0ull && !getenv("KJ_EMU_NOMONO")) ? 1 : 0;
@@ -195,13 +197,17 @@ int kjemu_stats(unsigned long long* out, int cap, int reset) {
 }
 int kjemu_native_read(const char* path) { KjHostIndex H; return kj_host_index_read(path, H); }
 
+int kjemu_classify_v2(void* h, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n, uint64_t* taxon_out, uint32_t* best_out,
+                      uint64_t* ids_out, uint8_t* nids_out, uint32_t* acc_out, uint8_t* nacc_out, char* frag_out, uint32_t frag_stride, uint32_t* frag_len_out, int nthreads);
 int kjemu_classify_ids(void* h, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
-                       uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out, int nthreads);
+                       uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out, int nthreads) {
+    return kjemu_classify_v2(h, seq1, off1, seq2, off2, n, taxon_out, best_out, ids_out, nids_out, nullptr, nullptr, nullptr, 0, nullptr, nthreads); }
 int kjemu_classify(void* h, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
                    uint64_t* taxon_out, uint32_t* best_out, int nthreads) { return kjemu_classify_ids(h, seq1, off1, seq2, off2, n, taxon_out, best_out, nullptr, nullptr, nthreads); }
 // ids_out[i*21 .. +nids_out[i]): the match-id set of read i, ascending (what kj_classify_verbose delivers)
-int kjemu_classify_ids(void* h, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n,
-                       uint64_t* taxon_out, uint32_t* best_out, uint64_t* ids_out, uint8_t* nids_out, int nthreads) {
+// all verbose outputs of kj_classify_verbose2 (accession ranks ascending, fragment strings)
+int kjemu_classify_v2(void* h, const char* seq1, const uint64_t* off1, const char* seq2, const uint64_t* off2, uint64_t n, uint64_t* taxon_out, uint32_t* best_out,
+                      uint64_t* ids_out, uint8_t* nids_out, uint32_t* acc_out, uint8_t* nacc_out, char* frag_out, uint32_t frag_stride, uint32_t* frag_len_out, int nthreads) {
     EmuCtx* c = (EmuCtx*)h; bool paired = seq2 != nullptr;
     uint32_t max1 = 0, max2 = 0;
     for (uint64_t i = 0; i < n; i++) { max1 = std::max<uint32_t>(max1, (uint32_t)(off1[i + 1] - off1[i])); if (paired) max2 = std::max<uint32_t>(max2, (uint32_t)(off2[i + 1] - off2[i])); }
@@ -222,6 +228,7 @@ int kjemu_classify_ids(void* h, const char* seq1, const uint64_t* off1, const ch
             ItemArg A; A.c = c; A.rp = &rp; A.smem = smem.data(); A.spill = spill.data(); A.gscratch = gscratch.data(); A.err = &err;
             A.s1 = (const uint8_t*)seq1 + off1[i]; A.n1 = (int)(off1[i + 1] - off1[i]);
             A.s2 = paired ? (const uint8_t*)seq2 + off2[i] : nullptr; A.n2 = paired ? (int)(off2[i + 1] - off2[i]) : 0; A.paired = paired;
+            A.text = frag_out ? frag_out + i * (size_t)frag_stride : nullptr; A.text_cap = frag_stride; A.text_len = 0; A.want_acc = acc_out != nullptr && c->D.sa_acc != nullptr; A.nacc = 0;
             memset(smem.data(), 0xA5, smem.size());      // poison: the kernel must not rely on zeroed shared memory
             kjemu::run_warp(s, item_body, &A);
             // the red zones between the work-space arrays must be untouched (a stray store would silently corrupt a neighbour on the GPU)
@@ -231,6 +238,8 @@ int kjemu_classify_ids(void* h, const char* seq1, const uint64_t* off1, const ch
             for (int l = 1; l < 32; l++) if (A.tax[l] != A.tax[0] || A.best[l] != A.best[0]) { fprintf(stderr, "kjemu: non-uniform result at read %llu\n", (unsigned long long)i); abort(); }
             taxon_out[i] = A.tax[0] == KJ_TAX_BAD ? 0 : c->H.tax_id[A.tax[0]];
             if (best_out) best_out[i] = taxon_out[i] ? A.best[0] : 0;
+            if (acc_out) { std::vector<uint32_t> v(A.accs, A.accs + std::min<uint32_t>(A.nacc, 20)); std::sort(v.begin(), v.end()); for (size_t u = 0; u < v.size(); u++) acc_out[i * 20 + u] = v[u]; nacc_out[i] = (uint8_t)v.size(); }
+            if (frag_len_out) frag_len_out[i] = taxon_out[i] ? A.text_len : 0;
             if (ids_out) { std::vector<uint64_t> v; if (taxon_out[i]) for (uint32_t u = 0; u < A.nids && u < 24; u++) v.push_back(c->H.tax_id[A.ids[u]]); std::sort(v.begin(), v.end());
                            for (size_t u = 0; u < v.size() && u < 21; u++) ids_out[i * 21 + u] = v[u]; nids_out[i] = (uint8_t)std::min<size_t>(v.size(), 21); }
         }

@@ -43,5 +43,23 @@ def main():
         print(cfg, "x/p outputs written; kaijup classified", out.count(b"\nC\t") + out.startswith(b"C\t"), "of 1200")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--v7" not in sys.argv:
     main()
+
+
+def main_v7():
+    """all seven columns of `kaiju -v` (raw reference output) for a few configurations: expected_v7_<cfg>_<tag>.tsv.gz"""
+    tmp = "/tmp/kj_xp"; os.makedirs(tmp, exist_ok=True)
+    fmi = os.path.join(HERE, "db.fmi"); nodes = os.path.join(HERE, "nodes.dmp")
+    inputs = {"se100": ["-i", plain(HERE + "/se100.fq.gz", tmp + "/se.fq")],
+              "pe150": ["-i", plain(HERE + "/pe150_1.fq.gz", tmp + "/a.fq"), "-j", plain(HERE + "/pe150_2.fq.gz", tmp + "/b.fq")]}
+    for cfg in ("mem_default", "mem_m5_noseg", "greedy_default", "greedy_e5_s40"):
+        for tag, inp in inputs.items():
+            out = subprocess.run([os.path.join(REF_DIR, "kaiju"), "-t", nodes, "-f", fmi, "-z", "1", "-v"] + inp + XP_CONFIGS[cfg], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+            with gzip.open(os.path.join(HERE, "expected_v7_%s_%s.tsv.gz" % (cfg, tag)), "wb") as g:
+                g.write(out)
+    print("7-column outputs written")
+
+
+if __name__ == "__main__" and "--v7" in sys.argv:
+    main_v7()

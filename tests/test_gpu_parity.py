@@ -166,7 +166,7 @@ def test_cli_matches_reference_output_format(kb, golden, tmp_path):
         for ln, nm, t, b, ids in zip(lines, names, etax, ebest, eids):
             p = ln.split("\t")
             if t:      # columns 1-5 of the reference's -v output (ids: std::set order, each followed by a comma)
-                assert p == ["C", nm, str(int(t)), str(int(b)), "".join("%d," % x for x in sorted(ids))], (ln, nm, t, b, ids)
+                assert p[:5] == ["C", nm, str(int(t)), str(int(b)), "".join("%d," % x for x in sorted(ids))] and len(p) == 7, (ln, nm, t, b, ids)
             else:
                 assert p == ["U", nm, "0"], ln
     # error paths: -p with a second input file (kaiju.cpp:201), missing arguments: usage + non-zero exit
@@ -268,7 +268,7 @@ def test_cli_protein_and_verbose_columns(kb, golden, tmp_path):
     for i, line in enumerate(out):
         t, b, ids = orc.classify_one(P, s[int(o[i]):int(o[i + 1])].tobytes())
         exp = "C\tq%d\t%d\t%d\t%s" % (i, t, b, "".join("%d," % x for x in sorted(ids))) if t else "U\tq%d\t0" % i
-        assert line == exp, (i, line, exp)
+        assert "\t".join(line.split("\t")[:5]) == exp, (i, line, exp)       # columns 6-7 (accessions, fragment strings) are pinned by test_gpu_frontends.py
     # kaiju-multi style: comma-separated lists of inputs and outputs against the index loaded once
     oa, ob = tmp_path / "a.tsv", tmp_path / "b.tsv"
     subprocess.run([os.path.join(ROOT, "kaiju_b200", "kaiju-b200"), "-t", golden.nodes, "-f", golden.fmi, "-i", "%s,%s" % (fa, fa), "-o", "%s,%s" % (oa, ob),

@@ -191,3 +191,33 @@ def test_emulated_name_frontend_matches_reference_kaijux(emu, golden, cfg):
                 bad.append((line[:120], want[i][:120]))
         assert not bad, bad[:3]
     L.kj_fmi_free(f)
+
+
+@pytest.mark.parametrize("cfg", ["mem_default", "mem_m5_noseg", "greedy_default", "greedy_e5_s40"])
+def test_emulated_verbose_columns_match_reference(emu, golden, cfg):
+    """All seven columns of `kaiju -v` (taxon, best, id set, accession set, fragment strings) from the emulated kernel logic == the raw output of the
+    reference binary (tests/golden/expected_v7_*)."""
+    import gzip
+    import kaiju_b200 as kb
+    from conftest import GOLD
+    L = kb.lib(); L.kj_fmi_accession.restype = C.c_char_p; L.kj_fmi_accession.argtypes = [C.c_void_p, C.c_uint32]
+    f = C.c_void_p(); assert L.kj_fmi_load(golden.fmi.encode(), C.byref(f)) == 0
+    emu.kjemu_classify_v2.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_uint64] + [C.c_void_p] * 7 + [C.c_uint32, C.c_void_p, C.c_int]
+    kw = XP_CONFIGS[cfg]; ST = 2048
+    for tag in ("se100", "pe150"):
+        names, s1, o1, s2, o2 = golden.reads(tag)
+        kp = KjParams(**make_params(**kw)); h = emu.kjemu_create(golden.fmi.encode(), golden.nodes.encode(), C.byref(kp)); assert h
+        n = len(o1) - 1; tax = np.zeros(n, np.uint64); best = np.zeros(n, np.uint32); ids = np.zeros((n, 21), np.uint64); nids = np.zeros(n, np.uint8)
+        acc = np.zeros((n, 20), np.uint32); nacc = np.zeros(n, np.uint8); frag = np.zeros((n, ST), np.uint8); flen = np.zeros(n, np.uint32)
+        rc = emu.kjemu_classify_v2(h, s1.ctypes.data, o1.ctypes.data, s2.ctypes.data if s2 is not None else None, o2.ctypes.data if s2 is not None else None, n,
+                                   tax.ctypes.data, best.ctypes.data, ids.ctypes.data, nids.ctypes.data, acc.ctypes.data, nacc.ctypes.data, frag.ctypes.data, ST, flen.ctypes.data, 4)
+        emu.kjemu_destroy(h); assert rc == 0
+        want = gzip.open(os.path.join(GOLD, "expected_v7_%s_%s.tsv.gz" % (cfg, tag)), "rt").read().split("\n"); bad = []
+        for i in range(n):
+            line = "U\t%s\t0" % names[i] if not tax[i] else "C\t%s\t%d\t%d\t%s,\t%s\t%s" % (
+                names[i], tax[i], best[i], ",".join(str(int(x)) for x in ids[i, :nids[i]]),
+                "".join(L.kj_fmi_accession(f, int(a)).decode() + "," for a in acc[i, :nacc[i]]), bytes(frag[i, :flen[i]]).decode())
+            if line != want[i]:
+                bad.append((line[:160], want[i][:160]))
+        assert not bad, bad[:3]
+    L.kj_fmi_free(f)
