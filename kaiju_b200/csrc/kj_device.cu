@@ -204,7 +204,9 @@ __global__ void kj_count_commit(unsigned long long* __restrict__ total, unsigned
 }
 
 // ------------------------------------------------------------------------------------------------
+struct KjFilesState; static void kj_files_state_free(KjFilesState* S);      // kj_ingest.h
 struct kj_ctx {
+    KjFilesState* files = nullptr;   // buffers of kj_classify_files, kept between calls
     int device = 0; kj_params params{}; int sm_count = 0;
     KjHostIndex H;                 // big arrays are released after upload; small ones stay
     KjDevIndex dix{};              // host copy of the descriptor (device pointers inside)
@@ -443,6 +445,7 @@ extern "C" int kj_set_params(kj_ctx* c, const kj_params* p) {
 extern "C" void kj_destroy(kj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    kj_files_state_free(c->files); c->files = nullptr;
     void* ptrs[] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_tax_parent, c->d_tax_depth, c->d_tax_id, c->d_lnfact, c->d_kmer, c->d_tables, c->d_ix,
                     c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evbreaks, c->d_ws, c->d_counts, c->d_counts_pending, c->d_quirk, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
                     c->d_seq[0][0], c->d_seq[0][1], c->d_seq[1][0], c->d_seq[1][1], c->d_off[0][0], c->d_off[0][1], c->d_off[1][0], c->d_off[1][1],

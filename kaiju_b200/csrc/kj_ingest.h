@@ -96,18 +96,83 @@ __global__ void kj_nl_scatter(const char* __restrict__ text, uint64_t n, const u
     if (blockIdx.x == 0 && threadIdx.x == 0) line_start[0] = 0;
 }
 
+// FASTQ records when blank lines occur between them (kaiju.cpp:288-289 skips empty lines while it looks for the next header, and only there):
+// the phase of a line (0 = header expected, 1 = sequence, 2 = '+', 3 = qualities) is a four-state automaton over the lines; its transition
+// functions compose associatively, so the phases come out of a scan.  A map is 4 x 2 bits: bits [2s+1:2s] = next phase from phase s.
+#define KJ_FQ_MAP_LINE  0x39u      // 0->1 1->2 2->3 3->0
+#define KJ_FQ_MAP_BLANK 0x38u      // 0->0 (skipped) 1->2 2->3 3->0
+#define KJ_FQ_MAP_ID    0xE4u
+static __device__ __forceinline__ uint32_t kj_fq_compose(uint32_t a, uint32_t b) {     // a first, then b
+    uint32_t r = 0;
+    #pragma unroll
+    for (int st = 0; st < 4; st++) r |= ((b >> (2u * ((a >> (2 * st)) & 3u))) & 3u) << (2 * st);
+    return r;
+}
+static __device__ __forceinline__ uint32_t kj_fq_line_map(const uint64_t* __restrict__ line_start, uint64_t i, uint64_t n_lines) {
+    if (i >= n_lines) return KJ_FQ_MAP_ID;
+    return line_start[i + 1] - 1 == line_start[i] ? KJ_FQ_MAP_BLANK : KJ_FQ_MAP_LINE;
+}
+// block-wide exclusive scan of maps under composition (256 threads); total = composition of the whole block
+static __device__ __forceinline__ uint32_t kj_fq_block_scan(uint32_t v, uint32_t* sm, uint32_t& total) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x = kj_fq_compose(o, x); }
+    if (lane == 31) sm[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t w = lane < (blockDim.x >> 5) ? sm[lane] : KJ_FQ_MAP_ID; uint32_t y = w;
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, y, d); if (lane >= (uint32_t)d) y = kj_fq_compose(o, y); }
+        const uint32_t ex = __shfl_up_sync(0xffffffffu, y, 1);
+        sm[32 + lane] = lane ? ex : KJ_FQ_MAP_ID;
+        if (lane == 31) sm[64] = y;
+    }
+    __syncthreads();
+    total = sm[64];
+    uint32_t ex = __shfl_up_sync(0xffffffffu, x, 1); if (lane == 0) ex = KJ_FQ_MAP_ID;
+    const uint32_t r = kj_fq_compose(sm[32 + wid], ex);
+    __syncthreads();
+    return r;
+}
+#define KJ_FQ_TILE 2048u            // lines per block: 256 threads x 8
+__global__ void kj_fq_tile_maps(const uint64_t* __restrict__ line_start, uint64_t n_lines, uint32_t* __restrict__ tile_map) {
+    __shared__ uint32_t sm[80];
+    const uint64_t base = (uint64_t)blockIdx.x * KJ_FQ_TILE + (uint64_t)threadIdx.x * 8u; uint32_t m = KJ_FQ_MAP_ID;
+    for (int k = 0; k < 8; k++) m = kj_fq_compose(m, kj_fq_line_map(line_start, base + k, n_lines));
+    uint32_t tot; (void)kj_fq_block_scan(m, sm, tot);
+    if (threadIdx.x == 0) tile_map[blockIdx.x] = tot;
+}
+__global__ void kj_fq_tile_prefix(uint32_t* __restrict__ tile_map, uint32_t ntiles) {     // one thread: a few hundred tiles per chunk
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t acc = KJ_FQ_MAP_ID;
+    for (uint32_t t = 0; t < ntiles; t++) { const uint32_t m = tile_map[t]; tile_map[t] = acc; acc = kj_fq_compose(acc, m); }
+}
+// phase[i] = phase before line i, for i in [0, n_lines] (the chunk starts at a record boundary: phase 0)
+__global__ void kj_fq_phases(const uint64_t* __restrict__ line_start, uint64_t n_lines, const uint32_t* __restrict__ tile_map, uint8_t* __restrict__ phase) {
+    __shared__ uint32_t sm[80];
+    const uint64_t base = (uint64_t)blockIdx.x * KJ_FQ_TILE + (uint64_t)threadIdx.x * 8u; uint32_t mk[8], m = KJ_FQ_MAP_ID;
+    for (int k = 0; k < 8; k++) { mk[k] = kj_fq_line_map(line_start, base + k, n_lines); m = kj_fq_compose(m, mk[k]); }
+    uint32_t tot; uint32_t pre = kj_fq_compose(tile_map[blockIdx.x], kj_fq_block_scan(m, sm, tot));
+    for (int k = 0; k < 8; k++) { if (base + k <= n_lines) phase[base + k] = (uint8_t)(pre & 3u); pre = kj_fq_compose(pre, mk[k]); }
+}
+
 struct KjParseDims { uint32_t fastq; uint32_t n_lines; };
 static __device__ __forceinline__ bool kj_is_letter(uint32_t c) { const uint32_t u = c & 0xDFu; return u >= 'A' && u <= 'Z'; }    // util.cpp:21-23
+// what line i is: header / sequence line / neither.  FASTQ without a phase array: four lines per record from the start of the chunk; an empty
+// line where a header is expected raises flag 64 (the chunk is then parsed again with the phases)
+static __device__ __forceinline__ void kj_line_kind(const char* __restrict__ text, KjParseDims d, const uint8_t* __restrict__ phase, uint64_t i, uint64_t s, uint64_t e, bool& is_hdr, bool& is_seq, bool& blank) {
+    blank = false;
+    if (d.fastq) { const uint32_t ph = phase ? phase[i] : (uint32_t)(i & 3u); blank = ph == 0 && e == s; is_hdr = ph == 0 && !(phase && blank); is_seq = ph == 1; }
+    else { is_hdr = e > s && text[s] == '>'; is_seq = !is_hdr; }
+}
 // one warp per complete line: cnt = letters of a sequence line, hdr = 1 for a header line, nlen = trimmed name length
-__global__ void kj_line_info(const char* __restrict__ text, const uint64_t* __restrict__ line_start, KjParseDims d,
+__global__ void kj_line_info(const char* __restrict__ text, const uint64_t* __restrict__ line_start, KjParseDims d, const uint8_t* __restrict__ phase,
                              uint32_t* __restrict__ cnt, uint32_t* __restrict__ hdr, uint32_t* __restrict__ nlen, uint32_t* __restrict__ err) {
     const uint32_t lane = threadIdx.x & 31; const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t i = warp; i <= d.n_lines; i += nwarps) {
         if (i == d.n_lines) { if (lane == 0) { cnt[i] = 0; hdr[i] = 0; nlen[i] = 0; } continue; }     // virtual line: the scans deliver the totals here
         const uint64_t s = line_start[i], e = line_start[i + 1] - 1;                                  // [s, e) without the newline
-        bool is_hdr, is_seq;
-        if (d.fastq) { is_hdr = (i & 3u) == 0; is_seq = (i & 3u) == 1; if (is_hdr && lane == 0 && e > s && text[s] != '@') atomicOr(err, 16u); }
-        else { is_hdr = e > s && text[s] == '>'; is_seq = !is_hdr; }
+        bool is_hdr, is_seq, blank; kj_line_kind(text, d, phase, i, s, e, is_hdr, is_seq, blank);
+        if (d.fastq && lane == 0) { if (blank && !phase) atomicOr(err, 64u); if (is_hdr && e > s && text[s] != '@') atomicOr(err, 16u); }
         uint32_t c = 0, nl = 0;
         if (is_seq) {
             for (uint64_t p = s + lane; p < e; p += 32) c += kj_is_letter((uint8_t)text[p]) ? 1u : 0u;
@@ -125,15 +190,14 @@ __global__ void kj_line_info(const char* __restrict__ text, const uint64_t* __re
     }
 }
 // after the scans: S = letters before line i, R = headers before line i, NS = name bytes before line i
-__global__ void kj_line_emit(const char* __restrict__ text, const uint64_t* __restrict__ line_start, KjParseDims d,
+__global__ void kj_line_emit(const char* __restrict__ text, const uint64_t* __restrict__ line_start, KjParseDims d, const uint8_t* __restrict__ phase,
                              const uint32_t* __restrict__ S, const uint32_t* __restrict__ R, const uint32_t* __restrict__ NS,
-                             char* __restrict__ seq, uint64_t* __restrict__ off, char* __restrict__ names, uint32_t* __restrict__ name_off, uint64_t* __restrict__ rec_pos, uint64_t nbytes) {
+                             char* __restrict__ seq, uint64_t* __restrict__ off, char* __restrict__ names, uint32_t* __restrict__ name_off, uint64_t* __restrict__ rec_pos) {
     const uint32_t lane = threadIdx.x & 31; const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t i = warp; i <= d.n_lines; i += nwarps) {
         if (i == d.n_lines) { if (lane == 0) { const uint32_t r = R[i]; off[r] = S[i]; name_off[r] = NS[i]; rec_pos[r] = line_start[i]; } continue; }
         const uint64_t s = line_start[i], e = line_start[i + 1] - 1;
-        const bool is_hdr = d.fastq ? (i & 3u) == 0 : (e > s && text[s] == '>');
-        const bool is_seq = d.fastq ? (i & 3u) == 1 : !is_hdr;
+        bool is_hdr, is_seq, blank; kj_line_kind(text, d, phase, i, s, e, is_hdr, is_seq, blank);
         if (is_hdr) {
             const uint32_t r = R[i], nl = NS[i + 1] - NS[i];
             if (lane == 0) { off[r] = S[i]; name_off[r] = NS[i]; rec_pos[r] = s; }
@@ -148,7 +212,6 @@ __global__ void kj_line_emit(const char* __restrict__ text, const uint64_t* __re
             }
         }
     }
-    (void)nbytes;
 }
 // paired input: names of both files must be identical record by record (kaiju.cpp:359-362, 377-380)
 __global__ void kj_names_equal(const char* __restrict__ na, const uint32_t* __restrict__ oa, const char* __restrict__ nb, const uint32_t* __restrict__ ob, uint64_t n, uint32_t* __restrict__ err) {
@@ -214,16 +277,28 @@ static int kj_scan_u32(uint32_t* d, uint64_t n, KjDevBuf& tmp, uint32_t* d_total
     return KJ_OK;
 }
 
-struct KjParsed {   // one side (file) of a chunk after parsing
-    KjDevBuf text[2]; int cur = 0; uint64_t nbytes = 0;         // device text (ping-pong for the carry), valid bytes
-    KjDevBuf line_start, cnt, hdr, nlen, tiles, scan_tmp, seq, off, names, name_off, rec_pos, totals;
-    int fastq = -1;                                              // file type, fixed by the first byte of the file
-    uint64_t n_lines = 0, n_rec = 0, consumed = 0; bool eof = false;
-    void release() { for (KjDevBuf* b : {&text[0], &text[1], &line_start, &cnt, &hdr, &nlen, &tiles, &scan_tmp, &seq, &off, &names, &name_off, &rec_pos, &totals}) b->release(); }
+struct KjPinnedPool {   // pinned host buffers outlive one kj_classify_files call (allocation and release cost ~0.3 ms per MB)
+    std::mutex mu; std::vector<std::pair<char*, size_t>> idle;
+    char* get(size_t bytes) {
+        { std::lock_guard<std::mutex> lk(mu); for (size_t k = 0; k < idle.size(); k++) if (idle[k].second == bytes) { char* b = idle[k].first; idle.erase(idle.begin() + k); return b; } }
+        char* b = nullptr; return cudaMallocHost((void**)&b, bytes) == cudaSuccess ? b : nullptr;
+    }
+    void put(char* b, size_t bytes) { std::lock_guard<std::mutex> lk(mu); idle.push_back({b, bytes}); }
+    void release() { std::lock_guard<std::mutex> lk(mu); for (auto& e : idle) cudaFreeHost(e.first); idle.clear(); }
 };
 
-// Parse the complete records in P.text[P.cur][0, P.nbytes).  Sets P.n_rec and P.consumed (bytes covered by those records).
-static int kj_parse_side(kj_ctx* c, KjParsed& P, const std::string& fname, cudaStream_t st) {
+struct KjBatchSide { KjDevBuf seq, off, names, name_off; };     // what the parser hands to the classifier for one input file
+struct KjParsed {   // one side (file) of a chunk while it is parsed
+    KjDevBuf text[2]; int cur = 0; uint64_t nbytes = 0;         // device text (ping-pong for the carry), valid bytes
+    KjDevBuf line_start, cnt, hdr, nlen, tiles, scan_tmp, rec_pos, totals, phase, phase_tiles;
+    int fastq = -1;                                              // file type, fixed by the first byte of the file
+    uint64_t n_lines = 0, n_rec = 0, consumed = 0; bool eof = false;
+    void release() { for (KjDevBuf* b : {&text[0], &text[1], &line_start, &cnt, &hdr, &nlen, &tiles, &scan_tmp, &rec_pos, &totals, &phase, &phase_tiles}) b->release(); }
+};
+
+// Parse the complete records in P.text[P.cur][0, P.nbytes) into O.  Sets P.n_rec; *launches counts the kernels.
+// exact: FASTQ with blank lines between records (phases from the automaton scan instead of line number mod 4)
+static int kj_parse_side(int sm_count, KjParsed& P, KjBatchSide& O, const std::string& fname, cudaStream_t st, uint32_t* d_perr, uint64_t* launches, bool exact) {
     P.n_rec = 0; P.consumed = 0; P.n_lines = 0;
     if (P.nbytes == 0) return KJ_OK;
     if (P.nbytes >= (1ull << 31)) { kj_err() = "kj_classify_files: a single record larger than 2 GB"; return KJ_ERR_UNSUPPORTED; }
@@ -240,39 +315,44 @@ static int kj_parse_side(kj_ctx* c, KjParsed& P, const std::string& fname, cudaS
     kj_nl_count<<<ntiles, 256, 0, st>>>(text, P.nbytes, P.tiles.as<uint32_t>());
     if ((rc = kj_scan_u32(P.tiles.as<uint32_t>(), ntiles, P.scan_tmp, tot + 0, st))) return rc;
     uint32_t nl = 0; CK(cudaMemcpyAsync(&nl, tot + 0, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-    P.n_lines = nl; c->launches += 4;
+    P.n_lines = nl; *launches += 4;
     if (nl == 0) return KJ_OK;                                                      // not even one complete line yet
     const size_t L1 = (size_t)nl + 1;
     if ((rc = P.line_start.need((L1 + 1) * 8)) || (rc = P.cnt.need((L1 + 1) * 4)) || (rc = P.hdr.need((L1 + 1) * 4)) || (rc = P.nlen.need((L1 + 1) * 4))) return rc;
     kj_nl_scatter<<<ntiles, 256, 0, st>>>(text, P.nbytes, P.tiles.as<uint32_t>(), P.line_start.as<uint64_t>());
     KjParseDims d; d.fastq = (uint32_t)P.fastq; d.n_lines = nl;
-    const int blocks = c->sm_count * 8;
-    kj_line_info<<<blocks, 256, 0, st>>>(text, P.line_start.as<uint64_t>(), d, P.cnt.as<uint32_t>(), P.hdr.as<uint32_t>(), P.nlen.as<uint32_t>(), c->d_err);
+    const int blocks = sm_count * 8;
+    const uint8_t* phase = nullptr;
+    if (P.fastq && exact) {
+        const uint32_t nt = (uint32_t)((L1 + KJ_FQ_TILE - 1) / KJ_FQ_TILE);
+        if ((rc = P.phase.need(L1 + 8)) || (rc = P.phase_tiles.need((size_t)(nt + 1) * 4))) return rc;
+        kj_fq_tile_maps<<<nt, 256, 0, st>>>(P.line_start.as<uint64_t>(), nl, P.phase_tiles.as<uint32_t>());
+        kj_fq_tile_prefix<<<1, 32, 0, st>>>(P.phase_tiles.as<uint32_t>(), nt);
+        kj_fq_phases<<<nt, 256, 0, st>>>(P.line_start.as<uint64_t>(), nl, P.phase_tiles.as<uint32_t>(), P.phase.as<uint8_t>());
+        phase = P.phase.as<uint8_t>(); *launches += 3;
+    }
+    kj_line_info<<<blocks, 256, 0, st>>>(text, P.line_start.as<uint64_t>(), d, phase, P.cnt.as<uint32_t>(), P.hdr.as<uint32_t>(), P.nlen.as<uint32_t>(), d_perr);
     if ((rc = kj_scan_u32(P.cnt.as<uint32_t>(), L1, P.scan_tmp, tot + 1, st)) || (rc = kj_scan_u32(P.hdr.as<uint32_t>(), L1, P.scan_tmp, tot + 2, st)) ||
         (rc = kj_scan_u32(P.nlen.as<uint32_t>(), L1, P.scan_tmp, tot + 3, st))) return rc;
-    uint32_t h[4]; CK(cudaMemcpyAsync(h, tot, 16, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    uint32_t h[4]; uint8_t end_phase = 0; CK(cudaMemcpyAsync(h, tot, 16, cudaMemcpyDeviceToHost, st));
+    if (phase) CK(cudaMemcpyAsync(&end_phase, phase + nl, 1, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     const uint64_t letters = h[1], headers = h[2], name_bytes = h[3];
-    if ((rc = P.seq.need(letters + 64)) || (rc = P.off.need((headers + 2) * 8)) || (rc = P.names.need(name_bytes + 64)) || (rc = P.name_off.need((headers + 2) * 4)) ||
+    if ((rc = O.seq.need(letters + 64)) || (rc = O.off.need((headers + 2) * 8)) || (rc = O.names.need(name_bytes + 64)) || (rc = O.name_off.need((headers + 2) * 4)) ||
         (rc = P.rec_pos.need((headers + 2) * 8))) return rc;
-    kj_line_emit<<<blocks, 256, 0, st>>>(text, P.line_start.as<uint64_t>(), d, P.cnt.as<uint32_t>(), P.hdr.as<uint32_t>(), P.nlen.as<uint32_t>(),
-                                        P.seq.as<char>(), P.off.as<uint64_t>(), P.names.as<char>(), P.name_off.as<uint32_t>(), P.rec_pos.as<uint64_t>(), P.nbytes);
-    CK(cudaGetLastError()); c->launches += 12;
+    kj_line_emit<<<blocks, 256, 0, st>>>(text, P.line_start.as<uint64_t>(), d, phase, P.cnt.as<uint32_t>(), P.hdr.as<uint32_t>(), P.nlen.as<uint32_t>(),
+                                        O.seq.as<char>(), O.off.as<uint64_t>(), O.names.as<char>(), O.name_off.as<uint32_t>(), P.rec_pos.as<uint64_t>());
+    CK(cudaGetLastError()); *launches += 12;
     // complete records: FASTQ = whole groups of four lines; FASTA = every header that is followed by another header (or by the end of the file)
-    if (P.fastq) { P.n_rec = nl / 4; }
+    if (P.fastq) { P.n_rec = phase ? (end_phase == 0 ? headers : (headers ? headers - 1 : 0)) : nl / 4; }       // a record is complete with its fourth line
     else { P.n_rec = P.eof ? headers : (headers ? headers - 1 : 0); }
     return KJ_OK;
-}
-// bytes of the text covered by the first n records (n <= n_rec)
-static int kj_parse_consumed(KjParsed& P, uint64_t n, uint64_t headers_total_hint, cudaStream_t st, uint64_t& consumed) {
-    (void)headers_total_hint;
-    uint64_t v = 0; CK(cudaMemcpyAsync(&v, P.rec_pos.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-    consumed = v; return KJ_OK;
 }
 
 struct KjChunk { char* p = nullptr; size_t n = 0; bool eof = false; std::string error; };
 struct KjFileReader {   // per input file: gz (zlib, one thread) or plain (a pool of pread() threads) -> pinned chunks
     gzFile fp = nullptr; int fd = -1; uint64_t file_off = 0; std::string path; size_t chunk; std::vector<char*> pool; std::deque<KjChunk> ready; std::deque<char*> free_;
-    std::mutex mu; std::condition_variable cv; std::thread th; bool stop = false;
+    std::mutex mu; std::condition_variable cv; std::thread th; bool stop = false; int device = 0, nbuf = 3; KjPinnedPool* pinned = nullptr;
     // plain files: NT worker threads copy 1 MB slices of the current chunk out of the page cache in parallel (one copy stream per thread;
     // a single thread moves ~1-3 GB/s, the device pipeline wants > 20 GB/s)
     static constexpr size_t SLICE = 1u << 20;
@@ -297,8 +377,8 @@ struct KjFileReader {   // per input file: gz (zlib, one thread) or plain (a poo
             seen = gen;
         }
     }
-    int open(const std::string& p, size_t chunk_bytes, int nbuf) {
-        path = p; chunk = chunk_bytes;
+    int open(const std::string& p, size_t chunk_bytes, int nbuf_, int device_, KjPinnedPool* pp) {
+        path = p; chunk = chunk_bytes; nbuf = nbuf_; device = device_; pinned = pp;
         fd = ::open(p.c_str(), O_RDONLY);
         if (fd < 0) { kj_err() = "Could not open file " + p; return KJ_ERR_IO; }
         unsigned char magic[2] = {0, 0}; const ssize_t got = ::pread(fd, magic, 2, 0);
@@ -313,14 +393,22 @@ struct KjFileReader {   // per input file: gz (zlib, one thread) or plain (a poo
             wgot.assign((chunk + SLICE - 1) / SLICE, 0);
             for (unsigned t = 0; t < nt; t++) workers.emplace_back([this] { worker(); });
         }
-        for (int i = 0; i < nbuf; i++) { char* b = nullptr; if (cudaMallocHost((void**)&b, chunk) != cudaSuccess) { kj_err() = "cudaMallocHost failed"; return KJ_ERR_NOMEM; } pool.push_back(b); free_.push_back(b); }
         th = std::thread([this] { run(); });
         return KJ_OK;
     }
     void run() {
+        cudaSetDevice(device);
         for (;;) {
-            char* b;
-            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || !free_.empty(); }); if (stop) return; b = free_.front(); free_.pop_front(); }
+            char* b = nullptr;
+            {   // a pinned buffer: a returned one, or (up to nbuf) a new one -- allocated here, next to the running pipeline, not before it starts
+                std::unique_lock<std::mutex> lk(mu);
+                if (free_.empty() && (int)pool.size() < nbuf) {
+                    lk.unlock(); b = pinned->get(chunk); lk.lock();
+                    if (b) pool.push_back(b);
+                    else { KjChunk ck; ck.error = "cudaMallocHost failed"; ready.push_back(ck); cv.notify_all(); return; }
+                } else { cv.wait(lk, [&] { return stop || !free_.empty(); }); if (stop) return; b = free_.front(); free_.pop_front(); }
+                if (stop) { free_.push_back(b); return; }
+            }
             KjChunk ck; ck.p = b; size_t got = 0;
             if (fd >= 0) {
                 const size_t ns = (chunk + SLICE - 1) / SLICE;
@@ -361,16 +449,16 @@ struct KjFileReader {   // per input file: gz (zlib, one thread) or plain (a poo
         workers.clear();
         if (fp) gzclose(fp); fp = nullptr;
         if (fd >= 0) ::close(fd); fd = -1;
-        for (char* b : pool) cudaFreeHost(b); pool.clear();
+        for (char* b : pool) pinned->put(b, chunk); pool.clear(); ready.clear(); free_.clear();
+        stop = false; wstop = false; file_off = 0; wgen = 0; wslices = 0; wnext = 0; wleft = 0;
     }
 };
 struct KjWriter {   // ordered output: pinned buffers filled by D2H copies, written by one thread
-    FILE* out = nullptr; bool own = false; std::vector<char*> pool; size_t cap = 0; std::deque<std::pair<char*, size_t>> ready; std::deque<char*> free_;
-    std::mutex mu; std::condition_variable cv; std::thread th; bool done = false, failed = false;
-    int open(const char* path, size_t cap_bytes, int nbuf) {
-        if (path && *path) { out = fopen(path, "w"); own = true; if (!out) { kj_err() = std::string("Could not open file ") + path + " for writing"; return KJ_ERR_IO; } } else out = stdout;
-        cap = cap_bytes;
-        for (int i = 0; i < nbuf; i++) { char* b = nullptr; if (cudaMallocHost((void**)&b, cap) != cudaSuccess) { kj_err() = "cudaMallocHost failed"; return KJ_ERR_NOMEM; } pool.push_back(b); free_.push_back(b); }
+    FILE* out = nullptr; bool own = false; std::vector<char*> pool; size_t cap = 0; int nbuf = 3; std::deque<std::pair<char*, size_t>> ready; std::deque<char*> free_;
+    std::mutex mu; std::condition_variable cv; std::thread th; bool done = false, failed = false; KjPinnedPool* pinned = nullptr;
+    int open(const char* path, size_t cap_bytes, int nbuf_, KjPinnedPool* pp) {
+        if (path && *path) { out = fopen(path, "w"); own = true; if (!out) { kj_err() = std::string("Could not open file ") + path + " for writing"; return KJ_ERR_IO; } } else { out = stdout; own = false; }
+        cap = cap_bytes; nbuf = nbuf_; pinned = pp; done = false; failed = false;
         th = std::thread([this] {
             for (;;) {
                 std::pair<char*, size_t> job;
@@ -381,67 +469,87 @@ struct KjWriter {   // ordered output: pinned buffers filled by D2H copies, writ
         });
         return KJ_OK;
     }
-    char* get() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !free_.empty(); }); char* b = free_.front(); free_.pop_front(); return b; }
+    char* get() {      // nullptr: out of pinned memory
+        std::unique_lock<std::mutex> lk(mu);
+        if (free_.empty() && (int)pool.size() < nbuf) { lk.unlock(); char* b = pinned->get(cap); lk.lock(); if (b) pool.push_back(b); return b; }
+        cv.wait(lk, [&] { return !free_.empty(); }); char* b = free_.front(); free_.pop_front(); return b;
+    }
     void put(char* b, size_t n) { { std::lock_guard<std::mutex> lk(mu); ready.push_back({b, n}); } cv.notify_all(); }
     int close() {
         { std::lock_guard<std::mutex> lk(mu); done = true; } cv.notify_all();
         if (th.joinable()) th.join();
         if (out) { fflush(out); if (own) fclose(out); } out = nullptr;
-        for (char* b : pool) cudaFreeHost(b); pool.clear();
+        for (char* b : pool) pinned->put(b, cap); pool.clear(); ready.clear(); free_.clear();
         if (failed) { kj_err() = "write error on the output file"; return KJ_ERR_IO; }
         return KJ_OK;
     }
 };
 
 struct KjPrefetch { KjDevBuf stage[2]; int cur = 0; cudaEvent_t done = nullptr; bool pending = false, eof = false; char* host = nullptr; size_t n = 0; char last = 0; };
+// One parsed chunk on its way from the parser thread to the classifying thread
+struct KjBatch { KjBatchSide s[2]; uint64_t n = 0; unsigned int maxlen[2] = {0, 0}; bool last = false; int rc = KJ_OK; std::string err; };
+#define KJ_FILE_SLOTS 3
+// Everything kj_classify_files needs besides the context; kept in the context between calls (device buffers and pinned memory are reused)
 struct KjFilesState {
     KjParsed side[2]; KjFileReader rd[2]; KjWriter wr; KjPrefetch pf[2]; int nfiles = 1; bool rd_open[2] = {false, false}, wr_open = false;
+    KjBatch slot[KJ_FILE_SLOTS]; KjPinnedPool pinned; cudaStream_t sp = nullptr, sh = nullptr; KjDevBuf pstat;
     KjDevBuf tax, best, ids, nids, len, out, scan_tmp, totals;
-    void cleanup() {
+    // parser thread -> classifying thread: filled slots in order; slots come back when their chunk has been written
+    std::mutex mu; std::condition_variable cv; std::deque<int> filled; int n_free = KJ_FILE_SLOTS; bool abort = false; std::thread parser;
+    std::string fn[2], perr; int prc = KJ_OK;                 // input names; the parser thread's error
+    uint64_t parse_launches = 0; double tm[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; uint64_t nchunks = 0;
+    void end_call() {      // threads, files and in-flight copies of one call
+        { std::lock_guard<std::mutex> lk(mu); abort = true; } cv.notify_all();
+        if (parser.joinable()) parser.join();
         for (int f = 0; f < 2; f++) {
             if (pf[f].pending && pf[f].done) cudaEventSynchronize(pf[f].done);
-            if (rd_open[f]) rd[f].close(); side[f].release(); pf[f].stage[0].release(); pf[f].stage[1].release(); if (pf[f].done) cudaEventDestroy(pf[f].done);
+            if (pf[f].pending && rd_open[f]) rd[f].give_back(pf[f].host);
+            pf[f].pending = false; pf[f].eof = false;
+            if (rd_open[f]) rd[f].close(); rd_open[f] = false;
+            KjParsed& P = side[f]; P.cur = 0; P.nbytes = 0; P.fastq = -1; P.n_lines = P.n_rec = P.consumed = 0; P.eof = false;
         }
-        if (wr_open) wr.close();
-        for (KjDevBuf* b : {&tax, &best, &ids, &nids, &len, &out, &scan_tmp, &totals}) b->release();
+        if (wr_open) wr.close(); wr_open = false;
+        filled.clear(); n_free = KJ_FILE_SLOTS; abort = false;
+    }
+    void release() {       // with the context
+        for (int f = 0; f < 2; f++) { side[f].release(); pf[f].stage[0].release(); pf[f].stage[1].release(); if (pf[f].done) cudaEventDestroy(pf[f].done); pf[f].done = nullptr; }
+        for (KjBatch& b : slot) for (KjBatchSide& o : b.s) for (KjDevBuf* d : {&o.seq, &o.off, &o.names, &o.name_off}) d->release();
+        for (KjDevBuf* b : {&tax, &best, &ids, &nids, &len, &out, &scan_tmp, &totals, &pstat}) b->release();
+        if (sp) cudaStreamDestroy(sp); if (sh) cudaStreamDestroy(sh); sp = sh = nullptr;
+        pinned.release();
     }
 };
+static void kj_files_state_free(KjFilesState* S) { if (!S) return; S->end_call(); S->release(); delete S; }
 
-// next chunk of file f: pinned buffer -> device staging buffer, asynchronously on the context's second stream
-static int kj_prefetch(kj_ctx* c, KjFilesState& S, int f) {
+// next chunk of file f: pinned buffer -> device staging buffer, asynchronously on the copy stream
+static int kj_prefetch(KjFilesState& S, int f) {
     KjPrefetch& F = S.pf[f];
     KjChunk ck = S.rd[f].next();
     if (!ck.error.empty()) { kj_err() = ck.error; return KJ_ERR_IO; }
     F.cur ^= 1; int rc = F.stage[F.cur].need(ck.n + 16); if (rc) return rc;
     if (!F.done) CK(cudaEventCreateWithFlags(&F.done, cudaEventDisableTiming));
-    if (ck.n) CK(cudaMemcpyAsync(F.stage[F.cur].p, ck.p, ck.n, cudaMemcpyHostToDevice, c->stream[1]));
-    CK(cudaEventRecord(F.done, c->stream[1]));
+    if (ck.n) CK(cudaMemcpyAsync(F.stage[F.cur].p, ck.p, ck.n, cudaMemcpyHostToDevice, S.sh));
+    CK(cudaEventRecord(F.done, S.sh));
     F.pending = true; F.eof = ck.eof; F.host = ck.p; F.n = ck.n; F.last = ck.n ? ck.p[ck.n - 1] : 0;
     return KJ_OK;
 }
 
-static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, const char* in2, const char* out_path, int verbose, uint64_t* n_reads_out, uint64_t* n_class_out) {
-    // developer hook KJ_FILES_TRACE: where the wall time of the file pipeline goes (ms per stage, summed over the chunks)
-    const bool ftrace = getenv("KJ_FILES_TRACE") != nullptr; double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint64_t nchunks = 0;
-    auto now = [] { return std::chrono::steady_clock::now(); }; auto t_last = now();
-    auto lap = [&](int k) { if (!ftrace) return; cudaStreamSynchronize(c->stream[0]); const auto t = now(); tm[k] += std::chrono::duration<double, std::milli>(t - t_last).count(); t_last = t; };
-    size_t chunk = 64u << 20;
-    if (const char* v = getenv("KJ_INGEST_CHUNK")) { long x = atol(v); if (x >= 256 && x <= (1l << 30)) chunk = (size_t)x; }       // test hook: many small chunks
-    const bool paired = in2 && *in2; S.nfiles = paired ? 2 : 1;
-    const std::string fn[2] = {in1, paired ? in2 : ""};
-    cudaStream_t st = c->stream[0];
-    int rc;
-    for (int f = 0; f < S.nfiles; f++) { if ((rc = S.rd[f].open(fn[f], chunk, 3))) return rc; S.rd_open[f] = true; }
-    size_t out_cap = 16u << 20;
-    if ((rc = S.wr.open(out_path, out_cap, 3))) return rc; S.wr_open = true;
-    if ((rc = S.totals.need(64))) return rc;
-    uint64_t n_reads = 0; unsigned long long n_class = 0;
-    CK(cudaMemsetAsync(S.totals.p, 0, 64, st));
-    CK(cudaMemsetAsync(c->d_counts_pending, 0, (size_t)c->n_counts * 8, st));
-    unsigned long long* d_nclass = (unsigned long long*)((char*)S.totals.p + 16);
-    for (int f = 0; f < S.nfiles; f++) if ((rc = kj_prefetch(c, S, f))) return rc;
+static inline double kj_ms_since(std::chrono::steady_clock::time_point& t) { const auto n = std::chrono::steady_clock::now(); const double d = std::chrono::duration<double, std::milli>(n - t).count(); t = n; return d; }
+
+// Parser thread: file chunks -> device text -> packed reads, names and offsets of the complete records, one KjBatch per chunk.
+// Stage 1 of the two-stage pipeline: while the caller's thread classifies and formats chunk k on its stream, this thread parses
+// chunk k+1 (and k+2) on another; the carry (the incomplete record at the end of a chunk) only depends on the parse.
+static int kj_parse_chunks(int device, int sm_count, KjFilesState& S, size_t chunk, bool paired) {
+    CK(cudaSetDevice(device));
+    const std::string* fn = S.fn;
+    cudaStream_t st = S.sp; int rc; auto t = std::chrono::steady_clock::now();
+    uint32_t* d_stat = S.pstat.as<uint32_t>();       // [0,1] longest read of each side, [2] error bits of the parse kernels
+    for (int f = 0; f < S.nfiles; f++) if ((rc = kj_prefetch(S, f))) return rc;
     for (;;) {
-        nchunks++; lap(7);
+        int si;
+        { std::unique_lock<std::mutex> lk(S.mu); S.cv.wait(lk, [&] { return S.abort || S.n_free > 0; }); if (S.abort) return KJ_OK; S.n_free--; }
+        si = (int)(S.nchunks % KJ_FILE_SLOTS); KjBatch& B = S.slot[si]; S.nchunks++;
+        S.tm[0] += kj_ms_since(t);
         // 1. top up both sides: carry (already at the front of the device text) + the chunk that was prefetched into the staging buffer
         for (int f = 0; f < S.nfiles; f++) {
             KjParsed& P = S.side[f]; KjPrefetch& F = S.pf[f];
@@ -462,34 +570,102 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
             P.nbytes += F.n;
             if (need_nl) { CK(cudaMemsetAsync(P.text[P.cur].as<char>() + P.nbytes, '\n', 1, st)); P.nbytes += 1; }      // the last line of a file may lack its newline
         }
-        lap(0);
-        // ... and start the host-to-device copy of the following chunks on the second stream: it overlaps with the kernels below
-        for (int f = 0; f < S.nfiles; f++) if (!S.side[f].eof && (rc = kj_prefetch(c, S, f))) return rc;
-        lap(1);
-        // 2. parse
-        for (int f = 0; f < S.nfiles; f++) if ((rc = kj_parse_side(c, S.side[f], fn[f], st))) return rc;
-        uint64_t n = S.side[0].n_rec; if (paired) n = std::min(n, S.side[1].n_rec);
-        const bool all_eof = S.side[0].eof && (!paired || S.side[1].eof);
-        if (paired && all_eof && S.side[0].n_rec > S.side[1].n_rec) { kj_err() = "File " + fn[0] + " contains more reads then file " + fn[1]; return KJ_ERR_IO; }   // kaiju.cpp:337-340
-        lap(2);
-        // 3. classify + format the first n records
-        if (n) {
+        S.tm[1] += kj_ms_since(t);
+        // ... and start the host-to-device copy of the following chunks on the copy stream (into the other staging buffer): it overlaps with the kernels below
+        for (int f = 0; f < S.nfiles; f++) if (!S.side[f].eof && (rc = kj_prefetch(S, f))) return rc;
+        S.tm[2] += kj_ms_since(t);
+        // 2. parse; a FASTQ chunk with an empty line where a header was expected (flag 64) is parsed again with the record phases from the automaton scan
+        uint64_t n = 0; bool all_eof = false; uint64_t pos[2] = {0, 0}; uint32_t hstat[4] = {0, 0, 0, 0};
+        for (int pass = 0; pass < 2; pass++) {
+            CK(cudaMemsetAsync(d_stat, 0, 16, st));
+            for (int f = 0; f < S.nfiles; f++) if ((rc = kj_parse_side(sm_count, S.side[f], B.s[f], fn[f], st, d_stat + 2, &S.parse_launches, pass == 1))) return rc;
+            n = S.side[0].n_rec; if (paired) n = std::min(n, S.side[1].n_rec);
+            all_eof = S.side[0].eof && (!paired || S.side[1].eof);
             if (n >= (1ull << 31)) { kj_err() = "kj_classify_files: chunk with too many records"; return KJ_ERR_UNSUPPORTED; }
-            if (paired) kj_names_equal<<<c->sm_count * 4, 256, 0, st>>>(S.side[0].names.as<char>(), S.side[0].name_off.as<uint32_t>(), S.side[1].names.as<char>(), S.side[1].name_off.as<uint32_t>(), n, c->d_err);
+            if (n) {
+                if (paired) kj_names_equal<<<sm_count * 4, 256, 0, st>>>(B.s[0].names.as<char>(), B.s[0].name_off.as<uint32_t>(), B.s[1].names.as<char>(), B.s[1].name_off.as<uint32_t>(), n, d_stat + 2);
+                kj_maxlen_kernel<<<256, 256, 0, st>>>(B.s[0].off.as<uint64_t>(), n, d_stat);
+                if (paired) kj_maxlen_kernel<<<256, 256, 0, st>>>(B.s[1].off.as<uint64_t>(), n, d_stat + 1);
+                S.parse_launches += paired ? 3 : 1;
+            }
+            // where the first n records end: the rest is carried over
+            for (int f = 0; f < S.nfiles; f++) if (S.side[f].n_lines) CK(cudaMemcpyAsync(&pos[f], S.side[f].rec_pos.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(hstat, d_stat, 16, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));       // the batch is complete in device memory from here on
+            if (!(hstat[2] & 64u)) break;
+        }
+        if (paired && all_eof && S.side[0].n_rec > S.side[1].n_rec) { kj_err() = "File " + fn[0] + " contains more reads then file " + fn[1]; return KJ_ERR_IO; }   // kaiju.cpp:337-340
+        if (hstat[2] & 16u) { kj_err() = "malformed FASTQ record (a header line does not start with '@') in the input"; return KJ_ERR_IO; }
+        if (n && (hstat[2] & 32u)) { kj_err() = "Read names are not identical between the two input files. Probably reads are not in the same order in both files."; return KJ_ERR_IO; }
+        B.n = n;
+        B.maxlen[0] = hstat[0]; B.maxlen[1] = hstat[1];
+        for (int f = 0; f < S.nfiles; f++) {
+            KjParsed& P = S.side[f]; const uint64_t consumed = P.n_lines ? pos[f] : 0;
+            const uint64_t tail = P.nbytes - consumed; const int other = P.cur ^ 1;
+            if ((rc = P.text[other].need(tail + chunk + 1))) return rc;
+            if (tail) CK(cudaMemcpyAsync(P.text[other].p, P.text[P.cur].as<char>() + consumed, tail, cudaMemcpyDeviceToDevice, st));
+            P.cur = other; P.nbytes = tail;
+        }
+        bool last = false;
+        if (all_eof) {
+            if (paired && S.side[1].n_rec > n) fprintf(stderr, "Warning: File %s has more reads then file %s\n", fn[1].c_str(), fn[0].c_str());        // kaiju.cpp:400-404
+            last = true;
+        } else if (paired && S.side[0].eof && S.side[0].nbytes == 0) {
+            // file 1 is exhausted (end of file, nothing carried over): the reference's loop ends here, whatever file 2 still holds (kaiju.cpp:288, 396-404)
+            if (S.side[1].nbytes > 0 || !S.side[1].eof) fprintf(stderr, "Warning: File %s has more reads then file %s\n", fn[1].c_str(), fn[0].c_str());
+            last = true;
+        }
+        B.last = last; B.rc = KJ_OK;
+        S.tm[3] += kj_ms_since(t);
+        { std::lock_guard<std::mutex> lk(S.mu); S.filled.push_back(si); } S.cv.notify_all();
+        if (last) return KJ_OK;
+    }
+}
+
+static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, const char* in2, const char* out_path, int verbose, uint64_t* n_reads_out, uint64_t* n_class_out) {
+    // developer hook KJ_FILES_TRACE: host time of each stage of the two threads (ms, summed over the chunks; waits included)
+    const bool ftrace = getenv("KJ_FILES_TRACE") != nullptr;
+    size_t chunk = 64u << 20;
+    if (const char* v = getenv("KJ_INGEST_CHUNK")) { long x = atol(v); if (x >= 256 && x <= (1l << 30)) chunk = (size_t)x; }       // test hook: many small chunks
+    const bool paired = in2 && *in2; S.nfiles = paired ? 2 : 1;
+    S.fn[0] = in1; S.fn[1] = paired ? in2 : ""; S.perr.clear(); S.prc = KJ_OK;
+    const std::string* fn = S.fn;
+    cudaStream_t st = c->stream[0];
+    int rc;
+    if (!S.sp) CK(cudaStreamCreateWithFlags(&S.sp, cudaStreamNonBlocking));
+    if (!S.sh) CK(cudaStreamCreateWithFlags(&S.sh, cudaStreamNonBlocking));
+    for (int f = 0; f < S.nfiles; f++) { if ((rc = S.rd[f].open(fn[f], chunk, 3, c->device, &S.pinned))) return rc; S.rd_open[f] = true; }
+    const size_t out_cap = 16u << 20;
+    if ((rc = S.wr.open(out_path, out_cap, 3, &S.pinned))) return rc; S.wr_open = true;
+    if ((rc = S.totals.need(64)) || (rc = S.pstat.need(64))) return rc;
+    uint64_t n_reads = 0; unsigned long long n_class = 0;
+    CK(cudaMemsetAsync(S.totals.p, 0, 64, st));
+    CK(cudaMemsetAsync(c->d_counts_pending, 0, (size_t)c->n_counts * 8, st));
+    CK(cudaStreamSynchronize(st));
+    unsigned long long* d_nclass = (unsigned long long*)((char*)S.totals.p + 16);
+    S.parse_launches = 0; S.nchunks = 0; for (double& x : S.tm) x = 0;
+    {   // the thread only touches S (which outlives this call) and its own copies
+        KjFilesState* Sp = &S; const int dev = c->device, sms = c->sm_count;
+        S.parser = std::thread([Sp, dev, sms, chunk, paired] {
+            const int r = kj_parse_chunks(dev, sms, *Sp, chunk, paired);
+            if (r) { std::lock_guard<std::mutex> lk(Sp->mu); Sp->prc = r; Sp->perr = kj_err(); Sp->filled.push_back(-1); }
+            Sp->cv.notify_all();
+        });
+    }
+    auto t = std::chrono::steady_clock::now();
+    for (;;) {
+        int si;
+        { std::unique_lock<std::mutex> lk(S.mu); S.cv.wait(lk, [&] { return !S.filled.empty(); }); si = S.filled.front(); S.filled.pop_front(); }
+        if (si < 0) { kj_err() = S.perr; return S.prc; }
+        S.tm[5] += kj_ms_since(t);
+        KjBatch& B = S.slot[si]; const uint64_t n = B.n;
+        if (n) {
             if ((rc = S.tax.need(n * 8)) || (rc = S.best.need(n * 4)) || (rc = S.len.need((n + 2) * 4))) return rc;
             if (verbose && ((rc = S.ids.need(n * KJ_MAX_IDS * 8)) || (rc = S.nids.need(n)))) return rc;
             for (;;) {     // repeated only when the Greedy variant ring had to grow
-                CK(cudaMemsetAsync(c->d_maxlen, 0, 2 * sizeof(unsigned int), st));
-                kj_maxlen_kernel<<<256, 256, 0, st>>>(S.side[0].off.as<uint64_t>(), n, c->d_maxlen);
-                if (paired) kj_maxlen_kernel<<<256, 256, 0, st>>>(S.side[1].off.as<uint64_t>(), n, c->d_maxlen + 1);
-                unsigned int h[2] = {0, 0}; CK(cudaMemcpyAsync(h, c->d_maxlen, sizeof h, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-                rc = launch(c, 0, S.side[0].seq.as<uint8_t>(), S.side[0].off.as<uint64_t>(), paired ? S.side[1].seq.as<uint8_t>() : nullptr, paired ? S.side[1].off.as<uint64_t>() : nullptr, 0, 0, n, h[0], h[1],
+                rc = launch(c, 0, B.s[0].seq.as<uint8_t>(), B.s[0].off.as<uint64_t>(), paired ? B.s[1].seq.as<uint8_t>() : nullptr, paired ? B.s[1].off.as<uint64_t>() : nullptr, 0, 0, n, B.maxlen[0], B.maxlen[1],
                             S.tax.as<uint64_t>(), S.best.as<uint32_t>(), st, false, verbose ? S.ids.as<uint64_t>() : nullptr, verbose ? S.nids.as<uint8_t>() : nullptr, c->d_counts_pending);
                 if (rc) return rc;
                 CK(cudaStreamSynchronize(st));
-                uint32_t e = 0; CK(cudaMemcpy(&e, c->d_err, sizeof e, cudaMemcpyDeviceToHost));
-                if (e & 16u) { CK(cudaMemset(c->d_err, 0, 4)); kj_err() = "malformed FASTQ record (a header line does not start with '@') in the input"; return KJ_ERR_IO; }
-                if (e & 32u) { CK(cudaMemset(c->d_err, 0, 4)); kj_err() = "Read names are not identical between the two input files. Probably reads are not in the same order in both files."; return KJ_ERR_IO; }
                 const uint32_t boost = c->variant_boost;
                 rc = check_err_flag(c);
                 if (rc) CK(cudaMemsetAsync(c->d_counts_pending, 0, (size_t)c->n_counts * 8, st));     // a failed launch does not count
@@ -497,44 +673,33 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
                 if (rc) return rc;
                 break;
             }
-            lap(3);
+            S.tm[6] += kj_ms_since(t);
             kj_count_commit<<<c->sm_count, 256, 0, st>>>(c->d_counts, c->d_counts_pending, c->n_counts); c->launches++;     // this chunk succeeded: its reads join the per-taxon counts
-            kj_fmt_len<<<c->sm_count * 4, 256, 0, st>>>(S.tax.as<uint64_t>(), S.best.as<uint32_t>(), S.ids.as<uint64_t>(), S.nids.as<uint8_t>(), S.side[0].name_off.as<uint32_t>(), n, verbose, S.len.as<uint32_t>(), d_nclass);
+            kj_fmt_len<<<c->sm_count * 4, 256, 0, st>>>(S.tax.as<uint64_t>(), S.best.as<uint32_t>(), S.ids.as<uint64_t>(), S.nids.as<uint8_t>(), B.s[0].name_off.as<uint32_t>(), n, verbose, S.len.as<uint32_t>(), d_nclass);
             if ((rc = kj_scan_u32(S.len.as<uint32_t>(), n + 1, S.scan_tmp, (uint32_t*)S.totals.p, st))) return rc;
             uint32_t out_bytes = 0; CK(cudaMemcpyAsync(&out_bytes, S.totals.p, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
             if ((rc = S.out.need(out_bytes + 64))) return rc;
-            kj_fmt_write<<<c->sm_count * 4, 256, 0, st>>>(S.tax.as<uint64_t>(), S.best.as<uint32_t>(), S.ids.as<uint64_t>(), S.nids.as<uint8_t>(), S.side[0].names.as<char>(), S.side[0].name_off.as<uint32_t>(), n, verbose,
+            kj_fmt_write<<<c->sm_count * 4, 256, 0, st>>>(S.tax.as<uint64_t>(), S.best.as<uint32_t>(), S.ids.as<uint64_t>(), S.nids.as<uint8_t>(), B.s[0].names.as<char>(), B.s[0].name_off.as<uint32_t>(), n, verbose,
                                                        S.len.as<uint32_t>(), S.out.as<char>());
             CK(cudaGetLastError()); c->launches += 6;
-            lap(4);
             for (size_t o = 0; o < out_bytes; o += out_cap) {
                 const size_t m = std::min<size_t>(out_cap, out_bytes - o); char* hb = S.wr.get();
+                if (!hb) { kj_err() = "cudaMallocHost failed"; return KJ_ERR_NOMEM; }
                 CK(cudaMemcpyAsync(hb, S.out.as<char>() + o, m, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
                 S.wr.put(hb, m);
             }
-            n_reads += n; lap(5);
+            CK(cudaStreamSynchronize(st));
+            n_reads += n; S.tm[7] += kj_ms_since(t);
         }
-        // 4. carry the unconsumed tail to the front of the other text buffer
-        for (int f = 0; f < S.nfiles; f++) {
-            KjParsed& P = S.side[f]; uint64_t consumed = 0;
-            if (P.n_lines) { if ((rc = kj_parse_consumed(P, n, 0, st, consumed))) return rc; }
-            const uint64_t tail = P.nbytes - consumed; const int other = P.cur ^ 1;
-            if ((rc = P.text[other].need(tail + chunk + 1))) return rc;
-            if (tail) CK(cudaMemcpyAsync(P.text[other].p, P.text[P.cur].as<char>() + consumed, tail, cudaMemcpyDeviceToDevice, st));
-            P.cur = other; P.nbytes = tail;
-        }
-        if (all_eof) {
-            if (paired && S.side[1].n_rec > n) fprintf(stderr, "Warning: File %s has more reads then file %s\n", fn[1].c_str(), fn[0].c_str());        // kaiju.cpp:400-404
-            break;
-        }
-        // file 1 is exhausted (end of file, nothing carried over): the reference's loop ends here, whatever file 2 still holds (kaiju.cpp:288, 396-404)
-        if (paired && S.side[0].eof && S.side[0].nbytes == 0) {
-            if (S.side[1].nbytes > 0 || !S.side[1].eof) fprintf(stderr, "Warning: File %s has more reads then file %s\n", fn[1].c_str(), fn[0].c_str());
-            break;
-        }
+        const bool last = B.last;
+        { std::lock_guard<std::mutex> lk(S.mu); S.n_free++; } S.cv.notify_all();        // the parser may overwrite this slot's buffers now
+        if (last) break;
     }
+    S.parser.join();
+    c->launches += S.parse_launches;
     CK(cudaMemcpyAsync(&n_class, d_nclass, 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-    if (ftrace) fprintf(stderr, "KJ_FILES_TRACE chunks %llu  wait-chunk+h2d %.1f  prefetch-issue(reader wait) %.1f  parse %.1f  classify %.1f  format %.1f  d2h+writer %.1f  carry %.1f ms\n", (unsigned long long)nchunks, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[7]);
+    if (ftrace) fprintf(stderr, "KJ_FILES_TRACE chunks %llu  parser: slot-wait %.1f  h2d-wait+append %.1f  reader-wait %.1f  parse+carry %.1f | classifier: batch-wait %.1f  classify %.1f  format+d2h %.1f ms\n",
+                        (unsigned long long)S.nchunks, S.tm[0], S.tm[1], S.tm[2], S.tm[3], S.tm[5], S.tm[6], S.tm[7]);
     if (n_reads_out) *n_reads_out = n_reads; if (n_class_out) *n_class_out = n_class;
     return KJ_OK;
 }
@@ -543,9 +708,11 @@ extern "C" int kj_classify_files(kj_ctx* c, const char* in1, const char* in2, co
     if (!c || !in1 || !*in1) { kj_err() = "kj_classify_files: null argument"; return KJ_ERR_ARG; }
     if (c->params.input_is_protein && in2 && *in2) { kj_err() = "Protein input only supports one input file."; return KJ_ERR_ARG; }
     CK(cudaSetDevice(c->device));
-    KjFilesState* S = new KjFilesState();
+    if (!c->files) c->files = new KjFilesState();
+    KjFilesState* S = c->files;
     int rc = kj_classify_files_impl(c, *S, in1, in2, out_path, verbose, n_reads, n_classified);
-    S->cleanup();
-    delete S;
+    const std::string keep = kj_err();
+    S->end_call();
+    if (rc) kj_err() = keep; else if (S->wr.failed) { kj_err() = "write error on the output file"; rc = KJ_ERR_IO; }
     return rc;
 }

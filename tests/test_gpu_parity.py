@@ -345,6 +345,46 @@ def test_file_ingest_on_device(kb, golden, tmp_path, monkeypatch, chunk):
     clf.close()
 
 
+@pytest.mark.parametrize("chunk", ["1024", "20000", ""])
+def test_fastq_with_blank_lines(kb, golden, tmp_path, monkeypatch, chunk):
+    """Empty lines between FASTQ records (and at the end of the file) are skipped where the reference's reader skips them (kaiju.cpp:288-289,
+    341-348); empty lines inside a record count as the record's lines.  Output == the output for the clean files == the reference binary's."""
+    import random
+    from helpers import run_ref_kaiju
+    if chunk:
+        monkeypatch.setenv("KJ_INGEST_CHUNK", chunk)
+    rnd = random.Random(11); db = SynthDB(800, 3)
+    s1, o1, s2, o2 = db.reads(93, 0, 500, 150, True)
+    r1 = [s1[int(o1[i]):int(o1[i + 1])].tobytes().decode() for i in range(500)]; r2 = [s2[int(o2[i]):int(o2[i + 1])].tobytes().decode() for i in range(500)]
+    def write(path, reads, blanks, mate):
+        with open(path, "w") as f:
+            for i, sq in enumerate(reads):
+                if blanks and i and rnd.random() < 0.2:
+                    f.write("\n" * rnd.choice([1, 1, 2, 5]))
+                if blanks and i % 97 == 5:
+                    sq = ""                                                   # an empty sequence line is a line of the record, not a skipped one
+                    f.write("@r%d/%d\n\n+\n\n" % (i, mate))
+                    continue
+                f.write("@r%d/%d\n%s\n+\n%s\n" % (i, mate, sq, "I" * len(sq)))
+            if blanks:
+                f.write("\n\n\n")
+    clean1, clean2, b1, b2 = (str(tmp_path / x) for x in ("c1.fq", "c2.fq", "b1.fq", "b2.fq"))
+    r1c = [("" if i % 97 == 5 else x) for i, x in enumerate(r1)]; r2c = [("" if i % 97 == 5 else x) for i, x in enumerate(r2)]
+    write(clean1, r1c, False, 1); write(clean2, r2c, False, 2); write(b1, r1, True, 1); write(b2, r2, True, 2)
+    clf = kb.Classifier(golden.fmi, golden.nodes, device=0, params=kb.make_params("greedy", e=3))
+    outs = []
+    for a, b in ((clean1, clean2), (b1, b2), (b1, clean2), (clean1, None), (b1, None)):
+        o = str(tmp_path / "o.tsv"); n, k = clf.classify_files(a, b, o, verbose=True)
+        assert n == 500
+        outs.append(open(o).read())
+    assert outs[0] == outs[1] == outs[2] and outs[3] == outs[4] and outs[0].count("C\t") > 200
+    clf.close()
+    if have_ref():
+        from helpers import parse_kaiju_output
+        assert parse_kaiju_output(outs[1]) == run_ref_kaiju(golden.nodes, golden.fmi, b1, b2, mode="greedy", e=3, threads=1)
+        assert parse_kaiju_output(outs[4]) == run_ref_kaiju(golden.nodes, golden.fmi, b1, None, mode="greedy", e=3, threads=1)
+
+
 def test_per_taxon_counts(kb, golden, tmp_path, monkeypatch):
     """The dense per-taxon count vector in HBM (kaiju2table's input): equals a histogram of the per-read results for the host-buffer,
     device-buffer and file entry points; a call repeated after a variant-ring overflow is counted once."""
