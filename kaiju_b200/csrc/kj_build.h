@@ -259,8 +259,10 @@ static int kj_device_build_kmer(kj_ctx* c, int k, uint64_t& tot) {
         CK(cudaGetLastError()); CK(cudaMemcpy(H.quirk_d, c->d_quirk, sizeof H.quirk_d, cudaMemcpyDeviceToHost)); c->launches++;
     }
     H.kmer_k = 0;
-    if (k < 2 || k > 6 || H.alen != 21) return KJ_OK;
+    if (k < 2 || k > 7 || H.alen != 21) return KJ_OK;
     uint64_t n_final = 1; for (int d = 0; d < k; d++) n_final *= 20;
+    { size_t fr = 0, to = 0; CK(cudaMemGetInfo(&fr, &to));      // two level buffers + the final table next to the index: a smaller k when that does not fit
+      while (k > 2 && (double)n_final * (2.0 * sizeof(KjKmer) + sizeof(KjKmer32)) > 0.8 * (double)fr) { k--; n_final /= 20; } }
     KjKmer* d_a = nullptr; KjKmer* d_b = nullptr;
     CK(cudaMalloc((void**)&d_a, n_final * sizeof(KjKmer))); struct Free { void* p; ~Free() { if (p) cudaFree(p); } } fa{d_a};
     CK(cudaMalloc((void**)&d_b, n_final * sizeof(KjKmer))); Free fb{d_b};
