@@ -252,13 +252,15 @@ static int kj_device_build(kj_ctx* c, const kj_index_view& v, const uint8_t lcod
 }
 
 // quirk constants and the k-mer table need rank queries on the finished records: run after the device descriptor exists
-static int kj_device_build_kmer(kj_ctx* c, int k, uint64_t& tot) {
+// d_dst/k_out: where the table and its k go (default: the context's table for both modes); the second, larger table of the MEM kernels passes its own
+static int kj_device_build_kmer(kj_ctx* c, int k, uint64_t& tot, void** d_dst = nullptr, int* k_out = nullptr) {
     KjHostIndex& H = c->H; const int wide = H.wide;
-    if (H.quirk_lo != ~0ull) {
+    if (!d_dst) { d_dst = &c->d_kmer; k_out = &H.kmer_k; }
+    if (H.quirk_lo != ~0ull && d_dst == &c->d_kmer) {
         if (wide) kj_bld_quirk<uint64_t><<<1, 32>>>(c->d_ix, H.bwtlen - 65536ull, c->d_quirk); else kj_bld_quirk<uint32_t><<<1, 32>>>(c->d_ix, H.bwtlen - 65536ull, c->d_quirk);
         CK(cudaGetLastError()); CK(cudaMemcpy(H.quirk_d, c->d_quirk, sizeof H.quirk_d, cudaMemcpyDeviceToHost)); c->launches++;
     }
-    H.kmer_k = 0;
+    *k_out = 0;
     if (k < 2 || k > 7 || H.alen != 21) return KJ_OK;
     uint64_t n_final = 1; for (int d = 0; d < k; d++) n_final *= 20;
     { size_t fr = 0, to = 0; CK(cudaMemGetInfo(&fr, &to));      // two level buffers + the final table next to the index: a smaller k when that does not fit
@@ -275,12 +277,12 @@ static int kj_device_build_kmer(kj_ctx* c, int k, uint64_t& tot) {
         CK(cudaGetLastError()); c->launches++;
         std::swap(d_a, d_b); fa.p = d_a; fb.p = d_b; n_cur *= 20;
     }
-    if (wide) { c->d_kmer = d_a; fa.p = nullptr; tot += n_final * sizeof(KjKmer); }
+    if (wide) { *d_dst = d_a; fa.p = nullptr; tot += n_final * sizeof(KjKmer); }
     else {
-        CK(cudaMalloc(&c->d_kmer, n_final * sizeof(KjKmer32))); tot += n_final * sizeof(KjKmer32);
-        kj_bld_kmer_narrow<<<c->sm_count * 8, 256>>>(d_a, n_final, (KjKmer32*)c->d_kmer); CK(cudaGetLastError()); c->launches++;
+        CK(cudaMalloc(d_dst, n_final * sizeof(KjKmer32))); tot += n_final * sizeof(KjKmer32);
+        kj_bld_kmer_narrow<<<c->sm_count * 8, 256>>>(d_a, n_final, (KjKmer32*)*d_dst); CK(cudaGetLastError()); c->launches++;
     }
     CK(cudaDeviceSynchronize());
-    H.kmer_k = k;
+    *k_out = k;
     return KJ_OK;
 }

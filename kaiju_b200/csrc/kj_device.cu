@@ -211,6 +211,7 @@ struct kj_ctx {
     KjHostIndex H;                 // big arrays are released after upload; small ones stay
     KjDevIndex dix{};              // host copy of the descriptor (device pointers inside)
     KjDevIndex* d_ix = nullptr; KjTables* d_tables = nullptr;
+    KjDevIndex* d_ix_mem = nullptr; void* d_kmer_mem = nullptr; int kmer_k_mem = 0;      // the MEM kernels' own descriptor: same index, 7-mer table (kj_create)
     void* d_rank = nullptr; void* d_letters = nullptr; void* d_sa_tax = nullptr; void* d_seq_tax = nullptr;
     void* d_sa_acc = nullptr; void* d_seq_acc = nullptr;
     uint32_t* d_acc[2] = {nullptr, nullptr}; uint8_t* d_nacc[2] = {nullptr, nullptr}; char* d_frag[2] = {nullptr, nullptr}; uint32_t* d_fraglen[2] = {nullptr, nullptr}; size_t d_v2_cap = 0, d_frag_stride = 0;
@@ -309,6 +310,7 @@ static int upload_evalue_breaks(kj_ctx* c) {
     return KJ_OK;
 }
 
+static thread_local bool kj_transient_ctx = false;      // the base context of kj_create_scaled lives for the construction only: no second k-mer table
 static int new_ctx(kj_ctx** out, int device, const kj_params* params) {
     int rc = kj_check_params(*params); if (rc) return rc;
     int ndev = 0;
@@ -336,6 +338,11 @@ static int upload_descriptor(kj_ctx* c) {
     D.quirk_lo = H.quirk_lo; D.mono = (H.quirk_lo == ~0ull && !getenv("KJ_NOMONO")) ? 1 : 0; D.quirk_d = c->d_quirk;      // KJ_NOMONO: developer hook (A/B of the chain bounds)
     if (!c->d_ix) CK(cudaMalloc((void**)&c->d_ix, sizeof(KjDevIndex)));
     CK(cudaMemcpy(c->d_ix, &D, sizeof(KjDevIndex), cudaMemcpyHostToDevice));
+    if (c->d_kmer_mem && c->kmer_k_mem) {
+        KjDevIndex M = D; M.kmer = c->d_kmer_mem; M.kmer_k = c->kmer_k_mem;
+        if (!c->d_ix_mem) CK(cudaMalloc((void**)&c->d_ix_mem, sizeof(KjDevIndex)));
+        CK(cudaMemcpy(c->d_ix_mem, &M, sizeof(KjDevIndex), cudaMemcpyHostToDevice));
+    }
     return KJ_OK;
 }
 static int upload_small(kj_ctx* c, uint64_t& tot) {
@@ -389,6 +396,13 @@ static int create_ctx_device(kj_ctx** out, int device, const kj_params* params, 
     c->H.kmer_k = 0;
     if ((rc = upload_descriptor(c))) return rc;
     { const char* ek = getenv("KJ_KMER_K"); if ((rc = kj_device_build_kmer(c, ek ? atoi(ek) : kj_default_kmer_k(c->H.bwtlen), tot))) return rc; }
+    // MEM runs 4 % faster with the intervals of all 20^7 7-mers (10.2 GB below 2^32 rows): one look-up replaces the first LF step of every chain, the one
+    // with all 32 lanes alive.  Greedy loses 2 % with it (its seeds rarely get that far), so it keeps the 6-mer table: two descriptors, one index.
+    // Only where HBM is plentiful: narrow indexes, and the two level buffers of the construction (41 GB) must fit next to the index.
+    if (!c->H.wide && c->H.kmer_k == 6 && !kj_transient_ctx && !getenv("KJ_KMER_K") && !getenv("KJ_NO_KMER7")) {
+        size_t fr = 0, to = 0; CK(cudaMemGetInfo(&fr, &to));
+        if ((double)fr > 1.28e9 * (2.0 * sizeof(KjKmer) + sizeof(KjKmer32)) + 16e9 && (rc = kj_device_build_kmer(c, 7, tot, &c->d_kmer_mem, &c->kmer_k_mem))) return rc;
+    }
     std::vector<uint32_t>().swap(c->H.seq_tax);
     if ((rc = finish_ctx(c, tot))) return rc;
     CK(cudaDeviceSynchronize());
@@ -404,7 +418,7 @@ extern "C" int kj_create(kj_ctx** out, int device, const kj_params* params, cons
 extern "C" int kj_create_scaled(kj_ctx** out, int device, const kj_params* params, const kj_index_view* index, const kj_taxonomy_view* taxonomy, uint32_t copies) {
     if (!out || !params || !index || !taxonomy) { kj_err() = "kj_create_scaled: null argument"; return KJ_ERR_ARG; }
     if (copies <= 1) return kj_create(out, device, params, index, taxonomy);
-    kj_ctx* base = nullptr; int rc = create_ctx_device(&base, device, params, *index, *taxonomy, 1, nullptr); if (rc) return rc;
+    kj_ctx* base = nullptr; kj_transient_ctx = true; int rc = create_ctx_device(&base, device, params, *index, *taxonomy, 1, nullptr); kj_transient_ctx = false; if (rc) return rc;
     rc = create_ctx_device(out, device, params, *index, *taxonomy, copies, base);
     kj_destroy(base);
     return rc;
@@ -446,6 +460,7 @@ extern "C" void kj_destroy(kj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     kj_files_state_free(c->files); c->files = nullptr;
+    if (c->d_ix_mem) cudaFree(c->d_ix_mem); if (c->d_kmer_mem) cudaFree(c->d_kmer_mem);
     void* ptrs[] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_tax_parent, c->d_tax_depth, c->d_tax_id, c->d_lnfact, c->d_kmer, c->d_tables, c->d_ix,
                     c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evbreaks, c->d_ws, c->d_counts, c->d_counts_pending, c->d_quirk, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
                     c->d_seq[0][0], c->d_seq[0][1], c->d_seq[1][0], c->d_seq[1][1], c->d_off[0][0], c->d_off[0][1], c->d_off[1][0], c->d_off[1][1],
@@ -478,9 +493,10 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
     const KjSmemLayout lay = kj_smem_layout(rp);
     const bool fixed = !verbose && kj_use_fixed(rp);
+    const KjDevIndex* dix = (rp.mode == 0 && c->d_ix_mem && rp.m >= (uint32_t)c->kmer_k_mem) ? c->d_ix_mem : c->d_ix;
 #define KJ_LAUNCH(M, T) if (verbose) { if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, true); else KJ_LAUNCH3(M, T, false, false, true); } \
                         else if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, false); else if (fixed) KJ_LAUNCH3(M, T, false, true, false); else KJ_LAUNCH3(M, T, false, false, false)
-#define KJ_LAUNCH3(M, T, G, F, V) kj_classify_kernel<M, T, G, F, V><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(c->d_ix, rp, lay, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, d_compact, \
+#define KJ_LAUNCH3(M, T, G, F, V) kj_classify_kernel<M, T, G, F, V><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(dix, rp, lay, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, d_compact, \
             c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
             c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), \
             rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err, d_acc, d_nacc, d_frag, frag_stride, d_fraglen)

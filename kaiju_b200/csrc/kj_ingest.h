@@ -349,12 +349,16 @@ static int kj_parse_side(int sm_count, KjParsed& P, KjBatchSide& O, const std::s
     return KJ_OK;
 }
 
-struct KjChunk { char* p = nullptr; size_t n = 0; bool eof = false; std::string error; };
-struct KjFileReader {   // per input file: gz (zlib, one thread) or plain (a pool of pread() threads) -> pinned chunks
-    gzFile fp = nullptr; int fd = -1; uint64_t file_off = 0; std::string path; size_t chunk; std::vector<char*> pool; std::deque<KjChunk> ready; std::deque<char*> free_;
-    std::mutex mu; std::condition_variable cv; std::thread th; bool stop = false; int device = 0, nbuf = 3; KjPinnedPool* pinned = nullptr;
-    // plain files: NT worker threads copy 1 MB slices of the current chunk out of the page cache in parallel (one copy stream per thread;
-    // a single thread moves ~1-3 GB/s, the device pipeline wants > 20 GB/s)
+// One I/O chunk of an input file, already on its way to the device: slot of the reader's staging ring + the event of its copy
+struct KjStaged { int slot = -1; size_t n = 0; bool eof = false; char last = 0; cudaEvent_t ev = nullptr; std::string error; };
+// Per input file: gz (zlib, one thread) or plain (a pool of pread() threads) -> two alternating pinned buffers -> host-to-device copies on the
+// reader's own stream into a ring of device staging buffers.  The parser only ever sees device memory; the pinned footprint is two chunks.
+struct KjFileReader {
+    gzFile fp = nullptr; int fd = -1; uint64_t file_off = 0; std::string path; size_t chunk = 0; int device = 0; KjPinnedPool* pinned = nullptr;
+    char* pin[2] = {nullptr, nullptr}; cudaEvent_t pin_ev[2] = {nullptr, nullptr}; bool pin_busy[2] = {false, false}; cudaStream_t stream = nullptr;
+    std::vector<KjDevBuf> ring; std::vector<cudaEvent_t> ring_ev; std::deque<int> free_slots; std::deque<KjStaged> ready;
+    std::mutex mu; std::condition_variable cv; std::thread th; bool stop = false;
+    // plain files: NT worker threads copy 1 MB slices of the current chunk out of the page cache in parallel (a single thread moves ~1-3 GB/s)
     static constexpr size_t SLICE = 1u << 20;
     std::vector<std::thread> workers; std::mutex wmu; std::condition_variable wcv, wdone; char* wbuf = nullptr; size_t wnext = 0, wslices = 0, wleft = 0; uint64_t wgen = 0; bool wstop = false, werr = false;
     std::vector<size_t> wgot;
@@ -377,8 +381,8 @@ struct KjFileReader {   // per input file: gz (zlib, one thread) or plain (a poo
             seen = gen;
         }
     }
-    int open(const std::string& p, size_t chunk_bytes, int nbuf_, int device_, KjPinnedPool* pp) {
-        path = p; chunk = chunk_bytes; nbuf = nbuf_; device = device_; pinned = pp;
+    int open(const std::string& p, size_t chunk_bytes, int depth, int device_, KjPinnedPool* pp) {
+        path = p; chunk = chunk_bytes; device = device_; pinned = pp; stop = false; wstop = false; file_off = 0;
         fd = ::open(p.c_str(), O_RDONLY);
         if (fd < 0) { kj_err() = "Could not open file " + p; return KJ_ERR_IO; }
         unsigned char magic[2] = {0, 0}; const ssize_t got = ::pread(fd, magic, 2, 0);
@@ -388,28 +392,30 @@ struct KjFileReader {   // per input file: gz (zlib, one thread) or plain (a poo
             gzbuffer(fp, 1 << 20);
         } else {
             posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
-            unsigned nt = std::max(2u, std::min(16u, std::thread::hardware_concurrency() / 4u));
+            unsigned nt = std::max(2u, std::min(8u, std::thread::hardware_concurrency() / 4u));
             if (const char* v = getenv("KJ_IO_THREADS")) { const long x = atol(v); if (x >= 1 && x <= 64) nt = (unsigned)x; }      // tuning hook
             wgot.assign((chunk + SLICE - 1) / SLICE, 0);
             for (unsigned t = 0; t < nt; t++) workers.emplace_back([this] { worker(); });
         }
+        if ((int)ring.size() != depth) { for (auto& b : ring) b.release(); ring.assign((size_t)depth, KjDevBuf()); }
+        free_slots.clear(); ready.clear(); for (int k = 0; k < depth; k++) free_slots.push_back(k);
         th = std::thread([this] { run(); });
         return KJ_OK;
     }
+    void fail(const std::string& what) { KjStaged e; e.error = what; { std::lock_guard<std::mutex> lk(mu); ready.push_back(e); } cv.notify_all(); }
     void run() {
-        cudaSetDevice(device);
-        for (;;) {
-            char* b = nullptr;
-            {   // a pinned buffer: a returned one, or (up to nbuf) a new one -- allocated here, next to the running pipeline, not before it starts
-                std::unique_lock<std::mutex> lk(mu);
-                if (free_.empty() && (int)pool.size() < nbuf) {
-                    lk.unlock(); b = pinned->get(chunk); lk.lock();
-                    if (b) pool.push_back(b);
-                    else { KjChunk ck; ck.error = "cudaMallocHost failed"; ready.push_back(ck); cv.notify_all(); return; }
-                } else { cv.wait(lk, [&] { return stop || !free_.empty(); }); if (stop) return; b = free_.front(); free_.pop_front(); }
-                if (stop) { free_.push_back(b); return; }
+        if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice failed"); return; }
+        if (!stream && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { fail("cudaStreamCreate failed"); return; }
+        while (ring_ev.size() < ring.size()) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { fail("cudaEventCreate failed"); return; } ring_ev.push_back(e); }
+        char prev_last = 0;
+        for (uint64_t it = 0;; it++) {
+            const int pb = (int)(it & 1);
+            if (!pin[pb]) {       // allocated here, next to the running pipeline, not before it starts
+                pin[pb] = pinned->get(chunk);
+                if (!pin[pb] || cudaEventCreateWithFlags(&pin_ev[pb], cudaEventDisableTiming) != cudaSuccess) { fail("cudaMallocHost failed"); return; }
             }
-            KjChunk ck; ck.p = b; size_t got = 0;
+            if (pin_busy[pb]) { cudaEventSynchronize(pin_ev[pb]); pin_busy[pb] = false; }     // the copy that read this buffer two chunks ago
+            char* b = pin[pb]; KjStaged ck; size_t got = 0;
             if (fd >= 0) {
                 const size_t ns = (chunk + SLICE - 1) / SLICE;
                 {
@@ -432,26 +438,36 @@ struct KjFileReader {   // per input file: gz (zlib, one thread) or plain (a poo
                 if (r == 0) { ck.eof = true; break; }
                 got += (size_t)r;
             }
-            ck.n = got;
-            const bool last = ck.eof || !ck.error.empty();
+            if (!ck.error.empty()) { fail(ck.error); return; }
+            ck.n = got; if (got) prev_last = b[got - 1]; ck.last = prev_last;
+            {   // a free staging buffer on the device
+                std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || !free_slots.empty(); }); if (stop) return;
+                ck.slot = free_slots.front(); free_slots.pop_front();
+            }
+            if (ring[ck.slot].cap < chunk + 16 && ring[ck.slot].need(chunk + 16) != KJ_OK) { fail("cudaMalloc failed (staging ring)"); return; }
+            if (got && cudaMemcpyAsync(ring[ck.slot].p, b, got, cudaMemcpyHostToDevice, stream) != cudaSuccess) { fail("cudaMemcpyAsync failed"); return; }
+            cudaEventRecord(ring_ev[ck.slot], stream); cudaEventRecord(pin_ev[pb], stream); pin_busy[pb] = true; ck.ev = ring_ev[ck.slot];
+            const bool last = ck.eof;
             { std::lock_guard<std::mutex> lk(mu); ready.push_back(ck); }
             cv.notify_all();
             if (last) return;
         }
     }
-    KjChunk next() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !ready.empty(); }); KjChunk ck = ready.front(); ready.pop_front(); return ck; }
-    void give_back(char* b) { { std::lock_guard<std::mutex> lk(mu); free_.push_back(b); } cv.notify_all(); }
+    KjStaged next() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !ready.empty(); }); KjStaged ck = ready.front(); ready.pop_front(); return ck; }
+    void release_slot(int slot) { { std::lock_guard<std::mutex> lk(mu); free_slots.push_back(slot); } cv.notify_all(); }
     void close() {
         { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_all();
         if (th.joinable()) th.join();
         { std::lock_guard<std::mutex> lk(wmu); wstop = true; } wcv.notify_all();
         for (auto& w : workers) if (w.joinable()) w.join();
         workers.clear();
+        if (stream) cudaStreamSynchronize(stream);
         if (fp) gzclose(fp); fp = nullptr;
         if (fd >= 0) ::close(fd); fd = -1;
-        for (char* b : pool) pinned->put(b, chunk); pool.clear(); ready.clear(); free_.clear();
-        stop = false; wstop = false; file_off = 0; wgen = 0; wslices = 0; wnext = 0; wleft = 0;
+        for (int k = 0; k < 2; k++) { if (pin[k]) pinned->put(pin[k], chunk); pin[k] = nullptr; pin_busy[k] = false; if (pin_ev[k]) cudaEventDestroy(pin_ev[k]); pin_ev[k] = nullptr; }
+        ready.clear(); free_slots.clear(); wgen = 0; wslices = 0; wnext = 0; wleft = 0;
     }
+    void release() { for (auto& b : ring) b.release(); ring.clear(); for (auto e : ring_ev) cudaEventDestroy(e); ring_ev.clear(); if (stream) cudaStreamDestroy(stream); stream = nullptr; }
 };
 struct KjWriter {   // ordered output: pinned buffers filled by D2H copies, written by one thread
     FILE* out = nullptr; bool own = false; std::vector<char*> pool; size_t cap = 0; int nbuf = 3; std::deque<std::pair<char*, size_t>> ready; std::deque<char*> free_;
@@ -485,103 +501,95 @@ struct KjWriter {   // ordered output: pinned buffers filled by D2H copies, writ
     }
 };
 
-struct KjPrefetch { KjDevBuf stage[2]; int cur = 0; cudaEvent_t done = nullptr; bool pending = false, eof = false; char* host = nullptr; size_t n = 0; char last = 0; };
-// One parsed chunk on its way from the parser thread to the classifying thread
-struct KjBatch { KjBatchSide s[2]; uint64_t n = 0; unsigned int maxlen[2] = {0, 0}; bool last = false; int rc = KJ_OK; std::string err; };
-#define KJ_FILE_SLOTS 3
+// One parsed batch on its way from the parser thread to the classifying thread
+struct KjBatch { KjBatchSide s[2]; uint64_t n = 0; unsigned int maxlen[2] = {0, 0}; bool last = false; };
+// One of the two classification lanes of the calling thread: while the kernel of batch k runs on one lane, batch k+1 is launched on the other
+// (its CTAs fill the SMs as the first kernel's CTAs retire), and batch k-1 is formatted and written
+struct KjLane { KjDevBuf tax, best, ids, nids, len, out, scan_tmp, totals; int batch = -1; bool busy = false; };
+#define KJ_FILE_SLOTS 4
 // Everything kj_classify_files needs besides the context; kept in the context between calls (device buffers and pinned memory are reused)
 struct KjFilesState {
-    KjParsed side[2]; KjFileReader rd[2]; KjWriter wr; KjPrefetch pf[2]; int nfiles = 1; bool rd_open[2] = {false, false}, wr_open = false;
-    KjBatch slot[KJ_FILE_SLOTS]; KjPinnedPool pinned; cudaStream_t sp = nullptr, sh = nullptr; KjDevBuf pstat;
-    KjDevBuf tax, best, ids, nids, len, out, scan_tmp, totals;
-    // parser thread -> classifying thread: filled slots in order; slots come back when their chunk has been written
+    KjParsed side[2]; KjFileReader rd[2]; KjWriter wr; int nfiles = 1; bool rd_open[2] = {false, false}, wr_open = false;
+    KjBatch slot[KJ_FILE_SLOTS]; KjLane lane[2]; KjPinnedPool pinned; cudaStream_t sp = nullptr; KjDevBuf pstat, pending2;
+    // parser thread -> classifying thread: filled slots in order; slots come back when their batch has been written
     std::mutex mu; std::condition_variable cv; std::deque<int> filled; int n_free = KJ_FILE_SLOTS; bool abort = false; std::thread parser;
     std::string fn[2], perr; int prc = KJ_OK;                 // input names; the parser thread's error
-    uint64_t parse_launches = 0; double tm[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; uint64_t nchunks = 0;
+    uint64_t parse_launches = 0; double tm[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; uint64_t nbatches = 0;
     void end_call() {      // threads, files and in-flight copies of one call
         { std::lock_guard<std::mutex> lk(mu); abort = true; } cv.notify_all();
         if (parser.joinable()) parser.join();
         for (int f = 0; f < 2; f++) {
-            if (pf[f].pending && pf[f].done) cudaEventSynchronize(pf[f].done);
-            if (pf[f].pending && rd_open[f]) rd[f].give_back(pf[f].host);
-            pf[f].pending = false; pf[f].eof = false;
             if (rd_open[f]) rd[f].close(); rd_open[f] = false;
             KjParsed& P = side[f]; P.cur = 0; P.nbytes = 0; P.fastq = -1; P.n_lines = P.n_rec = P.consumed = 0; P.eof = false;
         }
         if (wr_open) wr.close(); wr_open = false;
-        filled.clear(); n_free = KJ_FILE_SLOTS; abort = false;
+        filled.clear(); n_free = KJ_FILE_SLOTS; abort = false; lane[0].busy = lane[1].busy = false;
     }
     void release() {       // with the context
-        for (int f = 0; f < 2; f++) { side[f].release(); pf[f].stage[0].release(); pf[f].stage[1].release(); if (pf[f].done) cudaEventDestroy(pf[f].done); pf[f].done = nullptr; }
+        for (int f = 0; f < 2; f++) { side[f].release(); rd[f].release(); }
         for (KjBatch& b : slot) for (KjBatchSide& o : b.s) for (KjDevBuf* d : {&o.seq, &o.off, &o.names, &o.name_off}) d->release();
-        for (KjDevBuf* b : {&tax, &best, &ids, &nids, &len, &out, &scan_tmp, &totals, &pstat}) b->release();
-        if (sp) cudaStreamDestroy(sp); if (sh) cudaStreamDestroy(sh); sp = sh = nullptr;
+        for (KjLane& l : lane) for (KjDevBuf* d : {&l.tax, &l.best, &l.ids, &l.nids, &l.len, &l.out, &l.scan_tmp, &l.totals}) d->release();
+        pstat.release(); pending2.release();
+        if (sp) cudaStreamDestroy(sp); sp = nullptr;
         pinned.release();
     }
 };
 static void kj_files_state_free(KjFilesState* S) { if (!S) return; S->end_call(); S->release(); delete S; }
 
-// next chunk of file f: pinned buffer -> device staging buffer, asynchronously on the copy stream
-static int kj_prefetch(KjFilesState& S, int f) {
-    KjPrefetch& F = S.pf[f];
-    KjChunk ck = S.rd[f].next();
-    if (!ck.error.empty()) { kj_err() = ck.error; return KJ_ERR_IO; }
-    F.cur ^= 1; int rc = F.stage[F.cur].need(ck.n + 16); if (rc) return rc;
-    if (!F.done) CK(cudaEventCreateWithFlags(&F.done, cudaEventDisableTiming));
-    if (ck.n) CK(cudaMemcpyAsync(F.stage[F.cur].p, ck.p, ck.n, cudaMemcpyHostToDevice, S.sh));
-    CK(cudaEventRecord(F.done, S.sh));
-    F.pending = true; F.eof = ck.eof; F.host = ck.p; F.n = ck.n; F.last = ck.n ? ck.p[ck.n - 1] : 0;
-    return KJ_OK;
-}
-
 static inline double kj_ms_since(std::chrono::steady_clock::time_point& t) { const auto n = std::chrono::steady_clock::now(); const double d = std::chrono::duration<double, std::milli>(n - t).count(); t = n; return d; }
 
-// Parser thread: file chunks -> device text -> packed reads, names and offsets of the complete records, one KjBatch per chunk.
-// Stage 1 of the two-stage pipeline: while the caller's thread classifies and formats chunk k on its stream, this thread parses
-// chunk k+1 (and k+2) on another; the carry (the incomplete record at the end of a chunk) only depends on the parse.
-static int kj_parse_chunks(int device, int sm_count, KjFilesState& S, size_t chunk, bool paired) {
+// Parser thread: staged file chunks -> device text -> packed reads, names and offsets of the complete records, one KjBatch per round.
+// Stage 1 of the pipeline: while the caller's thread classifies and formats earlier batches on its streams, this thread assembles and parses the
+// next ones on another; the carry (the incomplete record at the end of a batch) only depends on the parse.  A batch is `target` bytes of text
+// per file: one I/O chunk at first (the pipeline starts after the first 16 MB), doubling up to batch_max (fewer, longer classify launches).
+static int kj_parse_chunks(int device, int sm_count, KjFilesState& S, size_t chunk, size_t batch_max, bool paired) {
     CK(cudaSetDevice(device));
     const std::string* fn = S.fn;
     cudaStream_t st = S.sp; int rc; auto t = std::chrono::steady_clock::now();
     uint32_t* d_stat = S.pstat.as<uint32_t>();       // [0,1] longest read of each side, [2] error bits of the parse kernels
-    for (int f = 0; f < S.nfiles; f++) if ((rc = kj_prefetch(S, f))) return rc;
+    size_t target = chunk; std::vector<int> used[2];
     for (;;) {
         int si;
         { std::unique_lock<std::mutex> lk(S.mu); S.cv.wait(lk, [&] { return S.abort || S.n_free > 0; }); if (S.abort) return KJ_OK; S.n_free--; }
-        si = (int)(S.nchunks % KJ_FILE_SLOTS); KjBatch& B = S.slot[si]; S.nchunks++;
+        si = (int)(S.nbatches % KJ_FILE_SLOTS); KjBatch& B = S.slot[si]; S.nbatches++;
         S.tm[0] += kj_ms_since(t);
-        // 1. top up both sides: carry (already at the front of the device text) + the chunk that was prefetched into the staging buffer
+        // 1. top up both sides to `target` bytes: the carry is already at the front of the device text, staged chunks are appended behind it
         for (int f = 0; f < S.nfiles; f++) {
-            KjParsed& P = S.side[f]; KjPrefetch& F = S.pf[f];
-            if (!F.pending) continue;
-            CK(cudaEventSynchronize(F.done));                          // H2D finished: the pinned chunk goes back to the reader
-            S.rd[f].give_back(F.host); F.pending = false;
-            if ((P.nbytes + F.n + 1) > P.text[P.cur].cap) {            // grow: move the carry into the larger buffer
-                KjDevBuf nb; if ((rc = nb.need(P.nbytes + F.n + chunk + 1))) return rc;
-                if (P.nbytes) CK(cudaMemcpyAsync(nb.p, P.text[P.cur].p, P.nbytes, cudaMemcpyDeviceToDevice, st));
-                CK(cudaStreamSynchronize(st)); P.text[P.cur].release(); P.text[P.cur] = nb;
+            KjParsed& P = S.side[f];
+            while (!P.eof && P.nbytes < target) {
+                KjStaged ck = S.rd[f].next();
+                if (!ck.error.empty()) { kj_err() = ck.error; return KJ_ERR_IO; }
+                if ((P.nbytes + ck.n + 1) > P.text[P.cur].cap) {           // grow: move what is there into the larger buffer
+                    KjDevBuf nb; if ((rc = nb.need(P.nbytes + ck.n + target + chunk + 1))) return rc;
+                    if (P.nbytes) CK(cudaMemcpyAsync(nb.p, P.text[P.cur].p, P.nbytes, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaStreamSynchronize(st)); P.text[P.cur].release(); P.text[P.cur] = nb;
+                }
+                CK(cudaStreamWaitEvent(st, ck.ev, 0));
+                if (ck.n) CK(cudaMemcpyAsync(P.text[P.cur].as<char>() + P.nbytes, S.rd[f].ring[ck.slot].p, ck.n, cudaMemcpyDeviceToDevice, st));
+                used[f].push_back(ck.slot);
+                if ((int)used[f].size() + 2 >= (int)S.rd[f].ring.size()) {   // never hold the whole ring: the reader needs free staging buffers to get ahead
+                    CK(cudaStreamSynchronize(st)); for (int sl : used[f]) S.rd[f].release_slot(sl); used[f].clear();
+                }
+                P.nbytes += ck.n;
+                if (ck.eof) {
+                    P.eof = true;
+                    if (P.nbytes && ck.last != '\n') { CK(cudaMemsetAsync(P.text[P.cur].as<char>() + P.nbytes, '\n', 1, st)); P.nbytes += 1; }      // the last line of a file may lack its newline
+                }
             }
-            if (F.n) CK(cudaMemcpyAsync(P.text[P.cur].as<char>() + P.nbytes, F.stage[F.cur].p, F.n, cudaMemcpyDeviceToDevice, st));
-            bool need_nl = false;
-            if (F.eof) {
-                P.eof = true; const uint64_t tot = P.nbytes + F.n;
-                if (tot) { char last = F.last; if (!F.n) { CK(cudaMemcpyAsync(&last, P.text[P.cur].as<char>() + tot - 1, 1, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); } need_nl = last != '\n'; }
-            }
-            P.nbytes += F.n;
-            if (need_nl) { CK(cudaMemsetAsync(P.text[P.cur].as<char>() + P.nbytes, '\n', 1, st)); P.nbytes += 1; }      // the last line of a file may lack its newline
         }
         S.tm[1] += kj_ms_since(t);
-        // ... and start the host-to-device copy of the following chunks on the copy stream (into the other staging buffer): it overlaps with the kernels below
-        for (int f = 0; f < S.nfiles; f++) if (!S.side[f].eof && (rc = kj_prefetch(S, f))) return rc;
-        S.tm[2] += kj_ms_since(t);
-        // 2. parse; a FASTQ chunk with an empty line where a header was expected (flag 64) is parsed again with the record phases from the automaton scan
+        // 2. parse; a FASTQ batch with an empty line where a header was expected (flag 64) is parsed again with the record phases from the automaton scan
         uint64_t n = 0; bool all_eof = false; uint64_t pos[2] = {0, 0}; uint32_t hstat[4] = {0, 0, 0, 0};
         for (int pass = 0; pass < 2; pass++) {
             CK(cudaMemsetAsync(d_stat, 0, 16, st));
-            for (int f = 0; f < S.nfiles; f++) if ((rc = kj_parse_side(sm_count, S.side[f], B.s[f], fn[f], st, d_stat + 2, &S.parse_launches, pass == 1))) return rc;
+            for (int f = 0; f < S.nfiles; f++) {
+                if ((rc = kj_parse_side(sm_count, S.side[f], B.s[f], fn[f], st, d_stat + 2, &S.parse_launches, pass == 1))) return rc;
+                // (kj_parse_side synchronises the stream: the staging buffers appended above are free again)
+                for (int sl : used[f]) S.rd[f].release_slot(sl); used[f].clear();
+            }
             n = S.side[0].n_rec; if (paired) n = std::min(n, S.side[1].n_rec);
             all_eof = S.side[0].eof && (!paired || S.side[1].eof);
-            if (n >= (1ull << 31)) { kj_err() = "kj_classify_files: chunk with too many records"; return KJ_ERR_UNSUPPORTED; }
+            if (n >= (1ull << 31)) { kj_err() = "kj_classify_files: batch with too many records"; return KJ_ERR_UNSUPPORTED; }
             if (n) {
                 if (paired) kj_names_equal<<<sm_count * 4, 256, 0, st>>>(B.s[0].names.as<char>(), B.s[0].name_off.as<uint32_t>(), B.s[1].names.as<char>(), B.s[1].name_off.as<uint32_t>(), n, d_stat + 2);
                 kj_maxlen_kernel<<<256, 256, 0, st>>>(B.s[0].off.as<uint64_t>(), n, d_stat);
@@ -593,18 +601,23 @@ static int kj_parse_chunks(int device, int sm_count, KjFilesState& S, size_t chu
             CK(cudaMemcpyAsync(hstat, d_stat, 16, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));       // the batch is complete in device memory from here on
             if (!(hstat[2] & 64u)) break;
         }
+        for (int f = 0; f < S.nfiles; f++) { for (int sl : used[f]) S.rd[f].release_slot(sl); used[f].clear(); }      // (a side without bytes does not synchronise in kj_parse_side)
         if (paired && all_eof && S.side[0].n_rec > S.side[1].n_rec) { kj_err() = "File " + fn[0] + " contains more reads then file " + fn[1]; return KJ_ERR_IO; }   // kaiju.cpp:337-340
         if (hstat[2] & 16u) { kj_err() = "malformed FASTQ record (a header line does not start with '@') in the input"; return KJ_ERR_IO; }
         if (n && (hstat[2] & 32u)) { kj_err() = "Read names are not identical between the two input files. Probably reads are not in the same order in both files."; return KJ_ERR_IO; }
-        B.n = n;
-        B.maxlen[0] = hstat[0]; B.maxlen[1] = hstat[1];
+        B.n = n; B.maxlen[0] = hstat[0]; B.maxlen[1] = hstat[1];
+        // 3. carry the unconsumed tail to the front of the other text buffer
+        if (target < batch_max) target = std::min(batch_max, target * 2);
         for (int f = 0; f < S.nfiles; f++) {
             KjParsed& P = S.side[f]; const uint64_t consumed = P.n_lines ? pos[f] : 0;
             const uint64_t tail = P.nbytes - consumed; const int other = P.cur ^ 1;
-            if ((rc = P.text[other].need(tail + chunk + 1))) return rc;
+            if ((rc = P.text[other].need(tail + target + chunk + 1))) return rc;
             if (tail) CK(cudaMemcpyAsync(P.text[other].p, P.text[P.cur].as<char>() + consumed, tail, cudaMemcpyDeviceToDevice, st));
             P.cur = other; P.nbytes = tail;
         }
+        // a side whose carry alone reaches the target cannot make progress by itself (a record longer than the batch, or the other file lagging):
+        // let the next round read more
+        for (int f = 0; f < S.nfiles; f++) if (!S.side[f].eof && S.side[f].nbytes >= target) target = S.side[f].nbytes + chunk;
         bool last = false;
         if (all_eof) {
             if (paired && S.side[1].n_rec > n) fprintf(stderr, "Warning: File %s has more reads then file %s\n", fn[1].c_str(), fn[0].c_str());        // kaiju.cpp:400-404
@@ -614,7 +627,7 @@ static int kj_parse_chunks(int device, int sm_count, KjFilesState& S, size_t chu
             if (S.side[1].nbytes > 0 || !S.side[1].eof) fprintf(stderr, "Warning: File %s has more reads then file %s\n", fn[1].c_str(), fn[0].c_str());
             last = true;
         }
-        B.last = last; B.rc = KJ_OK;
+        B.last = last;
         S.tm[3] += kj_ms_since(t);
         { std::lock_guard<std::mutex> lk(S.mu); S.filled.push_back(si); } S.cv.notify_all();
         if (last) return KJ_OK;
@@ -622,84 +635,120 @@ static int kj_parse_chunks(int device, int sm_count, KjFilesState& S, size_t chu
 }
 
 static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, const char* in2, const char* out_path, int verbose, uint64_t* n_reads_out, uint64_t* n_class_out) {
-    // developer hook KJ_FILES_TRACE: host time of each stage of the two threads (ms, summed over the chunks; waits included)
+    // developer hook KJ_FILES_TRACE: host time of each stage of the two threads (ms, summed over the batches; waits included)
     const bool ftrace = getenv("KJ_FILES_TRACE") != nullptr;
-    size_t chunk = 64u << 20;
-    if (const char* v = getenv("KJ_INGEST_CHUNK")) { long x = atol(v); if (x >= 256 && x <= (1l << 30)) chunk = (size_t)x; }       // test hook: many small chunks
+    size_t chunk = 16u << 20, batch_max = 128u << 20;
+    if (const char* v = getenv("KJ_INGEST_CHUNK")) { long x = atol(v); if (x >= 256 && x <= (1l << 30)) { chunk = (size_t)x; batch_max = chunk; } }       // test hook: many small batches
+    if (const char* v = getenv("KJ_INGEST_BATCH")) { long x = atol(v); if (x >= 256 && x <= (1l << 30)) batch_max = std::max((size_t)x, chunk); }
     const bool paired = in2 && *in2; S.nfiles = paired ? 2 : 1;
     S.fn[0] = in1; S.fn[1] = paired ? in2 : ""; S.perr.clear(); S.prc = KJ_OK;
     const std::string* fn = S.fn;
-    cudaStream_t st = c->stream[0];
     int rc;
-    if (!S.sp) CK(cudaStreamCreateWithFlags(&S.sp, cudaStreamNonBlocking));
-    if (!S.sh) CK(cudaStreamCreateWithFlags(&S.sh, cudaStreamNonBlocking));
-    for (int f = 0; f < S.nfiles; f++) { if ((rc = S.rd[f].open(fn[f], chunk, 3, c->device, &S.pinned))) return rc; S.rd_open[f] = true; }
+    if (!S.sp) { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&S.sp, cudaStreamNonBlocking, hi)); }    // the short parse kernels go first when SM slots free up
+    const int depth = (int)std::min<size_t>(64, batch_max / chunk + 4);
+    for (int f = 0; f < S.nfiles; f++) { if ((rc = S.rd[f].open(fn[f], chunk, depth, c->device, &S.pinned))) return rc; S.rd_open[f] = true; }
     const size_t out_cap = 16u << 20;
     if ((rc = S.wr.open(out_path, out_cap, 3, &S.pinned))) return rc; S.wr_open = true;
-    if ((rc = S.totals.need(64)) || (rc = S.pstat.need(64))) return rc;
-    uint64_t n_reads = 0; unsigned long long n_class = 0;
-    CK(cudaMemsetAsync(S.totals.p, 0, 64, st));
-    CK(cudaMemsetAsync(c->d_counts_pending, 0, (size_t)c->n_counts * 8, st));
-    CK(cudaStreamSynchronize(st));
-    unsigned long long* d_nclass = (unsigned long long*)((char*)S.totals.p + 16);
-    S.parse_launches = 0; S.nchunks = 0; for (double& x : S.tm) x = 0;
+    if ((rc = S.pstat.need(64)) || (rc = S.pending2.need((size_t)c->n_counts * 8 + 64))) return rc;
+    unsigned long long* pend[2] = {c->d_counts_pending, S.pending2.as<unsigned long long>()};
+    for (int l = 0; l < 2; l++) {
+        if ((rc = S.lane[l].totals.need(64))) return rc;
+        CK(cudaMemsetAsync(S.lane[l].totals.p, 0, 64, c->stream[l])); CK(cudaMemsetAsync(pend[l], 0, (size_t)c->n_counts * 8, c->stream[l])); CK(cudaStreamSynchronize(c->stream[l]));
+        S.lane[l].busy = false; S.lane[l].batch = -1;
+    }
+    uint64_t n_reads = 0;
+    S.parse_launches = 0; S.nbatches = 0; for (double& x : S.tm) x = 0;
     {   // the thread only touches S (which outlives this call) and its own copies
         KjFilesState* Sp = &S; const int dev = c->device, sms = c->sm_count;
-        S.parser = std::thread([Sp, dev, sms, chunk, paired] {
-            const int r = kj_parse_chunks(dev, sms, *Sp, chunk, paired);
+        S.parser = std::thread([Sp, dev, sms, chunk, batch_max, paired] {
+            const int r = kj_parse_chunks(dev, sms, *Sp, chunk, batch_max, paired);
             if (r) { std::lock_guard<std::mutex> lk(Sp->mu); Sp->prc = r; Sp->perr = kj_err(); Sp->filled.push_back(-1); }
             Sp->cv.notify_all();
         });
     }
     auto t = std::chrono::steady_clock::now();
-    for (;;) {
-        int si;
-        { std::unique_lock<std::mutex> lk(S.mu); S.cv.wait(lk, [&] { return !S.filled.empty(); }); si = S.filled.front(); S.filled.pop_front(); }
-        if (si < 0) { kj_err() = S.perr; return S.prc; }
-        S.tm[5] += kj_ms_since(t);
-        KjBatch& B = S.slot[si]; const uint64_t n = B.n;
+    auto start = [&](int l, int si) -> int {          // launch the classification of batch si on lane l
+        KjLane& Ln = S.lane[l]; KjBatch& B = S.slot[si]; const uint64_t n = B.n; int r;
+        Ln.batch = si; Ln.busy = true;
+        if (!n) return KJ_OK;
+        if ((r = Ln.tax.need(n * 8)) || (r = Ln.best.need(n * 4)) || (r = Ln.len.need((n + 2) * 4))) return r;
+        if (verbose && ((r = Ln.ids.need(n * KJ_MAX_IDS * 8)) || (r = Ln.nids.need(n)))) return r;
+        return launch(c, l, B.s[0].seq.as<uint8_t>(), B.s[0].off.as<uint64_t>(), paired ? B.s[1].seq.as<uint8_t>() : nullptr, paired ? B.s[1].off.as<uint64_t>() : nullptr, 0, 0, n, B.maxlen[0], B.maxlen[1],
+                      Ln.tax.as<uint64_t>(), Ln.best.as<uint32_t>(), c->stream[l], false, verbose ? Ln.ids.as<uint64_t>() : nullptr, verbose ? Ln.nids.as<uint8_t>() : nullptr, pend[l]);
+    };
+    auto finish = [&](int l) -> int {                 // wait for lane l's kernel, check, count, format, write; the batch slot goes back to the parser
+        KjLane& Ln = S.lane[l]; KjBatch& B = S.slot[Ln.batch]; const uint64_t n = B.n; cudaStream_t st = c->stream[l]; int r;
         if (n) {
-            if ((rc = S.tax.need(n * 8)) || (rc = S.best.need(n * 4)) || (rc = S.len.need((n + 2) * 4))) return rc;
-            if (verbose && ((rc = S.ids.need(n * KJ_MAX_IDS * 8)) || (rc = S.nids.need(n)))) return rc;
-            for (;;) {     // repeated only when the Greedy variant ring had to grow
-                rc = launch(c, 0, B.s[0].seq.as<uint8_t>(), B.s[0].off.as<uint64_t>(), paired ? B.s[1].seq.as<uint8_t>() : nullptr, paired ? B.s[1].off.as<uint64_t>() : nullptr, 0, 0, n, B.maxlen[0], B.maxlen[1],
-                            S.tax.as<uint64_t>(), S.best.as<uint32_t>(), st, false, verbose ? S.ids.as<uint64_t>() : nullptr, verbose ? S.nids.as<uint8_t>() : nullptr, c->d_counts_pending);
-                if (rc) return rc;
-                CK(cudaStreamSynchronize(st));
+            CK(cudaStreamSynchronize(st));
+            uint32_t e = 0; CK(cudaMemcpy(&e, c->d_err, sizeof e, cudaMemcpyDeviceToHost));
+            if (e) {
+                // the error word is shared by the two lanes: let the other kernel finish, then repeat what was in flight, one launch at a time
+                // (only a full Greedy variant ring is repaired by a repeat: the ring grows)
+                const int o = l ^ 1; const bool other = S.lane[o].busy && S.slot[S.lane[o].batch].n > 0;
+                if (other) CK(cudaStreamSynchronize(c->stream[o]));
                 const uint32_t boost = c->variant_boost;
-                rc = check_err_flag(c);
-                if (rc) CK(cudaMemsetAsync(c->d_counts_pending, 0, (size_t)c->n_counts * 8, st));     // a failed launch does not count
-                if (rc == KJ_ERR_OVERFLOW && c->variant_boost != boost) continue;
-                if (rc) return rc;
-                break;
+                r = check_err_flag(c);
+                for (int k = 0; k < 2; k++) CK(cudaMemset(pend[k], 0, (size_t)c->n_counts * 8));      // failed launches do not count
+                if (!(r == KJ_ERR_OVERFLOW && c->variant_boost != boost)) return r ? r : KJ_ERR_CUDA;
+                for (int k = 0; k < 2; k++) {
+                    const int ll = k == 0 ? l : o; if (k == 1 && !other) break;
+                    for (;;) {
+                        if ((r = start(ll, S.lane[ll].batch))) return r;
+                        CK(cudaStreamSynchronize(c->stream[ll]));
+                        const uint32_t b2 = c->variant_boost; r = check_err_flag(c);
+                        if (r) CK(cudaMemset(pend[ll], 0, (size_t)c->n_counts * 8));
+                        if (r == KJ_ERR_OVERFLOW && c->variant_boost != b2) continue;
+                        if (r) return r;
+                        break;
+                    }
+                }
             }
             S.tm[6] += kj_ms_since(t);
-            kj_count_commit<<<c->sm_count, 256, 0, st>>>(c->d_counts, c->d_counts_pending, c->n_counts); c->launches++;     // this chunk succeeded: its reads join the per-taxon counts
-            kj_fmt_len<<<c->sm_count * 4, 256, 0, st>>>(S.tax.as<uint64_t>(), S.best.as<uint32_t>(), S.ids.as<uint64_t>(), S.nids.as<uint8_t>(), B.s[0].name_off.as<uint32_t>(), n, verbose, S.len.as<uint32_t>(), d_nclass);
-            if ((rc = kj_scan_u32(S.len.as<uint32_t>(), n + 1, S.scan_tmp, (uint32_t*)S.totals.p, st))) return rc;
-            uint32_t out_bytes = 0; CK(cudaMemcpyAsync(&out_bytes, S.totals.p, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-            if ((rc = S.out.need(out_bytes + 64))) return rc;
-            kj_fmt_write<<<c->sm_count * 4, 256, 0, st>>>(S.tax.as<uint64_t>(), S.best.as<uint32_t>(), S.ids.as<uint64_t>(), S.nids.as<uint8_t>(), B.s[0].names.as<char>(), B.s[0].name_off.as<uint32_t>(), n, verbose,
-                                                       S.len.as<uint32_t>(), S.out.as<char>());
+            unsigned long long* d_nclass = (unsigned long long*)((char*)Ln.totals.p + 16);
+            kj_count_commit<<<c->sm_count, 256, 0, st>>>(c->d_counts, pend[l], c->n_counts); c->launches++;     // this batch succeeded: its reads join the per-taxon counts
+            kj_fmt_len<<<c->sm_count * 4, 256, 0, st>>>(Ln.tax.as<uint64_t>(), Ln.best.as<uint32_t>(), Ln.ids.as<uint64_t>(), Ln.nids.as<uint8_t>(), B.s[0].name_off.as<uint32_t>(), n, verbose, Ln.len.as<uint32_t>(), d_nclass);
+            if ((r = kj_scan_u32(Ln.len.as<uint32_t>(), n + 1, Ln.scan_tmp, (uint32_t*)Ln.totals.p, st))) return r;
+            uint32_t out_bytes = 0; CK(cudaMemcpyAsync(&out_bytes, Ln.totals.p, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+            if ((r = Ln.out.need(out_bytes + 64))) return r;
+            kj_fmt_write<<<c->sm_count * 4, 256, 0, st>>>(Ln.tax.as<uint64_t>(), Ln.best.as<uint32_t>(), Ln.ids.as<uint64_t>(), Ln.nids.as<uint8_t>(), B.s[0].names.as<char>(), B.s[0].name_off.as<uint32_t>(), n, verbose,
+                                                       Ln.len.as<uint32_t>(), Ln.out.as<char>());
             CK(cudaGetLastError()); c->launches += 6;
             for (size_t o = 0; o < out_bytes; o += out_cap) {
                 const size_t m = std::min<size_t>(out_cap, out_bytes - o); char* hb = S.wr.get();
                 if (!hb) { kj_err() = "cudaMallocHost failed"; return KJ_ERR_NOMEM; }
-                CK(cudaMemcpyAsync(hb, S.out.as<char>() + o, m, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+                CK(cudaMemcpyAsync(hb, Ln.out.as<char>() + o, m, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
                 S.wr.put(hb, m);
             }
             CK(cudaStreamSynchronize(st));
             n_reads += n; S.tm[7] += kj_ms_since(t);
         }
-        const bool last = B.last;
+        Ln.busy = false;
         { std::lock_guard<std::mutex> lk(S.mu); S.n_free++; } S.cv.notify_all();        // the parser may overwrite this slot's buffers now
-        if (last) break;
+        return KJ_OK;
+    };
+    uint64_t k = 0; bool done = false;
+    while (!done) {
+        int si = -2;
+        {   // the next parsed batch; while none is there, complete the older of the running lanes instead of waiting
+            std::unique_lock<std::mutex> lk(S.mu);
+            if (S.filled.empty() && (S.lane[0].busy || S.lane[1].busy)) si = -3;
+            else { S.cv.wait(lk, [&] { return !S.filled.empty(); }); si = S.filled.front(); S.filled.pop_front(); }
+        }
+        if (si == -3) { const int l = (S.lane[0].busy && S.lane[1].busy) ? (int)(k & 1) : (S.lane[0].busy ? 0 : 1); if ((rc = finish(l))) return rc; continue; }
+        if (si < 0) { kj_err() = S.perr; return S.prc; }
+        S.tm[5] += kj_ms_since(t);
+        const int l = (int)(k & 1);
+        if (S.lane[l].busy && (rc = finish(l))) return rc;      // batch k-2
+        if ((rc = start(l, si))) return rc;
+        done = S.slot[si].last; k++;
     }
+    for (int q = 0; q < 2; q++) { const int l = (int)((k + q) & 1); if (S.lane[l].busy && (rc = finish(l))) return rc; }       // older lane first
     S.parser.join();
     c->launches += S.parse_launches;
-    CK(cudaMemcpyAsync(&n_class, d_nclass, 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-    if (ftrace) fprintf(stderr, "KJ_FILES_TRACE chunks %llu  parser: slot-wait %.1f  h2d-wait+append %.1f  reader-wait %.1f  parse+carry %.1f | classifier: batch-wait %.1f  classify %.1f  format+d2h %.1f ms\n",
-                        (unsigned long long)S.nchunks, S.tm[0], S.tm[1], S.tm[2], S.tm[3], S.tm[5], S.tm[6], S.tm[7]);
+    unsigned long long n_class = 0;
+    for (int l = 0; l < 2; l++) { unsigned long long v = 0; CK(cudaMemcpy(&v, (char*)S.lane[l].totals.p + 16, 8, cudaMemcpyDeviceToHost)); n_class += v; }
+    if (ftrace) fprintf(stderr, "KJ_FILES_TRACE batches %llu  parser: slot-wait %.1f  chunk-wait+append %.1f  parse+carry %.1f | classifier: batch-wait %.1f  classify-wait %.1f  format+d2h %.1f ms\n",
+                        (unsigned long long)S.nbatches, S.tm[0], S.tm[1], S.tm[3], S.tm[5], S.tm[6], S.tm[7]);
     if (n_reads_out) *n_reads_out = n_reads; if (n_class_out) *n_class_out = n_class;
     return KJ_OK;
 }
@@ -712,7 +761,8 @@ extern "C" int kj_classify_files(kj_ctx* c, const char* in1, const char* in2, co
     KjFilesState* S = c->files;
     int rc = kj_classify_files_impl(c, *S, in1, in2, out_path, verbose, n_reads, n_classified);
     const std::string keep = kj_err();
+    cudaStreamSynchronize(c->stream[0]); cudaStreamSynchronize(c->stream[1]);
     S->end_call();
-    if (rc) kj_err() = keep; else if (S->wr.failed) { kj_err() = "write error on the output file"; rc = KJ_ERR_IO; }
+    if (rc) { cudaMemset(c->d_err, 0, 4); kj_err() = keep; } else if (S->wr.failed) { kj_err() = "write error on the output file"; rc = KJ_ERR_IO; }
     return rc;
 }

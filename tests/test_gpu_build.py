@@ -173,3 +173,23 @@ def test_classify_multi_and_cli_device_list(kb, golden, tmp_path):
     subprocess.run(base + ["-i", a, "-o", d + "/r1", "-d", "0"], check=True, stderr=subprocess.DEVNULL)
     subprocess.run(base + ["-i", c1, "-o", d + "/r2"], check=True, stderr=subprocess.DEVNULL)
     assert open(d + "/o1").read() == open(d + "/r1").read() == open(d + "/o3").read() and open(d + "/o2").read() == open(d + "/r2").read()
+
+
+def test_kmer_table_k7(kb, golden, monkeypatch):
+    """The 7-mer interval table (the MEM kernels use it on indexes of >= 5e7 rows; forced here for both modes on the small golden index):
+    results equal the oracle's and the default table's."""
+    names, s1, o1, s2, o2 = golden.reads("pe150")
+    ref = kb.Classifier(golden.fmi, golden.nodes, device=0, params=kb.make_params("mem"))
+    monkeypatch.setenv("KJ_KMER_K", "7")
+    clf = kb.Classifier(golden.fmi, golden.nodes, device=0, params=kb.make_params("mem"))
+    orc = Oracle(golden.fmi, golden.nodes)
+    for mode in ("mem", "greedy"):
+        ref.set_params(kb.make_params(mode)); clf.set_params(kb.make_params(mode))
+        a = clf.classify(s1, o1, s2, o2); b = ref.classify(s1, o1, s2, o2)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), mode
+        otax, obest = orc.classify_batch(make_params(mode), s1, o1, s2, o2)
+        assert np.array_equal(a[0], otax) and np.array_equal(a[1], obest), mode
+    clf.set_params(kb.make_params("mem", m=7)); ref.set_params(kb.make_params("mem", m=7))      # the shortest fragment length the table serves
+    a = clf.classify(s1, o1, s2, o2); b = ref.classify(s1, o1, s2, o2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    clf.close(); ref.close()
