@@ -18,6 +18,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    # a GPU test that hangs (a deadlocked pipeline, a kernel that never ends) must not hold the box: ten minutes per test (pytest-timeout)
+    if config.pluginmanager.hasplugin("timeout"):
+        for it in items:
+            if it.get_closest_marker("gpu") and not it.get_closest_marker("timeout"):
+                it.add_marker(pytest.mark.timeout(600))
+
+
 def _read_fq_gz(path):
     names, seqs = [], []
     with gzip.open(path, "rt") as f:
