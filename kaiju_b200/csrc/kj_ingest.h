@@ -292,19 +292,26 @@ struct KjParsed {   // one side (file) of a chunk while it is parsed
     KjDevBuf text[2]; int cur = 0; uint64_t nbytes = 0;         // device text (ping-pong for the carry), valid bytes
     KjDevBuf line_start, cnt, hdr, nlen, tiles, scan_tmp, rec_pos, totals, phase, phase_tiles;
     int fastq = -1;                                              // file type, fixed by the first byte of the file
-    uint64_t n_lines = 0, n_rec = 0, consumed = 0; bool eof = false;
+    uint64_t n_lines = 0, n_rec = 0, consumed = 0; bool eof = false, skip_all = false;
     void release() { for (KjDevBuf* b : {&text[0], &text[1], &line_start, &cnt, &hdr, &nlen, &tiles, &scan_tmp, &rec_pos, &totals, &phase, &phase_tiles}) b->release(); }
 };
 
 // Parse the complete records in P.text[P.cur][0, P.nbytes) into O.  Sets P.n_rec; *launches counts the kernels.
 // exact: FASTQ with blank lines between records (phases from the automaton scan instead of line number mod 4)
 static int kj_parse_side(int sm_count, KjParsed& P, KjBatchSide& O, const std::string& fname, cudaStream_t st, uint32_t* d_perr, uint64_t* launches, bool exact) {
-    P.n_rec = 0; P.consumed = 0; P.n_lines = 0;
+    P.n_rec = 0; P.consumed = 0; P.n_lines = 0; P.skip_all = false;
     if (P.nbytes == 0) return KJ_OK;
     if (P.nbytes >= (1ull << 31)) { kj_err() = "kj_classify_files: a single record larger than 2 GB"; return KJ_ERR_UNSUPPORTED; }
     const char* text = P.text[P.cur].as<char>();
     if (P.fastq < 0) {
-        char first = 0; CK(cudaMemcpyAsync(&first, text, 1, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        // the file type is the first character of the first non-empty line (kaiju.cpp:289-299: empty lines are skipped before it is looked at)
+        char first = '\n'; std::vector<char> head;
+        for (uint64_t at = 0, win = 256; first == '\n' && at < P.nbytes; at += head.size(), win *= 4) {
+            head.resize((size_t)std::min<uint64_t>(win, P.nbytes - at));
+            CK(cudaMemcpyAsync(head.data(), text + at, head.size(), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+            for (char ch : head) if (ch != '\n') { first = ch; break; }
+        }
+        if (first == '\n') { P.skip_all = true; return KJ_OK; }                   // nothing but empty lines so far: they are dropped
         if (first == '@') P.fastq = 1; else if (first == '>') P.fastq = 0;
         else { kj_err() = "Auto-detection of file type for file " + fname + " failed."; return KJ_ERR_IO; }                 // kaiju.cpp:296-299
     }
@@ -609,7 +616,7 @@ static int kj_parse_chunks(int device, int sm_count, KjFilesState& S, size_t chu
         // 3. carry the unconsumed tail to the front of the other text buffer
         if (target < batch_max) target = std::min(batch_max, target * 2);
         for (int f = 0; f < S.nfiles; f++) {
-            KjParsed& P = S.side[f]; const uint64_t consumed = P.n_lines ? pos[f] : 0;
+            KjParsed& P = S.side[f]; const uint64_t consumed = P.skip_all ? P.nbytes : (P.n_lines ? pos[f] : 0);
             const uint64_t tail = P.nbytes - consumed; const int other = P.cur ^ 1;
             if ((rc = P.text[other].need(tail + target + chunk + 1))) return rc;
             if (tail) CK(cudaMemcpyAsync(P.text[other].p, P.text[P.cur].as<char>() + consumed, tail, cudaMemcpyDeviceToDevice, st));

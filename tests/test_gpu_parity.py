@@ -358,6 +358,8 @@ def test_fastq_with_blank_lines(kb, golden, tmp_path, monkeypatch, chunk):
     r1 = [s1[int(o1[i]):int(o1[i + 1])].tobytes().decode() for i in range(500)]; r2 = [s2[int(o2[i]):int(o2[i + 1])].tobytes().decode() for i in range(500)]
     def write(path, reads, blanks, mate):
         with open(path, "w") as f:
+            if blanks:
+                f.write("\n\n")                                              # the file type comes from the first non-empty line
             for i, sq in enumerate(reads):
                 if blanks and i and rnd.random() < 0.2:
                     f.write("\n" * rnd.choice([1, 1, 2, 5]))
