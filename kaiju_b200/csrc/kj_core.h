@@ -503,7 +503,7 @@ static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s
         }
     }
     w.sync();
-#ifdef KJ_SPLIT_ROLLED
+#ifndef KJ_SPLIT_UNROLLED_GREEDY      // A/B round 2: Greedy +12 % (16.04 vs 14.30 M pairs/s) with the quarter-size splitting code
     if (greedy) kj_split_frames_rolled(cx, q, na1, na2, n1, n2, greedy, 3); else
 #endif
     kj_split_frames(cx, q, na1, na2, n1, n2, greedy, 3);
@@ -532,7 +532,7 @@ struct KjSeg { int begin, end; };
 // rare low-diversity windows need the composition count.  Returns whether any window can trigger SEG at all.
 // packed variant: the 12 residues of a window live in three 32-bit words; per distinct residue (<= 7 on the slow path)
 // the count is three byte-wise compares + popcounts instead of a 12-step nibble-counter loop
-static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
+static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n, const bool compact) {
     const uint8_t* frag = cx.smem + cx.L.frag_off; uint8_t* hf = cx.smem + cx.L.hflag_off; const KjTables& tb = *cx.tb;
     bool any_low = false;
     KJ_ROLLED
@@ -543,6 +543,9 @@ static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n) {
             const uint32_t a0 = aw[0], a1 = aw[1], a2 = aw[2], a3 = aw[3];
             const uint32_t w0 = kj_funnel_r(a0, a1, sh), w1 = kj_funnel_r(a1, a2, sh), w2 = kj_funnel_r(a2, a3, sh);
             uint32_t seen = 0;
+#ifdef KJ_GREEDY_COMPACT
+            if (compact) { KJ_ROLLED for (int t = 0; t < 4; t++) { seen |= 1u << ((w0 >> (8 * t)) & 0xffu); seen |= 1u << ((w1 >> (8 * t)) & 0xffu); seen |= 1u << ((w2 >> (8 * t)) & 0xffu); } } else
+#endif
             for (int t = 0; t < 4; t++) { seen |= 1u << ((w0 >> (8 * t)) & 0xffu); seen |= 1u << ((w1 >> (8 * t)) & 0xffu); seen |= 1u << ((w2 >> (8 * t)) & 0xffu); }
             if (kj_popc(seen) < 8) {
                 int32_t x = 0;
@@ -672,7 +675,20 @@ KJ_NOINLINE uint32_t kj_seg_trim(const Warp w, uint8_t* scratch, const uint8_t* 
                 if (nz < 20) ans1 = kj_dsub(ans1, lnf[20 - nz]);
                 double prob = kj_dsub(kj_dadd(ans1, ans2), kj_dmul((double)len, 2.9957322735539909));
                 if (prob < my_prob) { my_prob = prob; my_i = i; }
+#ifdef KJ_GREEDY_COMPACT
+                // one update body for "remove s[i]" and "add s[i+len]" (half the code of the two specialised ones)
+                if (i + len < n2) {
+                    KJ_ROLLED
+                    for (int k_ = 0; k_ < 2; k_++) {
+                        const uint32_t a_ = (uint32_t)(k_ ? s[i + len] : s[i]) - 1u; const uint32_t c_ = cnt[a_ * 32 + w.lane]; const uint32_t n_ = k_ ? c_ + 1u : c_ - 1u;
+                        if (c_ > 0) { uint8_t h_ = --hist[c_ * 32 + w.lane]; if (h_ == 0) { if (c_ < 64) m0 &= ~(1ull << c_); else m1 &= ~(1ull << (c_ - 64)); } } else nz++;
+                        cnt[a_ * 32 + w.lane] = (uint8_t)n_;
+                        if (n_ > 0) { hist[n_ * 32 + w.lane]++; if (n_ < 64) m0 |= 1ull << n_; else m1 |= 1ull << (n_ - 64); } else nz--;
+                    }
+                }
+#else
                 if (i + len < n2) { KJ_SEG_DEL(s[i]); KJ_SEG_ADD(s[i + len]); }
+#endif
             }
             #undef KJ_SEG_ADD
             #undef KJ_SEG_DEL
@@ -768,9 +784,9 @@ KJ_NOINLINE int kj_seg_regions(const KjSegArgs A, int n) {
     return ns;
 }
 // full SEG on frag[0..n): flags (inline, every fragment), regions (out of line, rare)
-static KJ_DEV int kj_seg(KjWarpCtx& cx, int n) {
+static KJ_DEV int kj_seg(KjWarpCtx& cx, int n, const bool compact) {
     if (n < KJ_SEG_WINDOW) return 0;
-    if (!kj_seg_flags(cx, n)) return 0;                      // no window at or below locut: s_SegSeq cannot trigger
+    if (!kj_seg_flags(cx, n, compact)) return 0;                      // no window at or below locut: s_SegSeq cannot trigger
     KjSegArgs A; A.w = cx.w; A.frag = cx.smem + cx.L.frag_off; A.hf = cx.smem + cx.L.hflag_off; A.segs = (KjSeg*)(cx.smem + cx.L.segs_off);
     A.scratch = cx.smem + cx.L.segcnt_off; A.lnf = cx.ix->lnfact; A.cap = (int)KJ_SEG_CAP(cx.rp->max_frag); A.err = cx.err;
     return kj_seg_regions(A, n);
@@ -858,7 +874,7 @@ static KJ_DEV uint32_t kj_ids_and_lca(KjWarpCtx& cx, uint32_t nkept) {
 
 // SEG gate of getNextFragment (ConsumerThread.cpp:285-339): returns true if the item was split (pieces pushed)
 static KJ_DEV bool kj_seg_gate(KjWarpCtx& cx, KjQueue& q, uint32_t arr, uint32_t start, uint32_t len, bool greedy) {
-    int ns = kj_seg(cx, (int)len);
+    int ns = kj_seg(cx, (int)len, greedy);
     if (ns == 0) return false;
     kj_queue_make_dirty(cx, q);
     const KjSeg* segs = (const KjSeg*)(cx.smem + cx.L.segs_off);
@@ -1060,7 +1076,7 @@ static KJ_DEV void kj_protein_fragments(KjWarpCtx& cx, KjQueue& q, const uint8_t
         aa[3 * t] = (u >= 'A' && u <= 'Z') ? tb.aa_index[u - 'A'] : (uint8_t)0;
     }
     w.sync();
-#ifdef KJ_SPLIT_ROLLED
+#ifndef KJ_SPLIT_UNROLLED_GREEDY
     if (greedy) kj_split_frames_rolled(cx, q, 3 * n1 - 2, 0, n1, 0, greedy, 1); else
 #endif
     kj_split_frames(cx, q, 3 * n1 - 2, 0, n1, 0, greedy, 1);
