@@ -141,10 +141,23 @@ static KJ_DEV IdxT kj_rank_at(const uint64_t* base, IdxT k) {
 static KJ_DEV const uint64_t* kj_letter_base(const KjDevIndex& ix, uint32_t c) { return ix.rank_base[c]; }
 template <class IdxT>
 static KJ_DEV IdxT kj_rank(const KjDevIndex& ix, uint32_t c, IdxT k) { return kj_rank_at<IdxT>(kj_letter_base(ix, c), k); }
+// The LF step of the 32-bit kernels as a real function (Greedy, -DKJ_GREEDY_OOL: the step is inlined at five sites of its hot loop, ~30 instructions each;
+// the call costs ~20 cycles next to a ~700-cycle memory round trip, the instruction cache is what Greedy is short of).  Returns nhi << 32 | nlo.
+KJ_NOINLINE uint64_t kj_lf_step32_fn(const uint64_t* base, uint32_t lo, uint32_t hi) {
+    const uint32_t nlo = kj_rank_at<uint32_t>(base, lo), nhi = kj_rank_at<uint32_t>(base, hi);
+    return ((uint64_t)nhi << 32) | (uint64_t)nlo;
+}
 // UpdateSI (bwt.c:160-173)
-template <class IdxT>
+template <class IdxT, bool OOL = false>
 static KJ_DEV bool kj_update_si(const KjDevIndex& ix, uint32_t c, IdxT& lo, IdxT& hi) {
     const uint64_t* base = kj_letter_base(ix, c);
+#ifdef KJ_GREEDY_OOL
+    if (OOL && sizeof(IdxT) == 4) {
+        const uint64_t r = kj_lf_step32_fn(base, (uint32_t)lo, (uint32_t)hi); const uint32_t a = (uint32_t)r, b = (uint32_t)(r >> 32);
+        if (a >= b) return false;
+        lo = (IdxT)a; hi = (IdxT)b; return true;
+    }
+#endif
     IdxT nlo = kj_rank_at<IdxT>(base, lo), nhi = kj_rank_at<IdxT>(base, hi);
     // the reference's checkpoint quirk (indexes with bwtlen = m * 2^16 only, kj_host.cpp): the last 129 positions rank lower by a per-letter
     // constant.  Such indexes are routed to the 64-bit kernels, so the 32-bit ones do not carry the test.
@@ -197,7 +210,7 @@ struct KjEmuStats { unsigned long long rounds, round_steps, lane_steps, chains, 
 extern thread_local KjEmuStats kj_emu_stats;
 #endif
 
-template <class IdxT>
+template <class IdxT, bool OOL = false>
 static KJ_DEV void kj_chain_start(const KjDevIndex& ix, const uint8_t* frag, int j, uint32_t Lmin, KjChain<IdxT>& ch) {
     const int k = ix.kmer_k; int i = j; int budget = KJ_PHASE_A_LETTERS - 1;
     ch.st = KJ_ST_OPEN;
@@ -214,24 +227,24 @@ static KJ_DEV void kj_chain_start(const KjDevIndex& ix, const uint8_t* frag, int
         const uint32_t c = frag[j]; ch.lo = (IdxT)ix.C[c]; ch.hi = (IdxT)ix.C[c + 1];      // InitialSI (bwt.c:146-152)
     }
     KJ_ROLLED
-    while (i > 0 && budget > 0) { if (!kj_update_si<IdxT>(ix, frag[i - 1], ch.lo, ch.hi)) { ch.st = KJ_ST_EXACT; break; } i--; budget--; }
+    while (i > 0 && budget > 0) { if (!kj_update_si<IdxT, OOL>(ix, frag[i - 1], ch.lo, ch.hi)) { ch.st = KJ_ST_EXACT; break; } i--; budget--; }
     if (i == 0) ch.st = KJ_ST_EXACT;
     ch.i = i;
 }
-template <class IdxT>
+template <class IdxT, bool OOL = false>
 static KJ_DEV void kj_chain_finish(const KjDevIndex& ix, const uint8_t* frag, KjChain<IdxT>& ch) {
     int i = ch.i;
     KJ_ROLLED
-    while (i > 0) { if (!kj_update_si<IdxT>(ix, frag[i - 1], ch.lo, ch.hi)) break; i--; }
+    while (i > 0) { if (!kj_update_si<IdxT, OOL>(ix, frag[i - 1], ch.lo, ch.hi)) break; i--; }
     ch.i = i; ch.st = KJ_ST_EXACT;
 }
 // complete the selected chains (one lane each)
-template <class IdxT>
+template <class IdxT, bool OOL = false>
 static KJ_DEV void kj_finish_selected(const Warp& w, const KjDevIndex& ix, const uint8_t* frag, bool sel, KjChain<IdxT>& ch) {
 #if defined(KJ_EMU)
     const int i0 = ch.i;
 #endif
-    if (sel) kj_chain_finish<IdxT>(ix, frag, ch);
+    if (sel) kj_chain_finish<IdxT, OOL>(ix, frag, ch);
     w.sync();
 #if defined(KJ_EMU)
     { const uint32_t st = sel ? (uint32_t)(i0 - ch.i) + 1u : 0u; const uint32_t mx = warp_max_u32(w, st); const uint32_t nsel = (uint32_t)kj_popc(w.ballot(sel));
@@ -543,7 +556,7 @@ static KJ_DEV bool kj_seg_flags(KjWarpCtx& cx, int n, const bool compact) {
             const uint32_t a0 = aw[0], a1 = aw[1], a2 = aw[2], a3 = aw[3];
             const uint32_t w0 = kj_funnel_r(a0, a1, sh), w1 = kj_funnel_r(a1, a2, sh), w2 = kj_funnel_r(a2, a3, sh);
             uint32_t seen = 0;
-#ifdef KJ_GREEDY_COMPACT
+#ifndef KJ_NO_GREEDY_COMPACT    // A/B round 2 (with the unified update in kj_seg_trim): Greedy 16.02 -> 16.73 M pairs/s, MEM +0.6 %
             if (compact) { KJ_ROLLED for (int t = 0; t < 4; t++) { seen |= 1u << ((w0 >> (8 * t)) & 0xffu); seen |= 1u << ((w1 >> (8 * t)) & 0xffu); seen |= 1u << ((w2 >> (8 * t)) & 0xffu); } } else
 #endif
             for (int t = 0; t < 4; t++) { seen |= 1u << ((w0 >> (8 * t)) & 0xffu); seen |= 1u << ((w1 >> (8 * t)) & 0xffu); seen |= 1u << ((w2 >> (8 * t)) & 0xffu); }
@@ -675,7 +688,7 @@ KJ_NOINLINE uint32_t kj_seg_trim(const Warp w, uint8_t* scratch, const uint8_t* 
                 if (nz < 20) ans1 = kj_dsub(ans1, lnf[20 - nz]);
                 double prob = kj_dsub(kj_dadd(ans1, ans2), kj_dmul((double)len, 2.9957322735539909));
                 if (prob < my_prob) { my_prob = prob; my_i = i; }
-#ifdef KJ_GREEDY_COMPACT
+#ifndef KJ_NO_GREEDY_COMPACT
                 // one update body for "remove s[i]" and "add s[i+len]" (half the code of the two specialised ones)
                 if (i + len < n2) {
                     KJ_ROLLED
@@ -1082,26 +1095,72 @@ static KJ_DEV void kj_protein_fragments(KjWarpCtx& cx, KjQueue& q, const uint8_t
     kj_split_frames(cx, q, 3 * n1 - 2, 0, n1, 0, greedy, 1);
 }
 
-template <int MODE, class IdxT>
-static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1, const uint8_t* s2, int n2, bool paired, uint32_t& best_out) {
+// ---------------------------------------------------------------------------------------------
+// Greedy in two kernels (ROLE 1 = front end, ROLE 2 = search; ROLE 0 = everything in one kernel, as MEM runs).  Greedy is bound by instruction
+// fetch (profiles/README.md, round 2): translation, frame splitting and queue ranking are 6 KB of its hot code that the search does not need.
+// The front end leaves, per item, the four translated arrays and the ranked fragment queue in a record in global memory (1.5 KB for PE150);
+// the search kernel copies the record into the same places of its work space and continues exactly where the single kernel would.
+//   record: [0] uint32 queue length (0xffffffff = unclassified by the length gates), [16] keys, pays, ranks, [..] the aa arrays
+// ---------------------------------------------------------------------------------------------
+static KJ_HD uint32_t kj_prep_keys_off() { return 16u; }
+static KJ_HD uint32_t kj_prep_pays_off(const KjRunParams& p) { return 16u + 8u * p.item_cap; }
+static KJ_HD uint32_t kj_prep_ords_off(const KjRunParams& p) { return kj_prep_pays_off(p) + 4u * kj_align(p.item_cap, 2); }
+static KJ_HD uint32_t kj_prep_aa_off(const KjRunParams& p) { return kj_align(kj_prep_ords_off(p) + kj_align(p.item_cap, 8), 16); }
+static KJ_HD uint32_t kj_prep_stride(const KjRunParams& p) { return kj_align(kj_prep_aa_off(p) + 4u * kj_align(p.max_len + 4, 8), 16); }
+static KJ_DEV void kj_prep_store(KjWarpCtx& cx, const KjQueue& q, bool ok, uint8_t* rec) {
+    const Warp& w = cx.w; const KjRunParams& rp = *cx.rp;
+    w.sync();
+    if (w.lane == 0) *(uint32_t*)rec = ok ? q.n : 0xffffffffu;
+    if (ok) {
+        uint64_t* rk = (uint64_t*)(rec + kj_prep_keys_off()); uint32_t* rp_ = (uint32_t*)(rec + kj_prep_pays_off(rp)); uint8_t* ro = rec + kj_prep_ords_off(rp);
+        KJ_ROLLED
+        for (uint32_t i = (uint32_t)w.lane; i < q.n; i += 32) { rk[i] = q.key[i]; rp_[i] = q.pay[i]; ro[i] = q.ord[i]; }
+        const uint32_t* a = (const uint32_t*)(cx.smem + cx.L.aa_off); uint32_t* ra = (uint32_t*)(rec + kj_prep_aa_off(rp));
+        KJ_ROLLED
+        for (uint32_t i = (uint32_t)w.lane; i < cx.L.aa_stride; i += 32) ra[i] = a[i];          // 4 arrays x stride bytes = stride words
+    }
+    w.sync();
+}
+static KJ_DEV bool kj_prep_load(KjWarpCtx& cx, KjQueue& q, const uint8_t* rec) {
+    const Warp& w = cx.w; const KjRunParams& rp = *cx.rp;
+    const uint32_t n = *(const uint32_t*)rec;
+    if (n == 0xffffffffu) return false;
+    const uint64_t* rk = (const uint64_t*)(rec + kj_prep_keys_off()); const uint32_t* rp_ = (const uint32_t*)(rec + kj_prep_pays_off(rp)); const uint8_t* ro = rec + kj_prep_ords_off(rp);
+    KJ_ROLLED
+    for (uint32_t i = (uint32_t)w.lane; i < n; i += 32) { q.key[i] = rk[i]; q.pay[i] = rp_[i]; q.ord[i] = ro[i]; }
+    uint32_t* a = (uint32_t*)(cx.smem + cx.L.aa_off); const uint32_t* ra = (const uint32_t*)(rec + kj_prep_aa_off(rp));
+    KJ_ROLLED
+    for (uint32_t i = (uint32_t)w.lane; i < cx.L.aa_stride; i += 32) a[i] = ra[i];
+    q.n = n; q.late = 0; q.next = 0; q.nsorted = n <= 255u ? n : 0u; q.dirty = n > 255u;          // as kj_queue_sort leaves it
+    w.sync();
+    return true;
+}
+
+template <int MODE, class IdxT, int ROLE = 0>
+static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1, const uint8_t* s2, int n2, bool paired, uint32_t& best_out, uint8_t* rec = nullptr) {
     const KjRunParams& rp = *cx.rp;
     best_out = 0; cx.nids = 0;
     KjQueue q; q.key = (uint64_t*)(cx.smem + cx.L.qkey_off); q.pay = (uint32_t*)(cx.smem + cx.L.qpay_off);
     q.ord = cx.smem + cx.L.qord_off; q.cap = rp.item_cap; q.n = 0; q.late = 0; q.next = 0; q.nsorted = 0; q.dirty = true;
     const bool greedy = MODE == 1;
+    const int m3 = (int)rp.m * 3;
+    if (ROLE != 2) {
+        bool ok = true;
+        if (rp.protein) {
+            if (n1 < (int)rp.m) ok = false;                                  // (640-646)
+            else kj_protein_fragments(cx, q, s1, n1, greedy);
+        } else {
+            // short-read gate (648-653): SE len1 < 3m; PE only if BOTH mates are short
+            if ((!paired && n1 < m3) || (paired && n1 < m3 && n2 < m3)) ok = false;
+            else kj_translate_pair(cx, q, s1, n1, n1 >= m3, s2, n2, paired && n2 >= m3, greedy);   // a short mate is skipped individually (699, 705)
+        }
+        if (ok && MODE == 1) kj_queue_sort(cx, q);     // greedy pops every fragment (and many variants): ranking once pays (A/B +9 %); MEM stops after a few pops (A/B -16 %)
+        if (ROLE == 1) { kj_prep_store(cx, q, ok, rec); return KJ_TAX_BAD; }
+        if (!ok) return KJ_TAX_BAD;
+    } else if (!kj_prep_load(cx, q, rec)) return KJ_TAX_BAD;
     double query_len;                                                    // E-value query length (659, 698, 704)
-    if (rp.protein) {
-        if (n1 < (int)rp.m) return KJ_TAX_BAD;                           // (640-646)
-        query_len = (double)n1;
-        kj_protein_fragments(cx, q, s1, n1, greedy);
-    } else {
-        const int m3 = (int)rp.m * 3;
-        // short-read gate (648-653): SE len1 < 3m; PE only if BOTH mates are short
-        if ((!paired && n1 < m3) || (paired && n1 < m3 && n2 < m3)) return KJ_TAX_BAD;
-        query_len = (double)n1 / 3.0; if (paired) query_len += (double)n2 / 3.0;
-        kj_translate_pair(cx, q, s1, n1, n1 >= m3, s2, n2, paired && n2 >= m3, greedy);   // a short mate is skipped individually (699, 705)
-    }
-    if (MODE == 1) kj_queue_sort(cx, q);     // greedy pops every fragment (and many variants): ranking once pays (A/B +9 %); MEM stops after a few pops (A/B -16 %)
+    if (rp.protein) query_len = (double)n1;
+    else { query_len = (double)n1 / 3.0; if (paired) query_len += (double)n2 / 3.0; }
     if (MODE == 0) return kj_classify_mem<IdxT>(cx, q, best_out);
     else return kj_classify_greedy<IdxT>(cx, q, query_len, best_out);
 }

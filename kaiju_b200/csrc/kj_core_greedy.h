@@ -136,7 +136,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
 #if defined(KJ_EMU)
             const int i0_ = one.i;
 #endif
-            kj_chain_finish<IdxT>(ix, frag, one);                          // every lane runs the same chain: identical addresses, one sector per step
+            kj_chain_finish<IdxT, true>(ix, frag, one);                          // every lane runs the same chain: identical addresses, one sector per step
 #if defined(KJ_EMU)
             if (w.lane == 0) kj_emu_stats.var_steps += (unsigned long long)(i0_ - one.i + 1);
 #endif
@@ -160,9 +160,9 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
                 if (jstart >= 0) {
                     KjChain<IdxT> t; t.lo = 0; t.hi = 0; t.i = 0; t.st = KJ_ST_EXACT;
 #ifndef KJ_PROBE
-                    if (jstart - w.lane >= L - 1 || (start_la && jstart - w.lane >= 0)) kj_chain_start<IdxT>(ix, frag, jstart - w.lane, rp.seed_length, t);
+                    if (jstart - w.lane >= L - 1 || (start_la && jstart - w.lane >= 0)) kj_chain_start<IdxT, true>(ix, frag, jstart - w.lane, rp.seed_length, t);
 #else
-                    if (jstart - w.lane >= 0) kj_chain_start<IdxT>(ix, frag, jstart - w.lane, rp.seed_length, t);
+                    if (jstart - w.lane >= 0) kj_chain_start<IdxT, true>(ix, frag, jstart - w.lane, rp.seed_length, t);
 #endif
                     w.sync();
                     if (start_la) { nxt = t; have_nxt = true; } else { cur = t; round = 0; }
@@ -199,7 +199,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
                     const bool top = need && !(w.lane > 0 && ((nm >> (w.lane - 1)) & 1u));
                     const int group = (round == 0 && mono) ? 0 : KJ_GROUP_LATE;
                     const bool sel = need && (top || kj_popc(nm & lanemask_lt(w.lane)) < group);
-                    kj_finish_selected<IdxT>(w, ix, frag, sel, cur);
+                    kj_finish_selected<IdxT, true>(w, ix, frag, sel, cur);
                     round++;
                     continue;
                 }
@@ -296,7 +296,7 @@ static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, KjQueue& q, double quer
                         const uint32_t failmask = ~w.ballot(pass) & 0x7ffffu;
                         const int n_ok = failmask ? kj_ffs(failmask) - 1 : 19;      // first failing substitute ends the loop (391)
                         IdxT lo = (IdxT)sm.lo, hi = (IdxT)(sm.lo + sm.len); bool ok = false;
-                        if (w.lane < n_ok) ok = kj_update_si<IdxT>(ix, sub, lo, hi);
+                        if (w.lane < n_ok) ok = kj_update_si<IdxT, true>(ix, sub, lo, hi);
                         w.sync();
                         const uint32_t okmask = w.ballot(ok); const uint32_t cnt = (uint32_t)kj_popc(okmask);
                         if (cnt) {

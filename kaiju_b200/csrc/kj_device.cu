@@ -66,7 +66,9 @@ static __host__ __device__ __forceinline__ KjRunParams kj_fixed_profile(int mode
     return p;
 }
 // VB = true: the verbose outputs (id sets, accession sets, fragment strings) are compiled in; the kernels of the normal path carry none of it.
-template <int MODE, class IdxT, bool GWS, bool FIX, bool VB>
+// ROLE: 0 = the whole item in this kernel; 1 = front end only (translation, fragments, ranked queue -> a record per item in `prep`); 2 = search only (from the records).
+// Greedy runs as the pair 1 + 2 over sub-batches of the launch (kj_core.h: the search loop then shares the instruction cache with nothing it does not need).
+template <int MODE, class IdxT, bool GWS, bool FIX, bool VB, int ROLE>
 __global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32, MODE == 0 ? KJ_MIN_BLOCKS : KJ_MIN_BLOCKS_GREEDY)
 kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ KjRunParams rp, const __grid_constant__ KjSmemLayout lay,
                    const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
@@ -75,7 +77,8 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
                    uint64_t* __restrict__ taxon_out, uint32_t* __restrict__ best_out, uint64_t* __restrict__ ids_out, uint8_t* __restrict__ nids_out, uint32_t* __restrict__ compact_out,
                    unsigned long long* __restrict__ counter, KjKept* __restrict__ spill, uint8_t* __restrict__ gscratch,
                    uint32_t gscratch_bytes, uint8_t* __restrict__ gws, unsigned long long* __restrict__ counts, uint32_t* __restrict__ err,
-                   uint32_t* __restrict__ acc_out, uint8_t* __restrict__ nacc_out, char* __restrict__ frag_out, uint32_t frag_stride, uint32_t* __restrict__ frag_len_out) {
+                   uint32_t* __restrict__ acc_out, uint8_t* __restrict__ nacc_out, char* __restrict__ frag_out, uint32_t frag_stride, uint32_t* __restrict__ frag_len_out,
+                   uint8_t* __restrict__ prep, uint32_t prep_stride, uint64_t r_begin) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     KjCtaShared* sh = (KjCtaShared*)smem_raw;
     {   // stage the index descriptor (C[] etc.) and the small tables once per CTA
@@ -112,7 +115,7 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
     KJ_ROLLED
     for (;;) {
         unsigned long long r0 = 0;
-        if (cx.w.lane == 0) r0 = atomicAdd(counter, (unsigned long long)KJ_CLAIM);
+        if (cx.w.lane == 0) r0 = r_begin + atomicAdd(counter, (unsigned long long)KJ_CLAIM);      // this launch covers items [r_begin, n_reads)
         r0 = cx.w.shfl64(r0, 0);
         if (r0 >= n_reads) break;
         const unsigned long long ri = r0 + (unsigned long long)cx.w.lane;
@@ -142,7 +145,8 @@ kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ 
             const uint8_t* p2 = !paired ? nullptr : stage ? stg + cx.L.stage_stride + al2 + (uint32_t)(b0 - f2) : seq2 + b0;
             uint32_t best = 0;
             if (VB && frag_out) { cx.text = frag_out + r * frag_stride; cx.text_len = 0; }
-            uint32_t t = kj_classify_item<MODE, IdxT>(cx, p1, (int)(a1 - a0), p2, (int)(b1 - b0), paired, best);
+            uint32_t t = kj_classify_item<MODE, IdxT, ROLE>(cx, p1, (int)(a1 - a0), p2, (int)(b1 - b0), paired, best, ROLE ? prep + (size_t)(r - r_begin) * prep_stride : nullptr);
+            if (ROLE == 1) { cx.w.sync(); continue; }
             const uint64_t id = t == KJ_TAX_BAD ? 0ull : sh->ix.tax_id[t];
             if (cx.w.lane == 0) {
                 if (taxon_out) taxon_out[r] = id;
@@ -224,6 +228,7 @@ struct kj_ctx {
     unsigned long long* d_counts = nullptr; unsigned long long* d_counts_pending = nullptr; uint32_t n_counts = 0, n_present = 0;   // per-taxon read counts (+1 slot: unclassified)
     uint32_t variant_boost = 1;    // Greedy variant-ring capacity multiplier, raised after an overflow (flag 4) so that a retry succeeds
     uint8_t* d_ws = nullptr; size_t ws_bytes = 0;
+    uint8_t* d_prep = nullptr; size_t prep_bytes = 0;      // prepared-item records of the two-kernel Greedy path (two slots)
     cudaStream_t stream[2] = {nullptr, nullptr}; cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // staging for kj_classify (host buffers)
     uint8_t* d_seq[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; size_t d_seq_cap[2][2] = {{0, 0}, {0, 0}};
@@ -274,14 +279,22 @@ static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid,
     { std::lock_guard<std::mutex> lk(attr_mu); if (c->device < 64 && smem > attr_set[c->device][inst]) { attr_set[c->device][inst] = smem; raise = true; } else if (c->device >= 64) raise = true; }
     if (!raise && smem == c->smem_bytes && c->grid > 0 && c->cfg_mode == cfg) { grid = c->grid; return KJ_OK; }
     int per_sm = 0;
-#define KJ_CFG(M, T, G, F, V) { if (raise) CK(cudaFuncSetAttribute(kj_classify_kernel<M, T, G, F, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<M, T, G, F, V>, KJ_WARPS_PER_CTA * 32, smem)); }
+#define KJ_CFGR(M, T, G, F, V, R) { if (raise) CK(cudaFuncSetAttribute(kj_classify_kernel<M, T, G, F, V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kj_classify_kernel<M, T, G, F, V, R>, KJ_WARPS_PER_CTA * 32, smem)); }
+#define KJ_CFG(M, T, G, F, V) KJ_CFGR(M, T, G, F, V, 0)
 #define KJ_CFG2(M, T) { if (verbose) { if (rp.ws_global) KJ_CFG(M, T, true, false, true) else KJ_CFG(M, T, false, false, true) } \
                         else if (rp.ws_global) KJ_CFG(M, T, true, false, false) else if (fixed) KJ_CFG(M, T, false, true, false) else KJ_CFG(M, T, false, false, false) }
+    // the Greedy front-end / search pair (launch()): the grid is the search kernel's, the front end needs no more than that
+#define KJ_CFGS(T) { if (fixed) { KJ_CFGR(1, T, false, true, false, 1) KJ_CFGR(1, T, false, true, false, 2) } else { KJ_CFGR(1, T, false, false, false, 1) KJ_CFGR(1, T, false, false, false, 2) } }
     if (rp.mode == 0) { if (c->H.wide) KJ_CFG2(0, uint64_t) else KJ_CFG2(0, uint32_t) }
-    else { if (c->H.wide) KJ_CFG2(1, uint64_t) else KJ_CFG2(1, uint32_t) }
+    else {
+        if (c->H.wide) KJ_CFG2(1, uint64_t) else KJ_CFG2(1, uint32_t)
+        if (!rp.ws_global && !verbose) { if (c->H.wide) KJ_CFGS(uint64_t) else KJ_CFGS(uint32_t) }
+    }
+#undef KJ_CFGS
 #undef KJ_CFG2
 #undef KJ_CFG
+#undef KJ_CFGR
     c->cfg_mode = cfg;
     if (per_sm < 1) { kj_err() = "kernel does not fit on an SM"; return KJ_ERR_UNSUPPORTED; }
     grid = c->sm_count * per_sm;             // persistent grid: a whole number of CTAs per SM
@@ -460,7 +473,7 @@ extern "C" void kj_destroy(kj_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     kj_files_state_free(c->files); c->files = nullptr;
-    if (c->d_ix_mem) cudaFree(c->d_ix_mem); if (c->d_kmer_mem) cudaFree(c->d_kmer_mem);
+    if (c->d_ix_mem) cudaFree(c->d_ix_mem); if (c->d_kmer_mem) cudaFree(c->d_kmer_mem); if (c->d_prep) cudaFree(c->d_prep);
     void* ptrs[] = {c->d_rank, c->d_letters, c->d_sa_tax, c->d_seq_tax, c->d_tax_parent, c->d_tax_depth, c->d_tax_id, c->d_lnfact, c->d_kmer, c->d_tables, c->d_ix,
                     c->d_counter, c->d_err, c->d_maxlen, c->d_spill, c->d_gscratch, c->d_evbreaks, c->d_ws, c->d_counts, c->d_counts_pending, c->d_quirk, c->d_tax[0], c->d_tax[1], c->d_best[0], c->d_best[1],
                     c->d_seq[0][0], c->d_seq[0][1], c->d_seq[1][0], c->d_seq[1][1], c->d_off[0][0], c->d_off[0][1], c->d_off[1][0], c->d_off[1][1],
@@ -488,22 +501,49 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     size_t smem; int grid; int rc = configure_launch(c, rp, smem, grid, verbose); if (rc) return rc;
     rc = ensure_scratch(c, rp, grid); if (rc) return rc;
     c->grid = grid; c->smem_bytes = smem;
-    CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
     if (time_it) CK(cudaEventRecord(c->ev_a, st));
     const size_t warps = (size_t)grid * KJ_WARPS_PER_CTA;
     const KjSmemLayout lay = kj_smem_layout(rp);
     const bool fixed = !verbose && kj_use_fixed(rp);
     const KjDevIndex* dix = (rp.mode == 0 && c->d_ix_mem && rp.m >= (uint32_t)c->kmer_k_mem) ? c->d_ix_mem : c->d_ix;
-#define KJ_LAUNCH(M, T) if (verbose) { if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, true); else KJ_LAUNCH3(M, T, false, false, true); } \
-                        else if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, false); else if (fixed) KJ_LAUNCH3(M, T, false, true, false); else KJ_LAUNCH3(M, T, false, false, false)
-#define KJ_LAUNCH3(M, T, G, F, V) kj_classify_kernel<M, T, G, F, V><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(dix, rp, lay, d_seq1, d_off1, d_seq2, d_off2, base1, base2, n, d_tax, d_best, d_ids, d_nids, d_compact, \
+    // Greedy with the work space in shared memory: front-end kernel + search kernel over sub-batches (the records of a sub-batch live in d_prep)
+    const bool split = rp.mode == 1 && !rp.ws_global && !verbose && !getenv("KJ_NO_SPLIT");
+    const uint32_t pstride = split ? kj_prep_stride(rp) : 0u; uint64_t sub = n;
+    if (split) {
+        sub = std::max<uint64_t>(65536, std::min<uint64_t>(n, (1ull << 31) / pstride));        // <= 2 GB of records per slot
+        if (const char* v = getenv("KJ_SPLIT_SUB")) { const long long x = atoll(v); if (x >= 1024) sub = (uint64_t)x; }
+        sub = std::min(sub, n);
+        const size_t need = (size_t)std::max<uint64_t>(sub, std::min<uint64_t>((1ull << 31) / pstride, 524288)) * pstride * 2;     // two pipeline slots; no regrowth while batches ramp up
+        if (need > c->prep_bytes) { if (c->d_prep) cudaFree(c->d_prep); c->d_prep = nullptr; c->prep_bytes = 0; CK(cudaMalloc((void**)&c->d_prep, need)); c->prep_bytes = need; }
+    }
+    uint8_t* prep = split ? c->d_prep + (size_t)slot * (c->prep_bytes / 2) : nullptr;
+#define KJ_ARGS(B0, B1) dix, rp, lay, d_seq1, d_off1, d_seq2, d_off2, base1, base2, (uint64_t)(B1), d_tax, d_best, d_ids, d_nids, d_compact, \
             c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
             c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), \
-            rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err, d_acc, d_nacc, d_frag, frag_stride, d_fraglen)
-    if (rp.mode == 0) { if (c->H.wide) KJ_LAUNCH(0, uint64_t); else KJ_LAUNCH(0, uint32_t); }
-    else { if (c->H.wide) KJ_LAUNCH(1, uint64_t); else KJ_LAUNCH(1, uint32_t); }
+            rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err, d_acc, d_nacc, d_frag, frag_stride, d_fraglen, prep, pstride, (uint64_t)(B0)
+#define KJ_LAUNCH3(M, T, G, F, V, R, B0, B1) kj_classify_kernel<M, T, G, F, V, R><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(KJ_ARGS(B0, B1))
+#define KJ_LAUNCH(M, T) if (verbose) { if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, true, 0, 0, n); else KJ_LAUNCH3(M, T, false, false, true, 0, 0, n); } \
+                        else if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, false, 0, 0, n); else if (fixed) KJ_LAUNCH3(M, T, false, true, false, 0, 0, n); else KJ_LAUNCH3(M, T, false, false, false, 0, 0, n)
+#define KJ_LAUNCH_SPLIT(T, R, B0, B1) if (fixed) KJ_LAUNCH3(1, T, false, true, false, R, B0, B1); else KJ_LAUNCH3(1, T, false, false, false, R, B0, B1)
+    if (split) {
+        for (uint64_t b0 = 0; b0 < n; b0 += sub) {
+            const uint64_t b1 = std::min(n, b0 + sub);
+            CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
+            if (c->H.wide) KJ_LAUNCH_SPLIT(uint64_t, 1, b0, b1); else KJ_LAUNCH_SPLIT(uint32_t, 1, b0, b1);
+            CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
+            if (c->H.wide) KJ_LAUNCH_SPLIT(uint64_t, 2, b0, b1); else KJ_LAUNCH_SPLIT(uint32_t, 2, b0, b1);
+            c->launches += 2;
+        }
+        c->launches--;          // (the common tail below counts one)
+    } else {
+        CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
+        if (rp.mode == 0) { if (c->H.wide) KJ_LAUNCH(0, uint64_t); else KJ_LAUNCH(0, uint32_t); }
+        else { if (c->H.wide) KJ_LAUNCH(1, uint64_t); else KJ_LAUNCH(1, uint32_t); }
+    }
 #undef KJ_LAUNCH
 #undef KJ_LAUNCH3
+#undef KJ_LAUNCH_SPLIT
+#undef KJ_ARGS
     CK(cudaGetLastError());
     if (time_it) CK(cudaEventRecord(c->ev_b, st));
     c->launches++;

@@ -262,8 +262,8 @@ __global__ void kj_fmt_write(const uint64_t* __restrict__ tax, const uint32_t* _
 // host side
 // ------------------------------------------------------------------------------------------------
 struct KjDevBuf {   // grow-only device buffer
-    void* p = nullptr; size_t cap = 0;
-    int need(size_t bytes) { if (bytes <= cap) return KJ_OK; if (p) cudaFree(p); p = nullptr; cap = 0; size_t c = bytes + bytes / 4 + 4096; CK(cudaMalloc(&p, c)); cap = c; return KJ_OK; }
+    void* p = nullptr; size_t cap = 0; float boost = 1.f;     // boost: allocate for a batch that many times as large (cudaFree waits for every running kernel: avoid regrowth while the batches ramp up)
+    int need(size_t bytes) { if (bytes <= cap) return KJ_OK; if (p) cudaFree(p); p = nullptr; cap = 0; size_t c = (size_t)((double)bytes * boost) + bytes / 4 + 4096; CK(cudaMalloc(&p, c)); cap = c; return KJ_OK; }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return (T*)p; }
 };
@@ -509,7 +509,7 @@ struct KjWriter {   // ordered output: pinned buffers filled by D2H copies, writ
 };
 
 // One parsed batch on its way from the parser thread to the classifying thread
-struct KjBatch { KjBatchSide s[2]; uint64_t n = 0; unsigned int maxlen[2] = {0, 0}; bool last = false; };
+struct KjBatch { KjBatchSide s[2]; uint64_t n = 0; unsigned int maxlen[2] = {0, 0}; bool last = false; float boost = 1.f; };
 // One of the two classification lanes of the calling thread: while the kernel of batch k runs on one lane, batch k+1 is launched on the other
 // (its CTAs fill the SMs as the first kernel's CTAs retire), and batch k-1 is formatted and written
 struct KjLane { KjDevBuf tax, best, ids, nids, len, out, scan_tmp, totals; int batch = -1; bool busy = false; };
@@ -560,6 +560,13 @@ static int kj_parse_chunks(int device, int sm_count, KjFilesState& S, size_t chu
         { std::unique_lock<std::mutex> lk(S.mu); S.cv.wait(lk, [&] { return S.abort || S.n_free > 0; }); if (S.abort) return KJ_OK; S.n_free--; }
         si = (int)(S.nbatches % KJ_FILE_SLOTS); KjBatch& B = S.slot[si]; S.nbatches++;
         S.tm[0] += kj_ms_since(t);
+        {   // buffers of the first, small batches are allocated for the final batch size
+            const float boost = target < batch_max ? (float)batch_max / (float)target : 1.f; B.boost = boost;
+            for (int f = 0; f < S.nfiles; f++) {
+                KjParsed& P = S.side[f]; for (KjDevBuf* b : {&P.line_start, &P.cnt, &P.hdr, &P.nlen, &P.tiles, &P.scan_tmp, &P.rec_pos, &P.phase, &P.phase_tiles}) b->boost = boost;
+                for (KjDevBuf* b : {&B.s[f].seq, &B.s[f].off, &B.s[f].names, &B.s[f].name_off}) b->boost = boost;
+            }
+        }
         // 1. top up both sides to `target` bytes: the carry is already at the front of the device text, staged chunks are appended behind it
         for (int f = 0; f < S.nfiles; f++) {
             KjParsed& P = S.side[f];
@@ -567,7 +574,7 @@ static int kj_parse_chunks(int device, int sm_count, KjFilesState& S, size_t chu
                 KjStaged ck = S.rd[f].next();
                 if (!ck.error.empty()) { kj_err() = ck.error; return KJ_ERR_IO; }
                 if ((P.nbytes + ck.n + 1) > P.text[P.cur].cap) {           // grow: move what is there into the larger buffer
-                    KjDevBuf nb; if ((rc = nb.need(P.nbytes + ck.n + target + chunk + 1))) return rc;
+                    KjDevBuf nb; if ((rc = nb.need(P.nbytes + ck.n + std::max(target, batch_max) + chunk + 1))) return rc;
                     if (P.nbytes) CK(cudaMemcpyAsync(nb.p, P.text[P.cur].p, P.nbytes, cudaMemcpyDeviceToDevice, st));
                     CK(cudaStreamSynchronize(st)); P.text[P.cur].release(); P.text[P.cur] = nb;
                 }
@@ -618,7 +625,7 @@ static int kj_parse_chunks(int device, int sm_count, KjFilesState& S, size_t chu
         for (int f = 0; f < S.nfiles; f++) {
             KjParsed& P = S.side[f]; const uint64_t consumed = P.skip_all ? P.nbytes : (P.n_lines ? pos[f] : 0);
             const uint64_t tail = P.nbytes - consumed; const int other = P.cur ^ 1;
-            if ((rc = P.text[other].need(tail + target + chunk + 1))) return rc;
+            if ((rc = P.text[other].need(tail + std::max(target, batch_max) + chunk + 1))) return rc;
             if (tail) CK(cudaMemcpyAsync(P.text[other].p, P.text[P.cur].as<char>() + consumed, tail, cudaMemcpyDeviceToDevice, st));
             P.cur = other; P.nbytes = tail;
         }
@@ -678,6 +685,7 @@ static int kj_classify_files_impl(kj_ctx* c, KjFilesState& S, const char* in1, c
         KjLane& Ln = S.lane[l]; KjBatch& B = S.slot[si]; const uint64_t n = B.n; int r;
         Ln.batch = si; Ln.busy = true;
         if (!n) return KJ_OK;
+        for (KjDevBuf* b : {&Ln.tax, &Ln.best, &Ln.ids, &Ln.nids, &Ln.len, &Ln.out, &Ln.scan_tmp}) b->boost = B.boost;
         if ((r = Ln.tax.need(n * 8)) || (r = Ln.best.need(n * 4)) || (r = Ln.len.need((n + 2) * 4))) return r;
         if (verbose && ((r = Ln.ids.need(n * KJ_MAX_IDS * 8)) || (r = Ln.nids.need(n)))) return r;
         return launch(c, l, B.s[0].seq.as<uint8_t>(), B.s[0].off.as<uint64_t>(), paired ? B.s[1].seq.as<uint8_t>() : nullptr, paired ? B.s[1].off.as<uint64_t>() : nullptr, 0, 0, n, B.maxlen[0], B.maxlen[1],

@@ -120,7 +120,7 @@ static KjEmuStats g_emu_total; static std::atomic<int> g_emu_lock(0);
 struct EmuCtx {
     KjHostIndex H; KjDevIndex D; kj_params P; std::vector<double> evbreaks;
 };
-struct ItemArg { char* text; uint32_t text_cap, text_len; bool want_acc; uint32_t nacc; uint32_t accs[24]; uint32_t nids; uint32_t ids[24]; EmuCtx* c; KjRunParams* rp; uint8_t* smem; KjKept* spill; void* gscratch; uint32_t* err; const uint8_t* s1; int n1; const uint8_t* s2; int n2; bool paired; uint32_t tax[32]; uint32_t best[32]; };
+struct ItemArg { uint8_t* rec; char* text; uint32_t text_cap, text_len; bool want_acc; uint32_t nacc; uint32_t accs[24]; uint32_t nids; uint32_t ids[24]; EmuCtx* c; KjRunParams* rp; uint8_t* smem; KjKept* spill; void* gscratch; uint32_t* err; const uint8_t* s1; int n1; const uint8_t* s2; int n2; bool paired; uint32_t tax[32]; uint32_t best[32]; };
 
 static void item_body(kjemu::Sched* s, int lane, void* a) {
     ItemArg* A = (ItemArg*)a;
@@ -129,7 +129,16 @@ static void item_body(kjemu::Sched* s, int lane, void* a) {
     cx.text = A->text; cx.text_cap = A->text_cap; cx.text_len = 0; cx.want_acc = A->want_acc;
     uint32_t best = 0;
     const bool wide = A->c->D.wide != 0;
-    uint32_t t = A->rp->mode == 0 ? (wide ? kj_classify_item<0, uint64_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best) : kj_classify_item<0, uint32_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best))
+    uint32_t t;
+    if (A->rp->mode == 1 && A->rec) {
+        // the two-kernel Greedy path: front end -> record -> (work space wiped) -> search
+        if (wide) (void)kj_classify_item<1, uint64_t, 1>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best, A->rec); else (void)kj_classify_item<1, uint32_t, 1>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best, A->rec);
+        cx.w.sync();
+        for (uint32_t i = (uint32_t)lane; i < cx.L.total; i += 32) cx.smem[i] = 0xA5;
+        cx.w.sync();
+        t = wide ? kj_classify_item<1, uint64_t, 2>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best, A->rec) : kj_classify_item<1, uint32_t, 2>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best, A->rec);
+    } else
+    t = A->rp->mode == 0 ? (wide ? kj_classify_item<0, uint64_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best) : kj_classify_item<0, uint32_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best))
         : wide ? kj_classify_item<1, uint64_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best) : kj_classify_item<1, uint32_t>(cx, A->s1, A->n1, A->s2, A->n2, A->paired, best);
     A->tax[lane] = t; A->best[lane] = best;
     if (lane == 0) { A->nids = cx.nids; const uint32_t* ids = (const uint32_t*)(cx.smem + cx.L.ids_off); for (uint32_t u = 0; u < cx.nids && u < 24; u++) A->ids[u] = ids[u];
@@ -223,9 +232,11 @@ int kjemu_classify_v2(void* h, const char* seq1, const uint64_t* off1, const cha
         kjemu::Sched* s = new kjemu::Sched();
         std::vector<uint8_t> smem(L.total + 64); std::vector<KjKept> spill(rp.scratch_entries);
         std::vector<uint8_t> gscratch(kj_greedy_scratch_bytes(rp)); uint32_t err = 0;
+        const bool split = getenv("KJ_EMU_SPLIT") != nullptr && rp.mode == 1;      // Greedy through the front-end / search pair of the two-kernel path
+        std::vector<uint8_t> rec(kj_prep_stride(rp) + 64, 0xA5);
         for (;;) {
             uint64_t i = next.fetch_add(1); if (i >= n) break;
-            ItemArg A; A.c = c; A.rp = &rp; A.smem = smem.data(); A.spill = spill.data(); A.gscratch = gscratch.data(); A.err = &err;
+            ItemArg A; A.rec = split ? rec.data() : nullptr; A.c = c; A.rp = &rp; A.smem = smem.data(); A.spill = spill.data(); A.gscratch = gscratch.data(); A.err = &err;
             A.s1 = (const uint8_t*)seq1 + off1[i]; A.n1 = (int)(off1[i + 1] - off1[i]);
             A.s2 = paired ? (const uint8_t*)seq2 + off2[i] : nullptr; A.n2 = paired ? (int)(off2[i + 1] - off2[i]) : 0; A.paired = paired;
             A.text = frag_out ? frag_out + i * (size_t)frag_stride : nullptr; A.text_cap = frag_stride; A.text_len = 0; A.want_acc = acc_out != nullptr && c->D.sa_acc != nullptr; A.nacc = 0;
@@ -235,6 +246,7 @@ int kjemu_classify_v2(void* h, const char* seq1, const uint64_t* off1, const cha
             for (uint32_t g = 0; g < L.nguard; g++) for (uint32_t b = 0; b < 64; b++) if (smem[L.guard[g] + b] != 0xA5) {
                 fprintf(stderr, "kjemu: work-space red zone %u (offset %u) overwritten at read %llu\n", g, L.guard[g], (unsigned long long)i); abort(); }
             for (size_t b = L.total; b < smem.size(); b++) if (smem[b] != 0xA5) { fprintf(stderr, "kjemu: store past the work space at read %llu\n", (unsigned long long)i); abort(); }
+            for (size_t b = kj_prep_stride(rp); b < rec.size(); b++) if (rec[b] != 0xA5) { fprintf(stderr, "kjemu: store past the prepared-item record at read %llu\n", (unsigned long long)i); abort(); }
             for (int l = 1; l < 32; l++) if (A.tax[l] != A.tax[0] || A.best[l] != A.best[0]) { fprintf(stderr, "kjemu: non-uniform result at read %llu\n", (unsigned long long)i); abort(); }
             taxon_out[i] = A.tax[0] == KJ_TAX_BAD ? 0 : c->H.tax_id[A.tax[0]];
             if (best_out) best_out[i] = taxon_out[i] ? A.best[0] : 0;

@@ -10,5 +10,3 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 echo "N=$N greedy exit $?"; tail -c 700 $o/bench_${tag}_greedy_n$N.json
 timeout 600 python bench.py --steps 4 --warmup 3 --skip-cpu --headline-only > $o/bench_${tag}_n1.json 2> $o/bench_${tag}_n1.err; tail -c 600 $o/bench_${tag}_n1.json
 timeout 600 python -m pytest tests/test_gpu_build.py -q -k "multi" 2>&1 | tail -3 | tee $o/pytest_multi_$tag.log
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -k "file_ingest or blank_lines or per_taxon" 2>&1 | tail -5 | tee -a $o/pytest_multi_$tag.log
-KJ_FILES_TRACE=1 python tools/file_bench.py --pairs 12000000 --ref-pairs 100000 > $o/file_bench_$tag.json 2> $o/file_trace_$tag.txt; cat $o/file_bench_$tag.json; tail -3 $o/file_trace_$tag.txt
