@@ -26,6 +26,9 @@
 #ifndef KJ_MIN_BLOCKS
 #define KJ_MIN_BLOCKS 4          // resident CTAs per SM the register allocation is tuned for (ncu: latency-bound, see profiles/)
 #endif
+#ifndef KJ_MIN_BLOCKS_GREEDY_SPLIT
+#define KJ_MIN_BLOCKS_GREEDY_SPLIT 5   // front-end / search kernels of the two-kernel Greedy path: A/B round 2 (r2i) 18.14 vs 17.90 M pairs/s, e2e 17.07 vs 16.41
+#endif
 #ifndef KJ_MIN_BLOCKS_GREEDY
 #define KJ_MIN_BLOCKS_GREEDY 4   // A/B round 2 (5 CTAs = 48 registers): 12.0 vs 12.3 M pairs/s -- more warps, but more spill traffic and more instruction-fetch stalls
 #endif
@@ -69,7 +72,7 @@ static __host__ __device__ __forceinline__ KjRunParams kj_fixed_profile(int mode
 // ROLE: 0 = the whole item in this kernel; 1 = front end only (translation, fragments, ranked queue -> a record per item in `prep`); 2 = search only (from the records).
 // Greedy runs as the pair 1 + 2 over sub-batches of the launch (kj_core.h: the search loop then shares the instruction cache with nothing it does not need).
 template <int MODE, class IdxT, bool GWS, bool FIX, bool VB, int ROLE>
-__global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32, MODE == 0 ? KJ_MIN_BLOCKS : KJ_MIN_BLOCKS_GREEDY)
+__global__ void __launch_bounds__(KJ_WARPS_PER_CTA * 32, MODE == 0 ? KJ_MIN_BLOCKS : ROLE != 0 ? KJ_MIN_BLOCKS_GREEDY_SPLIT : KJ_MIN_BLOCKS_GREEDY)
 kj_classify_kernel(const KjDevIndex* __restrict__ g_ix, const __grid_constant__ KjRunParams rp, const __grid_constant__ KjSmemLayout lay,
                    const uint8_t* __restrict__ seq1, const uint64_t* __restrict__ off1,
                    const uint8_t* __restrict__ seq2, const uint64_t* __restrict__ off2,
@@ -228,7 +231,8 @@ struct kj_ctx {
     unsigned long long* d_counts = nullptr; unsigned long long* d_counts_pending = nullptr; uint32_t n_counts = 0, n_present = 0;   // per-taxon read counts (+1 slot: unclassified)
     uint32_t variant_boost = 1;    // Greedy variant-ring capacity multiplier, raised after an overflow (flag 4) so that a retry succeeds
     uint8_t* d_ws = nullptr; size_t ws_bytes = 0;
-    uint8_t* d_prep = nullptr; size_t prep_bytes = 0;      // prepared-item records of the two-kernel Greedy path (two slots)
+    uint8_t* d_prep = nullptr; size_t prep_bytes = 0;      // prepared-item records of the two-kernel Greedy path (two slots x two buffers)
+    cudaStream_t fstream[2] = {nullptr, nullptr}; cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_f[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, ev_s[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // front-end stream + hand-over events per slot
     cudaStream_t stream[2] = {nullptr, nullptr}; cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // staging for kj_classify (host buffers)
     uint8_t* d_seq[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; size_t d_seq_cap[2][2] = {{0, 0}, {0, 0}};
@@ -289,7 +293,7 @@ static int configure_launch(kj_ctx* c, KjRunParams& rp, size_t& smem, int& grid,
     if (rp.mode == 0) { if (c->H.wide) KJ_CFG2(0, uint64_t) else KJ_CFG2(0, uint32_t) }
     else {
         if (c->H.wide) KJ_CFG2(1, uint64_t) else KJ_CFG2(1, uint32_t)
-        if (!rp.ws_global && !verbose) { if (c->H.wide) KJ_CFGS(uint64_t) else KJ_CFGS(uint32_t) }
+        if (!rp.ws_global && !verbose && !getenv("KJ_NO_SPLIT")) { if (c->H.wide) KJ_CFGS(uint64_t) else KJ_CFGS(uint32_t) }
     }
 #undef KJ_CFGS
 #undef KJ_CFG2
@@ -369,8 +373,12 @@ static int finish_ctx(kj_ctx* c, uint64_t tot) {
     CK(cudaMemcpy(c->d_quirk, H.quirk_d, sizeof H.quirk_d, cudaMemcpyHostToDevice));
     if ((rc = upload_descriptor(c))) return rc;
     c->index_bytes = tot;
-    CK(cudaMalloc((void**)&c->d_counter, 2 * sizeof(unsigned long long))); CK(cudaMalloc((void**)&c->d_maxlen, 2 * sizeof(unsigned int)));
-    for (int s = 0; s < 2; s++) CK(cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking));
+    CK(cudaMalloc((void**)&c->d_counter, 4 * sizeof(unsigned long long)));       // [slot] classify / search, [2 + slot] front end CK(cudaMalloc((void**)&c->d_maxlen, 2 * sizeof(unsigned int)));
+    for (int s = 0; s < 2; s++) {
+        CK(cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->fstream[s], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming));
+        for (int b = 0; b < 2; b++) { CK(cudaEventCreateWithFlags(&c->ev_f[s][b], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_s[s][b], cudaEventDisableTiming)); }
+    }
     CK(cudaEventCreate(&c->ev_a)); CK(cudaEventCreate(&c->ev_b));
     if ((rc = upload_evalue_breaks(c))) return rc;
     c->n_counts = (uint32_t)H.tax_id.size() + 1u; c->n_present = H.n_present;
@@ -480,7 +488,8 @@ extern "C" void kj_destroy(kj_ctx* c) {
                     c->d_ids[0], c->d_ids[1], c->d_nids[0], c->d_nids[1], c->d_sa_acc, c->d_seq_acc, c->d_acc[0], c->d_acc[1], c->d_nacc[0], c->d_nacc[1],
                     c->d_frag[0], c->d_frag[1], c->d_fraglen[0], c->d_fraglen[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (int s = 0; s < 2; s++) if (c->stream[s]) cudaStreamDestroy(c->stream[s]);
+    for (int s = 0; s < 2; s++) { if (c->stream[s]) cudaStreamDestroy(c->stream[s]); if (c->fstream[s]) cudaStreamDestroy(c->fstream[s]); if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]);
+                                  for (int b = 0; b < 2; b++) { if (c->ev_f[s][b]) cudaEventDestroy(c->ev_f[s][b]); if (c->ev_s[s][b]) cudaEventDestroy(c->ev_s[s][b]); } }
     if (c->ev_a) cudaEventDestroy(c->ev_a); if (c->ev_b) cudaEventDestroy(c->ev_b);
     delete c;
 }
@@ -510,33 +519,53 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     const bool split = rp.mode == 1 && !rp.ws_global && !verbose && !getenv("KJ_NO_SPLIT");
     const uint32_t pstride = split ? kj_prep_stride(rp) : 0u; uint64_t sub = n;
     if (split) {
-        sub = std::max<uint64_t>(65536, std::min<uint64_t>(n, (1ull << 31) / pstride));        // <= 2 GB of records per slot
-        if (const char* v = getenv("KJ_SPLIT_SUB")) { const long long x = atoll(v); if (x >= 1024) sub = (uint64_t)x; }
+        // records of one sub-batch per buffer; two buffers per slot (the front end of sub-batch b+1 runs in the tail of the search of sub-batch b).
+        // Up to 4 GB per buffer where HBM is plentiful: fewer, longer search launches (750 k vs 3 M pairs per launch: 17.9 vs 18.3 M pairs/s)
+        uint64_t per_buf = c->prep_bytes / 4;
+        if (per_buf < (4ull << 30) && per_buf < n * (uint64_t)pstride) {       // (re)allocate: what this launch needs, at least 1 GB, at most 4 GB or 1/24 of the free memory
+            size_t fr = 0, to = 0; CK(cudaMemGetInfo(&fr, &to)); fr += c->prep_bytes;
+            const uint64_t lim = std::max<uint64_t>(64ull << 20, std::min<uint64_t>(4ull << 30, fr / 24));
+            const uint64_t want = std::min<uint64_t>(lim, std::max<uint64_t>(1ull << 30, n * (uint64_t)pstride + (n * (uint64_t)pstride) / 4));
+            if (want > per_buf) {
+                if (c->d_prep) cudaFree(c->d_prep); c->d_prep = nullptr; c->prep_bytes = 0;
+                CK(cudaMalloc((void**)&c->d_prep, (size_t)want * 4)); c->prep_bytes = (size_t)want * 4; per_buf = want;
+            }
+        }
+        sub = std::max<uint64_t>(1024, per_buf / pstride);
+        if (const char* v = getenv("KJ_SPLIT_SUB")) { const long long x = atoll(v); if (x >= 1024 && (uint64_t)x < sub) sub = (uint64_t)x; }
         sub = std::min(sub, n);
-        const size_t need = (size_t)std::max<uint64_t>(sub, std::min<uint64_t>((1ull << 31) / pstride, 524288)) * pstride * 2;     // two pipeline slots; no regrowth while batches ramp up
-        if (need > c->prep_bytes) { if (c->d_prep) cudaFree(c->d_prep); c->d_prep = nullptr; c->prep_bytes = 0; CK(cudaMalloc((void**)&c->d_prep, need)); c->prep_bytes = need; }
     }
-    uint8_t* prep = split ? c->d_prep + (size_t)slot * (c->prep_bytes / 2) : nullptr;
 #define KJ_ARGS(B0, B1) dix, rp, lay, d_seq1, d_off1, d_seq2, d_off2, base1, base2, (uint64_t)(B1), d_tax, d_best, d_ids, d_nids, d_compact, \
-            c->d_counter + slot, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
+            ctr, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
             c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), \
-            rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err, d_acc, d_nacc, d_frag, frag_stride, d_fraglen, prep, pstride, (uint64_t)(B0)
-#define KJ_LAUNCH3(M, T, G, F, V, R, B0, B1) kj_classify_kernel<M, T, G, F, V, R><<<grid, KJ_WARPS_PER_CTA * 32, smem, st>>>(KJ_ARGS(B0, B1))
+            rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err, d_acc, d_nacc, d_frag, frag_stride, d_fraglen, pbuf, pstride, (uint64_t)(B0)
+#define KJ_LAUNCH3(M, T, G, F, V, R, B0, B1) kj_classify_kernel<M, T, G, F, V, R><<<grid, KJ_WARPS_PER_CTA * 32, smem, kst>>>(KJ_ARGS(B0, B1))
 #define KJ_LAUNCH(M, T) if (verbose) { if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, true, 0, 0, n); else KJ_LAUNCH3(M, T, false, false, true, 0, 0, n); } \
                         else if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, false, 0, 0, n); else if (fixed) KJ_LAUNCH3(M, T, false, true, false, 0, 0, n); else KJ_LAUNCH3(M, T, false, false, false, 0, 0, n)
 #define KJ_LAUNCH_SPLIT(T, R, B0, B1) if (fixed) KJ_LAUNCH3(1, T, false, true, false, R, B0, B1); else KJ_LAUNCH3(1, T, false, false, false, R, B0, B1)
+    uint8_t* pbuf = nullptr; unsigned long long* ctr = c->d_counter + slot; cudaStream_t kst = st;
     if (split) {
-        for (uint64_t b0 = 0; b0 < n; b0 += sub) {
-            const uint64_t b1 = std::min(n, b0 + sub);
-            CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
+        // front end on the slot's own stream, search on the caller's: F(b) -> S(b) through ev_f, S(b) -> F(b+2) (same buffer) through ev_s
+        cudaStream_t fs = c->fstream[slot]; uint8_t* base = c->d_prep + (size_t)slot * (c->prep_bytes / 2); uint64_t k = 0;
+        CK(cudaEventRecord(c->ev_in[slot], st)); CK(cudaStreamWaitEvent(fs, c->ev_in[slot], 0));      // the inputs may have been produced on the caller's stream
+        for (uint64_t b0 = 0; b0 < n; b0 += sub, k++) {
+            const uint64_t b1 = std::min(n, b0 + sub); const int pb = (int)(k & 1);
+            pbuf = base + (size_t)pb * (c->prep_bytes / 4);
+            CK(cudaStreamWaitEvent(fs, c->ev_s[slot][pb], 0));                 // the search that last read this buffer (of this or an earlier launch; no-op if none)
+            ctr = c->d_counter + 2 + slot; kst = fs;
+            CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), fs));
             if (c->H.wide) KJ_LAUNCH_SPLIT(uint64_t, 1, b0, b1); else KJ_LAUNCH_SPLIT(uint32_t, 1, b0, b1);
-            CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
+            CK(cudaEventRecord(c->ev_f[slot][pb], fs));
+            ctr = c->d_counter + slot; kst = st;
+            CK(cudaStreamWaitEvent(st, c->ev_f[slot][pb], 0));
+            CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
             if (c->H.wide) KJ_LAUNCH_SPLIT(uint64_t, 2, b0, b1); else KJ_LAUNCH_SPLIT(uint32_t, 2, b0, b1);
+            CK(cudaEventRecord(c->ev_s[slot][pb], st));
             c->launches += 2;
         }
         c->launches--;          // (the common tail below counts one)
     } else {
-        CK(cudaMemsetAsync(c->d_counter + slot, 0, sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
         if (rp.mode == 0) { if (c->H.wide) KJ_LAUNCH(0, uint64_t); else KJ_LAUNCH(0, uint32_t); }
         else { if (c->H.wide) KJ_LAUNCH(1, uint64_t); else KJ_LAUNCH(1, uint32_t); }
     }
