@@ -1155,7 +1155,24 @@ static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1
             else kj_translate_pair(cx, q, s1, n1, n1 >= m3, s2, n2, paired && n2 >= m3, greedy);   // a short mate is skipped individually (699, 705)
         }
         if (ok && MODE == 1) kj_queue_sort(cx, q);     // greedy pops every fragment (and many variants): ranking once pays (A/B +9 %); MEM stops after a few pops (A/B -16 %)
-        if (ROLE == 1) { kj_prep_store(cx, q, ok, rec); return KJ_TAX_BAD; }
+        if (ROLE == 1) {
+            // The search would run the SEG gate on every fragment it pops; for most of them the window classes already say "nothing to mask" (kj_seg
+            // returns 0 and the fragment is searched as it is).  Decide that here, for every queued fragment, and mark it as checked: the class scan
+            // leaves the search kernel's hot loop (6 % of its instructions, 1.5 KB of its hot code) for this kernel, which has issue slots to spare.
+#ifndef KJ_NO_FRONT_SEG
+            if (ok && MODE == 1 && rp.seg) {
+                KJ_ROLLED
+                for (uint32_t i = 0; i < q.n; i++) {
+                    const uint32_t p = q.pay[i]; const uint32_t arr = p >> 30, start = (p >> 14) & 0x7fffu, len = p & 0x3fffu;
+                    bool clean = (int)len < KJ_SEG_WINDOW;
+                    if (!clean) { kj_load_frag(cx, arr, start, len); clean = !kj_seg_flags(cx, (int)len, true); }
+                    if (clean && cx.w.lane == 0) q.pay[i] = p | (1u << 29);
+                    cx.w.sync();
+                }
+            }
+#endif
+            kj_prep_store(cx, q, ok, rec); return KJ_TAX_BAD;
+        }
         if (!ok) return KJ_TAX_BAD;
     } else if (!kj_prep_load(cx, q, rec)) return KJ_TAX_BAD;
     double query_len;                                                    // E-value query length (659, 698, 704)

@@ -373,7 +373,7 @@ static int finish_ctx(kj_ctx* c, uint64_t tot) {
     CK(cudaMemcpy(c->d_quirk, H.quirk_d, sizeof H.quirk_d, cudaMemcpyHostToDevice));
     if ((rc = upload_descriptor(c))) return rc;
     c->index_bytes = tot;
-    CK(cudaMalloc((void**)&c->d_counter, 4 * sizeof(unsigned long long)));       // [slot] classify / search, [2 + slot] front end CK(cudaMalloc((void**)&c->d_maxlen, 2 * sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&c->d_counter, 4 * sizeof(unsigned long long))); CK(cudaMalloc((void**)&c->d_maxlen, 2 * sizeof(unsigned int)));       // counters: [slot] classify / search, [2 + slot] front end
     for (int s = 0; s < 2; s++) {
         CK(cudaStreamCreateWithFlags(&c->stream[s], cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->fstream[s], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming));

@@ -41,6 +41,18 @@ def test_emulated_kernel_matches_reference_golden(emu, golden, cfg, tag):
     assert len(bad) == 0, [(names[i], int(tax[i]), int(etax[i]), int(best[i]), int(ebest[i])) for i in bad[:5]]
 
 
+@pytest.mark.parametrize("cfg", [c for c in sorted(GOLDEN_CONFIGS) if c.startswith("greedy")])
+def test_emulated_two_kernel_greedy_matches_reference_golden(emu, golden, cfg, monkeypatch):
+    """Greedy as the GPU runs it: front end -> per-item record (queue, translated arrays; SEG class scan done there) -> work space wiped -> search."""
+    monkeypatch.setenv("KJ_EMU_SPLIT", "1")
+    for tag in ("pe150", "se100"):
+        names, s1, o1, s2, o2 = golden.reads(tag)
+        tax, best = emu_classify(emu, golden.fmi, golden.nodes, make_params(**GOLDEN_CONFIGS[cfg]), s1, o1, s2, o2)
+        etax, ebest, _ = golden.expected(cfg, tag)
+        bad = np.nonzero((tax != etax) | (best != ebest))[0]
+        assert len(bad) == 0, [(names[i], int(tax[i]), int(etax[i]), int(best[i]), int(ebest[i])) for i in bad[:5]]
+
+
 def test_emulated_kernel_matches_oracle_on_random_parameters(emu, golden):
     """Seeded sweep over the CLI parameter space (-a, -m, -e, -s, -E, -x/-X): kernel logic (emulated) == oracle (pinned to the reference)."""
     import random
