@@ -491,7 +491,7 @@ static KJ_DEV void kj_split_frames_rolled(KjWarpCtx& cx, KjQueue& q, const int n
 
 // Both mates are translated and split in the SAME loops (array a = 2*mate + strand): the four arrays are independent, so
 // their load/ballot/bit-twiddling chains overlap instead of running back to back (the kernel is bound by dependent latency).
-static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s1, int n1, bool do1, const uint8_t* s2, int n2, bool do2, bool greedy) {
+static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s1, int n1, bool do1, const uint8_t* s2, int n2, bool do2, bool greedy, const bool small_code) {
     const Warp& w = cx.w; const KjTables& tb = *cx.tb;
     uint8_t* aa = cx.smem + cx.L.aa_off; const uint32_t st = cx.L.aa_stride;
     const int na1 = do1 ? n1 - 2 : 0, na2 = do2 ? n2 - 2 : 0;
@@ -517,7 +517,7 @@ static KJ_DEV void kj_translate_pair(KjWarpCtx& cx, KjQueue& q, const uint8_t* s
     }
     w.sync();
 #ifndef KJ_SPLIT_UNROLLED_GREEDY      // A/B round 2: Greedy +12 % (16.04 vs 14.30 M pairs/s) with the quarter-size splitting code
-    if (greedy) kj_split_frames_rolled(cx, q, na1, na2, n1, n2, greedy, 3); else
+    if (small_code) kj_split_frames_rolled(cx, q, na1, na2, n1, n2, greedy, 3); else
 #endif
     kj_split_frames(cx, q, na1, na2, n1, n2, greedy, 3);
 }
@@ -1080,7 +1080,7 @@ template <class IdxT> static KJ_DEV uint32_t kj_classify_greedy(KjWarpCtx& cx, K
 // "ACDEFGHIKLMNPQRSTVWY"; pieces of at least m residues (Greedy: and score >= min_score) are queued in order, the tail last.
 // The residues are stored like one reading frame of a translated read (residue e at array index 3e), so the queue
 // payloads, kj_load_frag and the SEG pieces need no second addressing mode.
-static KJ_DEV void kj_protein_fragments(KjWarpCtx& cx, KjQueue& q, const uint8_t* s1, int n1, bool greedy) {
+static KJ_DEV void kj_protein_fragments(KjWarpCtx& cx, KjQueue& q, const uint8_t* s1, int n1, bool greedy, const bool small_code) {
     const Warp& w = cx.w; const KjTables& tb = *cx.tb;
     uint8_t* aa = cx.smem + cx.L.aa_off;
     KJ_ROLLED
@@ -1090,7 +1090,7 @@ static KJ_DEV void kj_protein_fragments(KjWarpCtx& cx, KjQueue& q, const uint8_t
     }
     w.sync();
 #ifndef KJ_SPLIT_UNROLLED_GREEDY
-    if (greedy) kj_split_frames_rolled(cx, q, 3 * n1 - 2, 0, n1, 0, greedy, 1); else
+    if (small_code) kj_split_frames_rolled(cx, q, 3 * n1 - 2, 0, n1, 0, greedy, 1); else
 #endif
     kj_split_frames(cx, q, 3 * n1 - 2, 0, n1, 0, greedy, 1);
 }
@@ -1143,16 +1143,19 @@ static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1
     KjQueue q; q.key = (uint64_t*)(cx.smem + cx.L.qkey_off); q.pay = (uint32_t*)(cx.smem + cx.L.qpay_off);
     q.ord = cx.smem + cx.L.qord_off; q.cap = rp.item_cap; q.n = 0; q.late = 0; q.next = 0; q.nsorted = 0; q.dirty = true;
     const bool greedy = MODE == 1;
+    // the one-kernel Greedy path trades the interleaved (4 arrays at once) frame splitting for a quarter of its code; the front-end kernel of the
+    // two-kernel path has the instruction cache to itself and keeps the fast one
+    const bool small_code = MODE == 1 && ROLE == 0;
     const int m3 = (int)rp.m * 3;
     if (ROLE != 2) {
         bool ok = true;
         if (rp.protein) {
             if (n1 < (int)rp.m) ok = false;                                  // (640-646)
-            else kj_protein_fragments(cx, q, s1, n1, greedy);
+            else kj_protein_fragments(cx, q, s1, n1, greedy, small_code);
         } else {
             // short-read gate (648-653): SE len1 < 3m; PE only if BOTH mates are short
             if ((!paired && n1 < m3) || (paired && n1 < m3 && n2 < m3)) ok = false;
-            else kj_translate_pair(cx, q, s1, n1, n1 >= m3, s2, n2, paired && n2 >= m3, greedy);   // a short mate is skipped individually (699, 705)
+            else kj_translate_pair(cx, q, s1, n1, n1 >= m3, s2, n2, paired && n2 >= m3, greedy, small_code);   // a short mate is skipped individually (699, 705)
         }
         if (ok && MODE == 1) kj_queue_sort(cx, q);     // greedy pops every fragment (and many variants): ranking once pays (A/B +9 %); MEM stops after a few pops (A/B -16 %)
         if (ROLE == 1) {
@@ -1165,7 +1168,7 @@ static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1
                 for (uint32_t i = 0; i < q.n; i++) {
                     const uint32_t p = q.pay[i]; const uint32_t arr = p >> 30, start = (p >> 14) & 0x7fffu, len = p & 0x3fffu;
                     bool clean = (int)len < KJ_SEG_WINDOW;
-                    if (!clean) { kj_load_frag(cx, arr, start, len); clean = !kj_seg_flags(cx, (int)len, true); }
+                    if (!clean) { kj_load_frag(cx, arr, start, len); clean = !kj_seg_flags(cx, (int)len, false); }
                     if (clean && cx.w.lane == 0) q.pay[i] = p | (1u << 29);
                     cx.w.sync();
                 }
