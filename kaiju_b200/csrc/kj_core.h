@@ -1162,7 +1162,7 @@ static KJ_DEV uint32_t kj_classify_item(KjWarpCtx& cx, const uint8_t* s1, int n1
             // The search would run the SEG gate on every fragment it pops; for most of them the window classes already say "nothing to mask" (kj_seg
             // returns 0 and the fragment is searched as it is).  Decide that here, for every queued fragment, and mark it as checked: the class scan
             // leaves the search kernel's hot loop (6 % of its instructions, 1.5 KB of its hot code) for this kernel, which has issue slots to spare.
-#ifndef KJ_NO_FRONT_SEG
+#ifdef KJ_FRONT_SEG      // A/B round 2 (r2k, front end not yet running beside the search): 17.85 vs 18.50 M pairs/s -- the scan of ALL queued fragments costs more than the popped ones save
             if (ok && MODE == 1 && rp.seg) {
                 KJ_ROLLED
                 for (uint32_t i = 0; i < q.n; i++) {

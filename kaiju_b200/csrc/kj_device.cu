@@ -539,11 +539,14 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
             ctr, c->d_spill + (size_t)slot * warps * rp.scratch_entries, \
             c->d_gscratch + (size_t)slot * warps * kj_greedy_scratch_bytes(rp), kj_greedy_scratch_bytes(rp), \
             rp.ws_global ? c->d_ws + (size_t)slot * warps * kj_smem_layout(rp).total : nullptr, d_count_dst, c->d_err, d_acc, d_nacc, d_frag, frag_stride, d_fraglen, pbuf, pstride, (uint64_t)(B0)
-#define KJ_LAUNCH3(M, T, G, F, V, R, B0, B1) kj_classify_kernel<M, T, G, F, V, R><<<grid, KJ_WARPS_PER_CTA * 32, smem, kst>>>(KJ_ARGS(B0, B1))
+#define KJ_LAUNCH3(M, T, G, F, V, R, B0, B1) kj_classify_kernel<M, T, G, F, V, R><<<kgrid, KJ_WARPS_PER_CTA * 32, smem, kst>>>(KJ_ARGS(B0, B1))
 #define KJ_LAUNCH(M, T) if (verbose) { if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, true, 0, 0, n); else KJ_LAUNCH3(M, T, false, false, true, 0, 0, n); } \
                         else if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, false, 0, 0, n); else if (fixed) KJ_LAUNCH3(M, T, false, true, false, 0, 0, n); else KJ_LAUNCH3(M, T, false, false, false, 0, 0, n)
 #define KJ_LAUNCH_SPLIT(T, R, B0, B1) if (fixed) KJ_LAUNCH3(1, T, false, true, false, R, B0, B1); else KJ_LAUNCH3(1, T, false, false, false, R, B0, B1)
-    uint8_t* pbuf = nullptr; unsigned long long* ctr = c->d_counter + slot; cudaStream_t kst = st;
+    uint8_t* pbuf = nullptr; unsigned long long* ctr = c->d_counter + slot; cudaStream_t kst = st; int kgrid = grid;
+    // The search kernel leaves one CTA slot per SM free (its grid is one CTA per SM short of what fits): the front end of the NEXT sub-batch (or of the
+    // next launch on the other slot) runs there, beside the search instead of after it -- the front end is 12 % of Greedy's kernel time when run alone
+    const int per_sm = grid / c->sm_count; const int sgrid = (per_sm >= 3 && !getenv("KJ_SPLIT_FULL_GRID")) ? c->sm_count * (per_sm - 1) : grid;
     if (split) {
         // front end on the slot's own stream, search on the caller's: F(b) -> S(b) through ev_f, S(b) -> F(b+2) (same buffer) through ev_s
         cudaStream_t fs = c->fstream[slot]; uint8_t* base = c->d_prep + (size_t)slot * (c->prep_bytes / 2); uint64_t k = 0;
@@ -552,11 +555,11 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
             const uint64_t b1 = std::min(n, b0 + sub); const int pb = (int)(k & 1);
             pbuf = base + (size_t)pb * (c->prep_bytes / 4);
             CK(cudaStreamWaitEvent(fs, c->ev_s[slot][pb], 0));                 // the search that last read this buffer (of this or an earlier launch; no-op if none)
-            ctr = c->d_counter + 2 + slot; kst = fs;
+            ctr = c->d_counter + 2 + slot; kst = fs; kgrid = grid;
             CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), fs));
             if (c->H.wide) KJ_LAUNCH_SPLIT(uint64_t, 1, b0, b1); else KJ_LAUNCH_SPLIT(uint32_t, 1, b0, b1);
             CK(cudaEventRecord(c->ev_f[slot][pb], fs));
-            ctr = c->d_counter + slot; kst = st;
+            ctr = c->d_counter + slot; kst = st; kgrid = sgrid;
             CK(cudaStreamWaitEvent(st, c->ev_f[slot][pb], 0));
             CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
             if (c->H.wide) KJ_LAUNCH_SPLIT(uint64_t, 2, b0, b1); else KJ_LAUNCH_SPLIT(uint32_t, 2, b0, b1);
