@@ -520,11 +520,11 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
     const uint32_t pstride = split ? kj_prep_stride(rp) : 0u; uint64_t sub = n;
     if (split) {
         // records of one sub-batch per buffer; two buffers per slot (the front end of sub-batch b+1 runs in the tail of the search of sub-batch b).
-        // Up to 4 GB per buffer where HBM is plentiful: fewer, longer search launches (750 k vs 3 M pairs per launch: 17.9 vs 18.3 M pairs/s)
+        // Up to 8 GB per buffer where HBM is plentiful: fewer, longer search launches (750 k vs 3 M pairs per launch: 17.9 vs 18.3 M pairs/s)
         uint64_t per_buf = c->prep_bytes / 4;
-        if (per_buf < (4ull << 30) && per_buf < n * (uint64_t)pstride) {       // (re)allocate: what this launch needs, at least 1 GB, at most 4 GB or 1/24 of the free memory
+        if (per_buf < (8ull << 30) && per_buf < n * (uint64_t)pstride) {       // (re)allocate: what this launch needs, at least 1 GB, at most 8 GB or 1/16 of the free memory
             size_t fr = 0, to = 0; CK(cudaMemGetInfo(&fr, &to)); fr += c->prep_bytes;
-            const uint64_t lim = std::max<uint64_t>(64ull << 20, std::min<uint64_t>(4ull << 30, fr / 24));
+            const uint64_t lim = std::max<uint64_t>(64ull << 20, std::min<uint64_t>(8ull << 30, fr / 16));
             const uint64_t want = std::min<uint64_t>(lim, std::max<uint64_t>(1ull << 30, n * (uint64_t)pstride + (n * (uint64_t)pstride) / 4));
             if (want > per_buf) {
                 if (c->d_prep) cudaFree(c->d_prep); c->d_prep = nullptr; c->prep_bytes = 0;
@@ -544,9 +544,9 @@ static int launch(kj_ctx* c, int slot, const uint8_t* d_seq1, const uint64_t* d_
                         else if (rp.ws_global) KJ_LAUNCH3(M, T, true, false, false, 0, 0, n); else if (fixed) KJ_LAUNCH3(M, T, false, true, false, 0, 0, n); else KJ_LAUNCH3(M, T, false, false, false, 0, 0, n)
 #define KJ_LAUNCH_SPLIT(T, R, B0, B1) if (fixed) KJ_LAUNCH3(1, T, false, true, false, R, B0, B1); else KJ_LAUNCH3(1, T, false, false, false, R, B0, B1)
     uint8_t* pbuf = nullptr; unsigned long long* ctr = c->d_counter + slot; cudaStream_t kst = st; int kgrid = grid;
-    // The search kernel leaves one CTA slot per SM free (its grid is one CTA per SM short of what fits): the front end of the NEXT sub-batch (or of the
-    // next launch on the other slot) runs there, beside the search instead of after it -- the front end is 12 % of Greedy's kernel time when run alone
-    const int per_sm = grid / c->sm_count; const int sgrid = (per_sm >= 3 && !getenv("KJ_SPLIT_FULL_GRID")) ? c->sm_count * (per_sm - 1) : grid;
+    // (A/B r2l: a search grid that leaves one CTA slot per SM to the front end of the next sub-batch loses 9 % -- 32 instead of 40 search warps per SM cost
+    // more than the hidden front end (8 % of the kernel time) gives back; KJ_SPLIT_LEAVE_SLOT keeps the experiment)
+    const int per_sm = grid / c->sm_count; const int sgrid = (per_sm >= 3 && getenv("KJ_SPLIT_LEAVE_SLOT")) ? c->sm_count * (per_sm - 1) : grid;
     if (split) {
         // front end on the slot's own stream, search on the caller's: F(b) -> S(b) through ev_f, S(b) -> F(b+2) (same buffer) through ev_s
         cudaStream_t fs = c->fstream[slot]; uint8_t* base = c->d_prep + (size_t)slot * (c->prep_bytes / 2); uint64_t k = 0;
