@@ -209,13 +209,19 @@ class Runner:
         # dense taxon indices (uint32 as int32 storage), double-buffered: the gather of step i overlaps the kernel of step i+1
         self.d_compact = [torch.zeros(n, dtype=torch.int32, device="cuda") for _ in range(2)]
         self.gathered = [torch.zeros(n * world, dtype=torch.int32, device="cuda") for _ in range(2)] if dist else None
-        self.stream = torch.cuda.current_stream(); self.side = torch.cuda.Stream() if dist else None
+        # the gather runs on a high-priority stream: when the classify kernel of step i retires, the few CTAs of the NCCL kernel must get their SM slots
+        # before the persistent grid of step i+1 takes all of them (otherwise the gather sits behind that whole kernel and step i+2 waits for its buffer)
+        self.stream = torch.cuda.current_stream(); self.side = torch.cuda.Stream(priority=-1) if dist else None
         self.gather_done = [None, None]; self.i = 0
         self.in_bytes = int(s1.nbytes + s2.nbytes + o1.nbytes + o2.nbytes)
         torch.cuda.synchronize()
 
     def _gather(self, k):
         torch = self.torch
+        if os.environ.get("KJ_BENCH_GATHER_MAIN"):      # developer hook (A/B): the gather behind the kernel on the same stream
+            self.dist.all_gather_into_tensor(self.gathered[k], self.d_compact[k])
+            done = torch.cuda.Event(); done.record(self.stream); self.gather_done[k] = done
+            return
         ev = torch.cuda.Event(); ev.record(self.stream)
         with torch.cuda.stream(self.side):
             self.side.wait_event(ev)
@@ -347,6 +353,7 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")      # NCCL's own stream as well (see Runner)
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
