@@ -6,9 +6,6 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,driver_version --format=c
 timeout 300 python __graft_entry__.py smoke > $o/smoke_$tag.log 2>&1 || echo "smoke FAILED" | tee -a $o/smoke_$tag.log
 tail -1 $o/smoke_$tag.log
 timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee $o/pytest_gpu_$tag.log
-ab() { for m in ${AB_MODES:-mem greedy}; do r=5000000; [ $m = greedy ] && r=3000000
-  python bench.py --mode $m --steps 3 --warmup 3 --skip-cpu --headline-only --reads $r 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1 mode=$m reads=$r value=%.2fM e2e=%.2fM kernel_ms=%.1f launches=%d'%(d['value']/1e6, d['e2e']['value']/1e6, d['kernel_ms'], d['gpu_launches']), d['config']['launch'])"; done; }
-(ab "default"; AB_MODES=greedy; for v in nfs; do [ -f kaiju_b200/libkaijub200_v$v.so ] && KJ_B200_LIB=$PWD/kaiju_b200/libkaijub200_v$v.so ab "$v"; done; ab "default-again") > $o/ab_$tag.txt 2>&1; cat $o/ab_$tag.txt
 timeout 1500 python bench.py > $o/bench_$tag.json 2> $o/bench_$tag.err; tail -c 800 $o/bench_$tag.json; tail -3 $o/bench_$tag.err
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $o/bench_${tag}_reference.json 2> $o/bench_${tag}_reference.err; tail -c 400 $o/bench_${tag}_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/launches_$tag.csv python bench.py --steps 2 --warmup 1 --skip-cpu --headline-only > $o/launches_$tag.log 2>&1
