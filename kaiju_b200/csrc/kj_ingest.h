@@ -168,11 +168,7 @@ static __device__ __forceinline__ void kj_line_kind(const char* __restrict__ tex
 __global__ void kj_line_info(const char* __restrict__ text, const uint64_t* __restrict__ line_start, KjParseDims d, const uint8_t* __restrict__ phase,
                              uint32_t* __restrict__ cnt, uint32_t* __restrict__ hdr, uint32_t* __restrict__ nlen, uint32_t* __restrict__ err) {
     const uint32_t lane = threadIdx.x & 31; const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    // FASTQ by line number: only the header and sequence lines are visited (the other two of every record keep the zeros the arrays were cleared to)
-    const bool skip2 = d.fastq && !phase; const uint64_t W = skip2 ? 2ull * (((uint64_t)d.n_lines + 3) / 4) : (uint64_t)d.n_lines;
-    for (uint64_t wi = warp; wi <= W; wi += nwarps) {
-        const uint64_t i = wi == W ? (uint64_t)d.n_lines : (skip2 ? 4 * (wi >> 1) + (wi & 1) : wi);
-        if (wi < W && i >= d.n_lines) continue;
+    for (uint64_t i = warp; i <= d.n_lines; i += nwarps) {
         if (i == d.n_lines) { if (lane == 0) { cnt[i] = 0; hdr[i] = 0; nlen[i] = 0; } continue; }     // virtual line: the scans deliver the totals here
         const uint64_t s = line_start[i], e = line_start[i + 1] - 1;                                  // [s, e) without the newline
         bool is_hdr, is_seq, blank; kj_line_kind(text, d, phase, i, s, e, is_hdr, is_seq, blank);
@@ -198,10 +194,7 @@ __global__ void kj_line_emit(const char* __restrict__ text, const uint64_t* __re
                              const uint32_t* __restrict__ S, const uint32_t* __restrict__ R, const uint32_t* __restrict__ NS,
                              char* __restrict__ seq, uint64_t* __restrict__ off, char* __restrict__ names, uint32_t* __restrict__ name_off, uint64_t* __restrict__ rec_pos) {
     const uint32_t lane = threadIdx.x & 31; const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const bool skip2 = d.fastq && !phase; const uint64_t W = skip2 ? 2ull * (((uint64_t)d.n_lines + 3) / 4) : (uint64_t)d.n_lines;
-    for (uint64_t wi = warp; wi <= W; wi += nwarps) {
-        const uint64_t i = wi == W ? (uint64_t)d.n_lines : (skip2 ? 4 * (wi >> 1) + (wi & 1) : wi);
-        if (wi < W && i >= d.n_lines) continue;
+    for (uint64_t i = warp; i <= d.n_lines; i += nwarps) {
         if (i == d.n_lines) { if (lane == 0) { const uint32_t r = R[i]; off[r] = S[i]; name_off[r] = NS[i]; rec_pos[r] = line_start[i]; } continue; }
         const uint64_t s = line_start[i], e = line_start[i + 1] - 1;
         bool is_hdr, is_seq, blank; kj_line_kind(text, d, phase, i, s, e, is_hdr, is_seq, blank);
@@ -344,9 +337,6 @@ static int kj_parse_side(int sm_count, KjParsed& P, KjBatchSide& O, const std::s
         kj_fq_tile_prefix<<<1, 32, 0, st>>>(P.phase_tiles.as<uint32_t>(), nt);
         kj_fq_phases<<<nt, 256, 0, st>>>(P.line_start.as<uint64_t>(), nl, P.phase_tiles.as<uint32_t>(), P.phase.as<uint8_t>());
         phase = P.phase.as<uint8_t>(); *launches += 3;
-    }
-    if (P.fastq && !phase) {     // the line kernels skip the '+' and quality lines: their entries are zeros
-        CK(cudaMemsetAsync(P.cnt.p, 0, (L1 + 1) * 4, st)); CK(cudaMemsetAsync(P.hdr.p, 0, (L1 + 1) * 4, st)); CK(cudaMemsetAsync(P.nlen.p, 0, (L1 + 1) * 4, st));
     }
     kj_line_info<<<blocks, 256, 0, st>>>(text, P.line_start.as<uint64_t>(), d, phase, P.cnt.as<uint32_t>(), P.hdr.as<uint32_t>(), P.nlen.as<uint32_t>(), d_perr);
     if ((rc = kj_scan_u32(P.cnt.as<uint32_t>(), L1, P.scan_tmp, tot + 1, st)) || (rc = kj_scan_u32(P.hdr.as<uint32_t>(), L1, P.scan_tmp, tot + 2, st)) ||
