@@ -297,62 +297,81 @@ struct KjParsed {   // one side (file) of a chunk while it is parsed
 };
 
 // Parse the complete records in P.text[P.cur][0, P.nbytes) into O.  Sets P.n_rec; *launches counts the kernels.
-// exact: FASTQ with blank lines between records (phases from the automaton scan instead of line number mod 4)
-static int kj_parse_side(int sm_count, KjParsed& P, KjBatchSide& O, const std::string& fname, cudaStream_t st, uint32_t* d_perr, uint64_t* launches, bool exact) {
-    P.n_rec = 0; P.consumed = 0; P.n_lines = 0; P.skip_all = false;
-    if (P.nbytes == 0) return KJ_OK;
-    if (P.nbytes >= (1ull << 31)) { kj_err() = "kj_classify_files: a single record larger than 2 GB"; return KJ_ERR_UNSUPPORTED; }
-    const char* text = P.text[P.cur].as<char>();
-    if (P.fastq < 0) {
-        // the file type is the first character of the first non-empty line (kaiju.cpp:289-299: empty lines are skipped before it is looked at)
-        char first = '\n'; std::vector<char> head;
-        for (uint64_t at = 0, win = 256; first == '\n' && at < P.nbytes; at += head.size(), win *= 4) {
-            head.resize((size_t)std::min<uint64_t>(win, P.nbytes - at));
-            CK(cudaMemcpyAsync(head.data(), text + at, head.size(), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-            for (char ch : head) if (ch != '\n') { first = ch; break; }
-        }
-        if (first == '\n') { P.skip_all = true; return KJ_OK; }                   // nothing but empty lines so far: they are dropped
-        if (first == '@') P.fastq = 1; else if (first == '>') P.fastq = 0;
-        else { kj_err() = "Auto-detection of file type for file " + fname + " failed."; return KJ_ERR_IO; }                 // kaiju.cpp:296-299
-    }
-    int rc;
-    const uint32_t ntiles = (uint32_t)((P.nbytes + KJ_NL_TILE - 1) / KJ_NL_TILE);
-    if ((rc = P.tiles.need((size_t)(ntiles + 1) * 4)) || (rc = P.totals.need(64))) return rc;
-    uint32_t* tot = P.totals.as<uint32_t>();
-    kj_nl_count<<<ntiles, 256, 0, st>>>(text, P.nbytes, P.tiles.as<uint32_t>());
-    if ((rc = kj_scan_u32(P.tiles.as<uint32_t>(), ntiles, P.scan_tmp, tot + 0, st))) return rc;
-    uint32_t nl = 0; CK(cudaMemcpyAsync(&nl, tot + 0, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-    P.n_lines = nl; *launches += 4;
-    if (nl == 0) return KJ_OK;                                                      // not even one complete line yet
-    const size_t L1 = (size_t)nl + 1;
-    if ((rc = P.line_start.need((L1 + 1) * 8)) || (rc = P.cnt.need((L1 + 1) * 4)) || (rc = P.hdr.need((L1 + 1) * 4)) || (rc = P.nlen.need((L1 + 1) * 4))) return rc;
-    kj_nl_scatter<<<ntiles, 256, 0, st>>>(text, P.nbytes, P.tiles.as<uint32_t>(), P.line_start.as<uint64_t>());
-    KjParseDims d; d.fastq = (uint32_t)P.fastq; d.n_lines = nl;
+// exact: FASTQ with blank lines between records (phases from the automaton scan instead of line number mod 4).
+// Both files of a pair go through the three stages together: the parser's stream synchronises three times per batch (line count, totals, end), not
+// three times per file -- each host round trip is a gap in which the persistent classify grid of the other pipeline stage takes every free SM slot.
+static int kj_parse_sides(int sm_count, KjParsed* Ps, KjBatchSide* Os, int nfiles, const std::string* fn, cudaStream_t st, uint32_t* d_perr, uint64_t* launches, bool exact) {
+    int rc; bool on[2] = {false, false}; uint32_t ntiles[2] = {0, 0}, nl[2] = {0, 0}, h[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}; uint8_t end_phase[2] = {0, 0}; const uint8_t* phase[2] = {nullptr, nullptr};
     const int blocks = sm_count * 8;
-    const uint8_t* phase = nullptr;
-    if (P.fastq && exact) {
-        const uint32_t nt = (uint32_t)((L1 + KJ_FQ_TILE - 1) / KJ_FQ_TILE);
-        if ((rc = P.phase.need(L1 + 8)) || (rc = P.phase_tiles.need((size_t)(nt + 1) * 4))) return rc;
-        kj_fq_tile_maps<<<nt, 256, 0, st>>>(P.line_start.as<uint64_t>(), nl, P.phase_tiles.as<uint32_t>());
-        kj_fq_tile_prefix<<<1, 32, 0, st>>>(P.phase_tiles.as<uint32_t>(), nt);
-        kj_fq_phases<<<nt, 256, 0, st>>>(P.line_start.as<uint64_t>(), nl, P.phase_tiles.as<uint32_t>(), P.phase.as<uint8_t>());
-        phase = P.phase.as<uint8_t>(); *launches += 3;
+    // stage 0: file type (first batch of a file only), newline counts
+    for (int f = 0; f < nfiles; f++) {
+        KjParsed& P = Ps[f];
+        P.n_rec = 0; P.consumed = 0; P.n_lines = 0; P.skip_all = false;
+        if (P.nbytes == 0) continue;
+        if (P.nbytes >= (1ull << 31)) { kj_err() = "kj_classify_files: a single record larger than 2 GB"; return KJ_ERR_UNSUPPORTED; }
+        const char* text = P.text[P.cur].as<char>();
+        if (P.fastq < 0) {
+            // the file type is the first character of the first non-empty line (kaiju.cpp:289-299: empty lines are skipped before it is looked at)
+            char first = '\n'; std::vector<char> head;
+            for (uint64_t at = 0, win = 256; first == '\n' && at < P.nbytes; at += head.size(), win *= 4) {
+                head.resize((size_t)std::min<uint64_t>(win, P.nbytes - at));
+                CK(cudaMemcpyAsync(head.data(), text + at, head.size(), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+                for (char ch : head) if (ch != '\n') { first = ch; break; }
+            }
+            if (first == '\n') { P.skip_all = true; continue; }                       // nothing but empty lines so far: they are dropped
+            if (first == '@') P.fastq = 1; else if (first == '>') P.fastq = 0;
+            else { kj_err() = "Auto-detection of file type for file " + fn[f] + " failed."; return KJ_ERR_IO; }                 // kaiju.cpp:296-299
+        }
+        ntiles[f] = (uint32_t)((P.nbytes + KJ_NL_TILE - 1) / KJ_NL_TILE);
+        if ((rc = P.tiles.need((size_t)(ntiles[f] + 1) * 4)) || (rc = P.totals.need(64))) return rc;
+        kj_nl_count<<<ntiles[f], 256, 0, st>>>(text, P.nbytes, P.tiles.as<uint32_t>());
+        if ((rc = kj_scan_u32(P.tiles.as<uint32_t>(), ntiles[f], P.scan_tmp, P.totals.as<uint32_t>() + 0, st))) return rc;
+        CK(cudaMemcpyAsync(&nl[f], P.totals.as<uint32_t>() + 0, 4, cudaMemcpyDeviceToHost, st));
+        on[f] = true; *launches += 4;
     }
-    kj_line_info<<<blocks, 256, 0, st>>>(text, P.line_start.as<uint64_t>(), d, phase, P.cnt.as<uint32_t>(), P.hdr.as<uint32_t>(), P.nlen.as<uint32_t>(), d_perr);
-    if ((rc = kj_scan_u32(P.cnt.as<uint32_t>(), L1, P.scan_tmp, tot + 1, st)) || (rc = kj_scan_u32(P.hdr.as<uint32_t>(), L1, P.scan_tmp, tot + 2, st)) ||
-        (rc = kj_scan_u32(P.nlen.as<uint32_t>(), L1, P.scan_tmp, tot + 3, st))) return rc;
-    uint32_t h[4]; uint8_t end_phase = 0; CK(cudaMemcpyAsync(h, tot, 16, cudaMemcpyDeviceToHost, st));
-    if (phase) CK(cudaMemcpyAsync(&end_phase, phase + nl, 1, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const uint64_t letters = h[1], headers = h[2], name_bytes = h[3];
-    if ((rc = O.seq.need(letters + 64)) || (rc = O.off.need((headers + 2) * 8)) || (rc = O.names.need(name_bytes + 64)) || (rc = O.name_off.need((headers + 2) * 4)) ||
-        (rc = P.rec_pos.need((headers + 2) * 8))) return rc;
-    kj_line_emit<<<blocks, 256, 0, st>>>(text, P.line_start.as<uint64_t>(), d, phase, P.cnt.as<uint32_t>(), P.hdr.as<uint32_t>(), P.nlen.as<uint32_t>(),
-                                        O.seq.as<char>(), O.off.as<uint64_t>(), O.names.as<char>(), O.name_off.as<uint32_t>(), P.rec_pos.as<uint64_t>());
-    CK(cudaGetLastError()); *launches += 12;
-    // complete records: FASTQ = whole groups of four lines; FASTA = every header that is followed by another header (or by the end of the file)
-    if (P.fastq) { P.n_rec = phase ? (end_phase == 0 ? headers : (headers ? headers - 1 : 0)) : nl / 4; }       // a record is complete with its fourth line
-    else { P.n_rec = P.eof ? headers : (headers ? headers - 1 : 0); }
+    // stage 1: line starts, per-line classes, the three scans
+    for (int f = 0; f < nfiles; f++) {
+        KjParsed& P = Ps[f];
+        if (!on[f]) continue;
+        P.n_lines = nl[f];
+        if (nl[f] == 0) { on[f] = false; continue; }                                  // not even one complete line yet
+        const char* text = P.text[P.cur].as<char>(); uint32_t* tot = P.totals.as<uint32_t>();
+        const size_t L1 = (size_t)nl[f] + 1;
+        if ((rc = P.line_start.need((L1 + 1) * 8)) || (rc = P.cnt.need((L1 + 1) * 4)) || (rc = P.hdr.need((L1 + 1) * 4)) || (rc = P.nlen.need((L1 + 1) * 4))) return rc;
+        kj_nl_scatter<<<ntiles[f], 256, 0, st>>>(text, P.nbytes, P.tiles.as<uint32_t>(), P.line_start.as<uint64_t>());
+        KjParseDims d; d.fastq = (uint32_t)P.fastq; d.n_lines = nl[f];
+        if (P.fastq && exact) {
+            const uint32_t nt = (uint32_t)((L1 + KJ_FQ_TILE - 1) / KJ_FQ_TILE);
+            if ((rc = P.phase.need(L1 + 8)) || (rc = P.phase_tiles.need((size_t)(nt + 1) * 4))) return rc;
+            kj_fq_tile_maps<<<nt, 256, 0, st>>>(P.line_start.as<uint64_t>(), nl[f], P.phase_tiles.as<uint32_t>());
+            kj_fq_tile_prefix<<<1, 32, 0, st>>>(P.phase_tiles.as<uint32_t>(), nt);
+            kj_fq_phases<<<nt, 256, 0, st>>>(P.line_start.as<uint64_t>(), nl[f], P.phase_tiles.as<uint32_t>(), P.phase.as<uint8_t>());
+            phase[f] = P.phase.as<uint8_t>(); *launches += 3;
+        }
+        kj_line_info<<<blocks, 256, 0, st>>>(text, P.line_start.as<uint64_t>(), d, phase[f], P.cnt.as<uint32_t>(), P.hdr.as<uint32_t>(), P.nlen.as<uint32_t>(), d_perr);
+        if ((rc = kj_scan_u32(P.cnt.as<uint32_t>(), L1, P.scan_tmp, tot + 1, st)) || (rc = kj_scan_u32(P.hdr.as<uint32_t>(), L1, P.scan_tmp, tot + 2, st)) ||
+            (rc = kj_scan_u32(P.nlen.as<uint32_t>(), L1, P.scan_tmp, tot + 3, st))) return rc;
+        CK(cudaMemcpyAsync(h[f], tot, 16, cudaMemcpyDeviceToHost, st));
+        if (phase[f]) CK(cudaMemcpyAsync(&end_phase[f], phase[f] + nl[f], 1, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    // stage 2: packed sequences, offsets, names (the caller synchronises once more after its own kernels)
+    for (int f = 0; f < nfiles; f++) {
+        KjParsed& P = Ps[f]; KjBatchSide& O = Os[f];
+        if (!on[f]) continue;
+        const char* text = P.text[P.cur].as<char>();
+        const uint64_t letters = h[f][1], headers = h[f][2], name_bytes = h[f][3];
+        if ((rc = O.seq.need(letters + 64)) || (rc = O.off.need((headers + 2) * 8)) || (rc = O.names.need(name_bytes + 64)) || (rc = O.name_off.need((headers + 2) * 4)) ||
+            (rc = P.rec_pos.need((headers + 2) * 8))) return rc;
+        KjParseDims d; d.fastq = (uint32_t)P.fastq; d.n_lines = nl[f];
+        kj_line_emit<<<blocks, 256, 0, st>>>(text, P.line_start.as<uint64_t>(), d, phase[f], P.cnt.as<uint32_t>(), P.hdr.as<uint32_t>(), P.nlen.as<uint32_t>(),
+                                            O.seq.as<char>(), O.off.as<uint64_t>(), O.names.as<char>(), O.name_off.as<uint32_t>(), P.rec_pos.as<uint64_t>());
+        CK(cudaGetLastError()); *launches += 12;
+        // complete records: FASTQ = whole groups of four lines; FASTA = every header that is followed by another header (or by the end of the file)
+        if (P.fastq) { P.n_rec = phase[f] ? (end_phase[f] == 0 ? headers : (headers ? headers - 1 : 0)) : nl[f] / 4; }       // a record is complete with its fourth line
+        else { P.n_rec = P.eof ? headers : (headers ? headers - 1 : 0); }
+    }
     return KJ_OK;
 }
 
@@ -596,11 +615,9 @@ static int kj_parse_chunks(int device, int sm_count, KjFilesState& S, size_t chu
         uint64_t n = 0; bool all_eof = false; uint64_t pos[2] = {0, 0}; uint32_t hstat[4] = {0, 0, 0, 0};
         for (int pass = 0; pass < 2; pass++) {
             CK(cudaMemsetAsync(d_stat, 0, 16, st));
-            for (int f = 0; f < S.nfiles; f++) {
-                if ((rc = kj_parse_side(sm_count, S.side[f], B.s[f], fn[f], st, d_stat + 2, &S.parse_launches, pass == 1))) return rc;
-                // (kj_parse_side synchronises the stream: the staging buffers appended above are free again)
-                for (int sl : used[f]) S.rd[f].release_slot(sl); used[f].clear();
-            }
+            if ((rc = kj_parse_sides(sm_count, S.side, B.s, S.nfiles, fn, st, d_stat + 2, &S.parse_launches, pass == 1))) return rc;
+            // (kj_parse_sides synchronises the stream: the staging buffers appended above are free again)
+            for (int f = 0; f < S.nfiles; f++) { for (int sl : used[f]) S.rd[f].release_slot(sl); used[f].clear(); }
             n = S.side[0].n_rec; if (paired) n = std::min(n, S.side[1].n_rec);
             all_eof = S.side[0].eof && (!paired || S.side[1].eof);
             if (n >= (1ull << 31)) { kj_err() = "kj_classify_files: batch with too many records"; return KJ_ERR_UNSUPPORTED; }
