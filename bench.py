@@ -168,7 +168,8 @@ def reference_arm(args):
     """--impl reference: the unmodified reference on the host cores; nothing of kaiju_b200/ is imported or loaded."""
     db, fmi, nodes = build_workload(args, 0)
     cores = os.cpu_count() or 1
-    n_sample = args.cpu_sample or max(20000, min(2560000, 20000 * cores))
+    # a step = a bounded sample of the workload; all steps together ~10 M pairs of CPU work (about a minute at the reference's best -z on 128 vCPUs)
+    n_sample = args.cpu_sample or max(20000, min(2560000, 20000 * cores, 10_000_000 // max(1, args.warmup + args.steps)))
     cb, _ = ref_sweep(db, fmi, nodes, args.mode, args, 1000, n_sample, False)          # untimed: finds the best -z
     z = cb["threads_used"]; vals = []
     for s in range(args.warmup + args.steps):
