@@ -441,6 +441,7 @@ def main():
 
 def large_index(kb, torch, R, clf_base, fmi, nodes, mem_tax, args, local, alg_base):
     """configs[3]: MEM against a refseq_ref-scale index resident in HBM (see the module docstring)."""
+    clf_base.set_params(kb.make_params("mem", m=11))       # (a context that leaves Greedy mode returns its record buffers: HBM for the large index)
     free, total = torch.cuda.mem_get_info()
     copies = max(2, int(round(args.large_rows / clf_base.bwtlen)))
     per_row = 3.5 + 8.0 / 12 + 4.0 / 8 + 0.05                        # rank records + packed letters + taxon per sampled row (exponent 3) (+ slack)

@@ -474,6 +474,8 @@ extern "C" int kj_set_params(kj_ctx* c, const kj_params* p) {
     int rc = kj_check_params(*p); if (rc) return rc;
     CK(cudaSetDevice(c->device));
     c->params = *p;
+    // the record buffers of the two-kernel Greedy path (up to 32 GB) go back when the context leaves Greedy mode
+    if (c->params.mode != 1 && c->d_prep) { CK(cudaDeviceSynchronize()); cudaFree(c->d_prep); c->d_prep = nullptr; c->prep_bytes = 0; }
     return upload_evalue_breaks(c);
 }
 
