@@ -125,3 +125,35 @@ def test_bwtlen_multiple_of_65536(built):
         tax, best = orc.classify_batch(make_params(**kw), seq, off)
         for i in range(len(reads)):
             assert (ref["r%d" % i][1], ref["r%d" % i][2]) == (int(tax[i]), int(best[i])), (kw, i)
+
+
+def test_reference_reader_rules_for_blank_lines(work):
+    """What the device-side parser reproduces (kj_ingest.h, tests/test_gpu_parity.py::test_fastq_with_blank_lines), pinned on the reference itself:
+    empty lines before the first record and between FASTQ records are skipped (kaiju.cpp:288-289, 341-348), an empty sequence line inside a
+    record is the record's sequence, a missing final newline is fine."""
+    d, fmi = work
+    lines = open(d + "/r1.fq").read().split("\n")[:4 * 400]; lines2 = open(d + "/r2.fq").read().split("\n")[:4 * 400]
+    def dirty(ls):
+        out = ["", ""]                                                   # leading blank lines: the file type comes from the first non-empty line
+        for r in range(0, len(ls), 4):
+            rec = ls[r:r + 4]
+            if (r // 4) % 37 == 5:
+                rec = [rec[0], "", "+", ""]                               # empty sequence line: a line of the record
+            out += rec
+            if (r // 4) % 5 == 1:
+                out += [""] * (1 + (r // 4) % 3)                          # blank lines between records
+        return "\n".join(out)                                            # no newline at the end
+    def clean(ls):
+        out = []
+        for r in range(0, len(ls), 4):
+            rec = ls[r:r + 4]
+            if (r // 4) % 37 == 5:
+                rec = [rec[0], "", "+", ""]
+            out += rec
+        return "\n".join(out) + "\n"
+    for name, fn, src in (("c1", clean, lines), ("c2", clean, lines2), ("b1", dirty, lines), ("b2", dirty, lines2)):
+        open(d + "/" + name + ".fq", "w").write(fn(src))
+    a = run_ref_kaiju(d + "/nodes.dmp", fmi, d + "/c1.fq", d + "/c2.fq", mode="greedy")
+    b = run_ref_kaiju(d + "/nodes.dmp", fmi, d + "/b1.fq", d + "/b2.fq", mode="greedy")
+    assert len(a) == 400 and a == b and sum(1 for v in a.values() if v[0] == "C") > 100
+    assert run_ref_kaiju(d + "/nodes.dmp", fmi, d + "/c1.fq", mode="mem") == run_ref_kaiju(d + "/nodes.dmp", fmi, d + "/b1.fq", mode="mem")
