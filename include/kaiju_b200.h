@@ -167,7 +167,8 @@ int kj_device_count(void);                        /* number of usable CUDA devic
  * ConsumerThread.cpp:724-739): FASTA or FASTQ, plain or gzip, in2 = second file of paired-end reads or NULL.  The text is
  * parsed on the device (line splitting, name trimming at " /\t\r", strip() of non-letters), classified, and the output
  * lines "C\t<name>\t<taxid>" / "U\t<name>\t0" (verbose: plus "\t<best>\t<id,id,...,>") are formatted on the device and
- * written to out_path (NULL or "" = stdout) in INPUT order.  FASTQ must be 4-line records.  Errors mirror the
+ * written to out_path (NULL or "" = stdout) in INPUT order.  FASTQ = 4-line records; empty lines before the first and between
+ * records are skipped as the reference's reader does (kaiju.cpp:288-289, 341-348).  Errors mirror the
  * reference's messages (file type detection, differing read names, file 1 longer than file 2) as KJ_ERR_IO. */
 int kj_classify_files(kj_ctx *ctx, const char *in1, const char *in2, const char *out_path, int verbose,
                       uint64_t *n_reads_out, uint64_t *n_classified_out);

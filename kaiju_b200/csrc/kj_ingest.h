@@ -7,7 +7,11 @@
 //   newline positions (count + scan + scatter) -> per-line classification (header / sequence / ignored), letters and
 //   trimmed-name lengths (one warp per line) -> scans over lines -> packed sequences + offsets + names blob ->
 //   kj_classify_kernel -> per-record output line lengths -> scan -> formatted "C\tname\ttaxid..." text.
-// The host only moves bytes: file -> pinned buffer -> device, device -> pinned buffer -> file (kj_classify_files).
+// The host only moves bytes (kj_classify_files): reader threads (one per file: page cache -> two pinned buffers -> ring of device staging buffers),
+// a parser thread (staged chunks -> batches of device text -> the kernels above on a high-priority stream; the incomplete record at the end of a batch is
+// carried over on the device), the calling thread (two classification lanes: launch batch k+1 while batch k runs, count / format / copy out batch k-1) and
+// a writer thread.  Record rules beyond the happy path (kaiju.cpp:288-404): file type = first character of the first non-empty line, empty lines between
+// FASTQ records are skipped (phases from an automaton scan when a batch has any), last line without newline, the loop ends with file 1.
 // Included by kj_device.cu (one translation unit: it uses kj_ctx and launch()).
 #pragma once
 #include <fcntl.h>
